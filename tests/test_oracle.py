@@ -1,0 +1,166 @@
+"""CPU tests: pin the oracle (oracle/cvpath.py, oracle/restated.py) against the golden
+fixtures produced by the reference's own functions (oracle/make_golden.py) and against
+in-process cv2."""
+import cv2
+import numpy as np
+import pytest
+
+from oracle import cvpath, restated
+from sfm_mvs_b200 import synth
+
+
+# ----------------------------------------------------------------------------- matching
+def test_real_pair_matches_reference_find_features(golden):
+    g = golden("real_pair")
+    des0, des1 = g["des0"].astype(np.float32), g["des1"].astype(np.float32)
+    p0, p1 = cvpath.match_keypoints(g["kp0"], des0, g["kp1"], des1)
+    assert np.array_equal(p0, g["pts0"]) and np.array_equal(p1, g["pts1"])
+    # restated exact 2-NN + double-precision ratio test reproduce the same survivors
+    idx, dist = restated.knn2_l2(des0, des1)
+    good = restated.ratio_mask(dist)
+    assert np.array_equal(g["kp0"][good], g["pts0"])
+    assert np.array_equal(g["kp1"][idx[good, 0]], g["pts1"])
+
+
+@pytest.mark.parametrize("nq,nt,seed", [(257, 301, 0), (1000, 900, 1), (64, 2, 2), (5, 1, 3)])
+def test_restated_knn2_equals_cv2(nq, nt, seed):
+    q, t, _ = synth.matching_pair(nq, nt, seed=seed)
+    idx, dist = restated.knn2_l2(q, t)
+    cidx, cdist = cvpath.knn2_arrays(q, t)
+    assert np.array_equal(idx, cidx[:, :idx.shape[1]])
+    assert np.array_equal(dist, cdist[:, :dist.shape[1]])
+
+
+def test_knn2_ties_go_to_lower_train_index():
+    q = synth.sift_like_descriptors(40, 5)
+    t = np.vstack([q[::-1], q[::-1]])            # every train row duplicated
+    idx, dist = restated.knn2_l2(q, t)
+    cidx, cdist = cvpath.knn2_arrays(q, t)
+    assert np.array_equal(idx, cidx) and np.array_equal(dist, cdist)
+    assert np.all(idx[:, 0] < idx[:, 1]) and np.all(dist == 0)
+
+
+# ----------------------------------------------------------------------------- geometry
+def test_cvpath_geometry_equals_reference(golden):
+    g = golden("geometry")
+    a, b, cloud = cvpath.Triangulation(g["P1"], g["P2"], g["x0"], g["x1"])
+    assert np.array_equal(cloud, g["cloud"])
+    err, Xc, proj = cvpath.ReprojectionError(cloud, b, g["Rt1"], g["K"], 1)
+    assert err == float(g["tri_err"]) and np.array_equal(proj, g["tri_proj"])
+    R, t, p_in, X_in, _ = cvpath.PnP(g["pnp_X"], g["pnp_p"], g["K"], np.zeros((5, 1), np.float32),
+                                     g["x0"], 0)
+    assert np.array_equal(R, g["pnp_R"]) and np.array_equal(t, g["pnp_t"])
+    assert np.array_equal(p_in, g["pnp_p_in"])
+    i1, i2, tA, tB = cvpath.common_points(g["cp_A"], g["cp_B"], g["cp_C"])
+    assert np.array_equal(i1, g["cp_i1"]) and np.array_equal(i2, g["cp_i2"])
+    assert np.array_equal(tA, g["cp_tA"]) and np.array_equal(tB, g["cp_tB"])
+
+
+def test_restated_triangulation(golden):
+    g = golden("geometry")
+    X = restated.triangulate_dlt(g["P1"], g["P2"], g["x0"].T, g["x1"].T)
+    X = X / X[3]
+    ref = g["cloud"]
+    rel = np.abs(X[:3] - ref[:3]).max() / np.abs(ref[:3]).max()
+    assert rel < 1e-6, rel
+
+
+def test_restated_rodrigues_and_projection():
+    rng = np.random.default_rng(0)
+    for _ in range(50):
+        r = rng.normal(0, 1.0, 3)
+        R = restated.rodrigues_to_matrix(r)
+        Rc, _ = cv2.Rodrigues(r)
+        assert np.abs(R - Rc).max() < 1e-15
+        rv = restated.rodrigues_to_vector(Rc)
+        rc, _ = cv2.Rodrigues(Rc)
+        assert np.abs(rv - rc.ravel()).max() < 1e-12
+    X = rng.uniform(-3, 3, (20000, 3)).astype(np.float32); X[:, 2] += 8
+    r = np.array([0.1, -0.3, 0.05]); t = np.array([0.2, -0.1, 0.4])
+    pc, _ = cv2.projectPoints(X, r, t, synth.K_GUSTAV, None)
+    pr = restated.project_pinhole(X, restated.rodrigues_to_matrix(r), t, synth.K_GUSTAV).astype(np.float32)
+    assert np.array_equal(pr, pc[:, 0, :])          # float32-rounded output bit-identical
+
+
+def test_restated_reproj_error(golden):
+    g = golden("geometry")
+    X = g["tri_X"][:, 0, :]
+    e = restated.reproj_error(X, g["x1"], g["Rt1"], g["K"])
+    assert abs(e - float(g["tri_err"])) <= 1e-9 * float(g["tri_err"])
+
+
+# ----------------------------------------------------------------------------- PnP RANSAC
+def _epnp(X5, p5, K=synth.K_GUSTAV):
+    ok, r, t = cv2.solvePnP(X5, p5, K, np.zeros((5, 1), np.float32), flags=cv2.SOLVEPNP_EPNP)
+    return ok, r.ravel(), t.ravel()
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_restated_ransac_loop_reproduces_cv2_mask(seed):
+    rng = np.random.default_rng(100 + seed)
+    n = int(rng.integers(30, 1500))
+    K = synth.K_GUSTAV
+    R, t = synth.orbit_pose(rng.uniform(0, 0.5))
+    X = np.c_[rng.uniform(-2.5, 2.5, n), rng.uniform(-1.5, 1.5, n), rng.uniform(5, 11, n)].astype(np.float32)
+    uv, _ = synth.project(K, R, t, X.astype(np.float64))
+    p = (uv + rng.normal(0, rng.uniform(0.1, 2.0), uv.shape)).astype(np.float32)
+    bad = rng.random(n) < rng.uniform(0, 0.6)
+    p[bad] += rng.uniform(-80, 80, (int(bad.sum()), 2)).astype(np.float32)
+    ok, rvec, tvec, inl = cv2.solvePnPRansac(X, p, K, np.zeros((5, 1), np.float32))
+    res = restated.pnp_ransac(X, p, K, _epnp)
+    assert res["ok"] == ok
+    if ok:
+        assert np.array_equal(np.nonzero(res["mask"])[0], inl[:, 0])
+
+
+def test_golden_pnp_inliers(golden):
+    g = golden("geometry")
+    res = restated.pnp_ransac(g["pnp_X"], g["pnp_p"], g["K"], _epnp)
+    assert np.array_equal(np.nonzero(res["mask"])[0], g["pnp_inliers"][:, 0])
+
+
+def test_subset_stream_and_update_rule():
+    s = restated.ransac_subsets(50, 100)
+    assert s.shape == (100, 5) and all(len(set(r)) == 5 for r in s.tolist())
+    assert s.min() >= 0 and s.max() < 50
+    assert restated.update_num_iters(0.99, 0.0, 5, 100) == 0
+    assert restated.update_num_iters(0.99, 0.5, 5, 100) == 100
+    assert restated.update_num_iters(0.99, 0.2, 5, 100) == 12
+
+
+# ----------------------------------------------------------------------------- BA
+def test_cvpath_ba_equals_reference(golden):
+    g = golden("ba_small")
+    res = cvpath.OptimReprojectionError(g["x"])
+    assert np.array_equal(res, g["residual"])
+    X, p, Rt = cvpath.BundleAdjustment(g["X0"], g["obs"], g["Rt"], g["K"], 0.5)
+    assert np.allclose(X, g["ba_X"], rtol=0, atol=1e-9) and np.allclose(Rt, g["ba_Rt"], atol=1e-9)
+
+
+def test_restated_ba_jacobian_equals_cv2_projectpoints():
+    rng = np.random.default_rng(3)
+    K = synth.K_GUSTAV
+    cams = np.array([[0.05, -0.2, 0.1, 0.3, -0.1, 0.5], [1e-14, 0, 0, 0, 0, 0.2]])
+    pts = np.c_[rng.uniform(-2, 2, (30, 2)), rng.uniform(5, 11, 30)]
+    cam_idx = np.repeat([0, 1], 30).astype(np.int32)
+    pt_idx = np.tile(np.arange(30), 2).astype(np.int32)
+    obs = np.zeros((60, 2), np.float32)
+    r, Jc, Jp = restated.ba_residual_jacobian(cams, pts, cam_idx, pt_idx, obs, K)
+    for c in range(2):
+        proj, J = cv2.projectPoints(pts, cams[c, :3], cams[c, 3:], K, None)
+        sel = cam_idx == c
+        assert np.allclose(r[sel], proj[:, 0, :], rtol=1e-12)
+        Jcv = J.reshape(30, 2, 15)
+        assert np.allclose(Jc[sel], Jcv[:, :, :6], rtol=1e-7, atol=1e-7)
+        R = restated.rodrigues_to_matrix(cams[c, :3])
+        assert np.allclose(Jp[sel], Jcv[:, :, 3:6] @ R, rtol=1e-9, atol=1e-9)
+
+
+def test_chain_port_equals_reference_loop(golden):
+    g = golden("chain")
+    scene = synth.orbit_scene(int(g["n_views"]), int(g["n_pts"]), seed=int(g["seed"]))
+    outs = cvpath.register_chain(scene)
+    assert np.array_equal(np.array([o["Rt"] for o in outs]), g["Rt"])
+    assert np.array_equal(np.array([o["err_new"] for o in outs]), g["err_new"])
+    assert np.array_equal(np.array([o["err_pnp"] for o in outs]), g["err_pnp"])
+    assert np.array_equal(np.vstack([o["X_new"] for o in outs]), g["X_new"])
