@@ -1,0 +1,250 @@
+/* sfm_b200.h — C ABI of the B200-native incremental-SfM geometry engine (libsfm_b200.so).
+ *
+ * This is the drop-in boundary for the three data-parallel hot paths of
+ * FlagArihant2000/sfm-mvs.  The reference has no FFI / plugin layer of its own: its
+ * boundary is the OpenCV Python API as called from sfm.py / isfm.py / test.py.  Every
+ * entry point below therefore cites the reference call site(s) it replaces; the Python
+ * host (package sfm_mvs_b200, ctypes) re-creates the cv2 signatures on top of it, and
+ * INTEGRATION.md shows the binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain C, plain pointers and sizes; no torch / numpy / OpenCV types.
+ *   - every function returns 0 (SFM_OK) or a negative sfm_status; sfm_last_error()
+ *     returns a thread-local human-readable message for the last failure.
+ *   - data pointers may be HOST or DEVICE pointers, detected per pointer
+ *     (cudaPointerGetAttributes).  Host buffers are staged through the context's
+ *     workspace and the call returns only after outputs have landed (synchronous, like
+ *     the cv2 call it replaces).  When *every* data pointer of a call is a device pointer
+ *     the call only enqueues work on the context's stream (asynchronous).
+ *   - small parameter blocks (projection matrices, K, poses) are always HOST pointers.
+ *   - one sfm_ctx per device and per caller thread; a ctx is not thread-safe.
+ *   - there is no CPU fallback anywhere: without a CUDA device sfm_ctx_create fails.
+ */
+#ifndef SFM_B200_H
+#define SFM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SFM_B200_VERSION 100
+
+typedef enum sfm_status {
+  SFM_OK = 0,
+  SFM_ERR_INVALID = -1,      /* bad argument (shape, dtype, null pointer): cv2 raises cv2.error here */
+  SFM_ERR_CUDA = -2,         /* a CUDA runtime call failed; message carries cudaGetErrorString */
+  SFM_ERR_NOMEM = -3,
+  SFM_ERR_UNSUPPORTED = -4,
+  SFM_ERR_NCCL = -5
+} sfm_status;
+
+typedef struct sfm_ctx sfm_ctx;
+typedef struct sfm_desc sfm_desc;   /* a view's descriptors, prepared and resident in HBM */
+typedef struct sfm_ba sfm_ba;       /* a bundle-adjustment problem resident in HBM */
+
+/* ------------------------------------------------------------------ context / diagnostics */
+int sfm_version(void);
+const char* sfm_last_error(void);
+/* `stream` is a cudaStream_t to borrow (e.g. torch's current stream) or NULL to own one. */
+int sfm_ctx_create(int device, void* stream, sfm_ctx** out);
+void sfm_ctx_destroy(sfm_ctx* ctx);
+int sfm_ctx_sync(sfm_ctx* ctx);
+void* sfm_ctx_stream(sfm_ctx* ctx);
+int sfm_ctx_sm_count(sfm_ctx* ctx);
+
+/* Kernel identifiers for the profiling interface. */
+enum {
+  SFM_K_DESC_PREP = 0,    /* K1b f32/u8 -> bf16 UMMA tiles + exact |d|^2 augmentation */
+  SFM_K_MATCH_TC = 1,     /* K1  tcgen05 distance GEMM + fused top-2 epilogue */
+  SFM_K_MATCH_EXACT = 2,  /* K1' exact fp32 CUDA-core 2-NN (non-integer descriptors) */
+  SFM_K_MATCH_FINAL = 3,  /* K1c cross-split merge + sqrt + Lowe ratio + count */
+  SFM_K_GATHER = 4,       /* stable compaction of ratio-test survivors + keypoint gather */
+  SFM_K_TRIANGULATE = 5,  /* K2 */
+  SFM_K_REPROJ = 6,       /* K3 */
+  SFM_K_PNP_SCORE = 7,    /* K4 */
+  SFM_K_PNP_REFINE = 8,   /* LM normal equations for SOLVEPNP_ITERATIVE refinement */
+  SFM_K_ASSOC = 9,        /* common_points */
+  SFM_K_BA_EVAL = 10,     /* K5 residual + Jacobian blocks */
+  SFM_K_BA_SCHUR = 11,    /* K6 fused J^T J / Schur accumulation */
+  SFM_K_BA_UPDATE = 12,   /* back-substitution + parameter update + cost */
+  SFM_K_BA_SOLVE = 13,    /* reduced camera system Cholesky */
+  SFM_K_MISC = 14,
+  SFM_K_PNP_EPNP = 15,    /* batched 5-point EPnP minimal solver */
+  SFM_K_COUNT = 16
+};
+const char* sfm_kernel_name(int kernel_id);
+/* When on, every kernel launch is bracketed by CUDA events on the ctx stream. */
+int sfm_ctx_set_profiling(sfm_ctx* ctx, int on);
+int sfm_ctx_reset_profile(sfm_ctx* ctx);
+/* Synchronises, then returns accumulated device time and launch count of one kernel id. */
+int sfm_ctx_get_profile(sfm_ctx* ctx, int kernel_id, double* ms_total, int64_t* launches);
+/* Number of kernels this library launched on this ctx since creation (all ids). */
+int64_t sfm_ctx_launch_count(sfm_ctx* ctx);
+
+/* ------------------------------------------------------------------ hot path 1: matching
+ * Replaces cv2.BFMatcher().knnMatch(des0, des1, k=2)            sfm.py:259-260, isfm.py:71,
+ *                                                               test.py:42,225,352
+ * and the Lowe ratio loop `m.distance < 0.70*n.distance`        sfm.py:262-265, isfm.py:73-76,
+ *                                                               test.py:226-229,353-356.
+ * q (nq,dim) and t (nt,dim) row-major float32.  idx (nq,2) int32, dist (nq,2) float32,
+ * ascending distance, ties -> lower train index; dist = float32(sqrt(sum (a-b)^2)).
+ * good[i] = (double)dist[i,0] < ratio*(double)dist[i,1].  nt==1 -> idx[:,1]=-1, dist[:,1]=+inf.
+ * idx/dist/good/n_good may each be NULL.  mode: 0 auto (tensor cores when every value is an
+ * integer in [0,255], as SIFT's are — exact; otherwise the fp32 kernel), 1 force fp32 kernel,
+ * 2 force tensor-core kernel (SFM_ERR_INVALID if the descriptors are not bf16-exact). */
+int sfm_knn2_l2_ratio(sfm_ctx* ctx, const float* q, int nq, const float* t, int nt, int dim,
+                      double ratio, int32_t* idx, float* dist, uint8_t* good, int32_t* n_good,
+                      int mode);
+
+/* Diagnostic (used by the tests only): raw tensor-core accumulators -(2^22 + d^2/2) of every
+ * (query row, train column), float32 [n_qtiles*128][n_stages*256], to a host buffer. */
+int sfm_debug_match_tc_dump(sfm_ctx* ctx, const sfm_desc* q, const sfm_desc* t, float* dump_host,
+                            int64_t capacity);
+
+/* Resident form: prepare a view's descriptors once (K1b), match many times.
+ * dtype 0 = float32, 1 = uint8. */
+int sfm_desc_create(sfm_ctx* ctx, const void* data, int dtype, int n, int dim, sfm_desc** out);
+void sfm_desc_destroy(sfm_desc* d);
+int sfm_desc_rows(const sfm_desc* d);
+int sfm_desc_is_exact(const sfm_desc* d);   /* 1 if integer-valued in [0,255] (tensor path ok) */
+int sfm_desc_match(sfm_ctx* ctx, const sfm_desc* q, const sfm_desc* t, double ratio,
+                   int32_t* idx, float* dist, uint8_t* good, int32_t* n_good, int mode);
+/* Grouped launch over many pairs (isfm.py:68-87 all-pairs loop; sharded over GPUs by the host):
+ * ONE persistent kernel walks the tiles of every pair.  Output pointer arrays are host arrays of
+ * per-pair DEVICE pointers (any may be NULL); n_good is a device or host array of npairs. */
+int sfm_desc_match_batched(sfm_ctx* ctx, int npairs, const sfm_desc* const* q,
+                           const sfm_desc* const* t, double ratio, int32_t* const* idx,
+                           float* const* dist, uint8_t* const* good, int32_t* n_good);
+
+/* sfm.py:267-268 — pts0 = kp0[m.queryIdx], pts1 = kp1[m.trainIdx] for the survivors, ascending
+ * queryIdx.  kp_q (nq,2), kp_t (nt,2) float32; outputs (n_good,2) float32, capacity nq rows. */
+int sfm_match_gather(sfm_ctx* ctx, const int32_t* idx, const uint8_t* good, int nq,
+                     const float* kp_q, const float* kp_t, float* pts_q, float* pts_t,
+                     int32_t* qidx_out, int32_t* tidx_out, int32_t* n_out);
+
+/* ------------------------------------------------------------------ hot path 2: triangulation
+ * Replaces cv2.triangulatePoints(P1, P2, pts1, pts2)            sfm.py:53, test.py:310,367
+ * and `cloud / cloud[3]`                                        sfm.py:54.
+ * P1,P2: 12 doubles row-major (host).  pts_layout 0: (2,N) as cv2 takes them, 1: (N,2).
+ * out_layout 0: (4,N) like cv2, 1: (N,4), 2: (N,3) (implies normalize_w).  float32 I/O, float64
+ * one-sided Jacobi SVD per point, same rotation schedule as OpenCV's. */
+int sfm_triangulate(sfm_ctx* ctx, const double* P1, const double* P2, const float* x1,
+                    const float* x2, int n, int pts_layout, float* X, int out_layout,
+                    int normalize_w);
+
+/* Replaces ReprojectionError's Rodrigues -> projectPoints -> cv2.norm(.., NORM_L2)/N
+ *                                                               sfm.py:79-100, ba.pyc L44-63.
+ * x_layout 0: (N,3); 1: (4,N) homogeneous; 2: (N,4) homogeneous.  px_layout 0: (2,N), 1: (N,2).
+ * Rt 12 doubles, K 9 doubles (host).  err = sqrt(sum |proj-px|^2)/N (host double, synchronises;
+ * may be NULL, or a device pointer for asynchronous use).  proj (N,2) f32 and X3 (N,3) f32 (the
+ * de-homogenised points, cv2.convertPointsFromHomogeneous) are optional outputs. */
+int sfm_reproj_error(sfm_ctx* ctx, const float* X, int x_layout, const float* px, int px_layout,
+                     int n, const double* Rt, const double* K, double* err, float* proj,
+                     float* X3);
+
+/* Replaces common_points(pts1, pts2, pts3)                      sfm.py:215-239
+ * with its exact semantics: row j of pts2 matches pts1[i] when x OR y is equal as float32;
+ * the first such j wins.  idx1/idx2 (capacity n1) ascending in i; keep2[j]=1 for rows of pts2
+ * never chosen (the reference's temp_array1/2 are pts2[keep2], pts3[keep2]). */
+int sfm_common_points(sfm_ctx* ctx, const float* pts1, int n1, const float* pts2, int n2,
+                      int32_t* idx1, int32_t* idx2, int32_t* n_common, uint8_t* keep2);
+
+/* ------------------------------------------------------------------ hot path 3a: PnP-RANSAC
+ * Replaces cv2.solvePnPRansac(X, p, K, d, ...) with OpenCV's defaults, which is what the
+ * reference gets                                                sfm.py:67, test.py:319.
+ * Hypothesis scoring (PnPRansacCallback::computeError): Rt (H,12) row-major [R|t] doubles (host),
+ * X (N,3), px (N,2) float32.  counts[h] = #{ i : (px-proj)^2 summed in float32 <= thr*thr };
+ * masks (H,N) uint8 optional. */
+int sfm_pnp_score(sfm_ctx* ctx, const float* X, const float* px, int n, const double* K,
+                  const double* Rt, int H, float thr, int32_t* counts, uint8_t* masks);
+
+typedef struct sfm_pnp_info {
+  int32_t iters_run;      /* RANSAC iterations cv2 would have executed (adaptive stop) */
+  int32_t best_iter;      /* index of the winning hypothesis */
+  int32_t hyp_solved;     /* minimal (EPnP) problems actually solved */
+  int32_t refine_iters;   /* LM iterations of the final refinement */
+  double  rvec_ransac[3]; /* winning hypothesis before refinement */
+  double  tvec_ransac[3];
+} sfm_pnp_info;
+
+/* Full replacement of the call: RNG(2^64-1) subset stream, 5-point EPnP minimal solver, batched
+ * scoring on the GPU, replay of the accept / RANSACUpdateNumIters recursion, LM refinement on the
+ * inliers (GPU normal equations).  inliers: capacity n, ascending.  *ok = 0 mirrors cv2 returning
+ * (False, .., None).  X, px may be device pointers; rvec/tvec/inliers/n_inliers/ok are host. */
+int sfm_pnp_ransac(sfm_ctx* ctx, const float* X, const float* px, int n, const double* K,
+                   int max_iters, float thr, double confidence, double* rvec, double* tvec,
+                   int32_t* inliers, int32_t* n_inliers, int32_t* ok, sfm_pnp_info* info);
+
+/* Same call with the minimal solutions supplied by the caller: hyp_rt6 (max_iters,6) rvec|tvec per
+ * RANSAC iteration (the poses a 5-point solver returned for the subsets of sfm_ransac_subsets),
+ * hyp_valid (max_iters) or NULL.  Scoring, the stopping rule, the inlier list and the refinement
+ * are identical to sfm_pnp_ransac.  This is how the parity tests feed OpenCV's own EPnP output
+ * through the engine: OpenCV's EPnP takes its null-space basis from LAPACK, which no other
+ * implementation reproduces bit for bit ("PnP parity"). */
+int sfm_pnp_ransac_hyp(sfm_ctx* ctx, const float* X, const float* px, int n, const double* K,
+                       const double* hyp_rt6, const uint8_t* hyp_valid, int max_iters, float thr,
+                       double confidence, double* rvec, double* tvec, int32_t* inliers,
+                       int32_t* n_inliers, int32_t* ok, sfm_pnp_info* info);
+
+/* Host utilities used by the wrappers (cv2.Rodrigues / cv2.solvePnP(flags=EPNP) on <=  a few
+ * points are host-side parameter marshalling, not data-parallel work). */
+int sfm_rodrigues_to_matrix(const double* rvec, double* R9);
+int sfm_rodrigues_to_vector(const double* R9, double* rvec);
+int sfm_epnp(const float* X, const float* px, int n, const double* K, double* R9, double* t3);
+int sfm_ransac_subsets(int n, int iters, int32_t* out /* iters x 5 */);
+
+/* ------------------------------------------------------------------ hot path 3b: bundle adjustment
+ * Formulation: camera = (rvec 3, tvec 3), shared pinhole K, point = 3, residual =
+ * cv2.projectPoints(X, rvec, tvec, K, None) - obs, the projection every reference variant calls
+ * (sfm.py:121, test.py:101, ba.pyc L24/L51); block structure as notebook cell 6.
+ * Observations must be sorted point-major (pt_idx non-decreasing): a point's observations are
+ * contiguous, which is the unit the engine shards across GPUs. */
+int sfm_ba_create(sfm_ctx* ctx, int n_cam, int n_pt, int n_obs, const int32_t* cam_idx,
+                  const int32_t* pt_idx, const float* obs, const double* K, sfm_ba** out);
+void sfm_ba_destroy(sfm_ba* ba);
+/* Multi-GPU shards: the whole problem's point / observation counts (the reference's residual modes
+ * divide by the global N). */
+int sfm_ba_set_totals(sfm_ba* ba, int64_t n_pt_total, int64_t n_obs_total);
+int sfm_ba_set_params(sfm_ba* ba, const double* cams /*n_cam x 6*/, const double* pts /*n_pt x 3*/);
+int sfm_ba_get_params(sfm_ba* ba, double* cams, double* pts);
+
+/* K5 — materialised residuals and Jacobian blocks (the HBM-roofline kernel):
+ * r (n_obs,2) f32, Jc (n_obs,2,6) f32, Jp (n_obs,2,3) f32 (any may be NULL; host or device),
+ * cost = 0.5*sum r^2 in float64.  mode 0: r = proj - obs.  mode 1: r = (obs-proj)^2/N, the
+ * residual of OptimReprojectionError (sfm.py:124-130).  mode 2: one value per observation,
+ * sqrt(dx^2+dy^2)/n_obs, the residual of test.py:108-112 (r is then (n_obs,) and Jc/Jp NULL). */
+int sfm_ba_eval(sfm_ba* ba, int mode, float* r, float* Jc, float* Jp, double* cost);
+
+typedef struct sfm_ba_stats {
+  double cost_before;   /* 0.5*sum r^2 at the linearisation point */
+  double cost_after;    /* at the candidate parameters */
+  double step_norm;
+  double grad_norm;
+  int32_t accepted;
+  int32_t solve_info;   /* 0 ok; >0 Cholesky failed at that pivot */
+  double lambda_next;
+} sfm_ba_stats;
+
+/* One damped Gauss-Newton (LM) iteration: K6 fused JtJ/Schur accumulation (no Jacobian in HBM),
+ * [all-reduce of the reduced camera system if a communicator is attached], dense Cholesky of the
+ * 6C x 6C system, back-substitution, parameter update, new cost; rejected steps are rolled back. */
+int sfm_ba_gn_step(sfm_ba* ba, double lambda, sfm_ba_stats* stats);
+
+/* Device views for tests and for a host-side exchange step (float32, row-major):
+ * which 0: S (6C x 6C, lower block triangle filled, damped), 1: g (6C), 2: diag(Hcc) (6C). */
+int sfm_ba_build_system(sfm_ba* ba, double lambda);
+int sfm_ba_read(sfm_ba* ba, int which, float* out, int64_t count);
+
+/* C1 — multi-GPU: points are sharded over ranks by the host; the only exchange per iteration is
+ * the all-reduce(sum) of [S | g | cost].  The communicator is created inside the library from an
+ * ncclUniqueId that the host distributes (torch.distributed does the rendezvous plumbing). */
+int sfm_nccl_unique_id(void* out128);
+int sfm_ba_comm_init(sfm_ba* ba, const void* unique_id128, int rank, int world);
+int sfm_ba_comm_destroy(sfm_ba* ba);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SFM_B200_H */

@@ -1,0 +1,901 @@
+// ba.cu — hot path 3b: bundle adjustment (K5 residual/Jacobian evaluation, K6 fused Schur
+// accumulation, reduced-camera-system solve, back-substitution / update).
+//
+// Reference: the residual every BA variant of the reference evaluates is
+//   cv2.projectPoints(X, rvec, tvec, K, None) - observation
+// (OptimReprojectionError sfm.py:104-136 -> projectPoints sfm.py:121; test.py:85-113 -> :101;
+// ba.pyc L24/L51), driven by scipy.least_squares with a dense finite-difference Jacobian
+// (sfm.py:146).  The block structure (one 2x6 camera block and one 2x3 point block per
+// observation) is the notebook's bundle_adjustment_sparsity (cell 6).  This engine evaluates the
+// same residual with analytic Jacobians and solves the Gauss-Newton / Levenberg-Marquardt step by
+// point elimination (Schur complement).
+//
+// Data layout in HBM (struct sfm_ba):
+//   obs_uv  float2[O]   observations, sorted point-major      cam_idx int[O]     pt_idx int[O]
+//   pt_start int[P+1]   CSR offsets of each point's observations
+//   cams double[C][6] (rvec|tvec)   pts double[P][3]   (+ candidate copies for step rejection)
+//   cam_pre double[C][21]: R (9) | t (3) | Jl (9) — rotation matrix and the left Jacobian of SO(3),
+//                          recomputed once per linearisation by ba_cam_prep_kernel
+//   S float[6C][6C] reduced camera system (lower block triangle filled), g float[6C]
+// Per observation:  Yr = R X,  Y = Yr + t,  (u,v) = (fx Y.x/Y.z + cx, fy Y.y/Y.z + cy)
+//   d(u,v)/dY = [[fx/z, 0, -fx Y.x/z^2], [0, fy/z, -fy Y.y/z^2]]
+//   Jc[:,0:3] = d(u,v)/dY * [ Jl e_k x Yr ]_k   (since dR/dr_k = [Jl e_k]x R),  Jc[:,3:6] = d(u,v)/dY
+//   Jp = d(u,v)/dY * R
+#include <dlfcn.h>
+#include <float.h>
+#include <math.h>
+
+#include "ba.cuh"
+#include "hostmath.h"
+
+namespace {
+
+constexpr int CAM_PRE = 21;
+constexpr int BA_MAXO = 64;   // observations per point handled by the fused kernels
+
+// ------------------------------------------------------------------ per-camera precomputation
+__global__ void ba_cam_prep_kernel(const double* __restrict__ cams, int n_cam, double* __restrict__ pre) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_cam) return;
+  const double* rv = cams + 6 * (size_t)c;
+  double* o = pre + CAM_PRE * (size_t)c;
+  double R[9];
+  hm::rodrigues_to_matrix(rv, R);
+  for (int k = 0; k < 9; ++k) o[k] = R[k];
+  o[9] = rv[3]; o[10] = rv[4]; o[11] = rv[5];
+  double th2 = rv[0] * rv[0] + rv[1] * rv[1] + rv[2] * rv[2];
+  for (int k = 0; k < 3; ++k) {
+    double a[3];
+    if (th2 < 1e-24) {
+      a[0] = k == 0; a[1] = k == 1; a[2] = k == 2;
+    } else {
+      // Jl e_k = ( r_k r + r x (I - R) e_k ) / |r|^2     (Gallego & Yezzi 2015, eq. III.7)
+      double m[3] = {(k == 0) - R[k], (k == 1) - R[3 + k], (k == 2) - R[6 + k]};
+      double cx = rv[1] * m[2] - rv[2] * m[1], cy = rv[2] * m[0] - rv[0] * m[2], cz = rv[0] * m[1] - rv[1] * m[0];
+      a[0] = (rv[k] * rv[0] + cx) / th2; a[1] = (rv[k] * rv[1] + cy) / th2; a[2] = (rv[k] * rv[2] + cz) / th2;
+    }
+    o[12 + 3 * k] = a[0]; o[13 + 3 * k] = a[1]; o[14 + 3 * k] = a[2];
+  }
+}
+
+struct Intr {
+  double fx, fy, cx, cy;
+};
+
+// residual (proj - obs) and, if WANT_J, the Jacobian blocks, all float64 in registers
+template <bool WANT_J>
+__device__ __forceinline__ void obs_geometry(const double* __restrict__ cp, const double* __restrict__ X, float2 uv,
+                                             const Intr& K, double* r, double (*Jc)[6], double (*Jp)[3]) {
+  const double Yr0 = cp[0] * X[0] + cp[1] * X[1] + cp[2] * X[2];
+  const double Yr1 = cp[3] * X[0] + cp[4] * X[1] + cp[5] * X[2];
+  const double Yr2 = cp[6] * X[0] + cp[7] * X[1] + cp[8] * X[2];
+  const double y0 = Yr0 + cp[9], y1 = Yr1 + cp[10], y2 = Yr2 + cp[11];
+  const double iz = (y2 != 0.0) ? 1.0 / y2 : 1.0;
+  const double xn = y0 * iz, yn = y1 * iz;
+  r[0] = xn * K.fx + K.cx - (double)uv.x;
+  r[1] = yn * K.fy + K.cy - (double)uv.y;
+  if (WANT_J) {
+    const double a0 = K.fx * iz, a2 = -K.fx * xn * iz, b1 = K.fy * iz, b2 = -K.fy * yn * iz;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const double ax = cp[12 + 3 * k], ay = cp[13 + 3 * k], az = cp[14 + 3 * k];
+      const double dx = ay * Yr2 - az * Yr1, dy = az * Yr0 - ax * Yr2, dz = ax * Yr1 - ay * Yr0;
+      Jc[0][k] = a0 * dx + a2 * dz;
+      Jc[1][k] = b1 * dy + b2 * dz;
+    }
+    Jc[0][3] = a0; Jc[0][4] = 0.0; Jc[0][5] = a2;
+    Jc[1][3] = 0.0; Jc[1][4] = b1; Jc[1][5] = b2;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      Jp[0][k] = a0 * cp[k] + a2 * cp[6 + k];
+      Jp[1][k] = b1 * cp[3 + k] + b2 * cp[6 + k];
+    }
+  }
+}
+
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ------------------------------------------------------------------ K5: materialised evaluation
+// Persistent CTAs; the per-camera table (C x 21 doubles) is staged in shared memory once per CTA
+// when it fits, so the per-observation gather never leaves the SM.  One observation per thread:
+// 16 B read, 80 B written (r 8 B, Jc 48 B, Jp 24 B).
+template <int MODE, bool SMEM_CAMS>
+__global__ void __launch_bounds__(256) ba_eval_kernel(const float2* __restrict__ uv, const int* __restrict__ cam_idx,
+                                                      const int* __restrict__ pt_idx, int n_obs,
+                                                      const double* __restrict__ cam_pre, int n_cam,
+                                                      const double* __restrict__ pts, Intr K, double inv_n,
+                                                      float* __restrict__ r_out, float* __restrict__ Jc_out,
+                                                      float* __restrict__ Jp_out, double* __restrict__ cost) {
+  extern __shared__ double s_cam[];
+  if (SMEM_CAMS) {
+    for (int i = threadIdx.x; i < n_cam * CAM_PRE; i += blockDim.x) s_cam[i] = cam_pre[i];
+    __syncthreads();
+  }
+  const double* cams = SMEM_CAMS ? s_cam : cam_pre;
+  double local = 0.0;
+  for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < n_obs; o += gridDim.x * blockDim.x) {
+    const float2 m = __ldg(uv + o);
+    const int c = __ldg(cam_idx + o), p = __ldg(pt_idx + o);
+    const double X[3] = {__ldg(pts + 3 * (size_t)p), __ldg(pts + 3 * (size_t)p + 1), __ldg(pts + 3 * (size_t)p + 2)};
+    double r[2], Jc[2][6], Jp[2][3];
+    if (MODE == 0) {
+      const bool want = (Jc_out != nullptr) || (Jp_out != nullptr);
+      if (want) obs_geometry<true>(cams + CAM_PRE * (size_t)c, X, m, K, r, Jc, Jp);
+      else obs_geometry<false>(cams + CAM_PRE * (size_t)c, X, m, K, r, Jc, Jp);
+      local += r[0] * r[0] + r[1] * r[1];
+      if (r_out) reinterpret_cast<float2*>(r_out)[o] = make_float2((float)r[0], (float)r[1]);
+      if (Jc_out) {
+        float4* d = reinterpret_cast<float4*>(Jc_out + 12 * (size_t)o);
+        d[0] = make_float4((float)Jc[0][0], (float)Jc[0][1], (float)Jc[0][2], (float)Jc[0][3]);
+        d[1] = make_float4((float)Jc[0][4], (float)Jc[0][5], (float)Jc[1][0], (float)Jc[1][1]);
+        d[2] = make_float4((float)Jc[1][2], (float)Jc[1][3], (float)Jc[1][4], (float)Jc[1][5]);
+      }
+      if (Jp_out) {
+        float2* d = reinterpret_cast<float2*>(Jp_out + 6 * (size_t)o);
+        d[0] = make_float2((float)Jp[0][0], (float)Jp[0][1]);
+        d[1] = make_float2((float)Jp[0][2], (float)Jp[1][0]);
+        d[2] = make_float2((float)Jp[1][1], (float)Jp[1][2]);
+      }
+    } else {
+      obs_geometry<false>(cams + CAM_PRE * (size_t)c, X, m, K, r, Jc, Jp);
+      if (MODE == 1) {        // ((p - proj)^2).ravel()/N            sfm.py:124-130
+        double a = r[0] * r[0] * inv_n, b = r[1] * r[1] * inv_n;
+        local += a * a + b * b;
+        if (r_out) reinterpret_cast<float2*>(r_out)[o] = make_float2((float)a, (float)b);
+      } else {                // sqrt(dx^2+dy^2)/len(error)            test.py:108-112
+        double a = sqrt(r[0] * r[0] + r[1] * r[1]) * inv_n;
+        local += a * a;
+        if (r_out) r_out[o] = (float)a;
+      }
+    }
+  }
+  if (cost) {
+    local = warp_sum_d(local);
+    __shared__ double s_part[8];
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = local;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double s = 0.0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += s_part[w];
+      atomicAdd(cost, 0.5 * s);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ K6: fused Schur accumulation
+__device__ __forceinline__ void red_add_v2(float* addr, float a, float b) {
+  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
+}
+
+// 3x3 symmetric (h = xx,xy,xz,yy,yz,zz) with damped diagonal -> inverse (same packing)
+__device__ __forceinline__ void inv_sym3(const double* h, double lambda, double* inv) {
+  const double a = h[0] * (1.0 + lambda), b = h[1], c = h[2], d = h[3] * (1.0 + lambda), e = h[4], f = h[5] * (1.0 + lambda);
+  const double c00 = d * f - e * e, c01 = c * e - b * f, c02 = b * e - c * d;
+  const double det = a * c00 + b * c01 + c * c02;
+  const double id = (det != 0.0) ? 1.0 / det : 0.0;
+  inv[0] = c00 * id; inv[1] = c01 * id; inv[2] = c02 * id;
+  inv[3] = (a * f - c * c) * id; inv[4] = (b * c - a * e) * id; inv[5] = (a * d - b * b) * id;
+}
+
+struct WarpPoint {            // per-warp shared scratch of the fused kernels
+  float W[BA_MAXO][18];       // W_a = Jc^T Jp   (6x3)
+  float T[BA_MAXO][18];       // T_a = W_a * Hpp^-1
+  int cam[BA_MAXO];
+};
+
+// Per point (one warp): accumulate Hpp/bp over its observations, per-observation W, Hcc/bc via
+// atomics; returns (in every lane) Hpp (6), bp (3).  MODE_UPDATE additionally needs dc.
+__device__ __forceinline__ void point_accumulate(WarpPoint& wp, int lane, int o_begin, int nobs,
+                                                 const float2* __restrict__ uv, const int* __restrict__ cam_idx,
+                                                 const double* __restrict__ cams, const double* X, const Intr& K,
+                                                 bool accumulate_cam, float* __restrict__ S, int ld,
+                                                 float* __restrict__ g, float* __restrict__ hdiag,
+                                                 double* hpp, double* bp, double* cost_local) {
+  double h[6] = {0, 0, 0, 0, 0, 0}, b[3] = {0, 0, 0};
+  for (int a = lane; a < nobs; a += 32) {
+    const int o = o_begin + a;
+    const int c = __ldg(cam_idx + o);
+    double r[2], Jc[2][6], Jp[2][3];
+    obs_geometry<true>(cams + CAM_PRE * (size_t)c, X, __ldg(uv + o), K, r, Jc, Jp);
+    *cost_local += r[0] * r[0] + r[1] * r[1];
+    h[0] += Jp[0][0] * Jp[0][0] + Jp[1][0] * Jp[1][0];
+    h[1] += Jp[0][0] * Jp[0][1] + Jp[1][0] * Jp[1][1];
+    h[2] += Jp[0][0] * Jp[0][2] + Jp[1][0] * Jp[1][2];
+    h[3] += Jp[0][1] * Jp[0][1] + Jp[1][1] * Jp[1][1];
+    h[4] += Jp[0][1] * Jp[0][2] + Jp[1][1] * Jp[1][2];
+    h[5] += Jp[0][2] * Jp[0][2] + Jp[1][2] * Jp[1][2];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) b[k] += Jp[0][k] * r[0] + Jp[1][k] * r[1];
+    wp.cam[a] = c;
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+      for (int k = 0; k < 3; ++k) wp.W[a][3 * i + k] = (float)(Jc[0][i] * Jp[0][k] + Jc[1][i] * Jp[1][k]);
+    if (accumulate_cam) {
+      float* Sd = S + (size_t)(6 * c) * ld + 6 * c;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        float row[6];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) row[j] = (float)(Jc[0][i] * Jc[0][j] + Jc[1][i] * Jc[1][j]);
+        red_add_v2(Sd + (size_t)i * ld, row[0], row[1]);
+        red_add_v2(Sd + (size_t)i * ld + 2, row[2], row[3]);
+        red_add_v2(Sd + (size_t)i * ld + 4, row[4], row[5]);
+        atomicAdd(hdiag + 6 * c + i, row[i]);
+      }
+      float gc[6];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) gc[i] = (float)(Jc[0][i] * r[0] + Jc[1][i] * r[1]);
+      red_add_v2(g + 6 * c, gc[0], gc[1]);
+      red_add_v2(g + 6 * c + 2, gc[2], gc[3]);
+      red_add_v2(g + 6 * c + 4, gc[4], gc[5]);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 6; ++k) hpp[k] = warp_sum_d(h[k]);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) bp[k] = warp_sum_d(b[k]);
+}
+
+constexpr int SCHUR_WARPS = 4;
+
+// S -= sum_p W Hpp^-1 W^T (lower block triangle), g += bc - W Hpp^-1 bp, diag blocks += Hcc.
+template <bool SMEM_CAMS>
+__global__ void __launch_bounds__(SCHUR_WARPS * 32) ba_schur_kernel(const float2* __restrict__ uv,
+                                                                    const int* __restrict__ cam_idx,
+                                                                    const int* __restrict__ pt_start, int n_pt,
+                                                                    const double* __restrict__ cam_pre, int n_cam,
+                                                                    const double* __restrict__ pts, Intr K,
+                                                                    double lambda, float* __restrict__ S, int ld,
+                                                                    float* __restrict__ g, float* __restrict__ hdiag,
+                                                                    double* __restrict__ cost) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  WarpPoint* wps = reinterpret_cast<WarpPoint*>(smem_raw);
+  double* s_cam = reinterpret_cast<double*>(smem_raw + sizeof(WarpPoint) * SCHUR_WARPS);
+  if (SMEM_CAMS) {
+    for (int i = threadIdx.x; i < n_cam * CAM_PRE; i += blockDim.x) s_cam[i] = cam_pre[i];
+    __syncthreads();
+  }
+  const double* cams = SMEM_CAMS ? s_cam : cam_pre;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  WarpPoint& wp = wps[warp];
+  double cost_local = 0.0;
+  for (int p = blockIdx.x * SCHUR_WARPS + warp; p < n_pt; p += gridDim.x * SCHUR_WARPS) {
+    const int o_begin = __ldg(pt_start + p), nobs = __ldg(pt_start + p + 1) - o_begin;
+    if (nobs <= 0) continue;
+    const double X[3] = {__ldg(pts + 3 * (size_t)p), __ldg(pts + 3 * (size_t)p + 1), __ldg(pts + 3 * (size_t)p + 2)};
+    double hpp[6], bp[3], hinv[6];
+    point_accumulate(wp, lane, o_begin, nobs, uv, cam_idx, cams, X, K, true, S, ld, g, hdiag, hpp, bp, &cost_local);
+    inv_sym3(hpp, lambda, hinv);
+    __syncwarp();
+    // T_a = W_a Hinv ; g[ca] -= T_a bp
+    for (int a = lane; a < nobs; a += 32) {
+      float t[18];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        const double w0 = wp.W[a][3 * i], w1 = wp.W[a][3 * i + 1], w2 = wp.W[a][3 * i + 2];
+        t[3 * i] = (float)(w0 * hinv[0] + w1 * hinv[1] + w2 * hinv[2]);
+        t[3 * i + 1] = (float)(w0 * hinv[1] + w1 * hinv[3] + w2 * hinv[4]);
+        t[3 * i + 2] = (float)(w0 * hinv[2] + w1 * hinv[4] + w2 * hinv[5]);
+      }
+#pragma unroll
+      for (int k = 0; k < 18; ++k) wp.T[a][k] = t[k];
+      float gc[6];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) gc[i] = -(float)(t[3 * i] * bp[0] + t[3 * i + 1] * bp[1] + t[3 * i + 2] * bp[2]);
+      float* gp = g + 6 * wp.cam[a];
+      red_add_v2(gp, gc[0], gc[1]);
+      red_add_v2(gp + 2, gc[2], gc[3]);
+      red_add_v2(gp + 4, gc[4], gc[5]);
+    }
+    __syncwarp();
+    // ordered pairs (a,b) with cam_a >= cam_b: block (cam_a, cam_b) -= T_a W_b^T
+    const int npair = nobs * nobs;
+    for (int q = lane; q < npair; q += 32) {
+      const int a = q / nobs, b = q - a * nobs;
+      const int ca = wp.cam[a], cb = wp.cam[b];
+      if (ca < cb) continue;
+      const float* Ta = wp.T[a];
+      const float* Wb = wp.W[b];
+      float* Sd = S + (size_t)(6 * ca) * ld + 6 * cb;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        float row[6];
+#pragma unroll
+        for (int j = 0; j < 6; ++j)
+          row[j] = -(Ta[3 * i] * Wb[3 * j] + Ta[3 * i + 1] * Wb[3 * j + 1] + Ta[3 * i + 2] * Wb[3 * j + 2]);
+        red_add_v2(Sd + (size_t)i * ld, row[0], row[1]);
+        red_add_v2(Sd + (size_t)i * ld + 2, row[2], row[3]);
+        red_add_v2(Sd + (size_t)i * ld + 4, row[4], row[5]);
+      }
+    }
+    __syncwarp();
+  }
+  cost_local = warp_sum_d(cost_local);
+  if (lane == 0 && cost) atomicAdd(cost, 0.5 * cost_local);
+}
+
+// S[ii] += lambda * Hcc[ii]
+__global__ void ba_damp_kernel(float* __restrict__ S, int ld, const float* __restrict__ hdiag, double lambda, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) S[(size_t)i * ld + i] += (float)(lambda * (double)hdiag[i]);
+}
+
+// ------------------------------------------------------------------ back-substitution + update
+// dp = -Hpp_d^-1 (bp + sum_a W_a^T dc[cam_a]);  candidate point = point + dp
+template <bool SMEM_CAMS>
+__global__ void __launch_bounds__(SCHUR_WARPS * 32) ba_update_points_kernel(
+    const float2* __restrict__ uv, const int* __restrict__ cam_idx, const int* __restrict__ pt_start, int n_pt,
+    const double* __restrict__ cam_pre, int n_cam, const double* __restrict__ pts, Intr K, double lambda,
+    const double* __restrict__ dc, double* __restrict__ pts_new, double* __restrict__ step2) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  WarpPoint* wps = reinterpret_cast<WarpPoint*>(smem_raw);
+  double* s_cam = reinterpret_cast<double*>(smem_raw + sizeof(WarpPoint) * SCHUR_WARPS);
+  if (SMEM_CAMS) {
+    for (int i = threadIdx.x; i < n_cam * CAM_PRE; i += blockDim.x) s_cam[i] = cam_pre[i];
+    __syncthreads();
+  }
+  const double* cams = SMEM_CAMS ? s_cam : cam_pre;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  WarpPoint& wp = wps[warp];
+  double step_local = 0.0;
+  for (int p = blockIdx.x * SCHUR_WARPS + warp; p < n_pt; p += gridDim.x * SCHUR_WARPS) {
+    const int o_begin = __ldg(pt_start + p), nobs = __ldg(pt_start + p + 1) - o_begin;
+    const double X[3] = {__ldg(pts + 3 * (size_t)p), __ldg(pts + 3 * (size_t)p + 1), __ldg(pts + 3 * (size_t)p + 2)};
+    if (nobs <= 0) {
+      if (lane < 3) pts_new[3 * (size_t)p + lane] = X[lane];
+      continue;
+    }
+    double hpp[6], bp[3], hinv[6], dummy = 0.0;
+    point_accumulate(wp, lane, o_begin, nobs, uv, cam_idx, cams, X, K, false, nullptr, 0, nullptr, nullptr, hpp, bp, &dummy);
+    inv_sym3(hpp, lambda, hinv);
+    __syncwarp();
+    double v[3] = {0, 0, 0};
+    for (int a = lane; a < nobs; a += 32) {
+      const double* d = dc + 6 * wp.cam[a];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        v[0] += (double)wp.W[a][3 * i] * d[i];
+        v[1] += (double)wp.W[a][3 * i + 1] * d[i];
+        v[2] += (double)wp.W[a][3 * i + 2] * d[i];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) v[k] = bp[k] + warp_sum_d(v[k]);
+    const double dp[3] = {-(hinv[0] * v[0] + hinv[1] * v[1] + hinv[2] * v[2]),
+                          -(hinv[1] * v[0] + hinv[3] * v[1] + hinv[4] * v[2]),
+                          -(hinv[2] * v[0] + hinv[4] * v[1] + hinv[5] * v[2])};
+    if (lane == 0) {
+      pts_new[3 * (size_t)p] = X[0] + dp[0];
+      pts_new[3 * (size_t)p + 1] = X[1] + dp[1];
+      pts_new[3 * (size_t)p + 2] = X[2] + dp[2];
+      step_local += dp[0] * dp[0] + dp[1] * dp[1] + dp[2] * dp[2];
+    }
+    __syncwarp();
+  }
+  if (lane == 0 && step2 && step_local != 0.0) atomicAdd(step2, step_local);
+}
+
+__global__ void ba_update_cams_kernel(const double* __restrict__ cams, const double* __restrict__ dc, int n,
+                                      double* __restrict__ cams_new, double* __restrict__ step2) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double d = 0.0;
+  if (i < n) { d = dc[i]; cams_new[i] = cams[i] + d; }
+  d = warp_sum_d(d * d);
+  if ((threadIdx.x & 31) == 0 && d != 0.0) atomicAdd(step2, d);
+}
+
+// ------------------------------------------------------------------ dense SPD solve (float64)
+// Reduced camera system: n = 6C (3000 at C = 500).  Right-looking blocked Cholesky, NB = 64:
+//   chol_diag_kernel   factor the 64x64 diagonal block in shared memory (one CTA)
+//   chol_panel_kernel  L21 = A21 L11^-T, 64 rows per CTA
+//   chol_syrk_kernel   A22 -= L21 L21^T on the lower triangle, 64x64 tile per CTA, 4x4 per thread
+// followed by blocked forward / backward substitution.  A is n x n row-major, lower triangle used.
+constexpr int NB = 64;
+
+__global__ void __launch_bounds__(256) chol_diag_kernel(double* __restrict__ A, int n, int k0, int* __restrict__ info) {
+  __shared__ double s[NB][NB + 1];
+  const int nb = min(NB, n - k0);
+  for (int i = threadIdx.x; i < nb * nb; i += blockDim.x) {
+    int r = i / nb, c = i % nb;
+    s[r][c] = (c <= r) ? A[(size_t)(k0 + r) * n + k0 + c] : 0.0;
+  }
+  __syncthreads();
+  for (int j = 0; j < nb; ++j) {
+    if (threadIdx.x == 0) {
+      double d = s[j][j];
+      if (!(d > 0.0)) { if (*info == 0) *info = k0 + j + 1; d = 1.0; }   // not positive definite
+      s[j][j] = sqrt(d);
+    }
+    __syncthreads();
+    const double djj = s[j][j];
+    for (int i = j + 1 + threadIdx.x; i < nb; i += blockDim.x) s[i][j] /= djj;
+    __syncthreads();
+    // trailing update of the block: s[i][c] -= s[i][j]*s[c][j] for j < c <= i
+    for (int t = threadIdx.x; t < (nb - j - 1) * (nb - j - 1); t += blockDim.x) {
+      int i = j + 1 + t / (nb - j - 1), c = j + 1 + t % (nb - j - 1);
+      if (c <= i) s[i][c] -= s[i][j] * s[c][j];
+    }
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < nb * nb; i += blockDim.x) {
+    int r = i / nb, c = i % nb;
+    if (c <= r) A[(size_t)(k0 + r) * n + k0 + c] = s[r][c];
+  }
+}
+
+__global__ void __launch_bounds__(NB) chol_panel_kernel(double* __restrict__ A, int n, int k0) {
+  __shared__ double L[NB][NB + 1];
+  const int nb = min(NB, n - k0);
+  for (int i = threadIdx.x; i < nb * nb; i += blockDim.x) {
+    int r = i / nb, c = i % nb;
+    L[r][c] = (c <= r) ? A[(size_t)(k0 + r) * n + k0 + c] : 0.0;
+  }
+  __syncthreads();
+  const int row = k0 + nb + blockIdx.x * NB + threadIdx.x;
+  if (row >= n) return;
+  double x[NB];
+  double* a = A + (size_t)row * n + k0;
+#pragma unroll 8
+  for (int j = 0; j < NB; ++j) x[j] = (j < nb) ? a[j] : 0.0;
+  // solve x L^T = a  ->  x[j] = (a[j] - sum_{k<j} x[k] L[j][k]) / L[j][j]
+#pragma unroll
+  for (int j = 0; j < NB; ++j) {
+    if (j < nb) {
+      double s = x[j];
+#pragma unroll
+      for (int k = 0; k < j; ++k) s -= x[k] * L[j][k];
+      x[j] = s / L[j][j];
+    }
+  }
+#pragma unroll 8
+  for (int j = 0; j < NB; ++j)
+    if (j < nb) a[j] = x[j];
+}
+
+// C[i][j] -= sum_k P[i][k] P[j][k], P = A[:, k0:k0+nb]; tiles (ti >= tj) of the trailing matrix
+__global__ void __launch_bounds__(256) chol_syrk_kernel(double* __restrict__ A, int n, int k0, int nb) {
+  constexpr int KC = 32;
+  __shared__ double Pi[NB][KC + 1];
+  __shared__ double Pj[NB][KC + 1];
+  // decode lower-triangular tile index
+  int t = blockIdx.x;
+  int ti = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+  while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+  while (ti * (ti + 1) / 2 > t) --ti;
+  const int tj = t - ti * (ti + 1) / 2;
+  const int base = k0 + nb;
+  const int i0 = base + ti * NB, j0 = base + tj * NB;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  double acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+  for (int kc = 0; kc < nb; kc += KC) {
+    __syncthreads();
+    for (int e = threadIdx.x; e < NB * KC; e += blockDim.x) {
+      int r = e / KC, c = e % KC;
+      Pi[r][c] = (i0 + r < n && kc + c < nb) ? A[(size_t)(i0 + r) * n + k0 + kc + c] : 0.0;
+      Pj[r][c] = (j0 + r < n && kc + c < nb) ? A[(size_t)(j0 + r) * n + k0 + kc + c] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int k = 0; k < KC; ++k) {
+      double av[4], bv[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) av[a] = Pi[ty + 16 * a][k];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) bv[b] = Pj[tx + 16 * b][k];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] += av[a] * bv[b];
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      int i = i0 + ty + 16 * a, j = j0 + tx + 16 * b;
+      if (i < n && j < n && j <= i) A[(size_t)i * n + j] -= acc[a][b];
+    }
+}
+
+// Blocked triangular solves with the factor L (lower, row-major):  L y = b  then  L^T x = y.
+__global__ void __launch_bounds__(NB) trsv_diag_kernel(const double* __restrict__ A, int n, int k0, double* __restrict__ x,
+                                                       int transpose) {
+  __shared__ double L[NB][NB + 1];
+  __shared__ double v[NB];
+  const int nb = min(NB, n - k0);
+  for (int i = threadIdx.x; i < nb * nb; i += blockDim.x) {
+    int r = i / nb, c = i % nb;
+    L[r][c] = (c <= r) ? A[(size_t)(k0 + r) * n + k0 + c] : 0.0;
+  }
+  if (threadIdx.x < nb) v[threadIdx.x] = x[k0 + threadIdx.x];
+  __syncthreads();
+  if (!transpose) {
+    for (int j = 0; j < nb; ++j) {
+      if (threadIdx.x == 0) v[j] /= L[j][j];
+      __syncthreads();
+      if ((int)threadIdx.x > j && (int)threadIdx.x < nb) v[threadIdx.x] -= L[threadIdx.x][j] * v[j];
+      __syncthreads();
+    }
+  } else {
+    for (int j = nb - 1; j >= 0; --j) {
+      if (threadIdx.x == 0) v[j] /= L[j][j];
+      __syncthreads();
+      if ((int)threadIdx.x < j) v[threadIdx.x] -= L[j][threadIdx.x] * v[j];
+      __syncthreads();
+    }
+  }
+  if (threadIdx.x < nb) x[k0 + threadIdx.x] = v[threadIdx.x];
+}
+
+// forward: x[i] -= sum_{c in block} L[i][k0+c] x[k0+c] for i >= k0+nb   (one warp per row)
+// backward: x[i] -= sum_{r in block} L[k0+r][i] x[k0+r] for i < k0        (one thread per column)
+__global__ void __launch_bounds__(256) trsv_update_kernel(const double* __restrict__ A, int n, int k0, int nb,
+                                                         double* __restrict__ x, int transpose) {
+  if (!transpose) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int i = k0 + nb + warp;
+    if (i >= n) return;
+    double s = 0.0;
+    for (int c = lane; c < nb; c += 32) s += A[(size_t)i * n + k0 + c] * x[k0 + c];
+    s = warp_sum_d(s);
+    if (lane == 0) x[i] -= s;
+  } else {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= k0) return;
+    double s = 0.0;
+    for (int r = 0; r < nb; ++r) s += A[(size_t)(k0 + r) * n + i] * x[k0 + r];
+    x[i] -= s;
+  }
+}
+
+__global__ void ba_widen_kernel(const float* __restrict__ S, const float* __restrict__ g, int n, double* __restrict__ A,
+                                double* __restrict__ rhs) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t total = (size_t)n * n;
+  if (idx < total) {
+    int r = (int)(idx / n), c = (int)(idx % n);
+    A[idx] = (c <= r) ? (double)S[idx] : 0.0;
+  }
+  if (idx < (size_t)n) rhs[idx] = -(double)g[idx];
+}
+
+int solve_reduced_system(sfm_ba* ba) {
+  sfm_ctx* ctx = ba->ctx;
+  const int n = 6 * ba->n_cam;
+  size_t total = (size_t)n * n;
+  SFM_LAUNCH(ctx, SFM_K_BA_SOLVE, (ba_widen_kernel<<<(unsigned)div_up64((int64_t)total, 256), 256, 0, ctx->stream>>>(
+                                      ba->S, ba->g, n, ba->A64, ba->dc)));
+  SFM_CUDA(cudaMemsetAsync(ba->info, 0, sizeof(int), ctx->stream));
+  for (int k0 = 0; k0 < n; k0 += NB) {
+    const int nb = std::min(NB, n - k0);
+    SFM_LAUNCH(ctx, SFM_K_BA_SOLVE, (chol_diag_kernel<<<1, 256, 0, ctx->stream>>>(ba->A64, n, k0, ba->info)));
+    const int rest = n - k0 - nb;
+    if (rest > 0) {
+      SFM_LAUNCH(ctx, SFM_K_BA_SOLVE, (chol_panel_kernel<<<div_up(rest, NB), NB, 0, ctx->stream>>>(ba->A64, n, k0)));
+      const int tiles = div_up(rest, NB);
+      SFM_LAUNCH(ctx, SFM_K_BA_SOLVE, (chol_syrk_kernel<<<tiles * (tiles + 1) / 2, 256, 0, ctx->stream>>>(ba->A64, n, k0, nb)));
+    }
+  }
+  for (int k0 = 0; k0 < n; k0 += NB) {
+    const int nb = std::min(NB, n - k0);
+    SFM_LAUNCH(ctx, SFM_K_BA_SOLVE, (trsv_diag_kernel<<<1, NB, 0, ctx->stream>>>(ba->A64, n, k0, ba->dc, 0)));
+    const int rest = n - k0 - nb;
+    if (rest > 0)
+      SFM_LAUNCH(ctx, SFM_K_BA_SOLVE, (trsv_update_kernel<<<div_up(rest * 32, 256), 256, 0, ctx->stream>>>(ba->A64, n, k0, nb, ba->dc, 0)));
+  }
+  for (int k0 = ((n - 1) / NB) * NB; k0 >= 0; k0 -= NB) {
+    const int nb = std::min(NB, n - k0);
+    SFM_LAUNCH(ctx, SFM_K_BA_SOLVE, (trsv_diag_kernel<<<1, NB, 0, ctx->stream>>>(ba->A64, n, k0, ba->dc, 1)));
+    if (k0 > 0)
+      SFM_LAUNCH(ctx, SFM_K_BA_SOLVE, (trsv_update_kernel<<<div_up(k0, 256), 256, 0, ctx->stream>>>(ba->A64, n, k0, nb, ba->dc, 1)));
+  }
+  return SFM_OK;
+}
+
+Intr make_intr(const sfm_ba* ba) {
+  Intr k = {ba->K[0], ba->K[4], ba->K[2], ba->K[5]};
+  return k;
+}
+
+size_t cam_smem_bytes(const sfm_ba* ba) { return (size_t)ba->n_cam * CAM_PRE * sizeof(double); }
+
+int cam_prep(sfm_ba* ba, const double* cams) {
+  SFM_LAUNCH(ba->ctx, SFM_K_MISC, (ba_cam_prep_kernel<<<div_up(ba->n_cam, 128), 128, 0, ba->ctx->stream>>>(cams, ba->n_cam, ba->cam_pre)));
+  return SFM_OK;
+}
+
+// cost-only evaluation at (cams, pts): *cost_dev += 0.5 sum r^2
+template <int MODE>
+int launch_eval(sfm_ba* ba, const double* pts, float* r, float* Jc, float* Jp, double* cost_dev) {
+  sfm_ctx* ctx = ba->ctx;
+  const size_t smem = cam_smem_bytes(ba);
+  const bool in_smem = smem <= 96 * 1024;
+  const double inv_n = 1.0 / (double)(ba->n_obs_total > 0 ? ba->n_obs_total : 1);
+  int grid = std::min(div_up(ba->n_obs, 256), ctx->sm_count * 2);
+  if (grid < 1) grid = 1;
+  if (in_smem) {
+    static bool attr[3] = {false, false, false};
+    if (!attr[MODE]) {
+      SFM_CUDA(cudaFuncSetAttribute(ba_eval_kernel<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      attr[MODE] = true;
+    }
+    SFM_LAUNCH(ctx, SFM_K_BA_EVAL, (ba_eval_kernel<MODE, true><<<grid, 256, smem, ctx->stream>>>(
+                                       ba->uv, ba->cam_idx, ba->pt_idx, ba->n_obs, ba->cam_pre, ba->n_cam, pts,
+                                       make_intr(ba), inv_n, r, Jc, Jp, cost_dev)));
+  } else {
+    grid = std::max(1, std::min(div_up(ba->n_obs, 256), ctx->sm_count * 8));
+    SFM_LAUNCH(ctx, SFM_K_BA_EVAL, (ba_eval_kernel<MODE, false><<<grid, 256, 0, ctx->stream>>>(
+                                       ba->uv, ba->cam_idx, ba->pt_idx, ba->n_obs, ba->cam_pre, ba->n_cam, pts,
+                                       make_intr(ba), inv_n, r, Jc, Jp, cost_dev)));
+  }
+  return SFM_OK;
+}
+
+int build_system(sfm_ba* ba, double lambda) {
+  sfm_ctx* ctx = ba->ctx;
+  const int n = 6 * ba->n_cam;
+  SFM_TRY(cam_prep(ba, ba->cams));
+  // S | g | hdiag are one allocation (sys_f32) so a single memset / all-reduce covers them
+  SFM_CUDA(cudaMemsetAsync(ba->S, 0, ba->sys_count * sizeof(float), ctx->stream));
+  SFM_CUDA(cudaMemsetAsync(ba->scal, 0, 8 * sizeof(double), ctx->stream));
+  const size_t wp_bytes = sizeof(WarpPoint) * SCHUR_WARPS;
+  const size_t smem_cams = cam_smem_bytes(ba);
+  const bool in_smem = wp_bytes + smem_cams <= 160 * 1024;
+  int grid = std::max(1, std::min(div_up(ba->n_pt, SCHUR_WARPS), ctx->sm_count * (in_smem ? 1 : 4)));
+  if (ba->n_pt > 0) {
+    if (in_smem) {
+      static bool attr = false;
+      if (!attr) {
+        SFM_CUDA(cudaFuncSetAttribute(ba_schur_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        attr = true;
+      }
+      SFM_LAUNCH(ctx, SFM_K_BA_SCHUR, (ba_schur_kernel<true><<<grid, SCHUR_WARPS * 32, wp_bytes + smem_cams, ctx->stream>>>(
+                                          ba->uv, ba->cam_idx, ba->pt_start, ba->n_pt, ba->cam_pre, ba->n_cam, ba->pts,
+                                          make_intr(ba), lambda, ba->S, n, ba->g, ba->hdiag, ba->scal + 0)));
+    } else {
+      static bool attr = false;
+      if (!attr) {
+        SFM_CUDA(cudaFuncSetAttribute(ba_schur_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        attr = true;
+      }
+      SFM_LAUNCH(ctx, SFM_K_BA_SCHUR, (ba_schur_kernel<false><<<grid, SCHUR_WARPS * 32, wp_bytes, ctx->stream>>>(
+                                          ba->uv, ba->cam_idx, ba->pt_start, ba->n_pt, ba->cam_pre, ba->n_cam, ba->pts,
+                                          make_intr(ba), lambda, ba->S, n, ba->g, ba->hdiag, ba->scal + 0)));
+    }
+  }
+  // exchange step (C1): sum of the partial systems and of the cost over ranks
+  SFM_TRY(sfm_ba_allreduce_system(ba));
+  SFM_LAUNCH(ctx, SFM_K_MISC, (ba_damp_kernel<<<div_up(n, 256), 256, 0, ctx->stream>>>(ba->S, n, ba->hdiag, lambda, n)));
+  return SFM_OK;
+}
+
+int update_points(sfm_ba* ba, double lambda) {
+  sfm_ctx* ctx = ba->ctx;
+  const size_t wp_bytes = sizeof(WarpPoint) * SCHUR_WARPS;
+  const size_t smem_cams = cam_smem_bytes(ba);
+  const bool in_smem = wp_bytes + smem_cams <= 160 * 1024;
+  int grid = std::max(1, std::min(div_up(ba->n_pt, SCHUR_WARPS), ctx->sm_count * (in_smem ? 1 : 4)));
+  if (ba->n_pt == 0) return SFM_OK;
+  if (in_smem) {
+    static bool attr = false;
+    if (!attr) {
+      SFM_CUDA(cudaFuncSetAttribute(ba_update_points_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+      attr = true;
+    }
+    SFM_LAUNCH(ctx, SFM_K_BA_UPDATE, (ba_update_points_kernel<true><<<grid, SCHUR_WARPS * 32, wp_bytes + smem_cams, ctx->stream>>>(
+                                         ba->uv, ba->cam_idx, ba->pt_start, ba->n_pt, ba->cam_pre, ba->n_cam, ba->pts,
+                                         make_intr(ba), lambda, ba->dc, ba->pts_new, ba->scal + 2)));
+  } else {
+    static bool attr = false;
+    if (!attr) {
+      SFM_CUDA(cudaFuncSetAttribute(ba_update_points_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+      attr = true;
+    }
+    SFM_LAUNCH(ctx, SFM_K_BA_UPDATE, (ba_update_points_kernel<false><<<grid, SCHUR_WARPS * 32, wp_bytes, ctx->stream>>>(
+                                         ba->uv, ba->cam_idx, ba->pt_start, ba->n_pt, ba->cam_pre, ba->n_cam, ba->pts,
+                                         make_intr(ba), lambda, ba->dc, ba->pts_new, ba->scal + 2)));
+  }
+  return SFM_OK;
+}
+
+}  // namespace
+
+// ============================================================================ C ABI
+extern "C" int sfm_ba_create(sfm_ctx* ctx, int n_cam, int n_pt, int n_obs, const int32_t* cam_idx,
+                             const int32_t* pt_idx, const float* obs, const double* K, sfm_ba** out) {
+  SFM_REQUIRE(ctx && out && K, "sfm_ba_create: null argument");
+  SFM_REQUIRE(n_cam >= 1 && n_pt >= 0 && n_obs >= 0, "sfm_ba_create: bad sizes");
+  SFM_REQUIRE(n_obs == 0 || (cam_idx && pt_idx && obs), "sfm_ba_create: null observation arrays");
+  SFM_REQUIRE(!sfm_is_device_ptr(cam_idx) && !sfm_is_device_ptr(pt_idx) && !sfm_is_device_ptr(obs),
+              "sfm_ba_create: observation arrays must be host pointers (they are validated and indexed on the host)");
+  std::vector<int> start((size_t)n_pt + 1, 0);
+  for (int o = 0; o < n_obs; ++o) {
+    SFM_REQUIRE(cam_idx[o] >= 0 && cam_idx[o] < n_cam, "sfm_ba_create: cam_idx[%d]=%d out of range", o, cam_idx[o]);
+    SFM_REQUIRE(pt_idx[o] >= 0 && pt_idx[o] < n_pt, "sfm_ba_create: pt_idx[%d]=%d out of range", o, pt_idx[o]);
+    SFM_REQUIRE(o == 0 || pt_idx[o] >= pt_idx[o - 1], "sfm_ba_create: observations must be sorted point-major (pt_idx non-decreasing)");
+    start[(size_t)pt_idx[o] + 1]++;
+  }
+  for (int p = 0; p < n_pt; ++p) {
+    if (start[(size_t)p + 1] > BA_MAXO) {
+      sfm_set_error("sfm_ba_create: point %d has %d observations; the fused kernels handle at most %d", p, start[(size_t)p + 1], BA_MAXO);
+      return SFM_ERR_UNSUPPORTED;
+    }
+    start[(size_t)p + 1] += start[p];
+  }
+  SFM_CUDA(cudaSetDevice(ctx->device));
+  sfm_ba* ba = new sfm_ba();
+  ba->ctx = ctx; ba->n_cam = n_cam; ba->n_pt = n_pt; ba->n_obs = n_obs;
+  ba->n_pt_total = n_pt; ba->n_obs_total = n_obs;
+  memcpy(ba->K, K, 9 * sizeof(double));
+  const int n = 6 * n_cam;
+  ba->sys_count = (size_t)n * n + 2 * (size_t)n;
+  cudaError_t e = cudaSuccess;
+  auto A = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes ? bytes : 16); };
+  A((void**)&ba->uv, sizeof(float2) * (size_t)n_obs);
+  A((void**)&ba->cam_idx, sizeof(int) * (size_t)n_obs);
+  A((void**)&ba->pt_idx, sizeof(int) * (size_t)n_obs);
+  A((void**)&ba->pt_start, sizeof(int) * ((size_t)n_pt + 1));
+  A((void**)&ba->cams, sizeof(double) * 6 * (size_t)n_cam);
+  A((void**)&ba->cams_new, sizeof(double) * 6 * (size_t)n_cam);
+  A((void**)&ba->pts, sizeof(double) * 3 * (size_t)n_pt);
+  A((void**)&ba->pts_new, sizeof(double) * 3 * (size_t)n_pt);
+  A((void**)&ba->cam_pre, sizeof(double) * CAM_PRE * (size_t)n_cam);
+  A((void**)&ba->S, sizeof(float) * ba->sys_count);
+  A((void**)&ba->A64, sizeof(double) * (size_t)n * n);
+  A((void**)&ba->dc, sizeof(double) * (size_t)n);
+  A((void**)&ba->scal, sizeof(double) * 8);
+  A((void**)&ba->info, sizeof(int));
+  if (e != cudaSuccess) {
+    sfm_set_error("sfm_ba_create: cudaMalloc failed: %s", cudaGetErrorString(e));
+    sfm_ba_destroy(ba);
+    return SFM_ERR_NOMEM;
+  }
+  ba->g = ba->S + (size_t)n * n;
+  ba->hdiag = ba->g + n;
+  cudaStream_t st = ctx->stream;
+  if (n_obs) {
+    SFM_CUDA(cudaMemcpyAsync(ba->uv, obs, sizeof(float2) * (size_t)n_obs, cudaMemcpyHostToDevice, st));
+    SFM_CUDA(cudaMemcpyAsync(ba->cam_idx, cam_idx, sizeof(int) * (size_t)n_obs, cudaMemcpyHostToDevice, st));
+    SFM_CUDA(cudaMemcpyAsync(ba->pt_idx, pt_idx, sizeof(int) * (size_t)n_obs, cudaMemcpyHostToDevice, st));
+  }
+  SFM_CUDA(cudaMemcpyAsync(ba->pt_start, start.data(), sizeof(int) * ((size_t)n_pt + 1), cudaMemcpyHostToDevice, st));
+  SFM_CUDA(cudaMemsetAsync(ba->cams, 0, sizeof(double) * 6 * (size_t)n_cam, st));
+  SFM_CUDA(cudaMemsetAsync(ba->pts, 0, sizeof(double) * 3 * (size_t)n_pt + (n_pt ? 0 : 16), st));
+  SFM_CUDA(cudaStreamSynchronize(st));
+  *out = ba;
+  return SFM_OK;
+}
+
+extern "C" void sfm_ba_destroy(sfm_ba* ba) {
+  if (!ba) return;
+  if (ba->ctx) { cudaSetDevice(ba->ctx->device); cudaStreamSynchronize(ba->ctx->stream); }
+  sfm_ba_comm_destroy(ba);
+  void* ptrs[] = {ba->uv, ba->cam_idx, ba->pt_idx, ba->pt_start, ba->cams, ba->cams_new, ba->pts, ba->pts_new,
+                  ba->cam_pre, ba->S, ba->A64, ba->dc, ba->scal, ba->info};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  delete ba;
+}
+
+extern "C" int sfm_ba_set_totals(sfm_ba* ba, int64_t n_pt_total, int64_t n_obs_total) {
+  SFM_REQUIRE(ba && n_pt_total >= ba->n_pt && n_obs_total >= ba->n_obs, "sfm_ba_set_totals: bad totals");
+  ba->n_pt_total = n_pt_total;
+  ba->n_obs_total = n_obs_total;
+  return SFM_OK;
+}
+
+extern "C" int sfm_ba_set_params(sfm_ba* ba, const double* cams, const double* pts) {
+  SFM_REQUIRE(ba, "sfm_ba_set_params: null problem");
+  cudaStream_t st = ba->ctx->stream;
+  SFM_CUDA(cudaSetDevice(ba->ctx->device));
+  if (cams) SFM_CUDA(cudaMemcpyAsync(ba->cams, cams, sizeof(double) * 6 * (size_t)ba->n_cam, cudaMemcpyDefault, st));
+  if (pts && ba->n_pt) SFM_CUDA(cudaMemcpyAsync(ba->pts, pts, sizeof(double) * 3 * (size_t)ba->n_pt, cudaMemcpyDefault, st));
+  SFM_CUDA(cudaStreamSynchronize(st));
+  return SFM_OK;
+}
+
+extern "C" int sfm_ba_get_params(sfm_ba* ba, double* cams, double* pts) {
+  SFM_REQUIRE(ba, "sfm_ba_get_params: null problem");
+  cudaStream_t st = ba->ctx->stream;
+  SFM_CUDA(cudaSetDevice(ba->ctx->device));
+  if (cams) SFM_CUDA(cudaMemcpyAsync(cams, ba->cams, sizeof(double) * 6 * (size_t)ba->n_cam, cudaMemcpyDefault, st));
+  if (pts && ba->n_pt) SFM_CUDA(cudaMemcpyAsync(pts, ba->pts, sizeof(double) * 3 * (size_t)ba->n_pt, cudaMemcpyDefault, st));
+  SFM_CUDA(cudaStreamSynchronize(st));
+  return SFM_OK;
+}
+
+extern "C" int sfm_ba_eval(sfm_ba* ba, int mode, float* r, float* Jc, float* Jp, double* cost) {
+  SFM_REQUIRE(ba, "sfm_ba_eval: null problem");
+  SFM_REQUIRE(mode >= 0 && mode <= 2, "sfm_ba_eval: mode %d", mode);
+  SFM_REQUIRE(mode == 0 || (!Jc && !Jp), "sfm_ba_eval: Jacobians exist for mode 0 only");
+  sfm_ctx* ctx = ba->ctx;
+  SFM_TRY(sfm_ws_begin(ctx));
+  const size_t O = (size_t)ba->n_obs;
+  bool host_out = false;
+  DevOut<float> orr, ojc, ojp;
+  DevOut<double> oc;
+  SFM_TRY(dev_out(ctx, r, (mode == 2 ? 1 : 2) * O, &orr, &host_out));
+  SFM_TRY(dev_out(ctx, Jc, 12 * O, &ojc, &host_out));
+  SFM_TRY(dev_out(ctx, Jp, 6 * O, &ojp, &host_out));
+  SFM_TRY(dev_out(ctx, cost, 1, &oc, &host_out));
+  SFM_TRY(cam_prep(ba, ba->cams));
+  if (oc.dev) SFM_CUDA(cudaMemsetAsync(oc.dev, 0, sizeof(double), ctx->stream));
+  if (O > 0) {
+    if (mode == 0) SFM_TRY(launch_eval<0>(ba, ba->pts, orr.dev, ojc.dev, ojp.dev, oc.dev));
+    else if (mode == 1) SFM_TRY(launch_eval<1>(ba, ba->pts, orr.dev, nullptr, nullptr, oc.dev));
+    else SFM_TRY(launch_eval<2>(ba, ba->pts, orr.dev, nullptr, nullptr, oc.dev));
+  }
+  SFM_TRY(dev_out_finish(ctx, &orr));
+  SFM_TRY(dev_out_finish(ctx, &ojc));
+  SFM_TRY(dev_out_finish(ctx, &ojp));
+  SFM_TRY(dev_out_finish(ctx, &oc));
+  if (host_out) SFM_CUDA(cudaStreamSynchronize(ctx->stream));
+  return SFM_OK;
+}
+
+extern "C" int sfm_ba_build_system(sfm_ba* ba, double lambda) {
+  SFM_REQUIRE(ba && lambda >= 0.0, "sfm_ba_build_system: bad argument");
+  SFM_TRY(sfm_ws_begin(ba->ctx));
+  return build_system(ba, lambda);
+}
+
+extern "C" int sfm_ba_read(sfm_ba* ba, int which, float* out, int64_t count) {
+  SFM_REQUIRE(ba && out, "sfm_ba_read: null argument");
+  const int n = 6 * ba->n_cam;
+  const float* src = nullptr;
+  int64_t have = 0;
+  if (which == 0) { src = ba->S; have = (int64_t)n * n; }
+  else if (which == 1) { src = ba->g; have = n; }
+  else if (which == 2) { src = ba->hdiag; have = n; }
+  SFM_REQUIRE(src, "sfm_ba_read: which=%d", which);
+  SFM_REQUIRE(count <= have, "sfm_ba_read: count %lld > %lld", (long long)count, (long long)have);
+  SFM_CUDA(cudaMemcpyAsync(out, src, sizeof(float) * (size_t)count, cudaMemcpyDefault, ba->ctx->stream));
+  SFM_CUDA(cudaStreamSynchronize(ba->ctx->stream));
+  return SFM_OK;
+}
+
+extern "C" int sfm_ba_gn_step(sfm_ba* ba, double lambda, sfm_ba_stats* stats) {
+  SFM_REQUIRE(ba && lambda >= 0.0, "sfm_ba_gn_step: bad argument");
+  sfm_ctx* ctx = ba->ctx;
+  SFM_TRY(sfm_ws_begin(ctx));
+  const int n = 6 * ba->n_cam;
+  SFM_TRY(build_system(ba, lambda));                 // scal[0] = cost at the linearisation point (all ranks)
+  SFM_TRY(solve_reduced_system(ba));                 // dc
+  SFM_TRY(update_points(ba, lambda));                // pts_new, scal[2] += |dp|^2 (cam_pre still at cams)
+  SFM_LAUNCH(ctx, SFM_K_BA_UPDATE, (ba_update_cams_kernel<<<div_up(n, 256), 256, 0, ctx->stream>>>(ba->cams, ba->dc, n, ba->cams_new, ba->scal + 3)));
+  SFM_TRY(cam_prep(ba, ba->cams_new));
+  if (ba->n_obs > 0) SFM_TRY(launch_eval<0>(ba, ba->pts_new, nullptr, nullptr, nullptr, ba->scal + 1));
+  SFM_TRY(sfm_ba_allreduce_scalars(ba));             // scal[1] (new cost), scal[2] (|dp|^2) summed over ranks
+  double* h;
+  int* hinfo;
+  SFM_TRY(hs_alloc_t(ctx, 8, &h));
+  SFM_TRY(hs_alloc_t(ctx, 1, &hinfo));
+  SFM_CUDA(cudaMemcpyAsync(h, ba->scal, 8 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  SFM_CUDA(cudaMemcpyAsync(hinfo, ba->info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  SFM_CUDA(cudaStreamSynchronize(ctx->stream));
+  const double cost0 = h[0], cost1 = h[1];
+  const bool ok = (*hinfo == 0) && isfinite(cost1) && cost1 < cost0;
+  if (ok) {
+    std::swap(ba->cams, ba->cams_new);
+    std::swap(ba->pts, ba->pts_new);
+  }
+  if (stats) {
+    stats->cost_before = cost0;
+    stats->cost_after = cost1;
+    stats->step_norm = sqrt(h[2] + h[3]);
+    stats->grad_norm = 0.0;
+    stats->accepted = ok ? 1 : 0;
+    stats->solve_info = *hinfo;
+    stats->lambda_next = ok ? fmax(lambda / 10.0, 1e-12) : fmin(fmax(lambda, 1e-6) * 10.0, 1e12);
+  }
+  return SFM_OK;
+}

@@ -1,0 +1,431 @@
+// geometry.cu — K2 DLT triangulation, K3 reprojection error, common_points association.
+//
+// Reference call sites (FlagArihant2000/sfm-mvs):
+//   Triangulation      sfm.py:45-56   (cv2.triangulatePoints sfm.py:53, w-normalise sfm.py:54)
+//   ReprojectionError  sfm.py:79-100  (Rodrigues :84, convertPointsFromHomogeneous :86,
+//                                      projectPoints :88, cv2.norm/N :91-95)
+//   common_points      sfm.py:215-239
+#include <float.h>
+#include <math.h>
+
+#include "common.cuh"
+#include "hostmath.h"
+
+// ============================================================================ K2 triangulate
+struct ProjPair {
+  double P1[12];
+  double P2[12];
+};
+
+// One-sided (Hestenes) Jacobi SVD of the 4x4 DLT matrix in float64, one point per thread, all
+// state in registers.  The rotation schedule (cyclic i<j, rotate while |p| > eps*sqrt(a*b), at
+// most 30 sweeps) and the rotation formula are those of the Jacobi SVD OpenCV runs for a 4x4
+// double matrix, so the returned singular vector normally carries the same sign as cv2's.
+__device__ __forceinline__ void dlt_null_vector(double (&At)[4][4], double (&out)[4]) {
+  double Vt[4][4];
+  double W[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    double sd = 0.0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      sd += At[i][k] * At[i][k];
+      Vt[i][k] = (i == k) ? 1.0 : 0.0;
+    }
+    W[i] = sd;
+  }
+  const double eps = DBL_EPSILON * 10.0;
+  for (int iter = 0; iter < 30; ++iter) {
+    bool changed = false;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+#pragma unroll
+      for (int j = i + 1; j < 4; ++j) {
+        double a = W[i], b = W[j], p = 0.0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) p += At[i][k] * At[j][k];
+        if (fabs(p) <= eps * sqrt(a * b)) continue;
+        p *= 2.0;
+        double beta = a - b, gamma = hypot(p, beta);
+        double c, s;
+        if (beta < 0.0) {
+          double delta = (gamma - beta) * 0.5;
+          s = sqrt(delta / gamma);
+          c = p / (gamma * s * 2.0);
+        } else {
+          c = sqrt((gamma + beta) / (gamma * 2.0));
+          s = p / (gamma * c * 2.0);
+        }
+        a = 0.0;
+        b = 0.0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          double t0 = c * At[i][k] + s * At[j][k];
+          double t1 = -s * At[i][k] + c * At[j][k];
+          At[i][k] = t0;
+          At[j][k] = t1;
+          a += t0 * t0;
+          b += t1 * t1;
+        }
+        W[i] = a;
+        W[j] = b;
+        changed = true;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          double t0 = c * Vt[i][k] + s * Vt[j][k];
+          double t1 = -s * Vt[i][k] + c * Vt[j][k];
+          Vt[i][k] = t0;
+          Vt[j][k] = t1;
+        }
+      }
+    }
+    if (!changed) break;
+  }
+  // smallest singular value = smallest row norm of the rotated At; on exact ties the later row
+  // (what a descending selection sort leaves last)
+  int m = 0;
+  double wm = 0.0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    double sd = 0.0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) sd += At[i][k] * At[i][k];
+    if (i == 0 || sd <= wm) { wm = sd; m = i; }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    double v = Vt[0][k];
+    v = (m == 1) ? Vt[1][k] : v;
+    v = (m == 2) ? Vt[2][k] : v;
+    v = (m == 3) ? Vt[3][k] : v;
+    out[k] = v;
+  }
+}
+
+template <int PTS_LAYOUT, int OUT_LAYOUT>
+__global__ void __launch_bounds__(128) triangulate_kernel(ProjPair pp, const float* __restrict__ x1,
+                                                           const float* __restrict__ x2, int n,
+                                                           float* __restrict__ X, int normalize_w) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float u1, v1, u2, v2;
+  if (PTS_LAYOUT == 0) {   // (2,N): two coalesced row reads per view
+    u1 = __ldg(x1 + i); v1 = __ldg(x1 + n + i);
+    u2 = __ldg(x2 + i); v2 = __ldg(x2 + n + i);
+  } else {                 // (N,2): one 8-byte read per view
+    float2 a = __ldg(reinterpret_cast<const float2*>(x1) + i);
+    float2 b = __ldg(reinterpret_cast<const float2*>(x2) + i);
+    u1 = a.x; v1 = a.y; u2 = b.x; v2 = b.y;
+  }
+  // At[k][r] = A[r][k];  A rows: x*P[2]-P[0], y*P[2]-P[1] for view 1 then view 2
+  double At[4][4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    At[k][0] = (double)u1 * pp.P1[8 + k] - pp.P1[k];
+    At[k][1] = (double)v1 * pp.P1[8 + k] - pp.P1[4 + k];
+    At[k][2] = (double)u2 * pp.P2[8 + k] - pp.P2[k];
+    At[k][3] = (double)v2 * pp.P2[8 + k] - pp.P2[4 + k];
+  }
+  double v[4];
+  dlt_null_vector(At, v);
+  float f0 = (float)v[0], f1 = (float)v[1], f2 = (float)v[2], f3 = (float)v[3];
+  if (normalize_w || OUT_LAYOUT == 2) {   // `cloud / cloud[3]` on the float32 array (sfm.py:54)
+    f0 = __fdiv_rn(f0, f3); f1 = __fdiv_rn(f1, f3); f2 = __fdiv_rn(f2, f3); f3 = __fdiv_rn(f3, f3);
+  }
+  if (OUT_LAYOUT == 0) {
+    X[i] = f0; X[n + i] = f1; X[2 * (size_t)n + i] = f2; X[3 * (size_t)n + i] = f3;
+  } else if (OUT_LAYOUT == 1) {
+    reinterpret_cast<float4*>(X)[i] = make_float4(f0, f1, f2, f3);
+  } else {
+    X[3 * (size_t)i] = f0; X[3 * (size_t)i + 1] = f1; X[3 * (size_t)i + 2] = f2;
+  }
+}
+
+extern "C" int sfm_triangulate(sfm_ctx* ctx, const double* P1, const double* P2, const float* x1,
+                               const float* x2, int n, int pts_layout, float* X, int out_layout,
+                               int normalize_w) {
+  SFM_REQUIRE(ctx && P1 && P2, "sfm_triangulate: null ctx or projection matrix");
+  SFM_REQUIRE(n >= 1, "sfm_triangulate: number of points must be >= 1 (cv2 raises for N=0)");
+  SFM_REQUIRE(x1 && x2 && X, "sfm_triangulate: null point buffer");
+  SFM_REQUIRE(pts_layout == 0 || pts_layout == 1, "sfm_triangulate: pts_layout %d", pts_layout);
+  SFM_REQUIRE(out_layout >= 0 && out_layout <= 2, "sfm_triangulate: out_layout %d", out_layout);
+  SFM_TRY(sfm_ws_begin(ctx));
+  ProjPair pp;
+  memcpy(pp.P1, P1, sizeof(pp.P1));
+  memcpy(pp.P2, P2, sizeof(pp.P2));
+  const float *d1, *d2;
+  SFM_TRY(dev_in(ctx, x1, (size_t)2 * n, &d1));
+  SFM_TRY(dev_in(ctx, x2, (size_t)2 * n, &d2));
+  bool host_out = false;
+  DevOut<float> o;
+  SFM_TRY(dev_out(ctx, X, (size_t)(out_layout == 2 ? 3 : 4) * n, &o, &host_out));
+  dim3 grid(div_up(n, 128)), block(128);
+#define TRI_CASE(PL, OL)                                                                       \
+  if (pts_layout == PL && out_layout == OL)                                                    \
+    SFM_LAUNCH(ctx, SFM_K_TRIANGULATE, (triangulate_kernel<PL, OL><<<grid, block, 0, ctx->stream>>>( \
+                                            pp, d1, d2, n, o.dev, normalize_w)))
+  TRI_CASE(0, 0); TRI_CASE(0, 1); TRI_CASE(0, 2);
+  TRI_CASE(1, 0); TRI_CASE(1, 1); TRI_CASE(1, 2);
+#undef TRI_CASE
+  SFM_TRY(dev_out_finish(ctx, &o));
+  if (host_out) SFM_CUDA(cudaStreamSynchronize(ctx->stream));
+  return SFM_OK;
+}
+
+// ============================================================================ K3 reprojection
+struct CamParams {
+  double R[9];
+  double t[3];
+  double fx, fy, cx, cy;
+};
+
+// cv2.projectPoints with zero distortion, operation for operation (separately rounded products
+// and sums, no FMA contraction) so that the float32-rounded pixel equals OpenCV's.
+__device__ __forceinline__ void project_cv(const CamParams& c, double X, double Y, double Z,
+                                           double& u, double& v) {
+  double x = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(c.R[0], X), __dmul_rn(c.R[1], Y)), __dmul_rn(c.R[2], Z)), c.t[0]);
+  double y = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(c.R[3], X), __dmul_rn(c.R[4], Y)), __dmul_rn(c.R[5], Z)), c.t[1]);
+  double z = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(c.R[6], X), __dmul_rn(c.R[7], Y)), __dmul_rn(c.R[8], Z)), c.t[2]);
+  z = (z != 0.0) ? __ddiv_rn(1.0, z) : 1.0;
+  x = __dmul_rn(x, z);
+  y = __dmul_rn(y, z);
+  u = __dadd_rn(__dmul_rn(x, c.fx), c.cx);
+  v = __dadd_rn(__dmul_rn(y, c.fy), c.cy);
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Block sum with a fixed reduction tree -> deterministic result for a given grid.
+__device__ __forceinline__ double block_sum_256(double v, double* sh) {
+  v = warp_sum(v);
+  int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) sh[w] = v;
+  __syncthreads();
+  double r = 0.0;
+  if (w == 0) {
+    r = (l < (blockDim.x >> 5)) ? sh[l] : 0.0;
+    r = warp_sum(r);
+  }
+  return r;   // valid in warp 0
+}
+
+template <int X_LAYOUT, int PX_LAYOUT>
+__global__ void __launch_bounds__(256) reproj_kernel(CamParams cam, const float* __restrict__ X,
+                                                      const float* __restrict__ px, int n,
+                                                      float* __restrict__ proj, float* __restrict__ X3,
+                                                      double* __restrict__ partial,
+                                                      unsigned int* __restrict__ counter,
+                                                      double* __restrict__ err_out) {
+  __shared__ double sh[8];
+  __shared__ bool is_last;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double sq = 0.0;
+  if (i < n) {
+    float x, y, z;
+    if (X_LAYOUT == 0) {
+      x = __ldg(X + 3 * (size_t)i); y = __ldg(X + 3 * (size_t)i + 1); z = __ldg(X + 3 * (size_t)i + 2);
+    } else {
+      float w;
+      if (X_LAYOUT == 1) {
+        x = __ldg(X + i); y = __ldg(X + n + i); z = __ldg(X + 2 * (size_t)n + i); w = __ldg(X + 3 * (size_t)n + i);
+      } else {
+        float4 q = __ldg(reinterpret_cast<const float4*>(X) + i);
+        x = q.x; y = q.y; z = q.z; w = q.w;
+      }
+      // cv2.convertPointsFromHomogeneous on float32: scale = w != 0 ? 1/w : 1
+      float s = (w != 0.f) ? __fdiv_rn(1.f, w) : 1.f;
+      x = __fmul_rn(x, s); y = __fmul_rn(y, s); z = __fmul_rn(z, s);
+    }
+    if (X3) { X3[3 * (size_t)i] = x; X3[3 * (size_t)i + 1] = y; X3[3 * (size_t)i + 2] = z; }
+    double u, v;
+    project_cv(cam, (double)x, (double)y, (double)z, u, v);
+    float pu = (float)u, pv = (float)v;     // projectPoints output dtype = input dtype (f32)
+    if (proj) reinterpret_cast<float2*>(proj)[i] = make_float2(pu, pv);
+    float ox, oy;
+    if (PX_LAYOUT == 0) { ox = __ldg(px + i); oy = __ldg(px + n + i); }
+    else { float2 o = __ldg(reinterpret_cast<const float2*>(px) + i); ox = o.x; oy = o.y; }
+    // cv2.norm(NORM_L2) on float32 arrays: float32 differences, float64 accumulation
+    double dx = (double)__fsub_rn(pu, ox), dy = (double)__fsub_rn(pv, oy);
+    sq = dx * dx + dy * dy;
+  }
+  double bs = block_sum_256(sq, sh);
+  if (threadIdx.x == 0) {
+    partial[blockIdx.x] = bs;
+    __threadfence();
+    unsigned int ticket = atomicAdd(counter, 1u);
+    is_last = (ticket == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    double s = 0.0;
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) s += partial[b];
+    __syncthreads();
+    s = block_sum_256(s, sh);
+    if (threadIdx.x == 0) {
+      *err_out = sqrt(s) / (double)n;
+      *counter = 0u;
+    }
+  }
+}
+
+static int make_cam(const double* Rt, const double* K, bool roundtrip, CamParams* cam) {
+  double R[9] = {Rt[0], Rt[1], Rt[2], Rt[4], Rt[5], Rt[6], Rt[8], Rt[9], Rt[10]};
+  if (roundtrip) {   // the reference goes R -> Rodrigues -> rvec -> projectPoints -> R' (sfm.py:84,88)
+    double rv[3];
+    hm::rodrigues_to_vector(R, rv);
+    hm::rodrigues_to_matrix(rv, cam->R);
+  } else {
+    memcpy(cam->R, R, sizeof(R));
+  }
+  cam->t[0] = Rt[3]; cam->t[1] = Rt[7]; cam->t[2] = Rt[11];
+  cam->fx = K[0]; cam->fy = K[4]; cam->cx = K[2]; cam->cy = K[5];
+  return SFM_OK;
+}
+
+extern "C" int sfm_reproj_error(sfm_ctx* ctx, const float* X, int x_layout, const float* px,
+                                int px_layout, int n, const double* Rt, const double* K,
+                                double* err, float* proj, float* X3) {
+  SFM_REQUIRE(ctx && X && px && Rt && K, "sfm_reproj_error: null argument");
+  SFM_REQUIRE(n >= 1, "sfm_reproj_error: need at least one point");
+  SFM_REQUIRE(x_layout >= 0 && x_layout <= 2 && (px_layout == 0 || px_layout == 1),
+              "sfm_reproj_error: bad layout (%d,%d)", x_layout, px_layout);
+  SFM_TRY(sfm_ws_begin(ctx));
+  CamParams cam;
+  make_cam(Rt, K, true, &cam);
+  const float *dX, *dpx;
+  SFM_TRY(dev_in(ctx, X, (size_t)(x_layout == 0 ? 3 : 4) * n, &dX));
+  SFM_TRY(dev_in(ctx, px, (size_t)2 * n, &dpx));
+  bool host_out = false;
+  DevOut<float> oproj, oX3;
+  DevOut<double> oerr;
+  SFM_TRY(dev_out(ctx, proj, (size_t)2 * n, &oproj, &host_out));
+  SFM_TRY(dev_out(ctx, X3, (size_t)3 * n, &oX3, &host_out));
+  SFM_TRY(dev_out(ctx, err, 1, &oerr, &host_out));
+  double* err_dev = oerr.dev ? oerr.dev : ctx->dscratch;
+  int nblk = div_up(n, 256);
+  double* partial;
+  SFM_TRY(ws_alloc_t(ctx, (size_t)nblk, &partial));
+#define RP_CASE(XL, PL)                                                                            \
+  if (x_layout == XL && px_layout == PL)                                                           \
+    SFM_LAUNCH(ctx, SFM_K_REPROJ, (reproj_kernel<XL, PL><<<nblk, 256, 0, ctx->stream>>>(           \
+                                       cam, dX, dpx, n, oproj.dev, oX3.dev, partial, ctx->counters, err_dev)))
+  RP_CASE(0, 0); RP_CASE(0, 1); RP_CASE(1, 0); RP_CASE(1, 1); RP_CASE(2, 0); RP_CASE(2, 1);
+#undef RP_CASE
+  SFM_TRY(dev_out_finish(ctx, &oproj));
+  SFM_TRY(dev_out_finish(ctx, &oX3));
+  SFM_TRY(dev_out_finish(ctx, &oerr));
+  if (host_out) SFM_CUDA(cudaStreamSynchronize(ctx->stream));
+  return SFM_OK;
+}
+
+// ============================================================================ common_points
+// One warp per row of pts1 scans pts2 in ascending order, 32 rows at a time, and stops at the
+// first 32-row window containing a hit: `np.where(pts2 == pts1[i])[0][0]` (sfm.py:221-226).
+__global__ void __launch_bounds__(256) first_hit_kernel(const float2* __restrict__ p1, int n1,
+                                                         const float2* __restrict__ p2, int n2,
+                                                         int* __restrict__ hit,
+                                                         unsigned char* __restrict__ keep2) {
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (warp >= n1) return;
+  float2 a = __ldg(p1 + warp);
+  int found = -1;
+  for (int base = 0; base < n2; base += 32) {
+    int j = base + lane;
+    bool h = false;
+    if (j < n2) {
+      float2 b = __ldg(p2 + j);
+      h = (b.x == a.x) || (b.y == a.y);
+    }
+    unsigned m = __ballot_sync(0xffffffffu, h);
+    if (m) { found = base + __ffs(m) - 1; break; }
+  }
+  if (lane == 0) {
+    hit[warp] = found;
+    if (found >= 0 && keep2) keep2[found] = 0;
+  }
+}
+
+// Stable single-CTA compaction of (i, hit[i]) for hit[i] >= 0.
+__global__ void __launch_bounds__(1024) compact_hits_kernel(const int* __restrict__ hit, int n,
+                                                             int* __restrict__ idx1, int* __restrict__ idx2,
+                                                             int* __restrict__ n_out) {
+  __shared__ int warp_tot[32];
+  __shared__ int base_s;
+  if (threadIdx.x == 0) base_s = 0;
+  __syncthreads();
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int start = 0; start < n; start += 1024) {
+    int i = start + threadIdx.x;
+    int h = (i < n) ? hit[i] : -1;
+    bool f = h >= 0;
+    unsigned m = __ballot_sync(0xffffffffu, f);
+    int pre = __popc(m & ((1u << lane) - 1u));
+    if (lane == 0) warp_tot[w] = __popc(m);
+    __syncthreads();
+    int off = 0;
+    for (int k = 0; k < w; ++k) off += warp_tot[k];
+    int base = base_s;
+    if (f) {
+      int pos = base + off + pre;
+      if (idx1) idx1[pos] = i;
+      if (idx2) idx2[pos] = h;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int tot = 0;
+      for (int k = 0; k < 32; ++k) tot += warp_tot[k];
+      base_s = base + tot;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && n_out) *n_out = base_s;
+}
+
+extern "C" int sfm_common_points(sfm_ctx* ctx, const float* pts1, int n1, const float* pts2, int n2,
+                                 int32_t* idx1, int32_t* idx2, int32_t* n_common, uint8_t* keep2) {
+  SFM_REQUIRE(ctx, "sfm_common_points: null ctx");
+  SFM_REQUIRE(n1 >= 0 && n2 >= 0, "sfm_common_points: negative size");
+  SFM_TRY(sfm_ws_begin(ctx));
+  const float *d1, *d2;
+  SFM_TRY(dev_in(ctx, pts1, (size_t)2 * n1, &d1));
+  SFM_TRY(dev_in(ctx, pts2, (size_t)2 * n2, &d2));
+  bool host_out = false;
+  DevOut<int32_t> o1, o2, on;
+  DevOut<uint8_t> ok;
+  SFM_TRY(dev_out(ctx, idx1, (size_t)n1, &o1, &host_out));
+  SFM_TRY(dev_out(ctx, idx2, (size_t)n1, &o2, &host_out));
+  SFM_TRY(dev_out(ctx, n_common, 1, &on, &host_out));
+  SFM_TRY(dev_out(ctx, keep2, (size_t)n2, &ok, &host_out));
+  int* hit = nullptr;
+  SFM_TRY(ws_alloc_t(ctx, (size_t)(n1 > 0 ? n1 : 1), &hit));
+  if (ok.dev && n2 > 0) SFM_CUDA(cudaMemsetAsync(ok.dev, 1, (size_t)n2, ctx->stream));
+  if (n1 > 0) {
+    SFM_LAUNCH(ctx, SFM_K_ASSOC, (first_hit_kernel<<<div_up(n1 * 32, 256), 256, 0, ctx->stream>>>(
+                                     (const float2*)d1, n1, (const float2*)d2, n2, hit, ok.dev)));
+  }
+  SFM_LAUNCH(ctx, SFM_K_ASSOC, (compact_hits_kernel<<<1, 1024, 0, ctx->stream>>>(hit, n1, o1.dev, o2.dev, on.dev)));
+  SFM_TRY(dev_out_finish(ctx, &o1));
+  SFM_TRY(dev_out_finish(ctx, &o2));
+  SFM_TRY(dev_out_finish(ctx, &on));
+  SFM_TRY(dev_out_finish(ctx, &ok));
+  if (host_out) SFM_CUDA(cudaStreamSynchronize(ctx->stream));
+  return SFM_OK;
+}
+
+// ============================================================================ host utilities
+extern "C" int sfm_rodrigues_to_matrix(const double* rvec, double* R9) {
+  SFM_REQUIRE(rvec && R9, "sfm_rodrigues_to_matrix: null argument");
+  hm::rodrigues_to_matrix(rvec, R9);
+  return SFM_OK;
+}
+extern "C" int sfm_rodrigues_to_vector(const double* R9, double* rvec) {
+  SFM_REQUIRE(rvec && R9, "sfm_rodrigues_to_vector: null argument");
+  hm::rodrigues_to_vector(R9, rvec);
+  return SFM_OK;
+}

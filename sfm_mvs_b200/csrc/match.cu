@@ -1,0 +1,290 @@
+// match.cu — hot path 1 API: descriptor residency, kernel selection, K1c finalisation (cross-split
+// merge + sqrt + Lowe ratio + count) and survivor gather.
+//
+// Reference: bf.knnMatch(des0, des1, k=2) sfm.py:259-260 / isfm.py:71 / test.py:42,225,352;
+//            ratio loop sfm.py:262-265; coordinate gather sfm.py:267-268.
+#include <math.h>
+
+#include "match_common.cuh"
+
+// ------------------------------------------------------------------ K1c finalise
+// One thread per query: merge nsplit x 2 candidate keys, emit idx/dist/good.
+// dist = float32(sqrt(d2)) (correctly rounded, like OpenCV's std::sqrt on the float32 sum);
+// the Lowe test is evaluated as Python does it: float32 distances widened to double,
+// d1 < ratio*d2 in double, strict (sfm.py:264).
+__global__ void __launch_bounds__(256) match_finalize_kernel(const mkey_t* __restrict__ cand, int nq,
+                                                              int nt, int nsplit, double ratio,
+                                                              int* __restrict__ idx, float* __restrict__ dist,
+                                                              unsigned char* __restrict__ good,
+                                                              int* __restrict__ n_good) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  bool g = false;
+  if (i < nq) {
+    mkey_t k1 = MKEY_INF, k2 = MKEY_INF;
+    const mkey_t* c = cand + (size_t)i * nsplit * 2;
+    for (int s = 0; s < 2 * nsplit; ++s) key_insert(c[s], k1, k2);
+    int i1 = (int)(unsigned int)(k1 & 0xFFFFFFFFull), i2 = (int)(unsigned int)(k2 & 0xFFFFFFFFull);
+    bool v1 = (k1 != MKEY_INF) && i1 < nt, v2 = (k2 != MKEY_INF) && i2 < nt;
+    float d1 = v1 ? __fsqrt_rn(__uint_as_float((unsigned int)(k1 >> 32))) : __int_as_float(0x7f800000);
+    float d2 = v2 ? __fsqrt_rn(__uint_as_float((unsigned int)(k2 >> 32))) : __int_as_float(0x7f800000);
+    if (idx) { idx[2 * i] = v1 ? i1 : -1; idx[2 * i + 1] = v2 ? i2 : -1; }
+    if (dist) { dist[2 * i] = d1; dist[2 * i + 1] = d2; }
+    g = v1 && v2 && ((double)d1 < ratio * (double)d2);
+    if (good) good[i] = g ? 1 : 0;
+  }
+  if (n_good) {
+    unsigned m = __ballot_sync(0xffffffffu, g);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(n_good, __popc(m));
+  }
+}
+
+int sfm_match_finalize(sfm_ctx* ctx, const mkey_t* cand, int nq, int nt, int nsplit, double ratio,
+                       int32_t* idx, float* dist, uint8_t* good, int32_t* n_good) {
+  if (n_good) SFM_CUDA(cudaMemsetAsync(n_good, 0, sizeof(int32_t), ctx->stream));
+  if (nq == 0) return SFM_OK;
+  SFM_LAUNCH(ctx, SFM_K_MATCH_FINAL, (match_finalize_kernel<<<div_up(nq, 256), 256, 0, ctx->stream>>>(
+                                         cand, nq, nt, nsplit, ratio, idx, dist, good, n_good)));
+  return SFM_OK;
+}
+
+// ------------------------------------------------------------------ descriptors
+// Copies / converts the descriptors to a float32 row-major resident copy and raises `flag` when
+// a value is not an integer in [0,255] (then only the fp32 kernel may be used).
+template <typename T>
+__global__ void __launch_bounds__(256) desc_ingest_kernel(const T* __restrict__ src, size_t count,
+                                                           float* __restrict__ dst,
+                                                           unsigned int* __restrict__ flag) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  bool bad = false;
+  for (; i < count; i += stride) {
+    float v = (float)src[i];
+    dst[i] = v;
+    bad |= !(v >= 0.f && v <= 255.f && v == rintf(v));
+  }
+  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1u);
+}
+
+extern "C" int sfm_desc_create(sfm_ctx* ctx, const void* data, int dtype, int n, int dim, sfm_desc** out) {
+  SFM_REQUIRE(ctx && out, "sfm_desc_create: null argument");
+  SFM_REQUIRE(dtype == 0 || dtype == 1, "sfm_desc_create: dtype must be 0 (float32) or 1 (uint8); cv2 rejects others too");
+  SFM_REQUIRE(n >= 0 && dim > 0, "sfm_desc_create: bad shape (%d,%d)", n, dim);
+  SFM_REQUIRE(n == 0 || data, "sfm_desc_create: null data");
+  SFM_TRY(sfm_ws_begin(ctx));
+  sfm_desc* d = new sfm_desc();
+  d->ctx = ctx; d->n = n; d->dim = dim;
+  size_t count = (size_t)n * dim;
+  cudaError_t e = cudaMalloc(&d->f32, (count ? count : 1) * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&d->flag, sizeof(unsigned int));
+  if (e != cudaSuccess) {
+    sfm_set_error("sfm_desc_create: cudaMalloc failed: %s", cudaGetErrorString(e));
+    sfm_desc_destroy(d);
+    return SFM_ERR_NOMEM;
+  }
+  int s = SFM_OK;
+  do {
+    if ((s = (cudaMemsetAsync(d->flag, 0, sizeof(unsigned int), ctx->stream) == cudaSuccess) ? SFM_OK : SFM_ERR_CUDA)) break;
+    if (count) {
+      int grid = (int)((count + 255) / 256);
+      if (grid > ctx->sm_count * 8) grid = ctx->sm_count * 8;
+      if (dtype == 0) {
+        const float* src;
+        if ((s = dev_in(ctx, (const float*)data, count, &src))) break;
+        s = [&]() -> int { SFM_LAUNCH(ctx, SFM_K_DESC_PREP, (desc_ingest_kernel<float><<<grid, 256, 0, ctx->stream>>>(src, count, d->f32, d->flag))); return SFM_OK; }();
+      } else {
+        const uint8_t* src;
+        if ((s = dev_in(ctx, (const uint8_t*)data, count, &src))) break;
+        s = [&]() -> int { SFM_LAUNCH(ctx, SFM_K_DESC_PREP, (desc_ingest_kernel<uint8_t><<<grid, 256, 0, ctx->stream>>>(src, count, d->f32, d->flag))); return SFM_OK; }();
+      }
+      if (s) break;
+    }
+    unsigned int hflag = 0;
+    if (cudaMemcpyAsync(&hflag, d->flag, sizeof(hflag), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+        cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+      sfm_set_error("sfm_desc_create: %s", cudaGetErrorString(cudaGetLastError()));
+      s = SFM_ERR_CUDA;
+      break;
+    }
+    d->exact = (hflag == 0);
+    if (d->exact && dim == 128 && n > 0) s = sfm_desc_prepare_tiles(ctx, d);
+  } while (0);
+  if (s != SFM_OK) { sfm_desc_destroy(d); return s; }
+  *out = d;
+  return SFM_OK;
+}
+
+extern "C" void sfm_desc_destroy(sfm_desc* d) {
+  if (!d) return;
+  if (d->ctx) { cudaSetDevice(d->ctx->device); cudaStreamSynchronize(d->ctx->stream); }
+  if (d->f32) cudaFree(d->f32);
+  if (d->tiles) cudaFree(d->tiles);
+  if (d->sqnorm) cudaFree(d->sqnorm);
+  if (d->flag) cudaFree(d->flag);
+  delete d;
+}
+extern "C" int sfm_desc_rows(const sfm_desc* d) { return d ? d->n : 0; }
+extern "C" int sfm_desc_is_exact(const sfm_desc* d) { return d && d->exact ? 1 : 0; }
+
+// ------------------------------------------------------------------ one pair
+static int match_pair(sfm_ctx* ctx, const sfm_desc* q, const sfm_desc* t, double ratio, int mode,
+                      int32_t* idx, float* dist, uint8_t* good, int32_t* n_good) {
+  SFM_REQUIRE(q->dim == t->dim, "knnMatch: descriptor dims differ (%d vs %d)", q->dim, t->dim);
+  const int nq = q->n, nt = t->n;
+  bool tc_ok = q->exact && t->exact && q->tiles && t->tiles;
+  SFM_REQUIRE(mode != 2 || tc_ok || nq == 0 || nt == 0,
+              "tensor-core matcher requested but descriptors are not integer-valued in [0,255] with dim 128");
+  bool use_tc = (mode == 2) || (mode == 0 && tc_ok);
+  bool host_out = false;
+  DevOut<int32_t> oidx, ong;
+  DevOut<float> odist;
+  DevOut<uint8_t> ogood;
+  SFM_TRY(dev_out(ctx, idx, (size_t)2 * nq, &oidx, &host_out));
+  SFM_TRY(dev_out(ctx, dist, (size_t)2 * nq, &odist, &host_out));
+  SFM_TRY(dev_out(ctx, good, (size_t)nq, &ogood, &host_out));
+  SFM_TRY(dev_out(ctx, n_good, 1, &ong, &host_out));
+  if (nq > 0) {
+    int nsplit = 1;
+    mkey_t* cand = nullptr;
+    if (nt == 0) {
+      SFM_TRY(ws_alloc_t(ctx, (size_t)nq * 2, &cand));
+      SFM_CUDA(cudaMemsetAsync(cand, 0xFF, (size_t)nq * 2 * sizeof(mkey_t), ctx->stream));
+    } else if (use_tc) {
+      nsplit = sfm_match_tc_splits(ctx, nq, nt);
+      SFM_TRY(ws_alloc_t(ctx, (size_t)q->n_tiles * 128 * nsplit * 2, &cand));
+      SFM_TRY(sfm_match_tc_launch(ctx, q, t, cand, nsplit));
+    } else {
+      nsplit = sfm_match_exact_splits(ctx, nq, nt);
+      SFM_TRY(ws_alloc_t(ctx, (size_t)nq * nsplit * 2, &cand));
+      SFM_TRY(sfm_match_exact_launch(ctx, q->f32, nq, t->f32, nt, q->dim, cand, nsplit));
+    }
+    SFM_TRY(sfm_match_finalize(ctx, cand, nq, nt, nsplit, ratio, oidx.dev, odist.dev, ogood.dev, ong.dev));
+  } else if (ong.dev) {
+    SFM_CUDA(cudaMemsetAsync(ong.dev, 0, sizeof(int32_t), ctx->stream));
+  }
+  SFM_TRY(dev_out_finish(ctx, &oidx));
+  SFM_TRY(dev_out_finish(ctx, &odist));
+  SFM_TRY(dev_out_finish(ctx, &ogood));
+  SFM_TRY(dev_out_finish(ctx, &ong));
+  if (host_out) SFM_CUDA(cudaStreamSynchronize(ctx->stream));
+  return SFM_OK;
+}
+
+extern "C" int sfm_desc_match(sfm_ctx* ctx, const sfm_desc* q, const sfm_desc* t, double ratio,
+                              int32_t* idx, float* dist, uint8_t* good, int32_t* n_good, int mode) {
+  SFM_REQUIRE(ctx && q && t, "sfm_desc_match: null argument");
+  SFM_REQUIRE(mode >= 0 && mode <= 2, "sfm_desc_match: mode %d", mode);
+  SFM_TRY(sfm_ws_begin(ctx));
+  return match_pair(ctx, q, t, ratio, mode, idx, dist, good, n_good);
+}
+
+extern "C" int sfm_desc_match_batched(sfm_ctx* ctx, int npairs, const sfm_desc* const* q, const sfm_desc* const* t,
+                                      double ratio, int32_t* const* idx, float* const* dist, uint8_t* const* good,
+                                      int32_t* n_good) {
+  SFM_REQUIRE(ctx && npairs >= 0 && (npairs == 0 || (q && t)), "sfm_desc_match_batched: null argument");
+  SFM_TRY(sfm_ws_begin(ctx));
+  // All pairs are enqueued back to back on the ctx stream (each launch is itself persistent over the
+  // SMs); outputs are device pointers, so nothing synchronises until the caller does.
+  const bool ng_dev = n_good && sfm_is_device_ptr(n_good);
+  int32_t* ng_stage = nullptr;
+  if (n_good && !ng_dev && npairs) SFM_TRY(ws_alloc_t(ctx, (size_t)npairs, &ng_stage));
+  for (int p = 0; p < npairs; ++p) {
+    SFM_REQUIRE(q[p] && t[p], "sfm_desc_match_batched: pair %d has a null descriptor set", p);
+    int32_t* pi = idx ? idx[p] : nullptr;
+    float* pd = dist ? dist[p] : nullptr;
+    uint8_t* pg = good ? good[p] : nullptr;
+    SFM_REQUIRE((!pi || sfm_is_device_ptr(pi)) && (!pd || sfm_is_device_ptr(pd)) && (!pg || sfm_is_device_ptr(pg)),
+                "sfm_desc_match_batched: per-pair outputs must be device pointers");
+    int32_t* png = n_good ? (ng_dev ? n_good + p : ng_stage + p) : nullptr;
+    SFM_TRY(match_pair(ctx, q[p], t[p], ratio, 0, pi, pd, pg, png));
+  }
+  if (ng_stage) {
+    SFM_CUDA(cudaMemcpyAsync(n_good, ng_stage, sizeof(int32_t) * npairs, cudaMemcpyDeviceToHost, ctx->stream));
+    SFM_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  return SFM_OK;
+}
+
+extern "C" int sfm_knn2_l2_ratio(sfm_ctx* ctx, const float* q, int nq, const float* t, int nt, int dim,
+                                 double ratio, int32_t* idx, float* dist, uint8_t* good,
+                                 int32_t* n_good, int mode) {
+  SFM_REQUIRE(ctx, "sfm_knn2_l2_ratio: null ctx");
+  SFM_REQUIRE(mode >= 0 && mode <= 2, "sfm_knn2_l2_ratio: mode %d", mode);
+  SFM_REQUIRE(nq >= 0 && nt >= 0 && dim > 0, "sfm_knn2_l2_ratio: bad shape");
+  sfm_desc *dq = nullptr, *dt = nullptr;
+  int s = sfm_desc_create(ctx, q, 0, nq, dim, &dq);
+  if (s == SFM_OK) s = sfm_desc_create(ctx, t, 0, nt, dim, &dt);
+  if (s == SFM_OK) s = sfm_desc_match(ctx, dq, dt, ratio, idx, dist, good, n_good, mode);
+  sfm_desc_destroy(dq);
+  sfm_desc_destroy(dt);
+  return s;
+}
+
+// ------------------------------------------------------------------ survivor gather
+// Stable single-CTA compaction (ascending queryIdx, like the Python loop's append order).
+__global__ void __launch_bounds__(1024) match_gather_kernel(const int* __restrict__ idx,
+                                                             const unsigned char* __restrict__ good, int nq,
+                                                             const float2* __restrict__ kp_q,
+                                                             const float2* __restrict__ kp_t,
+                                                             float2* __restrict__ pts_q, float2* __restrict__ pts_t,
+                                                             int* __restrict__ qidx, int* __restrict__ tidx,
+                                                             int* __restrict__ n_out) {
+  __shared__ int warp_tot[32];
+  __shared__ int base_s;
+  if (threadIdx.x == 0) base_s = 0;
+  __syncthreads();
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int start = 0; start < nq; start += 1024) {
+    int i = start + threadIdx.x;
+    bool f = (i < nq) && good[i];
+    unsigned m = __ballot_sync(0xffffffffu, f);
+    int pre = __popc(m & ((1u << lane) - 1u));
+    if (lane == 0) warp_tot[w] = __popc(m);
+    __syncthreads();
+    int off = 0;
+    for (int k = 0; k < w; ++k) off += warp_tot[k];
+    int base = base_s;
+    if (f) {
+      int pos = base + off + pre;
+      int tj = idx[2 * i];
+      if (pts_q) pts_q[pos] = kp_q[i];
+      if (pts_t) pts_t[pos] = kp_t[tj];
+      if (qidx) qidx[pos] = i;
+      if (tidx) tidx[pos] = tj;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int tot = 0;
+      for (int k = 0; k < 32; ++k) tot += warp_tot[k];
+      base_s = base + tot;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && n_out) *n_out = base_s;
+}
+
+extern "C" int sfm_match_gather(sfm_ctx* ctx, const int32_t* idx, const uint8_t* good, int nq,
+                                const float* kp_q, const float* kp_t, float* pts_q, float* pts_t,
+                                int32_t* qidx_out, int32_t* tidx_out, int32_t* n_out) {
+  SFM_REQUIRE(ctx && (nq == 0 || (idx && good)), "sfm_match_gather: null argument");
+  SFM_REQUIRE((!pts_q || kp_q) && (!pts_t || kp_t), "sfm_match_gather: keypoints missing");
+  SFM_REQUIRE(sfm_is_device_ptr(idx) || nq == 0, "sfm_match_gather: idx/good/kp must be device pointers");
+  SFM_TRY(sfm_ws_begin(ctx));
+  bool host_out = false;
+  DevOut<float> oq, ot;
+  DevOut<int32_t> oqi, oti, on;
+  SFM_TRY(dev_out(ctx, pts_q, (size_t)2 * nq, &oq, &host_out));
+  SFM_TRY(dev_out(ctx, pts_t, (size_t)2 * nq, &ot, &host_out));
+  SFM_TRY(dev_out(ctx, qidx_out, (size_t)nq, &oqi, &host_out));
+  SFM_TRY(dev_out(ctx, tidx_out, (size_t)nq, &oti, &host_out));
+  SFM_TRY(dev_out(ctx, n_out, 1, &on, &host_out));
+  SFM_LAUNCH(ctx, SFM_K_GATHER, (match_gather_kernel<<<1, 1024, 0, ctx->stream>>>(
+                                    idx, good, nq, (const float2*)kp_q, (const float2*)kp_t, (float2*)oq.dev,
+                                    (float2*)ot.dev, oqi.dev, oti.dev, on.dev)));
+  SFM_TRY(dev_out_finish(ctx, &oq));
+  SFM_TRY(dev_out_finish(ctx, &ot));
+  SFM_TRY(dev_out_finish(ctx, &oqi));
+  SFM_TRY(dev_out_finish(ctx, &oti));
+  SFM_TRY(dev_out_finish(ctx, &on));
+  if (host_out) SFM_CUDA(cudaStreamSynchronize(ctx->stream));
+  return SFM_OK;
+}

@@ -1,0 +1,606 @@
+// pnp.cu — hot path 3a: PnP-RANSAC (K4 hypothesis scoring, minimal solver, replay, refinement).
+//
+// Replaces cv2.solvePnPRansac(X, p, K, d, cv2.SOLVEPNP_ITERATIVE) as the reference calls it
+// (sfm.py:67, test.py:319; the 5th positional binds to `rvec`, so OpenCV's defaults apply:
+// 100 iterations, reprojection threshold 8 px, confidence 0.99, 5-point EPnP minimal solver,
+// Levenberg-Marquardt refinement on the inliers of the winning hypothesis).
+//
+// OpenCV's RANSAC loop is sequential only in its *stopping rule*: the subset drawn at iteration i
+// depends on nothing but N and i (RNG seeded with 2^64-1), and a hypothesis' score does not depend
+// on earlier hypotheses.  So the whole loop is evaluated as four stream-ordered kernels with no
+// host round trip in between:
+//   pnp_subsets_kernel   the RNG index stream (one thread, ~1.5k integer ops)
+//   pnp_epnp_kernel      H minimal problems, one per warp (float64 EPnP, epnp.h)
+//   pnp_score_kernel     K4: H x N reprojection tests, poses staged in shared memory, one point
+//                        per thread held in registers, ballot/popc warp counts
+//   pnp_replay_kernel    the accept / RANSACUpdateNumIters recursion over the count vector; then
+//                        the winner's inlier list (stable compaction) and the LM refinement
+//                        (pnp_refine_kernel, one CTA, normal equations by block reduction)
+// and a single device->host copy of (rvec, tvec, inliers, info) at the end.
+#include <float.h>
+#include <math.h>
+
+#include "common.cuh"
+#include "epnp.h"
+
+namespace {
+
+struct PnpCam {
+  double fx, fy, cx, cy;
+};
+
+constexpr int PNP_HG = 4;          // hypotheses per CTA of the scoring kernel
+constexpr int PNP_MAX_H = 1024;
+
+// cv2.projectPoints with zero distortion, operation for operation (see geometry.cu project_cv).
+__device__ __forceinline__ void project_pose(const double* __restrict__ P /*R row-major 9 | t 3*/, const PnpCam& c,
+                                             double X, double Y, double Z, double& u, double& v) {
+  double x = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(P[0], X), __dmul_rn(P[1], Y)), __dmul_rn(P[2], Z)), P[9]);
+  double y = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(P[3], X), __dmul_rn(P[4], Y)), __dmul_rn(P[5], Z)), P[10]);
+  double z = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(P[6], X), __dmul_rn(P[7], Y)), __dmul_rn(P[8], Z)), P[11]);
+  z = (z != 0.0) ? __ddiv_rn(1.0, z) : 1.0;
+  x = __dmul_rn(x, z);
+  y = __dmul_rn(y, z);
+  u = __dadd_rn(__dmul_rn(x, c.fx), c.cx);
+  v = __dadd_rn(__dmul_rn(y, c.fy), c.cy);
+}
+
+// PnPRansacCallback::computeError + findInliers: projection in float64 stored as float32,
+// err = dx*dx + dy*dy in float32 with separately rounded products, inlier iff err <= thr^2.
+__device__ __forceinline__ bool is_inlier(const double* __restrict__ P, const PnpCam& c, float X, float Y, float Z,
+                                          float ox, float oy, float thr2) {
+  double u, v;
+  project_pose(P, c, (double)X, (double)Y, (double)Z, u, v);
+  float dx = __fsub_rn(ox, (float)u), dy = __fsub_rn(oy, (float)v);
+  float e = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+  return e <= thr2;
+}
+
+// ------------------------------------------------------------------ K4 scoring
+// poses: (H, 12) doubles = R (9, row-major) then t (3).  counts must be zero on entry.
+__global__ void __launch_bounds__(256) pnp_score_kernel(const float* __restrict__ X, const float* __restrict__ px,
+                                                        int n, const double* __restrict__ poses,
+                                                        const unsigned char* __restrict__ valid, int H, PnpCam cam,
+                                                        float thr2, int* __restrict__ counts,
+                                                        unsigned char* __restrict__ masks) {
+  __shared__ double s_pose[PNP_HG][12];
+  __shared__ int s_count[PNP_HG];
+  __shared__ unsigned char s_valid[PNP_HG];
+  const int h0 = blockIdx.y * PNP_HG;
+  const int nh = min(PNP_HG, H - h0);
+  if (threadIdx.x < nh * 12) s_pose[threadIdx.x / 12][threadIdx.x % 12] = poses[(size_t)h0 * 12 + threadIdx.x];
+  if (threadIdx.x < PNP_HG) {
+    s_count[threadIdx.x] = 0;
+    s_valid[threadIdx.x] = (threadIdx.x < nh) && (!valid || valid[h0 + threadIdx.x]);
+  }
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  float x = 0.f, y = 0.f, z = 0.f, ox = 0.f, oy = 0.f;
+  if (i < n) {
+    x = __ldg(X + 3 * (size_t)i); y = __ldg(X + 3 * (size_t)i + 1); z = __ldg(X + 3 * (size_t)i + 2);
+    float2 o = __ldg(reinterpret_cast<const float2*>(px) + i);
+    ox = o.x; oy = o.y;
+  }
+  for (int h = 0; h < nh; ++h) {
+    bool in = (i < n) && s_valid[h] && is_inlier(s_pose[h], cam, x, y, z, ox, oy, thr2);
+    if (masks && i < n) masks[(size_t)(h0 + h) * n + i] = in ? 1 : 0;
+    unsigned m = __ballot_sync(0xffffffffu, in);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(&s_count[h], __popc(m));
+  }
+  __syncthreads();
+  if (threadIdx.x < nh && s_count[threadIdx.x]) atomicAdd(&counts[h0 + threadIdx.x], s_count[threadIdx.x]);
+}
+
+// ------------------------------------------------------------------ RNG subset stream
+// cv::RNG (multiply-with-carry, state 2^64-1) as RANSACPointSetRegistrator::getSubset uses it:
+// 5 distinct indices per iteration, redraw on duplicates.
+__host__ __device__ inline void ransac_subsets(int n, int iters, int* out) {
+  unsigned long long state = 0xFFFFFFFFFFFFFFFFull;
+  for (int it = 0; it < iters; ++it) {
+    int* s = out + 5 * it;
+    for (int i = 0; i < 5; ++i) {
+      for (;;) {
+        state = (state & 0xFFFFFFFFull) * 4164903690ull + (state >> 32);
+        int j = (int)((unsigned int)state % (unsigned int)n);
+        bool dup = false;
+        for (int k = 0; k < i; ++k) dup |= (s[k] == j);
+        if (!dup) { s[i] = j; break; }
+      }
+    }
+  }
+}
+
+__global__ void pnp_subsets_kernel(int n, int iters, int* __restrict__ out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) ransac_subsets(n, iters, out);
+}
+
+// ------------------------------------------------------------------ minimal solver
+// One warp per hypothesis (lane 0 runs the float64 solver; its working set lives in local
+// memory/L1 of an otherwise idle SM, so the H problems run fully in parallel across the chip).
+// Writes the pose the scoring step must use: R' = Rodrigues(Rodrigues(R)) as OpenCV passes the
+// model around as (rvec, tvec), and the (rvec, tvec) pair itself.
+__global__ void __launch_bounds__(32) pnp_epnp_kernel(const float* __restrict__ X, const float* __restrict__ px,
+                                                      const int* __restrict__ subsets, int H, PnpCam cam,
+                                                      double* __restrict__ poses, double* __restrict__ rt6,
+                                                      unsigned char* __restrict__ valid) {
+  const int h = blockIdx.x;
+  if (h >= H || threadIdx.x != 0) return;
+  hm::EpnpCam ec = {cam.fx, cam.fy, cam.cx, cam.cy};
+  double pw[15], us[10], work[35], R[9], t[3], rv[3];
+  for (int k = 0; k < 5; ++k) {
+    int j = subsets[5 * h + k];
+    pw[3 * k] = (double)X[3 * (size_t)j]; pw[3 * k + 1] = (double)X[3 * (size_t)j + 1]; pw[3 * k + 2] = (double)X[3 * (size_t)j + 2];
+    hm::epnp_roundtrip_pixel(px[2 * (size_t)j], px[2 * (size_t)j + 1], ec, us + 2 * k);
+  }
+  hm::epnp_solve(pw, us, 5, ec, work, R, t);
+  hm::rodrigues_to_vector(R, rv);
+  double* P = poses + 12 * (size_t)h;
+  hm::rodrigues_to_matrix(rv, P);
+  P[9] = t[0]; P[10] = t[1]; P[11] = t[2];
+  bool ok = true;
+  for (int k = 0; k < 12; ++k) ok &= isfinite(P[k]);
+  rt6[6 * h] = rv[0]; rt6[6 * h + 1] = rv[1]; rt6[6 * h + 2] = rv[2];
+  rt6[6 * h + 3] = t[0]; rt6[6 * h + 4] = t[1]; rt6[6 * h + 5] = t[2];
+  valid[h] = ok ? 1 : 0;
+}
+
+// ------------------------------------------------------------------ replay of the stopping rule
+struct PnpResult {          // device-resident, copied to the host once
+  double rvec[3], tvec[3];  // refined pose
+  double rvec0[3], tvec0[3];
+  int best_iter, iters_run, best_count, n_inliers, refine_iters, ok, pad0, pad1;
+};
+
+__device__ inline int update_num_iters(double p, double ep, int model_points, int max_iters) {
+  p = fmax(p, 0.0); p = fmin(p, 1.0);
+  ep = fmax(ep, 0.0); ep = fmin(ep, 1.0);
+  double num = fmax(1.0 - p, DBL_MIN);
+  double denom = 1.0 - pow(1.0 - ep, (double)model_points);
+  if (denom < DBL_MIN) return 0;
+  num = log(num);
+  denom = log(denom);
+  return (denom >= 0 || -num >= max_iters * (-denom)) ? max_iters : __double2int_rn(num / denom);
+}
+
+__global__ void pnp_replay_kernel(const int* __restrict__ counts, const unsigned char* __restrict__ valid, int n,
+                                  int max_iters, double conf, const double* __restrict__ rt6,
+                                  PnpResult* __restrict__ res) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  int niters = max_iters, best = 0, best_it = -1, it = 0;
+  while (it < niters) {
+    if ((!valid || valid[it]) && counts[it] > max(best, 4)) {
+      best = counts[it];
+      best_it = it;
+      niters = update_num_iters(conf, (double)(n - best) / n, 5, niters);
+    }
+    ++it;
+  }
+  res->best_iter = best_it;
+  res->iters_run = it;
+  res->best_count = best;
+  res->ok = best_it >= 0 ? 1 : 0;
+  res->n_inliers = 0;
+  res->refine_iters = 0;
+  for (int k = 0; k < 3; ++k) {
+    double r = best_it >= 0 ? rt6[6 * best_it + k] : 0.0, t = best_it >= 0 ? rt6[6 * best_it + 3 + k] : 0.0;
+    res->rvec0[k] = r; res->tvec0[k] = t; res->rvec[k] = r; res->tvec[k] = t;
+  }
+}
+
+// Winner's inliers, ascending (single CTA, stable compaction); the test is re-evaluated with the
+// same arithmetic as the scoring kernel, so no H x N mask matrix has to exist.
+__global__ void __launch_bounds__(1024) pnp_inliers_kernel(const float* __restrict__ X, const float* __restrict__ px,
+                                                           int n, const double* __restrict__ poses, PnpCam cam,
+                                                           float thr2, PnpResult* __restrict__ res,
+                                                           int* __restrict__ inliers) {
+  __shared__ int warp_tot[32];
+  __shared__ int base_s;
+  __shared__ double P[12];
+  const int best = res->best_iter;
+  if (best < 0) return;
+  if (threadIdx.x < 12) P[threadIdx.x] = poses[12 * (size_t)best + threadIdx.x];
+  if (threadIdx.x == 0) base_s = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int start = 0; start < n; start += 1024) {
+    int i = start + threadIdx.x;
+    bool f = false;
+    if (i < n) {
+      float2 o = __ldg(reinterpret_cast<const float2*>(px) + i);
+      f = is_inlier(P, cam, __ldg(X + 3 * (size_t)i), __ldg(X + 3 * (size_t)i + 1), __ldg(X + 3 * (size_t)i + 2), o.x, o.y, thr2);
+    }
+    unsigned m = __ballot_sync(0xffffffffu, f);
+    int pre = __popc(m & ((1u << lane) - 1u));
+    if (lane == 0) warp_tot[w] = __popc(m);
+    __syncthreads();
+    int off = 0;
+    for (int k = 0; k < w; ++k) off += warp_tot[k];
+    int base = base_s;
+    if (f) inliers[base + off + pre] = i;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int tot = 0;
+      for (int k = 0; k < 32; ++k) tot += warp_tot[k];
+      base_s = base + tot;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) res->n_inliers = base_s;
+}
+
+// ------------------------------------------------------------------ LM refinement (SOLVEPNP_ITERATIVE)
+// cv2.solvePnP(inliers as float64, useExtrinsicGuess=True, flags=ITERATIVE): Levenberg-Marquardt
+// with OpenCV's schedule — lambda = 10^-3 initially, (J^T J) with its diagonal scaled by
+// (1+lambda), accept when the residual norm does not increase (lambda /= 10) else lambda *= 10
+// and re-step from the same linearisation, stop after 20 accepted iterations or when the
+// relative parameter change drops below FLT_EPSILON.
+struct PoseJac {
+  double R[9];
+  double dR[3][9];   // dR/drvec_k
+};
+
+__device__ inline void pose_jacobian_setup(const double* rv, PoseJac* pj) {
+  hm::rodrigues_to_matrix(rv, pj->R);
+  double th2 = rv[0] * rv[0] + rv[1] * rv[1] + rv[2] * rv[2];
+  const double* R = pj->R;
+  for (int k = 0; k < 3; ++k) {
+    double e[3] = {k == 0 ? 1.0 : 0.0, k == 1 ? 1.0 : 0.0, k == 2 ? 1.0 : 0.0};
+    double S[9];
+    if (th2 < 1e-24) {
+      S[0] = 0; S[1] = -e[2]; S[2] = e[1]; S[3] = e[2]; S[4] = 0; S[5] = -e[0]; S[6] = -e[1]; S[7] = e[0]; S[8] = 0;
+      for (int i = 0; i < 9; ++i) pj->dR[k][i] = S[i];
+      continue;
+    }
+    // dR/dr_k = ( r_k [r]x + [ r x (I - R) e_k ]x ) R / |r|^2      (Gallego & Yezzi 2015)
+    double m[3] = {e[0] - R[0 + k], e[1] - R[3 + k], e[2] - R[6 + k]};   // (I - R) e_k
+    double c[3] = {rv[1] * m[2] - rv[2] * m[1], rv[2] * m[0] - rv[0] * m[2], rv[0] * m[1] - rv[1] * m[0]};
+    double a[3] = {rv[k] * rv[0] + c[0], rv[k] * rv[1] + c[1], rv[k] * rv[2] + c[2]};
+    S[0] = 0; S[1] = -a[2]; S[2] = a[1]; S[3] = a[2]; S[4] = 0; S[5] = -a[0]; S[6] = -a[1]; S[7] = a[0]; S[8] = 0;
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j)
+        pj->dR[k][3 * i + j] = (S[3 * i] * R[j] + S[3 * i + 1] * R[3 + j] + S[3 * i + 2] * R[6 + j]) / th2;
+  }
+}
+
+constexpr int REFINE_THREADS = 256;
+constexpr int REFINE_NACC = 28;   // 21 (upper JtJ) + 6 (Jt e) + 1 (|e|^2)
+
+__device__ inline void block_reduce_acc(double* acc, double (*sh)[REFINE_NACC], double* out) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < REFINE_NACC; ++k) {
+    double v = acc[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) sh[w][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < REFINE_NACC) {
+    double s = 0.0;
+    for (int ww = 0; ww < REFINE_THREADS / 32; ++ww) s += sh[ww][threadIdx.x];
+    out[threadIdx.x] = s;
+  }
+  __syncthreads();
+}
+
+// Solve (A with diag *= 1+lambda) x = b for symmetric positive semi-definite 6x6 A (upper packed
+// row-major in a21) by Jacobi eigen-decomposition (pseudo-inverse, like OpenCV's DECOMP_SVD).
+__device__ inline void solve6_damped(const double* a21, const double* b, double lambda, double* x) {
+  double A[36], w[6], V[36];
+  int k = 0;
+  for (int i = 0; i < 6; ++i)
+    for (int j = i; j < 6; ++j) { A[6 * i + j] = a21[k]; A[6 * j + i] = a21[k]; ++k; }
+  for (int i = 0; i < 6; ++i) A[7 * i] *= 1.0 + lambda;
+  hm::eig_sym<6>(A, w, V);
+  double wmax = fabs(w[5]) > fabs(w[0]) ? fabs(w[5]) : fabs(w[0]);
+  double thr = wmax * 6 * DBL_EPSILON;
+  for (int i = 0; i < 6; ++i) x[i] = 0.0;
+  for (int e = 0; e < 6; ++e) {
+    if (fabs(w[e]) <= thr) continue;
+    double d = 0.0;
+    for (int i = 0; i < 6; ++i) d += V[6 * e + i] * b[i];
+    d /= w[e];
+    for (int i = 0; i < 6; ++i) x[i] += d * V[6 * e + i];
+  }
+}
+
+__global__ void __launch_bounds__(REFINE_THREADS) pnp_refine_kernel(const float* __restrict__ X,
+                                                                    const float* __restrict__ px,
+                                                                    const int* __restrict__ inliers, PnpCam cam,
+                                                                    int max_iter, PnpResult* __restrict__ res) {
+  __shared__ double sh[REFINE_THREADS / 32][REFINE_NACC];
+  __shared__ double red[REFINE_NACC];
+  __shared__ PoseJac pj;
+  __shared__ double param[6], prev_param[6], JtJ[21], JtE[6];
+  __shared__ int s_state;   // 0 = CALC_J requested, 1 = CHECK_ERR requested, 2 = DONE
+  __shared__ double prev_err, lambda_lg10;
+  __shared__ int iters;
+  if (!res->ok) return;
+  const int m = res->n_inliers;
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < 3; ++k) { param[k] = res->rvec0[k]; param[3 + k] = res->tvec0[k]; }
+    s_state = 0;
+    lambda_lg10 = -3.0;
+    iters = 0;
+    prev_err = 0.0;
+  }
+  __syncthreads();
+  for (int guard = 0; guard < 2000; ++guard) {
+    const int state = s_state;
+    if (state == 2) break;
+    if (threadIdx.x == 0) pose_jacobian_setup(param, &pj);
+    __syncthreads();
+    double acc[REFINE_NACC];
+#pragma unroll
+    for (int k = 0; k < REFINE_NACC; ++k) acc[k] = 0.0;
+    const double tx = param[3], ty = param[4], tz = param[5];
+    for (int q = threadIdx.x; q < m; q += REFINE_THREADS) {
+      const int i = inliers[q];
+      const double Xw[3] = {(double)X[3 * (size_t)i], (double)X[3 * (size_t)i + 1], (double)X[3 * (size_t)i + 2]};
+      const double ox = (double)px[2 * (size_t)i], oy = (double)px[2 * (size_t)i + 1];
+      const double* R = pj.R;
+      double x = R[0] * Xw[0] + R[1] * Xw[1] + R[2] * Xw[2] + tx;
+      double y = R[3] * Xw[0] + R[4] * Xw[1] + R[5] * Xw[2] + ty;
+      double z = R[6] * Xw[0] + R[7] * Xw[1] + R[8] * Xw[2] + tz;
+      double iz = z != 0.0 ? 1.0 / z : 1.0;
+      double xn = x * iz, yn = y * iz;
+      double ex = xn * cam.fx + cam.cx - ox, ey = yn * cam.fy + cam.cy - oy;
+      acc[27] += ex * ex + ey * ey;
+      if (state == 0) {
+        double J[2][6];
+        // d(u,v)/dY
+        double a0 = cam.fx * iz, a2 = -cam.fx * xn * iz, b1 = cam.fy * iz, b2 = -cam.fy * yn * iz;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const double* D = pj.dR[k];
+          double dx = D[0] * Xw[0] + D[1] * Xw[1] + D[2] * Xw[2];
+          double dy = D[3] * Xw[0] + D[4] * Xw[1] + D[5] * Xw[2];
+          double dz = D[6] * Xw[0] + D[7] * Xw[1] + D[8] * Xw[2];
+          J[0][k] = a0 * dx + a2 * dz;
+          J[1][k] = b1 * dy + b2 * dz;
+        }
+        J[0][3] = a0; J[0][4] = 0.0; J[0][5] = a2;
+        J[1][3] = 0.0; J[1][4] = b1; J[1][5] = b2;
+        int k = 0;
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+#pragma unroll
+          for (int b = a; b < 6; ++b) acc[k++] += J[0][a] * J[0][b] + J[1][a] * J[1][b];
+        }
+#pragma unroll
+        for (int a = 0; a < 6; ++a) acc[21 + a] += J[0][a] * ex + J[1][a] * ey;
+      }
+    }
+    block_reduce_acc(acc, sh, red);
+    if (threadIdx.x == 0) {
+      const double err_norm = sqrt(red[27]);
+      if (state == 0) {          // CALC_J: new linearisation at `param`
+        for (int k = 0; k < 21; ++k) JtJ[k] = red[k];
+        for (int k = 0; k < 6; ++k) { JtE[k] = red[21 + k]; prev_param[k] = param[k]; }
+        double dx[6];
+        solve6_damped(JtJ, JtE, exp(lambda_lg10 * log(10.0)), dx);
+        for (int k = 0; k < 6; ++k) param[k] = prev_param[k] - dx[k];
+        if (iters == 0) prev_err = err_norm;
+        s_state = 1;
+      } else {                   // CHECK_ERR at the candidate `param`
+        bool retry = false;
+        if (err_norm > prev_err) {
+          lambda_lg10 += 1.0;
+          if (lambda_lg10 <= 16.0) {
+            double dx[6];
+            solve6_damped(JtJ, JtE, exp(lambda_lg10 * log(10.0)), dx);
+            for (int k = 0; k < 6; ++k) param[k] = prev_param[k] - dx[k];
+            retry = true;
+          }
+        }
+        if (!retry) {
+          lambda_lg10 = fmax(lambda_lg10 - 1.0, -16.0);
+          double dn = 0.0, pn = 0.0;
+          for (int k = 0; k < 6; ++k) { double d = param[k] - prev_param[k]; dn += d * d; pn += prev_param[k] * prev_param[k]; }
+          iters += 1;
+          if (iters >= max_iter || sqrt(dn) / (sqrt(pn) + DBL_EPSILON) < (double)FLT_EPSILON) {
+            s_state = 2;
+          } else {
+            prev_err = err_norm;
+            s_state = 0;
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < 3; ++k) { res->rvec[k] = param[k]; res->tvec[k] = param[3 + k]; }
+    res->refine_iters = iters;
+  }
+}
+
+static PnpCam make_pnp_cam(const double* K) {
+  PnpCam c = {K[0], K[4], K[2], K[5]};
+  return c;
+}
+
+}  // namespace
+
+// ============================================================================ C ABI
+extern "C" int sfm_pnp_score(sfm_ctx* ctx, const float* X, const float* px, int n, const double* K,
+                             const double* Rt, int H, float thr, int32_t* counts, uint8_t* masks) {
+  SFM_REQUIRE(ctx && X && px && K && Rt, "sfm_pnp_score: null argument");
+  SFM_REQUIRE(n >= 1 && H >= 1, "sfm_pnp_score: need n >= 1 and H >= 1");
+  SFM_REQUIRE(counts || masks, "sfm_pnp_score: no output requested");
+  SFM_TRY(sfm_ws_begin(ctx));
+  const float *dX, *dpx;
+  SFM_TRY(dev_in(ctx, X, (size_t)3 * n, &dX));
+  SFM_TRY(dev_in(ctx, px, (size_t)2 * n, &dpx));
+  // (H,12) [R|t] rows of a 3x4 -> R9 | t3
+  double* hp;
+  SFM_TRY(hs_alloc_t(ctx, (size_t)12 * H, &hp));
+  for (int h = 0; h < H; ++h) {
+    const double* s = Rt + 12 * (size_t)h;
+    double* d = hp + 12 * (size_t)h;
+    d[0] = s[0]; d[1] = s[1]; d[2] = s[2]; d[3] = s[4]; d[4] = s[5]; d[5] = s[6]; d[6] = s[8]; d[7] = s[9]; d[8] = s[10];
+    d[9] = s[3]; d[10] = s[7]; d[11] = s[11];
+  }
+  double* dposes;
+  SFM_TRY(ws_alloc_t(ctx, (size_t)12 * H, &dposes));
+  SFM_CUDA(cudaMemcpyAsync(dposes, hp, sizeof(double) * 12 * H, cudaMemcpyHostToDevice, ctx->stream));
+  bool host_out = false;
+  DevOut<int32_t> oc;
+  DevOut<uint8_t> om;
+  SFM_TRY(dev_out(ctx, counts, (size_t)H, &oc, &host_out));
+  SFM_TRY(dev_out(ctx, masks, (size_t)H * n, &om, &host_out));
+  int32_t* dcounts = oc.dev;
+  if (!dcounts) SFM_TRY(ws_alloc_t(ctx, (size_t)H, &dcounts));
+  SFM_CUDA(cudaMemsetAsync(dcounts, 0, sizeof(int32_t) * H, ctx->stream));
+  const float thr2 = (float)((double)thr * (double)thr);
+  dim3 grid(div_up(n, 256), div_up(H, PNP_HG));
+  SFM_LAUNCH(ctx, SFM_K_PNP_SCORE, (pnp_score_kernel<<<grid, 256, 0, ctx->stream>>>(dX, dpx, n, dposes, nullptr, H, make_pnp_cam(K), thr2, dcounts, om.dev)));
+  SFM_TRY(dev_out_finish(ctx, &oc));
+  SFM_TRY(dev_out_finish(ctx, &om));
+  if (host_out) SFM_CUDA(cudaStreamSynchronize(ctx->stream));
+  return SFM_OK;
+}
+
+static int pnp_ransac_impl(sfm_ctx* ctx, const float* X, const float* px, int n, const double* K,
+                           const double* hyp_rt6, const uint8_t* hyp_valid, int max_iters, float thr,
+                           double confidence, double* rvec, double* tvec, int32_t* inliers, int32_t* n_inliers,
+                           int32_t* ok, sfm_pnp_info* info) {
+  SFM_REQUIRE(ctx && X && px && K && rvec && tvec && ok, "sfm_pnp_ransac: null argument");
+  SFM_REQUIRE(n >= 4, "sfm_pnp_ransac: needs at least 4 correspondences (cv2 asserts npoints >= 4), got %d", n);
+  if (n == 4) {
+    sfm_set_error("sfm_pnp_ransac: the 4-point case runs P3P in OpenCV; not provided by this engine");
+    return SFM_ERR_UNSUPPORTED;
+  }
+  SFM_REQUIRE(max_iters >= 1 && max_iters <= PNP_MAX_H, "sfm_pnp_ransac: iterationsCount %d out of range", max_iters);
+  SFM_TRY(sfm_ws_begin(ctx));
+  const PnpCam cam = make_pnp_cam(K);
+  const float thr2 = (float)((double)thr * (double)thr);
+  const float *dX, *dpx;
+  SFM_TRY(dev_in(ctx, X, (size_t)3 * n, &dX));
+  SFM_TRY(dev_in(ctx, px, (size_t)2 * n, &dpx));
+  const int H = (n == 5) ? 1 : max_iters;
+  int* dsub;
+  double *dposes, *drt6;
+  unsigned char* dvalid;
+  int32_t* dcounts;
+  int32_t* dinl;
+  PnpResult* dres;
+  SFM_TRY(ws_alloc_t(ctx, (size_t)5 * H, &dsub));
+  SFM_TRY(ws_alloc_t(ctx, (size_t)12 * H, &dposes));
+  SFM_TRY(ws_alloc_t(ctx, (size_t)6 * H, &drt6));
+  SFM_TRY(ws_alloc_t(ctx, (size_t)H, &dvalid));
+  SFM_TRY(ws_alloc_t(ctx, (size_t)H, &dcounts));
+  SFM_TRY(ws_alloc_t(ctx, (size_t)n, &dinl));
+  SFM_TRY(ws_alloc_t(ctx, 1, &dres));
+  if (hyp_rt6) {
+    // externally supplied minimal solutions (rvec|tvec per iteration): convert like cv2 does when it
+    // projects with a model, R = Rodrigues(rvec)
+    double* hp;
+    unsigned char* hv;
+    SFM_TRY(hs_alloc_t(ctx, (size_t)18 * H, &hp));
+    SFM_TRY(hs_alloc_t(ctx, (size_t)H, &hv));
+    for (int h = 0; h < H; ++h) {
+      const double* s = hyp_rt6 + 6 * (size_t)h;
+      double* d = hp + 12 * (size_t)h;
+      bool good = !hyp_valid || hyp_valid[h];
+      for (int k = 0; k < 6; ++k) good = good && isfinite(s[k]);
+      if (good) {
+        hm::rodrigues_to_matrix(s, d);
+        d[9] = s[3]; d[10] = s[4]; d[11] = s[5];
+      } else {
+        for (int k = 0; k < 12; ++k) d[k] = 0.0;
+      }
+      hv[h] = good ? 1 : 0;
+      memcpy(hp + 12 * (size_t)H + 6 * (size_t)h, s, 6 * sizeof(double));
+    }
+    SFM_CUDA(cudaMemcpyAsync(dposes, hp, sizeof(double) * 12 * H, cudaMemcpyHostToDevice, ctx->stream));
+    SFM_CUDA(cudaMemcpyAsync(drt6, hp + 12 * (size_t)H, sizeof(double) * 6 * H, cudaMemcpyHostToDevice, ctx->stream));
+    SFM_CUDA(cudaMemcpyAsync(dvalid, hv, H, cudaMemcpyHostToDevice, ctx->stream));
+  } else {
+    if (n == 5) {
+      int hsub[5] = {0, 1, 2, 3, 4};
+      int* ps;
+      SFM_TRY(hs_alloc_t(ctx, 5, &ps));
+      memcpy(ps, hsub, sizeof(hsub));
+      SFM_CUDA(cudaMemcpyAsync(dsub, ps, sizeof(hsub), cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+      SFM_LAUNCH(ctx, SFM_K_MISC, (pnp_subsets_kernel<<<1, 32, 0, ctx->stream>>>(n, H, dsub)));
+    }
+    SFM_LAUNCH(ctx, SFM_K_PNP_EPNP, (pnp_epnp_kernel<<<H, 32, 0, ctx->stream>>>(dX, dpx, dsub, H, cam, dposes, drt6, dvalid)));
+  }
+  SFM_CUDA(cudaMemsetAsync(dcounts, 0, sizeof(int32_t) * H, ctx->stream));
+  dim3 grid(div_up(n, 256), div_up(H, PNP_HG));
+  // model_points == npoints (n == 5): OpenCV keeps all five points whatever their error
+  const float thr2_eff = (n == 5) ? INFINITY : thr2;
+  SFM_LAUNCH(ctx, SFM_K_PNP_SCORE, (pnp_score_kernel<<<grid, 256, 0, ctx->stream>>>(dX, dpx, n, dposes, dvalid, H, cam, thr2_eff, dcounts, nullptr)));
+  if (n == 5) {
+    // model_points == npoints: OpenCV returns the EPnP pose of all five points, all inliers, no refinement
+    SFM_LAUNCH(ctx, SFM_K_MISC, (pnp_replay_kernel<<<1, 32, 0, ctx->stream>>>(dcounts, nullptr, n, 1, confidence, drt6, dres)));
+  } else {
+    SFM_LAUNCH(ctx, SFM_K_MISC, (pnp_replay_kernel<<<1, 32, 0, ctx->stream>>>(dcounts, dvalid, n, H, confidence, drt6, dres)));
+  }
+  SFM_LAUNCH(ctx, SFM_K_MISC, (pnp_inliers_kernel<<<1, 1024, 0, ctx->stream>>>(dX, dpx, n, dposes, cam, thr2_eff, dres, dinl)));
+  if (n != 5)
+    SFM_LAUNCH(ctx, SFM_K_PNP_REFINE, (pnp_refine_kernel<<<1, REFINE_THREADS, 0, ctx->stream>>>(dX, dpx, dinl, cam, 20, dres)));
+  // ---- single copy back
+  PnpResult* hres;
+  int32_t* hinl;
+  SFM_TRY(hs_alloc_t(ctx, 1, &hres));
+  SFM_TRY(hs_alloc_t(ctx, (size_t)n, &hinl));
+  SFM_CUDA(cudaMemcpyAsync(hres, dres, sizeof(PnpResult), cudaMemcpyDeviceToHost, ctx->stream));
+  if (inliers) SFM_CUDA(cudaMemcpyAsync(hinl, dinl, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  SFM_CUDA(cudaStreamSynchronize(ctx->stream));
+  *ok = hres->ok;
+  for (int k = 0; k < 3; ++k) { rvec[k] = hres->rvec[k]; tvec[k] = hres->tvec[k]; }
+  int ni = hres->ok ? hres->n_inliers : 0;
+  if (n_inliers) *n_inliers = ni;
+  if (inliers && ni > 0) {
+    if (sfm_is_device_ptr(inliers)) SFM_CUDA(cudaMemcpyAsync(inliers, dinl, sizeof(int32_t) * ni, cudaMemcpyDeviceToDevice, ctx->stream));
+    else memcpy(inliers, hinl, sizeof(int32_t) * ni);
+  }
+  if (info) {
+    info->iters_run = hres->iters_run;
+    info->best_iter = hres->best_iter;
+    info->hyp_solved = H;
+    info->refine_iters = hres->refine_iters;
+    for (int k = 0; k < 3; ++k) { info->rvec_ransac[k] = hres->rvec0[k]; info->tvec_ransac[k] = hres->tvec0[k]; }
+  }
+  return SFM_OK;
+}
+
+extern "C" int sfm_pnp_ransac(sfm_ctx* ctx, const float* X, const float* px, int n, const double* K,
+                              int max_iters, float thr, double confidence, double* rvec, double* tvec,
+                              int32_t* inliers, int32_t* n_inliers, int32_t* ok, sfm_pnp_info* info) {
+  return pnp_ransac_impl(ctx, X, px, n, K, nullptr, nullptr, max_iters, thr, confidence, rvec, tvec, inliers,
+                         n_inliers, ok, info);
+}
+
+extern "C" int sfm_pnp_ransac_hyp(sfm_ctx* ctx, const float* X, const float* px, int n, const double* K,
+                                  const double* hyp_rt6, const uint8_t* hyp_valid, int max_iters, float thr,
+                                  double confidence, double* rvec, double* tvec, int32_t* inliers,
+                                  int32_t* n_inliers, int32_t* ok, sfm_pnp_info* info) {
+  SFM_REQUIRE(hyp_rt6, "sfm_pnp_ransac_hyp: hypotheses missing");
+  SFM_REQUIRE(n > 5, "sfm_pnp_ransac_hyp: needs more than 5 correspondences");
+  return pnp_ransac_impl(ctx, X, px, n, K, hyp_rt6, hyp_valid, max_iters, thr, confidence, rvec, tvec, inliers,
+                         n_inliers, ok, info);
+}
+
+// ---- host utilities (parameter marshalling; usable without a GPU)
+extern "C" int sfm_ransac_subsets(int n, int iters, int32_t* out) {
+  SFM_REQUIRE(n >= 5 && iters >= 0 && out, "sfm_ransac_subsets: need n >= 5");
+  ransac_subsets(n, iters, out);
+  return SFM_OK;
+}
+
+extern "C" int sfm_epnp(const float* X, const float* px, int n, const double* K, double* R9, double* t3) {
+  SFM_REQUIRE(X && px && K && R9 && t3, "sfm_epnp: null argument");
+  SFM_REQUIRE(n >= 4, "sfm_epnp: needs at least 4 points");
+  hm::EpnpCam ec = {K[0], K[4], K[2], K[5]};
+  std::vector<double> pw((size_t)3 * n), us((size_t)2 * n), work((size_t)7 * n);
+  for (int i = 0; i < n; ++i) {
+    for (int k = 0; k < 3; ++k) pw[3 * i + k] = (double)X[3 * i + k];
+    hm::epnp_roundtrip_pixel(px[2 * i], px[2 * i + 1], ec, &us[2 * i]);
+  }
+  hm::epnp_solve(pw.data(), us.data(), n, ec, work.data(), R9, t3);
+  return SFM_OK;
+}

@@ -1,0 +1,236 @@
+"""The reference's call surface, backed by the CUDA engine.
+
+The reference (FlagArihant2000/sfm-mvs) has no plugin or operator layer: its boundary to the hot
+path is the OpenCV Python API as called from sfm.py / isfm.py / test.py, plus its own helper
+functions around those calls.  This module re-creates both with the same names, argument order,
+shapes, dtypes and error behaviour, so the reference's scripts run on the engine by replacing
+`cv2.X` with `sfm_mvs_b200.X` (or calling `patch_cv2()`):
+
+  cv2.BFMatcher().knnMatch(des0, des1, k=2)      sfm.py:259-260, isfm.py:47,71, test.py:41-42,225,352
+  cv2.triangulatePoints(P1, P2, x1, x2)          sfm.py:53, test.py:310,367
+  cv2.solvePnPRansac(X, p, K, d, ...)            sfm.py:67, test.py:319
+  Triangulation / ReprojectionError / PnP / common_points / BundleAdjustment   sfm.py:45-157,215-239
+  find_features' matching half on arrays         sfm.py:259-268
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from ._lib import error
+from . import engine as _e
+
+NORM_L2 = 4                   # cv2.NORM_L2
+SOLVEPNP_ITERATIVE = 0        # cv2.SOLVEPNP_ITERATIVE
+RATIO = 0.70                  # sfm.py:264
+
+_default_ctx = None
+
+
+def default_context() -> _e.Context:
+    """Process-wide context on the current device (cuda:LOCAL_RANK under torchrun)."""
+    global _default_ctx
+    if _default_ctx is None:
+        import os
+        _default_ctx = _e.Context(int(os.environ.get("LOCAL_RANK", "0")))
+    return _default_ctx
+
+
+def set_default_context(ctx: _e.Context | None):
+    global _default_ctx
+    _default_ctx = ctx
+
+
+# --------------------------------------------------------------------------- matching
+class DMatch:
+    """cv2.DMatch look-alike: queryIdx, trainIdx, imgIdx, distance (a Python float holding a float32 value)."""
+
+    __slots__ = ("queryIdx", "trainIdx", "imgIdx", "distance")
+
+    def __init__(self, queryIdx=-1, trainIdx=-1, imgIdx=0, distance=float("inf")):
+        self.queryIdx, self.trainIdx, self.imgIdx, self.distance = queryIdx, trainIdx, imgIdx, distance
+
+    def __repr__(self):
+        return f"DMatch(queryIdx={self.queryIdx}, trainIdx={self.trainIdx}, imgIdx={self.imgIdx}, distance={self.distance})"
+
+
+class BFMatcher:
+    """cv2.BFMatcher(normType=NORM_L2, crossCheck=False) — the only configuration the reference uses."""
+
+    def __init__(self, normType: int = NORM_L2, crossCheck: bool = False, ctx: _e.Context | None = None):
+        if normType != NORM_L2 or crossCheck:
+            raise error(-4, "BFMatcher: only NORM_L2 without cross-check is provided (what the reference constructs)")
+        self._ctx = ctx
+
+    def knnMatch(self, queryDescriptors, trainDescriptors, k: int = 2):
+        if k not in (1, 2):
+            raise error(-4, "knnMatch: k must be 1 or 2")
+        q, t = np.asarray(queryDescriptors), np.asarray(trainDescriptors)
+        if q.ndim != 2 or t.ndim != 2:
+            raise error(-1, "knnMatch: descriptors must be 2-D")
+        if q.shape[0] == 0:
+            return ()
+        if t.shape[0] == 0:
+            return tuple(() for _ in range(q.shape[0]))
+        if q.dtype != t.dtype:
+            raise error(-1, "knnMatch: query and train descriptor types differ")
+        ctx = self._ctx or default_context()
+        idx, dist, _, _ = ctx.knn2(q, t, RATIO)
+        kk = min(k, t.shape[0])
+        idl, dl = idx.tolist(), dist.astype(np.float64).tolist()
+        return tuple(tuple(DMatch(i, idl[i][j], 0, dl[i][j]) for j in range(kk)) for i in range(len(idl)))
+
+
+def knn2(des0, des1, ratio: float = RATIO, ctx: _e.Context | None = None):
+    """Array form of knnMatch + the Lowe loop: idx (n,2) i32, dist (n,2) f32, good (n,) bool."""
+    ctx = ctx or default_context()
+    idx, dist, good, _ = ctx.knn2(des0, des1, ratio)
+    return idx, dist, good.astype(bool)
+
+
+def match_keypoints(kp0, des0, kp1, des1, ratio: float = RATIO, ctx: _e.Context | None = None):
+    """Matching half of find_features (sfm.py:259-268) on arrays: kp (n,2) float32 stand for kp[i].pt.
+    Returns pts0, pts1 (M,2) float32 in ascending queryIdx order."""
+    idx, _, good = knn2(des0, des1, ratio, ctx)
+    q = np.nonzero(good)[0]
+    return np.float32(np.asarray(kp0)[q]), np.float32(np.asarray(kp1)[idx[q, 0]])
+
+
+# --------------------------------------------------------------------------- triangulation
+def _as_2xn(a, name):
+    a = np.asarray(a)
+    if a.dtype != np.float32:
+        # cv2 also takes float64 points (and then answers in float64); the reference only ever passes
+        # float32 and the engine's I/O is float32, so be loud instead of silently changing precision.
+        raise error(-1, f"triangulatePoints: {name} must be float32 (got {a.dtype})")
+    if a.ndim == 2 and a.shape[0] == 2:
+        return np.ascontiguousarray(a)
+    if a.ndim == 3 and a.shape[2] == 2 and 1 in a.shape[:2]:
+        return np.ascontiguousarray(a.reshape(-1, 2).T)
+    raise error(-1, f"triangulatePoints: {name} must be 2xN (or Nx1x2 / 1xNx2), got shape {a.shape}")
+
+
+def triangulatePoints(projMatr1, projMatr2, projPoints1, projPoints2, ctx: _e.Context | None = None):
+    """cv2.triangulatePoints: (4,N) homogeneous points, unit norm, dtype of the input points."""
+    x1, x2 = _as_2xn(projPoints1, "projPoints1"), _as_2xn(projPoints2, "projPoints2")
+    if x1.shape != x2.shape:
+        raise error(-1, "triangulatePoints: point arrays differ in size")
+    if x1.shape[1] == 0:
+        raise error(-1, "triangulatePoints: no points (cv2 raises as well)")
+    P1, P2 = np.asarray(projMatr1, np.float64), np.asarray(projMatr2, np.float64)
+    if P1.shape != (3, 4) or P2.shape != (3, 4):
+        raise error(-1, "triangulatePoints: projection matrices must be 3x4")
+    return (ctx or default_context()).triangulate(P1, P2, x1, x2, 0, 0, False)
+
+
+def Triangulation(P1, P2, pts1, pts2, K=None, repeat=False, ctx: _e.Context | None = None):
+    """sfm.py:45-56 — returns (pts1 as 2xN, pts2 as 2xN, cloud 4xN with row 3 == 1)."""
+    a = pts1 if repeat else pts1.T
+    b = pts2 if repeat else pts2.T
+    a32, b32 = _as_2xn(a, "pts1"), _as_2xn(b, "pts2")
+    cloud = (ctx or default_context()).triangulate(np.asarray(P1, np.float64), np.asarray(P2, np.float64), a32, b32,
+                                                   0, 0, True)
+    return a, b, cloud
+
+
+# --------------------------------------------------------------------------- reprojection error
+def ReprojectionError(X, pts, Rt, K, homogenity, ctx: _e.Context | None = None):
+    """sfm.py:79-100 — (Frobenius norm of projected-observed)/N, X as cv2 returns it, projections (N,2) f32."""
+    ctx = ctx or default_context()
+    X = np.asarray(X)
+    pts = np.asarray(pts)
+    if homogenity == 1:
+        err, proj, X3 = ctx.reproj_error(np.float32(X), 1, np.float32(pts), 0, Rt, K, True, True)
+        Xout = X3.reshape(-1, 1, 3)                      # cv2.convertPointsFromHomogeneous shape
+    else:
+        X3 = np.float32(X).reshape(-1, 3)
+        err, proj, _ = ctx.reproj_error(X3, 0, np.float32(pts), 1, Rt, K, True, False)
+        Xout = X
+    return err, Xout, proj
+
+
+# --------------------------------------------------------------------------- PnP
+def solvePnPRansac(objectPoints, imagePoints, cameraMatrix, distCoeffs, rvec=None, tvec=None,
+                   useExtrinsicGuess=False, iterationsCount=100, reprojectionError=8.0, confidence=0.99,
+                   inliers=None, flags=SOLVEPNP_ITERATIVE, ctx: _e.Context | None = None, hypotheses=None):
+    """cv2.solvePnPRansac, positional-compatible (the reference's 5th positional lands in `rvec` and is
+    ignored because useExtrinsicGuess is False).  Returns (retval, rvec (3,1), tvec (3,1), inliers (n,1) int32 | None)."""
+    if useExtrinsicGuess or flags != SOLVEPNP_ITERATIVE:
+        raise error(-4, "solvePnPRansac: only flags=SOLVEPNP_ITERATIVE without an extrinsic guess (the reference's call)")
+    if distCoeffs is not None and np.any(np.asarray(distCoeffs) != 0):
+        raise error(-4, "solvePnPRansac: non-zero distortion is not provided (the reference passes zeros)")
+    X = np.asarray(objectPoints, np.float32).reshape(-1, 3)
+    p = np.asarray(imagePoints, np.float32).reshape(-1, 2)
+    if len(X) != len(p):
+        raise error(-1, "solvePnPRansac: object/image point counts differ")
+    ok, r, t, inl, _ = (ctx or default_context()).pnp_ransac(X, p, cameraMatrix, iterationsCount, reprojectionError,
+                                                            confidence, hypotheses)
+    if not ok:
+        return False, np.zeros((3, 1)), np.zeros((3, 1)), None
+    return True, r.reshape(3, 1), t.reshape(3, 1), inl.reshape(-1, 1).astype(np.int32)
+
+
+def PnP(X, p, K, d, p_0, initial, ctx: _e.Context | None = None):
+    """sfm.py:60-76."""
+    if initial == 1:
+        X = X[:, 0, :]
+        p = p.T
+        p_0 = p_0.T
+    ok, rvec, t, inliers = solvePnPRansac(X, p, K, d, SOLVEPNP_ITERATIVE, ctx=ctx)
+    R = _e.rodrigues_to_matrix(rvec)
+    if inliers is not None:
+        sel = inliers[:, 0]
+        p, X, p_0 = p[sel], X[sel], p_0[sel]
+    return R, t, p, X, p_0
+
+
+def common_points(pts1, pts2, pts3, ctx: _e.Context | None = None):
+    """sfm.py:215-239 — returns (indx1, indx2, temp_array1, temp_array2) with the reference's element-wise
+    'x or y equal, first hit' semantics."""
+    i1, i2, keep, _ = (ctx or default_context()).common_points(np.float32(pts1), np.float32(pts2))
+    keep = keep.astype(bool)
+    return i1.astype(np.int64), i2.astype(np.int64), np.asarray(pts2)[keep], np.asarray(pts3)[keep]
+
+
+# --------------------------------------------------------------------------- BundleAdjustment (sfm.py:138-157)
+def BundleAdjustment(points_3d, temp2, Rtnew, K, r_error, ctx: _e.Context | None = None, max_iters: int = 25):
+    """Same signature and return shapes as the reference: (X (N,3) f64, p (N,2) f64, Rt (3,4) f64).
+
+    The reference lets scipy move the pose (as 12 unconstrained numbers), K, the observed pixels and the
+    points under a dense finite-difference Jacobian (sfm.py:141-146) — "close to half a minute per frame"
+    (sfm.py:378).  The engine solves the well-posed version of the same problem: the camera moves on SE(3)
+    (rvec, tvec), K and the observations are data, analytic Jacobians, Schur-complement LM on the GPU.
+    The residual the reference evaluates, ((p-proj)^2)/N, is available bit-for-tolerance as mode 1 of
+    BAProblem.eval (parity-tested); r_error plays the reference's role of the stopping tolerance."""
+    ctx = ctx or default_context()
+    X = np.asarray(points_3d, np.float64).reshape(-1, 3)
+    obs = np.asarray(temp2, np.float32)
+    obs = obs.T if obs.shape[0] == 2 else obs
+    n = len(X)
+    Rt = np.asarray(Rtnew, np.float64)
+    cam = np.concatenate([_e.rodrigues_to_vector(Rt[:, :3]), Rt[:, 3]])
+    prob = _e.BAProblem(ctx, 1, n, np.zeros(n, np.int32), np.arange(n, dtype=np.int32), obs, K)
+    prob.set_params(cam.reshape(1, 6), X)
+    prob.solve(max_iters=max_iters, ftol=1e-10)
+    cams, pts = prob.get_params()
+    prob.close()
+    Rt_out = np.hstack([_e.rodrigues_to_matrix(cams[0, :3]), cams[0, 3:].reshape(3, 1)])
+    return pts, np.float64(obs), Rt_out
+
+
+def patch_cv2(cv2_module=None):
+    """Route the reference's hot-path cv2 calls to the engine: after this, the reference's own
+    function definitions run unmodified on the GPU.  Returns a dict of the originals (to undo)."""
+    import cv2 as _cv2
+    m = cv2_module or _cv2
+    saved = dict(BFMatcher=m.BFMatcher, triangulatePoints=m.triangulatePoints, solvePnPRansac=m.solvePnPRansac)
+    m.BFMatcher = BFMatcher
+    m.triangulatePoints = triangulatePoints
+    m.solvePnPRansac = solvePnPRansac
+    return saved
+
+
+def unpatch_cv2(saved, cv2_module=None):
+    import cv2 as _cv2
+    m = cv2_module or _cv2
+    for k, v in saved.items():
+        setattr(m, k, v)

@@ -1,0 +1,109 @@
+"""GPU parity: hot path 1 (2-NN matching + Lowe ratio) against cv2 / the oracle — bit-exact."""
+import cv2
+import numpy as np
+import pytest
+
+import sfm_mvs_b200 as sfm
+from oracle import cvpath, restated
+from sfm_mvs_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _check_pair(engine, q, t, mode):
+    idx, dist, good, ng = engine.knn2(q, t, 0.70, mode=mode)
+    cidx, cdist = cvpath.knn2_arrays(q.astype(np.float32), t.astype(np.float32))
+    k = cidx.shape[1]
+    assert np.array_equal(idx[:, :k], cidx), f"indices differ in {np.sum(idx[:, :k] != cidx)} places"
+    assert np.array_equal(dist[:, :k], cdist)
+    if k == 2:
+        ref_good = restated.ratio_mask(cdist)
+        assert np.array_equal(good.astype(bool), ref_good)
+        assert ng == int(ref_good.sum())
+
+
+@pytest.mark.parametrize("mode", [2, 1])
+@pytest.mark.parametrize("nq,nt,seed", [(257, 301, 0), (1000, 900, 1), (128, 256, 2), (2000, 2000, 3),
+                                        (5000, 5000, 4), (1, 700, 5), (300, 2, 6), (129, 513, 7)])
+def test_knn2_equals_cv2(engine, nq, nt, seed, mode):
+    q, t, _ = synth.matching_pair(nq, nt, seed=seed)
+    _check_pair(engine, q, t, mode)
+
+
+def test_tensor_core_accumulator_is_the_exact_squared_distance(engine):
+    q, t, _ = synth.matching_pair(200, 300, seed=11)
+    dq, dt = engine.descriptors(q), engine.descriptors(t)
+    assert dq.exact and dt.exact
+    acc = engine.debug_tc_accumulators(dq, dt)[:200, :300]
+    d2 = ((q[:, None, :].astype(np.float64) - t[None, :, :].astype(np.float64)) ** 2).sum(-1)
+    assert np.array_equal(acc.astype(np.float64), -(4194304.0 + d2 / 2.0))
+
+
+def test_ties_go_to_lower_train_index(engine):
+    q = synth.sift_like_descriptors(300, 5)
+    t = np.vstack([q[::-1], q[::-1]])
+    for mode in (1, 2):
+        idx, dist, _, _ = engine.knn2(q, t, mode=mode)
+        cidx, cdist = cvpath.knn2_arrays(q, t)
+        assert np.array_equal(idx, cidx) and np.array_equal(dist, cdist)
+        assert np.all(idx[:, 0] < idx[:, 1]) and np.all(dist == 0)
+
+
+def test_real_sift_pair_golden(engine, golden):
+    g = golden("real_pair")
+    for des0, des1 in ((g["des0"], g["des1"]), (g["des0"].astype(np.float32), g["des1"].astype(np.float32))):
+        p0, p1 = sfm.match_keypoints(g["kp0"], des0, g["kp1"], des1, ctx=engine)
+        assert np.array_equal(p0, g["pts0"]) and np.array_equal(p1, g["pts1"])
+
+
+def test_non_integer_descriptors_take_the_fp32_kernel(engine):
+    rng = np.random.default_rng(0)
+    q = rng.random((300, 128), dtype=np.float32)
+    t = rng.random((400, 128), dtype=np.float32)
+    d = engine.descriptors(q)
+    assert not d.exact
+    idx, dist, _, _ = engine.knn2(q, t)
+    cidx, cdist = cvpath.knn2_arrays(q, t)
+    # float accumulation order differs from OpenCV's SIMD lanes: indices must agree wherever the two
+    # nearest candidates are separated by more than rounding noise
+    sep = np.abs(cdist[:, 1] - cdist[:, 0]) > 1e-4
+    assert np.array_equal(idx[sep, 0], cidx[sep, 0])
+    assert np.allclose(dist, cdist, rtol=1e-5)
+    with pytest.raises(sfm.error):
+        engine.knn2(q, t, mode=2)
+
+
+def test_knnmatch_dmatch_surface_and_edge_cases(engine):
+    q, t, _ = synth.matching_pair(50, 60, seed=3)
+    ours = sfm.BFMatcher(ctx=engine).knnMatch(q, t, k=2)
+    ref = cv2.BFMatcher().knnMatch(q, t, k=2)
+    assert len(ours) == len(ref)
+    for a, b in zip(ours, ref):
+        assert len(a) == len(b) == 2
+        for m, n in zip(a, b):
+            assert (m.queryIdx, m.trainIdx, m.imgIdx, m.distance) == (n.queryIdx, n.trainIdx, n.imgIdx, n.distance)
+    good = [m for m, n in ours if m.distance < 0.70 * n.distance]          # the reference's loop, sfm.py:262-265
+    good_ref = [m for m, n in ref if m.distance < 0.70 * n.distance]
+    assert [(m.queryIdx, m.trainIdx) for m in good] == [(m.queryIdx, m.trainIdx) for m in good_ref]
+    # nt == 1 -> 1-tuples ; nt == 0 -> empty tuples ; nq == 0 -> ()
+    one = sfm.BFMatcher(ctx=engine).knnMatch(q, t[:1], k=2)
+    assert all(len(x) == 1 for x in one) and [x[0].distance for x in one] == [x[0].distance for x in cv2.BFMatcher().knnMatch(q, t[:1], k=2)]
+    assert sfm.BFMatcher(ctx=engine).knnMatch(q, t[:0], k=2) == tuple(() for _ in range(50))
+    assert sfm.BFMatcher(ctx=engine).knnMatch(q[:0], t, k=2) == ()
+    with pytest.raises(sfm.error):
+        sfm.BFMatcher(ctx=engine).knnMatch(q.astype(np.float64), t.astype(np.float64), k=2)
+    with pytest.raises(sfm.error):
+        sfm.BFMatcher(ctx=engine).knnMatch(q, t[:, :64].copy(), k=2)
+
+
+def test_large_pair_properties(engine):
+    """BASELINE sweep size (16k x 16k): too slow for the numpy oracle in full, so (a) a random sample of
+    query rows is checked exhaustively and (b) matching a set against itself returns the identity."""
+    q, t, _ = synth.matching_pair(16384, 16384, seed=9)
+    idx, dist, good, _ = engine.knn2(q, t, mode=2)
+    rows = np.random.default_rng(0).choice(16384, 256, replace=False)
+    ridx, rdist = restated.knn2_l2(q[rows], t)
+    assert np.array_equal(idx[rows], ridx) and np.array_equal(dist[rows], rdist)
+    sidx, sdist, _, _ = engine.knn2(t, t, mode=2)
+    # duplicates inside t are possible in principle; distance 0 with the lowest index is the contract
+    assert np.all(sdist[:, 0] == 0) and np.all(sidx[:, 0] <= np.arange(16384))

@@ -1,0 +1,115 @@
+"""GPU parity: hot path 3a (PnP-RANSAC scoring, stopping rule, inliers, refinement) against cv2."""
+import cv2
+import numpy as np
+import pytest
+
+import sfm_mvs_b200 as sfm
+from oracle import restated
+from sfm_mvs_b200 import synth
+
+pytestmark = pytest.mark.gpu
+K = synth.K_GUSTAV
+D0 = np.zeros((5, 1), np.float32)
+
+
+def _problem(seed, n=None):
+    rng = np.random.default_rng(100 + seed)
+    n = int(rng.integers(30, 3000)) if n is None else n
+    R, t = synth.orbit_pose(rng.uniform(0, 0.5))
+    X = np.c_[rng.uniform(-2.5, 2.5, n), rng.uniform(-1.5, 1.5, n), rng.uniform(5, 11, n)].astype(np.float32)
+    uv, _ = synth.project(K, R, t, X.astype(np.float64))
+    p = (uv + rng.normal(0, rng.uniform(0.1, 2.0), uv.shape)).astype(np.float32)
+    bad = rng.random(n) < rng.uniform(0, 0.6)
+    p[bad] += rng.uniform(-80, 80, (int(bad.sum()), 2)).astype(np.float32)
+    return X, p
+
+
+def _cv_hypotheses(X, p, iters=100):
+    """OpenCV's own minimal solutions for the RNG subset stream (what cv2.solvePnPRansac computes inside)."""
+    subs = sfm.ransac_subsets(len(X), iters)
+    hyp = np.zeros((iters, 6))
+    valid = np.zeros(iters, np.uint8)
+    for i, s in enumerate(subs):
+        ok, r, t = cv2.solvePnP(X[s], p[s], K, D0, flags=cv2.SOLVEPNP_EPNP)
+        if ok:
+            hyp[i, :3], hyp[i, 3:] = r.ravel(), t.ravel()
+            valid[i] = 1
+    return hyp, valid
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_hypothesis_scoring_bit_exact(engine, seed):
+    X, p = _problem(seed)
+    hyp, valid = _cv_hypotheses(X, p, 40)
+    Rt = np.array([np.hstack([cv2.Rodrigues(h[:3])[0], h[3:].reshape(3, 1)]) for h in hyp])
+    counts, masks = engine.pnp_score(X, p, K, Rt, 8.0)
+    for h in range(len(hyp)):
+        ref = restated.score_hypothesis(X, p, cv2.Rodrigues(hyp[h, :3])[0], hyp[h, 3:], K, 8.0)
+        assert np.array_equal(masks[h].astype(bool), ref), h
+        assert counts[h] == int(ref.sum())
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_ransac_inlier_mask_bit_exact_given_opencv_minimal_solutions(engine, seed):
+    X, p = _problem(seed)
+    ok_ref, rvec_ref, tvec_ref, inl_ref = cv2.solvePnPRansac(X, p, K, D0, cv2.SOLVEPNP_ITERATIVE)
+    hyp, valid = _cv_hypotheses(X, p)
+    ok, rvec, tvec, inl, info = engine.pnp_ransac(X, p, K, hypotheses=hyp, hyp_valid=valid)
+    assert ok == ok_ref
+    if ok:
+        assert np.array_equal(inl, inl_ref[:, 0])                   # bit-exact mask
+        assert np.abs(rvec - rvec_ref.ravel()).max() <= 1e-4 * max(1.0, np.abs(rvec_ref).max())
+        assert np.abs(tvec - tvec_ref.ravel()).max() <= 1e-4 * max(1.0, np.abs(tvec_ref).max())
+
+
+def test_golden_pnp_inliers(engine, golden):
+    g = golden("geometry")
+    X, p = g["pnp_X"], g["pnp_p"]
+    hyp, valid = _cv_hypotheses(X, p)
+    ok, rvec, tvec, inl, _ = engine.pnp_ransac(X, p, g["K"], hypotheses=hyp, hyp_valid=valid)
+    ok_now, _, _, inl_now = cv2.solvePnPRansac(X, p, g["K"], D0)
+    assert ok and np.array_equal(inl, inl_now[:, 0])
+    # the committed fixture was produced by the reference's PnP() in the build container; OpenCV's EPnP
+    # depends on the host's LAPACK kernels, so only require it when this host reproduces the fixture
+    if np.array_equal(inl_now, g["pnp_inliers"]):
+        assert np.array_equal(inl, g["pnp_inliers"][:, 0])
+        R = sfm.rodrigues_to_matrix(rvec)
+        assert np.abs(R - g["pnp_R"]).max() < 1e-6 and np.abs(tvec - g["pnp_t"].ravel()).max() < 1e-5
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_ransac_with_engine_minimal_solver(engine, seed):
+    """Full GPU path (own EPnP).  OpenCV's EPnP picks its null-space basis with LAPACK, so individual
+    hypotheses differ; the estimate must still be the same pose and the same consensus set up to the
+    points within noise of the 8 px threshold."""
+    X, p = _problem(seed)
+    ok_ref, rvec_ref, tvec_ref, inl_ref = cv2.solvePnPRansac(X, p, K, D0)
+    ok, rvec, tvec, inl, info = engine.pnp_ransac(X, p, K)
+    assert ok == ok_ref
+    if ok:
+        a, b = set(inl.tolist()), set(inl_ref[:, 0].tolist())
+        assert len(a & b) / len(a | b) > 0.97
+        proj_ref, _ = cv2.projectPoints(X[inl_ref[:, 0]], rvec_ref, tvec_ref, K, None)
+        proj, _ = cv2.projectPoints(X[inl_ref[:, 0]], rvec, tvec, K, None)
+        assert np.abs(proj - proj_ref).max() < 0.5       # same pose: < 0.5 px on every consensus point
+        assert np.all(np.diff(inl) > 0) and info["hyp_solved"] == 100
+
+
+def test_solvepnpransac_surface(engine):
+    X, p = _problem(3, n=600)
+    ok, rvec, tvec, inl = sfm.solvePnPRansac(X, p, K, D0, cv2.SOLVEPNP_ITERATIVE, ctx=engine)   # the reference's call
+    assert ok and rvec.shape == (3, 1) and tvec.shape == (3, 1) and inl.dtype == np.int32 and inl.shape[1] == 1
+    R, t, p_in, X_in, p0_in = sfm.PnP(X, p, K, D0, p.copy(), 0, ctx=engine)
+    assert R.shape == (3, 3) and len(p_in) == len(X_in) == len(inl)
+    # failure is a return value, not an exception (pure noise -> no consensus of more than 4)
+    rng = np.random.default_rng(0)
+    Xn = rng.uniform(-1, 1, (40, 3)).astype(np.float32); Xn[:, 2] += 8
+    pn = rng.uniform(0, 900, (40, 2)).astype(np.float32)
+    okn, _, _, inln = sfm.solvePnPRansac(Xn, pn, K, D0, ctx=engine)
+    okc, _, _, inlc = cv2.solvePnPRansac(Xn, pn, K, D0)
+    assert okn == okc and ((inln is None) == (inlc is None))
+    with pytest.raises(sfm.error):
+        sfm.solvePnPRansac(X[:3], p[:3], K, D0, ctx=engine)
+    # five points: OpenCV returns the EPnP pose with all five as inliers
+    ok5, r5, t5, inl5 = sfm.solvePnPRansac(X[:5], p[:5], K, D0, ctx=engine)
+    assert ok5 and inl5[:, 0].tolist() == [0, 1, 2, 3, 4]
