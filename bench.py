@@ -1,0 +1,375 @@
+#!/usr/bin/env python
+"""bench.py — headline metric of BASELINE.json: views registered/sec (match + PnP + triangulate) on the
+synthetic 200-view x 5000-descriptor set (configs[2], the set north_star quotes its target on), plus
+BA Gauss-Newton iterations/sec on the 500-camera / 100k-point / 1M-observation problem (configs[3]).
+
+    python bench.py --gpus N --steps K --warmup W            # this engine (one process per GPU)
+    python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU path (oracle port)
+
+A step = one pass of the per-view registration loop (sfm.py:341-409, imread/SIFT/GUI removed) over the
+whole scene: V-2 views registered.  N > 1: every rank registers its own scene (the chain is sequential —
+"replicas only"), weak scaling, no data-path collective; the BA section shards points
+over ranks and all-reduces the reduced camera system over NCCL.
+One JSON line is printed by rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import contextlib
+import io
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--views", type=int, default=200)
+    ap.add_argument("--desc", type=int, default=5000)
+    ap.add_argument("--cpu-views", type=int, default=26, help="view prefix the CPU baseline registers")
+    ap.add_argument("--no-ba", action="store_true")
+    ap.add_argument("--ba-cams", type=int, default=500)
+    ap.add_argument("--ba-points", type=int, default=100_000)
+    ap.add_argument("--ba-obs-per-point", type=int, default=10)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            p = json.load(fh)
+        return dict(hbm=float(p["hbm_gbs"]), bf16=float(p["bf16_tflops"]), bf16_sustained=float(p["bf16_tflops_sustained"]),
+                    source="measured (MEASURED_PEAKS.json)")
+    except Exception:
+        return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+        return self
+
+    def __exit__(self, *a):
+        self.summary = dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
+        if not self.proc:
+            return
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        for line in out.splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            self.summary = dict(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons),
+                                samples=len(sm))
+
+
+def quiet(fn, *a, **k):
+    with contextlib.redirect_stdout(io.StringIO()):
+        return fn(*a, **k)
+
+
+# ====================================================================================== reference arm
+def cpu_register(scene, n_views):
+    """The reference's per-view loop on the host cores (oracle port of sfm.py:341-409, the same cv2 calls;
+    OpenCV threads = all cores, Python driver single-threaded as in the reference)."""
+    from oracle import cvpath
+    t0 = time.perf_counter()
+    outs = quiet(cvpath.register_chain, scene, n_views)
+    return len(outs), time.perf_counter() - t0
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import cv2
+    from sfm_mvs_b200 import synth
+    nv = min(args.cpu_views, args.views)
+    scene = synth.orbit_scene(nv, args.desc, seed=0)
+    for _ in range(max(args.warmup, 1)):
+        cpu_register(scene, min(4, nv))
+    t_tot, reg = 0.0, 0
+    for _ in range(args.steps):
+        r, t = cpu_register(scene, nv)
+        reg += r; t_tot += t
+    v = reg / t_tot
+    sample = f"{nv}-view prefix of the {args.views}x{args.desc} scene ({nv - 2} views registered per step)"
+    print(json.dumps({
+        "impl": "reference", "metric": "views registered/sec (match+PnP+tri)", "value": v, "unit": "views/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32/f64 (OpenCV)",
+        "data": "synthetic", "config": {"workload": f"synthetic {args.views} views x {args.desc} desc: full incremental register (PnP+triangulate)",
+                                        "sample": sample},
+        "cpu_baseline": {"value": v, "unit": "views/s", "cores": cv2.getNumThreads(), "kind": "port", "sample": sample,
+                         "host_cpus": os.cpu_count(), "cv2": cv2.__version__},
+        "e2e": {"value": v, "unit": "views/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ====================================================================================== engine arm
+def run_engine(args):
+    import torch
+    import torch.distributed as dist
+
+    import sfm_mvs_b200 as sfm
+    from sfm_mvs_b200 import pipeline, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    ctx = sfm.Context(local)
+    ts = ctx.torch_stream()
+    pk = peaks()
+    V, n = args.views, args.desc
+    scene = synth.orbit_scene(V, n, seed=rank)                 # every rank its own scene (replicas)
+    K = scene["K"]
+    Rt0 = np.hstack([scene["views"][0]["R"], scene["views"][0]["t"]])
+    Rt1 = np.hstack([scene["views"][1]["R"], scene["views"][1]["t"]])
+    # host inputs in pinned memory (e2e) and resident copies in HBM (value)
+    kp_host = [torch.from_numpy(v["kp"]).pin_memory() for v in scene["views"]]
+    des_host = [torch.from_numpy(v["des"]).pin_memory() for v in scene["views"]]
+    with torch.cuda.stream(ts):
+        kp_dev = [k.to("cuda", non_blocking=True) for k in kp_host]
+        des_dev = [d.to("cuda", non_blocking=True) for d in des_host]
+    ctx.sync()
+    h2d_bytes = sum(k.numel() * 4 + d.numel() * 4 for k, d in zip(kp_host, des_host))
+    input_bytes = h2d_bytes
+
+    def step(kps, dess, fetch: bool):
+        views = [pipeline.DeviceView(ctx, k, d) for k, d in zip(kps, dess)]      # K1b descriptor prep inside
+        chain = pipeline.RegistrationChain(ctx, K)
+        outs = chain.run(views, Rt0, Rt1)
+        d2h = 0
+        if fetch:                                                               # the step's result on the host
+            with torch.cuda.stream(ts):
+                clouds = [o["X_new"][:o["n_new"]].to("cpu", non_blocking=True) for o in outs]
+            ctx.sync()
+            d2h = sum(c.numel() * 4 for c in clouds) + len(outs) * (16 + 96)
+        return outs, d2h
+
+    registered = V - 2
+
+    def timed(kps, dess, fetch, steps):
+        barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = ctx.launch_count()
+        w0 = time.perf_counter()
+        e0.record(ts)
+        d2h = 0
+        for _ in range(steps):
+            _, d2h = step(kps, dess, fetch)
+        e1.record(ts)
+        torch.cuda.synchronize()
+        barrier()
+        wall = time.perf_counter() - w0
+        ms = e0.elapsed_time(e1)
+        return max_over_ranks(ms), wall, ctx.launch_count() - l0, d2h
+
+    for _ in range(args.warmup):
+        outs, _ = step(kp_dev, des_dev, False)
+    with ClockSampler(local) as cs:
+        ms, wall, launches, _ = timed(kp_dev, des_dev, False, args.steps)
+    value = world * registered * args.steps / (ms * 1e-3)
+    # end to end: pinned host buffers in, clouds + poses out, through the public API
+    step(kp_host, des_host, True)
+    ms_e2e, _, _, d2h_bytes = timed(kp_host, des_host, True, args.steps)
+    e2e = world * registered * args.steps / (ms_e2e * 1e-3)
+
+    # ---- per-kernel device time (CUDA events around every launch, same K steps) and the roofline
+    ctx.set_profiling(True)
+    ctx.reset_profile()
+    for _ in range(args.steps):
+        step(kp_dev, des_dev, False)
+    prof = ctx.profile()
+    ctx.set_profiling(False)
+    tot_ms = sum(p["ms"] for p in prof.values()) or 1.0
+    shares = {k: round(p["ms"] / tot_ms, 4) for k, p in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
+    per_launch_us = {k: round(1e3 * p["ms"] / p["launches"], 3) for k, p in prof.items()}
+    mt = prof.get("match_tc")
+    roofline = None
+    if mt:
+        flops = 2.0 * n * n * 128                                  # 2*Nq*Nt*128 per pair = per launch
+        t_launch = mt["ms"] * 1e-3 / mt["launches"]
+        ach = flops / t_launch / 1e12
+        roofline = {"kernel": "match_tc_kernel (K1 tcgen05 distance GEMM + top-2 epilogue)", "bound": "tensor",
+                    "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": ach / pk["bf16_sustained"],
+                    "traffic": None, "peak_source": pk["source"] + ", sustained bf16 (kernel timed inside a long step)",
+                    "algorithmic_flops_per_launch": flops, "avg_launch_us": 1e6 * t_launch, "launches": mt["launches"],
+                    "share_of_kernel_time": shares.get("match_tc")}
+
+    out = {
+        "metric": "views registered/sec (match+PnP+tri)", "value": value, "unit": "views/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16 tensor-core distances (exact on integer SIFT) + f64 geometry, f32 I/O",
+        "data": "synthetic",
+        "config": {"workload": f"synthetic {V} views x {n} desc: full incremental register (PnP+triangulate), BASELINE configs[2]",
+                   "views_registered_per_step": registered, "parallelism": "replicas (one scene per GPU)" if world > 1 else "1 GPU",
+                   "l2_policy": f"inputs larger than L2 ({input_bytes / 1e6:.0f} MB of descriptors+keypoints per step vs 126 MB L2)",
+                   "pnp_minimal_solver": "engine EPnP on GPU (throughput configuration)"},
+        "e2e": {"value": e2e, "unit": "views/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": launches, "wall_s": wall, "clocks": cs.summary,
+        "kernel_time_share": shares, "kernel_us_per_launch": per_launch_us, "roofline": roofline,
+    }
+
+    # ---- BA: GN iterations / s (configs[3]); points sharded over ranks, NCCL all-reduce of the reduced system
+    if not args.no_ba:
+        out["ba"] = bench_ba(args, ctx, world, rank, pk, barrier, max_over_ranks)
+
+    # ---- CPU baseline (rank 0, N = 1 only): the reference path on a bounded sample of the same scene
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        import cv2
+        nv = min(args.cpu_views, V)
+        cpu_register(scene, 4)
+        r, t = cpu_register(scene, nv)
+        out["cpu_baseline"] = {"value": r / t, "unit": "views/s", "cores": cv2.getNumThreads(), "kind": "port",
+                               "sample": f"first {nv} views of the same scene ({r} views registered, {t:.1f} s)",
+                               "host_cpus": os.cpu_count(), "cv2": cv2.__version__}
+    elif rank == 0:
+        out["cpu_baseline"] = None
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def bench_ba(args, ctx, world, rank, pk, barrier, max_over_ranks):
+    import torch
+    import torch.distributed as dist
+
+    import sfm_mvs_b200 as sfm
+    from sfm_mvs_b200 import synth
+
+    C_, P_, opp = args.ba_cams, args.ba_points, args.ba_obs_per_point
+    pb = synth.ba_problem(C_, P_, opp, seed=0)                      # identical on every rank
+    # shard by point (contiguous ranges; every point has opp observations, so ranges balance)
+    lo, hi = (P_ * rank) // world, (P_ * (rank + 1)) // world
+    osel = slice(lo * opp, hi * opp)
+    prob = sfm.BAProblem(ctx, C_, hi - lo, pb["cam_idx"][osel], pb["pt_idx"][osel] - lo, pb["obs"][osel], pb["K"],
+                         totals=(P_, P_ * opp))
+    prob.set_params(pb["cams0"], pb["pts0"][lo:hi])
+    if world > 1:
+        uid = [sfm.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        prob.comm_init(uid[0], rank, world)
+    ts = ctx.torch_stream()
+    O = prob.n_obs
+    # K5 materialised evaluation: the HBM-roofline kernel (96 B / observation)
+    with torch.cuda.stream(ts):
+        r = torch.empty((O, 2), dtype=torch.float32, device="cuda")
+        Jc = torch.empty((O, 2, 6), dtype=torch.float32, device="cuda")
+        Jp = torch.empty((O, 2, 3), dtype=torch.float32, device="cuda")
+        cost = torch.zeros((1,), dtype=torch.float64, device="cuda")
+        flush = torch.empty((256 << 20,), dtype=torch.uint8, device="cuda")
+    for _ in range(3):
+        prob.eval_into(0, r, Jc, Jp, cost)
+    ctx.sync()
+    ctx.set_profiling(True)
+    ctx.reset_profile()
+    reps = 10
+    for _ in range(reps):
+        with torch.cuda.stream(ts):
+            flush.zero_()                                            # flush L2 between timed launches (256 MB > 126 MB)
+        prob.eval_into(0, r, Jc, Jp, cost)
+    prof = ctx.profile()
+    ctx.set_profiling(False)
+    t_eval = prof["ba_eval"]["ms"] * 1e-3 / prof["ba_eval"]["launches"]
+    gbs = 96.0 * O / t_eval / 1e9
+    # GN iterations
+    lam = 1e-3
+    for _ in range(2):
+        lam = prob.gn_step(lam)["lambda_next"]
+    barrier()
+    torch.cuda.synchronize()
+    iters = 5
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(ts)
+    hist = []
+    for _ in range(iters):
+        st = prob.gn_step(lam)
+        lam = st["lambda_next"]
+        hist.append(st)
+    e1.record(ts)
+    torch.cuda.synchronize()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    ctx.set_profiling(True)
+    ctx.reset_profile()
+    prob.gn_step(lam)
+    prof2 = ctx.profile()
+    ctx.set_profiling(False)
+    res = {"metric": "BA GN-iters/sec", "value": iters / (ms * 1e-3), "unit": "iters/s", "ms_per_iter": ms / iters,
+           "config": {"workload": f"BA {C_} cams / {P_} points / {P_ * opp} obs synthetic, LM iterations, BASELINE configs[3]",
+                      "sharding": f"points over {world} rank(s); NCCL all-reduce of S|g|diag(Hcc) ({(6 * C_) ** 2 * 4 / 1e6:.0f} MB f32) per iteration"},
+           "cost_first": hist[0]["cost_before"], "cost_last": hist[-1]["cost_after"],
+           "accepted": [bool(h["accepted"]) for h in hist],
+           "iter_kernel_ms": {k: round(v["ms"], 3) for k, v in prof2.items()},
+           "roofline_eval": {"kernel": "ba_eval_kernel (K5 residual + Jacobian blocks, materialised)", "bound": "hbm",
+                             "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"], "traffic": None,
+                             "algorithmic_bytes_per_launch": 96.0 * O, "avg_launch_us": 1e6 * t_eval,
+                             "l2_policy": "256 MB flush between timed launches", "peak_source": pk["source"]}}
+    prob.close()
+    return res
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_engine(a)

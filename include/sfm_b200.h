@@ -151,6 +151,15 @@ int sfm_reproj_error(sfm_ctx* ctx, const float* X, int x_layout, const float* px
 int sfm_common_points(sfm_ctx* ctx, const float* pts1, int n1, const float* pts2, int n2,
                       int32_t* idx1, int32_t* idx2, int32_t* n_common, uint8_t* keep2);
 
+/* Device-side fancy indexing of the per-view loop (sfm.py:341-409), so that matched keypoints and
+ * 3-D points stay in HBM between the calls above.  Device pointers only.
+ *   dst[i,:] = src[idx[i],:]            (pts2[indx2], points_3d[indx1]           sfm.py:358-362)
+ *   a_out, b_out = a[keep], b[keep]     (temp_array1/2 = pts2[~mask], pts3[~mask] sfm.py:229-237), stable;
+ *   n_out may be a host pointer (synchronises) or a device pointer. */
+int sfm_gather_rows(sfm_ctx* ctx, const float* src, int width, const int32_t* idx, int n, float* dst);
+int sfm_compact_pairs(sfm_ctx* ctx, const float* a, const float* b, const uint8_t* keep, int n,
+                      float* a_out, float* b_out, int32_t* n_out);
+
 /* ------------------------------------------------------------------ hot path 3a: PnP-RANSAC
  * Replaces cv2.solvePnPRansac(X, p, K, d, ...) with OpenCV's defaults, which is what the
  * reference gets                                                sfm.py:67, test.py:319.

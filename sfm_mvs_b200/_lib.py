@@ -71,6 +71,8 @@ PROTOTYPES = {
     "sfm_triangulate": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _i, _i]),
     "sfm_reproj_error": (_i, [_vp, _vp, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "sfm_common_points": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp]),
+    "sfm_gather_rows": (_i, [_vp, _vp, _i, _vp, _i, _vp]),
+    "sfm_compact_pairs": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "sfm_pnp_score": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _f, _vp, _vp]),
     "sfm_pnp_ransac": (_i, [_vp, _vp, _vp, _i, _vp, _i, _f, _d, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sfm_pnp_ransac_hyp": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _f, _d, _vp, _vp, _vp, _vp, _vp, _vp]),

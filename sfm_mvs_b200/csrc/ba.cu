@@ -1,5 +1,5 @@
 // ba.cu — hot path 3b: bundle adjustment (K5 residual/Jacobian evaluation, K6 fused Schur
-// accumulation, reduced-camera-system solve, back-substitution / update).
+// accumulation, back-substitution / update; the reduced-camera-system solve is solve.cu).
 //
 // Reference: the residual every BA variant of the reference evaluates is
 //   cv2.projectPoints(X, rvec, tvec, K, None) - observation
@@ -21,12 +21,13 @@
 //   d(u,v)/dY = [[fx/z, 0, -fx Y.x/z^2], [0, fy/z, -fy Y.y/z^2]]
 //   Jc[:,0:3] = d(u,v)/dY * [ Jl e_k x Yr ]_k   (since dR/dr_k = [Jl e_k]x R),  Jc[:,3:6] = d(u,v)/dY
 //   Jp = d(u,v)/dY * R
-#include <dlfcn.h>
 #include <float.h>
+#include <stdlib.h>
 #include <math.h>
 
 #include "ba.cuh"
 #include "hostmath.h"
+#include "solve.cuh"
 
 namespace {
 
@@ -100,10 +101,13 @@ __device__ __forceinline__ double warp_sum_d(double v) {
 }
 
 // ------------------------------------------------------------------ K5: materialised evaluation
-// Persistent CTAs; the per-camera table (C x 21 doubles) is staged in shared memory once per CTA
-// when it fits, so the per-observation gather never leaves the SM.  One observation per thread:
-// 16 B read, 80 B written (r 8 B, Jc 48 B, Jp 24 B).
-template <int MODE, bool SMEM_CAMS>
+// Persistent CTAs, one observation per thread per trip: 16 B read (uv, cam index, point index),
+// 80 B written (r 8 B, Jc 48 B, Jp 24 B).  The per-camera table (C x 21 doubles) is staged in shared
+// memory once per CTA when SMEM_CAMS (otherwise it is read through L1).  With STAGE the 20 output
+// floats of a thread go through a per-warp shared-memory tile first (conflict-free 16 B / 8 B
+// shared stores at 48 B / 24 B stride) and leave the SM as fully coalesced 16-byte stores of
+// contiguous 256 / 1536 / 768-byte runs instead of 32 scattered 16-byte pieces per instruction.
+template <int MODE, bool SMEM_CAMS, bool STAGE>
 __global__ void __launch_bounds__(256) ba_eval_kernel(const float2* __restrict__ uv, const int* __restrict__ cam_idx,
                                                       const int* __restrict__ pt_idx, int n_obs,
                                                       const double* __restrict__ cam_pre, int n_cam,
@@ -111,37 +115,74 @@ __global__ void __launch_bounds__(256) ba_eval_kernel(const float2* __restrict__
                                                       float* __restrict__ r_out, float* __restrict__ Jc_out,
                                                       float* __restrict__ Jp_out, double* __restrict__ cost) {
   extern __shared__ double s_cam[];
+  __shared__ __align__(16) float s_stage[STAGE ? 8 : 1][STAGE ? 640 : 4];
   if (SMEM_CAMS) {
     for (int i = threadIdx.x; i < n_cam * CAM_PRE; i += blockDim.x) s_cam[i] = cam_pre[i];
     __syncthreads();
   }
   const double* cams = SMEM_CAMS ? s_cam : cam_pre;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double local = 0.0;
-  for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < n_obs; o += gridDim.x * blockDim.x) {
-    const float2 m = __ldg(uv + o);
-    const int c = __ldg(cam_idx + o), p = __ldg(pt_idx + o);
-    const double X[3] = {__ldg(pts + 3 * (size_t)p), __ldg(pts + 3 * (size_t)p + 1), __ldg(pts + 3 * (size_t)p + 2)};
-    double r[2], Jc[2][6], Jp[2][3];
-    if (MODE == 0) {
-      const bool want = (Jc_out != nullptr) || (Jp_out != nullptr);
-      if (want) obs_geometry<true>(cams + CAM_PRE * (size_t)c, X, m, K, r, Jc, Jp);
+  for (int o0 = blockIdx.x * blockDim.x + warp * 32; o0 < n_obs; o0 += gridDim.x * blockDim.x) {
+    const int o = o0 + lane;
+    const bool valid = o < n_obs;
+    double r[2] = {0, 0}, Jc[2][6], Jp[2][3];
+    if (valid) {
+      const float2 m = __ldg(uv + o);
+      const int c = __ldg(cam_idx + o), p = __ldg(pt_idx + o);
+      const double X[3] = {__ldg(pts + 3 * (size_t)p), __ldg(pts + 3 * (size_t)p + 1), __ldg(pts + 3 * (size_t)p + 2)};
+      if (MODE == 0 && (Jc_out != nullptr || Jp_out != nullptr)) obs_geometry<true>(cams + CAM_PRE * (size_t)c, X, m, K, r, Jc, Jp);
       else obs_geometry<false>(cams + CAM_PRE * (size_t)c, X, m, K, r, Jc, Jp);
+    }
+    if (MODE == 0) {
       local += r[0] * r[0] + r[1] * r[1];
-      if (r_out) reinterpret_cast<float2*>(r_out)[o] = make_float2((float)r[0], (float)r[1]);
-      if (Jc_out) {
-        float4* d = reinterpret_cast<float4*>(Jc_out + 12 * (size_t)o);
-        d[0] = make_float4((float)Jc[0][0], (float)Jc[0][1], (float)Jc[0][2], (float)Jc[0][3]);
-        d[1] = make_float4((float)Jc[0][4], (float)Jc[0][5], (float)Jc[1][0], (float)Jc[1][1]);
-        d[2] = make_float4((float)Jc[1][2], (float)Jc[1][3], (float)Jc[1][4], (float)Jc[1][5]);
+      const bool full = (o0 + 32 <= n_obs);
+      if (STAGE && full) {
+        float* st = s_stage[warp];
+        if (r_out) *reinterpret_cast<float2*>(st + 2 * lane) = make_float2((float)r[0], (float)r[1]);
+        if (Jc_out) {
+          float4* d = reinterpret_cast<float4*>(st + 64 + 12 * lane);
+          d[0] = make_float4((float)Jc[0][0], (float)Jc[0][1], (float)Jc[0][2], (float)Jc[0][3]);
+          d[1] = make_float4((float)Jc[0][4], (float)Jc[0][5], (float)Jc[1][0], (float)Jc[1][1]);
+          d[2] = make_float4((float)Jc[1][2], (float)Jc[1][3], (float)Jc[1][4], (float)Jc[1][5]);
+        }
+        if (Jp_out) {
+          float2* d = reinterpret_cast<float2*>(st + 448 + 6 * lane);
+          d[0] = make_float2((float)Jp[0][0], (float)Jp[0][1]);
+          d[1] = make_float2((float)Jp[0][2], (float)Jp[1][0]);
+          d[2] = make_float2((float)Jp[1][1], (float)Jp[1][2]);
+        }
+        __syncwarp();
+        const float4* s4 = reinterpret_cast<const float4*>(st);
+        if (r_out && lane < 16) reinterpret_cast<float4*>(r_out + 2 * (size_t)o0)[lane] = s4[lane];
+        if (Jc_out) {
+          float4* d = reinterpret_cast<float4*>(Jc_out + 12 * (size_t)o0);
+          d[lane] = s4[16 + lane];
+          d[lane + 32] = s4[48 + lane];
+          d[lane + 64] = s4[80 + lane];
+        }
+        if (Jp_out) {
+          float4* d = reinterpret_cast<float4*>(Jp_out + 6 * (size_t)o0);
+          d[lane] = s4[112 + lane];
+          if (lane < 16) d[lane + 32] = s4[144 + lane];
+        }
+        __syncwarp();
+      } else if (valid) {
+        if (r_out) reinterpret_cast<float2*>(r_out)[o] = make_float2((float)r[0], (float)r[1]);
+        if (Jc_out) {
+          float4* d = reinterpret_cast<float4*>(Jc_out + 12 * (size_t)o);
+          d[0] = make_float4((float)Jc[0][0], (float)Jc[0][1], (float)Jc[0][2], (float)Jc[0][3]);
+          d[1] = make_float4((float)Jc[0][4], (float)Jc[0][5], (float)Jc[1][0], (float)Jc[1][1]);
+          d[2] = make_float4((float)Jc[1][2], (float)Jc[1][3], (float)Jc[1][4], (float)Jc[1][5]);
+        }
+        if (Jp_out) {
+          float2* d = reinterpret_cast<float2*>(Jp_out + 6 * (size_t)o);
+          d[0] = make_float2((float)Jp[0][0], (float)Jp[0][1]);
+          d[1] = make_float2((float)Jp[0][2], (float)Jp[1][0]);
+          d[2] = make_float2((float)Jp[1][1], (float)Jp[1][2]);
+        }
       }
-      if (Jp_out) {
-        float2* d = reinterpret_cast<float2*>(Jp_out + 6 * (size_t)o);
-        d[0] = make_float2((float)Jp[0][0], (float)Jp[0][1]);
-        d[1] = make_float2((float)Jp[0][2], (float)Jp[1][0]);
-        d[2] = make_float2((float)Jp[1][1], (float)Jp[1][2]);
-      }
-    } else {
-      obs_geometry<false>(cams + CAM_PRE * (size_t)c, X, m, K, r, Jc, Jp);
+    } else if (valid) {
       if (MODE == 1) {        // ((p - proj)^2).ravel()/N            sfm.py:124-130
         double a = r[0] * r[0] * inv_n, b = r[1] * r[1] * inv_n;
         local += a * a + b * b;
@@ -156,7 +197,7 @@ __global__ void __launch_bounds__(256) ba_eval_kernel(const float2* __restrict__
   if (cost) {
     local = warp_sum_d(local);
     __shared__ double s_part[8];
-    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = local;
+    if (lane == 0) s_part[warp] = local;
     __syncthreads();
     if (threadIdx.x == 0) {
       double s = 0.0;
@@ -389,216 +430,8 @@ __global__ void ba_update_cams_kernel(const double* __restrict__ cams, const dou
   if ((threadIdx.x & 31) == 0 && d != 0.0) atomicAdd(step2, d);
 }
 
-// ------------------------------------------------------------------ dense SPD solve (float64)
-// Reduced camera system: n = 6C (3000 at C = 500).  Right-looking blocked Cholesky, NB = 64:
-//   chol_diag_kernel   factor the 64x64 diagonal block in shared memory (one CTA)
-//   chol_panel_kernel  L21 = A21 L11^-T, 64 rows per CTA
-//   chol_syrk_kernel   A22 -= L21 L21^T on the lower triangle, 64x64 tile per CTA, 4x4 per thread
-// followed by blocked forward / backward substitution.  A is n x n row-major, lower triangle used.
-constexpr int NB = 64;
-
-__global__ void __launch_bounds__(256) chol_diag_kernel(double* __restrict__ A, int n, int k0, int* __restrict__ info) {
-  __shared__ double s[NB][NB + 1];
-  const int nb = min(NB, n - k0);
-  for (int i = threadIdx.x; i < nb * nb; i += blockDim.x) {
-    int r = i / nb, c = i % nb;
-    s[r][c] = (c <= r) ? A[(size_t)(k0 + r) * n + k0 + c] : 0.0;
-  }
-  __syncthreads();
-  for (int j = 0; j < nb; ++j) {
-    if (threadIdx.x == 0) {
-      double d = s[j][j];
-      if (!(d > 0.0)) { if (*info == 0) *info = k0 + j + 1; d = 1.0; }   // not positive definite
-      s[j][j] = sqrt(d);
-    }
-    __syncthreads();
-    const double djj = s[j][j];
-    for (int i = j + 1 + threadIdx.x; i < nb; i += blockDim.x) s[i][j] /= djj;
-    __syncthreads();
-    // trailing update of the block: s[i][c] -= s[i][j]*s[c][j] for j < c <= i
-    for (int t = threadIdx.x; t < (nb - j - 1) * (nb - j - 1); t += blockDim.x) {
-      int i = j + 1 + t / (nb - j - 1), c = j + 1 + t % (nb - j - 1);
-      if (c <= i) s[i][c] -= s[i][j] * s[c][j];
-    }
-    __syncthreads();
-  }
-  for (int i = threadIdx.x; i < nb * nb; i += blockDim.x) {
-    int r = i / nb, c = i % nb;
-    if (c <= r) A[(size_t)(k0 + r) * n + k0 + c] = s[r][c];
-  }
-}
-
-__global__ void __launch_bounds__(NB) chol_panel_kernel(double* __restrict__ A, int n, int k0) {
-  __shared__ double L[NB][NB + 1];
-  const int nb = min(NB, n - k0);
-  for (int i = threadIdx.x; i < nb * nb; i += blockDim.x) {
-    int r = i / nb, c = i % nb;
-    L[r][c] = (c <= r) ? A[(size_t)(k0 + r) * n + k0 + c] : 0.0;
-  }
-  __syncthreads();
-  const int row = k0 + nb + blockIdx.x * NB + threadIdx.x;
-  if (row >= n) return;
-  double x[NB];
-  double* a = A + (size_t)row * n + k0;
-#pragma unroll 8
-  for (int j = 0; j < NB; ++j) x[j] = (j < nb) ? a[j] : 0.0;
-  // solve x L^T = a  ->  x[j] = (a[j] - sum_{k<j} x[k] L[j][k]) / L[j][j]
-#pragma unroll
-  for (int j = 0; j < NB; ++j) {
-    if (j < nb) {
-      double s = x[j];
-#pragma unroll
-      for (int k = 0; k < j; ++k) s -= x[k] * L[j][k];
-      x[j] = s / L[j][j];
-    }
-  }
-#pragma unroll 8
-  for (int j = 0; j < NB; ++j)
-    if (j < nb) a[j] = x[j];
-}
-
-// C[i][j] -= sum_k P[i][k] P[j][k], P = A[:, k0:k0+nb]; tiles (ti >= tj) of the trailing matrix
-__global__ void __launch_bounds__(256) chol_syrk_kernel(double* __restrict__ A, int n, int k0, int nb) {
-  constexpr int KC = 32;
-  __shared__ double Pi[NB][KC + 1];
-  __shared__ double Pj[NB][KC + 1];
-  // decode lower-triangular tile index
-  int t = blockIdx.x;
-  int ti = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
-  while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
-  while (ti * (ti + 1) / 2 > t) --ti;
-  const int tj = t - ti * (ti + 1) / 2;
-  const int base = k0 + nb;
-  const int i0 = base + ti * NB, j0 = base + tj * NB;
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  double acc[4][4];
-#pragma unroll
-  for (int a = 0; a < 4; ++a)
-#pragma unroll
-    for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
-  for (int kc = 0; kc < nb; kc += KC) {
-    __syncthreads();
-    for (int e = threadIdx.x; e < NB * KC; e += blockDim.x) {
-      int r = e / KC, c = e % KC;
-      Pi[r][c] = (i0 + r < n && kc + c < nb) ? A[(size_t)(i0 + r) * n + k0 + kc + c] : 0.0;
-      Pj[r][c] = (j0 + r < n && kc + c < nb) ? A[(size_t)(j0 + r) * n + k0 + kc + c] : 0.0;
-    }
-    __syncthreads();
-#pragma unroll 8
-    for (int k = 0; k < KC; ++k) {
-      double av[4], bv[4];
-#pragma unroll
-      for (int a = 0; a < 4; ++a) av[a] = Pi[ty + 16 * a][k];
-#pragma unroll
-      for (int b = 0; b < 4; ++b) bv[b] = Pj[tx + 16 * b][k];
-#pragma unroll
-      for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) acc[a][b] += av[a] * bv[b];
-    }
-  }
-#pragma unroll
-  for (int a = 0; a < 4; ++a)
-#pragma unroll
-    for (int b = 0; b < 4; ++b) {
-      int i = i0 + ty + 16 * a, j = j0 + tx + 16 * b;
-      if (i < n && j < n && j <= i) A[(size_t)i * n + j] -= acc[a][b];
-    }
-}
-
-// Blocked triangular solves with the factor L (lower, row-major):  L y = b  then  L^T x = y.
-__global__ void __launch_bounds__(NB) trsv_diag_kernel(const double* __restrict__ A, int n, int k0, double* __restrict__ x,
-                                                       int transpose) {
-  __shared__ double L[NB][NB + 1];
-  __shared__ double v[NB];
-  const int nb = min(NB, n - k0);
-  for (int i = threadIdx.x; i < nb * nb; i += blockDim.x) {
-    int r = i / nb, c = i % nb;
-    L[r][c] = (c <= r) ? A[(size_t)(k0 + r) * n + k0 + c] : 0.0;
-  }
-  if (threadIdx.x < nb) v[threadIdx.x] = x[k0 + threadIdx.x];
-  __syncthreads();
-  if (!transpose) {
-    for (int j = 0; j < nb; ++j) {
-      if (threadIdx.x == 0) v[j] /= L[j][j];
-      __syncthreads();
-      if ((int)threadIdx.x > j && (int)threadIdx.x < nb) v[threadIdx.x] -= L[threadIdx.x][j] * v[j];
-      __syncthreads();
-    }
-  } else {
-    for (int j = nb - 1; j >= 0; --j) {
-      if (threadIdx.x == 0) v[j] /= L[j][j];
-      __syncthreads();
-      if ((int)threadIdx.x < j) v[threadIdx.x] -= L[j][threadIdx.x] * v[j];
-      __syncthreads();
-    }
-  }
-  if (threadIdx.x < nb) x[k0 + threadIdx.x] = v[threadIdx.x];
-}
-
-// forward: x[i] -= sum_{c in block} L[i][k0+c] x[k0+c] for i >= k0+nb   (one warp per row)
-// backward: x[i] -= sum_{r in block} L[k0+r][i] x[k0+r] for i < k0        (one thread per column)
-__global__ void __launch_bounds__(256) trsv_update_kernel(const double* __restrict__ A, int n, int k0, int nb,
-                                                         double* __restrict__ x, int transpose) {
-  if (!transpose) {
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    const int i = k0 + nb + warp;
-    if (i >= n) return;
-    double s = 0.0;
-    for (int c = lane; c < nb; c += 32) s += A[(size_t)i * n + k0 + c] * x[k0 + c];
-    s = warp_sum_d(s);
-    if (lane == 0) x[i] -= s;
-  } else {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= k0) return;
-    double s = 0.0;
-    for (int r = 0; r < nb; ++r) s += A[(size_t)(k0 + r) * n + i] * x[k0 + r];
-    x[i] -= s;
-  }
-}
-
-__global__ void ba_widen_kernel(const float* __restrict__ S, const float* __restrict__ g, int n, double* __restrict__ A,
-                                double* __restrict__ rhs) {
-  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  size_t total = (size_t)n * n;
-  if (idx < total) {
-    int r = (int)(idx / n), c = (int)(idx % n);
-    A[idx] = (c <= r) ? (double)S[idx] : 0.0;
-  }
-  if (idx < (size_t)n) rhs[idx] = -(double)g[idx];
-}
-
 int solve_reduced_system(sfm_ba* ba) {
-  sfm_ctx* ctx = ba->ctx;
-  const int n = 6 * ba->n_cam;
-  size_t total = (size_t)n * n;
-  SFM_LAUNCH(ctx, SFM_K_BA_SOLVE, (ba_widen_kernel<<<(unsigned)div_up64((int64_t)total, 256), 256, 0, ctx->stream>>>(
-                                      ba->S, ba->g, n, ba->A64, ba->dc)));
-  SFM_CUDA(cudaMemsetAsync(ba->info, 0, sizeof(int), ctx->stream));
-  for (int k0 = 0; k0 < n; k0 += NB) {
-    const int nb = std::min(NB, n - k0);
-    SFM_LAUNCH(ctx, SFM_K_BA_SOLVE, (chol_diag_kernel<<<1, 256, 0, ctx->stream>>>(ba->A64, n, k0, ba->info)));
-    const int rest = n - k0 - nb;
-    if (rest > 0) {
-      SFM_LAUNCH(ctx, SFM_K_BA_SOLVE, (chol_panel_kernel<<<div_up(rest, NB), NB, 0, ctx->stream>>>(ba->A64, n, k0)));
-      const int tiles = div_up(rest, NB);
-      SFM_LAUNCH(ctx, SFM_K_BA_SOLVE, (chol_syrk_kernel<<<tiles * (tiles + 1) / 2, 256, 0, ctx->stream>>>(ba->A64, n, k0, nb)));
-    }
-  }
-  for (int k0 = 0; k0 < n; k0 += NB) {
-    const int nb = std::min(NB, n - k0);
-    SFM_LAUNCH(ctx, SFM_K_BA_SOLVE, (trsv_diag_kernel<<<1, NB, 0, ctx->stream>>>(ba->A64, n, k0, ba->dc, 0)));
-    const int rest = n - k0 - nb;
-    if (rest > 0)
-      SFM_LAUNCH(ctx, SFM_K_BA_SOLVE, (trsv_update_kernel<<<div_up(rest * 32, 256), 256, 0, ctx->stream>>>(ba->A64, n, k0, nb, ba->dc, 0)));
-  }
-  for (int k0 = ((n - 1) / NB) * NB; k0 >= 0; k0 -= NB) {
-    const int nb = std::min(NB, n - k0);
-    SFM_LAUNCH(ctx, SFM_K_BA_SOLVE, (trsv_diag_kernel<<<1, NB, 0, ctx->stream>>>(ba->A64, n, k0, ba->dc, 1)));
-    if (k0 > 0)
-      SFM_LAUNCH(ctx, SFM_K_BA_SOLVE, (trsv_update_kernel<<<div_up(k0, 256), 256, 0, ctx->stream>>>(ba->A64, n, k0, nb, ba->dc, 1)));
-  }
-  return SFM_OK;
+  return sfm_spd_solve(ba->ctx, ba->S, ba->g, 6 * ba->n_cam, ba->A64, ba->dc, ba->info);
 }
 
 Intr make_intr(const sfm_ba* ba) {
@@ -613,31 +446,42 @@ int cam_prep(sfm_ba* ba, const double* cams) {
   return SFM_OK;
 }
 
-// cost-only evaluation at (cams, pts): *cost_dev += 0.5 sum r^2
+// evaluation at (cams already in cam_pre, pts): *cost_dev += 0.5 sum r^2.
+// SFM_BA_EVAL_VARIANT (diagnostic): bit0 = stage outputs through shared memory, bit1 = camera table
+// through L1 instead of shared memory.  Default 1.
+template <int MODE, bool SM, bool ST>
+int launch_eval_v(sfm_ba* ba, const double* pts, float* r, float* Jc, float* Jp, double* cost_dev, int ctas_per_sm) {
+  sfm_ctx* ctx = ba->ctx;
+  const size_t smem = SM ? cam_smem_bytes(ba) : 0;
+  const double inv_n = 1.0 / (double)(ba->n_obs_total > 0 ? ba->n_obs_total : 1);
+  int grid = std::max(1, std::min(div_up(ba->n_obs, 256), ctx->sm_count * ctas_per_sm));
+  if (SM) {
+    static bool attr = false;
+    if (!attr) {
+      SFM_CUDA(cudaFuncSetAttribute(ba_eval_kernel<MODE, SM, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      attr = true;
+    }
+  }
+  SFM_LAUNCH(ctx, SFM_K_BA_EVAL, (ba_eval_kernel<MODE, SM, ST><<<grid, 256, smem, ctx->stream>>>(
+                                     ba->uv, ba->cam_idx, ba->pt_idx, ba->n_obs, ba->cam_pre, ba->n_cam, pts,
+                                     make_intr(ba), inv_n, r, Jc, Jp, cost_dev)));
+  return SFM_OK;
+}
+
 template <int MODE>
 int launch_eval(sfm_ba* ba, const double* pts, float* r, float* Jc, float* Jp, double* cost_dev) {
-  sfm_ctx* ctx = ba->ctx;
-  const size_t smem = cam_smem_bytes(ba);
-  const bool in_smem = smem <= 96 * 1024;
-  const double inv_n = 1.0 / (double)(ba->n_obs_total > 0 ? ba->n_obs_total : 1);
-  int grid = std::min(div_up(ba->n_obs, 256), ctx->sm_count * 2);
-  if (grid < 1) grid = 1;
-  if (in_smem) {
-    static bool attr[3] = {false, false, false};
-    if (!attr[MODE]) {
-      SFM_CUDA(cudaFuncSetAttribute(ba_eval_kernel<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-      attr[MODE] = true;
-    }
-    SFM_LAUNCH(ctx, SFM_K_BA_EVAL, (ba_eval_kernel<MODE, true><<<grid, 256, smem, ctx->stream>>>(
-                                       ba->uv, ba->cam_idx, ba->pt_idx, ba->n_obs, ba->cam_pre, ba->n_cam, pts,
-                                       make_intr(ba), inv_n, r, Jc, Jp, cost_dev)));
-  } else {
-    grid = std::max(1, std::min(div_up(ba->n_obs, 256), ctx->sm_count * 8));
-    SFM_LAUNCH(ctx, SFM_K_BA_EVAL, (ba_eval_kernel<MODE, false><<<grid, 256, 0, ctx->stream>>>(
-                                       ba->uv, ba->cam_idx, ba->pt_idx, ba->n_obs, ba->cam_pre, ba->n_cam, pts,
-                                       make_intr(ba), inv_n, r, Jc, Jp, cost_dev)));
+  static int variant = -1;
+  if (variant < 0) {
+    const char* e = getenv("SFM_BA_EVAL_VARIANT");
+    variant = e ? atoi(e) : 1;
   }
-  return SFM_OK;
+  const bool fits = cam_smem_bytes(ba) <= 96 * 1024;
+  const bool sm = fits && !(variant & 2);
+  const bool st = (variant & 1) && MODE == 0;
+  if (sm && st) return launch_eval_v<MODE, true, true>(ba, pts, r, Jc, Jp, cost_dev, 2);
+  if (sm && !st) return launch_eval_v<MODE, true, false>(ba, pts, r, Jc, Jp, cost_dev, 2);
+  if (!sm && st) return launch_eval_v<MODE, false, true>(ba, pts, r, Jc, Jp, cost_dev, 4);
+  return launch_eval_v<MODE, false, false>(ba, pts, r, Jc, Jp, cost_dev, 4);
 }
 
 int build_system(sfm_ba* ba, double lambda) {
@@ -750,7 +594,7 @@ extern "C" int sfm_ba_create(sfm_ctx* ctx, int n_cam, int n_pt, int n_obs, const
   A((void**)&ba->pts_new, sizeof(double) * 3 * (size_t)n_pt);
   A((void**)&ba->cam_pre, sizeof(double) * CAM_PRE * (size_t)n_cam);
   A((void**)&ba->S, sizeof(float) * ba->sys_count);
-  A((void**)&ba->A64, sizeof(double) * (size_t)n * n);
+  A((void**)&ba->A64, sizeof(double) * ((size_t)n + 1) * n);
   A((void**)&ba->dc, sizeof(double) * (size_t)n);
   A((void**)&ba->scal, sizeof(double) * 8);
   A((void**)&ba->info, sizeof(int));

@@ -59,7 +59,10 @@ struct sfm_ctx {
   // persistent zero-initialised device words for last-block-done reductions (self-resetting)
   unsigned int* counters = nullptr;
   double* dscratch = nullptr;       // 64 doubles of persistent device scratch
+  std::vector<void*> desc_pool;     // recycled DescBuf storage (match.cu)
 };
+
+void sfm_desc_pool_free(sfm_ctx* c);   // match.cu
 
 // ---- workspace -------------------------------------------------------------------------
 int sfm_ws_begin(sfm_ctx* c);                         // start of an API call: reset bump pointers

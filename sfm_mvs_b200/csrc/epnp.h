@@ -189,14 +189,10 @@ HM_HD inline void epnp_gauss_newton(const double* L, const double* rho, double* 
   }
 }
 
-// pw (n,3) object points, us (n,2) pixel coordinates (already passed through the float32
-// normalise / de-normalise round trip OpenCV applies), work: 7*n doubles of scratch.
-// Returns R (row-major 3x3), t.
-HM_HD inline void epnp_solve(const double* pw, const double* us, int n, const EpnpCam& cam, double* work,
-                             double* R, double* t) {
-  double* alphas = work;            // n x 4
-  // ---- control points
-  double cws[4][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+// ---- stage 1: control points, barycentric coordinates, M^T M.  alphas: n x 4 scratch.
+HM_HD inline void epnp_build(const double* pw, const double* us, int n, const EpnpCam& cam, double* alphas,
+                             double (*cws)[3], double* MtM) {
+  for (int k = 0; k < 3; ++k) cws[0][k] = 0.0;
   for (int i = 0; i < n; ++i)
     for (int k = 0; k < 3; ++k) cws[0][k] += pw[3 * i + k];
   for (int k = 0; k < 3; ++k) cws[0][k] /= n;
@@ -214,7 +210,7 @@ HM_HD inline void epnp_solve(const double* pw, const double* us, int n, const Ep
     double k = sqrt(lam / n);
     for (int j = 0; j < 3; ++j) cws[i][j] = cws[0][j] + k * uct[3 * e + j];
   }
-  // ---- barycentric coordinates: inverse of CC = [c1-c0 | c2-c0 | c3-c0]
+  // barycentric coordinates: inverse of CC = [c1-c0 | c2-c0 | c3-c0]
   double cc[9], ci[9];
   for (int i = 0; i < 3; ++i)
     for (int j = 1; j < 4; ++j) cc[3 * i + j - 1] = cws[j][i] - cws[0][i];
@@ -232,8 +228,6 @@ HM_HD inline void epnp_solve(const double* pw, const double* us, int n, const Ep
     for (int j = 0; j < 3; ++j) a[1 + j] = ci[3 * j] * d[0] + ci[3 * j + 1] * d[1] + ci[3 * j + 2] * d[2];
     a[0] = 1.0 - a[1] - a[2] - a[3];
   }
-  // ---- M^T M
-  double MtM[144];
   for (int i = 0; i < 144; ++i) MtM[i] = 0.0;
   for (int i = 0; i < n; ++i) {
     const double* a = alphas + 4 * i;
@@ -247,82 +241,103 @@ HM_HD inline void epnp_solve(const double* pw, const double* us, int n, const Ep
   }
   for (int r = 0; r < 12; ++r)
     for (int c = 0; c < r; ++c) MtM[12 * r + c] = MtM[12 * c + r];
-  double w12[12], V12[144];
-  eig_sym<12>(MtM, w12, V12);
-  const double* v[4] = {V12, V12 + 12, V12 + 24, V12 + 36};   // v[0] = smallest eigenvalue
-  // ---- L (6x10) and rho
-  double L[60], rho[6];
-  {
-    double dv[4][6][3];
-    for (int i = 0; i < 4; ++i) {
-      int a = 0, b = 1;
-      for (int j = 0; j < 6; ++j) {
-        for (int k = 0; k < 3; ++k) dv[i][j][k] = v[i][3 * a + k] - v[i][3 * b + k];
-        if (++b > 3) { ++a; b = a + 1; }
-      }
-    }
-    for (int i = 0; i < 6; ++i) {
-      double* row = L + 10 * i;
-      row[0] = epnp_dot3(dv[0][i], dv[0][i]);
-      row[1] = 2.0 * epnp_dot3(dv[0][i], dv[1][i]);
-      row[2] = epnp_dot3(dv[1][i], dv[1][i]);
-      row[3] = 2.0 * epnp_dot3(dv[0][i], dv[2][i]);
-      row[4] = 2.0 * epnp_dot3(dv[1][i], dv[2][i]);
-      row[5] = epnp_dot3(dv[2][i], dv[2][i]);
-      row[6] = 2.0 * epnp_dot3(dv[0][i], dv[3][i]);
-      row[7] = 2.0 * epnp_dot3(dv[1][i], dv[3][i]);
-      row[8] = 2.0 * epnp_dot3(dv[2][i], dv[3][i]);
-      row[9] = epnp_dot3(dv[3][i], dv[3][i]);
-    }
+}
+
+// ---- stage 2 (after the eigen-decomposition): L (6x10) and rho from the four null-space vectors
+HM_HD inline void epnp_L_rho(const double* const v[4], const double (*cws)[3], double* L, double* rho) {
+  double dv[4][6][3];
+  for (int i = 0; i < 4; ++i) {
     int a = 0, b = 1;
     for (int j = 0; j < 6; ++j) {
-      double s = 0.0;
-      for (int k = 0; k < 3; ++k) { double d = cws[a][k] - cws[b][k]; s += d * d; }
-      rho[j] = s;
+      for (int k = 0; k < 3; ++k) dv[i][j][k] = v[i][3 * a + k] - v[i][3 * b + k];
       if (++b > 3) { ++a; b = a + 1; }
     }
   }
-  // ---- three initialisations, Gauss-Newton, pick the best
-  double Rs[3][9], ts[3][3], errs[3];
-  for (int ap = 0; ap < 3; ++ap) {
-    double betas[4] = {0, 0, 0, 0};
-    if (ap == 0) {          // [B11 B12 B13 B14]
-      double A[24], r[6], b4[4];
-      for (int i = 0; i < 6; ++i) {
-        A[4 * i] = L[10 * i]; A[4 * i + 1] = L[10 * i + 1]; A[4 * i + 2] = L[10 * i + 3]; A[4 * i + 3] = L[10 * i + 6];
-        r[i] = rho[i];
-      }
-      ls_solve<6, 4>(A, r, b4);
-      if (b4[0] < 0) { betas[0] = sqrt(-b4[0]); betas[1] = -b4[1] / betas[0]; betas[2] = -b4[2] / betas[0]; betas[3] = -b4[3] / betas[0]; }
-      else { betas[0] = sqrt(b4[0]); betas[1] = b4[1] / betas[0]; betas[2] = b4[2] / betas[0]; betas[3] = b4[3] / betas[0]; }
-    } else if (ap == 1) {   // [B11 B12 B22]
-      double A[18], r[6], b3[3];
-      for (int i = 0; i < 6; ++i) {
-        A[3 * i] = L[10 * i]; A[3 * i + 1] = L[10 * i + 1]; A[3 * i + 2] = L[10 * i + 2];
-        r[i] = rho[i];
-      }
-      ls_solve<6, 3>(A, r, b3);
-      if (b3[0] < 0) { betas[0] = sqrt(-b3[0]); betas[1] = (b3[2] < 0) ? sqrt(-b3[2]) : 0.0; }
-      else { betas[0] = sqrt(b3[0]); betas[1] = (b3[2] > 0) ? sqrt(b3[2]) : 0.0; }
-      if (b3[1] < 0) betas[0] = -betas[0];
-    } else {                // [B11 B12 B22 B13 B23]
-      double A[30], r[6], b5[5];
-      for (int i = 0; i < 6; ++i) {
-        for (int k = 0; k < 5; ++k) A[5 * i + k] = L[10 * i + k];
-        r[i] = rho[i];
-      }
-      ls_solve<6, 5>(A, r, b5);
-      if (b5[0] < 0) { betas[0] = sqrt(-b5[0]); betas[1] = (b5[2] < 0) ? sqrt(-b5[2]) : 0.0; }
-      else { betas[0] = sqrt(b5[0]); betas[1] = (b5[2] > 0) ? sqrt(b5[2]) : 0.0; }
-      if (b5[1] < 0) betas[0] = -betas[0];
-      betas[2] = b5[3] / betas[0];
-    }
-    epnp_gauss_newton(L, rho, betas);
-    errs[ap] = epnp_pose_from_betas(v, betas, alphas, pw, us, n, cam, Rs[ap], ts[ap]);
+  for (int i = 0; i < 6; ++i) {
+    double* row = L + 10 * i;
+    row[0] = epnp_dot3(dv[0][i], dv[0][i]);
+    row[1] = 2.0 * epnp_dot3(dv[0][i], dv[1][i]);
+    row[2] = epnp_dot3(dv[1][i], dv[1][i]);
+    row[3] = 2.0 * epnp_dot3(dv[0][i], dv[2][i]);
+    row[4] = 2.0 * epnp_dot3(dv[1][i], dv[2][i]);
+    row[5] = epnp_dot3(dv[2][i], dv[2][i]);
+    row[6] = 2.0 * epnp_dot3(dv[0][i], dv[3][i]);
+    row[7] = 2.0 * epnp_dot3(dv[1][i], dv[3][i]);
+    row[8] = 2.0 * epnp_dot3(dv[2][i], dv[3][i]);
+    row[9] = epnp_dot3(dv[3][i], dv[3][i]);
   }
+  int a = 0, b = 1;
+  for (int j = 0; j < 6; ++j) {
+    double s = 0.0;
+    for (int k = 0; k < 3; ++k) { double d = cws[a][k] - cws[b][k]; s += d * d; }
+    rho[j] = s;
+    if (++b > 3) { ++a; b = a + 1; }
+  }
+}
+
+// ---- stage 3: one of the three beta initialisations (ap = 0: N=4 linearised, 1: N=2, 2: N=3),
+// Gauss-Newton, pose, mean reprojection error.
+HM_HD inline double epnp_candidate(int ap, const double* L, const double* rho, const double* const v[4],
+                                   const double* alphas, const double* pw, const double* us, int n,
+                                   const EpnpCam& cam, double* R, double* t) {
+  double betas[4] = {0, 0, 0, 0};
+  if (ap == 0) {          // [B11 B12 B13 B14]
+    double A[24], r[6], b4[4];
+    for (int i = 0; i < 6; ++i) {
+      A[4 * i] = L[10 * i]; A[4 * i + 1] = L[10 * i + 1]; A[4 * i + 2] = L[10 * i + 3]; A[4 * i + 3] = L[10 * i + 6];
+      r[i] = rho[i];
+    }
+    ls_solve<6, 4>(A, r, b4);
+    if (b4[0] < 0) { betas[0] = sqrt(-b4[0]); betas[1] = -b4[1] / betas[0]; betas[2] = -b4[2] / betas[0]; betas[3] = -b4[3] / betas[0]; }
+    else { betas[0] = sqrt(b4[0]); betas[1] = b4[1] / betas[0]; betas[2] = b4[2] / betas[0]; betas[3] = b4[3] / betas[0]; }
+  } else if (ap == 1) {   // [B11 B12 B22]
+    double A[18], r[6], b3[3];
+    for (int i = 0; i < 6; ++i) {
+      A[3 * i] = L[10 * i]; A[3 * i + 1] = L[10 * i + 1]; A[3 * i + 2] = L[10 * i + 2];
+      r[i] = rho[i];
+    }
+    ls_solve<6, 3>(A, r, b3);
+    if (b3[0] < 0) { betas[0] = sqrt(-b3[0]); betas[1] = (b3[2] < 0) ? sqrt(-b3[2]) : 0.0; }
+    else { betas[0] = sqrt(b3[0]); betas[1] = (b3[2] > 0) ? sqrt(b3[2]) : 0.0; }
+    if (b3[1] < 0) betas[0] = -betas[0];
+  } else {                // [B11 B12 B22 B13 B23]
+    double A[30], r[6], b5[5];
+    for (int i = 0; i < 6; ++i) {
+      for (int k = 0; k < 5; ++k) A[5 * i + k] = L[10 * i + k];
+      r[i] = rho[i];
+    }
+    ls_solve<6, 5>(A, r, b5);
+    if (b5[0] < 0) { betas[0] = sqrt(-b5[0]); betas[1] = (b5[2] < 0) ? sqrt(-b5[2]) : 0.0; }
+    else { betas[0] = sqrt(b5[0]); betas[1] = (b5[2] > 0) ? sqrt(b5[2]) : 0.0; }
+    if (b5[1] < 0) betas[0] = -betas[0];
+    betas[2] = b5[3] / betas[0];
+  }
+  epnp_gauss_newton(L, rho, betas);
+  return epnp_pose_from_betas(v, betas, alphas, pw, us, n, cam, R, t);
+}
+
+// OpenCV's selection among the three candidates: N=1; if e2 < e1 N=2; if e3 < e_N N=3 (NaN never wins)
+HM_HD inline int epnp_pick(const double* errs) {
   int N = 0;
   if (errs[1] < errs[0]) N = 1;
   if (errs[2] < errs[N]) N = 2;
+  return N;
+}
+
+// Serial solver (host utility sfm_epnp; also usable in a single device thread).
+// pw (n,3) object points, us (n,2) pixel coordinates (already passed through the float32
+// normalise / de-normalise round trip OpenCV applies), work: 4*n doubles of scratch.
+HM_HD inline void epnp_solve(const double* pw, const double* us, int n, const EpnpCam& cam, double* work,
+                             double* R, double* t) {
+  double* alphas = work;
+  double cws[4][3], MtM[144], w12[12], V12[144], L[60], rho[6];
+  epnp_build(pw, us, n, cam, alphas, cws, MtM);
+  eig_sym<12>(MtM, w12, V12);
+  const double* v[4] = {V12, V12 + 12, V12 + 24, V12 + 36};   // v[0] = smallest eigenvalue
+  epnp_L_rho(v, cws, L, rho);
+  double Rs[3][9], ts[3][3], errs[3];
+  for (int ap = 0; ap < 3; ++ap) errs[ap] = epnp_candidate(ap, L, rho, v, alphas, pw, us, n, cam, Rs[ap], ts[ap]);
+  int N = epnp_pick(errs);
   for (int k = 0; k < 9; ++k) R[k] = Rs[N][k];
   for (int k = 0; k < 3; ++k) t[k] = ts[N][k];
 }

@@ -48,8 +48,8 @@ int sfm_match_finalize(sfm_ctx* ctx, const mkey_t* cand, int nq, int nt, int nsp
 }
 
 // ------------------------------------------------------------------ descriptors
-// Copies / converts the descriptors to a float32 row-major resident copy and raises `flag` when
-// a value is not an integer in [0,255] (then only the fp32 kernel may be used).
+// Generic ingest (dim != 128): float32 resident copy + integrality flag.  dim == 128 uses the fused
+// K1b kernel in match_tc.cu, which also writes the tensor-core operand image in the same pass.
 template <typename T>
 __global__ void __launch_bounds__(256) desc_ingest_kernel(const T* __restrict__ src, size_t count,
                                                            float* __restrict__ dst,
@@ -65,70 +65,130 @@ __global__ void __launch_bounds__(256) desc_ingest_kernel(const T* __restrict__ 
   if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1u);
 }
 
+static void descbuf_free(DescBuf* b) {
+  if (!b) return;
+  if (b->f32) cudaFree(b->f32);
+  if (b->tiles) cudaFree(b->tiles);
+  if (b->sqnorm) cudaFree(b->sqnorm);
+  if (b->flag) cudaFree(b->flag);
+  if (b->hflag) cudaFreeHost(b->hflag);
+  if (b->ready) cudaEventDestroy(b->ready);
+  delete b;
+}
+
+void sfm_desc_pool_free(sfm_ctx* c) {
+  for (void* p : c->desc_pool) descbuf_free((DescBuf*)p);
+  c->desc_pool.clear();
+}
+
+static int descbuf_acquire(sfm_ctx* ctx, int n, int dim, DescBuf** out) {
+  size_t need = ((size_t)(n > 0 ? n : 1) + 255) & ~(size_t)255;
+  for (size_t i = 0; i < ctx->desc_pool.size(); ++i) {
+    DescBuf* b = (DescBuf*)ctx->desc_pool[i];
+    if (b->dim == dim && b->cap_rows >= need && b->cap_rows <= 2 * need) {
+      ctx->desc_pool.erase(ctx->desc_pool.begin() + i);
+      *out = b;
+      return SFM_OK;
+    }
+  }
+  DescBuf* b = new DescBuf();
+  b->cap_rows = need;
+  b->dim = dim;
+  cudaError_t e = cudaMalloc(&b->f32, need * dim * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&b->flag, sizeof(unsigned int));
+  if (e == cudaSuccess) e = cudaMallocHost(&b->hflag, sizeof(unsigned int));
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ready, cudaEventDisableTiming);
+  if (e == cudaSuccess && dim == 128) {
+    e = cudaMalloc(&b->tiles, (need / 128) * (size_t)40960);
+    if (e == cudaSuccess) e = cudaMalloc(&b->sqnorm, need * sizeof(float));
+  }
+  if (e != cudaSuccess) {
+    sfm_set_error("descriptor storage: %s", cudaGetErrorString(e));
+    descbuf_free(b);
+    return SFM_ERR_NOMEM;
+  }
+  *out = b;
+  return SFM_OK;
+}
+
 extern "C" int sfm_desc_create(sfm_ctx* ctx, const void* data, int dtype, int n, int dim, sfm_desc** out) {
   SFM_REQUIRE(ctx && out, "sfm_desc_create: null argument");
   SFM_REQUIRE(dtype == 0 || dtype == 1, "sfm_desc_create: dtype must be 0 (float32) or 1 (uint8); cv2 rejects others too");
   SFM_REQUIRE(n >= 0 && dim > 0, "sfm_desc_create: bad shape (%d,%d)", n, dim);
   SFM_REQUIRE(n == 0 || data, "sfm_desc_create: null data");
   SFM_TRY(sfm_ws_begin(ctx));
+  DescBuf* b = nullptr;
+  SFM_TRY(descbuf_acquire(ctx, n, dim, &b));
   sfm_desc* d = new sfm_desc();
-  d->ctx = ctx; d->n = n; d->dim = dim;
-  size_t count = (size_t)n * dim;
-  cudaError_t e = cudaMalloc(&d->f32, (count ? count : 1) * sizeof(float));
-  if (e == cudaSuccess) e = cudaMalloc(&d->flag, sizeof(unsigned int));
-  if (e != cudaSuccess) {
-    sfm_set_error("sfm_desc_create: cudaMalloc failed: %s", cudaGetErrorString(e));
-    sfm_desc_destroy(d);
-    return SFM_ERR_NOMEM;
-  }
+  d->ctx = ctx; d->n = n; d->dim = dim; d->buf = b;
+  d->f32 = b->f32;
   int s = SFM_OK;
   do {
-    if ((s = (cudaMemsetAsync(d->flag, 0, sizeof(unsigned int), ctx->stream) == cudaSuccess) ? SFM_OK : SFM_ERR_CUDA)) break;
+    if (cudaMemsetAsync(b->flag, 0, sizeof(unsigned int), ctx->stream) != cudaSuccess) { s = SFM_ERR_CUDA; break; }
+    size_t count = (size_t)n * dim;
     if (count) {
-      int grid = (int)((count + 255) / 256);
-      if (grid > ctx->sm_count * 8) grid = ctx->sm_count * 8;
-      if (dtype == 0) {
-        const float* src;
-        if ((s = dev_in(ctx, (const float*)data, count, &src))) break;
-        s = [&]() -> int { SFM_LAUNCH(ctx, SFM_K_DESC_PREP, (desc_ingest_kernel<float><<<grid, 256, 0, ctx->stream>>>(src, count, d->f32, d->flag))); return SFM_OK; }();
+      const void* src = nullptr;
+      if (dtype == 0) { const float* p; if ((s = dev_in(ctx, (const float*)data, count, &p))) break; src = p; }
+      else { const uint8_t* p; if ((s = dev_in(ctx, (const uint8_t*)data, count, &p))) break; src = p; }
+      if (dim == 128) {
+        if ((s = sfm_desc_prepare_launch(ctx, d, src, dtype))) break;
       } else {
-        const uint8_t* src;
-        if ((s = dev_in(ctx, (const uint8_t*)data, count, &src))) break;
-        s = [&]() -> int { SFM_LAUNCH(ctx, SFM_K_DESC_PREP, (desc_ingest_kernel<uint8_t><<<grid, 256, 0, ctx->stream>>>(src, count, d->f32, d->flag))); return SFM_OK; }();
+        int grid = (int)((count + 255) / 256);
+        if (grid > ctx->sm_count * 8) grid = ctx->sm_count * 8;
+        if (dtype == 0)
+          s = [&]() -> int { SFM_LAUNCH(ctx, SFM_K_DESC_PREP, (desc_ingest_kernel<float><<<grid, 256, 0, ctx->stream>>>((const float*)src, count, b->f32, b->flag))); return SFM_OK; }();
+        else
+          s = [&]() -> int { SFM_LAUNCH(ctx, SFM_K_DESC_PREP, (desc_ingest_kernel<uint8_t><<<grid, 256, 0, ctx->stream>>>((const uint8_t*)src, count, b->f32, b->flag))); return SFM_OK; }();
+        if (s) break;
       }
-      if (s) break;
     }
-    unsigned int hflag = 0;
-    if (cudaMemcpyAsync(&hflag, d->flag, sizeof(hflag), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
-        cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+    // the flag word travels to pinned memory asynchronously; it is only waited for at first use
+    if (cudaMemcpyAsync(b->hflag, b->flag, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+        cudaEventRecord(b->ready, ctx->stream) != cudaSuccess) {
       sfm_set_error("sfm_desc_create: %s", cudaGetErrorString(cudaGetLastError()));
       s = SFM_ERR_CUDA;
       break;
     }
-    d->exact = (hflag == 0);
-    if (d->exact && dim == 128 && n > 0) s = sfm_desc_prepare_tiles(ctx, d);
+    // a host source buffer was staged through the workspace: the caller may reuse it after return
+    if (count && !sfm_is_device_ptr(data) && cudaStreamSynchronize(ctx->stream) != cudaSuccess) { s = SFM_ERR_CUDA; break; }
   } while (0);
   if (s != SFM_OK) { sfm_desc_destroy(d); return s; }
   *out = d;
   return SFM_OK;
 }
 
+int sfm_desc_resolve(sfm_desc* d) {
+  if (d->resolved) return SFM_OK;
+  SFM_CUDA(cudaEventSynchronize(d->buf->ready));
+  unsigned int f = *d->buf->hflag;
+  d->exact = (f & 1u) == 0;
+  bool tc = d->exact && !(f & 2u) && d->dim == 128 && d->n > 0 && d->buf->tiles;
+  d->tiles = tc ? d->buf->tiles : nullptr;
+  d->sqnorm = tc ? d->buf->sqnorm : nullptr;
+  d->n_tiles = tc ? (d->n + 127) / 128 : 0;
+  d->resolved = true;
+  return SFM_OK;
+}
+
 extern "C" void sfm_desc_destroy(sfm_desc* d) {
   if (!d) return;
-  if (d->ctx) { cudaSetDevice(d->ctx->device); cudaStreamSynchronize(d->ctx->stream); }
-  if (d->f32) cudaFree(d->f32);
-  if (d->tiles) cudaFree(d->tiles);
-  if (d->sqnorm) cudaFree(d->sqnorm);
-  if (d->flag) cudaFree(d->flag);
+  // storage goes back to the pool; reuse is stream-ordered on the ctx stream, so no synchronisation
+  if (d->buf && d->ctx) d->ctx->desc_pool.push_back(d->buf);
   delete d;
 }
 extern "C" int sfm_desc_rows(const sfm_desc* d) { return d ? d->n : 0; }
-extern "C" int sfm_desc_is_exact(const sfm_desc* d) { return d && d->exact ? 1 : 0; }
+extern "C" int sfm_desc_is_exact(const sfm_desc* d) {
+  if (!d) return 0;
+  if (sfm_desc_resolve(const_cast<sfm_desc*>(d)) != SFM_OK) return 0;
+  return d->exact ? 1 : 0;
+}
 
 // ------------------------------------------------------------------ one pair
 static int match_pair(sfm_ctx* ctx, const sfm_desc* q, const sfm_desc* t, double ratio, int mode,
                       int32_t* idx, float* dist, uint8_t* good, int32_t* n_good) {
   SFM_REQUIRE(q->dim == t->dim, "knnMatch: descriptor dims differ (%d vs %d)", q->dim, t->dim);
+  SFM_TRY(sfm_desc_resolve(const_cast<sfm_desc*>(q)));
+  SFM_TRY(sfm_desc_resolve(const_cast<sfm_desc*>(t)));
   const int nq = q->n, nt = t->n;
   bool tc_ok = q->exact && t->exact && q->tiles && t->tiles;
   SFM_REQUIRE(mode != 2 || tc_ok || nq == 0 || nt == 0,

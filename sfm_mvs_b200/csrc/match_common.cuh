@@ -17,16 +17,32 @@ __device__ __forceinline__ void key_insert(mkey_t k, mkey_t& k1, mkey_t& k2) {
   }
 }
 
+// Device storage of one view's descriptors; recycled through a per-context pool so that creating /
+// destroying descriptor sets in a loop performs no cudaMalloc / cudaFree and no device synchronisation.
+struct DescBuf {
+  float* f32 = nullptr;            // (cap_rows, dim) float32 copy (fp32 kernel operand)
+  unsigned char* tiles = nullptr;  // UMMA operand image (dim == 128 only)
+  float* sqnorm = nullptr;         // (cap_rows) exact |d|^2
+  unsigned int* flag = nullptr;    // device word: bit0 = a value is not an integer in [0,255], bit1 = |d|^2 > 2^21
+  unsigned int* hflag = nullptr;   // pinned host copy of `flag`, valid once `ready` has completed
+  cudaEvent_t ready = nullptr;
+  size_t cap_rows = 0;             // multiple of 256
+  int dim = 0;
+};
+
 struct sfm_desc {
   sfm_ctx* ctx = nullptr;
   int n = 0, dim = 0;
+  DescBuf* buf = nullptr;
+  bool resolved = false;     // hflag has been read
   bool exact = false;        // every value is an integer in [0,255] -> bf16/tensor path is exact
-  float* f32 = nullptr;      // (n, dim) row-major copy for the fp32 kernel (always present)
-  void* tiles = nullptr;     // UMMA operand image: [n_tiles][TILE bytes] (only when exact && dim==128)
+  float* f32 = nullptr;      // aliases into buf
+  void* tiles = nullptr;     // non-null only when the tensor-core path may be used (after resolve)
   int n_tiles = 0;           // 128-row tiles
-  float* sqnorm = nullptr;   // (n_pad) exact |d|^2 as float (only when exact)
-  unsigned int* flag = nullptr;  // device word: non-zero if any value is not an integer in [0,255]
+  float* sqnorm = nullptr;
 };
+
+int sfm_desc_resolve(sfm_desc* d);   // waits for the flag word (first use only)
 
 // match_exact.cu
 int sfm_match_exact_launch(sfm_ctx* ctx, const float* q, int nq, const float* t, int nt, int dim,
@@ -35,7 +51,7 @@ int sfm_match_exact_splits(sfm_ctx* ctx, int nq, int nt);
 // match_tc.cu
 int sfm_match_tc_splits(sfm_ctx* ctx, int nq, int nt);
 int sfm_match_tc_launch(sfm_ctx* ctx, const sfm_desc* q, const sfm_desc* t, mkey_t* cand, int nsplit);
-int sfm_desc_prepare_tiles(sfm_ctx* ctx, sfm_desc* d);
+int sfm_desc_prepare_launch(sfm_ctx* ctx, sfm_desc* d, const void* src, int dtype);
 // match.cu
 int sfm_match_finalize(sfm_ctx* ctx, const mkey_t* cand, int nq, int nt, int nsplit, double ratio,
                        int32_t* idx, float* dist, uint8_t* good, int32_t* n_good);

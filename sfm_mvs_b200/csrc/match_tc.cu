@@ -59,36 +59,52 @@ constexpr unsigned MAX_SQNORM = 1u << 21;
 enum { A_FULL = 0, A_EMPTY = 1, B_FULL = 2, B_EMPTY = 4, ACC_FULL = 6, ACC_EMPTY = 8, NBAR = 10 };
 }  // namespace tc
 
-// ============================================================================ K1b tile prep
+// ============================================================================ K1b descriptor prep
+// One pass over a view's descriptors (float32 or uint8 source): float32 resident copy, bf16 UMMA
+// operand image with the |d|^2 augmentation columns, exact |d|^2, and the domain flags.
 // One warp per 8-row group: lane l owns row l/4 and the 2-element slice (l%4) of every core
 // matrix, so each of the 20 core matrices of the group is written as one coalesced 128-byte
-// store and read as 4 x 32 contiguous bytes per row.
-__global__ void __launch_bounds__(256) desc_tiles_kernel(const float* __restrict__ src, int n,
-                                                          unsigned char* __restrict__ tiles, int n_groups,
-                                                          float* __restrict__ sqnorm,
-                                                          unsigned int* __restrict__ flag) {
+// store and read as 4 x (8 or 2)-byte pieces of one 32-byte (float32) sector per row.
+template <typename T>
+__global__ void __launch_bounds__(256) desc_prepare_kernel(const T* __restrict__ src, int n,
+                                                            float* __restrict__ f32,
+                                                            unsigned char* __restrict__ tiles, int n_groups,
+                                                            float* __restrict__ sqnorm,
+                                                            unsigned int* __restrict__ flag) {
   int group = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   if (group >= n_groups) return;
   int row = group * 8 + (lane >> 2);
   int sub = lane & 3;
   bool valid = row < n;
-  const float* rp = src + (size_t)row * tc::KMAIN;
+  const T* rp = src + (size_t)row * tc::KMAIN;
   unsigned char* gbase = tiles + (size_t)group * tc::SBO;     // tiles are contiguous: group g at g*SBO
   float h = 0.f;
+  bool bad = false;
 #pragma unroll
   for (int kc = 0; kc < tc::KMAIN / 8; ++kc) {
-    float2 v = valid ? __ldg(reinterpret_cast<const float2*>(rp + kc * 8 + sub * 2)) : make_float2(0.f, 0.f);
+    float2 v = make_float2(0.f, 0.f);
+    if (valid) {
+      v.x = (float)rp[kc * 8 + sub * 2];
+      v.y = (float)rp[kc * 8 + sub * 2 + 1];
+      *reinterpret_cast<float2*>(f32 + (size_t)row * tc::KMAIN + kc * 8 + sub * 2) = v;
+      bad |= !(v.x >= 0.f && v.x <= 255.f && v.x == rintf(v.x)) || !(v.y >= 0.f && v.y <= 255.f && v.y == rintf(v.y));
+    }
     h = fmaf(v.x, v.x, h);
     h = fmaf(v.y, v.y, h);
     __nv_bfloat162 b = __floats2bfloat162_rn(v.x, v.y);
     *reinterpret_cast<__nv_bfloat162*>(gbase + kc * tc::LBO + lane * 4) = b;
   }
   h += __shfl_xor_sync(0xffffffffu, h, 1);
-  h += __shfl_xor_sync(0xffffffffu, h, 2);   // exact: integers < 2^24
-  unsigned int hi = (unsigned int)h;
-  if (valid && hi > tc::MAX_SQNORM) atomicOr(flag, 2u);
-  if (valid && sub == 0 && sqnorm) sqnorm[row] = h;
+  h += __shfl_xor_sync(0xffffffffu, h, 2);   // exact when the values are integers: sums < 2^24
+  unsigned int flags = bad ? 1u : 0u;
+  if (valid && !(h <= (float)tc::MAX_SQNORM)) flags |= 2u;
+  if (__any_sync(0xffffffffu, flags != 0u)) {
+    unsigned int f = __reduce_or_sync(0xffffffffu, flags);
+    if (lane == 0) atomicOr(flag, f);
+  }
+  unsigned int hi = (h >= 0.f && h <= (float)tc::MAX_SQNORM) ? (unsigned int)h : 0u;
+  if (valid && sub == 0) sqnorm[row] = h;
   float c0 = -0.5f * (float)(hi & 0xFFu), c1 = -0.5f * (float)(hi & 0xFF00u), c2 = -0.5f * (float)(hi & 0xFF0000u);
   // augmentation columns: element e (0..7) of core column 16 (A-role) and 18 (B-role); 17,19 zero
   float a0, a1, b0, b1;
@@ -103,29 +119,18 @@ __global__ void __launch_bounds__(256) desc_tiles_kernel(const float* __restrict
   *reinterpret_cast<__nv_bfloat162*>(gbase + 19 * tc::LBO + lane * 4) = __floats2bfloat162_rn(0.f, 0.f);
 }
 
-int sfm_desc_prepare_tiles(sfm_ctx* ctx, sfm_desc* d) {
-  // even number of tiles so that a train stage is always two full tiles (padding rows are zero)
-  int n_tiles = div_up(d->n, tc::TILE_ROWS);
-  int n_tiles_alloc = (n_tiles + 1) & ~1;
-  d->n_tiles = n_tiles;
-  size_t bytes = (size_t)n_tiles_alloc * tc::TILE_BYTES;
-  cudaError_t e = cudaMalloc(&d->tiles, bytes);
-  if (e == cudaSuccess) e = cudaMalloc(&d->sqnorm, (size_t)n_tiles_alloc * tc::TILE_ROWS * sizeof(float));
-  if (e != cudaSuccess) {
-    sfm_set_error("sfm_desc_prepare_tiles: cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
-    return SFM_ERR_NOMEM;
-  }
+int sfm_desc_prepare_launch(sfm_ctx* ctx, sfm_desc* d, const void* src, int dtype) {
+  // even number of tiles so that a train stage is always two full tiles (padding rows are zero);
+  // storage capacity is a multiple of 256 rows, so the padded tile always exists
+  int n_tiles_alloc = (div_up(d->n, tc::TILE_ROWS) + 1) & ~1;
   int n_groups = n_tiles_alloc * (tc::TILE_ROWS / 8);
-  SFM_LAUNCH(ctx, SFM_K_DESC_PREP, (desc_tiles_kernel<<<div_up(n_groups * 32, 256), 256, 0, ctx->stream>>>(
-                                       d->f32, d->n, (unsigned char*)d->tiles, n_groups, d->sqnorm, d->flag)));
-  unsigned int hflag = 0;
-  SFM_CUDA(cudaMemcpyAsync(&hflag, d->flag, sizeof(hflag), cudaMemcpyDeviceToHost, ctx->stream));
-  SFM_CUDA(cudaStreamSynchronize(ctx->stream));
-  if (hflag & 2u) {   // |d|^2 > 2^21: the exact-accumulator argument does not hold -> fp32 kernel only
-    cudaFree(d->tiles); d->tiles = nullptr;
-    cudaFree(d->sqnorm); d->sqnorm = nullptr;
-    d->n_tiles = 0;
-  }
+  DescBuf* b = d->buf;
+  if (dtype == 0)
+    SFM_LAUNCH(ctx, SFM_K_DESC_PREP, (desc_prepare_kernel<float><<<div_up(n_groups * 32, 256), 256, 0, ctx->stream>>>(
+                                         (const float*)src, d->n, b->f32, b->tiles, n_groups, b->sqnorm, b->flag)));
+  else
+    SFM_LAUNCH(ctx, SFM_K_DESC_PREP, (desc_prepare_kernel<unsigned char><<<div_up(n_groups * 32, 256), 256, 0, ctx->stream>>>(
+                                         (const unsigned char*)src, d->n, b->f32, b->tiles, n_groups, b->sqnorm, b->flag)));
   return SFM_OK;
 }
 
@@ -408,6 +413,8 @@ int sfm_match_tc_launch(sfm_ctx* ctx, const sfm_desc* q, const sfm_desc* t, mkey
 extern "C" int sfm_debug_match_tc_dump(sfm_ctx* ctx, const sfm_desc* q, const sfm_desc* t, float* dump_host,
                                        int64_t capacity) {
   SFM_REQUIRE(ctx && q && t && dump_host, "sfm_debug_match_tc_dump: null argument");
+  SFM_TRY(sfm_desc_resolve(const_cast<sfm_desc*>(q)));
+  SFM_TRY(sfm_desc_resolve(const_cast<sfm_desc*>(t)));
   SFM_TRY(sfm_ws_begin(ctx));
   int nsplit = 1;
   int n_stages = div_up(t->n_tiles, tc::STAGE_TILES);

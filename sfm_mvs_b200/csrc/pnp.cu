@@ -7,10 +7,10 @@
 //
 // OpenCV's RANSAC loop is sequential only in its *stopping rule*: the subset drawn at iteration i
 // depends on nothing but N and i (RNG seeded with 2^64-1), and a hypothesis' score does not depend
-// on earlier hypotheses.  So the whole loop is evaluated as four stream-ordered kernels with no
+// on earlier hypotheses.  So the whole loop is evaluated as a few stream-ordered kernels with no
 // host round trip in between:
-//   pnp_subsets_kernel   the RNG index stream (one thread, ~1.5k integer ops)
-//   pnp_epnp_kernel      H minimal problems, one per warp (float64 EPnP, epnp.h)
+//   pnp_epnp_kernel      H minimal problems, one warp each (float64 EPnP, epnp.h): the RNG index
+//                        stream of the iteration, M^T M, warp-parallel Jacobi, three candidates
 //   pnp_score_kernel     K4: H x N reprojection tests, poses staged in shared memory, one point
 //                        per thread held in registers, ballot/popc warp counts
 //   pnp_replay_kernel    the accept / RANSACUpdateNumIters recursion over the count vector; then
@@ -110,38 +110,160 @@ __host__ __device__ inline void ransac_subsets(int n, int iters, int* out) {
   }
 }
 
-__global__ void pnp_subsets_kernel(int n, int iters, int* __restrict__ out) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) ransac_subsets(n, iters, out);
+// ------------------------------------------------------------------ minimal solver
+// One warp per hypothesis.
+//   lane 0      regenerates the RNG stream up to its iteration (the subset depends on N and the
+//               iteration only), loads the five correspondences, builds M^T M (epnp_build)
+//   all lanes   parallel-ordered two-sided Jacobi on the 12x12 M^T M in shared memory: each of the 11
+//               rounds of a sweep rotates 6 disjoint index pairs at once (72 column + 72 row + 72
+//               eigenvector element updates spread over the 32 lanes)
+//   lanes 0-2   the three beta initialisations + Gauss-Newton + absolute orientation, one per lane
+//   winner      writes the pose the scoring step must use: R' = Rodrigues(Rodrigues(R)), as OpenCV
+//               passes the model around as (rvec, tvec), and the (rvec, tvec) pair itself.
+struct EpnpShared {
+  double A[144];
+  double V[144];
+  double cs[12];        // (c, s) of the 6 rotations of a round
+  double alphas[20], pw[15], us[10], cws[12], L[60], rho[6], v4[48];
+  int pq[12];
+};
+
+__device__ __forceinline__ void warp_jacobi12(EpnpShared& sh, int lane) {
+  for (int i = lane; i < 144; i += 32) sh.V[i] = (i / 12 == i % 12) ? 1.0 : 0.0;
+  __syncwarp();
+  for (int sweep = 0; sweep < 60; ++sweep) {
+    double off = 0.0, diag = 0.0;
+    for (int i = lane; i < 144; i += 32) {
+      double a = sh.A[i];
+      if (i / 12 == i % 12) diag += a * a; else off += a * a;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      off += __shfl_xor_sync(0xffffffffu, off, o);
+      diag += __shfl_xor_sync(0xffffffffu, diag, o);
+    }
+    if (off * 0.5 <= 1e-32 * diag || off == 0.0) break;
+    for (int round = 0; round < 11; ++round) {
+      if (lane < 6) {
+        int p = (lane == 0) ? 11 : (round + lane) % 11;
+        int q = (lane == 0) ? round : (round - lane + 11) % 11;
+        if (p > q) { int t = p; p = q; q = t; }
+        double apq = sh.A[p * 12 + q], app = sh.A[p * 12 + p], aqq = sh.A[q * 12 + q];
+        double c = 1.0, s = 0.0;
+        if (fabs(apq) > 1e-300) {
+          double theta = (aqq - app) / (2.0 * apq);
+          double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+          c = 1.0 / sqrt(t * t + 1.0);
+          s = t * c;
+        }
+        sh.cs[2 * lane] = c; sh.cs[2 * lane + 1] = s;
+        sh.pq[2 * lane] = p; sh.pq[2 * lane + 1] = q;
+      }
+      __syncwarp();
+      for (int it = lane; it < 72; it += 32) {      // columns p,q of every row
+        int k = it / 12, i = it - 12 * k;
+        int p = sh.pq[2 * k], q = sh.pq[2 * k + 1];
+        double c = sh.cs[2 * k], s = sh.cs[2 * k + 1];
+        double aip = sh.A[i * 12 + p], aiq = sh.A[i * 12 + q];
+        sh.A[i * 12 + p] = c * aip - s * aiq;
+        sh.A[i * 12 + q] = s * aip + c * aiq;
+      }
+      __syncwarp();
+      for (int it = lane; it < 72; it += 32) {      // rows p,q of every column; eigenvector rows
+        int k = it / 12, j = it - 12 * k;
+        int p = sh.pq[2 * k], q = sh.pq[2 * k + 1];
+        double c = sh.cs[2 * k], s = sh.cs[2 * k + 1];
+        double apj = sh.A[p * 12 + j], aqj = sh.A[q * 12 + j];
+        sh.A[p * 12 + j] = c * apj - s * aqj;
+        sh.A[q * 12 + j] = s * apj + c * aqj;
+        double vp = sh.V[p * 12 + j], vq = sh.V[q * 12 + j];
+        sh.V[p * 12 + j] = c * vp - s * vq;
+        sh.V[q * 12 + j] = s * vp + c * vq;
+      }
+      __syncwarp();
+      if (lane < 6) {
+        int p = sh.pq[2 * lane], q = sh.pq[2 * lane + 1];
+        sh.A[p * 12 + q] = 0.0;
+        sh.A[q * 12 + p] = 0.0;
+      }
+      __syncwarp();
+    }
+  }
 }
 
-// ------------------------------------------------------------------ minimal solver
-// One warp per hypothesis (lane 0 runs the float64 solver; its working set lives in local
-// memory/L1 of an otherwise idle SM, so the H problems run fully in parallel across the chip).
-// Writes the pose the scoring step must use: R' = Rodrigues(Rodrigues(R)) as OpenCV passes the
-// model around as (rvec, tvec), and the (rvec, tvec) pair itself.
-__global__ void __launch_bounds__(32) pnp_epnp_kernel(const float* __restrict__ X, const float* __restrict__ px,
-                                                      const int* __restrict__ subsets, int H, PnpCam cam,
-                                                      double* __restrict__ poses, double* __restrict__ rt6,
-                                                      unsigned char* __restrict__ valid) {
-  const int h = blockIdx.x;
-  if (h >= H || threadIdx.x != 0) return;
-  hm::EpnpCam ec = {cam.fx, cam.fy, cam.cx, cam.cy};
-  double pw[15], us[10], work[35], R[9], t[3], rv[3];
-  for (int k = 0; k < 5; ++k) {
-    int j = subsets[5 * h + k];
-    pw[3 * k] = (double)X[3 * (size_t)j]; pw[3 * k + 1] = (double)X[3 * (size_t)j + 1]; pw[3 * k + 2] = (double)X[3 * (size_t)j + 2];
-    hm::epnp_roundtrip_pixel(px[2 * (size_t)j], px[2 * (size_t)j + 1], ec, us + 2 * k);
+__global__ void __launch_bounds__(32) pnp_epnp_kernel(const float* __restrict__ X, const float* __restrict__ px, int n,
+                                                      int H, PnpCam cam, double* __restrict__ poses,
+                                                      double* __restrict__ rt6, unsigned char* __restrict__ valid) {
+  __shared__ EpnpShared sh;
+  const int h = blockIdx.x, lane = threadIdx.x;
+  if (h >= H) return;
+  const hm::EpnpCam ec = {cam.fx, cam.fy, cam.cx, cam.cy};
+  if (lane == 0) {
+    int sub[5] = {0, 1, 2, 3, 4};
+    if (n > 5) {                                   // the subset iteration h of OpenCV's RANSAC draws
+      unsigned long long state = 0xFFFFFFFFFFFFFFFFull;
+      for (int it = 0; it <= h; ++it)
+        for (int i = 0; i < 5; ++i)
+          for (;;) {
+            state = (state & 0xFFFFFFFFull) * 4164903690ull + (state >> 32);
+            int j = (int)((unsigned int)state % (unsigned int)n);
+            bool dup = false;
+            for (int k = 0; k < i; ++k) dup |= (sub[k] == j);
+            if (!dup) { sub[i] = j; break; }
+          }
+    }
+    for (int k = 0; k < 5; ++k) {
+      int j = sub[k];
+      sh.pw[3 * k] = (double)X[3 * (size_t)j]; sh.pw[3 * k + 1] = (double)X[3 * (size_t)j + 1]; sh.pw[3 * k + 2] = (double)X[3 * (size_t)j + 2];
+      hm::epnp_roundtrip_pixel(px[2 * (size_t)j], px[2 * (size_t)j + 1], ec, sh.us + 2 * k);
+    }
+    hm::epnp_build(sh.pw, sh.us, 5, ec, sh.alphas, reinterpret_cast<double(*)[3]>(sh.cws), sh.A);
   }
-  hm::epnp_solve(pw, us, 5, ec, work, R, t);
-  hm::rodrigues_to_vector(R, rv);
-  double* P = poses + 12 * (size_t)h;
-  hm::rodrigues_to_matrix(rv, P);
-  P[9] = t[0]; P[10] = t[1]; P[11] = t[2];
-  bool ok = true;
-  for (int k = 0; k < 12; ++k) ok &= isfinite(P[k]);
-  rt6[6 * h] = rv[0]; rt6[6 * h + 1] = rv[1]; rt6[6 * h + 2] = rv[2];
-  rt6[6 * h + 3] = t[0]; rt6[6 * h + 4] = t[1]; rt6[6 * h + 5] = t[2];
-  valid[h] = ok ? 1 : 0;
+  __syncwarp();
+  warp_jacobi12(sh, lane);
+  if (lane == 0) {
+    // the four eigenvectors of the smallest eigenvalues, smallest first, largest component positive
+    double w[12];
+    bool used[12];
+    for (int i = 0; i < 12; ++i) { w[i] = sh.A[13 * i]; used[i] = false; }
+    for (int r = 0; r < 4; ++r) {
+      int m = -1;
+      for (int i = 0; i < 12; ++i)
+        if (!used[i] && (m < 0 || w[i] < w[m])) m = i;
+      used[m] = true;
+      int big = 0;
+      for (int k = 1; k < 12; ++k)
+        if (fabs(sh.V[m * 12 + k]) > fabs(sh.V[m * 12 + big])) big = k;
+      double sgn = sh.V[m * 12 + big] < 0.0 ? -1.0 : 1.0;
+      for (int k = 0; k < 12; ++k) sh.v4[12 * r + k] = sgn * sh.V[m * 12 + k];
+    }
+    const double* v[4] = {sh.v4, sh.v4 + 12, sh.v4 + 24, sh.v4 + 36};
+    hm::epnp_L_rho(v, reinterpret_cast<const double(*)[3]>(sh.cws), sh.L, sh.rho);
+  }
+  __syncwarp();
+  double R[9], t[3], err = 0.0;
+  if (lane < 3) {
+    const double* v[4] = {sh.v4, sh.v4 + 12, sh.v4 + 24, sh.v4 + 36};
+    err = hm::epnp_candidate(lane, sh.L, sh.rho, v, sh.alphas, sh.pw, sh.us, 5, ec, R, t);
+  }
+  double errs[3];
+  errs[0] = __shfl_sync(0xffffffffu, err, 0);
+  errs[1] = __shfl_sync(0xffffffffu, err, 1);
+  errs[2] = __shfl_sync(0xffffffffu, err, 2);
+  const int N = hm::epnp_pick(errs);
+  if (lane == N) {
+    double rv[3];
+    hm::rodrigues_to_vector(R, rv);
+    double* P = poses + 12 * (size_t)h;
+    double Rr[9];
+    hm::rodrigues_to_matrix(rv, Rr);
+    bool ok = true;
+    for (int k = 0; k < 9; ++k) { P[k] = Rr[k]; ok &= isfinite(Rr[k]); }
+    for (int k = 0; k < 3; ++k) { P[9 + k] = t[k]; ok &= isfinite(t[k]); }
+    rt6[6 * h] = rv[0]; rt6[6 * h + 1] = rv[1]; rt6[6 * h + 2] = rv[2];
+    rt6[6 * h + 3] = t[0]; rt6[6 * h + 4] = t[1]; rt6[6 * h + 5] = t[2];
+    valid[h] = ok ? 1 : 0;
+  }
 }
 
 // ------------------------------------------------------------------ replay of the stopping rule
@@ -283,14 +405,44 @@ __device__ inline void block_reduce_acc(double* acc, double (*sh)[REFINE_NACC], 
   __syncthreads();
 }
 
-// Solve (A with diag *= 1+lambda) x = b for symmetric positive semi-definite 6x6 A (upper packed
-// row-major in a21) by Jacobi eigen-decomposition (pseudo-inverse, like OpenCV's DECOMP_SVD).
+// Solve (A with diag *= 1+lambda) x = b for the symmetric 6x6 normal matrix (upper packed row-major
+// in a21): Cholesky; a non-positive pivot (rank-deficient configuration) falls back to the
+// eigen-decomposition pseudo-inverse, which is what OpenCV's DECOMP_SVD solve amounts to.
 __device__ inline void solve6_damped(const double* a21, const double* b, double lambda, double* x) {
-  double A[36], w[6], V[36];
+  double A[36];
   int k = 0;
   for (int i = 0; i < 6; ++i)
     for (int j = i; j < 6; ++j) { A[6 * i + j] = a21[k]; A[6 * j + i] = a21[k]; ++k; }
   for (int i = 0; i < 6; ++i) A[7 * i] *= 1.0 + lambda;
+  double Lc[36];
+  bool pd = true;
+  for (int j = 0; j < 6 && pd; ++j) {
+    double d = A[7 * j];
+    for (int m = 0; m < j; ++m) d -= Lc[6 * j + m] * Lc[6 * j + m];
+    if (!(d > 1e-14 * fabs(A[7 * j]))) { pd = false; break; }
+    double dj = sqrt(d);
+    Lc[7 * j] = dj;
+    for (int i = j + 1; i < 6; ++i) {
+      double v = A[6 * i + j];
+      for (int m = 0; m < j; ++m) v -= Lc[6 * i + m] * Lc[6 * j + m];
+      Lc[6 * i + j] = v / dj;
+    }
+  }
+  if (pd) {
+    double y[6];
+    for (int i = 0; i < 6; ++i) {
+      double v = b[i];
+      for (int m = 0; m < i; ++m) v -= Lc[6 * i + m] * y[m];
+      y[i] = v / Lc[7 * i];
+    }
+    for (int i = 5; i >= 0; --i) {
+      double v = y[i];
+      for (int m = i + 1; m < 6; ++m) v -= Lc[6 * m + i] * x[m];
+      x[i] = v / Lc[7 * i];
+    }
+    return;
+  }
+  double w[6], V[36];
   hm::eig_sym<6>(A, w, V);
   double wmax = fabs(w[5]) > fabs(w[0]) ? fabs(w[5]) : fabs(w[0]);
   double thr = wmax * 6 * DBL_EPSILON;
@@ -479,13 +631,11 @@ static int pnp_ransac_impl(sfm_ctx* ctx, const float* X, const float* px, int n,
   SFM_TRY(dev_in(ctx, X, (size_t)3 * n, &dX));
   SFM_TRY(dev_in(ctx, px, (size_t)2 * n, &dpx));
   const int H = (n == 5) ? 1 : max_iters;
-  int* dsub;
   double *dposes, *drt6;
   unsigned char* dvalid;
   int32_t* dcounts;
   int32_t* dinl;
   PnpResult* dres;
-  SFM_TRY(ws_alloc_t(ctx, (size_t)5 * H, &dsub));
   SFM_TRY(ws_alloc_t(ctx, (size_t)12 * H, &dposes));
   SFM_TRY(ws_alloc_t(ctx, (size_t)6 * H, &drt6));
   SFM_TRY(ws_alloc_t(ctx, (size_t)H, &dvalid));
@@ -517,16 +667,7 @@ static int pnp_ransac_impl(sfm_ctx* ctx, const float* X, const float* px, int n,
     SFM_CUDA(cudaMemcpyAsync(drt6, hp + 12 * (size_t)H, sizeof(double) * 6 * H, cudaMemcpyHostToDevice, ctx->stream));
     SFM_CUDA(cudaMemcpyAsync(dvalid, hv, H, cudaMemcpyHostToDevice, ctx->stream));
   } else {
-    if (n == 5) {
-      int hsub[5] = {0, 1, 2, 3, 4};
-      int* ps;
-      SFM_TRY(hs_alloc_t(ctx, 5, &ps));
-      memcpy(ps, hsub, sizeof(hsub));
-      SFM_CUDA(cudaMemcpyAsync(dsub, ps, sizeof(hsub), cudaMemcpyHostToDevice, ctx->stream));
-    } else {
-      SFM_LAUNCH(ctx, SFM_K_MISC, (pnp_subsets_kernel<<<1, 32, 0, ctx->stream>>>(n, H, dsub)));
-    }
-    SFM_LAUNCH(ctx, SFM_K_PNP_EPNP, (pnp_epnp_kernel<<<H, 32, 0, ctx->stream>>>(dX, dpx, dsub, H, cam, dposes, drt6, dvalid)));
+    SFM_LAUNCH(ctx, SFM_K_PNP_EPNP, (pnp_epnp_kernel<<<H, 32, 0, ctx->stream>>>(dX, dpx, n, H, cam, dposes, drt6, dvalid)));
   }
   SFM_CUDA(cudaMemsetAsync(dcounts, 0, sizeof(int32_t) * H, ctx->stream));
   dim3 grid(div_up(n, 256), div_up(H, PNP_HG));

@@ -1,0 +1,10 @@
+// solve.cuh — dense SPD solve used by the bundle-adjustment step (solve.cu).
+#pragma once
+#include <algorithm>
+
+#include "common.cuh"
+
+// Solves S x = -g.  S (n x n float32, lower triangle read), g (n float32), A: (n+1) x n float64
+// scratch (factor L is left in its lower triangle), x (n float64), info: device int, 0 or the
+// 1-based index of the first non-positive pivot.  Stream-ordered, no host synchronisation.
+int sfm_spd_solve(sfm_ctx* ctx, const float* S, const float* g, int n, double* A, double* x, int* info);

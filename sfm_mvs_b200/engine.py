@@ -140,9 +140,13 @@ class Context:
         return torch.device("cuda", self.device)
 
     def torch_stream(self):
-        """The context's stream as a torch ExternalStream (for torch.cuda.Event timing on it)."""
+        """The context's stream as a torch ExternalStream.  Code that mixes torch allocations / copies
+        with engine calls must run under `torch.cuda.stream(ctx.torch_stream())` so that both are ordered
+        on one stream (the engine's own stream is non-blocking w.r.t. the legacy default stream)."""
         import torch
-        return torch.cuda.ExternalStream(self.stream, device=self.torch_device)
+        if getattr(self, "_tstream", None) is None:
+            self._tstream = torch.cuda.ExternalStream(self.stream, device=self.torch_device)
+        return self._tstream
 
     def launch_count(self) -> int:
         return int(lib.sfm_ctx_launch_count(self._h))

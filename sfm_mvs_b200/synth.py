@@ -106,24 +106,26 @@ def orbit_scene(n_views: int, n_pts: int, seed: int = 0, shared: float = 0.6,
     K = K_GUSTAV if K is None else K
     margin = 4.0
     views = []
-    base_desc: list[np.ndarray] = []   # per 3-D point, un-quantised
     pts3d: list[np.ndarray] = []
     n_total = 0
+    # only the previous view's points can be re-observed, so only its 3-D points / base descriptors
+    # are kept (aligned with prev_ids) — O(V) memory and time
     prev_ids = np.zeros(0, dtype=np.int64)
+    prev_X = np.zeros((0, 3))
+    prev_bd = np.zeros((0, 128))
     for v in range(n_views):
         R, t = orbit_pose(step * v)
-        keep_ids = np.zeros(0, dtype=np.int64)
+        sel = np.zeros(0, dtype=np.int64)
         keep_uv = np.zeros((0, 2))
         if v > 0 and prev_ids.size:
-            Xp = np.concatenate(pts3d)[prev_ids]
-            uv, z = project(K, R, t, Xp)
+            uv, z = project(K, R, t, prev_X)
             ok = (z > 0.5) & (uv[:, 0] > margin) & (uv[:, 0] < IMG_W - margin) & \
                  (uv[:, 1] > margin) & (uv[:, 1] < IMG_H - margin)
             cand = np.nonzero(ok)[0]
             take = min(int(shared * n_pts), cand.size)
             sel = rng.choice(cand, size=take, replace=False)
-            keep_ids = prev_ids[sel]
             keep_uv = uv[sel]
+        keep_ids = prev_ids[sel]
         n_new = n_pts - keep_ids.size
         uv_new = np.stack([rng.uniform(margin, IMG_W - margin, n_new),
                            rng.uniform(margin, IMG_H - margin, n_new)], axis=1)
@@ -134,14 +136,16 @@ def orbit_scene(n_views: int, n_pts: int, seed: int = 0, shared: float = 0.6,
         new_ids = np.arange(n_total, n_total + n_new, dtype=np.int64)
         n_total += n_new
         pts3d.append(Xw)
-        base_desc.append(_sift_base(n_new, rng))
+        new_bd = _sift_base(n_new, rng)
         ids = np.concatenate([keep_ids, new_ids])
         uv_all = np.concatenate([keep_uv, uv_new]) + rng.normal(0.0, px_noise, (n_pts, 2))
-        bd = np.concatenate(base_desc)[ids]
+        bd = np.concatenate([prev_bd[sel], new_bd])
         des = _quantise(np.maximum(bd + rng.normal(0.0, desc_sigma, bd.shape), 0.0))
         perm = rng.permutation(n_pts)
         views.append(dict(kp=uv_all[perm].astype(np.float32), des=des[perm], pid=ids[perm], R=R, t=t))
         prev_ids = ids
+        prev_X = np.concatenate([prev_X[sel], Xw])
+        prev_bd = bd
     return dict(K=K.copy(), views=views, X=np.concatenate(pts3d))
 
 

@@ -73,12 +73,12 @@ def test_reprojection_error_equals_reference_formula(engine, n, seed):
     e, X, p = sfm.ReprojectionError(cloud, b, Rt1, K, 1, ctx=engine)
     assert np.array_equal(X, X_ref)                       # convertPointsFromHomogeneous, bit exact
     assert np.array_equal(p, p_ref)                       # float32 projections, bit exact
-    assert abs(e - e_ref) <= 1e-12 * e_ref
+    assert abs(e - e_ref) <= 1e-9 * e_ref               # float64 sums in a different order
     e0_ref, _, p0_ref = cvpath.ReprojectionError(X_ref[:, 0, :], x1, Rt1, K, 0)
     e0, _, p0 = sfm.ReprojectionError(X_ref[:, 0, :], x1, Rt1, K, 0, ctx=engine)
-    assert np.array_equal(p0, p0_ref) and abs(e0 - e0_ref) <= 1e-12 * e0_ref
+    assert np.array_equal(p0, p0_ref) and abs(e0 - e0_ref) <= 1e-9 * e0_ref
     eb, _ = sfm.ba.ReprojectionError(X_ref[:, 0, :], b, Rt1, K, ctx=engine)   # ba.pyc L44-63
-    assert abs(eb - e0_ref) <= 1e-12 * e0_ref
+    assert abs(eb - e0_ref) <= 1e-9 * e0_ref
 
 
 def test_common_points_golden_and_quirk(engine, golden):

@@ -77,12 +77,27 @@ def test_golden_pnp_inliers(engine, golden):
         assert np.abs(R - g["pnp_R"]).max() < 1e-6 and np.abs(tvec - g["pnp_t"].ravel()).max() < 1e-5
 
 
-@pytest.mark.parametrize("seed", range(12))
+def _solvable_problem(seed):
+    """Outlier ratio <= 0.4 and noise <= 1 px: the 100 subsets then contain all-inlier ones, so RANSAC's
+    outcome does not hinge on which contaminated subset happens to score best (with ~60 % outliers none of
+    the 100 five-point subsets is clean and any two minimal solvers legitimately pick different models)."""
+    rng = np.random.default_rng(500 + seed)
+    n = int(rng.integers(60, 3000))
+    R, t = synth.orbit_pose(rng.uniform(0, 0.5))
+    X = np.c_[rng.uniform(-2.5, 2.5, n), rng.uniform(-1.5, 1.5, n), rng.uniform(5, 11, n)].astype(np.float32)
+    uv, _ = synth.project(K, R, t, X.astype(np.float64))
+    p = (uv + rng.normal(0, rng.uniform(0.1, 1.0), uv.shape)).astype(np.float32)
+    bad = rng.random(n) < rng.uniform(0, 0.4)
+    p[bad] += rng.uniform(-80, 80, (int(bad.sum()), 2)).astype(np.float32)
+    return X, p
+
+
+@pytest.mark.parametrize("seed", range(16))
 def test_ransac_with_engine_minimal_solver(engine, seed):
-    """Full GPU path (own EPnP).  OpenCV's EPnP picks its null-space basis with LAPACK, so individual
-    hypotheses differ; the estimate must still be the same pose and the same consensus set up to the
-    points within noise of the 8 px threshold."""
-    X, p = _problem(seed)
+    """Full GPU path (the engine's own EPnP).  OpenCV's EPnP takes its null-space basis from LAPACK, so the
+    individual hypotheses differ (PnP parity); the estimate must still be the same pose and the
+    same consensus set up to the points within noise of the 8 px threshold."""
+    X, p = _solvable_problem(seed)
     ok_ref, rvec_ref, tvec_ref, inl_ref = cv2.solvePnPRansac(X, p, K, D0)
     ok, rvec, tvec, inl, info = engine.pnp_ransac(X, p, K)
     assert ok == ok_ref
@@ -113,3 +128,45 @@ def test_solvepnpransac_surface(engine):
     # five points: OpenCV returns the EPnP pose with all five as inliers
     ok5, r5, t5, inl5 = sfm.solvePnPRansac(X[:5], p[:5], K, D0, ctx=engine)
     assert ok5 and inl5[:, 0].tolist() == [0, 1, 2, 3, 4]
+
+
+# ----------------------------------------------------------------------------- the per-view loop
+def _cv_hyp_fn(X, p):
+    return _cv_hypotheses(np.ascontiguousarray(X), np.ascontiguousarray(p))
+
+
+def test_registration_chain_equals_reference_loop(engine, golden):
+    """sfm.py:341-409 over a 7-view scene: the engine's device-resident loop against the oracle port of
+    the reference loop (and the golden fixture produced by the reference's own defs when this host's
+    OpenCV reproduces it).  PnP runs on OpenCV's minimal solutions, so poses must agree to rounding."""
+    from oracle import cvpath
+    from sfm_mvs_b200 import pipeline
+    g = golden("chain")
+    scene = synth.orbit_scene(int(g["n_views"]), int(g["n_pts"]), seed=int(g["seed"]))
+    ref = cvpath.register_chain(scene)
+    outs = pipeline.register_chain(scene, ctx=engine, hypothesis_fn=_cv_hyp_fn)
+    assert len(outs) == len(ref) == 5
+    for o, r in zip(outs, ref):
+        assert (o["n_match"], o["n_pnp"], o["n_inl"], o["n_new"]) == (r["n_match"], r["n_pnp"], r["n_inl"], len(r["X_new"]))
+        assert np.abs(o["Rt"] - r["Rt"]).max() < 1e-5
+        assert abs(o["err_pnp"] - r["err_pnp"]) <= 1e-4 * r["err_pnp"]
+        assert abs(o["err_new"] - r["err_new"]) <= 1e-4 * r["err_new"]
+        rel = np.abs(o["X_new"] - r["X_new"]).max() / np.abs(r["X_new"]).max()
+        assert rel < 1e-4, rel
+    if np.array_equal(np.array([r["Rt"] for r in ref]), g["Rt"]):
+        assert np.abs(np.array([o["Rt"] for o in outs]) - g["Rt"]).max() < 1e-5
+        assert np.abs(np.vstack([o["X_new"] for o in outs]) - g["X_new"]).max() / np.abs(g["X_new"]).max() < 1e-4
+
+
+def test_registration_chain_gpu_minimal_solver(engine):
+    """Throughput configuration (engine EPnP): same views registered, poses close to ground truth."""
+    from sfm_mvs_b200 import pipeline
+    scene = synth.orbit_scene(8, 1500, seed=4)
+    outs = pipeline.register_chain(scene, ctx=engine)
+    assert len(outs) == 6
+    for i, o in enumerate(outs):
+        v = scene["views"][i + 2]
+        Rt_gt = np.hstack([v["R"], v["t"].reshape(3, 1)])
+        assert np.abs(o["Rt"][:, :3] - Rt_gt[:, :3]).max() < 5e-3
+        assert np.abs(o["Rt"][:, 3] - Rt_gt[:, 3]).max() < 5e-2
+        assert o["err_new"] < 0.05 and o["n_inl"] > 0.8 * o["n_pnp"]
