@@ -101,88 +101,66 @@ __device__ __forceinline__ double warp_sum_d(double v) {
 }
 
 // ------------------------------------------------------------------ K5: materialised evaluation
-// Persistent CTAs, one observation per thread per trip: 16 B read (uv, cam index, point index),
-// 80 B written (r 8 B, Jc 48 B, Jp 24 B).  The per-camera table (C x 21 doubles) is staged in shared
-// memory once per CTA when SMEM_CAMS (otherwise it is read through L1).  With STAGE the 20 output
-// floats of a thread go through a per-warp shared-memory tile first (conflict-free 16 B / 8 B
-// shared stores at 48 B / 24 B stride) and leave the SM as fully coalesced 16-byte stores of
-// contiguous 256 / 1536 / 768-byte runs instead of 32 scattered 16-byte pieces per instruction.
-template <int MODE, bool SMEM_CAMS, bool STAGE>
-__global__ void __launch_bounds__(256) ba_eval_kernel(const float2* __restrict__ uv, const int* __restrict__ cam_idx,
-                                                      const int* __restrict__ pt_idx, int n_obs,
-                                                      const double* __restrict__ cam_pre, int n_cam,
-                                                      const double* __restrict__ pts, Intr K, double inv_n,
-                                                      float* __restrict__ r_out, float* __restrict__ Jc_out,
-                                                      float* __restrict__ Jp_out, double* __restrict__ cost) {
-  extern __shared__ double s_cam[];
-  __shared__ __align__(16) float s_stage[STAGE ? 8 : 1][STAGE ? 640 : 4];
+// One persistent CTA of 1024 threads per SM; one observation per thread per trip: 16 B read (uv, cam
+// index, point index), 80 B written (r 8 B, Jc 48 B, Jp 24 B).  The per-camera table (C x 21 doubles,
+// 84 KB at C = 500) is staged into shared memory by ONE bulk-copy instruction (cp.async.bulk, the TMA
+// engine, completion on an mbarrier) when it fits, so the random per-observation camera gather never
+// leaves the SM; otherwise it is read through L1.
+__device__ __forceinline__ uint32_t ba_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <int MODE, bool SMEM_CAMS>
+__global__ void __launch_bounds__(1024, 1) ba_eval_kernel(const float2* __restrict__ uv, const int* __restrict__ cam_idx,
+                                                          const int* __restrict__ pt_idx, int n_obs,
+                                                          const double* __restrict__ cam_pre, int n_cam,
+                                                          const double* __restrict__ pts, Intr K, double inv_n,
+                                                          float* __restrict__ r_out, float* __restrict__ Jc_out,
+                                                          float* __restrict__ Jp_out, double* __restrict__ cost) {
+  extern __shared__ __align__(128) double s_cam[];
+  __shared__ __align__(8) unsigned long long s_bar;
   if (SMEM_CAMS) {
-    for (int i = threadIdx.x; i < n_cam * CAM_PRE; i += blockDim.x) s_cam[i] = cam_pre[i];
-    __syncthreads();
+    const uint32_t bar = ba_smem_u32(&s_bar);
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      const uint32_t bytes = (uint32_t)((n_cam * CAM_PRE * sizeof(double) + 15) & ~(size_t)15);
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(ba_smem_u32(s_cam)), "l"(cam_pre), "r"(bytes), "r"(bar) : "memory");
+    }
+    __syncthreads();   // barrier initialised before anyone polls it
+    uint32_t ok = 0;
+    for (uint32_t spin = 0; !ok; ++spin) {
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                   : "=r"(ok) : "r"(bar) : "memory");
+      if (spin > (1u << 22)) asm volatile("trap;");
+    }
   }
   const double* cams = SMEM_CAMS ? s_cam : cam_pre;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double local = 0.0;
-  for (int o0 = blockIdx.x * blockDim.x + warp * 32; o0 < n_obs; o0 += gridDim.x * blockDim.x) {
-    const int o = o0 + lane;
-    const bool valid = o < n_obs;
-    double r[2] = {0, 0}, Jc[2][6], Jp[2][3];
-    if (valid) {
-      const float2 m = __ldg(uv + o);
-      const int c = __ldg(cam_idx + o), p = __ldg(pt_idx + o);
-      const double X[3] = {__ldg(pts + 3 * (size_t)p), __ldg(pts + 3 * (size_t)p + 1), __ldg(pts + 3 * (size_t)p + 2)};
-      if (MODE == 0 && (Jc_out != nullptr || Jp_out != nullptr)) obs_geometry<true>(cams + CAM_PRE * (size_t)c, X, m, K, r, Jc, Jp);
-      else obs_geometry<false>(cams + CAM_PRE * (size_t)c, X, m, K, r, Jc, Jp);
-    }
+  for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < n_obs; o += gridDim.x * blockDim.x) {
+    const float2 m = __ldg(uv + o);
+    const int c = __ldg(cam_idx + o), p = __ldg(pt_idx + o);
+    const double X[3] = {__ldg(pts + 3 * (size_t)p), __ldg(pts + 3 * (size_t)p + 1), __ldg(pts + 3 * (size_t)p + 2)};
+    double r[2], Jc[2][6], Jp[2][3];
     if (MODE == 0) {
+      if (Jc_out != nullptr || Jp_out != nullptr) obs_geometry<true>(cams + CAM_PRE * (size_t)c, X, m, K, r, Jc, Jp);
+      else obs_geometry<false>(cams + CAM_PRE * (size_t)c, X, m, K, r, Jc, Jp);
       local += r[0] * r[0] + r[1] * r[1];
-      const bool full = (o0 + 32 <= n_obs);
-      if (STAGE && full) {
-        float* st = s_stage[warp];
-        if (r_out) *reinterpret_cast<float2*>(st + 2 * lane) = make_float2((float)r[0], (float)r[1]);
-        if (Jc_out) {
-          float4* d = reinterpret_cast<float4*>(st + 64 + 12 * lane);
-          d[0] = make_float4((float)Jc[0][0], (float)Jc[0][1], (float)Jc[0][2], (float)Jc[0][3]);
-          d[1] = make_float4((float)Jc[0][4], (float)Jc[0][5], (float)Jc[1][0], (float)Jc[1][1]);
-          d[2] = make_float4((float)Jc[1][2], (float)Jc[1][3], (float)Jc[1][4], (float)Jc[1][5]);
-        }
-        if (Jp_out) {
-          float2* d = reinterpret_cast<float2*>(st + 448 + 6 * lane);
-          d[0] = make_float2((float)Jp[0][0], (float)Jp[0][1]);
-          d[1] = make_float2((float)Jp[0][2], (float)Jp[1][0]);
-          d[2] = make_float2((float)Jp[1][1], (float)Jp[1][2]);
-        }
-        __syncwarp();
-        const float4* s4 = reinterpret_cast<const float4*>(st);
-        if (r_out && lane < 16) reinterpret_cast<float4*>(r_out + 2 * (size_t)o0)[lane] = s4[lane];
-        if (Jc_out) {
-          float4* d = reinterpret_cast<float4*>(Jc_out + 12 * (size_t)o0);
-          d[lane] = s4[16 + lane];
-          d[lane + 32] = s4[48 + lane];
-          d[lane + 64] = s4[80 + lane];
-        }
-        if (Jp_out) {
-          float4* d = reinterpret_cast<float4*>(Jp_out + 6 * (size_t)o0);
-          d[lane] = s4[112 + lane];
-          if (lane < 16) d[lane + 32] = s4[144 + lane];
-        }
-        __syncwarp();
-      } else if (valid) {
-        if (r_out) reinterpret_cast<float2*>(r_out)[o] = make_float2((float)r[0], (float)r[1]);
-        if (Jc_out) {
-          float4* d = reinterpret_cast<float4*>(Jc_out + 12 * (size_t)o);
-          d[0] = make_float4((float)Jc[0][0], (float)Jc[0][1], (float)Jc[0][2], (float)Jc[0][3]);
-          d[1] = make_float4((float)Jc[0][4], (float)Jc[0][5], (float)Jc[1][0], (float)Jc[1][1]);
-          d[2] = make_float4((float)Jc[1][2], (float)Jc[1][3], (float)Jc[1][4], (float)Jc[1][5]);
-        }
-        if (Jp_out) {
-          float2* d = reinterpret_cast<float2*>(Jp_out + 6 * (size_t)o);
-          d[0] = make_float2((float)Jp[0][0], (float)Jp[0][1]);
-          d[1] = make_float2((float)Jp[0][2], (float)Jp[1][0]);
-          d[2] = make_float2((float)Jp[1][1], (float)Jp[1][2]);
-        }
+      if (r_out) reinterpret_cast<float2*>(r_out)[o] = make_float2((float)r[0], (float)r[1]);
+      if (Jc_out) {
+        float4* d = reinterpret_cast<float4*>(Jc_out + 12 * (size_t)o);
+        d[0] = make_float4((float)Jc[0][0], (float)Jc[0][1], (float)Jc[0][2], (float)Jc[0][3]);
+        d[1] = make_float4((float)Jc[0][4], (float)Jc[0][5], (float)Jc[1][0], (float)Jc[1][1]);
+        d[2] = make_float4((float)Jc[1][2], (float)Jc[1][3], (float)Jc[1][4], (float)Jc[1][5]);
       }
-    } else if (valid) {
+      if (Jp_out) {
+        float2* d = reinterpret_cast<float2*>(Jp_out + 6 * (size_t)o);
+        d[0] = make_float2((float)Jp[0][0], (float)Jp[0][1]);
+        d[1] = make_float2((float)Jp[0][2], (float)Jp[1][0]);
+        d[2] = make_float2((float)Jp[1][1], (float)Jp[1][2]);
+      }
+    } else {
+      obs_geometry<false>(cams + CAM_PRE * (size_t)c, X, m, K, r, Jc, Jp);
       if (MODE == 1) {        // ((p - proj)^2).ravel()/N            sfm.py:124-130
         double a = r[0] * r[0] * inv_n, b = r[1] * r[1] * inv_n;
         local += a * a + b * b;
@@ -196,8 +174,8 @@ __global__ void __launch_bounds__(256) ba_eval_kernel(const float2* __restrict__
   }
   if (cost) {
     local = warp_sum_d(local);
-    __shared__ double s_part[8];
-    if (lane == 0) s_part[warp] = local;
+    __shared__ double s_part[32];
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = local;
     __syncthreads();
     if (threadIdx.x == 0) {
       double s = 0.0;
@@ -446,23 +424,22 @@ int cam_prep(sfm_ba* ba, const double* cams) {
   return SFM_OK;
 }
 
-// evaluation at (cams already in cam_pre, pts): *cost_dev += 0.5 sum r^2.
-// SFM_BA_EVAL_VARIANT (diagnostic): bit0 = stage outputs through shared memory, bit1 = camera table
-// through L1 instead of shared memory.  Default 1.
-template <int MODE, bool SM, bool ST>
-int launch_eval_v(sfm_ba* ba, const double* pts, float* r, float* Jc, float* Jp, double* cost_dev, int ctas_per_sm) {
+// evaluation at (cams already in cam_pre, pts): *cost_dev += 0.5 sum r^2
+template <int MODE, bool SM>
+int launch_eval_v(sfm_ba* ba, const double* pts, float* r, float* Jc, float* Jp, double* cost_dev) {
   sfm_ctx* ctx = ba->ctx;
-  const size_t smem = SM ? cam_smem_bytes(ba) : 0;
+  const size_t smem = SM ? ((cam_smem_bytes(ba) + 15) & ~(size_t)15) : 0;
   const double inv_n = 1.0 / (double)(ba->n_obs_total > 0 ? ba->n_obs_total : 1);
-  int grid = std::max(1, std::min(div_up(ba->n_obs, 256), ctx->sm_count * ctas_per_sm));
+  const int threads = ba->n_obs >= 64 * 1024 ? 1024 : 256;
+  int grid = std::max(1, std::min(div_up(ba->n_obs, threads), ctx->sm_count * (SM ? 1 : 2)));
   if (SM) {
     static bool attr = false;
     if (!attr) {
-      SFM_CUDA(cudaFuncSetAttribute(ba_eval_kernel<MODE, SM, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      SFM_CUDA(cudaFuncSetAttribute(ba_eval_kernel<MODE, SM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       attr = true;
     }
   }
-  SFM_LAUNCH(ctx, SFM_K_BA_EVAL, (ba_eval_kernel<MODE, SM, ST><<<grid, 256, smem, ctx->stream>>>(
+  SFM_LAUNCH(ctx, SFM_K_BA_EVAL, (ba_eval_kernel<MODE, SM><<<grid, threads, smem, ctx->stream>>>(
                                      ba->uv, ba->cam_idx, ba->pt_idx, ba->n_obs, ba->cam_pre, ba->n_cam, pts,
                                      make_intr(ba), inv_n, r, Jc, Jp, cost_dev)));
   return SFM_OK;
@@ -470,18 +447,8 @@ int launch_eval_v(sfm_ba* ba, const double* pts, float* r, float* Jc, float* Jp,
 
 template <int MODE>
 int launch_eval(sfm_ba* ba, const double* pts, float* r, float* Jc, float* Jp, double* cost_dev) {
-  static int variant = -1;
-  if (variant < 0) {
-    const char* e = getenv("SFM_BA_EVAL_VARIANT");
-    variant = e ? atoi(e) : 1;
-  }
-  const bool fits = cam_smem_bytes(ba) <= 96 * 1024;
-  const bool sm = fits && !(variant & 2);
-  const bool st = (variant & 1) && MODE == 0;
-  if (sm && st) return launch_eval_v<MODE, true, true>(ba, pts, r, Jc, Jp, cost_dev, 2);
-  if (sm && !st) return launch_eval_v<MODE, true, false>(ba, pts, r, Jc, Jp, cost_dev, 2);
-  if (!sm && st) return launch_eval_v<MODE, false, true>(ba, pts, r, Jc, Jp, cost_dev, 4);
-  return launch_eval_v<MODE, false, false>(ba, pts, r, Jc, Jp, cost_dev, 4);
+  if (cam_smem_bytes(ba) <= 200 * 1024 - 64) return launch_eval_v<MODE, true>(ba, pts, r, Jc, Jp, cost_dev);
+  return launch_eval_v<MODE, false>(ba, pts, r, Jc, Jp, cost_dev);
 }
 
 int build_system(sfm_ba* ba, double lambda) {
@@ -592,7 +559,7 @@ extern "C" int sfm_ba_create(sfm_ctx* ctx, int n_cam, int n_pt, int n_obs, const
   A((void**)&ba->cams_new, sizeof(double) * 6 * (size_t)n_cam);
   A((void**)&ba->pts, sizeof(double) * 3 * (size_t)n_pt);
   A((void**)&ba->pts_new, sizeof(double) * 3 * (size_t)n_pt);
-  A((void**)&ba->cam_pre, sizeof(double) * CAM_PRE * (size_t)n_cam);
+  A((void**)&ba->cam_pre, sizeof(double) * CAM_PRE * (size_t)n_cam + 16);   // +16: bulk copies are 16-byte granular
   A((void**)&ba->S, sizeof(float) * ba->sys_count);
   A((void**)&ba->A64, sizeof(double) * ((size_t)n + 1) * n);
   A((void**)&ba->dc, sizeof(double) * (size_t)n);

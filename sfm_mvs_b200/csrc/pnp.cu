@@ -191,16 +191,26 @@ __device__ __forceinline__ void warp_jacobi12(EpnpShared& sh, int lane) {
   }
 }
 
+// The RNG index stream depends only on N: for the default 100 iterations the host draws it (a few
+// microseconds) and passes it by value in the kernel parameter block — no copy, no extra launch.
+struct PnpSubsets {
+  int count;            // iterations covered by idx (0: draw in the kernel)
+  int idx[500];
+};
+
 __global__ void __launch_bounds__(32) pnp_epnp_kernel(const float* __restrict__ X, const float* __restrict__ px, int n,
-                                                      int H, PnpCam cam, double* __restrict__ poses,
-                                                      double* __restrict__ rt6, unsigned char* __restrict__ valid) {
+                                                      int H, PnpCam cam, const __grid_constant__ PnpSubsets subs,
+                                                      double* __restrict__ poses, double* __restrict__ rt6,
+                                                      unsigned char* __restrict__ valid) {
   __shared__ EpnpShared sh;
   const int h = blockIdx.x, lane = threadIdx.x;
   if (h >= H) return;
   const hm::EpnpCam ec = {cam.fx, cam.fy, cam.cx, cam.cy};
   if (lane == 0) {
     int sub[5] = {0, 1, 2, 3, 4};
-    if (n > 5) {                                   // the subset iteration h of OpenCV's RANSAC draws
+    if (n > 5 && h < subs.count) {
+      for (int k = 0; k < 5; ++k) sub[k] = subs.idx[5 * h + k];
+    } else if (n > 5) {                            // the subset iteration h of OpenCV's RANSAC draws
       unsigned long long state = 0xFFFFFFFFFFFFFFFFull;
       for (int it = 0; it <= h; ++it)
         for (int i = 0; i < 5; ++i)
@@ -477,8 +487,10 @@ __global__ void __launch_bounds__(REFINE_THREADS) pnp_refine_kernel(const float*
     prev_err = 0.0;
   }
   __syncthreads();
+  // Every pass evaluates the residual AND the normal equations at `param`: when the candidate is
+  // accepted its linearisation is already there (OpenCV's CHECK_ERR -> CALC_J pair in one pass).
   for (int guard = 0; guard < 2000; ++guard) {
-    const int state = s_state;
+    const int state = s_state;       // 0: first linearisation, 1: candidate check, 2: done
     if (state == 2) break;
     if (threadIdx.x == 0) pose_jacobian_setup(param, &pj);
     __syncthreads();
@@ -498,65 +510,60 @@ __global__ void __launch_bounds__(REFINE_THREADS) pnp_refine_kernel(const float*
       double xn = x * iz, yn = y * iz;
       double ex = xn * cam.fx + cam.cx - ox, ey = yn * cam.fy + cam.cy - oy;
       acc[27] += ex * ex + ey * ey;
-      if (state == 0) {
-        double J[2][6];
-        // d(u,v)/dY
-        double a0 = cam.fx * iz, a2 = -cam.fx * xn * iz, b1 = cam.fy * iz, b2 = -cam.fy * yn * iz;
+      double J[2][6];
+      double a0 = cam.fx * iz, a2 = -cam.fx * xn * iz, b1 = cam.fy * iz, b2 = -cam.fy * yn * iz;
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          const double* D = pj.dR[k];
-          double dx = D[0] * Xw[0] + D[1] * Xw[1] + D[2] * Xw[2];
-          double dy = D[3] * Xw[0] + D[4] * Xw[1] + D[5] * Xw[2];
-          double dz = D[6] * Xw[0] + D[7] * Xw[1] + D[8] * Xw[2];
-          J[0][k] = a0 * dx + a2 * dz;
-          J[1][k] = b1 * dy + b2 * dz;
-        }
-        J[0][3] = a0; J[0][4] = 0.0; J[0][5] = a2;
-        J[1][3] = 0.0; J[1][4] = b1; J[1][5] = b2;
-        int k = 0;
-#pragma unroll
-        for (int a = 0; a < 6; ++a) {
-#pragma unroll
-          for (int b = a; b < 6; ++b) acc[k++] += J[0][a] * J[0][b] + J[1][a] * J[1][b];
-        }
-#pragma unroll
-        for (int a = 0; a < 6; ++a) acc[21 + a] += J[0][a] * ex + J[1][a] * ey;
+      for (int k = 0; k < 3; ++k) {
+        const double* D = pj.dR[k];
+        double dx = D[0] * Xw[0] + D[1] * Xw[1] + D[2] * Xw[2];
+        double dy = D[3] * Xw[0] + D[4] * Xw[1] + D[5] * Xw[2];
+        double dz = D[6] * Xw[0] + D[7] * Xw[1] + D[8] * Xw[2];
+        J[0][k] = a0 * dx + a2 * dz;
+        J[1][k] = b1 * dy + b2 * dz;
       }
+      J[0][3] = a0; J[0][4] = 0.0; J[0][5] = a2;
+      J[1][3] = 0.0; J[1][4] = b1; J[1][5] = b2;
+      int k = 0;
+#pragma unroll
+      for (int a = 0; a < 6; ++a) {
+#pragma unroll
+        for (int b = a; b < 6; ++b) acc[k++] += J[0][a] * J[0][b] + J[1][a] * J[1][b];
+      }
+#pragma unroll
+      for (int a = 0; a < 6; ++a) acc[21 + a] += J[0][a] * ex + J[1][a] * ey;
     }
     block_reduce_acc(acc, sh, red);
     if (threadIdx.x == 0) {
       const double err_norm = sqrt(red[27]);
-      if (state == 0) {          // CALC_J: new linearisation at `param`
-        for (int k = 0; k < 21; ++k) JtJ[k] = red[k];
-        for (int k = 0; k < 6; ++k) { JtE[k] = red[21 + k]; prev_param[k] = param[k]; }
-        double dx[6];
-        solve6_damped(JtJ, JtE, exp(lambda_lg10 * log(10.0)), dx);
-        for (int k = 0; k < 6; ++k) param[k] = prev_param[k] - dx[k];
-        if (iters == 0) prev_err = err_norm;
-        s_state = 1;
-      } else {                   // CHECK_ERR at the candidate `param`
+      bool relinearise = (state == 0);
+      if (state == 1) {
         bool retry = false;
         if (err_norm > prev_err) {
           lambda_lg10 += 1.0;
-          if (lambda_lg10 <= 16.0) {
+          if (lambda_lg10 <= 16.0) {               // reject: larger damping, same linearisation
             double dx[6];
             solve6_damped(JtJ, JtE, exp(lambda_lg10 * log(10.0)), dx);
             for (int k = 0; k < 6; ++k) param[k] = prev_param[k] - dx[k];
             retry = true;
           }
         }
-        if (!retry) {
+        if (!retry) {                               // accept
           lambda_lg10 = fmax(lambda_lg10 - 1.0, -16.0);
           double dn = 0.0, pn = 0.0;
           for (int k = 0; k < 6; ++k) { double d = param[k] - prev_param[k]; dn += d * d; pn += prev_param[k] * prev_param[k]; }
           iters += 1;
-          if (iters >= max_iter || sqrt(dn) / (sqrt(pn) + DBL_EPSILON) < (double)FLT_EPSILON) {
-            s_state = 2;
-          } else {
-            prev_err = err_norm;
-            s_state = 0;
-          }
+          if (iters >= max_iter || sqrt(dn) / (sqrt(pn) + DBL_EPSILON) < (double)FLT_EPSILON) s_state = 2;
+          else relinearise = true;
         }
+      }
+      if (relinearise) {
+        for (int k = 0; k < 21; ++k) JtJ[k] = red[k];
+        for (int k = 0; k < 6; ++k) { JtE[k] = red[21 + k]; prev_param[k] = param[k]; }
+        prev_err = err_norm;
+        double dx[6];
+        solve6_damped(JtJ, JtE, exp(lambda_lg10 * log(10.0)), dx);
+        for (int k = 0; k < 6; ++k) param[k] = prev_param[k] - dx[k];
+        s_state = 1;
       }
     }
     __syncthreads();
@@ -667,7 +674,10 @@ static int pnp_ransac_impl(sfm_ctx* ctx, const float* X, const float* px, int n,
     SFM_CUDA(cudaMemcpyAsync(drt6, hp + 12 * (size_t)H, sizeof(double) * 6 * H, cudaMemcpyHostToDevice, ctx->stream));
     SFM_CUDA(cudaMemcpyAsync(dvalid, hv, H, cudaMemcpyHostToDevice, ctx->stream));
   } else {
-    SFM_LAUNCH(ctx, SFM_K_PNP_EPNP, (pnp_epnp_kernel<<<H, 32, 0, ctx->stream>>>(dX, dpx, n, H, cam, dposes, drt6, dvalid)));
+    PnpSubsets subs;
+    subs.count = (n > 5 && H <= 100) ? H : 0;
+    if (subs.count) ransac_subsets(n, subs.count, subs.idx);
+    SFM_LAUNCH(ctx, SFM_K_PNP_EPNP, (pnp_epnp_kernel<<<H, 32, 0, ctx->stream>>>(dX, dpx, n, H, cam, subs, dposes, drt6, dvalid)));
   }
   SFM_CUDA(cudaMemsetAsync(dcounts, 0, sizeof(int32_t) * H, ctx->stream));
   dim3 grid(div_up(n, 256), div_up(H, PNP_HG));

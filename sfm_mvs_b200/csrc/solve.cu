@@ -43,6 +43,7 @@ __device__ __forceinline__ void warp_chol32(double (&r)[NB], int lane, int nb, i
 
 __global__ void __launch_bounds__(64) chol_panel_kernel(double* __restrict__ A, int n, int k0, int* __restrict__ info) {
   __shared__ double L[NB][NB + 1];
+  __shared__ double inv_d[NB];
   const int nb = min(NB, n - k0);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (warp == 0) {
@@ -53,6 +54,9 @@ __global__ void __launch_bounds__(64) chol_panel_kernel(double* __restrict__ A, 
     warp_chol32(r, lane, nb, blockIdx.x == 0 ? info : nullptr, k0);
 #pragma unroll
     for (int j = 0; j < NB; ++j) L[lane][j] = (j <= lane) ? r[j] : 0.0;
+#pragma unroll
+    for (int j = 0; j < NB; ++j)
+      if (j == lane) inv_d[lane] = 1.0 / r[j];
     if (blockIdx.x == 0 && lane < nb) {
 #pragma unroll
       for (int j = 0; j < NB; ++j)
@@ -71,7 +75,7 @@ __global__ void __launch_bounds__(64) chol_panel_kernel(double* __restrict__ A, 
     double s = x[j];
 #pragma unroll
     for (int k = 0; k < j; ++k) s -= x[k] * L[j][k];
-    x[j] = s / L[j][j];
+    x[j] = s * inv_d[j];
   }
 #pragma unroll
   for (int j = 0; j < NB; ++j)
@@ -129,15 +133,22 @@ __global__ void __launch_bounds__(256) chol_syrk_kernel(double* __restrict__ A, 
 __global__ void __launch_bounds__(256) chol_back_kernel(const double* __restrict__ A, int n, int k0, double* __restrict__ y,
                                                         double* __restrict__ x) {
   __shared__ double xs[NB];
+  __shared__ double Ls[NB][NB + 1];
   const int nb = min(NB, n - k0);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) {
+    int r = e / NB, c = e % NB;
+    Ls[r][c] = (r < nb && c <= r) ? A[(size_t)(k0 + r) * n + k0 + c] : ((r == c) ? 1.0 : 0.0);
+  }
+  __syncthreads();
   if (warp == 0) {
     double v = (lane < nb) ? y[k0 + lane] : 0.0;
-    for (int j = nb - 1; j >= 0; --j) {
-      double ljj = A[(size_t)(k0 + j) * n + k0 + j];
-      double xj = __shfl_sync(0xffffffffu, v, j) / ljj;
+    const double inv = 1.0 / Ls[lane][lane];
+#pragma unroll
+    for (int j = NB - 1; j >= 0; --j) {
+      double xj = __shfl_sync(0xffffffffu, v * inv, j);
       if (lane == j) v = xj;
-      if (lane < j) v -= A[(size_t)(k0 + j) * n + k0 + lane] * xj;
+      if (lane < j) v -= Ls[j][lane] * xj;
     }
     xs[lane] = v;
     if (blockIdx.x == 0 && lane < nb) x[k0 + lane] = v;
