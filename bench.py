@@ -298,12 +298,10 @@ def bench_ba(args, ctx, world, rank, pk, barrier, max_over_ranks):
 
     C_, P_, opp = args.ba_cams, args.ba_points, args.ba_obs_per_point
     pb = synth.ba_problem(C_, P_, opp, seed=0)                      # identical on every rank
-    # shard by point (contiguous ranges; every point has opp observations, so ranges balance)
-    lo, hi = (P_ * rank) // world, (P_ * (rank + 1)) // world
-    osel = slice(lo * opp, hi * opp)
-    prob = sfm.BAProblem(ctx, C_, hi - lo, pb["cam_idx"][osel], pb["pt_idx"][osel] - lo, pb["obs"][osel], pb["K"],
-                         totals=(P_, P_ * opp))
-    prob.set_params(pb["cams0"], pb["pts0"][lo:hi])
+    from sfm_mvs_b200 import sharding
+    sh = sharding.ba_shard(pb, rank, world)                         # contiguous point ranges, all cameras
+    prob = sfm.BAProblem(ctx, C_, len(sh["pts0"]), sh["cam_idx"], sh["pt_idx"], sh["obs"], sh["K"], totals=sh["totals"])
+    prob.set_params(sh["cams0"], sh["pts0"])
     if world > 1:
         uid = [sfm.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)

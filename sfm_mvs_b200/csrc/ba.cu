@@ -561,7 +561,7 @@ extern "C" int sfm_ba_create(sfm_ctx* ctx, int n_cam, int n_pt, int n_obs, const
   A((void**)&ba->pts_new, sizeof(double) * 3 * (size_t)n_pt);
   A((void**)&ba->cam_pre, sizeof(double) * CAM_PRE * (size_t)n_cam + 16);   // +16: bulk copies are 16-byte granular
   A((void**)&ba->S, sizeof(float) * ba->sys_count);
-  A((void**)&ba->A64, sizeof(double) * ((size_t)n + 1) * n);
+  A((void**)&ba->A64, sizeof(double) * sfm_spd_scratch_doubles(n));
   A((void**)&ba->dc, sizeof(double) * (size_t)n);
   A((void**)&ba->scal, sizeof(double) * 8);
   A((void**)&ba->info, sizeof(int));

@@ -1,16 +1,21 @@
 // solve.cu — dense symmetric-positive-definite solve of the reduced camera system (n = 6C; 3000 at
-// C = 500), float64, hand-written right-looking blocked Cholesky with NB = 32:
+// C = 500), float64, hand-written right-looking blocked Cholesky with NB = 32 and look-ahead.
 //
 //   A is (n+1) x n row-major, lower triangle used; row n carries the right-hand side, so the
-//   forward substitution L y = b falls out of the panel solves for free (row n ends up as y^T).
-//   per block column k:
-//     chol_panel_kernel  every CTA factors the 32x32 diagonal block redundantly in warp 0 with
-//                        register rows + shuffles (no block-level sync per column), then each
-//                        thread solves one row of the panel below against it (x L_kk^T = a)
-//     chol_syrk_kernel   trailing update A22 -= L21 L21^T, 64x64 tile per CTA, 4x4 per thread,
-//                        K = 32 staged in shared memory, lower-triangular tiles only
-//   backward substitution L^T x = y, one kernel per block from the bottom up: warp 0 of every CTA
-//   solves the transposed 32x32 triangle with shuffles, then each thread updates one earlier entry.
+//   forward substitution L y = b falls out of the panel products for free (row n ends up as y^T).
+//   Every 32x32 diagonal block is factored by ONE warp with its rows in registers (shuffles, no
+//   block-level sync per column) and its inverse L_kk^-1 is kept in a side buffer, which turns the
+//   two triangular solves into plain products without serial dependence chains:
+//     chol_diag_kernel   block 0 only: factor + invert
+//     chol_panel_kernel  rows below block k (incl. the rhs row): x = a * L_kk^-T, one row per thread
+//     chol_syrk_kernel   trailing update A22 -= L21 L21^T, 64x64 tile per CTA, 4x4 per thread, K = 32
+//                        staged in shared memory, lower-triangular tiles only; the CTA that owns the
+//                        first tile then factors + inverts diagonal block k+1 (look-ahead), so the
+//                        serial part of step k+1 overlaps the rest of step k's update
+//   backward substitution L^T x = y in 256-row super-blocks from the bottom up:
+//     back_diag_kernel   one CTA: eight 32-row sub-steps, x_s = L_ss^-T y_s then update of the
+//                        super-block's earlier rows
+//     back_update_kernel all earlier entries: y[i] -= sum_r L[k0+r][i] x[k0+r]
 #include <math.h>
 
 #include "common.cuh"
@@ -19,63 +24,77 @@
 namespace {
 
 constexpr int NB = 32;
+constexpr int SB = 256;   // backward-substitution super-block
 
-// Cholesky of a 32x32 SPD block held one row per lane (r[j], j <= lane meaningful).  Rows >= nb are
-// treated as identity.  On return lane i holds row i of L.
-__device__ __forceinline__ void warp_chol32(double (&r)[NB], int lane, int nb, int* info, int k0) {
-#pragma unroll
+// Factor + invert the 32x32 diagonal block starting at k0 with ONE warp, entirely in shared memory
+// (row stride 33 doubles: lane-per-row accesses are conflict-free, same-address reads broadcast), so it
+// costs few registers and can ride inside the update kernel.  Rows >= nb are treated as identity.
+// Reads the lower triangle of A, writes L back and L^-1 to Linv + (k0/NB)*NB*NB.
+__device__ __forceinline__ void factor_diag_block(double* __restrict__ A, int n, int k0, double* __restrict__ Linv,
+                                                  int* __restrict__ info, int lane, double (*Ls)[NB + 1],
+                                                  double (*Li)[NB + 1], double* __restrict__ Ld) {
+  const int nb = min(NB, n - k0);
+  for (int j = 0; j < NB; ++j)
+    Ls[lane][j] = (lane < nb && j <= lane) ? A[(size_t)(k0 + lane) * n + k0 + j] : ((j == lane) ? 1.0 : 0.0);
+  __syncwarp();
   for (int j = 0; j < NB; ++j) {
-    double d = __shfl_sync(0xffffffffu, r[j], j);
+    double d = Ls[j][j];
     if (j < nb && !(d > 0.0)) {
-      if (lane == 0 && info && *info == 0) *info = k0 + j + 1;
+      if (lane == 0 && info && *info == 0) *info = k0 + j + 1;   // not positive definite
       d = 1.0;
     }
-    const double ljj = sqrt(d);
-    const double lij = (lane == j) ? ljj : r[j] / ljj;      // column j of L, valid for lane >= j
-    r[j] = lij;
-#pragma unroll
-    for (int c = j + 1; c < NB; ++c) {
-      const double lcj = __shfl_sync(0xffffffffu, lij, c);
-      if (lane >= c) r[c] -= lij * lcj;
-    }
+    const double rinv = rsqrt(d);
+    const double lij = (lane == j) ? d * rinv : Ls[lane][j] * rinv;   // column j of L (lanes >= j)
+    __syncwarp();
+    Ls[lane][j] = (lane >= j) ? lij : 0.0;
+    if (lane == j) Ld[j] = rinv;
+    __syncwarp();
+    for (int c = j + 1; c < NB; ++c)
+      if (lane >= c) Ls[lane][c] = fma(-lij, Ls[c][j], Ls[lane][c]);
+    __syncwarp();
+  }
+  // lane c solves L z = e_c  ->  column c of L^-1 (kept in its own column of Li)
+  for (int i = 0; i < NB; ++i) {
+    double s = (i == lane) ? 1.0 : 0.0;
+    for (int k = lane; k < i; ++k) s = fma(-Ls[i][k], Li[k][lane], s);
+    Li[i][lane] = (i >= lane) ? s * Ld[i] : 0.0;
+  }
+  __syncwarp();
+  double* out = Linv + (size_t)(k0 / NB) * NB * NB;
+  for (int i = 0; i < NB; ++i) {
+    out[i * NB + lane] = Li[i][lane];
+    if (i < nb && lane <= i) A[(size_t)(k0 + i) * n + k0 + lane] = Ls[i][lane];
   }
 }
 
-__global__ void __launch_bounds__(64) chol_panel_kernel(double* __restrict__ A, int n, int k0, int* __restrict__ info) {
-  __shared__ double L[NB][NB + 1];
-  __shared__ double inv_d[NB];
+__global__ void __launch_bounds__(32) chol_diag_kernel(double* __restrict__ A, int n, int k0, double* __restrict__ Linv,
+                                                       int* __restrict__ info) {
+  __shared__ double Ls[NB][NB + 1];
+  __shared__ double Li[NB][NB + 1];
+  __shared__ double Ld[NB];
+  factor_diag_block(A, n, k0, Linv, info, threadIdx.x, Ls, Li, Ld);
+}
+
+// rows k0+nb .. n (the last one is the rhs row): a <- a * L_kk^-T
+__global__ void __launch_bounds__(128) chol_panel_kernel(double* __restrict__ A, int n, int k0,
+                                                         const double* __restrict__ Linv) {
+  __shared__ double Li[NB][NB + 1];
   const int nb = min(NB, n - k0);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (warp == 0) {
-    double r[NB];
-#pragma unroll
-    for (int j = 0; j < NB; ++j)
-      r[j] = (lane < nb && j <= lane) ? A[(size_t)(k0 + lane) * n + k0 + j] : ((j == lane) ? 1.0 : 0.0);
-    warp_chol32(r, lane, nb, blockIdx.x == 0 ? info : nullptr, k0);
-#pragma unroll
-    for (int j = 0; j < NB; ++j) L[lane][j] = (j <= lane) ? r[j] : 0.0;
-#pragma unroll
-    for (int j = 0; j < NB; ++j)
-      if (j == lane) inv_d[lane] = 1.0 / r[j];
-    if (blockIdx.x == 0 && lane < nb) {
-#pragma unroll
-      for (int j = 0; j < NB; ++j)
-        if (j <= lane) A[(size_t)(k0 + lane) * n + k0 + j] = r[j];
-    }
-  }
+  const double* src = Linv + (size_t)(k0 / NB) * NB * NB;
+  for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) Li[e / NB][e % NB] = src[e];
   __syncthreads();
-  const int row = k0 + nb + blockIdx.x * blockDim.x + threadIdx.x;      // rows below the block, incl. the rhs row n
+  const int row = k0 + nb + blockIdx.x * blockDim.x + threadIdx.x;
   if (row > n) return;
   double* a = A + (size_t)row * n + k0;
-  double x[NB];
+  double v[NB], x[NB];
 #pragma unroll
-  for (int j = 0; j < NB; ++j) x[j] = (j < nb) ? a[j] : 0.0;
+  for (int j = 0; j < NB; ++j) v[j] = (j < nb) ? a[j] : 0.0;
 #pragma unroll
   for (int j = 0; j < NB; ++j) {
-    double s = x[j];
+    double s = 0.0;
 #pragma unroll
-    for (int k = 0; k < j; ++k) s -= x[k] * L[j][k];
-    x[j] = s * inv_d[j];
+    for (int c = 0; c <= j; ++c) s = fma(v[c], Li[j][c], s);
+    x[j] = s;
   }
 #pragma unroll
   for (int j = 0; j < NB; ++j)
@@ -83,7 +102,8 @@ __global__ void __launch_bounds__(64) chol_panel_kernel(double* __restrict__ A, 
 }
 
 // rows [base, n] (n+1-base of them, the last is the rhs row), columns [base, n)
-__global__ void __launch_bounds__(256) chol_syrk_kernel(double* __restrict__ A, int n, int k0, int nb, int n_row_tiles) {
+__global__ void __launch_bounds__(256) chol_syrk_kernel(double* __restrict__ A, int n, int k0, int nb,
+                                                        double* __restrict__ Linv, int* __restrict__ info) {
   __shared__ double Pi[64][NB + 1];
   __shared__ double Pj[64][NB + 1];
   int t = blockIdx.x;
@@ -125,40 +145,65 @@ __global__ void __launch_bounds__(256) chol_syrk_kernel(double* __restrict__ A, 
       int i = i0 + ty + 16 * a, j = j0 + tx + 16 * b;
       if (i <= n && j < n && j <= i) A[(size_t)i * n + j] -= acc[a][b];
     }
+  // look-ahead: the first tile now holds the final values of diagonal block k+1
+  if (t == 0) {
+    __syncthreads();
+    if (threadIdx.x < 32)
+      factor_diag_block(A, n, base, Linv, info, threadIdx.x, reinterpret_cast<double(*)[NB + 1]>(&Pi[0][0]),
+                        reinterpret_cast<double(*)[NB + 1]>(&Pj[0][0]), &Pi[32][0]);
+  }
 }
 
-// y (row n of A after the factorisation) is consumed in place; the solution goes to a separate
-// array so that CTAs starting late still read the unsolved y_k.
-// Block k: x_k = L_kk^-T y_k ; y[0:k0] -= L[k-block rows, 0:k0]^T x_k.
-__global__ void __launch_bounds__(256) chol_back_kernel(const double* __restrict__ A, int n, int k0, double* __restrict__ y,
+// One CTA per call: rows [k0, k0+sb) of L^T x = y, eight 32-row sub-steps from the bottom.
+__global__ void __launch_bounds__(256) back_diag_kernel(const double* __restrict__ A, int n, int k0, int sb,
+                                                        const double* __restrict__ Linv, double* __restrict__ y,
                                                         double* __restrict__ x) {
+  __shared__ double ys[SB];
   __shared__ double xs[NB];
-  __shared__ double Ls[NB][NB + 1];
-  const int nb = min(NB, n - k0);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) {
-    int r = e / NB, c = e % NB;
-    Ls[r][c] = (r < nb && c <= r) ? A[(size_t)(k0 + r) * n + k0 + c] : ((r == c) ? 1.0 : 0.0);
-  }
+  for (int i = threadIdx.x; i < SB; i += blockDim.x) ys[i] = (i < sb) ? y[k0 + i] : 0.0;
   __syncthreads();
-  if (warp == 0) {
-    double v = (lane < nb) ? y[k0 + lane] : 0.0;
-    const double inv = 1.0 / Ls[lane][lane];
-#pragma unroll
-    for (int j = NB - 1; j >= 0; --j) {
-      double xj = __shfl_sync(0xffffffffu, v * inv, j);
-      if (lane == j) v = xj;
-      if (lane < j) v -= Ls[j][lane] * xj;
+  const int nsub = (sb + NB - 1) / NB;
+  for (int s = nsub - 1; s >= 0; --s) {
+    const int r0 = k0 + s * NB;                       // global row of the sub-block
+    const int nb = min(NB, n - r0);
+    if (threadIdx.x < 32) {
+      // x_s = L_ss^-T y_s : lane j sums Linv[i][j] * y[i] over i >= j
+      const double* Li = Linv + (size_t)(r0 / NB) * NB * NB;
+      const int lane = threadIdx.x;
+      double acc = 0.0;
+      for (int i = 0; i < nb; ++i) acc = fma(Li[i * NB + lane], ys[s * NB + i], acc);
+      xs[lane] = acc;
+      if (lane < nb) x[r0 + lane] = acc;
     }
-    xs[lane] = v;
-    if (blockIdx.x == 0 && lane < nb) x[k0 + lane] = v;
+    __syncthreads();
+    // earlier rows of this super-block: y[i] -= sum_r L[r0+r][k0+i] x_s[r]
+    for (int i = threadIdx.x; i < s * NB; i += blockDim.x) {
+      double acc = 0.0;
+      for (int r = 0; r < nb; ++r) acc = fma(A[(size_t)(r0 + r) * n + k0 + i], xs[r], acc);
+      ys[i] -= acc;
+    }
+    __syncthreads();
   }
+}
+
+// y[i] -= sum_{r < sb} L[k0+r][i] x[k0+r] for i < k0
+__global__ void __launch_bounds__(128) back_update_kernel(const double* __restrict__ A, int n, int k0, int sb,
+                                                          const double* __restrict__ x, double* __restrict__ y) {
+  __shared__ double xs[SB];
+  for (int i = threadIdx.x; i < sb; i += blockDim.x) xs[i] = x[k0 + i];
   __syncthreads();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= k0) return;
-  double s = 0.0;
-  for (int r = 0; r < nb; ++r) s = fma(A[(size_t)(k0 + r) * n + i], xs[r], s);
-  y[i] -= s;
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  int r = 0;
+  for (; r + 3 < sb; r += 4) {
+    a0 = fma(A[(size_t)(k0 + r) * n + i], xs[r], a0);
+    a1 = fma(A[(size_t)(k0 + r + 1) * n + i], xs[r + 1], a1);
+    a2 = fma(A[(size_t)(k0 + r + 2) * n + i], xs[r + 2], a2);
+    a3 = fma(A[(size_t)(k0 + r + 3) * n + i], xs[r + 3], a3);
+  }
+  for (; r < sb; ++r) a0 = fma(A[(size_t)(k0 + r) * n + i], xs[r], a0);
+  y[i] -= (a0 + a1) + (a2 + a3);
 }
 
 __global__ void widen_kernel(const float* __restrict__ S, const float* __restrict__ g, int n, double* __restrict__ A) {
@@ -171,22 +216,32 @@ __global__ void widen_kernel(const float* __restrict__ S, const float* __restric
 
 }  // namespace
 
+size_t sfm_spd_scratch_doubles(int n) {
+  return ((size_t)n + 1) * n + (size_t)div_up(n, NB) * NB * NB;
+}
+
 int sfm_spd_solve(sfm_ctx* ctx, const float* S, const float* g, int n, double* A, double* x, int* info) {
   size_t total = (size_t)(n + 1) * n;
+  double* Linv = A + total;
   SFM_LAUNCH(ctx, SFM_K_BA_SOLVE, (widen_kernel<<<(unsigned)div_up64((int64_t)total, 256), 256, 0, ctx->stream>>>(S, g, n, A)));
   SFM_CUDA(cudaMemsetAsync(info, 0, sizeof(int), ctx->stream));
+  SFM_LAUNCH(ctx, SFM_K_BA_SOLVE, (chol_diag_kernel<<<1, 32, 0, ctx->stream>>>(A, n, 0, Linv, info)));
   for (int k0 = 0; k0 < n; k0 += NB) {
     const int nb = std::min(NB, n - k0);
     const int rows_below = n + 1 - (k0 + nb);                 // >= 1: the rhs row
-    SFM_LAUNCH(ctx, SFM_K_BA_SOLVE, (chol_panel_kernel<<<div_up(rows_below, 64), 64, 0, ctx->stream>>>(A, n, k0, info)));
+    SFM_LAUNCH(ctx, SFM_K_BA_SOLVE, (chol_panel_kernel<<<div_up(rows_below, 128), 128, 0, ctx->stream>>>(A, n, k0, Linv)));
     const int cols = n - (k0 + nb);
     if (cols > 0) {
       const int tiles = div_up(rows_below, 64);
-      SFM_LAUNCH(ctx, SFM_K_BA_SOLVE, (chol_syrk_kernel<<<tiles * (tiles + 1) / 2, 256, 0, ctx->stream>>>(A, n, k0, nb, tiles)));
+      SFM_LAUNCH(ctx, SFM_K_BA_SOLVE, (chol_syrk_kernel<<<tiles * (tiles + 1) / 2, 256, 0, ctx->stream>>>(A, n, k0, nb, Linv, info)));
     }
   }
   double* y = A + (size_t)n * n;
-  for (int k0 = ((n - 1) / NB) * NB; k0 >= 0; k0 -= NB)
-    SFM_LAUNCH(ctx, SFM_K_BA_SOLVE, (chol_back_kernel<<<std::max(1, div_up(k0, 256)), 256, 0, ctx->stream>>>(A, n, k0, y, x)));
+  for (int k0 = ((n - 1) / SB) * SB; k0 >= 0; k0 -= SB) {
+    const int sb = std::min(SB, n - k0);
+    SFM_LAUNCH(ctx, SFM_K_BA_SOLVE, (back_diag_kernel<<<1, 256, 0, ctx->stream>>>(A, n, k0, sb, Linv, y, x)));
+    if (k0 > 0)
+      SFM_LAUNCH(ctx, SFM_K_BA_SOLVE, (back_update_kernel<<<div_up(k0, 128), 128, 0, ctx->stream>>>(A, n, k0, sb, x, y)));
+  }
   return SFM_OK;
 }

@@ -7,4 +7,6 @@
 // Solves S x = -g.  S (n x n float32, lower triangle read), g (n float32), A: (n+1) x n float64
 // scratch (factor L is left in its lower triangle), x (n float64), info: device int, 0 or the
 // 1-based index of the first non-positive pivot.  Stream-ordered, no host synchronisation.
+// doubles of scratch `A` must provide: (n+1) x n matrix + the inverses of the 32x32 diagonal blocks
+size_t sfm_spd_scratch_doubles(int n);
 int sfm_spd_solve(sfm_ctx* ctx, const float* S, const float* g, int n, double* A, double* x, int* info);

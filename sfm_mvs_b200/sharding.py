@@ -1,0 +1,52 @@
+"""Host-side partitioning of the hot path over ranks (one process per GPU).
+
+  * matching: independent (query view, train view) pairs — sfm.py:347 consecutive pairs or the
+    all-previous-pairs loop of isfm.py:68-87 — assigned by longest-processing-time-first on the
+    cost Nq*Nt.  No data-path collective.
+  * bundle adjustment: points (with all their observations) in contiguous ranges balanced by
+    observation count; every rank holds all cameras.  The only exchange per Gauss-Newton iteration
+    is the all-reduce(sum) of the partial reduced camera systems (csrc/comm.cu).
+  * the per-view registration chain is sequential (view i+1 needs view i's pose, sfm.py:399-409):
+    replicas only — independent scenes per rank.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def shard_pairs(pairs, costs, world: int):
+    """LPT assignment.  Returns a list (per rank) of lists of pair indices, each ascending."""
+    costs = np.asarray(costs, dtype=np.float64)
+    order = np.argsort(-costs, kind="stable")
+    load = np.zeros(world)
+    out = [[] for _ in range(world)]
+    for k in order:
+        r = int(np.argmin(load))
+        out[r].append(int(k))
+        load[r] += costs[k]
+    return [sorted(o) for o in out]
+
+
+def shard_points(pt_idx: np.ndarray, n_pt: int, world: int):
+    """Contiguous point ranges with ~equal observation counts.  pt_idx must be non-decreasing.
+    Returns [(p_lo, p_hi, o_lo, o_hi)] per rank."""
+    pt_idx = np.asarray(pt_idx)
+    counts = np.bincount(pt_idx, minlength=n_pt)
+    cum = np.concatenate([[0], np.cumsum(counts)])
+    total = cum[-1]
+    bounds = [0]
+    for r in range(1, world):
+        target = total * r / world
+        p = int(np.searchsorted(cum, target, side="left"))
+        bounds.append(min(max(p, bounds[-1]), n_pt))
+    bounds.append(n_pt)
+    return [(bounds[r], bounds[r + 1], int(cum[bounds[r]]), int(cum[bounds[r + 1]])) for r in range(world)]
+
+
+def ba_shard(problem: dict, rank: int, world: int) -> dict:
+    """Slice a synth.ba_problem-style dict for one rank (local point indices start at 0)."""
+    n_pt = len(problem["pts0"])
+    p_lo, p_hi, o_lo, o_hi = shard_points(problem["pt_idx"], n_pt, world)[rank]
+    return dict(K=problem["K"], cams0=problem["cams0"], pts0=problem["pts0"][p_lo:p_hi],
+                cam_idx=problem["cam_idx"][o_lo:o_hi], pt_idx=problem["pt_idx"][o_lo:o_hi] - p_lo,
+                obs=problem["obs"][o_lo:o_hi], p_lo=p_lo, p_hi=p_hi, totals=(n_pt, len(problem["pt_idx"])))
