@@ -14,8 +14,8 @@
 //   obs_uv  float2[O]   observations, sorted point-major      cam_idx int[O]     pt_idx int[O]
 //   pt_start int[P+1]   CSR offsets of each point's observations
 //   cams double[C][6] (rvec|tvec)   pts double[P][3]   (+ candidate copies for step rejection)
-//   cam_pre double[C][21]: R (9) | t (3) | Jl (9) — rotation matrix and the left Jacobian of SO(3),
-//                          recomputed once per linearisation by ba_cam_prep_kernel
+//   cam_pre 144-byte records [C]: R (9) | t (3) float64, Jl (9 of 12) float32 — rotation matrix and the
+//                          left Jacobian of SO(3), recomputed once per linearisation by ba_cam_prep_kernel
 //   S float[6C][6C] reduced camera system (lower block triangle filled), g float[6C]
 // Per observation:  Yr = R X,  Y = Yr + t,  (u,v) = (fx Y.x/Y.z + cx, fy Y.y/Y.z + cy)
 //   d(u,v)/dY = [[fx/z, 0, -fx Y.x/z^2], [0, fy/z, -fy Y.y/z^2]]
@@ -31,7 +31,7 @@
 
 namespace {
 
-constexpr int CAM_PRE = 21;
+constexpr int CAM_PRE = 18;   // doubles per camera record: R (9) | t (3) as float64, Jl (9, padded to 12) as float32 = 144 B
 constexpr int BA_MAXO = 64;   // observations per point handled by the fused kernels
 
 // ------------------------------------------------------------------ per-camera precomputation
@@ -44,6 +44,7 @@ __global__ void ba_cam_prep_kernel(const double* __restrict__ cams, int n_cam, d
   hm::rodrigues_to_matrix(rv, R);
   for (int k = 0; k < 9; ++k) o[k] = R[k];
   o[9] = rv[3]; o[10] = rv[4]; o[11] = rv[5];
+  float* jl = reinterpret_cast<float*>(o + 12);
   double th2 = rv[0] * rv[0] + rv[1] * rv[1] + rv[2] * rv[2];
   for (int k = 0; k < 3; ++k) {
     double a[3];
@@ -55,42 +56,48 @@ __global__ void ba_cam_prep_kernel(const double* __restrict__ cams, int n_cam, d
       double cx = rv[1] * m[2] - rv[2] * m[1], cy = rv[2] * m[0] - rv[0] * m[2], cz = rv[0] * m[1] - rv[1] * m[0];
       a[0] = (rv[k] * rv[0] + cx) / th2; a[1] = (rv[k] * rv[1] + cy) / th2; a[2] = (rv[k] * rv[2] + cz) / th2;
     }
-    o[12 + 3 * k] = a[0]; o[13 + 3 * k] = a[1]; o[14 + 3 * k] = a[2];
+    jl[3 * k] = (float)a[0]; jl[3 * k + 1] = (float)a[1]; jl[3 * k + 2] = (float)a[2];
   }
+  jl[9] = jl[10] = jl[11] = 0.f;
 }
 
 struct Intr {
   double fx, fy, cx, cy;
 };
 
-// residual (proj - obs) and, if WANT_J, the Jacobian blocks, all float64 in registers
+// residual (proj - obs) and, if WANT_J, the Jacobian blocks, in registers.  The camera record is read
+// with 16-byte loads (6 x double2 for R|t, 3 x float4 for Jl): from shared memory a 16-byte access is
+// served per quarter-warp, which keeps the random per-lane camera gather to ~2-3 wavefronts per load.
 template <bool WANT_J>
 __device__ __forceinline__ void obs_geometry(const double* __restrict__ cp, const double* __restrict__ X, float2 uv,
                                              const Intr& K, double* r, double (*Jc)[6], double (*Jp)[3]) {
-  const double Yr0 = cp[0] * X[0] + cp[1] * X[1] + cp[2] * X[2];
-  const double Yr1 = cp[3] * X[0] + cp[4] * X[1] + cp[5] * X[2];
-  const double Yr2 = cp[6] * X[0] + cp[7] * X[1] + cp[8] * X[2];
-  const double y0 = Yr0 + cp[9], y1 = Yr1 + cp[10], y2 = Yr2 + cp[11];
+  const double2* q = reinterpret_cast<const double2*>(cp);
+  const double2 q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3], q4 = q[4], q5 = q[5];
+  // R = [q0.x q0.y q1.x; q1.y q2.x q2.y; q3.x q3.y q4.x], t = (q4.y, q5.x, q5.y)
+  const double Yr0 = q0.x * X[0] + q0.y * X[1] + q1.x * X[2];
+  const double Yr1 = q1.y * X[0] + q2.x * X[1] + q2.y * X[2];
+  const double Yr2 = q3.x * X[0] + q3.y * X[1] + q4.x * X[2];
+  const double y0 = Yr0 + q4.y, y1 = Yr1 + q5.x, y2 = Yr2 + q5.y;
   const double iz = (y2 != 0.0) ? 1.0 / y2 : 1.0;
   const double xn = y0 * iz, yn = y1 * iz;
   r[0] = xn * K.fx + K.cx - (double)uv.x;
   r[1] = yn * K.fy + K.cy - (double)uv.y;
   if (WANT_J) {
+    const float4* f = reinterpret_cast<const float4*>(cp + 12);
+    const float4 f0 = f[0], f1 = f[1], f2 = f[2];
+    const double jl[9] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w, f2.x};
     const double a0 = K.fx * iz, a2 = -K.fx * xn * iz, b1 = K.fy * iz, b2 = -K.fy * yn * iz;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-      const double ax = cp[12 + 3 * k], ay = cp[13 + 3 * k], az = cp[14 + 3 * k];
+      const double ax = jl[3 * k], ay = jl[3 * k + 1], az = jl[3 * k + 2];
       const double dx = ay * Yr2 - az * Yr1, dy = az * Yr0 - ax * Yr2, dz = ax * Yr1 - ay * Yr0;
       Jc[0][k] = a0 * dx + a2 * dz;
       Jc[1][k] = b1 * dy + b2 * dz;
     }
     Jc[0][3] = a0; Jc[0][4] = 0.0; Jc[0][5] = a2;
     Jc[1][3] = 0.0; Jc[1][4] = b1; Jc[1][5] = b2;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      Jp[0][k] = a0 * cp[k] + a2 * cp[6 + k];
-      Jp[1][k] = b1 * cp[3 + k] + b2 * cp[6 + k];
-    }
+    Jp[0][0] = a0 * q0.x + a2 * q3.x; Jp[0][1] = a0 * q0.y + a2 * q3.y; Jp[0][2] = a0 * q1.x + a2 * q4.x;
+    Jp[1][0] = b1 * q1.y + b2 * q3.x; Jp[1][1] = b1 * q2.x + b2 * q3.y; Jp[1][2] = b1 * q2.y + b2 * q4.x;
   }
 }
 
@@ -102,8 +109,8 @@ __device__ __forceinline__ double warp_sum_d(double v) {
 
 // ------------------------------------------------------------------ K5: materialised evaluation
 // One persistent CTA of 1024 threads per SM; one observation per thread per trip: 16 B read (uv, cam
-// index, point index), 80 B written (r 8 B, Jc 48 B, Jp 24 B).  The per-camera table (C x 21 doubles,
-// 84 KB at C = 500) is staged into shared memory by ONE bulk-copy instruction (cp.async.bulk, the TMA
+// index, point index), 80 B written (r 8 B, Jc 48 B, Jp 24 B).  The per-camera table (C x 144 B,
+// 72 KB at C = 500) is staged into shared memory by ONE bulk-copy instruction (cp.async.bulk, the TMA
 // engine, completion on an mbarrier) when it fits, so the random per-observation camera gather never
 // leaves the SM; otherwise it is read through L1.
 __device__ __forceinline__ uint32_t ba_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

@@ -16,7 +16,7 @@ struct sfm_ba {
   int* pt_start = nullptr;
   // parameters and step candidates
   double *cams = nullptr, *cams_new = nullptr, *pts = nullptr, *pts_new = nullptr;
-  double* cam_pre = nullptr;                   // [C][21] R | t | Jl
+  double* cam_pre = nullptr;                   // [C] 144-byte records: R, t float64 | Jl float32
   // reduced camera system: one allocation S | g | hdiag (so one memset and one all-reduce cover it)
   float* S = nullptr;
   float* g = nullptr;
