@@ -28,14 +28,18 @@ namespace {
 constexpr int NB = 64;
 constexpr int SB = 256;   // backward-substitution super-block
 
-// Cholesky of the diagonal block at k0 by a 256-thread CTA.  Thread t holds row t/4, columns
-// 16*(t%4) .. +15 in registers.  Per column: owners publish the raw column in shared memory (double
-// buffered -> one barrier), every thread scales and applies the rank-1 update to its 16 entries.
+// Cholesky of the diagonal block at k0 by a 256-thread CTA.  Thread t holds row t%64, columns
+// 16*(t/64) .. +15 in registers (the column segment is warp-uniform, so warps whose segment is
+// already final, or lies entirely above their rows, skip a column step without divergence).
+// Per column j: the 64 owner threads publish the diagonal entry (64-thread named barrier), scale
+// their entry by 1/sqrt(d) and publish the scaled column; one block barrier; every live thread
+// applies the rank-1 update to its entries with one shared load + one FMA each.
 // Rows/columns >= nb are identity.  Writes L (lower) back to A and 1/diag(L) to dinv[k0 .. k0+63].
 __device__ __forceinline__ void factor_diag_block(double* __restrict__ A, int n, int k0, double* __restrict__ dinv,
-                                                  int* __restrict__ info, double (*colbuf)[NB]) {
+                                                  int* __restrict__ info, double (*colbuf)[NB + 2]) {
   const int nb = min(NB, n - k0);
-  const int row = threadIdx.x >> 2, cseg = threadIdx.x & 3;
+  const int row = threadIdx.x & 63, cseg = threadIdx.x >> 6;
+  const int warp_row_max = (row | 31);                  // largest row held by this warp
   double a[16];
 #pragma unroll
   for (int cc = 0; cc < 16; ++cc) {
@@ -47,22 +51,29 @@ __device__ __forceinline__ void factor_diag_block(double* __restrict__ A, int n,
 #pragma unroll
     for (int jj = 0; jj < 16; ++jj) {
       const int j = 16 * seg + jj;
-      double* cb = colbuf[j & 1];
-      if (cseg == seg) cb[row] = a[jj];
-      __syncthreads();
-      double d = cb[j];
-      if (j < nb && !(d > 0.0)) {
-        if (threadIdx.x == 0 && info && *info == 0) *info = k0 + j + 1;   // not positive definite
-        d = 1.0;
+      double* cb = colbuf[j & 1];                       // cb[0..63] scaled column, cb[64] raw diagonal
+      if (cseg == seg) {                                // owners of column j (two warps)
+        if (row == j) cb[NB] = a[jj];
+        asm volatile("bar.sync 1, 64;" ::: "memory");
+        double d = cb[NB];
+        if (j < nb && !(d > 0.0)) {
+          if (row == j && info && *info == 0) *info = k0 + j + 1;   // not positive definite
+          d = 1.0;
+        }
+        const double rinv = rsqrt(d);
+        const double li = (row == j) ? d * rinv : ((row > j) ? a[jj] * rinv : 0.0);   // L[row][j]
+        a[jj] = li;
+        cb[row] = li;
+        if (row == j) dinv[k0 + j] = rinv;
       }
-      const double rinv = rsqrt(d);
-      const double li = (row == j) ? d * rinv : cb[row] * rinv;          // L[row][j] (row >= j)
-      if (cseg == seg) a[jj] = (row >= j) ? li : 0.0;
-      if (threadIdx.x == 0) dinv[k0 + j] = rinv;
+      __syncthreads();
+      if (cseg >= seg && warp_row_max > j) {            // warp-uniform: something left to update
+        const double li = cb[row];
 #pragma unroll
-      for (int cc = 0; cc < 16; ++cc) {
-        const int c = 16 * cseg + cc;
-        if (c > j && row >= c) a[cc] = fma(-li, cb[c] * rinv, a[cc]);
+        for (int cc = 0; cc < 16; ++cc) {
+          const int c = 16 * cseg + cc;
+          if (c > j && row >= c) a[cc] = fma(-li, cb[c], a[cc]);
+        }
       }
     }
   }
@@ -75,15 +86,21 @@ __device__ __forceinline__ void factor_diag_block(double* __restrict__ A, int n,
 
 __global__ void __launch_bounds__(256) chol_diag_kernel(double* __restrict__ A, int n, int k0, double* __restrict__ dinv,
                                                         int* __restrict__ info) {
-  __shared__ double colbuf[2][NB];
+  __shared__ double colbuf[2][NB + 2];
   factor_diag_block(A, n, k0, dinv, info, colbuf);
 }
 
-// rows k0+nb .. n (the last one is the rhs row): solve x L_kk^T = a
-__global__ void __launch_bounds__(128) chol_panel_kernel(double* __restrict__ A, int n, int k0,
-                                                         const double* __restrict__ dinv) {
-  __shared__ double L[NB][NB + 1];
-  __shared__ double di[NB];
+// rows k0+nb .. n (the last one is the rhs row): solve x L_kk^T = a, one row per thread.  The
+// running solution lives in shared memory (column tid of xs: conflict-free), L_kk is read as
+// broadcasts, and the loops stay rolled so the kernel is a few hundred bytes of code instead of a
+// 2000-FMA straight line.
+constexpr int PANEL_THREADS = 64;
+__global__ void __launch_bounds__(PANEL_THREADS) chol_panel_kernel(double* __restrict__ A, int n, int k0,
+                                                                   const double* __restrict__ dinv) {
+  extern __shared__ double panel_smem[];
+  double (*L)[NB + 1] = reinterpret_cast<double(*)[NB + 1]>(panel_smem);
+  double (*xs)[PANEL_THREADS] = reinterpret_cast<double(*)[PANEL_THREADS]>(panel_smem + NB * (NB + 1));
+  double* di = panel_smem + NB * (NB + 1) + NB * PANEL_THREADS;
   const int nb = min(NB, n - k0);
   for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) {
     const int r = e / NB, c = e % NB;
@@ -94,19 +111,21 @@ __global__ void __launch_bounds__(128) chol_panel_kernel(double* __restrict__ A,
   const int row = k0 + nb + blockIdx.x * blockDim.x + threadIdx.x;
   if (row > n) return;
   double* a = A + (size_t)row * n + k0;
-  double x[NB];
-#pragma unroll
-  for (int j = 0; j < NB; ++j) x[j] = (j < nb) ? a[j] : 0.0;
-#pragma unroll
-  for (int j = 0; j < NB; ++j) {
-    double s = x[j];
-#pragma unroll
-    for (int k = 0; k < j; ++k) s = fma(-x[k], L[j][k], s);
-    x[j] = s * di[j];
+  const int t = threadIdx.x;
+  for (int j = 0; j < nb; ++j) {
+    double s0 = a[j], s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int k = 0;
+    for (; k + 3 < j; k += 4) {
+      s0 = fma(-xs[k][t], L[j][k], s0);
+      s1 = fma(-xs[k + 1][t], L[j][k + 1], s1);
+      s2 = fma(-xs[k + 2][t], L[j][k + 2], s2);
+      s3 = fma(-xs[k + 3][t], L[j][k + 3], s3);
+    }
+    for (; k < j; ++k) s0 = fma(-xs[k][t], L[j][k], s0);
+    const double xj = ((s0 + s1) + (s2 + s3)) * di[j];
+    xs[j][t] = xj;
+    a[j] = xj;
   }
-#pragma unroll
-  for (int j = 0; j < NB; ++j)
-    if (j < nb) a[j] = x[j];
 }
 
 // rows [base, n] (n+1-base of them, the last is the rhs row), columns [base, n)
@@ -160,7 +179,7 @@ __global__ void __launch_bounds__(256) chol_syrk_kernel(double* __restrict__ A, 
   // look-ahead: tile 0 of the update is exactly diagonal block k+1 and now holds its final values
   if (t == 0) {
     __syncthreads();
-    factor_diag_block(A, n, base, dinv, info, reinterpret_cast<double(*)[NB]>(&Pi[0][0]));
+    factor_diag_block(A, n, base, dinv, info, reinterpret_cast<double(*)[NB + 2]>(&Pi[0][0]));
   }
 }
 
@@ -188,11 +207,14 @@ __global__ void __launch_bounds__(256) back_diag_kernel(const double* __restrict
       v = ys[s * NB + threadIdx.x];
       di = (threadIdx.x < nb) ? dinv[r0 + threadIdx.x] : 1.0;
     }
-    for (int j = NB - 1; j >= 0; --j) {
-      if ((int)threadIdx.x == j) xs[j] = v * di;
-      __syncthreads();
-      if ((int)threadIdx.x < j) v = fma(-Ls[j][threadIdx.x], xs[j], v);
+    if (threadIdx.x < NB) {                          // two warps own the 64 unknowns
+      for (int j = NB - 1; j >= 0; --j) {
+        if ((int)threadIdx.x == j) xs[j] = v * di;
+        asm volatile("bar.sync 1, 64;" ::: "memory");
+        if ((int)threadIdx.x < j) v = fma(-Ls[j][threadIdx.x], xs[j], v);
+      }
     }
+    __syncthreads();
     if ((int)threadIdx.x < nb) x[r0 + threadIdx.x] = xs[threadIdx.x];
     // earlier rows of this super-block: y[i] -= sum_r L[r0+r][k0+i] x_s[r]
     for (int i = threadIdx.x; i < s * NB; i += blockDim.x) {
@@ -254,6 +276,12 @@ size_t sfm_spd_scratch_doubles(int n) {
 }
 
 int sfm_spd_solve(sfm_ctx* ctx, const float* S, const float* g, int n, double* A, double* x, int* info) {
+  constexpr size_t kPanelSmem = sizeof(double) * (NB * (NB + 1) + NB * PANEL_THREADS + NB);
+  static bool attr = false;
+  if (!attr) {
+    SFM_CUDA(cudaFuncSetAttribute(chol_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPanelSmem));
+    attr = true;
+  }
   const size_t total = (size_t)(n + 1) * n;
   double* dinv = A + total;
   SFM_LAUNCH(ctx, SFM_K_BA_SOLVE, (widen_kernel<<<dim3(div_up(n, 256), n + 1), 256, 0, ctx->stream>>>(S, g, n, A)));
@@ -262,7 +290,7 @@ int sfm_spd_solve(sfm_ctx* ctx, const float* S, const float* g, int n, double* A
   for (int k0 = 0; k0 < n; k0 += NB) {
     const int nb = std::min(NB, n - k0);
     const int rows_below = n + 1 - (k0 + nb);                 // >= 1: the rhs row
-    SFM_LAUNCH(ctx, SFM_K_BA_SOLVE, (chol_panel_kernel<<<div_up(rows_below, 128), 128, 0, ctx->stream>>>(A, n, k0, dinv)));
+    SFM_LAUNCH(ctx, SFM_K_BA_SOLVE, (chol_panel_kernel<<<div_up(rows_below, PANEL_THREADS), PANEL_THREADS, kPanelSmem, ctx->stream>>>(A, n, k0, dinv)));
     const int cols = n - (k0 + nb);
     if (cols > 0) {
       const int tiles = div_up(rows_below, 64);
