@@ -191,6 +191,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// Wait for outstanding tcgen05.ld and tie the destination registers to the wait, so that the compiler
+// cannot consume (or move) them before the asynchronous load has landed.
+__device__ __forceinline__ void tmem_ld_wait_regs(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                 "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                 "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :: "memory");
+}
 
 // K-major, no-swizzle shared-memory matrix descriptor (version 1 = Blackwell).
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
@@ -213,6 +223,7 @@ struct TcParams {
   int n_items;
   mkey_t* cand;                   // [n_qtiles*128][nsplit][2]
   float* dump;                    // debug: raw accumulators [n_qtiles*128][n_stages*256] or NULL
+  unsigned int key_mul;           // = 32, passed at run time so the key build stays an IMAD (FMA pipe)
 };
 
 // ============================================================================ K1 kernel
@@ -308,6 +319,11 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) match_tc_kernel(TcParams p) {
     const int row = quarter * 32 + lane;          // query row within the tile
     uint32_t acc_phase[2] = {0, 0};
     int buf = 0;
+    uint32_t jconst[32];            // 0..31 held in registers (opaque to the compiler: IMAD addend)
+#pragma unroll
+    for (int j = 0; j < 32; ++j) asm volatile("mov.u32 %0, %1;" : "=r"(jconst[j]) : "r"(j));
+    const uint32_t mul32 = p.key_mul;   // 32, opaque to the compiler: the key build stays an IMAD (FMA pipe),
+                                        // leaving the ALU pipe to the min/max chain
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
       int qt = item / p.nsplit, split = item % p.nsplit;
       int s_begin = split * p.stages_per_split;
@@ -320,33 +336,54 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) match_tc_kernel(TcParams p) {
         const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)buf * tc::STAGE_COLS;
         const int col0 = s * tc::STAGE_COLS;
         const int n_valid = p.nt - col0;          // columns of this stage that are real train rows
+        // Stage-local top-2 over 256 columns.  The eight 32-column chunks are fully unrolled and the
+        // TMEM load of chunk c+1 is in flight while chunk c is reduced.  Inside a chunk the key is
+        // (accumulator bits << 5) | j  (one IMAD on the FMA pipe, j from a register), the running
+        // top-2 costs 2.5 integer min/max per element on the ALU pipe; the chunk winners are then
+        // re-keyed with their chunk number (a handful of instructions per chunk).
         uint32_t k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu;
-#pragma unroll 1
+        uint32_t ra[32], rb[32];
+        tmem_ld32(t_addr, ra);
+#pragma unroll
         for (int c = 0; c < tc::STAGE_COLS / 32; ++c) {
-          uint32_t r[32];
-          tmem_ld32(t_addr + c * 32, r);
-          tmem_ld_wait();
+          uint32_t (&r)[32] = (c & 1) ? rb : ra;
+          uint32_t (&rn)[32] = (c & 1) ? ra : rb;
+          tmem_ld_wait_regs(r);
+          if (c + 1 < tc::STAGE_COLS / 32) tmem_ld32(t_addr + (c + 1) * 32, rn);
           if (p.dump) {
             float* drow = p.dump + ((size_t)(qt * 128 + row) * p.n_stages + s) * tc::STAGE_COLS + c * 32;
 #pragma unroll
             for (int j = 0; j < 32; ++j) drow[j] = __uint_as_float(r[j]);
           }
-          if (n_valid >= tc::STAGE_COLS) {
+          uint32_t c1 = 0xFFFFFFFFu, c2 = 0xFFFFFFFFu;
+          if (n_valid >= (c + 1) * 32) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              uint32_t key = (r[j] << 8) | (uint32_t)(c * 32 + j);
-              uint32_t t = max(k1, key);
-              k1 = min(k1, key);
-              k2 = min(k2, t);
+              uint32_t key = r[j] * mul32 + jconst[j];
+              uint32_t t = max(c1, key);
+              c1 = min(c1, key);
+              c2 = min(c2, t);
             }
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              uint32_t key = (c * 32 + j < n_valid) ? ((r[j] << 8) | (uint32_t)(c * 32 + j)) : 0xFFFFFFFFu;
-              uint32_t t = max(k1, key);
-              k1 = min(k1, key);
-              k2 = min(k2, t);
+              uint32_t key = (c * 32 + j < n_valid) ? (r[j] * mul32 + jconst[j]) : 0xFFFFFFFFu;
+              uint32_t t = max(c1, key);
+              c1 = min(c1, key);
+              c2 = min(c2, t);
             }
+          }
+          // chunk key (0x50000000 | d2 << 5 | j)  ->  stage key (0x80000000 | d2 << 8 | column)
+          if (c1 != 0xFFFFFFFFu) {
+            uint32_t w = ((c1 >> 5) << 8) | (uint32_t)(c * 32) | (c1 & 31u);
+            uint32_t t = max(k1, w);
+            k1 = min(k1, w);
+            k2 = min(k2, t);
+          }
+          if (c2 != 0xFFFFFFFFu) {
+            uint32_t w = ((c2 >> 5) << 8) | (uint32_t)(c * 32) | (c2 & 31u);
+            k2 = min(k2, max(k1, w));
+            k1 = min(k1, w);
           }
         }
         // accumulator drained -> hand the TMEM buffer back to the MMA warp
@@ -399,6 +436,7 @@ static int launch_tc(sfm_ctx* ctx, const sfm_desc* q, const sfm_desc* t, mkey_t*
   p.n_items = p.n_qtiles * nsplit;
   p.cand = cand;
   p.dump = dump;
+  p.key_mul = 32u;
   int grid = p.n_items < ctx->sm_count ? p.n_items : ctx->sm_count;
   SFM_LAUNCH(ctx, SFM_K_MATCH_TC, (match_tc_kernel<<<grid, tc::NTHREADS, tc::SMEM_BYTES, ctx->stream>>>(p)));
   return SFM_OK;

@@ -90,17 +90,13 @@ __global__ void __launch_bounds__(256) chol_diag_kernel(double* __restrict__ A, 
   factor_diag_block(A, n, k0, dinv, info, colbuf);
 }
 
-// rows k0+nb .. n (the last one is the rhs row): solve x L_kk^T = a, one row per thread.  The
-// running solution lives in shared memory (column tid of xs: conflict-free), L_kk is read as
-// broadcasts, and the loops stay rolled so the kernel is a few hundred bytes of code instead of a
-// 2000-FMA straight line.
-constexpr int PANEL_THREADS = 64;
+// rows k0+nb .. n (the last one is the rhs row): solve x L_kk^T = a, one row per thread, the running
+// solution in registers (fully unrolled), L_kk (strictly lower) and 1/diag read as shared broadcasts.
+constexpr int PANEL_THREADS = 128;
 __global__ void __launch_bounds__(PANEL_THREADS) chol_panel_kernel(double* __restrict__ A, int n, int k0,
                                                                    const double* __restrict__ dinv) {
-  extern __shared__ double panel_smem[];
-  double (*L)[NB + 1] = reinterpret_cast<double(*)[NB + 1]>(panel_smem);
-  double (*xs)[PANEL_THREADS] = reinterpret_cast<double(*)[PANEL_THREADS]>(panel_smem + NB * (NB + 1));
-  double* di = panel_smem + NB * (NB + 1) + NB * PANEL_THREADS;
+  __shared__ double L[NB][NB + 1];
+  __shared__ double di[NB];
   const int nb = min(NB, n - k0);
   for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) {
     const int r = e / NB, c = e % NB;
@@ -111,21 +107,19 @@ __global__ void __launch_bounds__(PANEL_THREADS) chol_panel_kernel(double* __res
   const int row = k0 + nb + blockIdx.x * blockDim.x + threadIdx.x;
   if (row > n) return;
   double* a = A + (size_t)row * n + k0;
-  const int t = threadIdx.x;
-  for (int j = 0; j < nb; ++j) {
-    double s0 = a[j], s1 = 0.0, s2 = 0.0, s3 = 0.0;
-    int k = 0;
-    for (; k + 3 < j; k += 4) {
-      s0 = fma(-xs[k][t], L[j][k], s0);
-      s1 = fma(-xs[k + 1][t], L[j][k + 1], s1);
-      s2 = fma(-xs[k + 2][t], L[j][k + 2], s2);
-      s3 = fma(-xs[k + 3][t], L[j][k + 3], s3);
-    }
-    for (; k < j; ++k) s0 = fma(-xs[k][t], L[j][k], s0);
-    const double xj = ((s0 + s1) + (s2 + s3)) * di[j];
-    xs[j][t] = xj;
-    a[j] = xj;
+  double x[NB];
+#pragma unroll
+  for (int j = 0; j < NB; ++j) x[j] = (j < nb) ? a[j] : 0.0;
+#pragma unroll
+  for (int j = 0; j < NB; ++j) {
+    double s = x[j];
+#pragma unroll
+    for (int k = 0; k < j; ++k) s = fma(-x[k], L[j][k], s);
+    x[j] = s * di[j];
   }
+#pragma unroll
+  for (int j = 0; j < NB; ++j)
+    if (j < nb) a[j] = x[j];
 }
 
 // rows [base, n] (n+1-base of them, the last is the rhs row), columns [base, n)
@@ -276,12 +270,6 @@ size_t sfm_spd_scratch_doubles(int n) {
 }
 
 int sfm_spd_solve(sfm_ctx* ctx, const float* S, const float* g, int n, double* A, double* x, int* info) {
-  constexpr size_t kPanelSmem = sizeof(double) * (NB * (NB + 1) + NB * PANEL_THREADS + NB);
-  static bool attr = false;
-  if (!attr) {
-    SFM_CUDA(cudaFuncSetAttribute(chol_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPanelSmem));
-    attr = true;
-  }
   const size_t total = (size_t)(n + 1) * n;
   double* dinv = A + total;
   SFM_LAUNCH(ctx, SFM_K_BA_SOLVE, (widen_kernel<<<dim3(div_up(n, 256), n + 1), 256, 0, ctx->stream>>>(S, g, n, A)));
@@ -290,7 +278,7 @@ int sfm_spd_solve(sfm_ctx* ctx, const float* S, const float* g, int n, double* A
   for (int k0 = 0; k0 < n; k0 += NB) {
     const int nb = std::min(NB, n - k0);
     const int rows_below = n + 1 - (k0 + nb);                 // >= 1: the rhs row
-    SFM_LAUNCH(ctx, SFM_K_BA_SOLVE, (chol_panel_kernel<<<div_up(rows_below, PANEL_THREADS), PANEL_THREADS, kPanelSmem, ctx->stream>>>(A, n, k0, dinv)));
+    SFM_LAUNCH(ctx, SFM_K_BA_SOLVE, (chol_panel_kernel<<<div_up(rows_below, PANEL_THREADS), PANEL_THREADS, 0, ctx->stream>>>(A, n, k0, dinv)));
     const int cols = n - (k0 + nb);
     if (cols > 0) {
       const int tiles = div_up(rows_below, 64);
