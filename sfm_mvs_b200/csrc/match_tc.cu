@@ -226,7 +226,51 @@ struct TcParams {
   unsigned int key_mul;           // = 32, passed at run time so the key build stays an IMAD (FMA pipe)
 };
 
+// Reduce one 32-column chunk (already in registers) into the stage-level top-2 (k1, k2).
+template <bool DUMP>
+__device__ __forceinline__ void chunk_top2(const uint32_t (&r)[32], const uint32_t (&jconst)[32], uint32_t mul32, int c,
+                                           int n_valid, uint32_t& k1, uint32_t& k2, const TcParams& p, int qt,
+                                           int row, int s) {
+  if (DUMP) {
+    float* drow = p.dump + ((size_t)(qt * 128 + row) * p.n_stages + s) * tc::STAGE_COLS + c * 32;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) drow[j] = __uint_as_float(r[j]);
+  }
+  uint32_t c1 = 0xFFFFFFFFu, c2 = 0xFFFFFFFFu;
+  const int nv = n_valid - c * 32;            // valid columns in this chunk (>= 32: all)
+  if (nv >= 32) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      uint32_t key = r[j] * mul32 + jconst[j];
+      uint32_t t = max(c1, key);
+      c1 = min(c1, key);
+      c2 = min(c2, t);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      uint32_t key = (j < nv) ? (r[j] * mul32 + jconst[j]) : 0xFFFFFFFFu;
+      uint32_t t = max(c1, key);
+      c1 = min(c1, key);
+      c2 = min(c2, t);
+    }
+  }
+  // chunk key (0x50000000 | d2 << 5 | j)  ->  stage key (0x80000000 | d2 << 8 | column)
+  if (c1 != 0xFFFFFFFFu) {
+    uint32_t w = ((c1 >> 5) << 8) | (uint32_t)(c * 32) | (c1 & 31u);
+    uint32_t t = max(k1, w);
+    k1 = min(k1, w);
+    k2 = min(k2, t);
+  }
+  if (c2 != 0xFFFFFFFFu) {
+    uint32_t w = ((c2 >> 5) << 8) | (uint32_t)(c * 32) | (c2 & 31u);
+    k2 = min(k2, max(k1, w));
+    k1 = min(k1, w);
+  }
+}
+
 // ============================================================================ K1 kernel
+template <bool DUMP>
 __global__ void __launch_bounds__(tc::NTHREADS, 1) match_tc_kernel(TcParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int warp = threadIdx.x >> 5;
@@ -336,55 +380,22 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) match_tc_kernel(TcParams p) {
         const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)buf * tc::STAGE_COLS;
         const int col0 = s * tc::STAGE_COLS;
         const int n_valid = p.nt - col0;          // columns of this stage that are real train rows
-        // Stage-local top-2 over 256 columns.  The eight 32-column chunks are fully unrolled and the
-        // TMEM load of chunk c+1 is in flight while chunk c is reduced.  Inside a chunk the key is
-        // (accumulator bits << 5) | j  (one IMAD on the FMA pipe, j from a register), the running
-        // top-2 costs 2.5 integer min/max per element on the ALU pipe; the chunk winners are then
-        // re-keyed with their chunk number (a handful of instructions per chunk).
+        // Stage-local top-2 over 256 columns in eight 32-column chunks; the TMEM load of the next chunk
+        // is in flight while the current one is reduced (two register buffers, loop over chunk pairs
+        // kept rolled so the hot loop stays a few KB of code).  Inside a chunk the key is
+        // (accumulator bits << 5) | j  (one IMAD on the FMA pipe), the running top-2 costs 2.5 integer
+        // min/max per element on the ALU pipe; the chunk winners are then re-keyed with their column.
         uint32_t k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu;
         uint32_t ra[32], rb[32];
         tmem_ld32(t_addr, ra);
-#pragma unroll
-        for (int c = 0; c < tc::STAGE_COLS / 32; ++c) {
-          uint32_t (&r)[32] = (c & 1) ? rb : ra;
-          uint32_t (&rn)[32] = (c & 1) ? ra : rb;
-          tmem_ld_wait_regs(r);
-          if (c + 1 < tc::STAGE_COLS / 32) tmem_ld32(t_addr + (c + 1) * 32, rn);
-          if (p.dump) {
-            float* drow = p.dump + ((size_t)(qt * 128 + row) * p.n_stages + s) * tc::STAGE_COLS + c * 32;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) drow[j] = __uint_as_float(r[j]);
-          }
-          uint32_t c1 = 0xFFFFFFFFu, c2 = 0xFFFFFFFFu;
-          if (n_valid >= (c + 1) * 32) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              uint32_t key = r[j] * mul32 + jconst[j];
-              uint32_t t = max(c1, key);
-              c1 = min(c1, key);
-              c2 = min(c2, t);
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              uint32_t key = (c * 32 + j < n_valid) ? (r[j] * mul32 + jconst[j]) : 0xFFFFFFFFu;
-              uint32_t t = max(c1, key);
-              c1 = min(c1, key);
-              c2 = min(c2, t);
-            }
-          }
-          // chunk key (0x50000000 | d2 << 5 | j)  ->  stage key (0x80000000 | d2 << 8 | column)
-          if (c1 != 0xFFFFFFFFu) {
-            uint32_t w = ((c1 >> 5) << 8) | (uint32_t)(c * 32) | (c1 & 31u);
-            uint32_t t = max(k1, w);
-            k1 = min(k1, w);
-            k2 = min(k2, t);
-          }
-          if (c2 != 0xFFFFFFFFu) {
-            uint32_t w = ((c2 >> 5) << 8) | (uint32_t)(c * 32) | (c2 & 31u);
-            k2 = min(k2, max(k1, w));
-            k1 = min(k1, w);
-          }
+#pragma unroll 1
+        for (int cp = 0; cp < tc::STAGE_COLS / 64; ++cp) {
+          tmem_ld_wait_regs(ra);
+          tmem_ld32(t_addr + (2 * cp + 1) * 32, rb);
+          chunk_top2<DUMP>(ra, jconst, mul32, 2 * cp, n_valid, k1, k2, p, qt, row, s);
+          tmem_ld_wait_regs(rb);
+          if (cp + 1 < tc::STAGE_COLS / 64) tmem_ld32(t_addr + (2 * cp + 2) * 32, ra);
+          chunk_top2<DUMP>(rb, jconst, mul32, 2 * cp + 1, n_valid, k1, k2, p, qt, row, s);
         }
         // accumulator drained -> hand the TMEM buffer back to the MMA warp
         tc_fence_before();
@@ -422,7 +433,8 @@ static int launch_tc(sfm_ctx* ctx, const sfm_desc* q, const sfm_desc* t, mkey_t*
   SFM_REQUIRE(q->tiles && t->tiles, "tensor-core matcher: descriptors have no tile image");
   static bool attr_set = false;
   if (!attr_set) {
-    SFM_CUDA(cudaFuncSetAttribute(match_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+    SFM_CUDA(cudaFuncSetAttribute(match_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+    SFM_CUDA(cudaFuncSetAttribute(match_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
     attr_set = true;
   }
   TcParams p;
@@ -438,7 +450,8 @@ static int launch_tc(sfm_ctx* ctx, const sfm_desc* q, const sfm_desc* t, mkey_t*
   p.dump = dump;
   p.key_mul = 32u;
   int grid = p.n_items < ctx->sm_count ? p.n_items : ctx->sm_count;
-  SFM_LAUNCH(ctx, SFM_K_MATCH_TC, (match_tc_kernel<<<grid, tc::NTHREADS, tc::SMEM_BYTES, ctx->stream>>>(p)));
+  if (dump) SFM_LAUNCH(ctx, SFM_K_MATCH_TC, (match_tc_kernel<true><<<grid, tc::NTHREADS, tc::SMEM_BYTES, ctx->stream>>>(p)));
+  else SFM_LAUNCH(ctx, SFM_K_MATCH_TC, (match_tc_kernel<false><<<grid, tc::NTHREADS, tc::SMEM_BYTES, ctx->stream>>>(p)));
   return SFM_OK;
 }
 
