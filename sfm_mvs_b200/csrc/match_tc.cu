@@ -25,14 +25,17 @@
 //   with three integer min/max ops per element.
 //
 // Kernel: persistent, warp-specialised, 1 CTA/SM, 192 threads:
-//   warp 0  producer  — cp.async.bulk of the query tile (once per work item) and of 2-tile train
-//                       stages into a 2-deep smem ring (full/empty mbarriers)
-//   warp 1  MMA       — one lane issues 9 x tcgen05.mma (M128 N256 K16, bf16 -> fp32 in TMEM);
-//                       tcgen05.commit releases the smem stage and publishes the accumulator
-//   warps 2-5 epilogue — tcgen05.ld 32x32b.x32 of their TMEM lane quarter (one query row per
-//                       thread), top-2 in registers; TMEM accumulators are double-buffered
+//   warp 0  producer  — cp.async.bulk of TWO query tiles (once per work item, 80 KiB) and of one
+//                       128-row train tile per stage into a 3-deep smem ring (full/empty mbarriers)
+//   warp 1  MMA       — one lane issues 2 x 9 tcgen05.mma (M128 N128 K16, bf16 -> fp32 in TMEM), one
+//                       set per resident query tile; tcgen05.commit releases the smem stage and
+//                       publishes the accumulator pair
+//   warps 2-5 epilogue — tcgen05.ld 32x32b.x32 of their TMEM lane quarter (one row of each query
+//                       tile per thread), top-2 in registers; TMEM accumulators are double-buffered
 //                       (2 x 256 columns) so the epilogue of stage s overlaps the MMAs of s+1.
-// A work item is (query tile, train split); per-split results are merged by K1c (match.cu).
+// A work item is (query tile pair, train split); per-split results are merged by K1c (match.cu).
+// Measured motivation for the tile pair: with one query tile per train tile the kernel saturated
+// L2 -> SM bandwidth (~6.4 TB/s of train-tile re-reads at 32k x 32k) at 31 % tensor-pipe activity.
 #include <cuda_bf16.h>
 
 #include "match_common.cuh"
@@ -45,18 +48,21 @@ constexpr int CORE_COLS = KAUG / 8;             // 20 core-matrix columns
 constexpr int LBO = 128;                        // bytes between K-adjacent core matrices
 constexpr int SBO = CORE_COLS * 128;            // bytes between 8-row groups (2560)
 constexpr int TILE_BYTES = (TILE_ROWS / 8) * SBO;   // 40960
-constexpr int STAGE_TILES = 2;                  // MMA N = 256
-constexpr int STAGE_COLS = STAGE_TILES * TILE_ROWS;
-constexpr int STAGE_BYTES = STAGE_TILES * TILE_BYTES;   // 81920
-constexpr int NSTAGE = 2;
+constexpr int QT_PER_ITEM = 2;                  // query tiles resident per work item: every train tile read
+                                                // from L2 feeds 2 x 128 query rows (halves L2 -> SM traffic,
+                                                // which is what bounds this kernel, not the tensor pipe)
+constexpr int STAGE_COLS = TILE_ROWS;           // one 128-row train tile per stage, MMA N = 128
+constexpr int STAGE_BYTES = TILE_BYTES;         // 40960
+constexpr int NSTAGE = 3;                       // train-tile ring depth
+constexpr int ACC_COLS = QT_PER_ITEM * STAGE_COLS;   // 256 TMEM columns per accumulator buffer (x2 buffers)
 constexpr int NTHREADS = 192;
 constexpr int SMEM_A = 0;
-constexpr int SMEM_B = TILE_BYTES;
-constexpr int SMEM_BAR = SMEM_B + NSTAGE * STAGE_BYTES;   // 204800
+constexpr int SMEM_B = QT_PER_ITEM * TILE_BYTES;            // 81920
+constexpr int SMEM_BAR = SMEM_B + NSTAGE * STAGE_BYTES;     // 204800
 constexpr int SMEM_BYTES = SMEM_BAR + 128;
 constexpr unsigned MAX_SQNORM = 1u << 21;
 // barrier indices
-enum { A_FULL = 0, A_EMPTY = 1, B_FULL = 2, B_EMPTY = 4, ACC_FULL = 6, ACC_EMPTY = 8, NBAR = 10 };
+enum { A_FULL = 0, A_EMPTY = 1, B_FULL = 2, B_EMPTY = 5, ACC_FULL = 8, ACC_EMPTY = 10, NBAR = 12 };
 }  // namespace tc
 
 // ============================================================================ K1b descriptor prep
@@ -216,28 +222,22 @@ struct TcParams {
   const unsigned char* q_tiles;   // query view image
   const unsigned char* t_tiles;   // train view image
   int n_qtiles;                   // 128-row query tiles
-  int n_stages;                   // two-tile train stages (even-padded)
+  int n_qpairs;                   // work-item rows: ceil(n_qtiles / 2)
+  int n_stages;                   // 128-row train tiles
   int nt;                         // valid train rows
   int nsplit;
   int stages_per_split;
   int n_items;
   mkey_t* cand;                   // [n_qtiles*128][nsplit][2]
-  float* dump;                    // debug: raw accumulators [n_qtiles*128][n_stages*256] or NULL
+  float* dump;                    // debug: raw accumulators [n_qtiles*128][n_stages*128] or NULL
   unsigned int key_mul;           // = 32, passed at run time so the key build stays an IMAD (FMA pipe)
 };
 
-// Reduce one 32-column chunk (already in registers) into the stage-level top-2 (k1, k2).
-template <bool DUMP>
+// Reduce one 32-column chunk (already in registers) into a stage-level top-2 (k1, k2).
+// c = chunk index inside the 128-column stage, nv = valid columns left from the chunk start.
 __device__ __forceinline__ void chunk_top2(const uint32_t (&r)[32], const uint32_t (&jconst)[32], uint32_t mul32, int c,
-                                           int n_valid, uint32_t& k1, uint32_t& k2, const TcParams& p, int qt,
-                                           int row, int s) {
-  if (DUMP) {
-    float* drow = p.dump + ((size_t)(qt * 128 + row) * p.n_stages + s) * tc::STAGE_COLS + c * 32;
-#pragma unroll
-    for (int j = 0; j < 32; ++j) drow[j] = __uint_as_float(r[j]);
-  }
+                                           int nv, uint32_t& k1, uint32_t& k2) {
   uint32_t c1 = 0xFFFFFFFFu, c2 = 0xFFFFFFFFu;
-  const int nv = n_valid - c * 32;            // valid columns in this chunk (>= 32: all)
   if (nv >= 32) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
@@ -286,12 +286,14 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) match_tc_kernel(TcParams p) {
     for (int s = 0; s < tc::NSTAGE; ++s) {
       mbar_init(bar(tc::B_FULL + s), 1);
       mbar_init(bar(tc::B_EMPTY + s), 1);
-      mbar_init(bar(tc::ACC_FULL + s), 1);
-      mbar_init(bar(tc::ACC_EMPTY + s), 4);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar(tc::ACC_FULL + b), 1);
+      mbar_init(bar(tc::ACC_EMPTY + b), 4);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {   // TMEM: all 512 columns = two 256-column accumulators
+  if (warp == 1) {   // TMEM: all 512 columns = two buffers of (2 query tiles x 128 columns)
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -303,15 +305,17 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) match_tc_kernel(TcParams p) {
   if (warp == 0) {
     // ------------------------------------------------------------------ producer
     if (lane == 0) {
-      uint32_t a_phase = 0, b_phase[tc::NSTAGE] = {0, 0};
+      uint32_t a_phase = 0, b_phase[tc::NSTAGE] = {0, 0, 0};
       int slot = 0;
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-        int qt = item / p.nsplit, split = item % p.nsplit;
-        int s_begin = split * p.stages_per_split;
-        int s_end = min(p.n_stages, s_begin + p.stages_per_split);
+        const int qp = item / p.nsplit, split = item % p.nsplit;
+        const int s_begin = split * p.stages_per_split;
+        const int s_end = min(p.n_stages, s_begin + p.stages_per_split);
+        const int nqt = min(tc::QT_PER_ITEM, p.n_qtiles - qp * tc::QT_PER_ITEM);
         mbar_wait(bar(tc::A_EMPTY), a_phase ^ 1);
-        mbar_expect_tx(bar(tc::A_FULL), tc::TILE_BYTES);
-        bulk_g2s(sbase + tc::SMEM_A, p.q_tiles + (size_t)qt * tc::TILE_BYTES, tc::TILE_BYTES, bar(tc::A_FULL));
+        mbar_expect_tx(bar(tc::A_FULL), (uint32_t)nqt * tc::TILE_BYTES);
+        bulk_g2s(sbase + tc::SMEM_A, p.q_tiles + (size_t)qp * tc::QT_PER_ITEM * tc::TILE_BYTES,
+                 (uint32_t)nqt * tc::TILE_BYTES, bar(tc::A_FULL));
         a_phase ^= 1;
         for (int s = s_begin; s < s_end; ++s) {
           mbar_wait(bar(tc::B_EMPTY + slot), b_phase[slot] ^ 1);
@@ -319,7 +323,7 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) match_tc_kernel(TcParams p) {
           bulk_g2s(sbase + tc::SMEM_B + slot * tc::STAGE_BYTES, p.t_tiles + (size_t)s * tc::STAGE_BYTES,
                    tc::STAGE_BYTES, bar(tc::B_FULL + slot));
           b_phase[slot] ^= 1;
-          slot ^= 1;
+          slot = (slot + 1 == tc::NSTAGE) ? 0 : slot + 1;
         }
       }
     }
@@ -327,75 +331,90 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) match_tc_kernel(TcParams p) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       const uint32_t idesc = make_idesc(128, tc::STAGE_COLS);
-      uint32_t a_phase = 0, b_phase[tc::NSTAGE] = {0, 0}, acc_phase[2] = {0, 0};
+      uint32_t a_phase = 0, b_phase[tc::NSTAGE] = {0, 0, 0}, acc_phase[2] = {0, 0};
       int slot = 0, buf = 0;
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-        int split = item % p.nsplit;
-        int s_begin = split * p.stages_per_split;
-        int s_end = min(p.n_stages, s_begin + p.stages_per_split);
+        const int qp = item / p.nsplit, split = item % p.nsplit;
+        const int s_begin = split * p.stages_per_split;
+        const int s_end = min(p.n_stages, s_begin + p.stages_per_split);
+        const int nqt = min(tc::QT_PER_ITEM, p.n_qtiles - qp * tc::QT_PER_ITEM);
         mbar_wait(bar(tc::A_FULL), a_phase);
         a_phase ^= 1;
-        const uint32_t a_addr = sbase + tc::SMEM_A;
         for (int s = s_begin; s < s_end; ++s) {
           mbar_wait(bar(tc::ACC_EMPTY + buf), acc_phase[buf] ^ 1);
           mbar_wait(bar(tc::B_FULL + slot), b_phase[slot]);
           b_phase[slot] ^= 1;
           tc_fence_after();
           const uint32_t b_addr = sbase + tc::SMEM_B + slot * tc::STAGE_BYTES;
-          const uint32_t d_addr = tmem_base + (uint32_t)buf * tc::STAGE_COLS;
+          for (int t = 0; t < nqt; ++t) {
+            const uint32_t a_addr = sbase + tc::SMEM_A + t * tc::TILE_BYTES;
+            const uint32_t d_addr = tmem_base + (uint32_t)(buf * tc::ACC_COLS + t * tc::STAGE_COLS);
 #pragma unroll
-          for (int k = 0; k < tc::KMAIN / 16; ++k)
-            tc_mma_bf16(d_addr, make_smem_desc(a_addr + k * 2 * tc::LBO), make_smem_desc(b_addr + k * 2 * tc::LBO),
-                        idesc, k > 0 ? 1u : 0u);
-          tc_mma_bf16(d_addr, make_smem_desc(a_addr + 16 * tc::LBO), make_smem_desc(b_addr + 18 * tc::LBO), idesc, 1u);
+            for (int k = 0; k < tc::KMAIN / 16; ++k)
+              tc_mma_bf16(d_addr, make_smem_desc(a_addr + k * 2 * tc::LBO), make_smem_desc(b_addr + k * 2 * tc::LBO),
+                          idesc, k > 0 ? 1u : 0u);
+            tc_mma_bf16(d_addr, make_smem_desc(a_addr + 16 * tc::LBO), make_smem_desc(b_addr + 18 * tc::LBO), idesc, 1u);
+          }
           tc_commit(bar(tc::B_EMPTY + slot));     // smem stage reusable once these MMAs retire
-          tc_commit(bar(tc::ACC_FULL + buf));     // accumulator complete
+          tc_commit(bar(tc::ACC_FULL + buf));     // accumulator pair complete
           acc_phase[buf] ^= 1;
-          slot ^= 1;
+          slot = (slot + 1 == tc::NSTAGE) ? 0 : slot + 1;
           buf ^= 1;
         }
-        tc_commit(bar(tc::A_EMPTY));              // query tile reusable
+        tc_commit(bar(tc::A_EMPTY));              // query tiles reusable
       }
     }
   } else {
     // ------------------------------------------------------------------ epilogue (warps 2..5)
     const int quarter = warp & 3;                 // TMEM lane quarter this warp may read
-    const int row = quarter * 32 + lane;          // query row within the tile
+    const int row = quarter * 32 + lane;          // query row within a tile
     uint32_t acc_phase[2] = {0, 0};
     int buf = 0;
-    uint32_t jconst[32];            // 0..31 held in registers (opaque to the compiler: IMAD addend)
+    uint32_t jconst[32];            // 0..31 held in registers (IMAD addend)
 #pragma unroll
-    for (int j = 0; j < 32; ++j) asm volatile("mov.u32 %0, %1;" : "=r"(jconst[j]) : "r"(j));
+    for (int j = 0; j < 32; ++j) jconst[j] = (uint32_t)j;
     const uint32_t mul32 = p.key_mul;   // 32, opaque to the compiler: the key build stays an IMAD (FMA pipe),
                                         // leaving the ALU pipe to the min/max chain
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-      int qt = item / p.nsplit, split = item % p.nsplit;
-      int s_begin = split * p.stages_per_split;
-      int s_end = min(p.n_stages, s_begin + p.stages_per_split);
-      mkey_t g1 = MKEY_INF, g2 = MKEY_INF;
+      const int qp = item / p.nsplit, split = item % p.nsplit;
+      const int s_begin = split * p.stages_per_split;
+      const int s_end = min(p.n_stages, s_begin + p.stages_per_split);
+      const int nqt = min(tc::QT_PER_ITEM, p.n_qtiles - qp * tc::QT_PER_ITEM);
+      mkey_t g[tc::QT_PER_ITEM][2] = {{MKEY_INF, MKEY_INF}, {MKEY_INF, MKEY_INF}};
       for (int s = s_begin; s < s_end; ++s) {
         mbar_wait(bar(tc::ACC_FULL + buf), acc_phase[buf]);
         acc_phase[buf] ^= 1;
         tc_fence_after();
-        const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)buf * tc::STAGE_COLS;
+        const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * tc::ACC_COLS);
         const int col0 = s * tc::STAGE_COLS;
         const int n_valid = p.nt - col0;          // columns of this stage that are real train rows
-        // Stage-local top-2 over 256 columns in eight 32-column chunks; the TMEM load of the next chunk
-        // is in flight while the current one is reduced (two register buffers, loop over chunk pairs
-        // kept rolled so the hot loop stays a few KB of code).  Inside a chunk the key is
-        // (accumulator bits << 5) | j  (one IMAD on the FMA pipe), the running top-2 costs 2.5 integer
-        // min/max per element on the ALU pipe; the chunk winners are then re-keyed with their column.
-        uint32_t k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu;
+        // Eight 32-column chunks (4 per query tile); the TMEM load of the next chunk is in flight while
+        // the current one is reduced (two register buffers, rolled loop over chunk pairs).
+        uint32_t k[tc::QT_PER_ITEM][2] = {{0xFFFFFFFFu, 0xFFFFFFFFu}, {0xFFFFFFFFu, 0xFFFFFFFFu}};
         uint32_t ra[32], rb[32];
+        const int nchunk = nqt * (tc::STAGE_COLS / 32);          // 4 or 8
         tmem_ld32(t_addr, ra);
 #pragma unroll 1
-        for (int cp = 0; cp < tc::STAGE_COLS / 64; ++cp) {
+        for (int c = 0; c < nchunk; c += 2) {
+          const int t = c >> 2, cc = c & 3;        // query tile, chunk inside its 128 columns (even)
           tmem_ld_wait_regs(ra);
-          tmem_ld32(t_addr + (2 * cp + 1) * 32, rb);
-          chunk_top2<DUMP>(ra, jconst, mul32, 2 * cp, n_valid, k1, k2, p, qt, row, s);
+          tmem_ld32(t_addr + (c + 1) * 32, rb);
+          if (DUMP) {
+            float* drow = p.dump + ((size_t)((qp * tc::QT_PER_ITEM + t) * 128 + row) * p.n_stages + s) * tc::STAGE_COLS + cc * 32;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) drow[j] = __uint_as_float(ra[j]);
+          }
+          if (t == 0) chunk_top2(ra, jconst, mul32, cc, n_valid - cc * 32, k[0][0], k[0][1]);
+          else chunk_top2(ra, jconst, mul32, cc, n_valid - cc * 32, k[1][0], k[1][1]);
           tmem_ld_wait_regs(rb);
-          if (cp + 1 < tc::STAGE_COLS / 64) tmem_ld32(t_addr + (2 * cp + 2) * 32, ra);
-          chunk_top2<DUMP>(rb, jconst, mul32, 2 * cp + 1, n_valid, k1, k2, p, qt, row, s);
+          if (c + 2 < nchunk) tmem_ld32(t_addr + (c + 2) * 32, ra);
+          if (DUMP) {
+            float* drow = p.dump + ((size_t)((qp * tc::QT_PER_ITEM + t) * 128 + row) * p.n_stages + s) * tc::STAGE_COLS + (cc + 1) * 32;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) drow[j] = __uint_as_float(rb[j]);
+          }
+          if (t == 0) chunk_top2(rb, jconst, mul32, cc + 1, n_valid - (cc + 1) * 32, k[0][0], k[0][1]);
+          else chunk_top2(rb, jconst, mul32, cc + 1, n_valid - (cc + 1) * 32, k[1][0], k[1][1]);
         }
         // accumulator drained -> hand the TMEM buffer back to the MMA warp
         tc_fence_before();
@@ -403,14 +422,22 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) match_tc_kernel(TcParams p) {
         if (lane == 0) mbar_arrive(bar(tc::ACC_EMPTY + buf));
         buf ^= 1;
         // fold the stage-local winners into the split-wide top-2 (64-bit keys: float bits of d^2, index)
-        if (k1 != 0xFFFFFFFFu)
-          key_insert(make_key((float)((k1 >> 8) & 0x7FFFFFu), col0 + (int)(k1 & 0xFFu)), g1, g2);
-        if (k2 != 0xFFFFFFFFu)
-          key_insert(make_key((float)((k2 >> 8) & 0x7FFFFFu), col0 + (int)(k2 & 0xFFu)), g1, g2);
+#pragma unroll
+        for (int t = 0; t < tc::QT_PER_ITEM; ++t) {
+          if (k[t][0] != 0xFFFFFFFFu)
+            key_insert(make_key((float)((k[t][0] >> 8) & 0x7FFFFFu), col0 + (int)(k[t][0] & 0xFFu)), g[t][0], g[t][1]);
+          if (k[t][1] != 0xFFFFFFFFu)
+            key_insert(make_key((float)((k[t][1] >> 8) & 0x7FFFFFu), col0 + (int)(k[t][1] & 0xFFu)), g[t][0], g[t][1]);
+        }
       }
-      mkey_t* out = p.cand + ((size_t)(qt * 128 + row) * p.nsplit + split) * 2;
-      out[0] = g1;
-      out[1] = g2;
+#pragma unroll
+      for (int t = 0; t < tc::QT_PER_ITEM; ++t) {
+        if (t < nqt) {
+          mkey_t* out = p.cand + ((size_t)((qp * tc::QT_PER_ITEM + t) * 128 + row) * p.nsplit + split) * 2;
+          out[0] = g[t][0];
+          out[1] = g[t][1];
+        }
+      }
     }
   }
   tc_fence_before();
@@ -421,9 +448,9 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) match_tc_kernel(TcParams p) {
 }
 
 int sfm_match_tc_splits(sfm_ctx* ctx, int nq, int nt) {
-  int qtiles = div_up(nq, tc::TILE_ROWS);
-  int stages = div_up(div_up(nt, tc::TILE_ROWS), tc::STAGE_TILES);
-  int s = ctx->sm_count / (qtiles > 0 ? qtiles : 1);
+  int qpairs = div_up(div_up(nq, tc::TILE_ROWS), tc::QT_PER_ITEM);
+  int stages = div_up(nt, tc::TILE_ROWS);
+  int s = ctx->sm_count / (qpairs > 0 ? qpairs : 1);
   if (s < 1) s = 1;
   if (s > stages) s = stages;
   return s < 1 ? 1 : s;
@@ -441,11 +468,12 @@ static int launch_tc(sfm_ctx* ctx, const sfm_desc* q, const sfm_desc* t, mkey_t*
   p.q_tiles = (const unsigned char*)q->tiles;
   p.t_tiles = (const unsigned char*)t->tiles;
   p.n_qtiles = q->n_tiles;
-  p.n_stages = div_up(t->n_tiles, tc::STAGE_TILES);
+  p.n_qpairs = div_up(q->n_tiles, tc::QT_PER_ITEM);
+  p.n_stages = t->n_tiles;
   p.nt = t->n;
   p.nsplit = nsplit;
   p.stages_per_split = div_up(p.n_stages, nsplit);
-  p.n_items = p.n_qtiles * nsplit;
+  p.n_items = p.n_qpairs * nsplit;
   p.cand = cand;
   p.dump = dump;
   p.key_mul = 32u;
@@ -460,7 +488,7 @@ int sfm_match_tc_launch(sfm_ctx* ctx, const sfm_desc* q, const sfm_desc* t, mkey
 }
 
 // Debug/self-test entry (not part of the reference-facing surface): raw accumulators of every
-// (query row, train column), i.e. -(2^22 + d^2/2), as float32 [n_qtiles*128][n_stages*256].
+// (query row, train column), i.e. -(2^22 + d^2/2), as float32 [n_qtiles*128][n_ttiles*128].
 extern "C" int sfm_debug_match_tc_dump(sfm_ctx* ctx, const sfm_desc* q, const sfm_desc* t, float* dump_host,
                                        int64_t capacity) {
   SFM_REQUIRE(ctx && q && t && dump_host, "sfm_debug_match_tc_dump: null argument");
@@ -468,8 +496,7 @@ extern "C" int sfm_debug_match_tc_dump(sfm_ctx* ctx, const sfm_desc* q, const sf
   SFM_TRY(sfm_desc_resolve(const_cast<sfm_desc*>(t)));
   SFM_TRY(sfm_ws_begin(ctx));
   int nsplit = 1;
-  int n_stages = div_up(t->n_tiles, tc::STAGE_TILES);
-  size_t count = (size_t)q->n_tiles * 128 * n_stages * tc::STAGE_COLS;
+  size_t count = (size_t)q->n_tiles * 128 * t->n_tiles * tc::STAGE_COLS;
   SFM_REQUIRE((int64_t)count <= capacity, "dump buffer too small: need %zu floats", count);
   mkey_t* cand;
   float* dump;

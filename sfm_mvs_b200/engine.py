@@ -203,8 +203,8 @@ class Context:
 
     def debug_tc_accumulators(self, q: Descriptors, t: Descriptors) -> np.ndarray:
         nqt = (q.n + 127) // 128
-        nst = ((t.n + 127) // 128 + 1) // 2
-        out = np.empty((nqt * 128, nst * 256), np.float32)
+        ntt = (t.n + 127) // 128
+        out = np.empty((nqt * 128, ntt * 128), np.float32)
         check(lib.sfm_debug_match_tc_dump(self._h, q._h, t._h, _dptr(out), out.size))
         return out
 
