@@ -24,19 +24,21 @@
 //   forms a sortable 32-bit key (bits<<8 | column) with one integer op and keeps a running top-2
 //   with three integer min/max ops per element.
 //
-// Kernel: persistent, warp-specialised, 1 CTA/SM, 192 threads:
+// Kernel: persistent, warp-specialised, 1 CTA/SM, 320 threads:
 //   warp 0  producer  — cp.async.bulk of TWO query tiles (once per work item, 80 KiB) and of one
 //                       128-row train tile per stage into a 3-deep smem ring (full/empty mbarriers)
 //   warp 1  MMA       — one lane issues 2 x 9 tcgen05.mma (M128 N128 K16, bf16 -> fp32 in TMEM), one
 //                       set per resident query tile; tcgen05.commit releases the smem stage and
 //                       publishes the accumulator pair
-//   warps 2-5 epilogue — tcgen05.ld 32x32b.x32 of their TMEM lane quarter (one row of each query
-//                       tile per thread), top-2 in registers; TMEM accumulators are double-buffered
-//                       (2 x 256 columns) so the epilogue of stage s overlaps the MMAs of s+1.
+//   warps 2-9 epilogue — tcgen05.ld 32x32b.x32 of their TMEM lane quarter (one query row per thread,
+//                       two warps per quarter, one per query tile), top-2 in registers; TMEM
+//                       accumulators are double-buffered (2 x 256 columns) so the epilogue of stage s
+//                       overlaps the MMAs of s+1.
 // A work item is (query tile pair, train split); per-split results are merged by K1c (match.cu).
 // Measured motivation for the tile pair: with one query tile per train tile the kernel saturated
 // L2 -> SM bandwidth (~6.4 TB/s of train-tile re-reads at 32k x 32k) at 31 % tensor-pipe activity.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "match_common.cuh"
 
@@ -55,7 +57,7 @@ constexpr int STAGE_COLS = TILE_ROWS;           // one 128-row train tile per st
 constexpr int STAGE_BYTES = TILE_BYTES;         // 40960
 constexpr int NSTAGE = 3;                       // train-tile ring depth
 constexpr int ACC_COLS = QT_PER_ITEM * STAGE_COLS;   // 256 TMEM columns per accumulator buffer (x2 buffers)
-constexpr int NTHREADS = 192;
+constexpr int NTHREADS = 320;                   // producer warp, MMA warp, 8 epilogue warps
 constexpr int SMEM_A = 0;
 constexpr int SMEM_B = QT_PER_ITEM * TILE_BYTES;            // 81920
 constexpr int SMEM_BAR = SMEM_B + NSTAGE * STAGE_BYTES;     // 204800
@@ -231,42 +233,66 @@ struct TcParams {
   mkey_t* cand;                   // [n_qtiles*128][nsplit][2]
   float* dump;                    // debug: raw accumulators [n_qtiles*128][n_stages*128] or NULL
   unsigned int key_mul;           // = 32, passed at run time so the key build stays an IMAD (FMA pipe)
+  unsigned int debug;             // diagnostics (env SFM_MATCH_DEBUG): bit0 skip epilogue math, bit1 skip MMAs
 };
 
 // Reduce one 32-column chunk (already in registers) into a stage-level top-2 (k1, k2).
 // c = chunk index inside the 128-column stage, nv = valid columns left from the chunk start.
+// Four independent (min, second-min) chains over interleaved columns: an epilogue warp has its SM
+// sub-partition to itself, so a single dependent min/max chain would run at instruction latency
+// (measured: ~18 cycles per element) instead of ALU throughput; the four chains are merged at the end.
 __device__ __forceinline__ void chunk_top2(const uint32_t (&r)[32], const uint32_t (&jconst)[32], uint32_t mul32, int c,
                                            int nv, uint32_t& k1, uint32_t& k2) {
-  uint32_t c1 = 0xFFFFFFFFu, c2 = 0xFFFFFFFFu;
+  uint32_t c1[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
+  uint32_t c2[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
   if (nv >= 32) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
-      uint32_t key = r[j] * mul32 + jconst[j];
-      uint32_t t = max(c1, key);
-      c1 = min(c1, key);
-      c2 = min(c2, t);
+      const uint32_t key = r[j] * mul32 + jconst[j];
+      const uint32_t t = max(c1[j & 3], key);
+      c1[j & 3] = min(c1[j & 3], key);
+      c2[j & 3] = min(c2[j & 3], t);
     }
   } else {
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
-      uint32_t key = (j < nv) ? (r[j] * mul32 + jconst[j]) : 0xFFFFFFFFu;
-      uint32_t t = max(c1, key);
-      c1 = min(c1, key);
-      c2 = min(c2, t);
+      const uint32_t key = (j < nv) ? (r[j] * mul32 + jconst[j]) : 0xFFFFFFFFu;
+      const uint32_t t = max(c1[j & 3], key);
+      c1[j & 3] = min(c1[j & 3], key);
+      c2[j & 3] = min(c2[j & 3], t);
     }
   }
+  // merge the four chains: (a1,a2) + (b1,b2) -> (min(a1,b1), min(max(a1,b1), min(a2,b2)))
+  const uint32_t m01 = min(c1[0], c1[1]), s01 = min(max(c1[0], c1[1]), min(c2[0], c2[1]));
+  const uint32_t m23 = min(c1[2], c1[3]), s23 = min(max(c1[2], c1[3]), min(c2[2], c2[3]));
+  const uint32_t w1 = min(m01, m23), w2 = min(max(m01, m23), min(s01, s23));
   // chunk key (0x50000000 | d2 << 5 | j)  ->  stage key (0x80000000 | d2 << 8 | column)
-  if (c1 != 0xFFFFFFFFu) {
-    uint32_t w = ((c1 >> 5) << 8) | (uint32_t)(c * 32) | (c1 & 31u);
-    uint32_t t = max(k1, w);
+  if (w1 != 0xFFFFFFFFu) {
+    const uint32_t w = ((w1 >> 5) << 8) | (uint32_t)(c * 32) | (w1 & 31u);
+    const uint32_t t = max(k1, w);
     k1 = min(k1, w);
     k2 = min(k2, t);
   }
-  if (c2 != 0xFFFFFFFFu) {
-    uint32_t w = ((c2 >> 5) << 8) | (uint32_t)(c * 32) | (c2 & 31u);
+  if (w2 != 0xFFFFFFFFu) {
+    const uint32_t w = ((w2 >> 5) << 8) | (uint32_t)(c * 32) | (w2 & 31u);
     k2 = min(k2, max(k1, w));
     k1 = min(k1, w);
   }
+}
+
+// Experiment (SFM_MATCH_DEBUG bit 3): top-2 VALUES only with floating-point min/max (FMNMX), two chains.
+__device__ __forceinline__ void chunk_top2_f32(const uint32_t (&r)[32], uint32_t& k1, uint32_t& k2) {
+  float a1 = -3.0e38f, a2 = -3.0e38f, b1 = -3.0e38f, b2 = -3.0e38f;
+#pragma unroll
+  for (int j = 0; j < 32; j += 2) {
+    const float x = __uint_as_float(r[j]), y = __uint_as_float(r[j + 1]);
+    const float ta = fminf(a1, x), tb = fminf(b1, y);
+    a1 = fmaxf(a1, x); b1 = fmaxf(b1, y);
+    a2 = fmaxf(a2, ta); b2 = fmaxf(b2, tb);
+  }
+  const float m1 = fmaxf(a1, b1), m2 = fmaxf(fminf(a1, b1), fmaxf(a2, b2));
+  k1 = min(k1, __float_as_uint(m1));
+  k2 = min(k2, __float_as_uint(m2));
 }
 
 // ============================================================================ K1 kernel
@@ -289,7 +315,7 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) match_tc_kernel(TcParams p) {
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar(tc::ACC_FULL + b), 1);
-      mbar_init(bar(tc::ACC_EMPTY + b), 4);
+      mbar_init(bar(tc::ACC_EMPTY + b), 8);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -346,7 +372,7 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) match_tc_kernel(TcParams p) {
           b_phase[slot] ^= 1;
           tc_fence_after();
           const uint32_t b_addr = sbase + tc::SMEM_B + slot * tc::STAGE_BYTES;
-          for (int t = 0; t < nqt; ++t) {
+          for (int t = 0; t < ((p.debug & 2u) ? 0 : nqt); ++t) {
             const uint32_t a_addr = sbase + tc::SMEM_A + t * tc::TILE_BYTES;
             const uint32_t d_addr = tmem_base + (uint32_t)(buf * tc::ACC_COLS + t * tc::STAGE_COLS);
 #pragma unroll
@@ -365,9 +391,13 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) match_tc_kernel(TcParams p) {
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    // ------------------------------------------------------------------ epilogue (warps 2..9)
+    // Two warps per TMEM lane quarter (= per SM sub-partition): warps 2-5 reduce query tile 0 of the
+    // pair, warps 6-9 query tile 1.  (Measured: a single warp per sub-partition issues min/max at
+    // ~4 cycles per instruction; two warps per sub-partition double the epilogue rate.)
     const int quarter = warp & 3;                 // TMEM lane quarter this warp may read
     const int row = quarter * 32 + lane;          // query row within a tile
+    const int tq = (warp - 2) >> 2;               // which query tile of the pair this warp owns
     uint32_t acc_phase[2] = {0, 0};
     int buf = 0;
     uint32_t jconst[32];            // 0..31 held in registers (IMAD addend)
@@ -380,41 +410,45 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) match_tc_kernel(TcParams p) {
       const int s_begin = split * p.stages_per_split;
       const int s_end = min(p.n_stages, s_begin + p.stages_per_split);
       const int nqt = min(tc::QT_PER_ITEM, p.n_qtiles - qp * tc::QT_PER_ITEM);
-      mkey_t g[tc::QT_PER_ITEM][2] = {{MKEY_INF, MKEY_INF}, {MKEY_INF, MKEY_INF}};
+      const bool active = tq < nqt;
+      mkey_t g1 = MKEY_INF, g2 = MKEY_INF;
       for (int s = s_begin; s < s_end; ++s) {
         mbar_wait(bar(tc::ACC_FULL + buf), acc_phase[buf]);
         acc_phase[buf] ^= 1;
         tc_fence_after();
-        const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * tc::ACC_COLS);
+        const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * tc::ACC_COLS + tq * tc::STAGE_COLS);
         const int col0 = s * tc::STAGE_COLS;
         const int n_valid = p.nt - col0;          // columns of this stage that are real train rows
-        // Eight 32-column chunks (4 per query tile); the TMEM load of the next chunk is in flight while
-        // the current one is reduced (two register buffers, rolled loop over chunk pairs).
-        uint32_t k[tc::QT_PER_ITEM][2] = {{0xFFFFFFFFu, 0xFFFFFFFFu}, {0xFFFFFFFFu, 0xFFFFFFFFu}};
-        uint32_t ra[32], rb[32];
-        const int nchunk = nqt * (tc::STAGE_COLS / 32);          // 4 or 8
-        tmem_ld32(t_addr, ra);
-#pragma unroll 1
-        for (int c = 0; c < nchunk; c += 2) {
-          const int t = c >> 2, cc = c & 3;        // query tile, chunk inside its 128 columns (even)
-          tmem_ld_wait_regs(ra);
-          tmem_ld32(t_addr + (c + 1) * 32, rb);
-          if (DUMP) {
-            float* drow = p.dump + ((size_t)((qp * tc::QT_PER_ITEM + t) * 128 + row) * p.n_stages + s) * tc::STAGE_COLS + cc * 32;
+        uint32_t k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu;
+        if (active) {
+          // four 32-column chunks; the TMEM load of the next chunk is in flight while the current one
+          // is reduced (two register buffers)
+          uint32_t ra[32], rb[32];
+          const bool do_ld = !(p.debug & 4u);
+          if (do_ld) tmem_ld32(t_addr, ra);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) drow[j] = __uint_as_float(ra[j]);
-          }
-          if (t == 0) chunk_top2(ra, jconst, mul32, cc, n_valid - cc * 32, k[0][0], k[0][1]);
-          else chunk_top2(ra, jconst, mul32, cc, n_valid - cc * 32, k[1][0], k[1][1]);
-          tmem_ld_wait_regs(rb);
-          if (c + 2 < nchunk) tmem_ld32(t_addr + (c + 2) * 32, ra);
-          if (DUMP) {
-            float* drow = p.dump + ((size_t)((qp * tc::QT_PER_ITEM + t) * 128 + row) * p.n_stages + s) * tc::STAGE_COLS + (cc + 1) * 32;
+          for (int c = 0; c < tc::STAGE_COLS / 32; c += 2) {
+            tmem_ld_wait_regs(ra);
+            if (do_ld) tmem_ld32(t_addr + (c + 1) * 32, rb);
+            if (DUMP) {
+              float* drow = p.dump + ((size_t)((qp * tc::QT_PER_ITEM + tq) * 128 + row) * p.n_stages + s) * tc::STAGE_COLS + c * 32;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) drow[j] = __uint_as_float(rb[j]);
+              for (int j = 0; j < 32; ++j) drow[j] = __uint_as_float(ra[j]);
+            }
+            if (p.debug & 8u) chunk_top2_f32(ra, k1, k2);
+            else if (p.debug & 1u) k1 = min(k1, ra[0] ^ ra[31]);
+            else chunk_top2(ra, jconst, mul32, c, n_valid - c * 32, k1, k2);
+            tmem_ld_wait_regs(rb);
+            if (do_ld && c + 2 < tc::STAGE_COLS / 32) tmem_ld32(t_addr + (c + 2) * 32, ra);
+            if (DUMP) {
+              float* drow = p.dump + ((size_t)((qp * tc::QT_PER_ITEM + tq) * 128 + row) * p.n_stages + s) * tc::STAGE_COLS + (c + 1) * 32;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) drow[j] = __uint_as_float(rb[j]);
+            }
+            if (p.debug & 8u) chunk_top2_f32(rb, k1, k2);
+            else if (p.debug & 1u) k1 = min(k1, rb[0] ^ rb[31]);
+            else chunk_top2(rb, jconst, mul32, c + 1, n_valid - (c + 1) * 32, k1, k2);
           }
-          if (t == 0) chunk_top2(rb, jconst, mul32, cc + 1, n_valid - (cc + 1) * 32, k[0][0], k[0][1]);
-          else chunk_top2(rb, jconst, mul32, cc + 1, n_valid - (cc + 1) * 32, k[1][0], k[1][1]);
         }
         // accumulator drained -> hand the TMEM buffer back to the MMA warp
         tc_fence_before();
@@ -422,21 +456,13 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) match_tc_kernel(TcParams p) {
         if (lane == 0) mbar_arrive(bar(tc::ACC_EMPTY + buf));
         buf ^= 1;
         // fold the stage-local winners into the split-wide top-2 (64-bit keys: float bits of d^2, index)
-#pragma unroll
-        for (int t = 0; t < tc::QT_PER_ITEM; ++t) {
-          if (k[t][0] != 0xFFFFFFFFu)
-            key_insert(make_key((float)((k[t][0] >> 8) & 0x7FFFFFu), col0 + (int)(k[t][0] & 0xFFu)), g[t][0], g[t][1]);
-          if (k[t][1] != 0xFFFFFFFFu)
-            key_insert(make_key((float)((k[t][1] >> 8) & 0x7FFFFFu), col0 + (int)(k[t][1] & 0xFFu)), g[t][0], g[t][1]);
-        }
+        if (k1 != 0xFFFFFFFFu) key_insert(make_key((float)((k1 >> 8) & 0x7FFFFFu), col0 + (int)(k1 & 0xFFu)), g1, g2);
+        if (k2 != 0xFFFFFFFFu) key_insert(make_key((float)((k2 >> 8) & 0x7FFFFFu), col0 + (int)(k2 & 0xFFu)), g1, g2);
       }
-#pragma unroll
-      for (int t = 0; t < tc::QT_PER_ITEM; ++t) {
-        if (t < nqt) {
-          mkey_t* out = p.cand + ((size_t)((qp * tc::QT_PER_ITEM + t) * 128 + row) * p.nsplit + split) * 2;
-          out[0] = g[t][0];
-          out[1] = g[t][1];
-        }
+      if (active) {
+        mkey_t* out = p.cand + ((size_t)((qp * tc::QT_PER_ITEM + tq) * 128 + row) * p.nsplit + split) * 2;
+        out[0] = g1;
+        out[1] = g2;
       }
     }
   }
@@ -477,6 +503,7 @@ static int launch_tc(sfm_ctx* ctx, const sfm_desc* q, const sfm_desc* t, mkey_t*
   p.cand = cand;
   p.dump = dump;
   p.key_mul = 32u;
+  { const char* e = getenv("SFM_MATCH_DEBUG"); p.debug = e ? (unsigned)atoi(e) : 0u; }
   int grid = p.n_items < ctx->sm_count ? p.n_items : ctx->sm_count;
   if (dump) SFM_LAUNCH(ctx, SFM_K_MATCH_TC, (match_tc_kernel<true><<<grid, tc::NTHREADS, tc::SMEM_BYTES, ctx->stream>>>(p)));
   else SFM_LAUNCH(ctx, SFM_K_MATCH_TC, (match_tc_kernel<false><<<grid, tc::NTHREADS, tc::SMEM_BYTES, ctx->stream>>>(p)));
