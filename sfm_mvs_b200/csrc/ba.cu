@@ -70,7 +70,7 @@ struct Intr {
 // served per quarter-warp, which keeps the random per-lane camera gather to ~2-3 wavefronts per load.
 template <bool WANT_J>
 __device__ __forceinline__ void obs_geometry(const double* __restrict__ cp, const double* __restrict__ X, float2 uv,
-                                             const Intr& K, double* r, double (*Jc)[6], double (*Jp)[3]) {
+                                             const Intr& K, double* r, float (*Jc)[6], float (*Jp)[3]) {
   const double2* q = reinterpret_cast<const double2*>(cp);
   const double2 q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3], q4 = q[4], q5 = q[5];
   // R = [q0.x q0.y q1.x; q1.y q2.x q2.y; q3.x q3.y q4.x], t = (q4.y, q5.x, q5.y)
@@ -83,21 +83,27 @@ __device__ __forceinline__ void obs_geometry(const double* __restrict__ cp, cons
   r[0] = xn * K.fx + K.cx - (double)uv.x;
   r[1] = yn * K.fy + K.cy - (double)uv.y;
   if (WANT_J) {
+    // Jacobian blocks are delivered as float32, so they are formed in float32 from the float64
+    // projection state (relative error ~1e-7); only the residual path needs float64.
     const float4* f = reinterpret_cast<const float4*>(cp + 12);
     const float4 f0 = f[0], f1 = f[1], f2 = f[2];
-    const double jl[9] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w, f2.x};
-    const double a0 = K.fx * iz, a2 = -K.fx * xn * iz, b1 = K.fy * iz, b2 = -K.fy * yn * iz;
+    const float jl[9] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w, f2.x};
+    const float fiz = (float)iz, fxn = (float)xn, fyn = (float)yn;
+    const float a0 = (float)K.fx * fiz, a2 = -a0 * fxn, b1 = (float)K.fy * fiz, b2 = -b1 * fyn;
+    const float yr0 = (float)Yr0, yr1 = (float)Yr1, yr2 = (float)Yr2;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-      const double ax = jl[3 * k], ay = jl[3 * k + 1], az = jl[3 * k + 2];
-      const double dx = ay * Yr2 - az * Yr1, dy = az * Yr0 - ax * Yr2, dz = ax * Yr1 - ay * Yr0;
+      const float ax = jl[3 * k], ay = jl[3 * k + 1], az = jl[3 * k + 2];
+      const float dx = ay * yr2 - az * yr1, dy = az * yr0 - ax * yr2, dz = ax * yr1 - ay * yr0;
       Jc[0][k] = a0 * dx + a2 * dz;
       Jc[1][k] = b1 * dy + b2 * dz;
     }
-    Jc[0][3] = a0; Jc[0][4] = 0.0; Jc[0][5] = a2;
-    Jc[1][3] = 0.0; Jc[1][4] = b1; Jc[1][5] = b2;
-    Jp[0][0] = a0 * q0.x + a2 * q3.x; Jp[0][1] = a0 * q0.y + a2 * q3.y; Jp[0][2] = a0 * q1.x + a2 * q4.x;
-    Jp[1][0] = b1 * q1.y + b2 * q3.x; Jp[1][1] = b1 * q2.x + b2 * q3.y; Jp[1][2] = b1 * q2.y + b2 * q4.x;
+    Jc[0][3] = a0; Jc[0][4] = 0.f; Jc[0][5] = a2;
+    Jc[1][3] = 0.f; Jc[1][4] = b1; Jc[1][5] = b2;
+    const float r00 = (float)q0.x, r01 = (float)q0.y, r02 = (float)q1.x, r10 = (float)q1.y, r11 = (float)q2.x,
+                r12 = (float)q2.y, r20 = (float)q3.x, r21 = (float)q3.y, r22 = (float)q4.x;
+    Jp[0][0] = a0 * r00 + a2 * r20; Jp[0][1] = a0 * r01 + a2 * r21; Jp[0][2] = a0 * r02 + a2 * r22;
+    Jp[1][0] = b1 * r10 + b2 * r20; Jp[1][1] = b1 * r11 + b2 * r21; Jp[1][2] = b1 * r12 + b2 * r22;
   }
 }
 
@@ -135,6 +141,18 @@ __global__ void __launch_bounds__(1024, 1) ba_eval_kernel(const float2* __restri
                    ::"r"(ba_smem_u32(s_cam)), "l"(cam_pre), "r"(bytes), "r"(bar) : "memory");
     }
     __syncthreads();   // barrier initialised before anyone polls it
+  }
+  const double* cams = SMEM_CAMS ? s_cam : cam_pre;
+  double local = 0.0;
+  // Software pipeline: the (uv, camera index, point index) triple of the next trip is loaded before the
+  // current observation is processed, so its DRAM latency overlaps this trip's gather + arithmetic.
+  const int stride = gridDim.x * blockDim.x;
+  int o = blockIdx.x * blockDim.x + threadIdx.x;
+  float2 m_n = make_float2(0.f, 0.f);
+  int c_n = 0, p_n = 0;
+  if (o < n_obs) { m_n = __ldg(uv + o); c_n = __ldg(cam_idx + o); p_n = __ldg(pt_idx + o); }
+  if (SMEM_CAMS) {           // wait for the bulk copy only now: the first index loads are already in flight
+    const uint32_t bar = ba_smem_u32(&s_bar);
     uint32_t ok = 0;
     for (uint32_t spin = 0; !ok; ++spin) {
       asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.b32 %0, 1, 0, p;\n\t}"
@@ -142,13 +160,13 @@ __global__ void __launch_bounds__(1024, 1) ba_eval_kernel(const float2* __restri
       if (spin > (1u << 22)) asm volatile("trap;");
     }
   }
-  const double* cams = SMEM_CAMS ? s_cam : cam_pre;
-  double local = 0.0;
-  for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < n_obs; o += gridDim.x * blockDim.x) {
-    const float2 m = __ldg(uv + o);
-    const int c = __ldg(cam_idx + o), p = __ldg(pt_idx + o);
+  for (; o < n_obs; o += stride) {
+    const float2 m = m_n;
+    const int c = c_n, p = p_n;
     const double X[3] = {__ldg(pts + 3 * (size_t)p), __ldg(pts + 3 * (size_t)p + 1), __ldg(pts + 3 * (size_t)p + 2)};
-    double r[2], Jc[2][6], Jp[2][3];
+    if (o + stride < n_obs) { m_n = __ldg(uv + o + stride); c_n = __ldg(cam_idx + o + stride); p_n = __ldg(pt_idx + o + stride); }
+    double r[2];
+    float Jc[2][6], Jp[2][3];
     if (MODE == 0) {
       if (Jc_out != nullptr || Jp_out != nullptr) obs_geometry<true>(cams + CAM_PRE * (size_t)c, X, m, K, r, Jc, Jp);
       else obs_geometry<false>(cams + CAM_PRE * (size_t)c, X, m, K, r, Jc, Jp);
@@ -225,7 +243,8 @@ __device__ __forceinline__ void point_accumulate(WarpPoint& wp, int lane, int o_
   for (int a = lane; a < nobs; a += 32) {
     const int o = o_begin + a;
     const int c = __ldg(cam_idx + o);
-    double r[2], Jc[2][6], Jp[2][3];
+    double r[2];
+    float Jc[2][6], Jp[2][3];
     obs_geometry<true>(cams + CAM_PRE * (size_t)c, X, __ldg(uv + o), K, r, Jc, Jp);
     *cost_local += r[0] * r[0] + r[1] * r[1];
     h[0] += Jp[0][0] * Jp[0][0] + Jp[1][0] * Jp[1][0];
