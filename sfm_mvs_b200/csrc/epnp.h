@@ -83,32 +83,42 @@ HM_HD inline void eig_sym(double* A, double* w, double* V) {
 // reprojection error" selection then discards (NaN never compares smaller).
 template <int M, int N>
 HM_HD inline void ls_solve(double* A, double* b, double* x) {
+  HM_UNROLL
   for (int k = 0; k < N; ++k) {
     double nrm = 0.0;
+    HM_UNROLL
     for (int i = k; i < M; ++i) nrm += A[i * N + k] * A[i * N + k];
     nrm = sqrt(nrm);
     double alpha = A[k * N + k] > 0.0 ? -nrm : nrm;
     double vk = A[k * N + k] - alpha;
     double vnorm2 = vk * vk;
+    HM_UNROLL
     for (int i = k + 1; i < M; ++i) vnorm2 += A[i * N + k] * A[i * N + k];
     if (vnorm2 > 0.0) {
+      HM_UNROLL
       for (int j = k + 1; j < N; ++j) {
         double dot = vk * A[k * N + j];
+        HM_UNROLL
         for (int i = k + 1; i < M; ++i) dot += A[i * N + k] * A[i * N + j];
         double f = 2.0 * dot / vnorm2;
         A[k * N + j] -= f * vk;
+        HM_UNROLL
         for (int i = k + 1; i < M; ++i) A[i * N + j] -= f * A[i * N + k];
       }
       double dot = vk * b[k];
+      HM_UNROLL
       for (int i = k + 1; i < M; ++i) dot += A[i * N + k] * b[i];
       double f = 2.0 * dot / vnorm2;
       b[k] -= f * vk;
+      HM_UNROLL
       for (int i = k + 1; i < M; ++i) b[i] -= f * A[i * N + k];
     }
     A[k * N + k] = alpha;
   }
+  HM_UNROLL
   for (int k = N - 1; k >= 0; --k) {
     double s = b[k];
+    HM_UNROLL
     for (int j = k + 1; j < N; ++j) s -= A[k * N + j] * x[j];
     x[k] = s / A[k * N + k];
   }
@@ -174,6 +184,7 @@ HM_HD inline double epnp_pose_from_betas(const double* const v[4], const double*
 HM_HD inline void epnp_gauss_newton(const double* L, const double* rho, double* b) {
   for (int it = 0; it < 5; ++it) {
     double A[24], r[6], dx[4];
+    HM_UNROLL
     for (int i = 0; i < 6; ++i) {
       const double* l = L + 10 * i;
       A[4 * i + 0] = 2 * l[0] * b[0] + l[1] * b[1] + l[3] * b[2] + l[6] * b[3];
@@ -185,13 +196,24 @@ HM_HD inline void epnp_gauss_newton(const double* L, const double* rho, double* 
                        l[8] * b[2] * b[3] + l[9] * b[3] * b[3]);
     }
     ls_solve<6, 4>(A, r, dx);
+    HM_UNROLL
     for (int k = 0; k < 4; ++k) b[k] += dx[k];
   }
 }
 
+HM_HD inline void epnp_MtM(const double* alphas, const double* us, int n, const EpnpCam& cam, double* MtM);
+
+// ---- stage 1a: control points and barycentric coordinates (alphas: n x 4)
+HM_HD inline void epnp_control_alphas(const double* pw, int n, double* alphas, double (*cws)[3]);
+
 // ---- stage 1: control points, barycentric coordinates, M^T M.  alphas: n x 4 scratch.
 HM_HD inline void epnp_build(const double* pw, const double* us, int n, const EpnpCam& cam, double* alphas,
                              double (*cws)[3], double* MtM) {
+  epnp_control_alphas(pw, n, alphas, cws);
+  epnp_MtM(alphas, us, n, cam, MtM);
+}
+
+HM_HD inline void epnp_control_alphas(const double* pw, int n, double* alphas, double (*cws)[3]) {
   for (int k = 0; k < 3; ++k) cws[0][k] = 0.0;
   for (int i = 0; i < n; ++i)
     for (int k = 0; k < 3; ++k) cws[0][k] += pw[3 * i + k];
@@ -228,6 +250,10 @@ HM_HD inline void epnp_build(const double* pw, const double* us, int n, const Ep
     for (int j = 0; j < 3; ++j) a[1 + j] = ci[3 * j] * d[0] + ci[3 * j + 1] * d[1] + ci[3 * j + 2] * d[2];
     a[0] = 1.0 - a[1] - a[2] - a[3];
   }
+}
+
+// M^T M (12x12, symmetric) from the barycentric coordinates: two rows of M per correspondence.
+HM_HD inline void epnp_MtM(const double* alphas, const double* us, int n, const EpnpCam& cam, double* MtM) {
   for (int i = 0; i < 144; ++i) MtM[i] = 0.0;
   for (int i = 0; i < n; ++i) {
     const double* a = alphas + 4 * i;

@@ -46,7 +46,7 @@ __device__ __forceinline__ void dlt_null_vector(double (&At)[4][4], double (&out
         for (int k = 0; k < 4; ++k) p += At[i][k] * At[j][k];
         if (fabs(p) <= eps * sqrt(a * b)) continue;
         p *= 2.0;
-        double beta = a - b, gamma = hypot(p, beta);
+        double beta = a - b, gamma = sqrt(p * p + beta * beta);   // moderate magnitudes: no overflow guard needed
         double c, s;
         if (beta < 0.0) {
           double delta = (gamma - beta) * 0.5;
@@ -324,31 +324,65 @@ extern "C" int sfm_reproj_error(sfm_ctx* ctx, const float* X, int x_layout, cons
 }
 
 // ============================================================================ common_points
-// One warp per row of pts1 scans pts2 in ascending order, 32 rows at a time, and stops at the
-// first 32-row window containing a hit: `np.where(pts2 == pts1[i])[0][0]` (sfm.py:221-226).
-__global__ void __launch_bounds__(256) first_hit_kernel(const float2* __restrict__ p1, int n1,
-                                                         const float2* __restrict__ p2, int n2,
-                                                         int* __restrict__ hit,
-                                                         unsigned char* __restrict__ keep2) {
-  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  int lane = threadIdx.x & 31;
-  if (warp >= n1) return;
-  float2 a = __ldg(p1 + warp);
-  int found = -1;
-  for (int base = 0; base < n2; base += 32) {
-    int j = base + lane;
-    bool h = false;
-    if (j < n2) {
-      float2 b = __ldg(p2 + j);
-      h = (b.x == a.x) || (b.y == a.y);
-    }
-    unsigned m = __ballot_sync(0xffffffffu, h);
-    if (m) { found = base + __ffs(m) - 1; break; }
+// `np.where(pts2 == pts1[i])[0][0]` (sfm.py:221-226): the first row j of pts2 whose x equals pts1[i].x
+// OR whose y equals pts1[i].y (element-wise comparison — the reference's quirk), float32 equality.
+// Instead of the reference's O(n1*n2) scan: two open-addressing hash tables over pts2 (one keyed by the
+// bits of x, one by the bits of y) holding the smallest row index per distinct value (atomicMin), then
+// one lookup pair per row of pts1: hit = min(first row with equal x, first row with equal y).
+struct HashSlot {
+  unsigned int key;   // float bits (0xFFFFFFFF = empty; a NaN pattern, which never compares equal anyway)
+  unsigned int row;   // smallest row index seen for this key
+};
+
+__device__ __forceinline__ unsigned int float_key(float v) { return (v == 0.f) ? 0u : __float_as_uint(v); }   // -0 == +0
+__device__ __forceinline__ unsigned int hash_u32(unsigned int k) {
+  k ^= k >> 16; k *= 0x7feb352du; k ^= k >> 15; k *= 0x846ca68bu; k ^= k >> 16;
+  return k;
+}
+
+__device__ __forceinline__ void hash_insert_min(HashSlot* __restrict__ tab, unsigned int mask, float v, unsigned int row) {
+  if (v != v) return;                                   // NaN never matches
+  const unsigned int key = float_key(v);
+  unsigned int h = hash_u32(key) & mask;
+  for (;;) {
+    const unsigned int prev = atomicCAS(&tab[h].key, 0xFFFFFFFFu, key);
+    if (prev == 0xFFFFFFFFu || prev == key) { atomicMin(&tab[h].row, row); return; }
+    h = (h + 1) & mask;
   }
-  if (lane == 0) {
-    hit[warp] = found;
-    if (found >= 0 && keep2) keep2[found] = 0;
+}
+
+__device__ __forceinline__ unsigned int hash_lookup(const HashSlot* __restrict__ tab, unsigned int mask, float v) {
+  if (v != v) return 0xFFFFFFFFu;
+  const unsigned int key = float_key(v);
+  unsigned int h = hash_u32(key) & mask;
+  for (;;) {
+    const unsigned int k = tab[h].key;
+    if (k == key) return tab[h].row;
+    if (k == 0xFFFFFFFFu) return 0xFFFFFFFFu;
+    h = (h + 1) & mask;
   }
+}
+
+__global__ void __launch_bounds__(256) hash_build_kernel(const float2* __restrict__ p2, int n2, HashSlot* __restrict__ tx,
+                                                          HashSlot* __restrict__ ty, unsigned int mask) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n2) return;
+  float2 b = __ldg(p2 + j);
+  hash_insert_min(tx, mask, b.x, (unsigned int)j);
+  hash_insert_min(ty, mask, b.y, (unsigned int)j);
+}
+
+__global__ void __launch_bounds__(256) first_hit_kernel(const float2* __restrict__ p1, int n1, const HashSlot* __restrict__ tx,
+                                                         const HashSlot* __restrict__ ty, unsigned int mask,
+                                                         int* __restrict__ hit, unsigned char* __restrict__ keep2) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n1) return;
+  float2 a = __ldg(p1 + i);
+  const unsigned int jx = hash_lookup(tx, mask, a.x), jy = hash_lookup(ty, mask, a.y);
+  const unsigned int j = min(jx, jy);
+  const int found = (j == 0xFFFFFFFFu) ? -1 : (int)j;
+  hit[i] = found;
+  if (found >= 0 && keep2) keep2[found] = 0;
 }
 
 // Stable single-CTA compaction of (i, hit[i]) for hit[i] >= 0.
@@ -406,8 +440,16 @@ extern "C" int sfm_common_points(sfm_ctx* ctx, const float* pts1, int n1, const 
   SFM_TRY(ws_alloc_t(ctx, (size_t)(n1 > 0 ? n1 : 1), &hit));
   if (ok.dev && n2 > 0) SFM_CUDA(cudaMemsetAsync(ok.dev, 1, (size_t)n2, ctx->stream));
   if (n1 > 0) {
-    SFM_LAUNCH(ctx, SFM_K_ASSOC, (first_hit_kernel<<<div_up(n1 * 32, 256), 256, 0, ctx->stream>>>(
-                                     (const float2*)d1, n1, (const float2*)d2, n2, hit, ok.dev)));
+    unsigned int size = 64;
+    while (size < 2u * (unsigned int)(n2 > 0 ? n2 : 1)) size <<= 1;
+    HashSlot* tabs = nullptr;
+    SFM_TRY(ws_alloc_t(ctx, (size_t)2 * size, &tabs));
+    SFM_CUDA(cudaMemsetAsync(tabs, 0xFF, sizeof(HashSlot) * 2 * (size_t)size, ctx->stream));
+    if (n2 > 0)
+      SFM_LAUNCH(ctx, SFM_K_ASSOC, (hash_build_kernel<<<div_up(n2, 256), 256, 0, ctx->stream>>>(
+                                       (const float2*)d2, n2, tabs, tabs + size, size - 1)));
+    SFM_LAUNCH(ctx, SFM_K_ASSOC, (first_hit_kernel<<<div_up(n1, 256), 256, 0, ctx->stream>>>(
+                                     (const float2*)d1, n1, tabs, tabs + size, size - 1, hit, ok.dev)));
   }
   SFM_LAUNCH(ctx, SFM_K_ASSOC, (compact_hits_kernel<<<1, 1024, 0, ctx->stream>>>(hit, n1, o1.dev, o2.dev, on.dev)));
   SFM_TRY(dev_out_finish(ctx, &o1));

@@ -227,7 +227,25 @@ __global__ void __launch_bounds__(32) pnp_epnp_kernel(const float* __restrict__ 
       sh.pw[3 * k] = (double)X[3 * (size_t)j]; sh.pw[3 * k + 1] = (double)X[3 * (size_t)j + 1]; sh.pw[3 * k + 2] = (double)X[3 * (size_t)j + 2];
       hm::epnp_roundtrip_pixel(px[2 * (size_t)j], px[2 * (size_t)j + 1], ec, sh.us + 2 * k);
     }
-    hm::epnp_build(sh.pw, sh.us, 5, ec, sh.alphas, reinterpret_cast<double(*)[3]>(sh.cws), sh.A);
+    hm::epnp_control_alphas(sh.pw, 5, sh.alphas, reinterpret_cast<double(*)[3]>(sh.cws));
+  }
+  __syncwarp();
+  // M (10 x 12, two rows per correspondence) into sh.V, then M^T M (144 entries) spread over the lanes
+  for (int e = lane; e < 120; e += 32) {
+    const int rw = e / 12, col = e - 12 * rw, i = rw >> 1, jcp = col / 3, comp = col - 3 * jcp;
+    const double a = sh.alphas[4 * i + jcp];
+    double v;
+    if ((rw & 1) == 0) v = (comp == 0) ? a * ec.fu : ((comp == 1) ? 0.0 : a * (ec.uc - sh.us[2 * i]));
+    else v = (comp == 0) ? 0.0 : ((comp == 1) ? a * ec.fv : a * (ec.vc - sh.us[2 * i + 1]));
+    sh.V[e] = v;
+  }
+  __syncwarp();
+  for (int e = lane; e < 144; e += 32) {
+    const int rr = e / 12, cc = e - 12 * rr;
+    double acc = 0.0;
+#pragma unroll
+    for (int rw = 0; rw < 10; ++rw) acc += sh.V[12 * rw + rr] * sh.V[12 * rw + cc];
+    sh.A[e] = acc;
   }
   __syncwarp();
   warp_jacobi12(sh, lane);
