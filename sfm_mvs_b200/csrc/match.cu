@@ -12,8 +12,13 @@
 // dist = float32(sqrt(d2)) (correctly rounded, like OpenCV's std::sqrt on the float32 sum);
 // the Lowe test is evaluated as Python does it: float32 distances widened to double,
 // d1 < ratio*d2 in double, strict (sfm.py:264).
+// STRIDE 3 (tensor-core kernel): the third key of a split names a column that has the runner-up's
+// distance IF it is real (match_tc.cu, epilogue comment); it is evaluated exactly (integer-valued
+// float32 arithmetic on the resident copies) only when it would enter the top-2.
+template <int STRIDE>
 __global__ void __launch_bounds__(256) match_finalize_kernel(const mkey_t* __restrict__ cand, int nq,
                                                               int nt, int nsplit, double ratio,
+                                                              const float* __restrict__ qf, const float* __restrict__ tf,
                                                               int* __restrict__ idx, float* __restrict__ dist,
                                                               unsigned char* __restrict__ good,
                                                               int* __restrict__ n_good) {
@@ -21,8 +26,30 @@ __global__ void __launch_bounds__(256) match_finalize_kernel(const mkey_t* __res
   bool g = false;
   if (i < nq) {
     mkey_t k1 = MKEY_INF, k2 = MKEY_INF;
-    const mkey_t* c = cand + (size_t)i * nsplit * 2;
-    for (int s = 0; s < 2 * nsplit; ++s) key_insert(c[s], k1, k2);
+    const mkey_t* c = cand + (size_t)i * nsplit * STRIDE;
+    for (int s = 0; s < nsplit; ++s) {
+      key_insert(c[s * STRIDE], k1, k2);
+      key_insert(c[s * STRIDE + 1], k1, k2);
+    }
+    if (STRIDE == 3) {
+      for (int s = 0; s < nsplit; ++s) {
+        const mkey_t k3 = c[s * STRIDE + 2];
+        if (k3 < k2) {
+          const int col = (int)(unsigned int)(k3 & 0xFFFFFFFFull);
+          if (col < nt) {
+            const float4* a = reinterpret_cast<const float4*>(qf + (size_t)i * 128);
+            const float4* b = reinterpret_cast<const float4*>(tf + (size_t)col * 128);
+            float d2 = 0.f;
+            for (int k = 0; k < 32; ++k) {
+              const float4 x = a[k], y = b[k];
+              const float e0 = x.x - y.x, e1 = x.y - y.y, e2 = x.z - y.z, e3 = x.w - y.w;
+              d2 += e0 * e0 + e1 * e1 + e2 * e2 + e3 * e3;     // integers < 2^24: exact in any order
+            }
+            if (__float_as_uint(d2) == (unsigned int)(k3 >> 32)) key_insert(k3, k1, k2);
+          }
+        }
+      }
+    }
     int i1 = (int)(unsigned int)(k1 & 0xFFFFFFFFull), i2 = (int)(unsigned int)(k2 & 0xFFFFFFFFull);
     bool v1 = (k1 != MKEY_INF) && i1 < nt, v2 = (k2 != MKEY_INF) && i2 < nt;
     float d1 = v1 ? __fsqrt_rn(__uint_as_float((unsigned int)(k1 >> 32))) : __int_as_float(0x7f800000);
@@ -39,11 +66,15 @@ __global__ void __launch_bounds__(256) match_finalize_kernel(const mkey_t* __res
 }
 
 int sfm_match_finalize(sfm_ctx* ctx, const mkey_t* cand, int nq, int nt, int nsplit, double ratio,
-                       int32_t* idx, float* dist, uint8_t* good, int32_t* n_good) {
+                       const float* qf, const float* tf, int32_t* idx, float* dist, uint8_t* good, int32_t* n_good) {
   if (n_good) SFM_CUDA(cudaMemsetAsync(n_good, 0, sizeof(int32_t), ctx->stream));
   if (nq == 0) return SFM_OK;
-  SFM_LAUNCH(ctx, SFM_K_MATCH_FINAL, (match_finalize_kernel<<<div_up(nq, 256), 256, 0, ctx->stream>>>(
-                                         cand, nq, nt, nsplit, ratio, idx, dist, good, n_good)));
+  if (qf && tf)
+    SFM_LAUNCH(ctx, SFM_K_MATCH_FINAL, (match_finalize_kernel<3><<<div_up(nq, 256), 256, 0, ctx->stream>>>(
+                                           cand, nq, nt, nsplit, ratio, qf, tf, idx, dist, good, n_good)));
+  else
+    SFM_LAUNCH(ctx, SFM_K_MATCH_FINAL, (match_finalize_kernel<2><<<div_up(nq, 256), 256, 0, ctx->stream>>>(
+                                           cand, nq, nt, nsplit, ratio, nullptr, nullptr, idx, dist, good, n_good)));
   return SFM_OK;
 }
 
@@ -210,14 +241,16 @@ static int match_pair(sfm_ctx* ctx, const sfm_desc* q, const sfm_desc* t, double
       SFM_CUDA(cudaMemsetAsync(cand, 0xFF, (size_t)nq * 2 * sizeof(mkey_t), ctx->stream));
     } else if (use_tc) {
       nsplit = sfm_match_tc_splits(ctx, nq, nt);
-      SFM_TRY(ws_alloc_t(ctx, (size_t)q->n_tiles * 128 * nsplit * 2, &cand));
+      SFM_TRY(ws_alloc_t(ctx, (size_t)q->n_tiles * 128 * nsplit * 3, &cand));
       SFM_TRY(sfm_match_tc_launch(ctx, q, t, cand, nsplit));
     } else {
       nsplit = sfm_match_exact_splits(ctx, nq, nt);
       SFM_TRY(ws_alloc_t(ctx, (size_t)nq * nsplit * 2, &cand));
       SFM_TRY(sfm_match_exact_launch(ctx, q->f32, nq, t->f32, nt, q->dim, cand, nsplit));
     }
-    SFM_TRY(sfm_match_finalize(ctx, cand, nq, nt, nsplit, ratio, oidx.dev, odist.dev, ogood.dev, ong.dev));
+    const bool tc_cand = nt > 0 && use_tc;
+    SFM_TRY(sfm_match_finalize(ctx, cand, nq, nt, nsplit, ratio, tc_cand ? q->f32 : nullptr, tc_cand ? t->f32 : nullptr,
+                               oidx.dev, odist.dev, ogood.dev, ong.dev));
   } else if (ong.dev) {
     SFM_CUDA(cudaMemsetAsync(ong.dev, 0, sizeof(int32_t), ctx->stream));
   }

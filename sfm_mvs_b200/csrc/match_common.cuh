@@ -53,5 +53,6 @@ int sfm_match_tc_splits(sfm_ctx* ctx, int nq, int nt);
 int sfm_match_tc_launch(sfm_ctx* ctx, const sfm_desc* q, const sfm_desc* t, mkey_t* cand, int nsplit);
 int sfm_desc_prepare_launch(sfm_ctx* ctx, sfm_desc* d, const void* src, int dtype);
 // match.cu
+// qf/tf non-null: candidates come from the tensor-core kernel ([nq][nsplit][3]); null: [nq][nsplit][2]
 int sfm_match_finalize(sfm_ctx* ctx, const mkey_t* cand, int nq, int nt, int nsplit, double ratio,
-                       int32_t* idx, float* dist, uint8_t* good, int32_t* n_good);
+                       const float* qf, const float* tf, int32_t* idx, float* dist, uint8_t* good, int32_t* n_good);

@@ -120,7 +120,9 @@ __global__ void __launch_bounds__(256) desc_prepare_kernel(const T* __restrict__
   else if (sub == 1) { a0 = c2; a1 = 1.f; b0 = 1.f; b1 = c0; }
   else if (sub == 2) { a0 = 1.f; a1 = 1.f; b0 = c1; b1 = c2; }
   else { a0 = 1.f; a1 = 0.f; b0 = -4194304.f; b1 = 0.f; }
-  if (!valid) { a0 = a1 = b0 = b1 = 0.f; }
+  // padding rows: as a query they produce garbage nobody reads; as a train column the accumulator becomes
+  // exactly -255 * 2^15 (bits 0xCAFF0000, a "distance" above any real one), so the epilogue needs no masking
+  if (!valid) { a0 = a1 = b1 = 0.f; b0 = (sub == 3) ? -8355840.f : 0.f; }
   *reinterpret_cast<__nv_bfloat162*>(gbase + 16 * tc::LBO + lane * 4) = __floats2bfloat162_rn(a0, a1);
   *reinterpret_cast<__nv_bfloat162*>(gbase + 17 * tc::LBO + lane * 4) = __floats2bfloat162_rn(0.f, 0.f);
   *reinterpret_cast<__nv_bfloat162*>(gbase + 18 * tc::LBO + lane * 4) = __floats2bfloat162_rn(b0, b1);
@@ -230,69 +232,50 @@ struct TcParams {
   int nsplit;
   int stages_per_split;
   int n_items;
-  mkey_t* cand;                   // [n_qtiles*128][nsplit][2]
+  mkey_t* cand;                   // [n_qtiles*128][nsplit][3]: best, runner-up, "check this column" (K1c)
   float* dump;                    // debug: raw accumulators [n_qtiles*128][n_stages*128] or NULL
-  unsigned int key_mul;           // = 32, passed at run time so the key build stays an IMAD (FMA pipe)
+  unsigned int key_mul;           // = 256, passed at run time so the key build stays an IMAD (FMA pipe)
   unsigned int debug;             // diagnostics (env SFM_MATCH_DEBUG): bit0 skip epilogue math, bit1 skip MMAs
 };
 
-// Reduce one 32-column chunk (already in registers) into a stage-level top-2 (k1, k2).
-// c = chunk index inside the 128-column stage, nv = valid columns left from the chunk start.
-// Four independent (min, second-min) chains over interleaved columns: an epilogue warp has its SM
-// sub-partition to itself, so a single dependent min/max chain would run at instruction latency
-// (measured: ~18 cycles per element) instead of ALU throughput; the four chains are merged at the end.
-__device__ __forceinline__ void chunk_top2(const uint32_t (&r)[32], const uint32_t (&jconst)[32], uint32_t mul32, int c,
-                                           int nv, uint32_t& k1, uint32_t& k2) {
-  uint32_t c1[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
-  uint32_t c2[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
-  if (nv >= 32) {
+// ---------------------------------------------------------------------------- epilogue arithmetic
+// The accumulator bits are 0xCA800000 | d^2.  key = bits * 256 + tag (one IMAD, FMA pipe) is
+// 0x80000000 | d^2 << 8 | tag with tag = index of the 32-column chunk inside the split (< 256), so
+// unsigned order on keys is (d^2, chunk) order.  Per query row (= per thread) the epilogue keeps
+//   acc[j], j = column mod 32 : the minimum key of every residue class ("vertical" minima), and
+//   (h1, h2)                  : the two smallest per-chunk minima ("horizontal" minima).
+// That is ONE integer min/max-pipe operation per element (two 3-input minima per two elements) instead
+// of the three a running top-2 needs, and it still determines the exact top-2 of the row: the best
+// element e1 is the smallest (acc[j], j); the runner-up e2 is either in another class than e1 — then it
+// is the minimum of its class and shows up as the second smallest (acc[j], j) — or in e1's class j1 —
+// then it is in another chunk, is the minimum of that chunk, and h2 is its key (column = chunk*32+j1).
+// Columns inside one chunk have distinct classes, so no pair of elements can hide in both views.
+__device__ __forceinline__ uint32_t umin3(uint32_t a, uint32_t b, uint32_t c) { return min(min(a, b), c); }
+
+__device__ __forceinline__ uint32_t chunk_min(const uint32_t (&k)[32]) {
+  uint32_t m[11];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const uint32_t key = r[j] * mul32 + jconst[j];
-      const uint32_t t = max(c1[j & 3], key);
-      c1[j & 3] = min(c1[j & 3], key);
-      c2[j & 3] = min(c2[j & 3], t);
-    }
-  } else {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const uint32_t key = (j < nv) ? (r[j] * mul32 + jconst[j]) : 0xFFFFFFFFu;
-      const uint32_t t = max(c1[j & 3], key);
-      c1[j & 3] = min(c1[j & 3], key);
-      c2[j & 3] = min(c2[j & 3], t);
-    }
-  }
-  // merge the four chains: (a1,a2) + (b1,b2) -> (min(a1,b1), min(max(a1,b1), min(a2,b2)))
-  const uint32_t m01 = min(c1[0], c1[1]), s01 = min(max(c1[0], c1[1]), min(c2[0], c2[1]));
-  const uint32_t m23 = min(c1[2], c1[3]), s23 = min(max(c1[2], c1[3]), min(c2[2], c2[3]));
-  const uint32_t w1 = min(m01, m23), w2 = min(max(m01, m23), min(s01, s23));
-  // chunk key (0x50000000 | d2 << 5 | j)  ->  stage key (0x80000000 | d2 << 8 | column)
-  if (w1 != 0xFFFFFFFFu) {
-    const uint32_t w = ((w1 >> 5) << 8) | (uint32_t)(c * 32) | (w1 & 31u);
-    const uint32_t t = max(k1, w);
-    k1 = min(k1, w);
-    k2 = min(k2, t);
-  }
-  if (w2 != 0xFFFFFFFFu) {
-    const uint32_t w = ((w2 >> 5) << 8) | (uint32_t)(c * 32) | (w2 & 31u);
-    k2 = min(k2, max(k1, w));
-    k1 = min(k1, w);
-  }
+  for (int i = 0; i < 10; ++i) m[i] = umin3(k[3 * i], k[3 * i + 1], k[3 * i + 2]);
+  m[10] = min(k[30], k[31]);
+  const uint32_t a = umin3(m[0], m[1], m[2]), b = umin3(m[3], m[4], m[5]), c = umin3(m[6], m[7], m[8]);
+  return umin3(umin3(a, b, c), m[9], m[10]);
 }
 
-// Experiment (SFM_MATCH_DEBUG bit 3): top-2 VALUES only with floating-point min/max (FMNMX), two chains.
-__device__ __forceinline__ void chunk_top2_f32(const uint32_t (&r)[32], uint32_t& k1, uint32_t& k2) {
-  float a1 = -3.0e38f, a2 = -3.0e38f, b1 = -3.0e38f, b2 = -3.0e38f;
+// Two 32-column chunks (raw accumulator bits in a, b) folded into the row state.
+__device__ __forceinline__ void fold_pair(uint32_t (&a)[32], uint32_t (&b)[32], uint32_t mul256, uint32_t tag_a,
+                                          uint32_t (&acc)[32], uint32_t& h1, uint32_t& h2) {
+  const uint32_t tag_b = tag_a + 1u;
 #pragma unroll
-  for (int j = 0; j < 32; j += 2) {
-    const float x = __uint_as_float(r[j]), y = __uint_as_float(r[j + 1]);
-    const float ta = fminf(a1, x), tb = fminf(b1, y);
-    a1 = fmaxf(a1, x); b1 = fmaxf(b1, y);
-    a2 = fmaxf(a2, ta); b2 = fmaxf(b2, tb);
+  for (int j = 0; j < 32; ++j) {
+    a[j] = a[j] * mul256 + tag_a;
+    b[j] = b[j] * mul256 + tag_b;
   }
-  const float m1 = fmaxf(a1, b1), m2 = fmaxf(fminf(a1, b1), fmaxf(a2, b2));
-  k1 = min(k1, __float_as_uint(m1));
-  k2 = min(k2, __float_as_uint(m2));
+#pragma unroll
+  for (int j = 0; j < 32; ++j) acc[j] = umin3(acc[j], a[j], b[j]);
+  const uint32_t ha = chunk_min(a), hb = chunk_min(b);     // ha != hb (different tags)
+  const uint32_t lo = min(ha, hb), hi = max(ha, hb);
+  h2 = umin3(max(h1, lo), h2, hi);
+  h1 = min(h1, lo);
 }
 
 // ============================================================================ K1 kernel
@@ -393,76 +376,94 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) match_tc_kernel(TcParams p) {
   } else {
     // ------------------------------------------------------------------ epilogue (warps 2..9)
     // Two warps per TMEM lane quarter (= per SM sub-partition): warps 2-5 reduce query tile 0 of the
-    // pair, warps 6-9 query tile 1.  (Measured: a single warp per sub-partition issues min/max at
-    // ~4 cycles per instruction; two warps per sub-partition double the epilogue rate.)
+    // pair, warps 6-9 query tile 1; one query row per thread.
     const int quarter = warp & 3;                 // TMEM lane quarter this warp may read
     const int row = quarter * 32 + lane;          // query row within a tile
     const int tq = (warp - 2) >> 2;               // which query tile of the pair this warp owns
     uint32_t acc_phase[2] = {0, 0};
     int buf = 0;
-    uint32_t jconst[32];            // 0..31 held in registers (IMAD addend)
-#pragma unroll
-    for (int j = 0; j < 32; ++j) jconst[j] = (uint32_t)j;
-    const uint32_t mul32 = p.key_mul;   // 32, opaque to the compiler: the key build stays an IMAD (FMA pipe),
-                                        // leaving the ALU pipe to the min/max chain
+    const uint32_t mul256 = p.key_mul;  // 256, opaque to the compiler: the key build stays an IMAD (FMA pipe),
+                                        // leaving the integer min/max pipe to the minima
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
       const int qp = item / p.nsplit, split = item % p.nsplit;
       const int s_begin = split * p.stages_per_split;
       const int s_end = min(p.n_stages, s_begin + p.stages_per_split);
       const int nqt = min(tc::QT_PER_ITEM, p.n_qtiles - qp * tc::QT_PER_ITEM);
       const bool active = tq < nqt;
-      mkey_t g1 = MKEY_INF, g2 = MKEY_INF;
+      uint32_t acc[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) acc[j] = 0xFFFFFFFFu;
+      uint32_t h1 = 0xFFFFFFFFu, h2 = 0xFFFFFFFFu;
       for (int s = s_begin; s < s_end; ++s) {
         mbar_wait(bar(tc::ACC_FULL + buf), acc_phase[buf]);
         acc_phase[buf] ^= 1;
         tc_fence_after();
         const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * tc::ACC_COLS + tq * tc::STAGE_COLS);
-        const int col0 = s * tc::STAGE_COLS;
-        const int n_valid = p.nt - col0;          // columns of this stage that are real train rows
-        uint32_t k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu;
-        if (active) {
-          // four 32-column chunks; the TMEM load of the next chunk is in flight while the current one
-          // is reduced (two register buffers)
-          uint32_t ra[32], rb[32];
-          const bool do_ld = !(p.debug & 4u);
-          if (do_ld) tmem_ld32(t_addr, ra);
+        const uint32_t tag0 = (uint32_t)(s - s_begin) * (tc::STAGE_COLS / 32);
+        if (active && !(p.debug & 4u)) {
+          uint32_t ra[32], rb[32], rc[32];
+          tmem_ld32(t_addr, ra);
+          tmem_ld32(t_addr + 32, rb);
+          tmem_ld_wait_regs(ra);
+          tmem_ld_wait_regs(rb);
+          tmem_ld32(t_addr + 64, rc);             // third chunk in flight while the first two are folded
+          if (DUMP) {
+            float* drow = p.dump + ((size_t)((qp * tc::QT_PER_ITEM + tq) * 128 + row) * p.n_stages + s) * tc::STAGE_COLS;
 #pragma unroll
-          for (int c = 0; c < tc::STAGE_COLS / 32; c += 2) {
-            tmem_ld_wait_regs(ra);
-            if (do_ld) tmem_ld32(t_addr + (c + 1) * 32, rb);
-            if (DUMP) {
-              float* drow = p.dump + ((size_t)((qp * tc::QT_PER_ITEM + tq) * 128 + row) * p.n_stages + s) * tc::STAGE_COLS + c * 32;
-#pragma unroll
-              for (int j = 0; j < 32; ++j) drow[j] = __uint_as_float(ra[j]);
-            }
-            if (p.debug & 8u) chunk_top2_f32(ra, k1, k2);
-            else if (p.debug & 1u) k1 = min(k1, ra[0] ^ ra[31]);
-            else chunk_top2(ra, jconst, mul32, c, n_valid - c * 32, k1, k2);
-            tmem_ld_wait_regs(rb);
-            if (do_ld && c + 2 < tc::STAGE_COLS / 32) tmem_ld32(t_addr + (c + 2) * 32, ra);
-            if (DUMP) {
-              float* drow = p.dump + ((size_t)((qp * tc::QT_PER_ITEM + tq) * 128 + row) * p.n_stages + s) * tc::STAGE_COLS + (c + 1) * 32;
-#pragma unroll
-              for (int j = 0; j < 32; ++j) drow[j] = __uint_as_float(rb[j]);
-            }
-            if (p.debug & 8u) chunk_top2_f32(rb, k1, k2);
-            else if (p.debug & 1u) k1 = min(k1, rb[0] ^ rb[31]);
-            else chunk_top2(rb, jconst, mul32, c + 1, n_valid - (c + 1) * 32, k1, k2);
+            for (int j = 0; j < 32; ++j) { drow[j] = __uint_as_float(ra[j]); drow[32 + j] = __uint_as_float(rb[j]); }
           }
+          if (p.debug & 1u) h1 = min(h1, ra[0] ^ rb[31]);
+          else fold_pair(ra, rb, mul256, tag0, acc, h1, h2);
+          tmem_ld32(t_addr + 96, ra);
+          tmem_ld_wait_regs(rc);
+          tmem_ld_wait_regs(ra);
+          // every column of this accumulator is in registers: hand the TMEM buffer back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar(tc::ACC_EMPTY + buf));
+          if (DUMP) {
+            float* drow = p.dump + ((size_t)((qp * tc::QT_PER_ITEM + tq) * 128 + row) * p.n_stages + s) * tc::STAGE_COLS + 64;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { drow[j] = __uint_as_float(rc[j]); drow[32 + j] = __uint_as_float(ra[j]); }
+          }
+          if (p.debug & 1u) h1 = min(h1, rc[0] ^ ra[31]);
+          else fold_pair(rc, ra, mul256, tag0 + 2u, acc, h1, h2);
+        } else {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar(tc::ACC_EMPTY + buf));
         }
-        // accumulator drained -> hand the TMEM buffer back to the MMA warp
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar(tc::ACC_EMPTY + buf));
         buf ^= 1;
-        // fold the stage-local winners into the split-wide top-2 (64-bit keys: float bits of d^2, index)
-        if (k1 != 0xFFFFFFFFu) key_insert(make_key((float)((k1 >> 8) & 0x7FFFFFu), col0 + (int)(k1 & 0xFFu)), g1, g2);
-        if (k2 != 0xFFFFFFFFu) key_insert(make_key((float)((k2 >> 8) & 0x7FFFFFu), col0 + (int)(k2 & 0xFFu)), g1, g2);
       }
       if (active) {
-        mkey_t* out = p.cand + ((size_t)((qp * tc::QT_PER_ITEM + tq) * 128 + row) * p.nsplit + split) * 2;
-        out[0] = g1;
-        out[1] = g2;
+        // row state -> the split's candidates.  (key, class) order == (d^2, column) order.
+        uint32_t b1 = 0xFFFFFFFFu, b2 = 0xFFFFFFFFu;
+        int j1 = 0, j2 = 0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const uint32_t k = acc[j];
+          if (k < b1) { b2 = b1; j2 = j1; b1 = k; j1 = j; }
+          else if (k < b2) { b2 = k; j2 = j; }
+        }
+        const int col_base = s_begin * tc::STAGE_COLS;
+        auto key_d2 = [](uint32_t k) { return (k >> 8) & 0x7FFFFFu; };
+        auto key_col = [&](uint32_t k, int j) { return col_base + (int)(k & 0xFFu) * 32 + j; };
+        mkey_t o1 = MKEY_INF, o2 = MKEY_INF, o3 = MKEY_INF;
+        if (key_d2(b1) <= 2u * tc::MAX_SQNORM) o1 = make_key((float)key_d2(b1), key_col(b1, j1));
+        if (h2 < b2) {                       // runner-up hidden behind e1 in class j1: it is chunk h2's minimum
+          if (key_d2(h2) <= 2u * tc::MAX_SQNORM) o2 = make_key((float)key_d2(h2), key_col(h2, j1));
+        } else {
+          if (key_d2(b2) <= 2u * tc::MAX_SQNORM) {
+            o2 = make_key((float)key_d2(b2), key_col(b2, j2));
+            // same d^2 in the same chunk: the chunk may also hold an equal element in class j1 (hidden behind
+            // e1); if j1 < j2 it would precede o2.  K1c checks that column when it matters.
+            if (h2 == b2 && j1 < j2) o3 = make_key((float)key_d2(b2), key_col(b2, j1));
+          }
+        }
+        mkey_t* out = p.cand + ((size_t)((qp * tc::QT_PER_ITEM + tq) * 128 + row) * p.nsplit + split) * 3;
+        out[0] = o1;
+        out[1] = o2;
+        out[2] = o3;
       }
     }
   }
@@ -477,6 +478,8 @@ int sfm_match_tc_splits(sfm_ctx* ctx, int nq, int nt) {
   int qpairs = div_up(div_up(nq, tc::TILE_ROWS), tc::QT_PER_ITEM);
   int stages = div_up(nt, tc::TILE_ROWS);
   int s = ctx->sm_count / (qpairs > 0 ? qpairs : 1);
+  int s_min = div_up(stages, 256 / (tc::STAGE_COLS / 32));   // chunk tags are 8 bits: <= 256 chunks per split
+  if (s < s_min) s = s_min;
   if (s < 1) s = 1;
   if (s > stages) s = stages;
   return s < 1 ? 1 : s;
@@ -502,7 +505,7 @@ static int launch_tc(sfm_ctx* ctx, const sfm_desc* q, const sfm_desc* t, mkey_t*
   p.n_items = p.n_qpairs * nsplit;
   p.cand = cand;
   p.dump = dump;
-  p.key_mul = 32u;
+  p.key_mul = 256u;
   { const char* e = getenv("SFM_MATCH_DEBUG"); p.debug = e ? (unsigned)atoi(e) : 0u; }
   int grid = p.n_items < ctx->sm_count ? p.n_items : ctx->sm_count;
   if (dump) SFM_LAUNCH(ctx, SFM_K_MATCH_TC, (match_tc_kernel<true><<<grid, tc::NTHREADS, tc::SMEM_BYTES, ctx->stream>>>(p)));
@@ -527,7 +530,7 @@ extern "C" int sfm_debug_match_tc_dump(sfm_ctx* ctx, const sfm_desc* q, const sf
   SFM_REQUIRE((int64_t)count <= capacity, "dump buffer too small: need %zu floats", count);
   mkey_t* cand;
   float* dump;
-  SFM_TRY(ws_alloc_t(ctx, (size_t)q->n_tiles * 128 * nsplit * 2, &cand));
+  SFM_TRY(ws_alloc_t(ctx, (size_t)q->n_tiles * 128 * nsplit * 3, &cand));
   SFM_TRY(ws_alloc_t(ctx, count, &dump));
   SFM_TRY(launch_tc(ctx, q, t, cand, nsplit, dump));
   SFM_CUDA(cudaMemcpyAsync(dump_host, dump, count * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
