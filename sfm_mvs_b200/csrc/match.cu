@@ -24,32 +24,38 @@ __global__ void __launch_bounds__(256) match_finalize_kernel(const mkey_t* __res
                                                               int* __restrict__ n_good) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   bool g = false;
+  mkey_t k1 = MKEY_INF, k2 = MKEY_INF;
   if (i < nq) {
-    mkey_t k1 = MKEY_INF, k2 = MKEY_INF;
     const mkey_t* c = cand + (size_t)i * nsplit * STRIDE;
     for (int s = 0; s < nsplit; ++s) {
       key_insert(c[s * STRIDE], k1, k2);
       key_insert(c[s * STRIDE + 1], k1, k2);
     }
-    if (STRIDE == 3) {
-      for (int s = 0; s < nsplit; ++s) {
-        const mkey_t k3 = c[s * STRIDE + 2];
-        if (k3 < k2) {
-          const int col = (int)(unsigned int)(k3 & 0xFFFFFFFFull);
-          if (col < nt) {
-            const float4* a = reinterpret_cast<const float4*>(qf + (size_t)i * 128);
-            const float4* b = reinterpret_cast<const float4*>(tf + (size_t)col * 128);
-            float d2 = 0.f;
-            for (int k = 0; k < 32; ++k) {
-              const float4 x = a[k], y = b[k];
-              const float e0 = x.x - y.x, e1 = x.y - y.y, e2 = x.z - y.z, e3 = x.w - y.w;
-              d2 += e0 * e0 + e1 * e1 + e2 * e2 + e3 * e3;     // integers < 2^24: exact in any order
-            }
-            if (__float_as_uint(d2) == (unsigned int)(k3 >> 32)) key_insert(k3, k1, k2);
-          }
-        }
+  }
+  if (STRIDE == 3) {
+    // "check this column" keys: evaluated by the whole warp, one 128-dimensional difference at a time
+    // (coalesced 512-byte rows, shuffle reduction) — a few per warp, instead of a divergent per-lane loop
+    const int lane = threadIdx.x & 31;
+    const mkey_t* c = cand + (size_t)(i < nq ? i : 0) * nsplit * STRIDE;
+    for (int s = 0; s < nsplit; ++s) {
+      const mkey_t k3 = (i < nq) ? c[s * STRIDE + 2] : MKEY_INF;
+      const int col = (int)(unsigned int)(k3 & 0xFFFFFFFFull);
+      unsigned need = __ballot_sync(0xffffffffu, k3 < k2 && col < nt);
+      while (need) {
+        const int src = __ffs(need) - 1;
+        need &= need - 1;
+        const int r = __shfl_sync(0xffffffffu, i, src), cc = __shfl_sync(0xffffffffu, col, src);
+        const float4 x = reinterpret_cast<const float4*>(qf + (size_t)r * 128)[lane];
+        const float4 y = reinterpret_cast<const float4*>(tf + (size_t)cc * 128)[lane];
+        const float e0 = x.x - y.x, e1 = x.y - y.y, e2 = x.z - y.z, e3 = x.w - y.w;
+        float d2 = e0 * e0 + e1 * e1 + e2 * e2 + e3 * e3;     // integers < 2^24: exact in any order
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+        if (lane == src && __float_as_uint(d2) == (unsigned int)(k3 >> 32)) key_insert(k3, k1, k2);
       }
     }
+  }
+  if (i < nq) {
     int i1 = (int)(unsigned int)(k1 & 0xFFFFFFFFull), i2 = (int)(unsigned int)(k2 & 0xFFFFFFFFull);
     bool v1 = (k1 != MKEY_INF) && i1 < nt, v2 = (k2 != MKEY_INF) && i2 < nt;
     float d1 = v1 ? __fsqrt_rn(__uint_as_float((unsigned int)(k1 >> 32))) : __int_as_float(0x7f800000);

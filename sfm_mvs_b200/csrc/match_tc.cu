@@ -12,31 +12,37 @@
 //   image the tensor core wants — K-major, no swizzle, 8x(16 B) core matrices:
 //     byte(r,k) = (r/8)*SBO + (k/8)*LBO + (r%8)*16 + (k%8)*2,  LBO = 128, SBO = 20*128
 //   with K = 160 bf16 columns: 128 descriptor values + 16 "A-role" + 16 "B-role" augmentation
-//   columns.  Because the image already is the smem layout, a tile (40 KiB) or a two-tile stage
-//   (80 KiB) moves HBM->smem with ONE cp.async.bulk (TMA bulk engine, mbarrier complete_tx),
-//   no tensor map, no swizzle bookkeeping, fully contiguous reads.
+//   columns.  Because the image already is the smem layout, a tile (40 KiB) moves HBM->smem with
+//   ONE cp.async.bulk (TMA bulk engine, mbarrier complete_tx), no tensor map, no swizzle
+//   bookkeeping, fully contiguous reads.
 //
 // Augmentation (h = |d|^2, integer <= 2^21; c0,c1,c2 = the three bytes of h, each halved — all
 // bf16-exact):   A-role cols 128..143 = [-c0,-c1,-c2, 1,1,1,1, 0...]
 //                B-role cols 144..159 = [ 1, 1, 1,-c0,-c1,-c2,-2^22, 0...]
 //   acc = q.t  - (|q|^2+|t|^2)/2 - 2^22 = -(2^22 + d^2/2)   in (-2^23, -2^22]
-//   so the fp32 bit pattern of acc is 0xCA800000 | d^2 : the epilogue never converts or adds, it
-//   forms a sortable 32-bit key (bits<<8 | column) with one integer op and keeps a running top-2
-//   with three integer min/max ops per element.
+//   so the fp32 bit pattern of acc is 0xCA800000 | d^2 : the epilogue never converts or adds.
+//   Padding rows of a train tile carry B-role [0,0,0,0,0,0,-255*2^15]: their accumulator is
+//   0xCAFF0000, above every real distance, so the epilogue needs no column masking.
 //
-// Kernel: persistent, warp-specialised, 1 CTA/SM, 320 threads:
-//   warp 0  producer  — cp.async.bulk of TWO query tiles (once per work item, 80 KiB) and of one
-//                       128-row train tile per stage into a 3-deep smem ring (full/empty mbarriers)
-//   warp 1  MMA       — one lane issues 2 x 9 tcgen05.mma (M128 N128 K16, bf16 -> fp32 in TMEM), one
-//                       set per resident query tile; tcgen05.commit releases the smem stage and
-//                       publishes the accumulator pair
-//   warps 2-9 epilogue — tcgen05.ld 32x32b.x32 of their TMEM lane quarter (one query row per thread,
-//                       two warps per quarter, one per query tile), top-2 in registers; TMEM
-//                       accumulators are double-buffered (2 x 256 columns) so the epilogue of stage s
-//                       overlaps the MMAs of s+1.
-// A work item is (query tile pair, train split); per-split results are merged by K1c (match.cu).
-// Measured motivation for the tile pair: with one query tile per train tile the kernel saturated
-// L2 -> SM bandwidth (~6.4 TB/s of train-tile re-reads at 32k x 32k) at 31 % tensor-pipe activity.
+// Kernel: persistent, warp-specialised, ONE CTA PAIR per TPC (cluster of 2, tcgen05 cta_group::2),
+// 352 threads per CTA.  The pair multiplies a 256-row query block (128 rows from each CTA's shared
+// memory) with a 256-column train stage (128 columns from each CTA's shared memory): one
+// tcgen05.mma M256 N256 K16 per 128 cycles reads only 8 KiB of shared memory per CTA — half of what
+// two independent M128 N128 instructions need, which is what bounded the single-CTA version
+// (measured: 128 B/clk of operand reads + the TMA writes saturate shared memory at ~57 % tensor
+// activity) — and every train tile fetched from L2 feeds 256 (QT=1) or 512 (QT=2) query rows.
+//   warp 0   B producer — cp.async.bulk of this CTA's 128-column half of every train stage into a
+//                         3-deep ring
+//   warp 2   A producer — this CTA's query tiles (2-slot ring: the next item's tile loads while the
+//                         last jobs of the current item run)
+//   warp 1   leader CTA: one lane issues 9 x tcgen05.mma (8 K-steps + the augmentation step) per job
+//                         and multicast tcgen05.commit to both CTAs' barriers;
+//            peer CTA:   relays "my TMA data landed" to the leader's barriers (remote mbarrier arrive)
+//   warps 3-10 epilogue — tcgen05.ld 32x32b.x32 of their TMEM lane quarter (one query row per thread,
+//                         two warps per quarter, each taking 128 of the 256 columns)
+// A job = (query tile t of the item, train stage s); its accumulator (128 lanes x 256 columns per
+// CTA) lives in TMEM slot job&1, so the epilogue of job j overlaps the MMAs of job j+1.
+// A work item is (query group, train split); per-(split, column half) candidates are merged by K1c.
 #include <cuda_bf16.h>
 #include <stdlib.h>
 
@@ -50,21 +56,19 @@ constexpr int CORE_COLS = KAUG / 8;             // 20 core-matrix columns
 constexpr int LBO = 128;                        // bytes between K-adjacent core matrices
 constexpr int SBO = CORE_COLS * 128;            // bytes between 8-row groups (2560)
 constexpr int TILE_BYTES = (TILE_ROWS / 8) * SBO;   // 40960
-constexpr int QT_PER_ITEM = 2;                  // query tiles resident per work item: every train tile read
-                                                // from L2 feeds 2 x 128 query rows (halves L2 -> SM traffic,
-                                                // which is what bounds this kernel, not the tensor pipe)
-constexpr int STAGE_COLS = TILE_ROWS;           // one 128-row train tile per stage, MMA N = 128
-constexpr int STAGE_BYTES = TILE_BYTES;         // 40960
-constexpr int NSTAGE = 3;                       // train-tile ring depth
-constexpr int ACC_COLS = QT_PER_ITEM * STAGE_COLS;   // 256 TMEM columns per accumulator buffer (x2 buffers)
-constexpr int NTHREADS = 320;                   // producer warp, MMA warp, 8 epilogue warps
+constexpr int STAGE_COLS = 256;                 // train columns per stage: 128 from each CTA of the pair
+constexpr int NA = 2;                           // query-tile ring depth (per CTA)
+constexpr int NB = 3;                           // train-tile ring depth (per CTA)
+constexpr int NTHREADS = 352;                   // B producer, MMA/relay, A producer, 8 epilogue warps
 constexpr int SMEM_A = 0;
-constexpr int SMEM_B = QT_PER_ITEM * TILE_BYTES;            // 81920
-constexpr int SMEM_BAR = SMEM_B + NSTAGE * STAGE_BYTES;     // 204800
-constexpr int SMEM_BYTES = SMEM_BAR + 128;
+constexpr int SMEM_B = NA * TILE_BYTES;                 // 81920
+constexpr int SMEM_BAR = SMEM_B + NB * TILE_BYTES;      // 204800
 constexpr unsigned MAX_SQNORM = 1u << 21;
-// barrier indices
-enum { A_FULL = 0, A_EMPTY = 1, B_FULL = 2, B_EMPTY = 5, ACC_FULL = 8, ACC_EMPTY = 10, NBAR = 12 };
+constexpr int CHUNK = 16;                       // epilogue chunk width = number of residue classes
+constexpr int MAX_STAGES_PER_SPLIT = 256 / (STAGE_COLS / CHUNK);   // chunk tags are 8 bits -> 16 stages
+// barrier indices (same layout in both CTAs)
+enum { A_FULL = 0, A_EMPTY = 2, A_PEER = 4, B_FULL = 6, B_EMPTY = 9, B_PEER = 12, ACC_FULL = 15, ACC_EMPTY = 17, NBAR = 19 };
+constexpr int SMEM_BYTES = SMEM_BAR + 256;
 }  // namespace tc
 
 // ============================================================================ K1b descriptor prep
@@ -225,296 +229,390 @@ __device__ __forceinline__ constexpr uint32_t make_idesc(int M, int N) {
 struct TcParams {
   const unsigned char* q_tiles;   // query view image
   const unsigned char* t_tiles;   // train view image
-  int n_qtiles;                   // 128-row query tiles
-  int n_qpairs;                   // work-item rows: ceil(n_qtiles / 2)
-  int n_stages;                   // 128-row train tiles
-  int nt;                         // valid train rows
+  int n_qtiles;                   // 128-row query tiles holding real rows
+  int n_qtiles_alloc;             // tiles present in the image (even)
+  int n_stages;                   // 256-column train stages
+  int n_groups;                   // query groups of 2*QT tiles
   int nsplit;
-  int stages_per_split;
   int n_items;
-  mkey_t* cand;                   // [n_qtiles*128][nsplit][3]: best, runner-up, "check this column" (K1c)
-  float* dump;                    // debug: raw accumulators [n_qtiles*128][n_stages*128] or NULL
+  mkey_t* cand;                   // [n_qtiles*128][2*nsplit][3]: best, runner-up, "check this column" (K1c)
+  float* dump;                    // debug: raw accumulators [n_qtiles*128][dump_cols] or NULL
+  int dump_cols;
   unsigned int key_mul;           // = 256, passed at run time so the key build stays an IMAD (FMA pipe)
-  unsigned int debug;             // diagnostics (env SFM_MATCH_DEBUG): bit0 skip epilogue math, bit1 skip MMAs
+  unsigned int debug;             // diagnostics (env SFM_MATCH_DEBUG): bit0 skip epilogue math, bit1 skip MMAs, bit2 skip TMEM loads
 };
 
 // ---------------------------------------------------------------------------- epilogue arithmetic
 // The accumulator bits are 0xCA800000 | d^2.  key = bits * 256 + tag (one IMAD, FMA pipe) is
-// 0x80000000 | d^2 << 8 | tag with tag = index of the 32-column chunk inside the split (< 256), so
+// 0x80000000 | d^2 << 8 | tag with tag = index of the 16-column chunk inside the split (< 256), so
 // unsigned order on keys is (d^2, chunk) order.  Per query row (= per thread) the epilogue keeps
-//   acc[j], j = column mod 32 : the minimum key of every residue class ("vertical" minima), and
+//   acc[j], j = column mod 16 : the minimum key of every residue class ("vertical" minima), and
 //   (h1, h2)                  : the two smallest per-chunk minima ("horizontal" minima).
-// That is ONE integer min/max-pipe operation per element (two 3-input minima per two elements) instead
-// of the three a running top-2 needs, and it still determines the exact top-2 of the row: the best
-// element e1 is the smallest (acc[j], j); the runner-up e2 is either in another class than e1 — then it
-// is the minimum of its class and shows up as the second smallest (acc[j], j) — or in e1's class j1 —
-// then it is in another chunk, is the minimum of that chunk, and h2 is its key (column = chunk*32+j1).
+// That is ~ONE integer min/max-pipe operation per element (3-input minima) instead of the three a
+// running top-2 needs, and it still determines the exact top-2 of the row: the best element e1 is
+// the smallest (acc[j], j); the runner-up e2 is either in another class than e1 — then it is the
+// minimum of its class and shows up as the second smallest (acc[j], j) — or in e1's class j1 — then
+// it is in another chunk, is the minimum of that chunk, and h2 is its key (column = chunk*16 + j1).
 // Columns inside one chunk have distinct classes, so no pair of elements can hide in both views.
 __device__ __forceinline__ uint32_t umin3(uint32_t a, uint32_t b, uint32_t c) { return min(min(a, b), c); }
 
-__device__ __forceinline__ uint32_t chunk_min(const uint32_t (&k)[32]) {
-  uint32_t m[11];
-#pragma unroll
-  for (int i = 0; i < 10; ++i) m[i] = umin3(k[3 * i], k[3 * i + 1], k[3 * i + 2]);
-  m[10] = min(k[30], k[31]);
-  const uint32_t a = umin3(m[0], m[1], m[2]), b = umin3(m[3], m[4], m[5]), c = umin3(m[6], m[7], m[8]);
-  return umin3(umin3(a, b, c), m[9], m[10]);
+__device__ __forceinline__ uint32_t chunk_min16(const uint32_t* k) {
+  const uint32_t a = umin3(k[0], k[1], k[2]), b = umin3(k[3], k[4], k[5]), c = umin3(k[6], k[7], k[8]);
+  const uint32_t d = umin3(k[9], k[10], k[11]), e = umin3(k[12], k[13], k[14]);
+  return umin3(umin3(a, b, c), umin3(d, e, k[15]), 0xFFFFFFFFu);
 }
 
-// Two 32-column chunks (raw accumulator bits in a, b) folded into the row state.
-__device__ __forceinline__ void fold_pair(uint32_t (&a)[32], uint32_t (&b)[32], uint32_t mul256, uint32_t tag_a,
-                                          uint32_t (&acc)[32], uint32_t& h1, uint32_t& h2) {
-  const uint32_t tag_b = tag_a + 1u;
+struct RowState {
+  uint32_t acc[tc::CHUNK];
+  uint32_t h1, h2;
+  __device__ __forceinline__ void reset() {
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    a[j] = a[j] * mul256 + tag_a;
-    b[j] = b[j] * mul256 + tag_b;
+    for (int j = 0; j < tc::CHUNK; ++j) acc[j] = 0xFFFFFFFFu;
+    h1 = h2 = 0xFFFFFFFFu;
+  }
+};
+
+// 32 columns (raw accumulator bits, two 16-column chunks tagged tag and tag+1) folded into the row state.
+__device__ __forceinline__ void fold32(uint32_t (&r)[32], uint32_t mul256, uint32_t tag, RowState& st) {
+  const uint32_t tag_b = tag + 1u;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    r[j] = r[j] * mul256 + tag;
+    r[16 + j] = r[16 + j] * mul256 + tag_b;
   }
 #pragma unroll
-  for (int j = 0; j < 32; ++j) acc[j] = umin3(acc[j], a[j], b[j]);
-  const uint32_t ha = chunk_min(a), hb = chunk_min(b);     // ha != hb (different tags)
+  for (int j = 0; j < 16; ++j) st.acc[j] = umin3(st.acc[j], r[j], r[16 + j]);
+  const uint32_t ha = chunk_min16(r), hb = chunk_min16(r + 16);     // ha != hb (different tags)
   const uint32_t lo = min(ha, hb), hi = max(ha, hb);
-  h2 = umin3(max(h1, lo), h2, hi);
-  h1 = min(h1, lo);
+  st.h2 = umin3(max(st.h1, lo), st.h2, hi);
+  st.h1 = min(st.h1, lo);
+}
+
+// Row state -> the sub-split's three candidate keys.  (key, class) order == (d^2, column) order.
+__device__ __forceinline__ void emit_candidates(const RowState& st, int col_base, mkey_t* out) {
+  uint32_t b1 = 0xFFFFFFFFu, b2 = 0xFFFFFFFFu;
+  int j1 = 0, j2 = 0;
+#pragma unroll
+  for (int j = 0; j < tc::CHUNK; ++j) {
+    const uint32_t k = st.acc[j];
+    if (k < b1) { b2 = b1; j2 = j1; b1 = k; j1 = j; }
+    else if (k < b2) { b2 = k; j2 = j; }
+  }
+  auto key_d2 = [](uint32_t k) { return (k >> 8) & 0x7FFFFFu; };
+  auto key_col = [&](uint32_t k, int j) { return col_base + (int)(k & 0xFFu) * tc::CHUNK + j; };
+  mkey_t o1 = MKEY_INF, o2 = MKEY_INF, o3 = MKEY_INF;
+  if (key_d2(b1) <= 2u * tc::MAX_SQNORM) o1 = make_key((float)key_d2(b1), key_col(b1, j1));
+  if (st.h2 < b2) {                      // runner-up hidden behind e1 in class j1: it is chunk h2's minimum
+    if (key_d2(st.h2) <= 2u * tc::MAX_SQNORM) o2 = make_key((float)key_d2(st.h2), key_col(st.h2, j1));
+  } else if (key_d2(b2) <= 2u * tc::MAX_SQNORM) {
+    o2 = make_key((float)key_d2(b2), key_col(b2, j2));
+    // same d^2 in the same chunk: the chunk may also hold an equal element in class j1 (hidden behind
+    // e1); if j1 < j2 it would precede o2.  K1c checks that column when it matters.
+    if (st.h2 == b2 && j1 < j2) o3 = make_key((float)key_d2(b2), key_col(b2, j1));
+  }
+  out[0] = o1;
+  out[1] = o2;
+  out[2] = o3;
+}
+
+// ---------------------------------------------------------------------------- cluster helpers
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(bar), "r"(rank) : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {   // arrives on `bar` in BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 
 // ============================================================================ K1 kernel
-template <bool DUMP>
-__global__ void __launch_bounds__(tc::NTHREADS, 1) match_tc_kernel(TcParams p) {
+// QT = query tiles per CTA and item (the pair holds 2*QT tiles = 256*QT query rows per train stage).
+template <int QT, bool DUMP>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(tc::NTHREADS, 1) match_tc_kernel(TcParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();          // 0 = leader (issues the MMAs)
+  const int pair = blockIdx.x >> 1;
+  const int n_pairs = gridDim.x >> 1;
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bar0 = sbase + tc::SMEM_BAR;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + tc::SMEM_BAR + tc::NBAR * 8);
   auto bar = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+  auto s_begin_of = [&](int split) { return (int)(((long long)split * p.n_stages) / p.nsplit); };
 
   if (threadIdx.x == 0) {
-    mbar_init(bar(tc::A_FULL), 1);
-    mbar_init(bar(tc::A_EMPTY), 1);
-    for (int s = 0; s < tc::NSTAGE; ++s) {
-      mbar_init(bar(tc::B_FULL + s), 1);
-      mbar_init(bar(tc::B_EMPTY + s), 1);
-    }
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(bar(tc::ACC_FULL + b), 1);
-      mbar_init(bar(tc::ACC_EMPTY + b), 8);
-    }
+    for (int i = 0; i < tc::NBAR; ++i) mbar_init(bar(i), i >= tc::ACC_EMPTY ? 16u : 1u);   // ACC_EMPTY: 8 warps x 2 CTAs
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {   // TMEM: all 512 columns = two buffers of (2 query tiles x 128 columns)
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  if (warp == 1) {   // TMEM: all 512 columns = two accumulator slots of 256 columns, allocated for the pair
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();        // the peer's barriers are initialised before anything can arrive on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ producer
+    // ------------------------------------------------------------------ B producer (this CTA's half of every stage)
     if (lane == 0) {
-      uint32_t a_phase = 0, b_phase[tc::NSTAGE] = {0, 0, 0};
-      int slot = 0;
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-        const int qp = item / p.nsplit, split = item % p.nsplit;
-        const int s_begin = split * p.stages_per_split;
-        const int s_end = min(p.n_stages, s_begin + p.stages_per_split);
-        const int nqt = min(tc::QT_PER_ITEM, p.n_qtiles - qp * tc::QT_PER_ITEM);
-        mbar_wait(bar(tc::A_EMPTY), a_phase ^ 1);
-        mbar_expect_tx(bar(tc::A_FULL), (uint32_t)nqt * tc::TILE_BYTES);
-        bulk_g2s(sbase + tc::SMEM_A, p.q_tiles + (size_t)qp * tc::QT_PER_ITEM * tc::TILE_BYTES,
-                 (uint32_t)nqt * tc::TILE_BYTES, bar(tc::A_FULL));
-        a_phase ^= 1;
-        for (int s = s_begin; s < s_end; ++s) {
-          mbar_wait(bar(tc::B_EMPTY + slot), b_phase[slot] ^ 1);
-          mbar_expect_tx(bar(tc::B_FULL + slot), tc::STAGE_BYTES);
-          bulk_g2s(sbase + tc::SMEM_B + slot * tc::STAGE_BYTES, p.t_tiles + (size_t)s * tc::STAGE_BYTES,
-                   tc::STAGE_BYTES, bar(tc::B_FULL + slot));
-          b_phase[slot] ^= 1;
-          slot = (slot + 1 == tc::NSTAGE) ? 0 : slot + 1;
+      uint32_t seq = 0;
+      for (int item = pair; item < p.n_items; item += n_pairs) {
+        const int split = item % p.nsplit;
+        const int s_begin = s_begin_of(split), s_end = s_begin_of(split + 1);
+        for (int s = s_begin; s < s_end; ++s, ++seq) {
+          const int slot = (int)(seq % tc::NB);
+          const uint32_t ph = (seq / tc::NB) & 1u;
+          mbar_wait(bar(tc::B_EMPTY + slot), ph ^ 1u);
+          mbar_expect_tx(bar(tc::B_FULL + slot), tc::TILE_BYTES);
+          bulk_g2s(sbase + tc::SMEM_B + slot * tc::TILE_BYTES, p.t_tiles + (size_t)(2 * s + (int)rank) * tc::TILE_BYTES,
+                   tc::TILE_BYTES, bar(tc::B_FULL + slot));
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ------------------------------------------------------------------ A producer (this CTA's query tiles)
+    if (lane == 0) {
+      uint32_t seq = 0;
+      for (int item = pair; item < p.n_items; item += n_pairs) {
+        const int g = item / p.nsplit;
+        for (int t = 0; t < QT; ++t, ++seq) {
+          const int slot = (int)(seq & 1u);
+          const uint32_t ph = (seq >> 1) & 1u;
+          const int qt = min((g * QT + t) * 2 + (int)rank, p.n_qtiles_alloc - 1);
+          mbar_wait(bar(tc::A_EMPTY + slot), ph ^ 1u);
+          mbar_expect_tx(bar(tc::A_FULL + slot), tc::TILE_BYTES);
+          bulk_g2s(sbase + tc::SMEM_A + slot * tc::TILE_BYTES, p.q_tiles + (size_t)qt * tc::TILE_BYTES, tc::TILE_BYTES,
+                   bar(tc::A_FULL + slot));
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
+    // ------------------------------------------------------------------ MMA issuer (leader) / data-landed relay (peer)
     if (lane == 0) {
-      const uint32_t idesc = make_idesc(128, tc::STAGE_COLS);
-      uint32_t a_phase = 0, b_phase[tc::NSTAGE] = {0, 0, 0}, acc_phase[2] = {0, 0};
-      int slot = 0, buf = 0;
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-        const int qp = item / p.nsplit, split = item % p.nsplit;
-        const int s_begin = split * p.stages_per_split;
-        const int s_end = min(p.n_stages, s_begin + p.stages_per_split);
-        const int nqt = min(tc::QT_PER_ITEM, p.n_qtiles - qp * tc::QT_PER_ITEM);
-        mbar_wait(bar(tc::A_FULL), a_phase);
-        a_phase ^= 1;
-        for (int s = s_begin; s < s_end; ++s) {
-          mbar_wait(bar(tc::ACC_EMPTY + buf), acc_phase[buf] ^ 1);
-          mbar_wait(bar(tc::B_FULL + slot), b_phase[slot]);
-          b_phase[slot] ^= 1;
-          tc_fence_after();
-          const uint32_t b_addr = sbase + tc::SMEM_B + slot * tc::STAGE_BYTES;
-          for (int t = 0; t < ((p.debug & 2u) ? 0 : nqt); ++t) {
-            const uint32_t a_addr = sbase + tc::SMEM_A + t * tc::TILE_BYTES;
-            const uint32_t d_addr = tmem_base + (uint32_t)(buf * tc::ACC_COLS + t * tc::STAGE_COLS);
+      const uint32_t idesc = make_idesc(256, tc::STAGE_COLS);
+      uint32_t a_seq = 0, b_seq = 0, job = 0;
+      for (int item = pair; item < p.n_items; item += n_pairs) {
+        const int split = item % p.nsplit;
+        const int s_begin = s_begin_of(split), s_end = s_begin_of(split + 1);
+        for (int s = s_begin; s < s_end; ++s, ++b_seq) {
+          const int bslot = (int)(b_seq % tc::NB);
+          const uint32_t bph = (b_seq / tc::NB) & 1u;
+          mbar_wait(bar(tc::B_FULL + bslot), bph);
+          if (rank == 0) mbar_wait(bar(tc::B_PEER + bslot), bph);
+          else mbar_arrive_remote(bar(tc::B_PEER + bslot), 0);
+          const uint32_t b_addr = sbase + tc::SMEM_B + bslot * tc::TILE_BYTES;
+          for (int t = 0; t < QT; ++t, ++job) {
+            const int aslot = (int)((a_seq + t) & 1u);
+            const uint32_t aph = ((a_seq + t) >> 1) & 1u;
+            if (s == s_begin) {
+              mbar_wait(bar(tc::A_FULL + aslot), aph);
+              if (rank == 0) mbar_wait(bar(tc::A_PEER + aslot), aph);
+              else mbar_arrive_remote(bar(tc::A_PEER + aslot), 0);
+            }
+            if (rank != 0) continue;
+            const int cslot = (int)(job & 1u);
+            mbar_wait(bar(tc::ACC_EMPTY + cslot), ((job >> 1) & 1u) ^ 1u);
+            tc_fence_after();
+            if (!(p.debug & 2u)) {
+              const uint32_t a_addr = sbase + tc::SMEM_A + aslot * tc::TILE_BYTES;
+              const uint32_t d_addr = tmem_base + (uint32_t)(cslot * tc::STAGE_COLS);
 #pragma unroll
-            for (int k = 0; k < tc::KMAIN / 16; ++k)
-              tc_mma_bf16(d_addr, make_smem_desc(a_addr + k * 2 * tc::LBO), make_smem_desc(b_addr + k * 2 * tc::LBO),
-                          idesc, k > 0 ? 1u : 0u);
-            tc_mma_bf16(d_addr, make_smem_desc(a_addr + 16 * tc::LBO), make_smem_desc(b_addr + 18 * tc::LBO), idesc, 1u);
+              for (int k = 0; k < tc::KMAIN / 16; ++k)
+                tc_mma_bf16_pair(d_addr, make_smem_desc(a_addr + k * 2 * tc::LBO), make_smem_desc(b_addr + k * 2 * tc::LBO),
+                                 idesc, k > 0 ? 1u : 0u);
+              tc_mma_bf16_pair(d_addr, make_smem_desc(a_addr + 16 * tc::LBO), make_smem_desc(b_addr + 18 * tc::LBO), idesc, 1u);
+            }
+            tc_commit_pair(bar(tc::ACC_FULL + cslot));                     // accumulator complete (both CTAs)
+            if (s == s_end - 1) tc_commit_pair(bar(tc::A_EMPTY + aslot));    // query tile slot reusable
           }
-          tc_commit(bar(tc::B_EMPTY + slot));     // smem stage reusable once these MMAs retire
-          tc_commit(bar(tc::ACC_FULL + buf));     // accumulator pair complete
-          acc_phase[buf] ^= 1;
-          slot = (slot + 1 == tc::NSTAGE) ? 0 : slot + 1;
-          buf ^= 1;
+          if (rank == 0) tc_commit_pair(bar(tc::B_EMPTY + bslot));           // train tile slot reusable
         }
-        tc_commit(bar(tc::A_EMPTY));              // query tiles reusable
+        a_seq += QT;
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..9)
-    // Two warps per TMEM lane quarter (= per SM sub-partition): warps 2-5 reduce query tile 0 of the
-    // pair, warps 6-9 query tile 1; one query row per thread.
+    // ------------------------------------------------------------------ epilogue (warps 3..10)
+    // Two warps per TMEM lane quarter (= per SM sub-partition); warp set `half` takes columns
+    // half*128 .. half*128+127 of every accumulator, one query row per thread.
     const int quarter = warp & 3;                 // TMEM lane quarter this warp may read
     const int row = quarter * 32 + lane;          // query row within a tile
-    const int tq = (warp - 2) >> 2;               // which query tile of the pair this warp owns
-    uint32_t acc_phase[2] = {0, 0};
-    int buf = 0;
+    const int half = (warp - 3) >> 2;
     const uint32_t mul256 = p.key_mul;  // 256, opaque to the compiler: the key build stays an IMAD (FMA pipe),
                                         // leaving the integer min/max pipe to the minima
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-      const int qp = item / p.nsplit, split = item % p.nsplit;
-      const int s_begin = split * p.stages_per_split;
-      const int s_end = min(p.n_stages, s_begin + p.stages_per_split);
-      const int nqt = min(tc::QT_PER_ITEM, p.n_qtiles - qp * tc::QT_PER_ITEM);
-      const bool active = tq < nqt;
-      uint32_t acc[32];
+    uint32_t job = 0;
+    for (int item = pair; item < p.n_items; item += n_pairs) {
+      const int g = item / p.nsplit, split = item % p.nsplit;
+      const int s_begin = s_begin_of(split), s_end = s_begin_of(split + 1);
+      RowState st[QT];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) acc[j] = 0xFFFFFFFFu;
-      uint32_t h1 = 0xFFFFFFFFu, h2 = 0xFFFFFFFFu;
+      for (int t = 0; t < QT; ++t) st[t].reset();
       for (int s = s_begin; s < s_end; ++s) {
-        mbar_wait(bar(tc::ACC_FULL + buf), acc_phase[buf]);
-        acc_phase[buf] ^= 1;
-        tc_fence_after();
-        const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * tc::ACC_COLS + tq * tc::STAGE_COLS);
-        const uint32_t tag0 = (uint32_t)(s - s_begin) * (tc::STAGE_COLS / 32);
-        if (active && !(p.debug & 4u)) {
-          uint32_t ra[32], rb[32], rc[32];
-          tmem_ld32(t_addr, ra);
-          tmem_ld32(t_addr + 32, rb);
-          tmem_ld_wait_regs(ra);
-          tmem_ld_wait_regs(rb);
-          tmem_ld32(t_addr + 64, rc);             // third chunk in flight while the first two are folded
-          if (DUMP) {
-            float* drow = p.dump + ((size_t)((qp * tc::QT_PER_ITEM + tq) * 128 + row) * p.n_stages + s) * tc::STAGE_COLS;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) { drow[j] = __uint_as_float(ra[j]); drow[32 + j] = __uint_as_float(rb[j]); }
-          }
-          if (p.debug & 1u) h1 = min(h1, ra[0] ^ rb[31]);
-          else fold_pair(ra, rb, mul256, tag0, acc, h1, h2);
-          tmem_ld32(t_addr + 96, ra);
-          tmem_ld_wait_regs(rc);
-          tmem_ld_wait_regs(ra);
-          // every column of this accumulator is in registers: hand the TMEM buffer back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar(tc::ACC_EMPTY + buf));
-          if (DUMP) {
-            float* drow = p.dump + ((size_t)((qp * tc::QT_PER_ITEM + tq) * 128 + row) * p.n_stages + s) * tc::STAGE_COLS + 64;
+        for (int t = 0; t < QT; ++t, ++job) {
+          const int cslot = (int)(job & 1u);
+          mbar_wait(bar(tc::ACC_FULL + cslot), (job >> 1) & 1u);
+          tc_fence_after();
+          const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(cslot * tc::STAGE_COLS + half * 128);
+          const uint32_t tag0 = (uint32_t)((s - s_begin) * (tc::STAGE_COLS / tc::CHUNK) + half * (128 / tc::CHUNK));
+          if (!(p.debug & 4u)) {
+            uint32_t ra[32], rb[32];
+            float* drow = nullptr;
+            if (DUMP) {
+              const int qt = (g * QT + t) * 2 + (int)rank;
+              drow = p.dump + (size_t)(qt * 128 + row) * p.dump_cols + s * tc::STAGE_COLS + half * 128;
+              if (qt >= p.n_qtiles) drow = nullptr;
+            }
+            auto dump32 = [&](const uint32_t (&r)[32], int c) {
+              if (DUMP && drow && s * tc::STAGE_COLS + half * 128 + c * 32 < p.dump_cols) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) { drow[j] = __uint_as_float(rc[j]); drow[32 + j] = __uint_as_float(ra[j]); }
+                for (int j = 0; j < 32; ++j) drow[c * 32 + j] = __uint_as_float(r[j]);
+              }
+            };
+            tmem_ld32(t_addr, ra);
+            tmem_ld_wait_regs(ra);
+            tmem_ld32(t_addr + 32, rb);           // next 32 columns in flight while these are folded
+            dump32(ra, 0);
+            if (p.debug & 1u) st[t].h1 = min(st[t].h1, ra[0] ^ ra[31]); else fold32(ra, mul256, tag0, st[t]);
+            tmem_ld_wait_regs(rb);
+            tmem_ld32(t_addr + 64, ra);
+            dump32(rb, 1);
+            if (p.debug & 1u) st[t].h1 = min(st[t].h1, rb[0] ^ rb[31]); else fold32(rb, mul256, tag0 + 2u, st[t]);
+            tmem_ld_wait_regs(ra);
+            tmem_ld32(t_addr + 96, rb);
+            dump32(ra, 2);
+            if (p.debug & 1u) st[t].h1 = min(st[t].h1, ra[0] ^ ra[31]); else fold32(ra, mul256, tag0 + 4u, st[t]);
+            tmem_ld_wait_regs(rb);
+            // every column of this warp's share is in registers: hand the TMEM slot back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote(bar(tc::ACC_EMPTY + cslot), 0);
+            dump32(rb, 3);
+            if (p.debug & 1u) st[t].h1 = min(st[t].h1, rb[0] ^ rb[31]); else fold32(rb, mul256, tag0 + 6u, st[t]);
+          } else {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote(bar(tc::ACC_EMPTY + cslot), 0);
           }
-          if (p.debug & 1u) h1 = min(h1, rc[0] ^ ra[31]);
-          else fold_pair(rc, ra, mul256, tag0 + 2u, acc, h1, h2);
-        } else {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar(tc::ACC_EMPTY + buf));
         }
-        buf ^= 1;
       }
-      if (active) {
-        // row state -> the split's candidates.  (key, class) order == (d^2, column) order.
-        uint32_t b1 = 0xFFFFFFFFu, b2 = 0xFFFFFFFFu;
-        int j1 = 0, j2 = 0;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const uint32_t k = acc[j];
-          if (k < b1) { b2 = b1; j2 = j1; b1 = k; j1 = j; }
-          else if (k < b2) { b2 = k; j2 = j; }
-        }
-        const int col_base = s_begin * tc::STAGE_COLS;
-        auto key_d2 = [](uint32_t k) { return (k >> 8) & 0x7FFFFFu; };
-        auto key_col = [&](uint32_t k, int j) { return col_base + (int)(k & 0xFFu) * 32 + j; };
-        mkey_t o1 = MKEY_INF, o2 = MKEY_INF, o3 = MKEY_INF;
-        if (key_d2(b1) <= 2u * tc::MAX_SQNORM) o1 = make_key((float)key_d2(b1), key_col(b1, j1));
-        if (h2 < b2) {                       // runner-up hidden behind e1 in class j1: it is chunk h2's minimum
-          if (key_d2(h2) <= 2u * tc::MAX_SQNORM) o2 = make_key((float)key_d2(h2), key_col(h2, j1));
-        } else {
-          if (key_d2(b2) <= 2u * tc::MAX_SQNORM) {
-            o2 = make_key((float)key_d2(b2), key_col(b2, j2));
-            // same d^2 in the same chunk: the chunk may also hold an equal element in class j1 (hidden behind
-            // e1); if j1 < j2 it would precede o2.  K1c checks that column when it matters.
-            if (h2 == b2 && j1 < j2) o3 = make_key((float)key_d2(b2), key_col(b2, j1));
-          }
-        }
-        mkey_t* out = p.cand + ((size_t)((qp * tc::QT_PER_ITEM + tq) * 128 + row) * p.nsplit + split) * 3;
-        out[0] = o1;
-        out[1] = o2;
-        out[2] = o3;
+      for (int t = 0; t < QT; ++t) {
+        const int qt = (g * QT + t) * 2 + (int)rank;
+        if (qt < p.n_qtiles)
+          emit_candidates(st[t], s_begin * tc::STAGE_COLS,
+                          p.cand + ((size_t)(qt * 128 + row) * (2 * p.nsplit) + 2 * split + half) * 3);
       }
     }
   }
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();          // both CTAs are done with the pair's TMEM and with each other's barriers
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 
-int sfm_match_tc_splits(sfm_ctx* ctx, int nq, int nt) {
-  int qpairs = div_up(div_up(nq, tc::TILE_ROWS), tc::QT_PER_ITEM);
-  int stages = div_up(nt, tc::TILE_ROWS);
-  int s = ctx->sm_count / (qpairs > 0 ? qpairs : 1);
-  int s_min = div_up(stages, 256 / (tc::STAGE_COLS / 32));   // chunk tags are 8 bits: <= 256 chunks per split
-  if (s < s_min) s = s_min;
-  if (s < 1) s = 1;
-  if (s > stages) s = stages;
-  return s < 1 ? 1 : s;
+// ---------------------------------------------------------------------------- launch plan
+// items = query groups x train splits, dealt round-robin to the CTA pairs.  The split count balances
+// (a) whole waves over the pairs, (b) per-item ramp (query tile load) against item length, (c) the
+// 8-bit chunk tag (<= 16 stages per split).
+struct TcPlan { int qt, nsplit, n_groups, n_stages, n_items, n_pairs; };
+
+static TcPlan tc_plan(sfm_ctx* ctx, int nq, int nt) {
+  TcPlan pl;
+  const int n_qtiles = div_up(nq, tc::TILE_ROWS);
+  pl.n_stages = div_up(div_up(nt, tc::TILE_ROWS), 2);
+  const int pairs = ctx->sm_count / 2 > 0 ? ctx->sm_count / 2 : 1;
+  const char* e = getenv("SFM_MATCH_QT");
+  int best_qt = 1, best_split = 1;
+  double best = -1.0;
+  for (int qt = 1; qt <= 2; ++qt) {
+    if (e && atoi(e) != qt) continue;
+    const int groups = div_up(n_qtiles, 2 * qt);
+    const int smin = div_up(pl.n_stages, tc::MAX_STAGES_PER_SPLIT);
+    for (int ns = smin; ns <= pl.n_stages && ns <= smin + 4 * pairs; ++ns) {
+      const int items = groups * ns;
+      const int waves = div_up(items, pairs);
+      const double jobs = (double)div_up(pl.n_stages, ns) * qt;          // jobs of the longest item
+      // time ~ waves * (jobs + ramp); useful work = n_qtiles/2 * n_stages job-equivalents per pair-wave slot
+      const double ramp = 1.5;
+      const double t = waves * (jobs + ramp) + 0.02 * ns;                // slight preference for fewer splits
+      const double score = -t * (qt == 2 ? 1.0 : 1.04);                  // QT=2 halves L2 traffic per job
+      if (best < 0.0 || score > -best) { best = -score; best_qt = qt; best_split = ns; }
+    }
+  }
+  const char* es = getenv("SFM_MATCH_NSPLIT");
+  if (es && atoi(es) >= div_up(pl.n_stages, tc::MAX_STAGES_PER_SPLIT) && atoi(es) <= pl.n_stages) best_split = atoi(es);
+  pl.qt = best_qt;
+  pl.nsplit = best_split;
+  pl.n_groups = div_up(n_qtiles, 2 * best_qt);
+  pl.n_items = pl.n_groups * pl.nsplit;
+  pl.n_pairs = pl.n_items < pairs ? pl.n_items : pairs;
+  return pl;
 }
 
-static int launch_tc(sfm_ctx* ctx, const sfm_desc* q, const sfm_desc* t, mkey_t* cand, int nsplit, float* dump) {
-  SFM_REQUIRE(q->tiles && t->tiles, "tensor-core matcher: descriptors have no tile image");
+// number of candidate sub-splits per query row (K1c merges them)
+int sfm_match_tc_splits(sfm_ctx* ctx, int nq, int nt) { return 2 * tc_plan(ctx, nq, nt).nsplit; }
+
+template <int QT, bool DUMP>
+static int launch_tc_t(sfm_ctx* ctx, const TcParams& p, int n_pairs) {
   static bool attr_set = false;
   if (!attr_set) {
-    SFM_CUDA(cudaFuncSetAttribute(match_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
-    SFM_CUDA(cudaFuncSetAttribute(match_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+    SFM_CUDA(cudaFuncSetAttribute(match_tc_kernel<QT, DUMP>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
     attr_set = true;
   }
+  SFM_LAUNCH(ctx, SFM_K_MATCH_TC, (match_tc_kernel<QT, DUMP><<<2 * n_pairs, tc::NTHREADS, tc::SMEM_BYTES, ctx->stream>>>(p)));
+  return SFM_OK;
+}
+
+static int launch_tc(sfm_ctx* ctx, const sfm_desc* q, const sfm_desc* t, mkey_t* cand, int nsub, float* dump, int dump_cols) {
+  SFM_REQUIRE(q->tiles && t->tiles, "tensor-core matcher: descriptors have no tile image");
+  TcPlan pl = tc_plan(ctx, q->n, t->n);
+  SFM_REQUIRE(nsub == 2 * pl.nsplit, "tensor-core matcher: candidate buffer was sized for another plan");
   TcParams p;
   p.q_tiles = (const unsigned char*)q->tiles;
   p.t_tiles = (const unsigned char*)t->tiles;
   p.n_qtiles = q->n_tiles;
-  p.n_qpairs = div_up(q->n_tiles, tc::QT_PER_ITEM);
-  p.n_stages = t->n_tiles;
-  p.nt = t->n;
-  p.nsplit = nsplit;
-  p.stages_per_split = div_up(p.n_stages, nsplit);
-  p.n_items = p.n_qpairs * nsplit;
+  p.n_qtiles_alloc = (q->n_tiles + 1) & ~1;
+  p.n_stages = pl.n_stages;
+  p.n_groups = pl.n_groups;
+  p.nsplit = pl.nsplit;
+  p.n_items = pl.n_items;
   p.cand = cand;
   p.dump = dump;
+  p.dump_cols = dump_cols;
   p.key_mul = 256u;
   { const char* e = getenv("SFM_MATCH_DEBUG"); p.debug = e ? (unsigned)atoi(e) : 0u; }
-  int grid = p.n_items < ctx->sm_count ? p.n_items : ctx->sm_count;
-  if (dump) SFM_LAUNCH(ctx, SFM_K_MATCH_TC, (match_tc_kernel<true><<<grid, tc::NTHREADS, tc::SMEM_BYTES, ctx->stream>>>(p)));
-  else SFM_LAUNCH(ctx, SFM_K_MATCH_TC, (match_tc_kernel<false><<<grid, tc::NTHREADS, tc::SMEM_BYTES, ctx->stream>>>(p)));
-  return SFM_OK;
+  if (dump) return pl.qt == 2 ? launch_tc_t<2, true>(ctx, p, pl.n_pairs) : launch_tc_t<1, true>(ctx, p, pl.n_pairs);
+  return pl.qt == 2 ? launch_tc_t<2, false>(ctx, p, pl.n_pairs) : launch_tc_t<1, false>(ctx, p, pl.n_pairs);
 }
 
-int sfm_match_tc_launch(sfm_ctx* ctx, const sfm_desc* q, const sfm_desc* t, mkey_t* cand, int nsplit) {
-  return launch_tc(ctx, q, t, cand, nsplit, nullptr);
+int sfm_match_tc_launch(sfm_ctx* ctx, const sfm_desc* q, const sfm_desc* t, mkey_t* cand, int nsub) {
+  return launch_tc(ctx, q, t, cand, nsub, nullptr, 0);
 }
 
 // Debug/self-test entry (not part of the reference-facing surface): raw accumulators of every
@@ -525,14 +623,15 @@ extern "C" int sfm_debug_match_tc_dump(sfm_ctx* ctx, const sfm_desc* q, const sf
   SFM_TRY(sfm_desc_resolve(const_cast<sfm_desc*>(q)));
   SFM_TRY(sfm_desc_resolve(const_cast<sfm_desc*>(t)));
   SFM_TRY(sfm_ws_begin(ctx));
-  int nsplit = 1;
-  size_t count = (size_t)q->n_tiles * 128 * t->n_tiles * tc::STAGE_COLS;
+  const int nsub = sfm_match_tc_splits(ctx, q->n, t->n);
+  const int dump_cols = t->n_tiles * 128;
+  size_t count = (size_t)q->n_tiles * 128 * dump_cols;
   SFM_REQUIRE((int64_t)count <= capacity, "dump buffer too small: need %zu floats", count);
   mkey_t* cand;
   float* dump;
-  SFM_TRY(ws_alloc_t(ctx, (size_t)q->n_tiles * 128 * nsplit * 3, &cand));
+  SFM_TRY(ws_alloc_t(ctx, (size_t)q->n_tiles * 128 * nsub * 3, &cand));
   SFM_TRY(ws_alloc_t(ctx, count, &dump));
-  SFM_TRY(launch_tc(ctx, q, t, cand, nsplit, dump));
+  SFM_TRY(launch_tc(ctx, q, t, cand, nsub, dump, dump_cols));
   SFM_CUDA(cudaMemcpyAsync(dump_host, dump, count * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
   SFM_CUDA(cudaStreamSynchronize(ctx->stream));
   return SFM_OK;
