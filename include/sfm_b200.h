@@ -99,9 +99,13 @@ int sfm_knn2_l2_ratio(sfm_ctx* ctx, const float* q, int nq, const float* t, int 
                       int mode);
 
 /* Diagnostic (used by the tests only): raw tensor-core accumulators -(2^22 + d^2/2) of every
- * (query row, train column), float32 [n_qtiles*128][n_stages*256], to a host buffer. */
+ * (query row, train column), float32 [n_qtiles*128][n_ttiles*128], to a host buffer. */
 int sfm_debug_match_tc_dump(sfm_ctx* ctx, const sfm_desc* q, const sfm_desc* t, float* dump_host,
                             int64_t capacity);
+/* Diagnostic (tools/match_timeline.py): clock64 stamps of the jobs of CTA pair 0 of one K1 launch,
+ * 8 per job (see match_tc.cu); info = {qt, nsplit, n_items, n_pairs, jobs of pair 0}. */
+int sfm_debug_match_tc_timeline(sfm_ctx* ctx, const sfm_desc* q, const sfm_desc* t, long long* stamps_host,
+                                int max_jobs, int* info);
 
 /* Resident form: prepare a view's descriptors once (K1b), match many times.
  * dtype 0 = float32, 1 = uint8. */

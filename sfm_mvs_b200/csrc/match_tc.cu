@@ -42,7 +42,9 @@
 //                         two warps per quarter, each taking 128 of the 256 columns)
 // A job = (query tile t of the item, train stage s); its accumulator (128 lanes x 256 columns per
 // CTA) lives in TMEM slot job&1, so the epilogue of job j overlaps the MMAs of job j+1.
-// A work item is (query group, train split); per-(split, column half) candidates are merged by K1c.
+// A work item is (query group, train split), numbered split-major so that the pairs running at the
+// same time stream the SAME train tiles (L2 serves one line to many SMs much faster than many lines);
+// per-(split, column half) candidates are merged by K1c.
 #include <cuda_bf16.h>
 #include <stdlib.h>
 
@@ -238,6 +240,7 @@ struct TcParams {
   mkey_t* cand;                   // [n_qtiles*128][2*nsplit][3]: best, runner-up, "check this column" (K1c)
   float* dump;                    // debug: raw accumulators [n_qtiles*128][dump_cols] or NULL
   int dump_cols;
+  long long* timeline;            // debug (MODE 2): per job of pair 0, 8 clock64 stamps taken on the leader SM
   unsigned int key_mul;           // = 256, passed at run time so the key build stays an IMAD (FMA pipe)
   unsigned int debug;             // diagnostics (env SFM_MATCH_DEBUG): bit0 skip epilogue math, bit1 skip MMAs, bit2 skip TMEM loads
 };
@@ -325,12 +328,16 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster
+// Arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster.  Default
+// (.release.cta) semantics on purpose: what the barriers order here travels through the async proxy
+// (TMA writes, tcgen05 reads of TMEM/smem) and is already complete when the arrive is issued
+// (mbarrier complete_tx / tcgen05.wait::ld); `.release.cluster` would put a MEMBAR.ALL.GPU
+// (~1000 cycles, measured) in front of every arrive.
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) {
   asm volatile(
       "{\n\t.reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
       ::"r"(bar), "r"(rank) : "memory");
 }
 __device__ __forceinline__ void tc_commit_pair(uint32_t bar) {   // arrives on `bar` in BOTH CTAs of the pair
@@ -348,7 +355,7 @@ __device__ __forceinline__ void tc_mma_bf16_pair(uint32_t tmem_d, uint64_t adesc
 
 // ============================================================================ K1 kernel
 // QT = query tiles per CTA and item (the pair holds 2*QT tiles = 256*QT query rows per train stage).
-template <int QT, bool DUMP>
+template <int QT, int MODE>   // MODE 0: product, 1: dump raw accumulators, 2: record a timeline
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(tc::NTHREADS, 1) match_tc_kernel(TcParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int warp = threadIdx.x >> 5;
@@ -375,13 +382,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(tc::NTHREADS, 1) mat
   cluster_sync_all();        // the peer's barriers are initialised before anything can arrive on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  constexpr bool DUMP = MODE == 1;
+  const bool stamp = MODE == 2 && pair == 0 && rank == 0;
+  auto tick = [&](uint32_t job, int k) { if (MODE == 2 && stamp) p.timeline[(size_t)job * 8 + k] = clock64(); };
 
   if (warp == 0) {
     // ------------------------------------------------------------------ B producer (this CTA's half of every stage)
     if (lane == 0) {
       uint32_t seq = 0;
       for (int item = pair; item < p.n_items; item += n_pairs) {
-        const int split = item % p.nsplit;
+        const int split = item / p.n_groups;
         const int s_begin = s_begin_of(split), s_end = s_begin_of(split + 1);
         for (int s = s_begin; s < s_end; ++s, ++seq) {
           const int slot = (int)(seq % tc::NB);
@@ -398,7 +408,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(tc::NTHREADS, 1) mat
     if (lane == 0) {
       uint32_t seq = 0;
       for (int item = pair; item < p.n_items; item += n_pairs) {
-        const int g = item / p.nsplit;
+        const int g = item % p.n_groups;
         for (int t = 0; t < QT; ++t, ++seq) {
           const int slot = (int)(seq & 1u);
           const uint32_t ph = (seq >> 1) & 1u;
@@ -416,14 +426,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(tc::NTHREADS, 1) mat
       const uint32_t idesc = make_idesc(256, tc::STAGE_COLS);
       uint32_t a_seq = 0, b_seq = 0, job = 0;
       for (int item = pair; item < p.n_items; item += n_pairs) {
-        const int split = item % p.nsplit;
+        const int split = item / p.n_groups;
         const int s_begin = s_begin_of(split), s_end = s_begin_of(split + 1);
         for (int s = s_begin; s < s_end; ++s, ++b_seq) {
           const int bslot = (int)(b_seq % tc::NB);
           const uint32_t bph = (b_seq / tc::NB) & 1u;
           mbar_wait(bar(tc::B_FULL + bslot), bph);
+          tick(job, 0);
           if (rank == 0) mbar_wait(bar(tc::B_PEER + bslot), bph);
           else mbar_arrive_remote(bar(tc::B_PEER + bslot), 0);
+          tick(job, 1);
           const uint32_t b_addr = sbase + tc::SMEM_B + bslot * tc::TILE_BYTES;
           for (int t = 0; t < QT; ++t, ++job) {
             const int aslot = (int)((a_seq + t) & 1u);
@@ -435,8 +447,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(tc::NTHREADS, 1) mat
             }
             if (rank != 0) continue;
             const int cslot = (int)(job & 1u);
+            tick(job, 2);
             mbar_wait(bar(tc::ACC_EMPTY + cslot), ((job >> 1) & 1u) ^ 1u);
             tc_fence_after();
+            tick(job, 3);
             if (!(p.debug & 2u)) {
               const uint32_t a_addr = sbase + tc::SMEM_A + aslot * tc::TILE_BYTES;
               const uint32_t d_addr = tmem_base + (uint32_t)(cslot * tc::STAGE_COLS);
@@ -447,6 +461,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(tc::NTHREADS, 1) mat
               tc_mma_bf16_pair(d_addr, make_smem_desc(a_addr + 16 * tc::LBO), make_smem_desc(b_addr + 18 * tc::LBO), idesc, 1u);
             }
             tc_commit_pair(bar(tc::ACC_FULL + cslot));                     // accumulator complete (both CTAs)
+            tick(job, 4);
             if (s == s_end - 1) tc_commit_pair(bar(tc::A_EMPTY + aslot));    // query tile slot reusable
           }
           if (rank == 0) tc_commit_pair(bar(tc::B_EMPTY + bslot));           // train tile slot reusable
@@ -465,7 +480,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(tc::NTHREADS, 1) mat
                                         // leaving the integer min/max pipe to the minima
     uint32_t job = 0;
     for (int item = pair; item < p.n_items; item += n_pairs) {
-      const int g = item / p.nsplit, split = item % p.nsplit;
+      const int g = item % p.n_groups, split = item / p.n_groups;
       const int s_begin = s_begin_of(split), s_end = s_begin_of(split + 1);
       RowState st[QT];
 #pragma unroll
@@ -476,6 +491,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(tc::NTHREADS, 1) mat
           const int cslot = (int)(job & 1u);
           mbar_wait(bar(tc::ACC_FULL + cslot), (job >> 1) & 1u);
           tc_fence_after();
+          if (warp == 3 && lane == 0) tick(job, 5);
           const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(cslot * tc::STAGE_COLS + half * 128);
           const uint32_t tag0 = (uint32_t)((s - s_begin) * (tc::STAGE_COLS / tc::CHUNK) + half * (128 / tc::CHUNK));
           if (!(p.debug & 4u)) {
@@ -510,8 +526,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(tc::NTHREADS, 1) mat
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_remote(bar(tc::ACC_EMPTY + cslot), 0);
+            if (warp == 3 && lane == 0) tick(job, 6);
             dump32(rb, 3);
             if (p.debug & 1u) st[t].h1 = min(st[t].h1, rb[0] ^ rb[31]); else fold32(rb, mul256, tag0 + 6u, st[t]);
+            if (warp == 3 && lane == 0) tick(job, 7);
           } else {
             tc_fence_before();
             __syncwarp();
@@ -578,18 +596,19 @@ static TcPlan tc_plan(sfm_ctx* ctx, int nq, int nt) {
 // number of candidate sub-splits per query row (K1c merges them)
 int sfm_match_tc_splits(sfm_ctx* ctx, int nq, int nt) { return 2 * tc_plan(ctx, nq, nt).nsplit; }
 
-template <int QT, bool DUMP>
+template <int QT, int MODE>
 static int launch_tc_t(sfm_ctx* ctx, const TcParams& p, int n_pairs) {
   static bool attr_set = false;
   if (!attr_set) {
-    SFM_CUDA(cudaFuncSetAttribute(match_tc_kernel<QT, DUMP>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+    SFM_CUDA(cudaFuncSetAttribute(match_tc_kernel<QT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
     attr_set = true;
   }
-  SFM_LAUNCH(ctx, SFM_K_MATCH_TC, (match_tc_kernel<QT, DUMP><<<2 * n_pairs, tc::NTHREADS, tc::SMEM_BYTES, ctx->stream>>>(p)));
+  SFM_LAUNCH(ctx, SFM_K_MATCH_TC, (match_tc_kernel<QT, MODE><<<2 * n_pairs, tc::NTHREADS, tc::SMEM_BYTES, ctx->stream>>>(p)));
   return SFM_OK;
 }
 
-static int launch_tc(sfm_ctx* ctx, const sfm_desc* q, const sfm_desc* t, mkey_t* cand, int nsub, float* dump, int dump_cols) {
+static int launch_tc(sfm_ctx* ctx, const sfm_desc* q, const sfm_desc* t, mkey_t* cand, int nsub, float* dump, int dump_cols,
+                     long long* timeline = nullptr) {
   SFM_REQUIRE(q->tiles && t->tiles, "tensor-core matcher: descriptors have no tile image");
   TcPlan pl = tc_plan(ctx, q->n, t->n);
   SFM_REQUIRE(nsub == 2 * pl.nsplit, "tensor-core matcher: candidate buffer was sized for another plan");
@@ -605,10 +624,12 @@ static int launch_tc(sfm_ctx* ctx, const sfm_desc* q, const sfm_desc* t, mkey_t*
   p.cand = cand;
   p.dump = dump;
   p.dump_cols = dump_cols;
+  p.timeline = timeline;
   p.key_mul = 256u;
   { const char* e = getenv("SFM_MATCH_DEBUG"); p.debug = e ? (unsigned)atoi(e) : 0u; }
-  if (dump) return pl.qt == 2 ? launch_tc_t<2, true>(ctx, p, pl.n_pairs) : launch_tc_t<1, true>(ctx, p, pl.n_pairs);
-  return pl.qt == 2 ? launch_tc_t<2, false>(ctx, p, pl.n_pairs) : launch_tc_t<1, false>(ctx, p, pl.n_pairs);
+  if (timeline) return pl.qt == 2 ? launch_tc_t<2, 2>(ctx, p, pl.n_pairs) : launch_tc_t<1, 2>(ctx, p, pl.n_pairs);
+  if (dump) return pl.qt == 2 ? launch_tc_t<2, 1>(ctx, p, pl.n_pairs) : launch_tc_t<1, 1>(ctx, p, pl.n_pairs);
+  return pl.qt == 2 ? launch_tc_t<2, 0>(ctx, p, pl.n_pairs) : launch_tc_t<1, 0>(ctx, p, pl.n_pairs);
 }
 
 int sfm_match_tc_launch(sfm_ctx* ctx, const sfm_desc* q, const sfm_desc* t, mkey_t* cand, int nsub) {
@@ -634,5 +655,33 @@ extern "C" int sfm_debug_match_tc_dump(sfm_ctx* ctx, const sfm_desc* q, const sf
   SFM_TRY(launch_tc(ctx, q, t, cand, nsub, dump, dump_cols));
   SFM_CUDA(cudaMemcpyAsync(dump_host, dump, count * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
   SFM_CUDA(cudaStreamSynchronize(ctx->stream));
+  return SFM_OK;
+}
+
+// Debug entry: clock64 stamps of the first `max_jobs` jobs of CTA pair 0 (leader SM), 8 per job:
+// MMA thread: 0 own train tile landed, 1 peer's landed, 2 ready to issue, 3 accumulator slot free, 4 MMAs issued;
+// epilogue warp 3: 5 accumulator complete, 6 TMEM slot released, 7 job folded.  Returns the job count of pair 0.
+extern "C" int sfm_debug_match_tc_timeline(sfm_ctx* ctx, const sfm_desc* q, const sfm_desc* t, long long* stamps_host,
+                                           int max_jobs, int* info /* qt, nsplit, n_items, n_pairs, jobs_pair0 */) {
+  SFM_REQUIRE(ctx && q && t && stamps_host && info, "sfm_debug_match_tc_timeline: null argument");
+  SFM_TRY(sfm_desc_resolve(const_cast<sfm_desc*>(q)));
+  SFM_TRY(sfm_desc_resolve(const_cast<sfm_desc*>(t)));
+  SFM_TRY(sfm_ws_begin(ctx));
+  TcPlan pl = tc_plan(ctx, q->n, t->n);
+  int jobs = 0;
+  for (int item = 0; item < pl.n_items; item += pl.n_pairs) {
+    const int split = item / pl.n_groups;
+    jobs += (int)(((long long)(split + 1) * pl.n_stages) / pl.nsplit - ((long long)split * pl.n_stages) / pl.nsplit) * pl.qt;
+  }
+  SFM_REQUIRE(jobs <= max_jobs, "timeline buffer too small: %d jobs", jobs);
+  mkey_t* cand;
+  long long* tl;
+  SFM_TRY(ws_alloc_t(ctx, (size_t)q->n_tiles * 128 * 2 * pl.nsplit * 3, &cand));
+  SFM_TRY(ws_alloc_t(ctx, (size_t)jobs * 8, &tl));
+  SFM_CUDA(cudaMemsetAsync(tl, 0, (size_t)jobs * 8 * sizeof(long long), ctx->stream));
+  SFM_TRY(launch_tc(ctx, q, t, cand, 2 * pl.nsplit, nullptr, 0, tl));
+  SFM_CUDA(cudaMemcpyAsync(stamps_host, tl, (size_t)jobs * 8 * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+  SFM_CUDA(cudaStreamSynchronize(ctx->stream));
+  info[0] = pl.qt; info[1] = pl.nsplit; info[2] = pl.n_items; info[3] = pl.n_pairs; info[4] = jobs;
   return SFM_OK;
 }
