@@ -398,6 +398,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(tc::NTHREADS, 1) mat
           const uint32_t ph = (seq / tc::NB) & 1u;
           mbar_wait(bar(tc::B_EMPTY + slot), ph ^ 1u);
           mbar_expect_tx(bar(tc::B_FULL + slot), tc::TILE_BYTES);
+          if (QT == 2) tick(2 * seq + 1, 0);      // timeline: when this stage's load was issued
           bulk_g2s(sbase + tc::SMEM_B + slot * tc::TILE_BYTES, p.t_tiles + (size_t)(2 * s + (int)rank) * tc::TILE_BYTES,
                    tc::TILE_BYTES, bar(tc::B_FULL + slot));
         }
@@ -627,6 +628,7 @@ static int launch_tc(sfm_ctx* ctx, const sfm_desc* q, const sfm_desc* t, mkey_t*
   p.timeline = timeline;
   p.key_mul = 256u;
   { const char* e = getenv("SFM_MATCH_DEBUG"); p.debug = e ? (unsigned)atoi(e) : 0u; }
+  if (p.debug & 16u) p.n_items = 0;     // diagnostics: launch + setup + teardown only
   if (timeline) return pl.qt == 2 ? launch_tc_t<2, 2>(ctx, p, pl.n_pairs) : launch_tc_t<1, 2>(ctx, p, pl.n_pairs);
   if (dump) return pl.qt == 2 ? launch_tc_t<2, 1>(ctx, p, pl.n_pairs) : launch_tc_t<1, 1>(ctx, p, pl.n_pairs);
   return pl.qt == 2 ? launch_tc_t<2, 0>(ctx, p, pl.n_pairs) : launch_tc_t<1, 0>(ctx, p, pl.n_pairs);

@@ -25,6 +25,9 @@ for j in range(min(jobs, show)):
     r = s[j] - t0
     print(f"{j:3d}  " + " ".join(f"{x:9.0f}" for x in r) +
           f" | {r[1]-r[0]:6.0f} {r[3]-r[2]:7.0f} {r[5]-r[4]:8.0f} {r[6]-r[5]:8.0f} {r[7]-r[6]:5.0f}")
+if qt == 2:
+    lat = [s[2 * k, 0] - s[2 * k + 1, 0] for k in range(jobs // 2) if s[2 * k + 1, 0] > 0]
+    print("train-tile load: issue -> landed (cycles):", " ".join(f"{x:.0f}" for x in lat[:24]))
 if jobs > 2:
     d = np.diff(s[:jobs, 4])
     print("issue-to-issue cycles: median %.0f mean %.0f min %.0f max %.0f; total %.0f cycles for %d jobs" %
