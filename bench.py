@@ -244,13 +244,15 @@ def run_engine(args):
     mt = prof.get("match_tc")
     roofline = None
     if mt:
-        flops = 2.0 * n * n * 128                                  # 2*Nq*Nt*128 per pair = per launch
+        # 2*Nq*Nt*128 flops per pair; one K1 launch covers the V-1 consecutive pairs of the scene
+        flops = 2.0 * n * n * 128 * (V - 1)
         t_launch = mt["ms"] * 1e-3 / mt["launches"]
         ach = flops / t_launch / 1e12
         roofline = {"kernel": "match_tc_kernel (K1 tcgen05 distance GEMM + top-2 epilogue)", "bound": "tensor",
                     "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": ach / pk["bf16_sustained"],
                     "traffic": None, "peak_source": pk["source"] + ", sustained bf16 (kernel timed inside a long step)",
-                    "algorithmic_flops_per_launch": flops, "avg_launch_us": 1e6 * t_launch, "launches": mt["launches"],
+                    "algorithmic_flops_per_launch": flops, "pairs_per_launch": V - 1, "avg_launch_us": 1e6 * t_launch,
+                    "launches": mt["launches"],
                     "share_of_kernel_time": shares.get("match_tc")}
 
     out = {

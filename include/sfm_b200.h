@@ -122,6 +122,15 @@ int sfm_desc_match_batched(sfm_ctx* ctx, int npairs, const sfm_desc* const* q,
                            const sfm_desc* const* t, double ratio, int32_t* const* idx,
                            float* const* dist, uint8_t* const* good, int32_t* n_good);
 
+/* The same plus the survivor gather of sfm.py:267-268 for every pair, three launches in total (K1 over
+ * the items of all pairs, K1c, gather).  All arrays are host arrays of per-pair DEVICE pointers;
+ * idx / good / qidx / tidx arrays (or single entries) may be NULL; n_out is a DEVICE array of npairs. */
+int sfm_desc_match_gather_batched(sfm_ctx* ctx, int npairs, const sfm_desc* const* q,
+                                  const sfm_desc* const* t, double ratio, const float* const* kp_q,
+                                  const float* const* kp_t, int32_t* const* idx, uint8_t* const* good,
+                                  float* const* pts_q, float* const* pts_t, int32_t* const* qidx,
+                                  int32_t* const* tidx, int32_t* n_out);
+
 /* sfm.py:267-268 — pts0 = kp0[m.queryIdx], pts1 = kp1[m.trainIdx] for the survivors, ascending
  * queryIdx.  kp_q (nq,2), kp_t (nt,2) float32; outputs (n_good,2) float32, capacity nq rows. */
 int sfm_match_gather(sfm_ctx* ctx, const int32_t* idx, const uint8_t* good, int nq,

@@ -16,13 +16,10 @@
 // distance IF it is real (match_tc.cu, epilogue comment); it is evaluated exactly (integer-valued
 // float32 arithmetic on the resident copies) only when it would enter the top-2.
 template <int STRIDE>
-__global__ void __launch_bounds__(256) match_finalize_kernel(const mkey_t* __restrict__ cand, int nq,
-                                                              int nt, int nsplit, double ratio,
-                                                              const float* __restrict__ qf, const float* __restrict__ tf,
-                                                              int* __restrict__ idx, float* __restrict__ dist,
-                                                              unsigned char* __restrict__ good,
-                                                              int* __restrict__ n_good) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void finalize_row(int i, const mkey_t* __restrict__ cand, int nq, int nt, int nsplit, double ratio,
+                                             const float* __restrict__ qf, const float* __restrict__ tf,
+                                             int* __restrict__ idx, float* __restrict__ dist,
+                                             unsigned char* __restrict__ good, int* __restrict__ n_good) {
   bool g = false;
   mkey_t k1 = MKEY_INF, k2 = MKEY_INF;
   if (i < nq) {
@@ -69,6 +66,31 @@ __global__ void __launch_bounds__(256) match_finalize_kernel(const mkey_t* __res
     unsigned m = __ballot_sync(0xffffffffu, g);
     if ((threadIdx.x & 31) == 0 && m) atomicAdd(n_good, __popc(m));
   }
+}
+
+template <int STRIDE>
+__global__ void __launch_bounds__(256) match_finalize_kernel(const mkey_t* __restrict__ cand, int nq,
+                                                              int nt, int nsplit, double ratio,
+                                                              const float* __restrict__ qf, const float* __restrict__ tf,
+                                                              int* __restrict__ idx, float* __restrict__ dist,
+                                                              unsigned char* __restrict__ good,
+                                                              int* __restrict__ n_good) {
+  finalize_row<STRIDE>(blockIdx.x * blockDim.x + threadIdx.x, cand, nq, nt, nsplit, ratio, qf, tf, idx, dist, good, n_good);
+}
+
+// Per-pair work record of the batched path (device array): K1c finalisation and survivor gather.
+struct PairWork {
+  const mkey_t* cand; const float* qf; const float* tf;
+  int nq, nt, nsub, pad_;
+  int* idx; float* dist; unsigned char* good; int* n_good;
+  const float2* kp_q; const float2* kp_t; float2* pts_q; float2* pts_t; int* qidx; int* tidx; int* n_out;
+};
+
+__global__ void __launch_bounds__(256) match_finalize_batched_kernel(const PairWork* __restrict__ work, double ratio) {
+  const PairWork w = work[blockIdx.y];
+  if ((int)(blockIdx.x * blockDim.x) >= w.nq) return;
+  finalize_row<3>(blockIdx.x * blockDim.x + threadIdx.x, w.cand, w.nq, w.nt, w.nsub, ratio, w.qf, w.tf, w.idx, w.dist, w.good,
+                  w.n_good);
 }
 
 int sfm_match_finalize(sfm_ctx* ctx, const mkey_t* cand, int nq, int nt, int nsplit, double ratio,
@@ -221,6 +243,10 @@ extern "C" int sfm_desc_is_exact(const sfm_desc* d) {
 }
 
 // ------------------------------------------------------------------ one pair
+static int match_pairs_batched(sfm_ctx* ctx, int npairs, const sfm_desc* const* q, const sfm_desc* const* t, double ratio,
+                               int32_t* const* idx, float* const* dist, uint8_t* const* good, int32_t* n_good_dev,
+                               const float* const* kp_q, const float* const* kp_t, float* const* pts_q, float* const* pts_t,
+                               int32_t* const* qidx, int32_t* const* tidx, int32_t* n_out_dev);
 static int match_pair(sfm_ctx* ctx, const sfm_desc* q, const sfm_desc* t, double ratio, int mode,
                       int32_t* idx, float* dist, uint8_t* good, int32_t* n_good) {
   SFM_REQUIRE(q->dim == t->dim, "knnMatch: descriptor dims differ (%d vs %d)", q->dim, t->dim);
@@ -281,22 +307,21 @@ extern "C" int sfm_desc_match_batched(sfm_ctx* ctx, int npairs, const sfm_desc* 
                                       int32_t* n_good) {
   SFM_REQUIRE(ctx && npairs >= 0 && (npairs == 0 || (q && t)), "sfm_desc_match_batched: null argument");
   SFM_TRY(sfm_ws_begin(ctx));
-  // All pairs are enqueued back to back on the ctx stream (each launch is itself persistent over the
-  // SMs); outputs are device pointers, so nothing synchronises until the caller does.
-  const bool ng_dev = n_good && sfm_is_device_ptr(n_good);
-  int32_t* ng_stage = nullptr;
-  if (n_good && !ng_dev && npairs) SFM_TRY(ws_alloc_t(ctx, (size_t)npairs, &ng_stage));
   for (int p = 0; p < npairs; ++p) {
-    SFM_REQUIRE(q[p] && t[p], "sfm_desc_match_batched: pair %d has a null descriptor set", p);
     int32_t* pi = idx ? idx[p] : nullptr;
     float* pd = dist ? dist[p] : nullptr;
     uint8_t* pg = good ? good[p] : nullptr;
     SFM_REQUIRE((!pi || sfm_is_device_ptr(pi)) && (!pd || sfm_is_device_ptr(pd)) && (!pg || sfm_is_device_ptr(pg)),
                 "sfm_desc_match_batched: per-pair outputs must be device pointers");
-    int32_t* png = n_good ? (ng_dev ? n_good + p : ng_stage + p) : nullptr;
-    SFM_TRY(match_pair(ctx, q[p], t[p], ratio, 0, pi, pd, pg, png));
   }
-  if (ng_stage) {
+  // ONE K1 launch over the items of all pairs + one K1c grid; outputs are device pointers, so nothing
+  // synchronises until the caller does (or until a host n_good is copied back).
+  const bool ng_dev = n_good && sfm_is_device_ptr(n_good);
+  int32_t* ng_stage = n_good;
+  if (n_good && !ng_dev && npairs) SFM_TRY(ws_alloc_t(ctx, (size_t)npairs, &ng_stage));
+  SFM_TRY(match_pairs_batched(ctx, npairs, q, t, ratio, idx, dist, good, ng_stage, nullptr, nullptr, nullptr, nullptr, nullptr,
+                              nullptr, nullptr));
+  if (n_good && !ng_dev && npairs) {
     SFM_CUDA(cudaMemcpyAsync(n_good, ng_stage, sizeof(int32_t) * npairs, cudaMemcpyDeviceToHost, ctx->stream));
     SFM_CUDA(cudaStreamSynchronize(ctx->stream));
   }
@@ -320,13 +345,10 @@ extern "C" int sfm_knn2_l2_ratio(sfm_ctx* ctx, const float* q, int nq, const flo
 
 // ------------------------------------------------------------------ survivor gather
 // Stable single-CTA compaction (ascending queryIdx, like the Python loop's append order).
-__global__ void __launch_bounds__(1024) match_gather_kernel(const int* __restrict__ idx,
-                                                             const unsigned char* __restrict__ good, int nq,
-                                                             const float2* __restrict__ kp_q,
-                                                             const float2* __restrict__ kp_t,
-                                                             float2* __restrict__ pts_q, float2* __restrict__ pts_t,
-                                                             int* __restrict__ qidx, int* __restrict__ tidx,
-                                                             int* __restrict__ n_out) {
+__device__ __forceinline__ void gather_cta(const int* __restrict__ idx, const unsigned char* __restrict__ good, int nq,
+                                           const float2* __restrict__ kp_q, const float2* __restrict__ kp_t,
+                                           float2* __restrict__ pts_q, float2* __restrict__ pts_t,
+                                           int* __restrict__ qidx, int* __restrict__ tidx, int* __restrict__ n_out) {
   __shared__ int warp_tot[32];
   __shared__ int base_s;
   if (threadIdx.x == 0) base_s = 0;
@@ -361,6 +383,21 @@ __global__ void __launch_bounds__(1024) match_gather_kernel(const int* __restric
   if (threadIdx.x == 0 && n_out) *n_out = base_s;
 }
 
+__global__ void __launch_bounds__(1024) match_gather_kernel(const int* __restrict__ idx,
+                                                             const unsigned char* __restrict__ good, int nq,
+                                                             const float2* __restrict__ kp_q,
+                                                             const float2* __restrict__ kp_t,
+                                                             float2* __restrict__ pts_q, float2* __restrict__ pts_t,
+                                                             int* __restrict__ qidx, int* __restrict__ tidx,
+                                                             int* __restrict__ n_out) {
+  gather_cta(idx, good, nq, kp_q, kp_t, pts_q, pts_t, qidx, tidx, n_out);
+}
+
+__global__ void __launch_bounds__(1024) match_gather_batched_kernel(const PairWork* __restrict__ work) {
+  const PairWork w = work[blockIdx.x];
+  gather_cta(w.idx, w.good, w.nq, w.kp_q, w.kp_t, w.pts_q, w.pts_t, w.qidx, w.tidx, w.n_out);
+}
+
 extern "C" int sfm_match_gather(sfm_ctx* ctx, const int32_t* idx, const uint8_t* good, int nq,
                                 const float* kp_q, const float* kp_t, float* pts_q, float* pts_t,
                                 int32_t* qidx_out, int32_t* tidx_out, int32_t* n_out) {
@@ -386,4 +423,96 @@ extern "C" int sfm_match_gather(sfm_ctx* ctx, const int32_t* idx, const uint8_t*
   SFM_TRY(dev_out_finish(ctx, &on));
   if (host_out) SFM_CUDA(cudaStreamSynchronize(ctx->stream));
   return SFM_OK;
+}
+
+// ------------------------------------------------------------------ batched pairs
+// Match + ratio test (+ optional survivor gather) for many pairs with THREE launches in total: one K1
+// kernel over the items of every pair, one K1c grid, one gather grid (one CTA per pair).  All per-pair
+// outputs are device pointers; idx/good may be NULL per pair (workspace is used).  Pairs whose
+// descriptors are not tensor-core eligible (or empty) go through the single-pair path.
+static int match_pairs_batched(sfm_ctx* ctx, int npairs, const sfm_desc* const* q, const sfm_desc* const* t, double ratio,
+                               int32_t* const* idx, float* const* dist, uint8_t* const* good, int32_t* n_good_dev,
+                               const float* const* kp_q, const float* const* kp_t, float* const* pts_q, float* const* pts_t,
+                               int32_t* const* qidx, int32_t* const* tidx, int32_t* n_out_dev) {
+  const bool gather = n_out_dev != nullptr;
+  std::vector<int> fast, slow;
+  for (int p = 0; p < npairs; ++p) {
+    SFM_REQUIRE(q[p] && t[p], "batched match: pair %d has a null descriptor set", p);
+    SFM_REQUIRE(q[p]->dim == t[p]->dim, "knnMatch: descriptor dims differ (%d vs %d)", q[p]->dim, t[p]->dim);
+    SFM_TRY(sfm_desc_resolve(const_cast<sfm_desc*>(q[p])));
+    SFM_TRY(sfm_desc_resolve(const_cast<sfm_desc*>(t[p])));
+    const bool tc_ok = q[p]->exact && t[p]->exact && q[p]->tiles && t[p]->tiles && q[p]->n > 0 && t[p]->n > 0;
+    (tc_ok ? fast : slow).push_back(p);
+  }
+  if (n_good_dev) SFM_CUDA(cudaMemsetAsync(n_good_dev, 0, sizeof(int32_t) * npairs, ctx->stream));
+  // per-pair idx / good buffers (needed by the gather even if the caller does not want them)
+  std::vector<int32_t*> idx_p(npairs);
+  std::vector<uint8_t*> good_p(npairs);
+  for (int p = 0; p < npairs; ++p) {
+    idx_p[p] = idx ? idx[p] : nullptr;
+    good_p[p] = good ? good[p] : nullptr;
+    const size_t nq = (size_t)q[p]->n;
+    if (gather && !idx_p[p]) SFM_TRY(ws_alloc_t(ctx, 2 * nq + 2, &idx_p[p]));
+    if (gather && !good_p[p]) SFM_TRY(ws_alloc_t(ctx, nq + 1, &good_p[p]));
+  }
+  for (int p : slow) {
+    int32_t* ng = n_good_dev ? n_good_dev + p : nullptr;
+    SFM_TRY(match_pair(ctx, q[p], t[p], ratio, 0, idx_p[p], dist ? dist[p] : nullptr, good_p[p], ng));
+  }
+  // tables are staged from pageable vectors: cudaMemcpyAsync copies a small pageable source before it
+  // returns, so nothing here has to outlive the call (the pinned staging area is recycled per API call)
+  std::vector<PairWork> host((size_t)(npairs > 0 ? npairs : 1));
+  PairWork* dev = nullptr;
+  SFM_TRY(ws_alloc_t(ctx, (size_t)(npairs > 0 ? npairs : 1), &dev));
+  int max_nq = 0;
+  if (!fast.empty()) {
+    std::vector<const sfm_desc*> fq(fast.size()), ft(fast.size());
+    std::vector<mkey_t*> cand(fast.size());
+    std::vector<int> nsub(fast.size());
+    for (size_t k = 0; k < fast.size(); ++k) { fq[k] = q[fast[k]]; ft[k] = t[fast[k]]; }
+    SFM_TRY(sfm_match_tc_launch_batched(ctx, (int)fast.size(), fq.data(), ft.data(), cand.data(), nsub.data()));
+    for (size_t k = 0; k < fast.size(); ++k) {
+      const int p = fast[k];
+      PairWork& w = host[k];
+      memset(&w, 0, sizeof(w));
+      w.cand = cand[k]; w.qf = q[p]->f32; w.tf = t[p]->f32;
+      w.nq = q[p]->n; w.nt = t[p]->n; w.nsub = nsub[k];
+      w.idx = idx_p[p]; w.dist = dist ? dist[p] : nullptr; w.good = good_p[p];
+      w.n_good = n_good_dev ? n_good_dev + p : nullptr;
+      if (w.nq > max_nq) max_nq = w.nq;
+    }
+    SFM_CUDA(cudaMemcpyAsync(dev, host.data(), sizeof(PairWork) * fast.size(), cudaMemcpyHostToDevice, ctx->stream));
+    dim3 grid(div_up(max_nq, 256), (unsigned)fast.size());
+    SFM_LAUNCH(ctx, SFM_K_MATCH_FINAL, (match_finalize_batched_kernel<<<grid, 256, 0, ctx->stream>>>(dev, ratio)));
+  }
+  if (gather && npairs > 0) {
+    std::vector<PairWork> ghost((size_t)npairs);
+    PairWork* gdev = nullptr;
+    SFM_TRY(ws_alloc_t(ctx, (size_t)npairs, &gdev));
+    for (int p = 0; p < npairs; ++p) {
+      PairWork& w = ghost[p];
+      memset(&w, 0, sizeof(w));
+      w.nq = q[p]->n;
+      w.idx = idx_p[p]; w.good = good_p[p];
+      w.kp_q = (const float2*)(kp_q ? kp_q[p] : nullptr); w.kp_t = (const float2*)(kp_t ? kp_t[p] : nullptr);
+      w.pts_q = (float2*)(pts_q ? pts_q[p] : nullptr); w.pts_t = (float2*)(pts_t ? pts_t[p] : nullptr);
+      w.qidx = qidx ? qidx[p] : nullptr; w.tidx = tidx ? tidx[p] : nullptr;
+      w.n_out = n_out_dev + p;
+      SFM_REQUIRE((!w.pts_q || w.kp_q) && (!w.pts_t || w.kp_t), "batched match: keypoints missing for pair %d", p);
+    }
+    SFM_CUDA(cudaMemcpyAsync(gdev, ghost.data(), sizeof(PairWork) * npairs, cudaMemcpyHostToDevice, ctx->stream));
+    SFM_LAUNCH(ctx, SFM_K_GATHER, (match_gather_batched_kernel<<<npairs, 1024, 0, ctx->stream>>>(gdev)));
+  }
+  return SFM_OK;
+}
+
+extern "C" int sfm_desc_match_gather_batched(sfm_ctx* ctx, int npairs, const sfm_desc* const* q, const sfm_desc* const* t,
+                                             double ratio, const float* const* kp_q, const float* const* kp_t,
+                                             int32_t* const* idx, uint8_t* const* good, float* const* pts_q,
+                                             float* const* pts_t, int32_t* const* qidx, int32_t* const* tidx,
+                                             int32_t* n_out) {
+  SFM_REQUIRE(ctx && npairs >= 0 && (npairs == 0 || (q && t && n_out)), "sfm_desc_match_gather_batched: null argument");
+  SFM_REQUIRE(npairs == 0 || sfm_is_device_ptr(n_out), "sfm_desc_match_gather_batched: n_out must be a device array of npairs");
+  SFM_TRY(sfm_ws_begin(ctx));
+  return match_pairs_batched(ctx, npairs, q, t, ratio, idx, nullptr, good, nullptr, kp_q, kp_t, pts_q, pts_t, qidx, tidx, n_out);
 }

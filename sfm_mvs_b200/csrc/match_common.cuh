@@ -51,6 +51,8 @@ int sfm_match_exact_splits(sfm_ctx* ctx, int nq, int nt);
 // match_tc.cu
 int sfm_match_tc_splits(sfm_ctx* ctx, int nq, int nt);
 int sfm_match_tc_launch(sfm_ctx* ctx, const sfm_desc* q, const sfm_desc* t, mkey_t* cand, int nsplit);
+int sfm_match_tc_launch_batched(sfm_ctx* ctx, int npairs, const sfm_desc* const* q, const sfm_desc* const* t,
+                                mkey_t** cand_out, int* nsub_out);
 int sfm_desc_prepare_launch(sfm_ctx* ctx, sfm_desc* d, const void* src, int dtype);
 // match.cu
 // qf/tf non-null: candidates come from the tensor-core kernel ([nq][nsplit][3]); null: [nq][nsplit][2]

@@ -228,21 +228,45 @@ __device__ __forceinline__ constexpr uint32_t make_idesc(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-struct TcParams {
+// One (query view, train view) problem of a launch.  A launch covers one or many of them ("batched":
+// the items of all pairs form one list, so the fixed cost of a launch — cluster start, TMEM allocation,
+// pipeline ramp and tail, ~7 us — is paid once for e.g. the 199 consecutive pairs of a 200-view scene).
+struct TcPair {
   const unsigned char* q_tiles;   // query view image
   const unsigned char* t_tiles;   // train view image
+  mkey_t* cand;                   // [n_qtiles*128][2*nsplit][3]: best, runner-up, "check this column" (K1c)
   int n_qtiles;                   // 128-row query tiles holding real rows
   int n_qtiles_alloc;             // tiles present in the image (even)
   int n_stages;                   // 256-column train stages
   int n_groups;                   // query groups of 2*QT tiles
-  int nsplit;
+  int nsplit;                     // train splits; items of the pair = n_groups * nsplit, split-major
+  int item_begin;                 // first item of this pair in the launch's item list
   int n_items;
-  mkey_t* cand;                   // [n_qtiles*128][2*nsplit][3]: best, runner-up, "check this column" (K1c)
+  int pad_;
+};
+
+struct TcParams {
+  TcPair one;                     // the pair of a single-pair launch (pairs == nullptr)
+  const TcPair* pairs;            // device array of a batched launch, ordered by item_begin
+  int n_items;                    // all items of the launch
   float* dump;                    // debug: raw accumulators [n_qtiles*128][dump_cols] or NULL
   int dump_cols;
   long long* timeline;            // debug (MODE 2): per job of pair 0, 8 clock64 stamps taken on the leader SM
   unsigned int key_mul;           // = 256, passed at run time so the key build stays an IMAD (FMA pipe)
   unsigned int debug;             // diagnostics (env SFM_MATCH_DEBUG): bit0 skip epilogue math, bit1 skip MMAs, bit2 skip TMEM loads
+};
+
+// Walks the pair list as a role's item index grows (items are visited in increasing order).
+struct PairCursor {
+  const TcParams& p;
+  TcPair pd;
+  int pi;
+  __device__ __forceinline__ explicit PairCursor(const TcParams& prm) : p(prm), pd(prm.pairs ? prm.pairs[0] : prm.one), pi(0) {}
+  __device__ __forceinline__ int seek(int item) {          // -> item index inside its pair
+    while (item >= pd.item_begin + pd.n_items) pd = p.pairs[++pi];
+    return item - pd.item_begin;
+  }
+  __device__ __forceinline__ int s_begin_of(int split) const { return (int)(((long long)split * pd.n_stages) / pd.nsplit); }
 };
 
 // ---------------------------------------------------------------------------- epilogue arithmetic
@@ -367,7 +391,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(tc::NTHREADS, 1) mat
   const uint32_t bar0 = sbase + tc::SMEM_BAR;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + tc::SMEM_BAR + tc::NBAR * 8);
   auto bar = [&](int i) { return bar0 + 8u * (uint32_t)i; };
-  auto s_begin_of = [&](int split) { return (int)(((long long)split * p.n_stages) / p.nsplit); };
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < tc::NBAR; ++i) mbar_init(bar(i), i >= tc::ACC_EMPTY ? 16u : 1u);   // ACC_EMPTY: 8 warps x 2 CTAs
@@ -390,16 +413,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(tc::NTHREADS, 1) mat
     // ------------------------------------------------------------------ B producer (this CTA's half of every stage)
     if (lane == 0) {
       uint32_t seq = 0;
+      PairCursor cur(p);
       for (int item = pair; item < p.n_items; item += n_pairs) {
-        const int split = item / p.n_groups;
-        const int s_begin = s_begin_of(split), s_end = s_begin_of(split + 1);
+        const int split = cur.seek(item) / cur.pd.n_groups;
+        const int s_begin = cur.s_begin_of(split), s_end = cur.s_begin_of(split + 1);
+        const unsigned char* t_tiles = cur.pd.t_tiles;
         for (int s = s_begin; s < s_end; ++s, ++seq) {
           const int slot = (int)(seq % tc::NB);
           const uint32_t ph = (seq / tc::NB) & 1u;
           mbar_wait(bar(tc::B_EMPTY + slot), ph ^ 1u);
           mbar_expect_tx(bar(tc::B_FULL + slot), tc::TILE_BYTES);
           if (QT == 2) tick(2 * seq + 1, 0);      // timeline: when this stage's load was issued
-          bulk_g2s(sbase + tc::SMEM_B + slot * tc::TILE_BYTES, p.t_tiles + (size_t)(2 * s + (int)rank) * tc::TILE_BYTES,
+          bulk_g2s(sbase + tc::SMEM_B + slot * tc::TILE_BYTES, t_tiles + (size_t)(2 * s + (int)rank) * tc::TILE_BYTES,
                    tc::TILE_BYTES, bar(tc::B_FULL + slot));
         }
       }
@@ -408,15 +433,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(tc::NTHREADS, 1) mat
     // ------------------------------------------------------------------ A producer (this CTA's query tiles)
     if (lane == 0) {
       uint32_t seq = 0;
+      PairCursor cur(p);
       for (int item = pair; item < p.n_items; item += n_pairs) {
-        const int g = item % p.n_groups;
+        const int g = cur.seek(item) % cur.pd.n_groups;
         for (int t = 0; t < QT; ++t, ++seq) {
           const int slot = (int)(seq & 1u);
           const uint32_t ph = (seq >> 1) & 1u;
-          const int qt = min((g * QT + t) * 2 + (int)rank, p.n_qtiles_alloc - 1);
+          const int qt = min((g * QT + t) * 2 + (int)rank, cur.pd.n_qtiles_alloc - 1);
           mbar_wait(bar(tc::A_EMPTY + slot), ph ^ 1u);
           mbar_expect_tx(bar(tc::A_FULL + slot), tc::TILE_BYTES);
-          bulk_g2s(sbase + tc::SMEM_A + slot * tc::TILE_BYTES, p.q_tiles + (size_t)qt * tc::TILE_BYTES, tc::TILE_BYTES,
+          bulk_g2s(sbase + tc::SMEM_A + slot * tc::TILE_BYTES, cur.pd.q_tiles + (size_t)qt * tc::TILE_BYTES, tc::TILE_BYTES,
                    bar(tc::A_FULL + slot));
         }
       }
@@ -426,9 +452,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(tc::NTHREADS, 1) mat
     if (lane == 0) {
       const uint32_t idesc = make_idesc(256, tc::STAGE_COLS);
       uint32_t a_seq = 0, b_seq = 0, job = 0;
+      PairCursor cur(p);
       for (int item = pair; item < p.n_items; item += n_pairs) {
-        const int split = item / p.n_groups;
-        const int s_begin = s_begin_of(split), s_end = s_begin_of(split + 1);
+        const int split = cur.seek(item) / cur.pd.n_groups;
+        const int s_begin = cur.s_begin_of(split), s_end = cur.s_begin_of(split + 1);
         for (int s = s_begin; s < s_end; ++s, ++b_seq) {
           const int bslot = (int)(b_seq % tc::NB);
           const uint32_t bph = (b_seq / tc::NB) & 1u;
@@ -480,9 +507,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(tc::NTHREADS, 1) mat
     const uint32_t mul256 = p.key_mul;  // 256, opaque to the compiler: the key build stays an IMAD (FMA pipe),
                                         // leaving the integer min/max pipe to the minima
     uint32_t job = 0;
+    PairCursor cur(p);
     for (int item = pair; item < p.n_items; item += n_pairs) {
-      const int g = item % p.n_groups, split = item / p.n_groups;
-      const int s_begin = s_begin_of(split), s_end = s_begin_of(split + 1);
+      const int local = cur.seek(item);
+      const int g = local % cur.pd.n_groups, split = local / cur.pd.n_groups;
+      const int s_begin = cur.s_begin_of(split), s_end = cur.s_begin_of(split + 1);
       RowState st[QT];
 #pragma unroll
       for (int t = 0; t < QT; ++t) st[t].reset();
@@ -501,7 +530,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(tc::NTHREADS, 1) mat
             if (DUMP) {
               const int qt = (g * QT + t) * 2 + (int)rank;
               drow = p.dump + (size_t)(qt * 128 + row) * p.dump_cols + s * tc::STAGE_COLS + half * 128;
-              if (qt >= p.n_qtiles) drow = nullptr;
+              if (qt >= cur.pd.n_qtiles) drow = nullptr;
             }
             auto dump32 = [&](const uint32_t (&r)[32], int c) {
               if (DUMP && drow && s * tc::STAGE_COLS + half * 128 + c * 32 < p.dump_cols) {
@@ -541,9 +570,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(tc::NTHREADS, 1) mat
 #pragma unroll
       for (int t = 0; t < QT; ++t) {
         const int qt = (g * QT + t) * 2 + (int)rank;
-        if (qt < p.n_qtiles)
+        if (qt < cur.pd.n_qtiles)
           emit_candidates(st[t], s_begin * tc::STAGE_COLS,
-                          p.cand + ((size_t)(qt * 128 + row) * (2 * p.nsplit) + 2 * split + half) * 3);
+                          cur.pd.cand + ((size_t)(qt * 128 + row) * (2 * cur.pd.nsplit) + 2 * split + half) * 3);
       }
     }
   }
@@ -561,10 +590,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(tc::NTHREADS, 1) mat
 // 8-bit chunk tag (<= 16 stages per split).
 struct TcPlan { int qt, nsplit, n_groups, n_stages, n_items, n_pairs; };
 
+static int tc_stages(int nt) { return div_up(div_up(nt, tc::TILE_ROWS), 2); }
+static int tc_min_split(int n_stages) { return div_up(n_stages, tc::MAX_STAGES_PER_SPLIT); }
+
 static TcPlan tc_plan(sfm_ctx* ctx, int nq, int nt) {
   TcPlan pl;
   const int n_qtiles = div_up(nq, tc::TILE_ROWS);
-  pl.n_stages = div_up(div_up(nt, tc::TILE_ROWS), 2);
+  pl.n_stages = tc_stages(nt);
   const int pairs = ctx->sm_count / 2 > 0 ? ctx->sm_count / 2 : 1;
   const char* e = getenv("SFM_MATCH_QT");
   int best_qt = 1, best_split = 1;
@@ -572,20 +604,19 @@ static TcPlan tc_plan(sfm_ctx* ctx, int nq, int nt) {
   for (int qt = 1; qt <= 2; ++qt) {
     if (e && atoi(e) != qt) continue;
     const int groups = div_up(n_qtiles, 2 * qt);
-    const int smin = div_up(pl.n_stages, tc::MAX_STAGES_PER_SPLIT);
+    const int smin = tc_min_split(pl.n_stages);
     for (int ns = smin; ns <= pl.n_stages && ns <= smin + 4 * pairs; ++ns) {
       const int items = groups * ns;
       const int waves = div_up(items, pairs);
       const double jobs = (double)div_up(pl.n_stages, ns) * qt;          // jobs of the longest item
-      // time ~ waves * (jobs + ramp); useful work = n_qtiles/2 * n_stages job-equivalents per pair-wave slot
-      const double ramp = 1.5;
-      const double t = waves * (jobs + ramp) + 0.02 * ns;                // slight preference for fewer splits
-      const double score = -t * (qt == 2 ? 1.0 : 1.04);                  // QT=2 halves L2 traffic per job
-      if (best < 0.0 || score > -best) { best = -score; best_qt = qt; best_split = ns; }
+      const double ramp = 1.5;                                           // query tile load, in job units
+      double t = waves * (jobs + ramp) + 0.02 * ns;                      // slight preference for fewer splits
+      if (qt == 1) t *= 1.04;                                            // QT=2 halves L2 traffic per job
+      if (best < 0.0 || t < best) { best = t; best_qt = qt; best_split = ns; }
     }
   }
   const char* es = getenv("SFM_MATCH_NSPLIT");
-  if (es && atoi(es) >= div_up(pl.n_stages, tc::MAX_STAGES_PER_SPLIT) && atoi(es) <= pl.n_stages) best_split = atoi(es);
+  if (es && atoi(es) >= tc_min_split(pl.n_stages) && atoi(es) <= pl.n_stages) best_split = atoi(es);
   pl.qt = best_qt;
   pl.nsplit = best_split;
   pl.n_groups = div_up(n_qtiles, 2 * best_qt);
@@ -594,7 +625,7 @@ static TcPlan tc_plan(sfm_ctx* ctx, int nq, int nt) {
   return pl;
 }
 
-// number of candidate sub-splits per query row (K1c merges them)
+// number of candidate sub-splits per query row of a single-pair launch (K1c merges them)
 int sfm_match_tc_splits(sfm_ctx* ctx, int nq, int nt) { return 2 * tc_plan(ctx, nq, nt).nsplit; }
 
 template <int QT, int MODE>
@@ -608,27 +639,35 @@ static int launch_tc_t(sfm_ctx* ctx, const TcParams& p, int n_pairs) {
   return SFM_OK;
 }
 
+static void fill_pair(TcPair& d, const sfm_desc* q, const sfm_desc* t, mkey_t* cand, int qt, int nsplit, int item_begin) {
+  d.q_tiles = (const unsigned char*)q->tiles;
+  d.t_tiles = (const unsigned char*)t->tiles;
+  d.cand = cand;
+  d.n_qtiles = q->n_tiles;
+  d.n_qtiles_alloc = (q->n_tiles + 1) & ~1;
+  d.n_stages = tc_stages(t->n);
+  d.n_groups = div_up(q->n_tiles, 2 * qt);
+  d.nsplit = nsplit;
+  d.item_begin = item_begin;
+  d.n_items = d.n_groups * nsplit;
+  d.pad_ = 0;
+}
+
 static int launch_tc(sfm_ctx* ctx, const sfm_desc* q, const sfm_desc* t, mkey_t* cand, int nsub, float* dump, int dump_cols,
                      long long* timeline = nullptr) {
   SFM_REQUIRE(q->tiles && t->tiles, "tensor-core matcher: descriptors have no tile image");
   TcPlan pl = tc_plan(ctx, q->n, t->n);
   SFM_REQUIRE(nsub == 2 * pl.nsplit, "tensor-core matcher: candidate buffer was sized for another plan");
   TcParams p;
-  p.q_tiles = (const unsigned char*)q->tiles;
-  p.t_tiles = (const unsigned char*)t->tiles;
-  p.n_qtiles = q->n_tiles;
-  p.n_qtiles_alloc = (q->n_tiles + 1) & ~1;
-  p.n_stages = pl.n_stages;
-  p.n_groups = pl.n_groups;
-  p.nsplit = pl.nsplit;
+  fill_pair(p.one, q, t, cand, pl.qt, pl.nsplit, 0);
+  p.pairs = nullptr;
   p.n_items = pl.n_items;
-  p.cand = cand;
   p.dump = dump;
   p.dump_cols = dump_cols;
   p.timeline = timeline;
   p.key_mul = 256u;
   { const char* e = getenv("SFM_MATCH_DEBUG"); p.debug = e ? (unsigned)atoi(e) : 0u; }
-  if (p.debug & 16u) p.n_items = 0;     // diagnostics: launch + setup + teardown only
+  if (p.debug & 16u) { p.n_items = 0; p.one.n_items = 0; }     // diagnostics: launch + setup + teardown only
   if (timeline) return pl.qt == 2 ? launch_tc_t<2, 2>(ctx, p, pl.n_pairs) : launch_tc_t<1, 2>(ctx, p, pl.n_pairs);
   if (dump) return pl.qt == 2 ? launch_tc_t<2, 1>(ctx, p, pl.n_pairs) : launch_tc_t<1, 1>(ctx, p, pl.n_pairs);
   return pl.qt == 2 ? launch_tc_t<2, 0>(ctx, p, pl.n_pairs) : launch_tc_t<1, 0>(ctx, p, pl.n_pairs);
@@ -636,6 +675,51 @@ static int launch_tc(sfm_ctx* ctx, const sfm_desc* q, const sfm_desc* t, mkey_t*
 
 int sfm_match_tc_launch(sfm_ctx* ctx, const sfm_desc* q, const sfm_desc* t, mkey_t* cand, int nsub) {
   return launch_tc(ctx, q, t, cand, nsub, nullptr, 0);
+}
+
+// Batched launch: ONE kernel over the items of all pairs.  nsub_out[k] = candidate sub-splits of pair k,
+// cand_out[k] = its candidate array (workspace).  Every pair must be tensor-core eligible.
+int sfm_match_tc_launch_batched(sfm_ctx* ctx, int npairs, const sfm_desc* const* q, const sfm_desc* const* t,
+                                mkey_t** cand_out, int* nsub_out) {
+  const int cta_pairs = ctx->sm_count / 2 > 0 ? ctx->sm_count / 2 : 1;
+  // query tiles per CTA: 2 unless the whole batch is too small to fill the machine that way
+  long long groups2 = 0;
+  for (int k = 0; k < npairs; ++k) groups2 += (long long)div_up(q[k]->n_tiles, 4) * tc_min_split(tc_stages(t[k]->n));
+  const int qt = groups2 >= cta_pairs ? 2 : 1;
+  long long base_items = 0;
+  for (int k = 0; k < npairs; ++k) base_items += (long long)div_up(q[k]->n_tiles, 2 * qt) * tc_min_split(tc_stages(t[k]->n));
+  // more splits only while the item list is shorter than ~3 waves
+  int scale = 1;
+  if (base_items < 3LL * cta_pairs) scale = (int)div_up64(3LL * cta_pairs, base_items > 0 ? base_items : 1);
+  std::vector<TcPair> host((size_t)(npairs > 0 ? npairs : 1));   // pageable: copied by cudaMemcpyAsync before it returns
+  TcPair* dev = nullptr;
+  SFM_TRY(ws_alloc_t(ctx, (size_t)(npairs > 0 ? npairs : 1), &dev));
+  int item = 0;
+  for (int k = 0; k < npairs; ++k) {
+    SFM_REQUIRE(q[k]->tiles && t[k]->tiles, "tensor-core matcher: descriptors have no tile image");
+    const int stages = tc_stages(t[k]->n);
+    int ns = tc_min_split(stages) * scale;
+    if (ns > stages) ns = stages;
+    mkey_t* cand = nullptr;
+    SFM_TRY(ws_alloc_t(ctx, (size_t)q[k]->n_tiles * 128 * 2 * ns * 3, &cand));
+    fill_pair(host[k], q[k], t[k], cand, qt, ns, item);
+    item += host[k].n_items;
+    cand_out[k] = cand;
+    nsub_out[k] = 2 * ns;
+  }
+  SFM_CUDA(cudaMemcpyAsync(dev, host.data(), sizeof(TcPair) * npairs, cudaMemcpyHostToDevice, ctx->stream));
+  TcParams p;
+  p.one = host[0];
+  p.pairs = dev;
+  p.n_items = item;
+  p.dump = nullptr;
+  p.dump_cols = 0;
+  p.timeline = nullptr;
+  p.key_mul = 256u;
+  { const char* e = getenv("SFM_MATCH_DEBUG"); p.debug = e ? (unsigned)atoi(e) : 0u; }
+  const int n_pairs = item < cta_pairs ? item : cta_pairs;
+  if (n_pairs == 0) return SFM_OK;
+  return qt == 2 ? launch_tc_t<2, 0>(ctx, p, n_pairs) : launch_tc_t<1, 0>(ctx, p, n_pairs);
 }
 
 // Debug/self-test entry (not part of the reference-facing surface): raw accumulators of every

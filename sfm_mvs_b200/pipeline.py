@@ -62,30 +62,43 @@ class RegistrationChain:
     # ------------------------------------------------------------------ matching (batched over pairs)
     @_on_ctx_stream
     def match_pairs(self, views, pairs):
-        """knn2 + ratio + survivor gather for every (q, t) view-index pair; one host sync at the end."""
+        """knn2 + ratio + survivor gather for every (q, t) view-index pair: ONE K1 launch over the items of
+        all pairs, one K1c grid, one gather grid (sfm_desc_match_gather_batched); one host sync at the end."""
         torch = self.torch
-        out = []
-        counts = torch.empty((max(len(pairs), 1),), dtype=torch.int32, device=self.dev)
-        for k, (a, b) in enumerate(pairs):
-            va, vb = views[a], views[b]
-            idx = torch.empty((va.n, 2), dtype=torch.int32, device=self.dev)
-            good = torch.empty((va.n,), dtype=torch.uint8, device=self.dev)
-            check(lib.sfm_desc_match(self.ctx._h, va.desc._h, vb.desc._h, self.ratio, idx.data_ptr(), None,
-                                     good.data_ptr(), None, 0))
-            pm = PairMatches()
-            pm.pts_q = torch.empty((va.n, 2), dtype=torch.float32, device=self.dev)
-            pm.pts_t = torch.empty((va.n, 2), dtype=torch.float32, device=self.dev)
-            pm.qidx = torch.empty((va.n,), dtype=torch.int32, device=self.dev)
-            pm.tidx = torch.empty((va.n,), dtype=torch.int32, device=self.dev)
-            pm.n_dev = counts[k:k + 1]
-            check(lib.sfm_match_gather(self.ctx._h, idx.data_ptr(), good.data_ptr(), va.n, va.kp.data_ptr(),
-                                       vb.kp.data_ptr(), pm.pts_q.data_ptr(), pm.pts_t.data_ptr(), pm.qidx.data_ptr(),
-                                       pm.tidx.data_ptr(), pm.n_dev.data_ptr()))
-            out.append(pm)
+        n = len(pairs)
+        if n == 0:
+            return []
+        nq = np.array([views[a].n for a, _ in pairs], np.int64)
+        off = np.concatenate([[0], np.cumsum(nq)])
+        tot = int(max(off[-1], 1))
+        counts = torch.empty((n,), dtype=torch.int32, device=self.dev)
+        pts_q = torch.empty((tot, 2), dtype=torch.float32, device=self.dev)
+        pts_t = torch.empty((tot, 2), dtype=torch.float32, device=self.dev)
+        qidx = torch.empty((tot,), dtype=torch.int32, device=self.dev)
+        tidx = torch.empty((tot,), dtype=torch.int32, device=self.dev)
+
+        def ptrs(base, stride):
+            return np.ascontiguousarray(base + off[:-1] * stride, np.uint64)
+
+        hq = np.array([views[a].desc._h.value if hasattr(views[a].desc._h, "value") else views[a].desc._h for a, _ in pairs], np.uint64)
+        ht = np.array([views[b].desc._h.value if hasattr(views[b].desc._h, "value") else views[b].desc._h for _, b in pairs], np.uint64)
+        kq = np.array([views[a].kp.data_ptr() for a, _ in pairs], np.uint64)
+        kt = np.array([views[b].kp.data_ptr() for _, b in pairs], np.uint64)
+        a_pq, a_pt = ptrs(pts_q.data_ptr(), 8), ptrs(pts_t.data_ptr(), 8)
+        a_qi, a_ti = ptrs(qidx.data_ptr(), 4), ptrs(tidx.data_ptr(), 4)
+        check(lib.sfm_desc_match_gather_batched(self.ctx._h, n, hq.ctypes.data, ht.ctypes.data, self.ratio, kq.ctypes.data,
+                                                kt.ctypes.data, None, None, a_pq.ctypes.data, a_pt.ctypes.data,
+                                                a_qi.ctypes.data, a_ti.ctypes.data, counts.data_ptr()))
         self.ctx.sync()
         host = counts.cpu().numpy()
-        for k, pm in enumerate(out):
+        out = []
+        for k in range(n):
+            pm = PairMatches()
+            lo, hi = int(off[k]), int(off[k + 1])
+            pm.pts_q, pm.pts_t, pm.qidx, pm.tidx = pts_q[lo:hi], pts_t[lo:hi], qidx[lo:hi], tidx[lo:hi]
+            pm.n_dev = counts[k:k + 1]
             pm.n = int(host[k])
+            out.append(pm)
         return out
 
     # ------------------------------------------------------------------ geometry helpers (device buffers)

@@ -107,3 +107,56 @@ def test_large_pair_properties(engine):
     sidx, sdist, _, _ = engine.knn2(t, t, mode=2)
     # duplicates inside t are possible in principle; distance 0 with the lowest index is the contract
     assert np.all(sdist[:, 0] == 0) and np.all(sidx[:, 0] <= np.arange(16384))
+
+
+def test_batched_pairs_equal_single_pair_calls(engine):
+    """sfm_desc_match_gather_batched: one K1 launch over the items of all pairs (different sizes, one pair
+    that must take the fp32 kernel) == per-pair knn2 + gather, bit for bit."""
+    import ctypes as C
+    import torch
+    from sfm_mvs_b200._lib import check, lib
+    rng = np.random.default_rng(3)
+    sizes = [(700, 900), (257, 129), (1500, 1500), (300, 400), (1, 50), (2100, 640)]
+    sets = []
+    for k, (nq, nt) in enumerate(sizes):
+        q, t, _ = synth.matching_pair(nq, nt, seed=20 + k)
+        if k == 3:                                   # non-integer descriptors -> fp32 kernel inside the batch
+            q = q + rng.random(q.shape, dtype=np.float32) * 0.25
+        sets.append((q, t, rng.random((nq, 2), dtype=np.float32) * 900, rng.random((nt, 2), dtype=np.float32) * 900))
+    dq = [engine.descriptors(s[0]) for s in sets]
+    dt = [engine.descriptors(s[1]) for s in sets]
+    dev = engine.torch_device
+    with torch.cuda.stream(engine.torch_stream()):
+        kq = [torch.from_numpy(s[2]).to(dev) for s in sets]
+        kt = [torch.from_numpy(s[3]).to(dev) for s in sets]
+        pq = [torch.zeros((s[0].shape[0], 2), dtype=torch.float32, device=dev) for s in sets]
+        pt = [torch.zeros((s[0].shape[0], 2), dtype=torch.float32, device=dev) for s in sets]
+        qi = [torch.zeros((s[0].shape[0],), dtype=torch.int32, device=dev) for s in sets]
+        ti = [torch.zeros((s[0].shape[0],), dtype=torch.int32, device=dev) for s in sets]
+        idx = [torch.zeros((s[0].shape[0], 2), dtype=torch.int32, device=dev) for s in sets]
+        good = [torch.zeros((s[0].shape[0],), dtype=torch.uint8, device=dev) for s in sets]
+        n_out = torch.zeros((len(sets),), dtype=torch.int32, device=dev)
+    arr = lambda xs: np.array(xs, np.uint64)
+    a = [arr([d._h.value for d in dq]), arr([d._h.value for d in dt]), arr([x.data_ptr() for x in kq]),
+         arr([x.data_ptr() for x in kt]), arr([x.data_ptr() for x in idx]), arr([x.data_ptr() for x in good]),
+         arr([x.data_ptr() for x in pq]), arr([x.data_ptr() for x in pt]), arr([x.data_ptr() for x in qi]),
+         arr([x.data_ptr() for x in ti])]
+    check(lib.sfm_desc_match_gather_batched(engine._h, len(sets), a[0].ctypes.data, a[1].ctypes.data, 0.70, a[2].ctypes.data,
+                                            a[3].ctypes.data, a[4].ctypes.data, a[5].ctypes.data, a[6].ctypes.data,
+                                            a[7].ctypes.data, a[8].ctypes.data, a[9].ctypes.data, n_out.data_ptr()))
+    engine.sync()
+    counts = n_out.cpu().numpy()
+    for k, (q, t, kpq, kpt) in enumerate(sets):
+        ridx, rdist, rgood, rng_ = engine.knn2(q, t, 0.70)
+        assert np.array_equal(idx[k].cpu().numpy(), ridx), f"pair {k}: indices differ"
+        assert np.array_equal(good[k].cpu().numpy().astype(bool), rgood.astype(bool))
+        m = int(counts[k])
+        assert m == int(rgood.sum())
+        sel = np.flatnonzero(rgood)
+        assert np.array_equal(qi[k].cpu().numpy()[:m], sel)
+        assert np.array_equal(ti[k].cpu().numpy()[:m], ridx[sel, 0])
+        assert np.array_equal(pq[k].cpu().numpy()[:m], kpq[sel])
+        assert np.array_equal(pt[k].cpu().numpy()[:m], kpt[ridx[sel, 0]])
+    if sizes[0][1] > 2:
+        cidx, _ = cvpath.knn2_arrays(sets[0][0], sets[0][1])
+        assert np.array_equal(idx[0].cpu().numpy(), cidx)
