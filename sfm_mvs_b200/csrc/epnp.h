@@ -95,12 +95,13 @@ HM_HD inline void ls_solve(double* A, double* b, double* x) {
     HM_UNROLL
     for (int i = k + 1; i < M; ++i) vnorm2 += A[i * N + k] * A[i * N + k];
     if (vnorm2 > 0.0) {
+      const double two_inv = 2.0 / vnorm2;     // one division per reflector instead of one per column
       HM_UNROLL
       for (int j = k + 1; j < N; ++j) {
         double dot = vk * A[k * N + j];
         HM_UNROLL
         for (int i = k + 1; i < M; ++i) dot += A[i * N + k] * A[i * N + j];
-        double f = 2.0 * dot / vnorm2;
+        double f = dot * two_inv;
         A[k * N + j] -= f * vk;
         HM_UNROLL
         for (int i = k + 1; i < M; ++i) A[i * N + j] -= f * A[i * N + k];
@@ -108,7 +109,7 @@ HM_HD inline void ls_solve(double* A, double* b, double* x) {
       double dot = vk * b[k];
       HM_UNROLL
       for (int i = k + 1; i < M; ++i) dot += A[i * N + k] * b[i];
-      double f = 2.0 * dot / vnorm2;
+      double f = dot * two_inv;
       b[k] -= f * vk;
       HM_UNROLL
       for (int i = k + 1; i < M; ++i) b[i] -= f * A[i * N + k];

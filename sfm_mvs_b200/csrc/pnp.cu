@@ -19,6 +19,7 @@
 // and a single device->host copy of (rvec, tvec, inliers, info) at the end.
 #include <float.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "epnp.h"
@@ -128,10 +129,17 @@ struct EpnpShared {
   int pq[12];
 };
 
+// Parallel-ordered two-sided Jacobi: a round rotates 6 disjoint index pairs at once.  With disjoint
+// pairs A' = J^T A J decomposes into 36 independent 2x2 blocks (row pair x column pair), each owned by
+// one lane, so a round is: 6 lanes form (c, s) -> one warp barrier -> every lane rewrites its blocks and
+// its share of the eigenvector rows -> one warp barrier.  Rotation parameters avoid two of the three
+// float64 divisions and one square root of the textbook form (t = sgn(a) b / (|a| + hypot(a, b)),
+// c = rsqrt(1 + t^2)); the sweep stops at off^2 <= 1e-28 diag^2 (off/diag ~ 1e-14: the null-space
+// basis inside the degenerate eigenvalue is arbitrary anyway, see DESIGN.md "PnP parity").
 __device__ __forceinline__ void warp_jacobi12(EpnpShared& sh, int lane) {
   for (int i = lane; i < 144; i += 32) sh.V[i] = (i / 12 == i % 12) ? 1.0 : 0.0;
   __syncwarp();
-  for (int sweep = 0; sweep < 60; ++sweep) {
+  for (int sweep = 0; sweep < 40; ++sweep) {
     double off = 0.0, diag = 0.0;
     for (int i = lane; i < 144; i += 32) {
       double a = sh.A[i];
@@ -142,49 +150,59 @@ __device__ __forceinline__ void warp_jacobi12(EpnpShared& sh, int lane) {
       off += __shfl_xor_sync(0xffffffffu, off, o);
       diag += __shfl_xor_sync(0xffffffffu, diag, o);
     }
-    if (off * 0.5 <= 1e-32 * diag || off == 0.0) break;
+    if (off * 0.5 <= 1e-28 * diag || off == 0.0) break;
     for (int round = 0; round < 11; ++round) {
       if (lane < 6) {
         int p = (lane == 0) ? 11 : (round + lane) % 11;
         int q = (lane == 0) ? round : (round - lane + 11) % 11;
         if (p > q) { int t = p; p = q; q = t; }
-        double apq = sh.A[p * 12 + q], app = sh.A[p * 12 + p], aqq = sh.A[q * 12 + q];
+        const double apq = sh.A[p * 12 + q], app = sh.A[p * 12 + p], aqq = sh.A[q * 12 + q];
         double c = 1.0, s = 0.0;
         if (fabs(apq) > 1e-300) {
-          double theta = (aqq - app) / (2.0 * apq);
-          double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-          c = 1.0 / sqrt(t * t + 1.0);
+          // tan of the rotation angle in float32 (MUFU sqrt / divide); (c, s) from it in float64, so the
+          // rotation is orthogonal to working precision and merely annihilates a_pq to ~1e-7 relative —
+          // the residue is carried exactly (no forced zero) and vanishes in the next sweeps.
+          const double al = 0.5 * (aqq - app);
+          const double sc = 1.0 / fmax(fabs(al), fabs(apq));
+          const float fa = (float)(al * sc), fb = (float)(apq * sc);
+          const float fr = sqrtf(fa * fa + fb * fb);
+          const double t = (double)(fb / (fa + (fa >= 0.f ? fr : -fr)));
+          c = rsqrt(t * t + 1.0);
           s = t * c;
         }
         sh.cs[2 * lane] = c; sh.cs[2 * lane + 1] = s;
         sh.pq[2 * lane] = p; sh.pq[2 * lane + 1] = q;
       }
       __syncwarp();
-      for (int it = lane; it < 72; it += 32) {      // columns p,q of every row
-        int k = it / 12, i = it - 12 * k;
-        int p = sh.pq[2 * k], q = sh.pq[2 * k + 1];
-        double c = sh.cs[2 * k], s = sh.cs[2 * k + 1];
-        double aip = sh.A[i * 12 + p], aiq = sh.A[i * 12 + q];
-        sh.A[i * 12 + p] = c * aip - s * aiq;
-        sh.A[i * 12 + q] = s * aip + c * aiq;
+      // 36 blocks: rows (p1,q1) of pair kp, columns (p2,q2) of pair kq
+#pragma unroll
+      for (int n = 0; n < 2; ++n) {
+        const int b = lane + 32 * n;
+        if (b < 36) {
+          const int kp = b / 6, kq = b - 6 * kp;
+          const int p1 = sh.pq[2 * kp], q1 = sh.pq[2 * kp + 1], p2 = sh.pq[2 * kq], q2 = sh.pq[2 * kq + 1];
+          const double c1 = sh.cs[2 * kp], s1 = sh.cs[2 * kp + 1], c2 = sh.cs[2 * kq], s2 = sh.cs[2 * kq + 1];
+          const double a = sh.A[p1 * 12 + p2], bb = sh.A[p1 * 12 + q2], cc = sh.A[q1 * 12 + p2], d = sh.A[q1 * 12 + q2];
+          // rows: J1^T from the left
+          const double ra = c1 * a - s1 * cc, rb = c1 * bb - s1 * d, rc = s1 * a + c1 * cc, rd = s1 * bb + c1 * d;
+          // columns: J2 from the right
+          sh.A[p1 * 12 + p2] = c2 * ra - s2 * rb;
+          sh.A[p1 * 12 + q2] = s2 * ra + c2 * rb;
+          sh.A[q1 * 12 + p2] = c2 * rc - s2 * rd;
+          sh.A[q1 * 12 + q2] = s2 * rc + c2 * rd;
+        }
       }
-      __syncwarp();
-      for (int it = lane; it < 72; it += 32) {      // rows p,q of every column; eigenvector rows
-        int k = it / 12, j = it - 12 * k;
-        int p = sh.pq[2 * k], q = sh.pq[2 * k + 1];
-        double c = sh.cs[2 * k], s = sh.cs[2 * k + 1];
-        double apj = sh.A[p * 12 + j], aqj = sh.A[q * 12 + j];
-        sh.A[p * 12 + j] = c * apj - s * aqj;
-        sh.A[q * 12 + j] = s * apj + c * aqj;
-        double vp = sh.V[p * 12 + j], vq = sh.V[q * 12 + j];
-        sh.V[p * 12 + j] = c * vp - s * vq;
-        sh.V[q * 12 + j] = s * vp + c * vq;
-      }
-      __syncwarp();
-      if (lane < 6) {
-        int p = sh.pq[2 * lane], q = sh.pq[2 * lane + 1];
-        sh.A[p * 12 + q] = 0.0;
-        sh.A[q * 12 + p] = 0.0;
+#pragma unroll
+      for (int n = 0; n < 3; ++n) {                  // eigenvector rows p,q of every rotation
+        const int it = lane + 32 * n;
+        if (it < 72) {
+          const int k = it / 12, j = it - 12 * k;
+          const int p = sh.pq[2 * k], q = sh.pq[2 * k + 1];
+          const double c = sh.cs[2 * k], s = sh.cs[2 * k + 1];
+          const double vp = sh.V[p * 12 + j], vq = sh.V[q * 12 + j];
+          sh.V[p * 12 + j] = c * vp - s * vq;
+          sh.V[q * 12 + j] = s * vp + c * vq;
+        }
       }
       __syncwarp();
     }
@@ -201,10 +219,12 @@ struct PnpSubsets {
 __global__ void __launch_bounds__(32) pnp_epnp_kernel(const float* __restrict__ X, const float* __restrict__ px, int n,
                                                       int H, PnpCam cam, const __grid_constant__ PnpSubsets subs,
                                                       double* __restrict__ poses, double* __restrict__ rt6,
-                                                      unsigned char* __restrict__ valid) {
+                                                      unsigned char* __restrict__ valid, long long* __restrict__ dbg) {
   __shared__ EpnpShared sh;
   const int h = blockIdx.x, lane = threadIdx.x;
   if (h >= H) return;
+  auto tick = [&](int k) { if (dbg && h == 0 && lane == 0) dbg[k] = clock64(); };
+  tick(0);
   const hm::EpnpCam ec = {cam.fx, cam.fy, cam.cx, cam.cy};
   if (lane == 0) {
     int sub[5] = {0, 1, 2, 3, 4};
@@ -230,6 +250,7 @@ __global__ void __launch_bounds__(32) pnp_epnp_kernel(const float* __restrict__ 
     hm::epnp_control_alphas(sh.pw, 5, sh.alphas, reinterpret_cast<double(*)[3]>(sh.cws));
   }
   __syncwarp();
+  tick(1);
   // M (10 x 12, two rows per correspondence) into sh.V, then M^T M (144 entries) spread over the lanes
   for (int e = lane; e < 120; e += 32) {
     const int rw = e / 12, col = e - 12 * rw, i = rw >> 1, jcp = col / 3, comp = col - 3 * jcp;
@@ -248,7 +269,9 @@ __global__ void __launch_bounds__(32) pnp_epnp_kernel(const float* __restrict__ 
     sh.A[e] = acc;
   }
   __syncwarp();
+  tick(2);
   warp_jacobi12(sh, lane);
+  tick(3);
   if (lane == 0) {
     // the four eigenvectors of the smallest eigenvalues, smallest first, largest component positive
     double w[12];
@@ -269,6 +292,7 @@ __global__ void __launch_bounds__(32) pnp_epnp_kernel(const float* __restrict__ 
     hm::epnp_L_rho(v, reinterpret_cast<const double(*)[3]>(sh.cws), sh.L, sh.rho);
   }
   __syncwarp();
+  tick(4);
   double R[9], t[3], err = 0.0;
   if (lane < 3) {
     const double* v[4] = {sh.v4, sh.v4 + 12, sh.v4 + 24, sh.v4 + 36};
@@ -279,6 +303,7 @@ __global__ void __launch_bounds__(32) pnp_epnp_kernel(const float* __restrict__ 
   errs[1] = __shfl_sync(0xffffffffu, err, 1);
   errs[2] = __shfl_sync(0xffffffffu, err, 2);
   const int N = hm::epnp_pick(errs);
+  tick(5);
   if (lane == N) {
     double rv[3];
     hm::rodrigues_to_vector(R, rv);
@@ -292,6 +317,8 @@ __global__ void __launch_bounds__(32) pnp_epnp_kernel(const float* __restrict__ 
     rt6[6 * h + 3] = t[0]; rt6[6 * h + 4] = t[1]; rt6[6 * h + 5] = t[2];
     valid[h] = ok ? 1 : 0;
   }
+  __syncwarp();
+  tick(6);
 }
 
 // ------------------------------------------------------------------ replay of the stopping rule
@@ -312,10 +339,9 @@ __device__ inline int update_num_iters(double p, double ep, int model_points, in
   return (denom >= 0 || -num >= max_iters * (-denom)) ? max_iters : __double2int_rn(num / denom);
 }
 
-__global__ void pnp_replay_kernel(const int* __restrict__ counts, const unsigned char* __restrict__ valid, int n,
+__device__ inline void pnp_replay(const int* __restrict__ counts, const unsigned char* __restrict__ valid, int n,
                                   int max_iters, double conf, const double* __restrict__ rt6,
                                   PnpResult* __restrict__ res) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
   int niters = max_iters, best = 0, best_it = -1, it = 0;
   while (it < niters) {
     if ((!valid || valid[it]) && counts[it] > max(best, 4)) {
@@ -339,20 +365,20 @@ __global__ void pnp_replay_kernel(const int* __restrict__ counts, const unsigned
 
 // Winner's inliers, ascending (single CTA, stable compaction); the test is re-evaluated with the
 // same arithmetic as the scoring kernel, so no H x N mask matrix has to exist.
-__global__ void __launch_bounds__(1024) pnp_inliers_kernel(const float* __restrict__ X, const float* __restrict__ px,
-                                                           int n, const double* __restrict__ poses, PnpCam cam,
-                                                           float thr2, PnpResult* __restrict__ res,
-                                                           int* __restrict__ inliers) {
+__device__ inline void pnp_inliers(const float* __restrict__ X, const float* __restrict__ px,
+                                   int n, const double* __restrict__ poses, PnpCam cam,
+                                   float thr2, PnpResult* __restrict__ res,
+                                   int* __restrict__ inliers) {
   __shared__ int warp_tot[32];
   __shared__ int base_s;
   __shared__ double P[12];
   const int best = res->best_iter;
-  if (best < 0) return;
+  if (best < 0) return;                       // uniform over the CTA
   if (threadIdx.x < 12) P[threadIdx.x] = poses[12 * (size_t)best + threadIdx.x];
   if (threadIdx.x == 0) base_s = 0;
   __syncthreads();
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  for (int start = 0; start < n; start += 1024) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int start = 0; start < n; start += blockDim.x) {
     int i = start + threadIdx.x;
     bool f = false;
     if (i < n) {
@@ -370,12 +396,13 @@ __global__ void __launch_bounds__(1024) pnp_inliers_kernel(const float* __restri
     __syncthreads();
     if (threadIdx.x == 0) {
       int tot = 0;
-      for (int k = 0; k < 32; ++k) tot += warp_tot[k];
+      for (int k = 0; k < nw; ++k) tot += warp_tot[k];
       base_s = base + tot;
     }
     __syncthreads();
   }
   if (threadIdx.x == 0) res->n_inliers = base_s;
+  __syncthreads();
 }
 
 // ------------------------------------------------------------------ LM refinement (SOLVEPNP_ITERATIVE)
@@ -392,6 +419,7 @@ struct PoseJac {
 __device__ inline void pose_jacobian_setup(const double* rv, PoseJac* pj) {
   hm::rodrigues_to_matrix(rv, pj->R);
   double th2 = rv[0] * rv[0] + rv[1] * rv[1] + rv[2] * rv[2];
+  const double inv_th2 = th2 < 1e-24 ? 0.0 : 1.0 / th2;
   const double* R = pj->R;
   for (int k = 0; k < 3; ++k) {
     double e[3] = {k == 0 ? 1.0 : 0.0, k == 1 ? 1.0 : 0.0, k == 2 ? 1.0 : 0.0};
@@ -408,7 +436,7 @@ __device__ inline void pose_jacobian_setup(const double* rv, PoseJac* pj) {
     S[0] = 0; S[1] = -a[2]; S[2] = a[1]; S[3] = a[2]; S[4] = 0; S[5] = -a[0]; S[6] = -a[1]; S[7] = a[0]; S[8] = 0;
     for (int i = 0; i < 3; ++i)
       for (int j = 0; j < 3; ++j)
-        pj->dR[k][3 * i + j] = (S[3 * i] * R[j] + S[3 * i + 1] * R[3 + j] + S[3 * i + 2] * R[6 + j]) / th2;
+        pj->dR[k][3 * i + j] = (S[3 * i] * R[j] + S[3 * i + 1] * R[3 + j] + S[3 * i + 2] * R[6 + j]) * inv_th2;
   }
 }
 
@@ -448,12 +476,12 @@ __device__ inline void solve6_damped(const double* a21, const double* b, double 
     double d = A[7 * j];
     for (int m = 0; m < j; ++m) d -= Lc[6 * j + m] * Lc[6 * j + m];
     if (!(d > 1e-14 * fabs(A[7 * j]))) { pd = false; break; }
-    double dj = sqrt(d);
-    Lc[7 * j] = dj;
+    const double rj = rsqrt(d);           // Lc[j][j] = d * rj; its reciprocal rj serves every later division
+    Lc[7 * j] = rj;                       // (the diagonal is stored inverted)
     for (int i = j + 1; i < 6; ++i) {
       double v = A[6 * i + j];
       for (int m = 0; m < j; ++m) v -= Lc[6 * i + m] * Lc[6 * j + m];
-      Lc[6 * i + j] = v / dj;
+      Lc[6 * i + j] = v * rj;
     }
   }
   if (pd) {
@@ -461,12 +489,12 @@ __device__ inline void solve6_damped(const double* a21, const double* b, double 
     for (int i = 0; i < 6; ++i) {
       double v = b[i];
       for (int m = 0; m < i; ++m) v -= Lc[6 * i + m] * y[m];
-      y[i] = v / Lc[7 * i];
+      y[i] = v * Lc[7 * i];
     }
     for (int i = 5; i >= 0; --i) {
       double v = y[i];
       for (int m = i + 1; m < 6; ++m) v -= Lc[6 * m + i] * x[m];
-      x[i] = v / Lc[7 * i];
+      x[i] = v * Lc[7 * i];
     }
     return;
   }
@@ -484,7 +512,15 @@ __device__ inline void solve6_damped(const double* a21, const double* b, double 
   }
 }
 
-__global__ void __launch_bounds__(REFINE_THREADS) pnp_refine_kernel(const float* __restrict__ X,
+// 10^k for the integer-valued log10(lambda) of OpenCV's LM schedule
+__device__ inline double pow10_int(double k) {
+  int n = __double2int_rn(k);
+  double r = 1.0, b = n < 0 ? 0.1 : 10.0;
+  for (int i = n < 0 ? -n : n; i > 0; --i) r *= b;
+  return r;
+}
+
+__device__ inline void pnp_refine(const float* __restrict__ X,
                                                                     const float* __restrict__ px,
                                                                     const int* __restrict__ inliers, PnpCam cam,
                                                                     int max_iter, PnpResult* __restrict__ res) {
@@ -560,7 +596,7 @@ __global__ void __launch_bounds__(REFINE_THREADS) pnp_refine_kernel(const float*
           lambda_lg10 += 1.0;
           if (lambda_lg10 <= 16.0) {               // reject: larger damping, same linearisation
             double dx[6];
-            solve6_damped(JtJ, JtE, exp(lambda_lg10 * log(10.0)), dx);
+            solve6_damped(JtJ, JtE, pow10_int(lambda_lg10), dx);
             for (int k = 0; k < 6; ++k) param[k] = prev_param[k] - dx[k];
             retry = true;
           }
@@ -579,7 +615,7 @@ __global__ void __launch_bounds__(REFINE_THREADS) pnp_refine_kernel(const float*
         for (int k = 0; k < 6; ++k) { JtE[k] = red[21 + k]; prev_param[k] = param[k]; }
         prev_err = err_norm;
         double dx[6];
-        solve6_damped(JtJ, JtE, exp(lambda_lg10 * log(10.0)), dx);
+        solve6_damped(JtJ, JtE, pow10_int(lambda_lg10), dx);
         for (int k = 0; k < 6; ++k) param[k] = prev_param[k] - dx[k];
         s_state = 1;
       }
@@ -590,6 +626,22 @@ __global__ void __launch_bounds__(REFINE_THREADS) pnp_refine_kernel(const float*
     for (int k = 0; k < 3; ++k) { res->rvec[k] = param[k]; res->tvec[k] = param[3 + k]; }
     res->refine_iters = iters;
   }
+}
+
+// Tail of the RANSAC in ONE single-CTA launch: replay of the stopping rule (thread 0), the winner's
+// inlier list (stable compaction), the LM refinement.
+__global__ void __launch_bounds__(REFINE_THREADS) pnp_finish_kernel(const float* __restrict__ X, const float* __restrict__ px,
+                                                                    int n, const int* __restrict__ counts,
+                                                                    const unsigned char* __restrict__ valid, int H,
+                                                                    double conf, const double* __restrict__ poses,
+                                                                    const double* __restrict__ rt6, PnpCam cam, float thr2,
+                                                                    int refine_iters, int* __restrict__ inliers,
+                                                                    PnpResult* __restrict__ res) {
+  if (threadIdx.x == 0) pnp_replay(counts, valid, n, H, conf, rt6, res);
+  __threadfence_block();
+  __syncthreads();
+  pnp_inliers(X, px, n, poses, cam, thr2, res, inliers);
+  if (refine_iters > 0) pnp_refine(X, px, inliers, cam, refine_iters, res);
 }
 
 static PnpCam make_pnp_cam(const double* K) {
@@ -695,22 +747,26 @@ static int pnp_ransac_impl(sfm_ctx* ctx, const float* X, const float* px, int n,
     PnpSubsets subs;
     subs.count = (n > 5 && H <= 100) ? H : 0;
     if (subs.count) ransac_subsets(n, subs.count, subs.idx);
-    SFM_LAUNCH(ctx, SFM_K_PNP_EPNP, (pnp_epnp_kernel<<<H, 32, 0, ctx->stream>>>(dX, dpx, n, H, cam, subs, dposes, drt6, dvalid)));
+    long long* dbg = nullptr;
+    if (getenv("SFM_PNP_TIMELINE")) SFM_TRY(ws_alloc_t(ctx, 8, &dbg));
+    SFM_LAUNCH(ctx, SFM_K_PNP_EPNP, (pnp_epnp_kernel<<<H, 32, 0, ctx->stream>>>(dX, dpx, n, H, cam, subs, dposes, drt6, dvalid, dbg)));
+    if (dbg) {   // diagnostics: phase boundaries of hypothesis 0 in SM clocks
+      long long hs[8];
+      SFM_CUDA(cudaMemcpyAsync(hs, dbg, sizeof(hs), cudaMemcpyDeviceToHost, ctx->stream));
+      SFM_CUDA(cudaStreamSynchronize(ctx->stream));
+      fprintf(stderr, "[epnp cycles] subset+alphas %lld | MtM %lld | jacobi %lld | L,rho %lld | candidates %lld | rodrigues+store %lld\n",
+              hs[1] - hs[0], hs[2] - hs[1], hs[3] - hs[2], hs[4] - hs[3], hs[5] - hs[4], hs[6] - hs[5]);
+    }
   }
   SFM_CUDA(cudaMemsetAsync(dcounts, 0, sizeof(int32_t) * H, ctx->stream));
   dim3 grid(div_up(n, 256), div_up(H, PNP_HG));
   // model_points == npoints (n == 5): OpenCV keeps all five points whatever their error
   const float thr2_eff = (n == 5) ? INFINITY : thr2;
   SFM_LAUNCH(ctx, SFM_K_PNP_SCORE, (pnp_score_kernel<<<grid, 256, 0, ctx->stream>>>(dX, dpx, n, dposes, dvalid, H, cam, thr2_eff, dcounts, nullptr)));
-  if (n == 5) {
-    // model_points == npoints: OpenCV returns the EPnP pose of all five points, all inliers, no refinement
-    SFM_LAUNCH(ctx, SFM_K_MISC, (pnp_replay_kernel<<<1, 32, 0, ctx->stream>>>(dcounts, nullptr, n, 1, confidence, drt6, dres)));
-  } else {
-    SFM_LAUNCH(ctx, SFM_K_MISC, (pnp_replay_kernel<<<1, 32, 0, ctx->stream>>>(dcounts, dvalid, n, H, confidence, drt6, dres)));
-  }
-  SFM_LAUNCH(ctx, SFM_K_MISC, (pnp_inliers_kernel<<<1, 1024, 0, ctx->stream>>>(dX, dpx, n, dposes, cam, thr2_eff, dres, dinl)));
-  if (n != 5)
-    SFM_LAUNCH(ctx, SFM_K_PNP_REFINE, (pnp_refine_kernel<<<1, REFINE_THREADS, 0, ctx->stream>>>(dX, dpx, dinl, cam, 20, dres)));
+  // model_points == npoints (n == 5): OpenCV returns the EPnP pose of all five points, all inliers, no refinement
+  SFM_LAUNCH(ctx, SFM_K_PNP_REFINE, (pnp_finish_kernel<<<1, REFINE_THREADS, 0, ctx->stream>>>(
+                                        dX, dpx, n, dcounts, n == 5 ? nullptr : dvalid, n == 5 ? 1 : H, confidence, dposes, drt6,
+                                        cam, thr2_eff, n == 5 ? 0 : 20, dinl, dres)));
   // ---- single copy back
   PnpResult* hres;
   int32_t* hinl;
