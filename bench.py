@@ -191,16 +191,18 @@ def run_engine(args):
     input_bytes = h2d_bytes
 
     def step(kps, dess, fetch: bool):
-        views = [pipeline.DeviceView(ctx, k, d) for k, d in zip(kps, dess)]      # K1b descriptor prep inside
-        chain = pipeline.RegistrationChain(ctx, K)
-        outs = chain.run(views, Rt0, Rt1)
-        d2h = 0
-        if fetch:                                                               # the step's result on the host
+        if fetch:
+            # end to end through the public host-array entry: chunked upload on a copy stream overlapping
+            # descriptor prep + batched match + registration (pipeline.register_host), clouds read back
+            outs = pipeline.register_host(ctx, K, kps, dess, Rt0, Rt1)
             with torch.cuda.stream(ts):
                 clouds = [o["X_new"][:o["n_new"]].to("cpu", non_blocking=True) for o in outs]
             ctx.sync()
-            d2h = sum(c.numel() * 4 for c in clouds) + len(outs) * (16 + 96)
-        return outs, d2h
+            return outs, sum(c.numel() * 4 for c in clouds) + len(outs) * (16 + 96)
+        views = [pipeline.DeviceView(ctx, k, d) for k, d in zip(kps, dess)]      # K1b descriptor prep inside
+        chain = pipeline.RegistrationChain(ctx, K)
+        outs = chain.run(views, Rt0, Rt1)
+        return outs, 0
 
     registered = V - 2
 
@@ -227,7 +229,8 @@ def run_engine(args):
         ms, wall, launches, _ = timed(kp_dev, des_dev, False, args.steps)
     value = world * registered * args.steps / (ms * 1e-3)
     # end to end: pinned host buffers in, clouds + poses out, through the public API
-    step(kp_host, des_host, True)
+    for _ in range(args.warmup):
+        step(kp_host, des_host, True)
     ms_e2e, _, _, d2h_bytes = timed(kp_host, des_host, True, args.steps)
     e2e = world * registered * args.steps / (ms_e2e * 1e-3)
 

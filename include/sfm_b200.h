@@ -173,6 +173,33 @@ int sfm_gather_rows(sfm_ctx* ctx, const float* src, int width, const int32_t* id
 int sfm_compact_pairs(sfm_ctx* ctx, const float* a, const float* b, const uint8_t* keep, int n,
                       float* a_out, float* b_out, int32_t* n_out);
 
+/* The whole per-view loop of sfm.py:341-409 (imread / SIFT / GUI removed) in one call: for the
+ * matches of consecutive pairs k = (view k, view k+1) — device arrays pts_q[k], pts_t[k] of
+ * n_match[k] rows, ascending queryIdx — bootstrap on pair 0 with the two given poses
+ * (sfm.py:304-339), then register views 2 .. n_pairs: re-triangulate, common_points, PnP-RANSAC,
+ * reprojection error, triangulate the new points.  X_new[v] (device, capacity n_match[v+1] x 3)
+ * receives view v+2's new points; out[v] (host) its pose, errors and counts. */
+typedef struct sfm_view_out {
+  double Rt[12];          /* [R|t] of the registered view, row-major 3x4 */
+  double err_pnp;         /* ReprojectionError on the PnP inliers     sfm.py:368 */
+  double err_new;         /* ReprojectionError on the new points      sfm.py:372 */
+  int32_t n_new, n_pnp, n_inl, n_match;
+} sfm_view_out;
+int sfm_chain_run(sfm_ctx* ctx, const double* K, const double* Rt0, const double* Rt1, int n_pairs,
+                  const float* const* pts_q, const float* const* pts_t, const int32_t* n_match,
+                  float* const* X_new, sfm_view_out* out);
+/* The same loop fed incrementally (pairs arrive while later views are still being uploaded and
+ * matched): create with the two bootstrap poses and an upper bound on matches per pair, then extend
+ * with consecutive pairs.  The first pair ever fed bootstraps the model; every other pair registers
+ * one view (X_new / out: one entry per view registered by that call, *n_registered says how many).
+ * The match arrays of the last pair fed must stay valid until the next call. */
+typedef struct sfm_chain sfm_chain;
+int sfm_chain_create(sfm_ctx* ctx, const double* K, const double* Rt0, const double* Rt1, int max_matches,
+                     sfm_chain** out);
+void sfm_chain_destroy(sfm_chain* chain);
+int sfm_chain_extend(sfm_chain* chain, int n_pairs, const float* const* pts_q, const float* const* pts_t,
+                     const int32_t* n_match, float* const* X_new, sfm_view_out* out, int32_t* n_registered);
+
 /* ------------------------------------------------------------------ hot path 3a: PnP-RANSAC
  * Replaces cv2.solvePnPRansac(X, p, K, d, ...) with OpenCV's defaults, which is what the
  * reference gets                                                sfm.py:67, test.py:319.

@@ -152,6 +152,15 @@ bool sfm_is_device_ptr(const void* p) {
   return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
 
+// Pinned (page-locked, UVA-mapped) host memory: kernels can store to it directly.
+bool sfm_is_pinned_ptr(const void* p) {
+  if (!p) return false;
+  cudaPointerAttributes a;
+  cudaError_t e = cudaPointerGetAttributes(&a, p);
+  if (e != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost && a.devicePointer != nullptr;
+}
+
 // ---------------------------------------------------------------------------- profiling
 static int drain_events(sfm_ctx* c) {
   if (c->pending.empty()) return SFM_OK;

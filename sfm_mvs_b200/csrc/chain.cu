@@ -3,7 +3,11 @@
 // keypoints, 3-D points and masks never travel to the host.
 //   pts2[indx2], points_3d[indx1]                     sfm.py:358-362   -> sfm_gather_rows
 //   temp_array1/2 = pts2[~mask], pts3[~mask]          sfm.py:229-237   -> sfm_compact_pairs
+#include <algorithm>
+#include <stdlib.h>
+
 #include "common.cuh"
+#include "hostmath.h"
 
 __global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ src, int width,
                                                           const int* __restrict__ idx, int n, float* __restrict__ dst) {
@@ -74,4 +78,214 @@ extern "C" int sfm_compact_pairs(sfm_ctx* ctx, const float* a, const float* b, c
   SFM_TRY(dev_out_finish(ctx, &on));
   if (host_out) SFM_CUDA(cudaStreamSynchronize(ctx->stream));
   return SFM_OK;
+}
+
+// ============================================================================ the per-view loop, native
+// sfm.py:341-409 (imread / SIFT / GUI removed) for a whole view sequence in ONE C call: the host side of
+// the loop — sizing, launching, reading back the two association counts and the PnP pose each view
+// needs before it can size the next launches — runs here instead of in the Python caller, so the GPU
+// is not left idle between a view's ~14 launches while an interpreter marshals arguments.
+// Matches of pair k = (view k, view k+1) are device arrays pts_q[k], pts_t[k] (n_match[k] rows,
+// ascending queryIdx: the output of sfm_desc_match_gather_batched).
+namespace {
+
+struct Arena {                 // chain-owned device scratch, sized for the largest pair
+  char* base = nullptr;
+  size_t cap = 0, off = 0;
+  template <typename T>
+  T* take(size_t count) {
+    size_t bytes = (count * sizeof(T) + 255) & ~(size_t)255;
+    if (off + bytes > cap) return nullptr;
+    T* p = reinterpret_cast<T*>(base + off);
+    off += bytes;
+    return p;
+  }
+};
+
+void matmul_K_Rt(const double* K, const double* Rt, double* P) {
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 4; ++j) P[4 * i + j] = K[3 * i] * Rt[j] + K[3 * i + 1] * Rt[4 + j] + K[3 * i + 2] * Rt[8 + j];
+}
+
+}  // namespace
+
+struct sfm_chain {
+  sfm_ctx* ctx = nullptr;
+  double K[9];
+  double P1[12], P2[12], Rt1[12];
+  int nmax = 0;
+  Arena ar;
+  float *X4 = nullptr, *pts3d_a = nullptr, *boot_pts1 = nullptr, *boot_p3d = nullptr, *temp1 = nullptr, *temp2 = nullptr,
+        *Xc = nullptr, *com2 = nullptr, *X_in = nullptr, *p_in = nullptr;
+  int32_t *i1 = nullptr, *i2 = nullptr, *inl = nullptr, *cnt = nullptr;
+  uint8_t* keep = nullptr;
+  double* errs = nullptr;          // device: 2 per call slot, ERR_SLOTS slots
+  int32_t* hcnt = nullptr;         // pinned
+  double* herrs = nullptr;         // pinned
+  // loop state (sfm.py:399-409)
+  bool started = false;
+  const float* prev_q = nullptr;   // previous pair's matches (re-triangulated for the next view)
+  const float* prev_t = nullptr;
+  int prev_n = 0;
+  const float* pts1 = nullptr;
+  const float* points_3d = nullptr;
+  int n1 = 0;
+  int views_done = 0;
+};
+constexpr int ERR_SLOTS = 4096;
+
+extern "C" int sfm_chain_create(sfm_ctx* ctx, const double* K, const double* Rt0, const double* Rt1, int max_matches,
+                                sfm_chain** out) {
+  SFM_REQUIRE(ctx && K && Rt0 && Rt1 && out && max_matches >= 6, "sfm_chain_create: bad argument");
+  sfm_chain* c = new sfm_chain();
+  c->ctx = ctx;
+  memcpy(c->K, K, sizeof(c->K));
+  memcpy(c->Rt1, Rt1, sizeof(c->Rt1));
+  matmul_K_Rt(K, Rt0, c->P1);
+  matmul_K_Rt(K, Rt1, c->P2);
+  const int nmax = c->nmax = max_matches;
+  c->ar.cap = (size_t)nmax * 160 + (size_t)ERR_SLOTS * 16 + 64 * 1024;
+  cudaError_t e = cudaMalloc(&c->ar.base, c->ar.cap);
+  if (e == cudaSuccess) e = cudaMallocHost(&c->hcnt, 4 * sizeof(int32_t));
+  if (e == cudaSuccess) e = cudaMallocHost(&c->herrs, sizeof(double) * 2 * ERR_SLOTS);
+  if (e != cudaSuccess) {
+    sfm_set_error("sfm_chain_create: %s", cudaGetErrorString(e));
+    sfm_chain_destroy(c);
+    return SFM_ERR_NOMEM;
+  }
+  Arena& ar = c->ar;
+  c->X4 = ar.take<float>((size_t)4 * nmax);          // triangulated points (N,4)
+  c->pts3d_a = ar.take<float>((size_t)3 * nmax);     // points_3d of the previous pair
+  c->boot_pts1 = ar.take<float>((size_t)2 * nmax);
+  c->boot_p3d = ar.take<float>((size_t)3 * nmax);
+  c->i1 = ar.take<int32_t>(nmax);
+  c->i2 = ar.take<int32_t>(nmax);
+  c->keep = ar.take<uint8_t>(nmax);
+  c->temp1 = ar.take<float>((size_t)2 * nmax);
+  c->temp2 = ar.take<float>((size_t)2 * nmax);
+  c->Xc = ar.take<float>((size_t)3 * nmax);
+  c->com2 = ar.take<float>((size_t)2 * nmax);
+  c->X_in = ar.take<float>((size_t)3 * nmax);
+  c->p_in = ar.take<float>((size_t)2 * nmax);
+  c->inl = ar.take<int32_t>(nmax);
+  c->cnt = ar.take<int32_t>(4);
+  c->errs = ar.take<double>((size_t)2 * ERR_SLOTS);
+  if (!c->errs) {
+    sfm_set_error("sfm_chain_create: arena too small");
+    sfm_chain_destroy(c);
+    return SFM_ERR_NOMEM;
+  }
+  *out = c;
+  return SFM_OK;
+}
+
+extern "C" void sfm_chain_destroy(sfm_chain* c) {
+  if (!c) return;
+  if (c->ctx) cudaStreamSynchronize(c->ctx->stream);
+  if (c->ar.base) cudaFree(c->ar.base);
+  if (c->hcnt) cudaFreeHost(c->hcnt);
+  if (c->herrs) cudaFreeHost(c->herrs);
+  delete c;
+}
+
+// Feed the next n_pairs consecutive pairs.  The very first pair bootstraps the model (no view is
+// registered by it); every further pair registers one view: out / X_new have one entry per registered
+// view of THIS call.  The match arrays of the last pair must stay alive until the next call (they are
+// re-triangulated against the next view, sfm.py:348-352).
+extern "C" int sfm_chain_extend(sfm_chain* c, int n_pairs, const float* const* pts_q, const float* const* pts_t,
+                                const int32_t* n_match, float* const* X_new, sfm_view_out* out, int32_t* n_registered) {
+  SFM_REQUIRE(c && n_pairs >= 0 && (n_pairs == 0 || (pts_q && pts_t && n_match)), "sfm_chain_extend: null argument");
+  sfm_ctx* ctx = c->ctx;
+  const double* K = c->K;
+  int reg = 0;
+  if (n_registered) *n_registered = 0;
+  for (int k = 0; k < n_pairs; ++k)
+    SFM_REQUIRE(n_match[k] >= 6 && n_match[k] <= c->nmax, "sfm_chain_extend: pair %d has %d matches (need 6..%d)", k, n_match[k], c->nmax);
+  const int n_views = n_pairs - (c->started ? 0 : 1);
+  SFM_REQUIRE(n_views <= 0 || (X_new && out), "sfm_chain_extend: output arrays missing");
+  SFM_REQUIRE(n_views < ERR_SLOTS, "sfm_chain_extend: at most %d views per call", ERR_SLOTS - 1);
+  if (n_pairs == 0) return SFM_OK;
+  SFM_CUDA(cudaMemsetAsync(c->errs, 0, sizeof(double) * 2 * (size_t)(n_views > 0 ? n_views : 1), ctx->stream));
+  int k0 = 0;
+  if (!c->started) {
+    // ---- state when the reference's loop starts (sfm.py:304-339; the second pose is given)
+    const int M = n_match[0];
+    SFM_TRY(sfm_triangulate(ctx, c->P1, c->P2, pts_q[0], pts_t[0], M, 1, c->X4, 1, 1));
+    SFM_TRY(sfm_reproj_error(ctx, c->X4, 2, pts_t[0], 1, M, c->Rt1, K, c->errs + 2 * (ERR_SLOTS - 1), nullptr, c->Xc));
+    double rvec[3], tvec[3];
+    int32_t ni = 0, ok = 0;
+    SFM_TRY(sfm_pnp_ransac(ctx, c->Xc, pts_t[0], M, K, 100, 8.0f, 0.99, rvec, tvec, c->inl, &ni, &ok, nullptr));
+    SFM_REQUIRE(ok && ni >= 1, "registration failed: solvePnPRansac found no consensus on the first pair");
+    SFM_TRY(sfm_gather_rows(ctx, pts_t[0], 2, c->inl, ni, c->boot_pts1));
+    SFM_TRY(sfm_gather_rows(ctx, c->Xc, 3, c->inl, ni, c->boot_p3d));
+    c->pts1 = c->boot_pts1; c->points_3d = c->boot_p3d; c->n1 = ni;
+    c->prev_q = nullptr; c->prev_t = nullptr; c->prev_n = 0;
+    c->started = true;
+    k0 = 1;
+  }
+  for (int k = k0; k < n_pairs; ++k, ++reg) {
+    const int M = n_match[k];
+    const float* q = pts_q[k];
+    const float* t = pts_t[k];
+    if (c->prev_q) {                                     // re-triangulate the previous pair's matches (sfm.py:348-352)
+      c->n1 = c->prev_n;
+      c->pts1 = c->prev_t;
+      SFM_TRY(sfm_triangulate(ctx, c->P1, c->P2, c->prev_q, c->prev_t, c->n1, 1, c->pts3d_a, 2, 1));
+      c->points_3d = c->pts3d_a;
+    }
+    // data association (sfm.py:356) and the complement (new points)
+    SFM_TRY(sfm_common_points(ctx, c->pts1, c->n1, q, M, c->i1, c->i2, c->cnt, c->keep));
+    SFM_TRY(sfm_compact_pairs(ctx, q, t, c->keep, M, c->temp1, c->temp2, c->cnt + 1));
+    SFM_CUDA(cudaMemcpyAsync(c->hcnt, c->cnt, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    SFM_CUDA(cudaStreamSynchronize(ctx->stream));
+    const int nc = c->hcnt[0], m = c->hcnt[1];
+    SFM_REQUIRE(nc >= 6, "registration failed: view %d shares %d points with the model", c->views_done + 2, nc);
+    SFM_TRY(sfm_gather_rows(ctx, c->points_3d, 3, c->i1, nc, c->Xc));
+    SFM_TRY(sfm_gather_rows(ctx, t, 2, c->i2, nc, c->com2));
+    double rvec[3], tvec[3];
+    int32_t ki = 0, ok = 0;
+    SFM_TRY(sfm_pnp_ransac(ctx, c->Xc, c->com2, nc, K, 100, 8.0f, 0.99, rvec, tvec, c->inl, &ki, &ok, nullptr));   // sfm.py:362
+    SFM_REQUIRE(ok, "registration failed: solvePnPRansac found no consensus (view %d)", c->views_done + 2);
+    sfm_view_out& o = out[reg];
+    double R[9];
+    hm::rodrigues_to_matrix(rvec, R);
+    for (int i = 0; i < 3; ++i) { o.Rt[4 * i] = R[3 * i]; o.Rt[4 * i + 1] = R[3 * i + 1]; o.Rt[4 * i + 2] = R[3 * i + 2]; o.Rt[4 * i + 3] = tvec[i]; }
+    double Pnew[12];
+    matmul_K_Rt(K, o.Rt, Pnew);
+    if (ki > 0) {
+      SFM_TRY(sfm_gather_rows(ctx, c->Xc, 3, c->inl, ki, c->X_in));
+      SFM_TRY(sfm_gather_rows(ctx, c->com2, 2, c->inl, ki, c->p_in));
+      SFM_TRY(sfm_reproj_error(ctx, c->X_in, 0, c->p_in, 1, ki, o.Rt, K, c->errs + 2 * reg, nullptr, nullptr));     // sfm.py:368
+    }
+    if (m > 0) {
+      SFM_TRY(sfm_triangulate(ctx, c->P2, Pnew, c->temp1, c->temp2, m, 1, c->X4, 1, 1));                            // sfm.py:371
+      SFM_TRY(sfm_reproj_error(ctx, c->X4, 2, c->temp2, 1, m, o.Rt, K, c->errs + 2 * reg + 1, nullptr, X_new[reg])); // sfm.py:372
+    }
+    o.n_new = m; o.n_pnp = nc; o.n_inl = ki; o.n_match = M;
+    o.err_pnp = o.err_new = 0.0;
+    memcpy(c->P1, c->P2, sizeof(c->P1));
+    memcpy(c->P2, Pnew, sizeof(c->P2));
+    c->prev_q = q; c->prev_t = t; c->prev_n = M;
+    c->views_done += 1;
+  }
+  if (reg > 0) {
+    SFM_CUDA(cudaMemcpyAsync(c->herrs, c->errs, sizeof(double) * 2 * reg, cudaMemcpyDeviceToHost, ctx->stream));
+    SFM_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int v = 0; v < reg; ++v) { out[v].err_pnp = c->herrs[2 * v]; out[v].err_new = c->herrs[2 * v + 1]; }
+  }
+  if (n_registered) *n_registered = reg;
+  return SFM_OK;
+}
+
+extern "C" int sfm_chain_run(sfm_ctx* ctx, const double* K, const double* Rt0, const double* Rt1, int n_pairs,
+                             const float* const* pts_q, const float* const* pts_t, const int32_t* n_match,
+                             float* const* X_new, sfm_view_out* out) {
+  SFM_REQUIRE(ctx && K && Rt0 && Rt1 && n_pairs >= 1 && pts_q && pts_t && n_match, "sfm_chain_run: null argument");
+  int nmax = 6;
+  for (int k = 0; k < n_pairs; ++k) nmax = std::max(nmax, n_match[k]);
+  sfm_chain* c = nullptr;
+  SFM_TRY(sfm_chain_create(ctx, K, Rt0, Rt1, nmax, &c));
+  int s = sfm_chain_extend(c, n_pairs, pts_q, pts_t, n_match, X_new, out, nullptr);
+  sfm_chain_destroy(c);
+  return s;
 }

@@ -85,6 +85,7 @@ static inline int hs_alloc_t(sfm_ctx* c, size_t count, T** out) {
 }
 
 bool sfm_is_device_ptr(const void* p);
+bool sfm_is_pinned_ptr(const void* p);
 
 // An input that must be readable by kernels: device pointers pass through, host buffers are
 // copied into the workspace on the ctx stream.

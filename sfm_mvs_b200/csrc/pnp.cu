@@ -763,24 +763,25 @@ static int pnp_ransac_impl(sfm_ctx* ctx, const float* X, const float* px, int n,
   // model_points == npoints (n == 5): OpenCV keeps all five points whatever their error
   const float thr2_eff = (n == 5) ? INFINITY : thr2;
   SFM_LAUNCH(ctx, SFM_K_PNP_SCORE, (pnp_score_kernel<<<grid, 256, 0, ctx->stream>>>(dX, dpx, n, dposes, dvalid, H, cam, thr2_eff, dcounts, nullptr)));
-  // model_points == npoints (n == 5): OpenCV returns the EPnP pose of all five points, all inliers, no refinement
-  SFM_LAUNCH(ctx, SFM_K_PNP_REFINE, (pnp_finish_kernel<<<1, REFINE_THREADS, 0, ctx->stream>>>(
-                                        dX, dpx, n, dcounts, n == 5 ? nullptr : dvalid, n == 5 ? 1 : H, confidence, dposes, drt6,
-                                        cam, thr2_eff, n == 5 ? 0 : 20, dinl, dres)));
-  // ---- single copy back
   PnpResult* hres;
   int32_t* hinl;
   SFM_TRY(hs_alloc_t(ctx, 1, &hres));
   SFM_TRY(hs_alloc_t(ctx, (size_t)n, &hinl));
+  // model_points == npoints (n == 5): OpenCV returns the EPnP pose of all five points, all inliers, no refinement
+  SFM_LAUNCH(ctx, SFM_K_PNP_REFINE, (pnp_finish_kernel<<<1, REFINE_THREADS, 0, ctx->stream>>>(
+                                        dX, dpx, n, dcounts, n == 5 ? nullptr : dvalid, n == 5 ? 1 : H, confidence, dposes, drt6,
+                                        cam, thr2_eff, n == 5 ? 0 : 20, dinl, dres)));
+  // ---- single copy back (the inlier list only when the caller wants it on the host)
   SFM_CUDA(cudaMemcpyAsync(hres, dres, sizeof(PnpResult), cudaMemcpyDeviceToHost, ctx->stream));
-  if (inliers) SFM_CUDA(cudaMemcpyAsync(hinl, dinl, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  const bool inl_host = inliers && !sfm_is_device_ptr(inliers);
+  if (inl_host) SFM_CUDA(cudaMemcpyAsync(hinl, dinl, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
   SFM_CUDA(cudaStreamSynchronize(ctx->stream));
   *ok = hres->ok;
   for (int k = 0; k < 3; ++k) { rvec[k] = hres->rvec[k]; tvec[k] = hres->tvec[k]; }
   int ni = hres->ok ? hres->n_inliers : 0;
   if (n_inliers) *n_inliers = ni;
   if (inliers && ni > 0) {
-    if (sfm_is_device_ptr(inliers)) SFM_CUDA(cudaMemcpyAsync(inliers, dinl, sizeof(int32_t) * ni, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (!inl_host) SFM_CUDA(cudaMemcpyAsync(inliers, dinl, sizeof(int32_t) * ni, cudaMemcpyDeviceToDevice, ctx->stream));
     else memcpy(inliers, hinl, sizeof(int32_t) * ni);
   }
   if (info) {

@@ -45,6 +45,11 @@ class DeviceView:
         self.desc = ctx.descriptors(des)
 
 
+# sfm_view_out (include/sfm_b200.h)
+VIEW_OUT = np.dtype([("Rt", np.float64, (12,)), ("err_pnp", np.float64), ("err_new", np.float64),
+                     ("n_new", np.int32), ("n_pnp", np.int32), ("n_inl", np.int32), ("n_match", np.int32)])
+
+
 class PairMatches:
     __slots__ = ("pts_q", "pts_t", "qidx", "tidx", "n_dev", "n")
 
@@ -210,10 +215,14 @@ class RegistrationChain:
     @_on_ctx_stream
     def run(self, views, Rt0, Rt1, matches=None):
         """Register views[2:] sequentially.  `views` are DeviceView.  Returns per-view dicts with host
-        values (Rt, err_pnp, err_new, counts) and device X_new."""
+        values (Rt, err_pnp, err_new, counts) and device X_new.  The loop itself runs in the library
+        (sfm_chain_run); the Python loop below is kept for the parity mode in which the caller supplies
+        the minimal solutions (hypothesis_fn)."""
         V = len(views)
         if matches is None:
             matches = self.match_pairs(views, [(i, i + 1) for i in range(V - 1)])
+        if self.hypothesis_fn is None and V >= 3:
+            return self._run_native(matches, Rt0, Rt1)
         self.bootstrap(views, Rt0, Rt1, matches[0])
         outs = []
         for i in range(V - 2):
@@ -225,6 +234,114 @@ class RegistrationChain:
                 o["err_pnp"], o["err_new"] = float(e[0]), float(e[1])
         return outs
 
+    def _run_native(self, matches, Rt0, Rt1):
+        nc = NativeChain(self.ctx, self.K, Rt0, Rt1, max(pm.n for pm in matches))
+        try:
+            return nc.extend(matches)
+        finally:
+            nc.close()
+
+
+class NativeChain:
+    """sfm_chain_create / sfm_chain_extend / sfm_chain_destroy: the per-view loop running in the library,
+    fed with consecutive pairs' matches (PairMatches) as they become available."""
+
+    def __init__(self, ctx: _e.Context, K, Rt0, Rt1, max_matches: int):
+        self.ctx = ctx
+        self._h = C.c_void_p()
+        K = np.ascontiguousarray(K, np.float64)
+        Rt0 = np.ascontiguousarray(Rt0, np.float64)
+        Rt1 = np.ascontiguousarray(Rt1, np.float64)
+        check(lib.sfm_chain_create(ctx._h, _e._dptr(K), _e._dptr(Rt0), _e._dptr(Rt1), int(max(max_matches, 6)), C.byref(self._h)))
+        self._alive = []          # match arrays of the last pair must outlive the next extend()
+        self._fed = 0
+
+    def extend(self, matches):
+        import torch
+        n_pairs = len(matches)
+        if n_pairs == 0:
+            return []
+        first = self._fed == 0
+        n = np.array([pm.n for pm in matches], np.int32)
+        reg_n = n[1:] if first else n                      # matches of the pairs that register a view
+        cap = np.maximum(reg_n, 1).astype(np.int64)
+        off = np.concatenate([[0], np.cumsum(cap)])
+        with torch.cuda.stream(self.ctx.torch_stream()):
+            X_all = torch.empty((int(max(off[-1], 1)), 3), dtype=torch.float32, device=self.ctx.torch_device)
+        pq = np.array([pm.pts_q.data_ptr() for pm in matches], np.uint64)
+        pt = np.array([pm.pts_t.data_ptr() for pm in matches], np.uint64)
+        xn = np.ascontiguousarray(X_all.data_ptr() + off[:-1] * 12, np.uint64)
+        out = np.zeros((max(len(reg_n), 1),), dtype=VIEW_OUT)
+        nreg = C.c_int32(0)
+        check(lib.sfm_chain_extend(self._h, n_pairs, pq.ctypes.data, pt.ctypes.data, n.ctypes.data, xn.ctypes.data,
+                                   out.ctypes.data, C.byref(nreg)))
+        self._alive = [matches[-1], X_all]
+        self._fed += n_pairs
+        outs = []
+        for v in range(nreg.value):
+            o = out[v]
+            outs.append(dict(Rt=o["Rt"].reshape(3, 4).copy(), X_new=X_all[int(off[v]):int(off[v + 1])], n_new=int(o["n_new"]),
+                             n_pnp=int(o["n_pnp"]), n_inl=int(o["n_inl"]), n_match=int(o["n_match"]),
+                             err_pnp=float(o["err_pnp"]), err_new=float(o["err_new"])))
+        return outs
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib.sfm_chain_destroy(self._h)
+            self._h = None
+        self._alive = []
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def register_host(ctx: _e.Context, K, kps, dess, Rt0, Rt1, chunk: int = 25, ratio: float = 0.70):
+    """Host arrays in, registered views out — the call a user makes with a sequence of views whose keypoints
+    (n,2) and descriptors (n,128) sit in host memory (numpy arrays or torch CPU tensors; pinned memory lets the
+    upload overlap).  Views are uploaded on a copy stream in chunks; descriptor preparation, the batched match
+    of a chunk's pairs and the registration of its views run on the engine stream while later chunks are
+    still crossing PCIe."""
+    import torch
+    V = len(kps)
+    dev = ctx.torch_device
+    ts = ctx.torch_stream()
+    as_t = lambda a: a if _e._is_torch(a) else torch.from_numpy(np.ascontiguousarray(a))
+    kps = [as_t(a) for a in kps]
+    dess = [as_t(a) for a in dess]
+    cs = torch.cuda.Stream(device=dev)
+    bounds = [(lo, min(lo + chunk, V)) for lo in range(0, V, chunk)]
+    kp_d, des_d, events = [None] * V, [None] * V, []
+    with torch.cuda.stream(cs):
+        for lo, hi in bounds:
+            for i in range(lo, hi):
+                kp_d[i] = kps[i].to(dev, non_blocking=True)
+                des_d[i] = dess[i].to(dev, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(cs)
+            events.append(ev)
+    chain = RegistrationChain(ctx, K, ratio=ratio)
+    native = NativeChain(ctx, K, Rt0, Rt1, max(int(k.shape[0]) for k in kps))
+    views, outs, keep = [], [], []
+    try:
+        for (lo, hi), ev in zip(bounds, events):
+            ts.wait_event(ev)
+            views += [DeviceView(ctx, kp_d[i], des_d[i]) for i in range(lo, hi)]
+            pairs = [(i, i + 1) for i in range(max(lo - 1, 0), hi - 1)]
+            if not pairs:
+                continue
+            matches = chain.match_pairs(views, pairs)
+            keep.append(matches)
+            outs += native.extend(matches)
+        ctx.sync()
+    finally:
+        native.close()
+    for o in outs:
+        o["_keep"] = (kp_d, des_d)      # uploaded on the copy stream: stay referenced until the caller drops the result
+    return outs
+
 
 def register_chain(scene, ctx: _e.Context | None = None, n_views: int | None = None, hypothesis_fn=None,
                    des_dtype=np.float32):
@@ -233,13 +350,18 @@ def register_chain(scene, ctx: _e.Context | None = None, n_views: int | None = N
     from .cv2_compat import default_context
     ctx = ctx or default_context()
     views = scene["views"] if n_views is None else scene["views"][:n_views]
-    dviews = [DeviceView(ctx, v["kp"], v["des"].astype(des_dtype, copy=False)) for v in views]
     Rt0 = np.hstack([views[0]["R"], views[0]["t"].reshape(3, 1)])
     Rt1 = np.hstack([views[1]["R"], views[1]["t"].reshape(3, 1)])
-    chain = RegistrationChain(ctx, scene["K"], hypothesis_fn=hypothesis_fn)
-    outs = chain.run(dviews, Rt0, Rt1)
     import torch
+    if hypothesis_fn is None and len(views) >= 3:
+        outs = register_host(ctx, scene["K"], [v["kp"] for v in views],
+                             [v["des"].astype(des_dtype, copy=False) for v in views], Rt0, Rt1)
+    else:
+        dviews = [DeviceView(ctx, v["kp"], v["des"].astype(des_dtype, copy=False)) for v in views]
+        chain = RegistrationChain(ctx, scene["K"], hypothesis_fn=hypothesis_fn)
+        outs = chain.run(dviews, Rt0, Rt1)
     with torch.cuda.stream(ctx.torch_stream()):
         for o in outs:
             o["X_new"] = o["X_new"][:o["n_new"]].cpu().numpy()
+            o.pop("_keep", None)
     return outs

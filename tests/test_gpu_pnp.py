@@ -170,3 +170,32 @@ def test_registration_chain_gpu_minimal_solver(engine):
         assert np.abs(o["Rt"][:, :3] - Rt_gt[:, :3]).max() < 5e-3
         assert np.abs(o["Rt"][:, 3] - Rt_gt[:, 3]).max() < 5e-2
         assert o["err_new"] < 0.05 and o["n_inl"] > 0.8 * o["n_pnp"]
+
+
+def test_native_and_streamed_chain_equal_the_python_loop(engine):
+    """sfm_chain_run (the loop in the library) and register_host (chunked upload + sfm_chain_extend) launch the
+    same kernels in the same order as the Python loop: identical poses, counts, errors and new points."""
+    import torch
+    from sfm_mvs_b200 import pipeline
+    scene = synth.orbit_scene(9, 1200, seed=7)
+    K = scene["K"]
+    Rt0 = np.hstack([scene["views"][0]["R"], scene["views"][0]["t"]])
+    Rt1 = np.hstack([scene["views"][1]["R"], scene["views"][1]["t"]])
+    views = [pipeline.DeviceView(engine, v["kp"], v["des"]) for v in scene["views"]]
+    chain = pipeline.RegistrationChain(engine, K)
+    matches = chain.match_pairs(views, [(i, i + 1) for i in range(len(views) - 1)])
+    # Python loop
+    chain.bootstrap(views, Rt0, Rt1, matches[0])
+    py = [chain.register(matches[i] if i > 0 else None, matches[i + 1], first=(i == 0)) for i in range(len(views) - 2)]
+    engine.sync()
+    native = chain.run(views, Rt0, Rt1, matches=matches)
+    streamed = pipeline.register_host(engine, K, [v["kp"] for v in scene["views"]], [v["des"] for v in scene["views"]],
+                                      Rt0, Rt1, chunk=4)
+    assert len(py) == len(native) == len(streamed) == 7
+    for a, b, c in zip(py, native, streamed):
+        e = a["errs"].cpu().numpy()
+        for o in (b, c):
+            assert (o["n_match"], o["n_pnp"], o["n_inl"], o["n_new"]) == (a["n_match"], a["n_pnp"], a["n_inl"], a["n_new"])
+            assert np.array_equal(o["Rt"], a["Rt"])
+            assert o["err_pnp"] == e[0] and o["err_new"] == e[1]
+            assert torch.equal(o["X_new"][:o["n_new"]], a["X_new"][:a["n_new"]])
