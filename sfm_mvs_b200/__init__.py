@@ -14,3 +14,4 @@ from .cv2_compat import (NORM_L2, RATIO, SOLVEPNP_ITERATIVE, BFMatcher, BundleAd
 from . import ba  # noqa: F401
 
 __version__ = "0.1.0"
+from .io import to_ply, save_poses, load_poses, load_ply  # noqa: E402,F401  (sfm.py:169-201, :423)
