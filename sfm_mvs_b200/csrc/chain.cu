@@ -7,10 +7,13 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "chain_dev.cuh"
 #include "hostmath.h"
 
 __global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ src, int width,
-                                                          const int* __restrict__ idx, int n, float* __restrict__ dst) {
+                                                          const int* __restrict__ idx, int n, float* __restrict__ dst,
+                                                          const int* __restrict__ n_dev = nullptr) {
+  if (n_dev) n = min(n, *n_dev);
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n * width) return;
   int r = i / width, c = i - r * width;
@@ -24,6 +27,12 @@ extern "C" int sfm_gather_rows(sfm_ctx* ctx, const float* src, int width, const 
   SFM_REQUIRE(sfm_is_device_ptr(src) && sfm_is_device_ptr(idx) && sfm_is_device_ptr(dst),
               "sfm_gather_rows: device pointers only (host arrays are indexed by the caller)");
   SFM_LAUNCH(ctx, SFM_K_GATHER, (gather_rows_kernel<<<div_up(n * width, 256), 256, 0, ctx->stream>>>(src, width, idx, n, dst)));
+  return SFM_OK;
+}
+
+int sfm_gather_rows_dev(sfm_ctx* ctx, const float* src, int width, const int32_t* idx, int n_cap, const int* n_dev, float* dst) {
+  if (n_cap <= 0) return SFM_OK;
+  SFM_LAUNCH(ctx, SFM_K_GATHER, (gather_rows_kernel<<<div_up(n_cap * width, 256), 256, 0, ctx->stream>>>(src, width, idx, n_cap, dst, n_dev)));
   return SFM_OK;
 }
 
@@ -120,6 +129,13 @@ struct sfm_chain {
   int32_t *i1 = nullptr, *i2 = nullptr, *inl = nullptr, *cnt = nullptr;
   uint8_t* keep = nullptr;
   double* errs = nullptr;          // device: 2 per call slot, ERR_SLOTS slots
+  // synchronisation-free path: everything a view produces stays in HBM until the end of the call
+  struct ViewRec* recs = nullptr;  // [ERR_SLOTS]   per registered view of a call
+  double* P_view = nullptr;        // [ERR_SLOTS+2][12]  projection matrix K[R|t] of every view so far
+  CamParams* cams = nullptr;       // [ERR_SLOTS]   projectPoints operands of the view registered in that slot
+  double* pose6 = nullptr;         // rvec | tvec of the PnP just run
+  double* K_dev = nullptr;
+  struct ViewRec* hrecs = nullptr; // pinned
   int32_t* hcnt = nullptr;         // pinned
   double* herrs = nullptr;         // pinned
   // loop state (sfm.py:399-409)
@@ -134,6 +150,12 @@ struct sfm_chain {
 };
 constexpr int ERR_SLOTS = 4096;
 
+struct ViewRec {                  // device-side result record of one registered view
+  double Rt[12];
+  double err_pnp, err_new;
+  int n_new, n_pnp, n_inl, ok;
+};
+
 extern "C" int sfm_chain_create(sfm_ctx* ctx, const double* K, const double* Rt0, const double* Rt1, int max_matches,
                                 sfm_chain** out) {
   SFM_REQUIRE(ctx && K && Rt0 && Rt1 && out && max_matches >= 6, "sfm_chain_create: bad argument");
@@ -144,10 +166,11 @@ extern "C" int sfm_chain_create(sfm_ctx* ctx, const double* K, const double* Rt0
   matmul_K_Rt(K, Rt0, c->P1);
   matmul_K_Rt(K, Rt1, c->P2);
   const int nmax = c->nmax = max_matches;
-  c->ar.cap = (size_t)nmax * 160 + (size_t)ERR_SLOTS * 16 + 64 * 1024;
+  c->ar.cap = (size_t)nmax * 160 + (size_t)ERR_SLOTS * (16 + sizeof(ViewRec) + 96 + sizeof(CamParams)) + 64 * 1024;
   cudaError_t e = cudaMalloc(&c->ar.base, c->ar.cap);
   if (e == cudaSuccess) e = cudaMallocHost(&c->hcnt, 4 * sizeof(int32_t));
   if (e == cudaSuccess) e = cudaMallocHost(&c->herrs, sizeof(double) * 2 * ERR_SLOTS);
+  if (e == cudaSuccess) e = cudaMallocHost(&c->hrecs, sizeof(ViewRec) * ERR_SLOTS);
   if (e != cudaSuccess) {
     sfm_set_error("sfm_chain_create: %s", cudaGetErrorString(e));
     sfm_chain_destroy(c);
@@ -170,7 +193,18 @@ extern "C" int sfm_chain_create(sfm_ctx* ctx, const double* K, const double* Rt0
   c->inl = ar.take<int32_t>(nmax);
   c->cnt = ar.take<int32_t>(4);
   c->errs = ar.take<double>((size_t)2 * ERR_SLOTS);
-  if (!c->errs) {
+  c->recs = ar.take<ViewRec>(ERR_SLOTS);
+  c->P_view = ar.take<double>((size_t)12 * (ERR_SLOTS + 2));
+  c->cams = ar.take<CamParams>(ERR_SLOTS);
+  c->pose6 = ar.take<double>(16);
+  double* Kdev = ar.take<double>(16);
+  if (Kdev) {
+    c->K_dev = Kdev;
+    cudaMemcpy(Kdev, K, 9 * sizeof(double), cudaMemcpyHostToDevice);
+    cudaMemcpy(c->P_view, c->P1, 12 * sizeof(double), cudaMemcpyHostToDevice);
+    cudaMemcpy(c->P_view + 12, c->P2, 12 * sizeof(double), cudaMemcpyHostToDevice);
+  }
+  if (!Kdev) {
     sfm_set_error("sfm_chain_create: arena too small");
     sfm_chain_destroy(c);
     return SFM_ERR_NOMEM;
@@ -185,6 +219,7 @@ extern "C" void sfm_chain_destroy(sfm_chain* c) {
   if (c->ar.base) cudaFree(c->ar.base);
   if (c->hcnt) cudaFreeHost(c->hcnt);
   if (c->herrs) cudaFreeHost(c->herrs);
+  if (c->hrecs) cudaFreeHost(c->hrecs);
   delete c;
 }
 
@@ -222,6 +257,52 @@ extern "C" int sfm_chain_extend(sfm_chain* c, int n_pairs, const float* const* p
     c->prev_q = nullptr; c->prev_t = nullptr; c->prev_n = 0;
     c->started = true;
     k0 = 1;
+  }
+  const bool sync_free = getenv("SFM_CHAIN_SYNC") == nullptr;
+  if (sync_free && n_views > 0) {
+    // ---- no host round trip inside the loop: counts, poses and matrices are produced and consumed in HBM
+    SFM_REQUIRE(c->views_done + n_views < ERR_SLOTS, "sfm_chain_extend: more than %d views in one chain", ERR_SLOTS);
+    SFM_CUDA(cudaMemsetAsync(c->recs, 0, sizeof(ViewRec) * (size_t)n_views, ctx->stream));
+    for (int k = k0; k < n_pairs; ++k, ++reg) {
+      const int M = n_match[k];
+      const float* q = pts_q[k];
+      const float* t = pts_t[k];
+      const int g = c->views_done;                         // views g, g+1 are the previous pair; g+2 is registered now
+      ViewRec* rec = c->recs + reg;
+      if (c->prev_q) {                                     // re-triangulate the previous pair's matches (sfm.py:348-352)
+        c->n1 = c->prev_n;
+        c->pts1 = c->prev_t;
+        SFM_TRY(sfm_triangulate_dev(ctx, c->P_view + 12 * (size_t)g, c->prev_q, c->prev_t, c->n1, nullptr, c->pts3d_a, 2));
+        c->points_3d = c->pts3d_a;
+      }
+      const int n1 = c->n1;
+      SFM_TRY(sfm_common_points(ctx, c->pts1, n1, q, M, c->i1, c->i2, &rec->n_pnp, c->keep));          // sfm.py:356
+      SFM_TRY(sfm_compact_pairs(ctx, q, t, c->keep, M, c->temp1, c->temp2, &rec->n_new));
+      SFM_TRY(sfm_gather_rows_dev(ctx, c->points_3d, 3, c->i1, n1, &rec->n_pnp, c->Xc));
+      SFM_TRY(sfm_gather_rows_dev(ctx, t, 2, c->i2, n1, &rec->n_pnp, c->com2));
+      SFM_TRY(sfm_pnp_ransac_dev(ctx, c->Xc, c->com2, n1, &rec->n_pnp, K, c->K_dev, c->pose6, c->inl, &rec->n_inl, &rec->ok,
+                                 rec->Rt, c->P_view + 12 * (size_t)(g + 2), c->cams + reg));                        // sfm.py:362
+      SFM_TRY(sfm_gather_rows_dev(ctx, c->Xc, 3, c->inl, n1, &rec->n_inl, c->X_in));
+      SFM_TRY(sfm_gather_rows_dev(ctx, c->com2, 2, c->inl, n1, &rec->n_inl, c->p_in));
+      SFM_TRY(sfm_reproj_error_dev(ctx, c->X_in, 0, c->p_in, n1, &rec->n_inl, c->cams + reg, &rec->err_pnp, nullptr));  // sfm.py:368
+      SFM_TRY(sfm_triangulate_dev(ctx, c->P_view + 12 * (size_t)(g + 1), c->temp1, c->temp2, M, &rec->n_new, c->X4, 1)); // sfm.py:371
+      SFM_TRY(sfm_reproj_error_dev(ctx, c->X4, 2, c->temp2, M, &rec->n_new, c->cams + reg, &rec->err_new, X_new[reg])); // sfm.py:372
+      c->prev_q = q; c->prev_t = t; c->prev_n = M;
+      c->views_done += 1;
+    }
+    SFM_CUDA(cudaMemcpyAsync(c->hrecs, c->recs, sizeof(ViewRec) * (size_t)reg, cudaMemcpyDeviceToHost, ctx->stream));
+    SFM_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int v = 0; v < reg; ++v) {
+      const ViewRec& r = c->hrecs[v];
+      sfm_view_out& o = out[v];
+      memcpy(o.Rt, r.Rt, sizeof(o.Rt));
+      o.err_pnp = r.err_pnp; o.err_new = r.err_new;
+      o.n_new = r.n_new; o.n_pnp = r.n_pnp; o.n_inl = r.n_inl; o.n_match = n_match[k0 + v];
+      SFM_REQUIRE(r.n_pnp >= 6, "registration failed: view %d shares %d points with the model", c->views_done - reg + v + 2, r.n_pnp);
+      SFM_REQUIRE(r.ok, "registration failed: solvePnPRansac found no consensus (view %d)", c->views_done - reg + v + 2);
+    }
+    if (n_registered) *n_registered = reg;
+    return SFM_OK;
   }
   for (int k = k0; k < n_pairs; ++k, ++reg) {
     const int M = n_match[k];

@@ -9,6 +9,7 @@
 #include <math.h>
 
 #include "common.cuh"
+#include "chain_dev.cuh"
 #include "hostmath.h"
 
 // ============================================================================ K2 triangulate
@@ -105,9 +106,16 @@ __device__ __forceinline__ void dlt_null_vector(double (&At)[4][4], double (&out
 template <int PTS_LAYOUT, int OUT_LAYOUT>
 __global__ void __launch_bounds__(128) triangulate_kernel(ProjPair pp, const float* __restrict__ x1,
                                                            const float* __restrict__ x2, int n,
-                                                           float* __restrict__ X, int normalize_w) {
+                                                           float* __restrict__ X, int normalize_w,
+                                                           const int* __restrict__ n_dev = nullptr,
+                                                           const double* __restrict__ P_dev = nullptr) {
+  if (n_dev) n = min(n, *n_dev);             // row count produced by an earlier kernel of the same stream
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  if (P_dev) {                               // projection matrices produced on the device (registration loop)
+#pragma unroll
+    for (int k = 0; k < 12; ++k) { pp.P1[k] = P_dev[k]; pp.P2[k] = P_dev[12 + k]; }
+  }
   float u1, v1, u2, v2;
   if (PTS_LAYOUT == 0) {   // (2,N): two coalesced row reads per view
     u1 = __ldg(x1 + i); v1 = __ldg(x1 + n + i);
@@ -173,12 +181,6 @@ extern "C" int sfm_triangulate(sfm_ctx* ctx, const double* P1, const double* P2,
 }
 
 // ============================================================================ K3 reprojection
-struct CamParams {
-  double R[9];
-  double t[3];
-  double fx, fy, cx, cy;
-};
-
 // cv2.projectPoints with zero distortion, operation for operation (separately rounded products
 // and sums, no FMA contraction) so that the float32-rounded pixel equals OpenCV's.
 __device__ __forceinline__ void project_cv(const CamParams& c, double X, double Y, double Z,
@@ -219,9 +221,13 @@ __global__ void __launch_bounds__(256) reproj_kernel(CamParams cam, const float*
                                                       float* __restrict__ proj, float* __restrict__ X3,
                                                       double* __restrict__ partial,
                                                       unsigned int* __restrict__ counter,
-                                                      double* __restrict__ err_out) {
+                                                      double* __restrict__ err_out,
+                                                      const int* __restrict__ n_dev = nullptr,
+                                                      const CamParams* __restrict__ cam_dev = nullptr) {
   __shared__ double sh[8];
   __shared__ bool is_last;
+  if (n_dev) n = min(n, *n_dev);
+  if (cam_dev) cam = *cam_dev;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   double sq = 0.0;
   if (i < n) {
@@ -267,7 +273,7 @@ __global__ void __launch_bounds__(256) reproj_kernel(CamParams cam, const float*
     __syncthreads();
     s = block_sum_256(s, sh);
     if (threadIdx.x == 0) {
-      *err_out = sqrt(s) / (double)n;
+      *err_out = n > 0 ? sqrt(s) / (double)n : 0.0;
       *counter = 0u;
     }
   }
@@ -320,6 +326,38 @@ extern "C" int sfm_reproj_error(sfm_ctx* ctx, const float* X, int x_layout, cons
   SFM_TRY(dev_out_finish(ctx, &oX3));
   SFM_TRY(dev_out_finish(ctx, &oerr));
   if (host_out) SFM_CUDA(cudaStreamSynchronize(ctx->stream));
+  return SFM_OK;
+}
+
+// ---- registration-loop variants: counts and matrices in HBM, nothing synchronises (chain_dev.cuh)
+int sfm_triangulate_dev(sfm_ctx* ctx, const double* P1P2_dev, const float* x1, const float* x2, int n_cap,
+                        const int* n_dev, float* X, int out_layout) {
+  if (n_cap <= 0) return SFM_OK;
+  ProjPair pp;
+  memset(&pp, 0, sizeof(pp));
+  dim3 grid(div_up(n_cap, 128)), block(128);
+  if (out_layout == 1)
+    SFM_LAUNCH(ctx, SFM_K_TRIANGULATE, (triangulate_kernel<1, 1><<<grid, block, 0, ctx->stream>>>(pp, x1, x2, n_cap, X, 1, n_dev, P1P2_dev)));
+  else
+    SFM_LAUNCH(ctx, SFM_K_TRIANGULATE, (triangulate_kernel<1, 2><<<grid, block, 0, ctx->stream>>>(pp, x1, x2, n_cap, X, 1, n_dev, P1P2_dev)));
+  return SFM_OK;
+}
+
+int sfm_reproj_error_dev(sfm_ctx* ctx, const float* X, int x_layout, const float* px, int n_cap, const int* n_dev,
+                         const CamParams* cam_dev, double* err_dev, float* X3) {
+  if (n_cap <= 0) return SFM_OK;
+  CamParams cam;
+  memset(&cam, 0, sizeof(cam));
+  SFM_TRY(sfm_ws_begin(ctx));
+  int nblk = div_up(n_cap, 256);
+  double* partial;
+  SFM_TRY(ws_alloc_t(ctx, (size_t)nblk, &partial));
+  if (x_layout == 0)
+    SFM_LAUNCH(ctx, SFM_K_REPROJ, (reproj_kernel<0, 1><<<nblk, 256, 0, ctx->stream>>>(cam, X, px, n_cap, nullptr, X3, partial,
+                                                                                     ctx->counters, err_dev, n_dev, cam_dev)));
+  else
+    SFM_LAUNCH(ctx, SFM_K_REPROJ, (reproj_kernel<2, 1><<<nblk, 256, 0, ctx->stream>>>(cam, X, px, n_cap, nullptr, X3, partial,
+                                                                                     ctx->counters, err_dev, n_dev, cam_dev)));
   return SFM_OK;
 }
 

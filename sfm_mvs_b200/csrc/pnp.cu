@@ -20,8 +20,10 @@
 #include <float.h>
 #include <math.h>
 #include <stdlib.h>
+#include <vector>
 
 #include "common.cuh"
+#include "chain_dev.cuh"
 #include "epnp.h"
 
 namespace {
@@ -63,7 +65,9 @@ __global__ void __launch_bounds__(256) pnp_score_kernel(const float* __restrict_
                                                         int n, const double* __restrict__ poses,
                                                         const unsigned char* __restrict__ valid, int H, PnpCam cam,
                                                         float thr2, int* __restrict__ counts,
-                                                        unsigned char* __restrict__ masks) {
+                                                        unsigned char* __restrict__ masks,
+                                                        const int* __restrict__ n_dev = nullptr) {
+  if (n_dev) n = min(n, *n_dev);
   __shared__ double s_pose[PNP_HG][12];
   __shared__ int s_count[PNP_HG];
   __shared__ unsigned char s_valid[PNP_HG];
@@ -219,16 +223,27 @@ struct PnpSubsets {
 __global__ void __launch_bounds__(32) pnp_epnp_kernel(const float* __restrict__ X, const float* __restrict__ px, int n,
                                                       int H, PnpCam cam, const __grid_constant__ PnpSubsets subs,
                                                       double* __restrict__ poses, double* __restrict__ rt6,
-                                                      unsigned char* __restrict__ valid, long long* __restrict__ dbg) {
+                                                      unsigned char* __restrict__ valid, long long* __restrict__ dbg,
+                                                      const int* __restrict__ n_dev = nullptr,
+                                                      const int* __restrict__ subs_dev = nullptr) {
   __shared__ EpnpShared sh;
   const int h = blockIdx.x, lane = threadIdx.x;
   if (h >= H) return;
+  if (n_dev) {
+    n = *n_dev;
+    if (n < 6) {                             // no minimal problem to solve: every hypothesis invalid -> ok = 0 downstream
+      if (lane == 0) valid[h] = 0;
+      return;
+    }
+  }
   auto tick = [&](int k) { if (dbg && h == 0 && lane == 0) dbg[k] = clock64(); };
   tick(0);
   const hm::EpnpCam ec = {cam.fx, cam.fy, cam.cx, cam.cy};
   if (lane == 0) {
     int sub[5] = {0, 1, 2, 3, 4};
-    if (n > 5 && h < subs.count) {
+    if (subs_dev) {
+      for (int k = 0; k < 5; ++k) sub[k] = subs_dev[5 * h + k];
+    } else if (n > 5 && h < subs.count) {
       for (int k = 0; k < 5; ++k) sub[k] = subs.idx[5 * h + k];
     } else if (n > 5) {                            // the subset iteration h of OpenCV's RANSAC draws
       unsigned long long state = 0xFFFFFFFFFFFFFFFFull;
@@ -628,6 +643,84 @@ __device__ inline void pnp_refine(const float* __restrict__ X,
   }
 }
 
+// The RNG index stream of OpenCV's RANSAC for a row count that only the device knows.  The raw
+// multiply-with-carry states do not depend on n (only how many of them an iteration consumes does, through
+// the duplicate redraws), so they come from a table computed once on the host; the kernel reduces them
+// modulo n in parallel and one thread replays the "five distinct indices" bookkeeping on the results.
+constexpr int PNP_RAW = 2048;
+
+// five distinct values starting at r[pos]; returns how many entries were consumed (0: ran off the table)
+__device__ __forceinline__ int take_five(const int* r, int pos, int* five) {
+  int got = 0, used = 0;
+  while (got < 5) {
+    if (pos + used >= PNP_RAW) return 0;
+    const int j = r[pos + used];
+    ++used;
+    bool dup = false;
+    for (int k = 0; k < got; ++k) dup |= (five[k] == j);
+    if (!dup) five[got++] = j;
+  }
+  return used;
+}
+
+// Iteration `it` starts where the previous ones stopped, which depends on their redraws — rare events.  So
+// every iteration is evaluated in parallel from a guessed start (5 entries each at first), the consumed counts
+// are prefix-summed into new starts, and the round repeats until no start moves (iteration k is exact after at
+// most k rounds; with a handful of redraws in 100 iterations that is a handful of rounds).
+__global__ void __launch_bounds__(1024) pnp_subsets_kernel(const int* __restrict__ n_dev, int iters,
+                                                           const unsigned int* __restrict__ raw, int* __restrict__ out) {
+  __shared__ int r[PNP_RAW];
+  __shared__ int cnt[128], warp_tot[4];
+  __shared__ int overflow;
+  const int n = *n_dev;
+  if (n < 6) return;
+  const int t = threadIdx.x;
+  for (int k = t; k < PNP_RAW; k += blockDim.x) r[k] = (int)(raw[k] % (unsigned int)n);
+  if (t < 128) cnt[t] = (t < iters) ? 5 : 0;
+  if (t == 0) overflow = 0;
+  __syncthreads();
+  int five[5] = {0, 0, 0, 0, 0};
+  for (int round = 0; round <= iters; ++round) {
+    // exclusive prefix sum of cnt over the first 128 threads
+    int start = 0;
+    if (t < 128) {
+      int v = cnt[t], x = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if ((t & 31) >= o) x += y; }
+      if ((t & 31) == 31) warp_tot[t >> 5] = x;
+      start = x - v;
+    }
+    __syncthreads();
+    bool changed = false;
+    if (t < 128 && t < iters) {
+      for (int w = 0; w < (t >> 5); ++w) start += warp_tot[w];
+      const int used = take_five(r, start, five);
+      if (used == 0) overflow = 1;
+      else if (used != cnt[t]) { changed = true; }
+      if (used) cnt[t] = used;       // own slot only; read again after the barrier below
+    }
+    if (!__syncthreads_or(changed ? 1 : 0)) break;
+  }
+  if (overflow) {                     // tiny n: the table is too short — one thread replays the recurrence
+    if (t == 0) ransac_subsets(n, iters, out);
+    return;
+  }
+  if (t < iters && t < 128) {
+    int* o = out + 5 * t;
+    o[0] = five[0]; o[1] = five[1]; o[2] = five[2]; o[3] = five[3]; o[4] = five[4];
+  }
+}
+
+struct PoseOut {              // registration loop: what the next launches need, formed on the device (chain.cu)
+  double* pose6;              // rvec | tvec
+  int* n_inl;
+  int* ok;
+  double* Rt;                 // 12: [R|t]
+  double* P;                  // 12: K [R|t]
+  CamParams* cam;             // projectPoints operands of the reference's ReprojectionError (sfm.py:84,88)
+  const double* K;            // 9 (device)
+};
+
 // Tail of the RANSAC in ONE single-CTA launch: replay of the stopping rule (thread 0), the winner's
 // inlier list (stable compaction), the LM refinement.
 __global__ void __launch_bounds__(REFINE_THREADS) pnp_finish_kernel(const float* __restrict__ X, const float* __restrict__ px,
@@ -636,12 +729,46 @@ __global__ void __launch_bounds__(REFINE_THREADS) pnp_finish_kernel(const float*
                                                                     double conf, const double* __restrict__ poses,
                                                                     const double* __restrict__ rt6, PnpCam cam, float thr2,
                                                                     int refine_iters, int* __restrict__ inliers,
-                                                                    PnpResult* __restrict__ res) {
+                                                                    PnpResult* __restrict__ res,
+                                                                    const int* __restrict__ n_dev = nullptr,
+                                                                    PoseOut po = PoseOut()) {
+  if (n_dev) n = min(n, *n_dev);
   if (threadIdx.x == 0) pnp_replay(counts, valid, n, H, conf, rt6, res);
   __threadfence_block();
   __syncthreads();
   pnp_inliers(X, px, n, poses, cam, thr2, res, inliers);
   if (refine_iters > 0) pnp_refine(X, px, inliers, cam, refine_iters, res);
+  __syncthreads();
+  if (threadIdx.x == 0 && po.pose6) {        // registration loop: the result stays in HBM
+    double p6[6];
+    for (int k = 0; k < 3; ++k) { p6[k] = res->rvec[k]; p6[3 + k] = res->tvec[k]; po.pose6[k] = p6[k]; po.pose6[3 + k] = p6[3 + k]; }
+    *po.n_inl = res->ok ? res->n_inliers : 0;
+    *po.ok = res->ok;
+    if (po.Rt) {
+      // [R|t], P = K [R|t] for the next triangulations, and R' = Rodrigues(log(R)): the reference's
+      // ReprojectionError passes R through cv2.Rodrigues twice.  R is orthonormal by construction here, so the
+      // log map is taken directly (cv2's SVD re-orthonormalisation would change it by ~1e-16).
+      double R[9], Rt[12];
+      hm::rodrigues_to_matrix(p6, R);
+      for (int i = 0; i < 3; ++i) { Rt[4 * i] = R[3 * i]; Rt[4 * i + 1] = R[3 * i + 1]; Rt[4 * i + 2] = R[3 * i + 2]; Rt[4 * i + 3] = p6[3 + i]; }
+      for (int k = 0; k < 12; ++k) po.Rt[k] = Rt[k];
+      const double* K = po.K;
+      for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 4; ++j) po.P[4 * i + j] = K[3 * i] * Rt[j] + K[3 * i + 1] * Rt[4 + j] + K[3 * i + 2] * Rt[8 + j];
+      double rx = R[7] - R[5], ry = R[2] - R[6], rz = R[3] - R[1];
+      double sn = sqrt((rx * rx + ry * ry + rz * rz) * 0.25);
+      double cs = (R[0] + R[4] + R[8] - 1.0) * 0.5;
+      cs = cs > 1.0 ? 1.0 : (cs < -1.0 ? -1.0 : cs);
+      double rv[3] = {p6[0], p6[1], p6[2]};
+      if (sn >= 1e-5) {
+        const double vth = acos(cs) / (2.0 * sn);
+        rv[0] = rx * vth; rv[1] = ry * vth; rv[2] = rz * vth;
+      }
+      hm::rodrigues_to_matrix(rv, po.cam->R);
+      po.cam->t[0] = p6[3]; po.cam->t[1] = p6[4]; po.cam->t[2] = p6[5];
+      po.cam->fx = K[0]; po.cam->fy = K[4]; po.cam->cx = K[2]; po.cam->cy = K[5];
+    }
+  }
 }
 
 static PnpCam make_pnp_cam(const double* K) {
@@ -791,6 +918,62 @@ static int pnp_ransac_impl(sfm_ctx* ctx, const float* X, const float* px, int n,
     info->refine_iters = hres->refine_iters;
     for (int k = 0; k < 3; ++k) { info->rvec_ransac[k] = hres->rvec0[k]; info->tvec_ransac[k] = hres->tvec0[k]; }
   }
+  return SFM_OK;
+}
+
+static const unsigned int* pnp_raw_table(sfm_ctx* ctx) {
+  // low words of the first PNP_RAW states of cv::RNG(2^64-1): one table per device, uploaded once
+  static unsigned int* tab[64] = {nullptr};
+  const int dev = ctx->device & 63;
+  if (!tab[dev]) {
+    std::vector<unsigned int> h(PNP_RAW);
+    unsigned long long state = 0xFFFFFFFFFFFFFFFFull;
+    for (int k = 0; k < PNP_RAW; ++k) {
+      state = (state & 0xFFFFFFFFull) * 4164903690ull + (state >> 32);
+      h[k] = (unsigned int)state;
+    }
+    unsigned int* d = nullptr;
+    if (cudaMalloc(&d, sizeof(unsigned int) * PNP_RAW) != cudaSuccess) return nullptr;
+    if (cudaMemcpy(d, h.data(), sizeof(unsigned int) * PNP_RAW, cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
+    tab[dev] = d;
+  }
+  return tab[dev];
+}
+
+int sfm_pnp_ransac_dev(sfm_ctx* ctx, const float* X, const float* px, int n_cap, const int* n_dev, const double* K,
+                       const double* K_dev, double* pose6_dev, int32_t* inliers_dev, int32_t* n_inl_dev, int32_t* ok_dev,
+                       double* Rt_dev, double* P_dev, CamParams* cam_dev) {
+  SFM_REQUIRE(n_cap >= 1, "sfm_pnp_ransac_dev: empty capacity");
+  SFM_TRY(sfm_ws_begin(ctx));
+  const unsigned int* raw = pnp_raw_table(ctx);
+  SFM_REQUIRE(raw, "sfm_pnp_ransac_dev: RNG table allocation failed");
+  const PnpCam cam = make_pnp_cam(K);
+  const int H = 100;
+  const float thr2 = 64.0f;
+  double *dposes, *drt6;
+  unsigned char* dvalid;
+  int32_t *dcounts, *dsubs;
+  PnpResult* dres;
+  SFM_TRY(ws_alloc_t(ctx, (size_t)12 * H, &dposes));
+  SFM_TRY(ws_alloc_t(ctx, (size_t)6 * H, &drt6));
+  SFM_TRY(ws_alloc_t(ctx, (size_t)H, &dvalid));
+  SFM_TRY(ws_alloc_t(ctx, (size_t)H, &dcounts));
+  SFM_TRY(ws_alloc_t(ctx, (size_t)5 * H, &dsubs));
+  SFM_TRY(ws_alloc_t(ctx, 1, &dres));
+  PnpSubsets subs;
+  subs.count = 0;
+  SFM_CUDA(cudaMemsetAsync(dcounts, 0, sizeof(int32_t) * H, ctx->stream));
+  SFM_LAUNCH(ctx, SFM_K_MISC, (pnp_subsets_kernel<<<1, 1024, 0, ctx->stream>>>(n_dev, H, raw, dsubs)));
+  SFM_LAUNCH(ctx, SFM_K_PNP_EPNP, (pnp_epnp_kernel<<<H, 32, 0, ctx->stream>>>(X, px, n_cap, H, cam, subs, dposes, drt6, dvalid,
+                                                                            nullptr, n_dev, dsubs)));
+  dim3 grid(div_up(n_cap, 256), div_up(H, PNP_HG));
+  SFM_LAUNCH(ctx, SFM_K_PNP_SCORE, (pnp_score_kernel<<<grid, 256, 0, ctx->stream>>>(X, px, n_cap, dposes, dvalid, H, cam, thr2, dcounts,
+                                                                                   nullptr, n_dev)));
+  PoseOut po;
+  po.pose6 = pose6_dev; po.n_inl = n_inl_dev; po.ok = ok_dev; po.Rt = Rt_dev; po.P = P_dev; po.cam = cam_dev; po.K = K_dev;
+  SFM_LAUNCH(ctx, SFM_K_PNP_REFINE, (pnp_finish_kernel<<<1, REFINE_THREADS, 0, ctx->stream>>>(
+                                        X, px, n_cap, dcounts, dvalid, H, 0.99, dposes, drt6, cam, thr2, 20, inliers_dev, dres, n_dev,
+                                        po)));
   return SFM_OK;
 }
 

@@ -311,7 +311,9 @@ def register_host(ctx: _e.Context, K, kps, dess, Rt0, Rt1, chunk: int = 25, rati
     as_t = lambda a: a if _e._is_torch(a) else torch.from_numpy(np.ascontiguousarray(a))
     kps = [as_t(a) for a in kps]
     dess = [as_t(a) for a in dess]
-    cs = torch.cuda.Stream(device=dev)
+    cs = getattr(ctx, "_copy_stream", None)          # one upload stream per context: torch's caching allocator keeps a
+    if cs is None:                                    # pool per stream, a fresh stream per call would cudaMalloc every buffer
+        cs = ctx._copy_stream = torch.cuda.Stream(device=dev)
     bounds = [(lo, min(lo + chunk, V)) for lo in range(0, V, chunk)]
     kp_d, des_d, events = [None] * V, [None] * V, []
     with torch.cuda.stream(cs):
