@@ -29,30 +29,31 @@ constexpr int NB = 64;
 constexpr int SB = 256;   // backward-substitution super-block
 
 // Cholesky of the diagonal block at k0 by a 256-thread CTA.  Thread t holds row t%64, columns
-// 16*(t/64) .. +15 in registers (the column segment is warp-uniform, so warps whose segment is
-// already final, or lies entirely above their rows, skip a column step without divergence).
-// Per column j: the 64 owner threads publish the diagonal entry (64-thread named barrier), scale
-// their entry by 1/sqrt(d) and publish the scaled column; one block barrier; every live thread
-// applies the rank-1 update to its entries with one shared load + one FMA each.
+// 16*(t/64) .. +15 in registers.  The block is factored in four 16-column panels:
+//   inside a panel only its 64 owner threads work — per column two 64-thread named barriers (publish the
+//   diagonal, publish the scaled column) and <= 15 FMAs per thread for the columns of the same panel;
+//   after a panel ONE block barrier, then the threads holding columns to its right apply the whole rank-16
+//   update from shared memory (256 independent FMAs per thread).
+// 4 block barriers instead of 64, and the serial part is 64 x (two cheap barriers + a handful of FMAs).
 // Rows/columns >= nb are identity.  Writes L (lower) back to A and 1/diag(L) to dinv[k0 .. k0+63].
+// colbuf: 16 x (NB+2) doubles of shared memory.
 __device__ __forceinline__ void factor_diag_block(double* __restrict__ A, int n, int k0, double* __restrict__ dinv,
                                                   int* __restrict__ info, double (*colbuf)[NB + 2]) {
   const int nb = min(NB, n - k0);
   const int row = threadIdx.x & 63, cseg = threadIdx.x >> 6;
-  const int warp_row_max = (row | 31);                  // largest row held by this warp
   double a[16];
 #pragma unroll
   for (int cc = 0; cc < 16; ++cc) {
     const int c = 16 * cseg + cc;
     a[cc] = (row < nb && c <= row) ? A[(size_t)(k0 + row) * n + k0 + c] : ((c == row) ? 1.0 : 0.0);
   }
-#pragma unroll
+#pragma unroll 1
   for (int seg = 0; seg < 4; ++seg) {
+    if (cseg == seg) {                                  // the panel's owners: two warps, rows 0..63
 #pragma unroll
-    for (int jj = 0; jj < 16; ++jj) {
-      const int j = 16 * seg + jj;
-      double* cb = colbuf[j & 1];                       // cb[0..63] scaled column, cb[64] raw diagonal
-      if (cseg == seg) {                                // owners of column j (two warps)
+      for (int jj = 0; jj < 16; ++jj) {
+        const int j = 16 * seg + jj;
+        double* cb = colbuf[jj];                        // cb[0..63] scaled column j, cb[64] raw diagonal
         if (row == j) cb[NB] = a[jj];
         asm volatile("bar.sync 1, 64;" ::: "memory");
         double d = cb[NB];
@@ -65,17 +66,27 @@ __device__ __forceinline__ void factor_diag_block(double* __restrict__ A, int n,
         a[jj] = li;
         cb[row] = li;
         if (row == j) dinv[k0 + j] = rinv;
-      }
-      __syncthreads();
-      if (cseg >= seg && warp_row_max > j) {            // warp-uniform: something left to update
-        const double li = cb[row];
+        asm volatile("bar.sync 1, 64;" ::: "memory");
 #pragma unroll
-        for (int cc = 0; cc < 16; ++cc) {
-          const int c = 16 * cseg + cc;
-          if (c > j && row >= c) a[cc] = fma(-li, cb[c], a[cc]);
+        for (int cc = jj + 1; cc < 16; ++cc) {          // remaining columns of this panel
+          const int c = 16 * seg + cc;
+          if (row >= c) a[cc] = fma(-li, cb[c], a[cc]);
         }
       }
     }
+    __syncthreads();
+    if (cseg > seg) {                                   // rank-16 update of the columns to the right
+#pragma unroll
+      for (int jj = 0; jj < 16; ++jj) {
+        const double li = colbuf[jj][row];
+#pragma unroll
+        for (int cc = 0; cc < 16; ++cc) {
+          const int c = 16 * cseg + cc;
+          if (row >= c) a[cc] = fma(-li, colbuf[jj][c], a[cc]);
+        }
+      }
+    }
+    __syncthreads();                                    // colbuf is rewritten by the next panel
   }
 #pragma unroll
   for (int cc = 0; cc < 16; ++cc) {
@@ -86,7 +97,7 @@ __device__ __forceinline__ void factor_diag_block(double* __restrict__ A, int n,
 
 __global__ void __launch_bounds__(256) chol_diag_kernel(double* __restrict__ A, int n, int k0, double* __restrict__ dinv,
                                                         int* __restrict__ info) {
-  __shared__ double colbuf[2][NB + 2];
+  __shared__ double colbuf[16][NB + 2];
   factor_diag_block(A, n, k0, dinv, info, colbuf);
 }
 
@@ -112,10 +123,15 @@ __global__ void __launch_bounds__(PANEL_THREADS) chol_panel_kernel(double* __res
   for (int j = 0; j < NB; ++j) x[j] = (j < nb) ? a[j] : 0.0;
 #pragma unroll
   for (int j = 0; j < NB; ++j) {
-    double s = x[j];
+    double s0 = x[j], s1 = 0.0, s2 = 0.0, s3 = 0.0;    // four chains: the sum over k < j is latency-bound otherwise
 #pragma unroll
-    for (int k = 0; k < j; ++k) s = fma(-x[k], L[j][k], s);
-    x[j] = s * di[j];
+    for (int k = 0; k < j; ++k) {
+      if ((k & 3) == 0) s0 = fma(-x[k], L[j][k], s0);
+      else if ((k & 3) == 1) s1 = fma(-x[k], L[j][k], s1);
+      else if ((k & 3) == 2) s2 = fma(-x[k], L[j][k], s2);
+      else s3 = fma(-x[k], L[j][k], s3);
+    }
+    x[j] = ((s0 + s1) + (s2 + s3)) * di[j];
   }
 #pragma unroll
   for (int j = 0; j < NB; ++j)
@@ -201,11 +217,32 @@ __global__ void __launch_bounds__(256) back_diag_kernel(const double* __restrict
       v = ys[s * NB + threadIdx.x];
       di = (threadIdx.x < nb) ? dinv[r0 + threadIdx.x] : 1.0;
     }
-    if (threadIdx.x < NB) {                          // two warps own the 64 unknowns
-      for (int j = NB - 1; j >= 0; --j) {
-        if ((int)threadIdx.x == j) xs[j] = v * di;
-        asm volatile("bar.sync 1, 64;" ::: "memory");
-        if ((int)threadIdx.x < j) v = fma(-Ls[j][threadIdx.x], xs[j], v);
+    // 64 unknowns, bottom up.  Unknown j lives in lane j%32 of warp j/32; inside a 32-unknown half the solved value
+    // travels by shuffle (no barrier), the upper half's effect on the lower one is a 32x32 matvec.
+    if (threadIdx.x < NB) xs[threadIdx.x] = 0.0;
+    __syncthreads();
+    if (threadIdx.x >= 32 && threadIdx.x < NB) {       // upper half (unknowns 32..63), warp 1
+      const int l = threadIdx.x - 32;
+      for (int j = 31; j >= 0; --j) {
+        const double xj = __shfl_sync(0xffffffffu, v * di, j);
+        if (l == j) xs[32 + j] = xj;
+        if (l < j) v = fma(-Ls[32 + j][32 + l], xj, v);
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {                            // lower half (unknowns 0..31), warp 0
+      const int l = threadIdx.x;
+      double s0 = 0.0, s1 = 0.0;
+#pragma unroll 8
+      for (int r = 0; r < 32; r += 2) {
+        s0 = fma(Ls[32 + r][l], xs[32 + r], s0);
+        s1 = fma(Ls[33 + r][l], xs[33 + r], s1);
+      }
+      v -= s0 + s1;
+      for (int j = 31; j >= 0; --j) {
+        const double xj = __shfl_sync(0xffffffffu, v * di, j);
+        if (l == j) xs[j] = xj;
+        if (l < j) v = fma(-Ls[j][l], xj, v);
       }
     }
     __syncthreads();
