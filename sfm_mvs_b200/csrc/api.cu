@@ -65,6 +65,7 @@ extern "C" void sfm_ctx_destroy(sfm_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   sfm_desc_pool_free(c);
+  sfm_chain_parked_free(c);
   for (void* p : c->retired) cudaFree(p);
   for (void* p : c->hs_retired) cudaFreeHost(p);
   if (c->ws) cudaFree(c->ws);

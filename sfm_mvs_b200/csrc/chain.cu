@@ -135,6 +135,14 @@ struct sfm_chain {
   CamParams* cams = nullptr;       // [ERR_SLOTS]   projectPoints operands of the view registered in that slot
   double* pose6 = nullptr;         // rvec | tvec of the PnP just run
   double* K_dev = nullptr;
+  // Data association of view v+1 (common_points, complement, pixel gather) needs no pose, so it runs on a
+  // second stream (own context = own workspace) while view v is inside PnP: second set of its outputs + events.
+  sfm_ctx* ctxB = nullptr;
+  int32_t *i1b = nullptr, *i2b = nullptr;
+  uint8_t* keepb = nullptr;
+  float *temp1b = nullptr, *temp2b = nullptr, *com2b = nullptr;
+  cudaEvent_t ev_assoc[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_start = nullptr;
+  bool set_used[2] = {false, false};
   struct ViewRec* hrecs = nullptr; // pinned
   int32_t* hcnt = nullptr;         // pinned
   double* herrs = nullptr;         // pinned
@@ -156,9 +164,30 @@ struct ViewRec {                  // device-side result record of one registered
   int n_new, n_pnp, n_inl, ok;
 };
 
+static void sfm_chain_release(sfm_chain* c);
+
 extern "C" int sfm_chain_create(sfm_ctx* ctx, const double* K, const double* Rt0, const double* Rt1, int max_matches,
                                 sfm_chain** out) {
   SFM_REQUIRE(ctx && K && Rt0 && Rt1 && out && max_matches >= 6, "sfm_chain_create: bad argument");
+  if (ctx->chain_parked) {                               // reuse the buffers of the last chain on this context
+    sfm_chain* p = static_cast<sfm_chain*>(ctx->chain_parked);
+    ctx->chain_parked = nullptr;
+    if (p->nmax >= max_matches) {
+      memcpy(p->K, K, sizeof(p->K));
+      memcpy(p->Rt1, Rt1, sizeof(p->Rt1));
+      matmul_K_Rt(K, Rt0, p->P1);
+      matmul_K_Rt(K, Rt1, p->P2);
+      p->started = false; p->prev_q = p->prev_t = nullptr; p->prev_n = 0; p->pts1 = p->points_3d = nullptr; p->n1 = 0;
+      p->views_done = 0; p->set_used[0] = p->set_used[1] = false;
+      SFM_CUDA(cudaMemcpyAsync(p->K_dev, p->K, 9 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+      SFM_CUDA(cudaMemcpyAsync(p->P_view, p->P1, 12 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+      SFM_CUDA(cudaMemcpyAsync(p->P_view + 12, p->P2, 12 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+      *out = p;
+      return SFM_OK;
+    }
+    p->ctx->chain_parked = nullptr;
+    sfm_chain_release(p);
+  }
   sfm_chain* c = new sfm_chain();
   c->ctx = ctx;
   memcpy(c->K, K, sizeof(c->K));
@@ -166,7 +195,7 @@ extern "C" int sfm_chain_create(sfm_ctx* ctx, const double* K, const double* Rt0
   matmul_K_Rt(K, Rt0, c->P1);
   matmul_K_Rt(K, Rt1, c->P2);
   const int nmax = c->nmax = max_matches;
-  c->ar.cap = (size_t)nmax * 160 + (size_t)ERR_SLOTS * (16 + sizeof(ViewRec) + 96 + sizeof(CamParams)) + 64 * 1024;
+  c->ar.cap = (size_t)nmax * 200 + (size_t)ERR_SLOTS * (16 + sizeof(ViewRec) + 96 + sizeof(CamParams)) + 64 * 1024;
   cudaError_t e = cudaMalloc(&c->ar.base, c->ar.cap);
   if (e == cudaSuccess) e = cudaMallocHost(&c->hcnt, 4 * sizeof(int32_t));
   if (e == cudaSuccess) e = cudaMallocHost(&c->herrs, sizeof(double) * 2 * ERR_SLOTS);
@@ -197,7 +226,19 @@ extern "C" int sfm_chain_create(sfm_ctx* ctx, const double* K, const double* Rt0
   c->P_view = ar.take<double>((size_t)12 * (ERR_SLOTS + 2));
   c->cams = ar.take<CamParams>(ERR_SLOTS);
   c->pose6 = ar.take<double>(16);
-  double* Kdev = ar.take<double>(16);
+  c->i1b = ar.take<int32_t>(nmax);
+  c->i2b = ar.take<int32_t>(nmax);
+  c->keepb = ar.take<uint8_t>(nmax);
+  c->temp1b = ar.take<float>((size_t)2 * nmax);
+  c->temp2b = ar.take<float>((size_t)2 * nmax);
+  c->com2b = ar.take<float>((size_t)2 * nmax);
+  if (sfm_ctx_create(ctx->device, nullptr, &c->ctxB) != SFM_OK) c->ctxB = nullptr;
+  for (int k = 0; k < 2; ++k) {
+    cudaEventCreateWithFlags(&c->ev_assoc[k], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->ev_done[k], cudaEventDisableTiming);
+  }
+  cudaEventCreateWithFlags(&c->ev_start, cudaEventDisableTiming);
+  double* Kdev = c->com2b && c->ctxB ? ar.take<double>(16) : nullptr;
   if (Kdev) {
     c->K_dev = Kdev;
     cudaMemcpy(Kdev, K, 9 * sizeof(double), cudaMemcpyHostToDevice);
@@ -213,9 +254,35 @@ extern "C" int sfm_chain_create(sfm_ctx* ctx, const double* K, const double* Rt0
   return SFM_OK;
 }
 
+static void sfm_chain_release(sfm_chain* c);
+
 extern "C" void sfm_chain_destroy(sfm_chain* c) {
   if (!c) return;
   if (c->ctx) cudaStreamSynchronize(c->ctx->stream);
+  if (c->ctxB) {
+    cudaStreamSynchronize(c->ctxB->stream);
+    if (c->ctx) c->ctx->total_launches += c->ctxB->total_launches;
+    c->ctxB->total_launches = 0;
+  }
+  if (c->ctx && !c->ctx->chain_parked && c->ctxB && c->K_dev) {   // park: the next chain on this context reuses everything
+    c->ctx->chain_parked = c;
+    return;
+  }
+  sfm_chain_release(c);
+}
+
+void sfm_chain_parked_free(sfm_ctx* ctx) {
+  if (ctx->chain_parked) sfm_chain_release(static_cast<sfm_chain*>(ctx->chain_parked));
+  ctx->chain_parked = nullptr;
+}
+
+static void sfm_chain_release(sfm_chain* c) {
+  if (c->ctxB) sfm_ctx_destroy(c->ctxB);
+  for (int k = 0; k < 2; ++k) {
+    if (c->ev_assoc[k]) cudaEventDestroy(c->ev_assoc[k]);
+    if (c->ev_done[k]) cudaEventDestroy(c->ev_done[k]);
+  }
+  if (c->ev_start) cudaEventDestroy(c->ev_start);
   if (c->ar.base) cudaFree(c->ar.base);
   if (c->hcnt) cudaFreeHost(c->hcnt);
   if (c->herrs) cudaFreeHost(c->herrs);
@@ -263,30 +330,46 @@ extern "C" int sfm_chain_extend(sfm_chain* c, int n_pairs, const float* const* p
     // ---- no host round trip inside the loop: counts, poses and matrices are produced and consumed in HBM
     SFM_REQUIRE(c->views_done + n_views < ERR_SLOTS, "sfm_chain_extend: more than %d views in one chain", ERR_SLOTS);
     SFM_CUDA(cudaMemsetAsync(c->recs, 0, sizeof(ViewRec) * (size_t)n_views, ctx->stream));
+    sfm_ctx* cb = c->ctxB;
+    SFM_CUDA(cudaEventRecord(c->ev_start, ctx->stream));
+    SFM_CUDA(cudaStreamWaitEvent(cb->stream, c->ev_start, 0));          // records are zeroed before B writes counts
     for (int k = k0; k < n_pairs; ++k, ++reg) {
       const int M = n_match[k];
       const float* q = pts_q[k];
       const float* t = pts_t[k];
       const int g = c->views_done;                         // views g, g+1 are the previous pair; g+2 is registered now
+      const int set = g & 1;
       ViewRec* rec = c->recs + reg;
+      int32_t* i1 = set ? c->i1b : c->i1;
+      int32_t* i2 = set ? c->i2b : c->i2;
+      uint8_t* keep = set ? c->keepb : c->keep;
+      float* temp1 = set ? c->temp1b : c->temp1;
+      float* temp2 = set ? c->temp2b : c->temp2;
+      float* com2 = set ? c->com2b : c->com2;
+      if (c->prev_q) { c->n1 = c->prev_n; c->pts1 = c->prev_t; }
+      const int n1 = c->n1;
+      // ---- stream B: data association (sfm.py:356) and the complement — 2-D data only, no pose needed
+      if (c->set_used[set]) SFM_CUDA(cudaStreamWaitEvent(cb->stream, c->ev_done[set], 0));
+      SFM_TRY(sfm_common_points(cb, c->pts1, n1, q, M, i1, i2, &rec->n_pnp, keep));
+      SFM_TRY(sfm_compact_pairs(cb, q, t, keep, M, temp1, temp2, &rec->n_new));
+      SFM_TRY(sfm_gather_rows_dev(cb, t, 2, i2, n1, &rec->n_pnp, com2));
+      SFM_CUDA(cudaEventRecord(c->ev_assoc[set], cb->stream));
+      // ---- main stream: everything that needs the previous pose
       if (c->prev_q) {                                     // re-triangulate the previous pair's matches (sfm.py:348-352)
-        c->n1 = c->prev_n;
-        c->pts1 = c->prev_t;
-        SFM_TRY(sfm_triangulate_dev(ctx, c->P_view + 12 * (size_t)g, c->prev_q, c->prev_t, c->n1, nullptr, c->pts3d_a, 2));
+        SFM_TRY(sfm_triangulate_dev(ctx, c->P_view + 12 * (size_t)g, c->prev_q, c->prev_t, n1, nullptr, c->pts3d_a, 2));
         c->points_3d = c->pts3d_a;
       }
-      const int n1 = c->n1;
-      SFM_TRY(sfm_common_points(ctx, c->pts1, n1, q, M, c->i1, c->i2, &rec->n_pnp, c->keep));          // sfm.py:356
-      SFM_TRY(sfm_compact_pairs(ctx, q, t, c->keep, M, c->temp1, c->temp2, &rec->n_new));
-      SFM_TRY(sfm_gather_rows_dev(ctx, c->points_3d, 3, c->i1, n1, &rec->n_pnp, c->Xc));
-      SFM_TRY(sfm_gather_rows_dev(ctx, t, 2, c->i2, n1, &rec->n_pnp, c->com2));
-      SFM_TRY(sfm_pnp_ransac_dev(ctx, c->Xc, c->com2, n1, &rec->n_pnp, K, c->K_dev, c->pose6, c->inl, &rec->n_inl, &rec->ok,
+      SFM_CUDA(cudaStreamWaitEvent(ctx->stream, c->ev_assoc[set], 0));
+      SFM_TRY(sfm_gather_rows_dev(ctx, c->points_3d, 3, i1, n1, &rec->n_pnp, c->Xc));
+      SFM_TRY(sfm_pnp_ransac_dev(ctx, c->Xc, com2, n1, &rec->n_pnp, K, c->K_dev, c->pose6, c->inl, &rec->n_inl, &rec->ok,
                                  rec->Rt, c->P_view + 12 * (size_t)(g + 2), c->cams + reg));                        // sfm.py:362
       SFM_TRY(sfm_gather_rows_dev(ctx, c->Xc, 3, c->inl, n1, &rec->n_inl, c->X_in));
-      SFM_TRY(sfm_gather_rows_dev(ctx, c->com2, 2, c->inl, n1, &rec->n_inl, c->p_in));
+      SFM_TRY(sfm_gather_rows_dev(ctx, com2, 2, c->inl, n1, &rec->n_inl, c->p_in));
       SFM_TRY(sfm_reproj_error_dev(ctx, c->X_in, 0, c->p_in, n1, &rec->n_inl, c->cams + reg, &rec->err_pnp, nullptr));  // sfm.py:368
-      SFM_TRY(sfm_triangulate_dev(ctx, c->P_view + 12 * (size_t)(g + 1), c->temp1, c->temp2, M, &rec->n_new, c->X4, 1)); // sfm.py:371
-      SFM_TRY(sfm_reproj_error_dev(ctx, c->X4, 2, c->temp2, M, &rec->n_new, c->cams + reg, &rec->err_new, X_new[reg])); // sfm.py:372
+      SFM_TRY(sfm_triangulate_dev(ctx, c->P_view + 12 * (size_t)(g + 1), temp1, temp2, M, &rec->n_new, c->X4, 1));       // sfm.py:371
+      SFM_TRY(sfm_reproj_error_dev(ctx, c->X4, 2, temp2, M, &rec->n_new, c->cams + reg, &rec->err_new, X_new[reg]));     // sfm.py:372
+      SFM_CUDA(cudaEventRecord(c->ev_done[set], ctx->stream));
+      c->set_used[set] = true;
       c->prev_q = q; c->prev_t = t; c->prev_n = M;
       c->views_done += 1;
     }

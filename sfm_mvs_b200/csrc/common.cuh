@@ -60,9 +60,12 @@ struct sfm_ctx {
   unsigned int* counters = nullptr;
   double* dscratch = nullptr;       // 64 doubles of persistent device scratch
   std::vector<void*> desc_pool;     // recycled DescBuf storage (match.cu)
+  void* chain_parked = nullptr;     // a destroyed registration chain's buffers / second context, kept for the next
+                                    // sfm_chain_create (pinned allocations and context creation cost milliseconds)
 };
 
 void sfm_desc_pool_free(sfm_ctx* c);   // match.cu
+void sfm_chain_parked_free(sfm_ctx* c);   // chain.cu
 
 // ---- workspace -------------------------------------------------------------------------
 int sfm_ws_begin(sfm_ctx* c);                         // start of an API call: reset bump pointers
