@@ -7,8 +7,9 @@ import numpy as np, torch
 import sfm_mvs_b200 as sfm
 from sfm_mvs_b200 import synth
 ctx = sfm.Context(0)
-pb = synth.ba_problem(500, 100000, 10, seed=0)
-prob = sfm.BAProblem(ctx, 500, 100000, pb["cam_idx"], pb["pt_idx"], pb["obs"], pb["K"])
+NPTS = int(sys.argv[1]) if len(sys.argv) > 1 else 100000
+pb = synth.ba_problem(500, NPTS, 10, seed=0)
+prob = sfm.BAProblem(ctx, 500, NPTS, pb["cam_idx"], pb["pt_idx"], pb["obs"], pb["K"])
 prob.set_params(pb["cams0"], pb["pts0"])
 O = prob.n_obs
 ts = ctx.torch_stream()
