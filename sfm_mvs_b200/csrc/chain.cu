@@ -138,6 +138,13 @@ struct sfm_chain {
   // Data association of view v+1 (common_points, complement, pixel gather) needs no pose, so it runs on a
   // second stream (own context = own workspace) while view v is inside PnP: second set of its outputs + events.
   sfm_ctx* ctxB = nullptr;
+  // The outputs of a view that nothing later depends on (its two reprojection errors, its new 3-D points) run on
+  // a third stream/context after the pose is known; the main stream only carries the pose dependency:
+  // re-triangulation -> PnP.  Buffers both sides touch exist twice (view parity).
+  sfm_ctx* ctxC = nullptr;
+  float* Xcb = nullptr;
+  int32_t* inlb = nullptr;
+  cudaEvent_t ev_core[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
   int32_t *i1b = nullptr, *i2b = nullptr;
   uint8_t* keepb = nullptr;
   float *temp1b = nullptr, *temp2b = nullptr, *com2b = nullptr;
@@ -195,7 +202,7 @@ extern "C" int sfm_chain_create(sfm_ctx* ctx, const double* K, const double* Rt0
   matmul_K_Rt(K, Rt0, c->P1);
   matmul_K_Rt(K, Rt1, c->P2);
   const int nmax = c->nmax = max_matches;
-  c->ar.cap = (size_t)nmax * 200 + (size_t)ERR_SLOTS * (16 + sizeof(ViewRec) + 96 + sizeof(CamParams)) + 64 * 1024;
+  c->ar.cap = (size_t)nmax * 220 + (size_t)ERR_SLOTS * (16 + sizeof(ViewRec) + 96 + sizeof(CamParams)) + 64 * 1024;
   cudaError_t e = cudaMalloc(&c->ar.base, c->ar.cap);
   if (e == cudaSuccess) e = cudaMallocHost(&c->hcnt, 4 * sizeof(int32_t));
   if (e == cudaSuccess) e = cudaMallocHost(&c->herrs, sizeof(double) * 2 * ERR_SLOTS);
@@ -232,13 +239,18 @@ extern "C" int sfm_chain_create(sfm_ctx* ctx, const double* K, const double* Rt0
   c->temp1b = ar.take<float>((size_t)2 * nmax);
   c->temp2b = ar.take<float>((size_t)2 * nmax);
   c->com2b = ar.take<float>((size_t)2 * nmax);
+  c->Xcb = ar.take<float>((size_t)3 * nmax);
+  c->inlb = ar.take<int32_t>(nmax);
   if (sfm_ctx_create(ctx->device, nullptr, &c->ctxB) != SFM_OK) c->ctxB = nullptr;
+  if (sfm_ctx_create(ctx->device, nullptr, &c->ctxC) != SFM_OK) c->ctxC = nullptr;
   for (int k = 0; k < 2; ++k) {
     cudaEventCreateWithFlags(&c->ev_assoc[k], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&c->ev_done[k], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->ev_core[k], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->ev_out[k], cudaEventDisableTiming);
   }
   cudaEventCreateWithFlags(&c->ev_start, cudaEventDisableTiming);
-  double* Kdev = c->com2b && c->ctxB ? ar.take<double>(16) : nullptr;
+  double* Kdev = c->inlb && c->ctxB && c->ctxC ? ar.take<double>(16) : nullptr;
   if (Kdev) {
     c->K_dev = Kdev;
     cudaMemcpy(Kdev, K, 9 * sizeof(double), cudaMemcpyHostToDevice);
@@ -259,11 +271,12 @@ static void sfm_chain_release(sfm_chain* c);
 extern "C" void sfm_chain_destroy(sfm_chain* c) {
   if (!c) return;
   if (c->ctx) cudaStreamSynchronize(c->ctx->stream);
-  if (c->ctxB) {
-    cudaStreamSynchronize(c->ctxB->stream);
-    if (c->ctx) c->ctx->total_launches += c->ctxB->total_launches;
-    c->ctxB->total_launches = 0;
-  }
+  for (sfm_ctx* side : {c->ctxB, c->ctxC})
+    if (side) {
+      cudaStreamSynchronize(side->stream);
+      if (c->ctx) c->ctx->total_launches += side->total_launches;
+      side->total_launches = 0;
+    }
   if (c->ctx && !c->ctx->chain_parked && c->ctxB && c->K_dev) {   // park: the next chain on this context reuses everything
     c->ctx->chain_parked = c;
     return;
@@ -278,9 +291,12 @@ void sfm_chain_parked_free(sfm_ctx* ctx) {
 
 static void sfm_chain_release(sfm_chain* c) {
   if (c->ctxB) sfm_ctx_destroy(c->ctxB);
+  if (c->ctxC) sfm_ctx_destroy(c->ctxC);
   for (int k = 0; k < 2; ++k) {
     if (c->ev_assoc[k]) cudaEventDestroy(c->ev_assoc[k]);
     if (c->ev_done[k]) cudaEventDestroy(c->ev_done[k]);
+    if (c->ev_core[k]) cudaEventDestroy(c->ev_core[k]);
+    if (c->ev_out[k]) cudaEventDestroy(c->ev_out[k]);
   }
   if (c->ev_start) cudaEventDestroy(c->ev_start);
   if (c->ar.base) cudaFree(c->ar.base);
@@ -331,8 +347,10 @@ extern "C" int sfm_chain_extend(sfm_chain* c, int n_pairs, const float* const* p
     SFM_REQUIRE(c->views_done + n_views < ERR_SLOTS, "sfm_chain_extend: more than %d views in one chain", ERR_SLOTS);
     SFM_CUDA(cudaMemsetAsync(c->recs, 0, sizeof(ViewRec) * (size_t)n_views, ctx->stream));
     sfm_ctx* cb = c->ctxB;
+    sfm_ctx* cc = c->ctxC;
     SFM_CUDA(cudaEventRecord(c->ev_start, ctx->stream));
-    SFM_CUDA(cudaStreamWaitEvent(cb->stream, c->ev_start, 0));          // records are zeroed before B writes counts
+    SFM_CUDA(cudaStreamWaitEvent(cb->stream, c->ev_start, 0));          // records are zeroed before B / C write into them
+    SFM_CUDA(cudaStreamWaitEvent(cc->stream, c->ev_start, 0));
     for (int k = k0; k < n_pairs; ++k, ++reg) {
       const int M = n_match[k];
       const float* q = pts_q[k];
@@ -346,33 +364,42 @@ extern "C" int sfm_chain_extend(sfm_chain* c, int n_pairs, const float* const* p
       float* temp1 = set ? c->temp1b : c->temp1;
       float* temp2 = set ? c->temp2b : c->temp2;
       float* com2 = set ? c->com2b : c->com2;
+      float* Xc = set ? c->Xcb : c->Xc;
+      int32_t* inl = set ? c->inlb : c->inl;
       if (c->prev_q) { c->n1 = c->prev_n; c->pts1 = c->prev_t; }
       const int n1 = c->n1;
-      // ---- stream B: data association (sfm.py:356) and the complement — 2-D data only, no pose needed
-      if (c->set_used[set]) SFM_CUDA(cudaStreamWaitEvent(cb->stream, c->ev_done[set], 0));
+      // ---- stream B: data association (sfm.py:356) and the complement — 2-D data only, no pose needed.
+      // This parity's buffers were last read by the outputs of view g-2.
+      if (c->set_used[set]) SFM_CUDA(cudaStreamWaitEvent(cb->stream, c->ev_out[set], 0));
       SFM_TRY(sfm_common_points(cb, c->pts1, n1, q, M, i1, i2, &rec->n_pnp, keep));
       SFM_TRY(sfm_compact_pairs(cb, q, t, keep, M, temp1, temp2, &rec->n_new));
       SFM_TRY(sfm_gather_rows_dev(cb, t, 2, i2, n1, &rec->n_pnp, com2));
       SFM_CUDA(cudaEventRecord(c->ev_assoc[set], cb->stream));
-      // ---- main stream: everything that needs the previous pose
+      // ---- main stream: the pose dependency — re-triangulation with the previous pose, then PnP
       if (c->prev_q) {                                     // re-triangulate the previous pair's matches (sfm.py:348-352)
         SFM_TRY(sfm_triangulate_dev(ctx, c->P_view + 12 * (size_t)g, c->prev_q, c->prev_t, n1, nullptr, c->pts3d_a, 2));
         c->points_3d = c->pts3d_a;
       }
       SFM_CUDA(cudaStreamWaitEvent(ctx->stream, c->ev_assoc[set], 0));
-      SFM_TRY(sfm_gather_rows_dev(ctx, c->points_3d, 3, i1, n1, &rec->n_pnp, c->Xc));
-      SFM_TRY(sfm_pnp_ransac_dev(ctx, c->Xc, com2, n1, &rec->n_pnp, K, c->K_dev, c->pose6, c->inl, &rec->n_inl, &rec->ok,
+      if (c->set_used[set]) SFM_CUDA(cudaStreamWaitEvent(ctx->stream, c->ev_out[set], 0));   // Xc / inl of this parity free again
+      SFM_TRY(sfm_gather_rows_dev(ctx, c->points_3d, 3, i1, n1, &rec->n_pnp, Xc));
+      SFM_TRY(sfm_pnp_ransac_dev(ctx, Xc, com2, n1, &rec->n_pnp, K, c->K_dev, c->pose6, inl, &rec->n_inl, &rec->ok,
                                  rec->Rt, c->P_view + 12 * (size_t)(g + 2), c->cams + reg));                        // sfm.py:362
-      SFM_TRY(sfm_gather_rows_dev(ctx, c->Xc, 3, c->inl, n1, &rec->n_inl, c->X_in));
-      SFM_TRY(sfm_gather_rows_dev(ctx, com2, 2, c->inl, n1, &rec->n_inl, c->p_in));
-      SFM_TRY(sfm_reproj_error_dev(ctx, c->X_in, 0, c->p_in, n1, &rec->n_inl, c->cams + reg, &rec->err_pnp, nullptr));  // sfm.py:368
-      SFM_TRY(sfm_triangulate_dev(ctx, c->P_view + 12 * (size_t)(g + 1), temp1, temp2, M, &rec->n_new, c->X4, 1));       // sfm.py:371
-      SFM_TRY(sfm_reproj_error_dev(ctx, c->X4, 2, temp2, M, &rec->n_new, c->cams + reg, &rec->err_new, X_new[reg]));     // sfm.py:372
-      SFM_CUDA(cudaEventRecord(c->ev_done[set], ctx->stream));
+      SFM_CUDA(cudaEventRecord(c->ev_core[set], ctx->stream));
+      // ---- stream C: what nothing later depends on — the two reprojection errors and the new points
+      SFM_CUDA(cudaStreamWaitEvent(cc->stream, c->ev_core[set], 0));
+      SFM_TRY(sfm_gather_rows_dev(cc, Xc, 3, inl, n1, &rec->n_inl, c->X_in));
+      SFM_TRY(sfm_gather_rows_dev(cc, com2, 2, inl, n1, &rec->n_inl, c->p_in));
+      SFM_TRY(sfm_reproj_error_dev(cc, c->X_in, 0, c->p_in, n1, &rec->n_inl, c->cams + reg, &rec->err_pnp, nullptr));   // sfm.py:368
+      SFM_TRY(sfm_triangulate_dev(cc, c->P_view + 12 * (size_t)(g + 1), temp1, temp2, M, &rec->n_new, c->X4, 1));        // sfm.py:371
+      SFM_TRY(sfm_reproj_error_dev(cc, c->X4, 2, temp2, M, &rec->n_new, c->cams + reg, &rec->err_new, X_new[reg]));      // sfm.py:372
+      SFM_CUDA(cudaEventRecord(c->ev_out[set], cc->stream));
       c->set_used[set] = true;
       c->prev_q = q; c->prev_t = t; c->prev_n = M;
       c->views_done += 1;
     }
+    for (int k = 0; k < 2; ++k)
+      if (c->set_used[k]) SFM_CUDA(cudaStreamWaitEvent(ctx->stream, c->ev_out[k], 0));   // the records are complete
     SFM_CUDA(cudaMemcpyAsync(c->hrecs, c->recs, sizeof(ViewRec) * (size_t)reg, cudaMemcpyDeviceToHost, ctx->stream));
     SFM_CUDA(cudaStreamSynchronize(ctx->stream));
     for (int v = 0; v < reg; ++v) {
