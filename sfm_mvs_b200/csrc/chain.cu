@@ -144,6 +144,7 @@ struct sfm_chain {
   sfm_ctx* ctxC = nullptr;
   float* Xcb = nullptr;
   int32_t* inlb = nullptr;
+  int32_t* subs[2] = {nullptr, nullptr};   // RNG subsets of the PnP (needs only the association count: stream B)
   cudaEvent_t ev_core[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
   int32_t *i1b = nullptr, *i2b = nullptr;
   uint8_t* keepb = nullptr;
@@ -241,6 +242,8 @@ extern "C" int sfm_chain_create(sfm_ctx* ctx, const double* K, const double* Rt0
   c->com2b = ar.take<float>((size_t)2 * nmax);
   c->Xcb = ar.take<float>((size_t)3 * nmax);
   c->inlb = ar.take<int32_t>(nmax);
+  c->subs[0] = ar.take<int32_t>(512);
+  c->subs[1] = ar.take<int32_t>(512);
   if (sfm_ctx_create(ctx->device, nullptr, &c->ctxB) != SFM_OK) c->ctxB = nullptr;
   if (sfm_ctx_create(ctx->device, nullptr, &c->ctxC) != SFM_OK) c->ctxC = nullptr;
   for (int k = 0; k < 2; ++k) {
@@ -374,17 +377,20 @@ extern "C" int sfm_chain_extend(sfm_chain* c, int n_pairs, const float* const* p
       SFM_TRY(sfm_common_points(cb, c->pts1, n1, q, M, i1, i2, &rec->n_pnp, keep));
       SFM_TRY(sfm_compact_pairs(cb, q, t, keep, M, temp1, temp2, &rec->n_new));
       SFM_TRY(sfm_gather_rows_dev(cb, t, 2, i2, n1, &rec->n_pnp, com2));
+      SFM_TRY(sfm_pnp_subsets_dev(cb, &rec->n_pnp, c->subs[set]));     // the RANSAC index stream needs only the count
       SFM_CUDA(cudaEventRecord(c->ev_assoc[set], cb->stream));
       // ---- main stream: the pose dependency — re-triangulation with the previous pose, then PnP
-      if (c->prev_q) {                                     // re-triangulate the previous pair's matches (sfm.py:348-352)
-        SFM_TRY(sfm_triangulate_dev(ctx, c->P_view + 12 * (size_t)g, c->prev_q, c->prev_t, n1, nullptr, c->pts3d_a, 2));
-        c->points_3d = c->pts3d_a;
-      }
       SFM_CUDA(cudaStreamWaitEvent(ctx->stream, c->ev_assoc[set], 0));
       if (c->set_used[set]) SFM_CUDA(cudaStreamWaitEvent(ctx->stream, c->ev_out[set], 0));   // Xc / inl of this parity free again
-      SFM_TRY(sfm_gather_rows_dev(ctx, c->points_3d, 3, i1, n1, &rec->n_pnp, Xc));
+      if (c->prev_q) {
+        // re-triangulate the previous pair's matches (sfm.py:348-352) — only the rows data association kept
+        // (points_3d is used through points_3d[indx1] alone, sfm.py:362), straight into the PnP's point array
+        SFM_TRY(sfm_triangulate_dev(ctx, c->P_view + 12 * (size_t)g, c->prev_q, c->prev_t, n1, &rec->n_pnp, Xc, 2, i1));
+      } else {
+        SFM_TRY(sfm_gather_rows_dev(ctx, c->points_3d, 3, i1, n1, &rec->n_pnp, Xc));
+      }
       SFM_TRY(sfm_pnp_ransac_dev(ctx, Xc, com2, n1, &rec->n_pnp, K, c->K_dev, c->pose6, inl, &rec->n_inl, &rec->ok,
-                                 rec->Rt, c->P_view + 12 * (size_t)(g + 2), c->cams + reg));                        // sfm.py:362
+                                 rec->Rt, c->P_view + 12 * (size_t)(g + 2), c->cams + reg, c->subs[set]));          // sfm.py:362
       SFM_CUDA(cudaEventRecord(c->ev_core[set], ctx->stream));
       // ---- stream C: what nothing later depends on — the two reprojection errors and the new points
       SFM_CUDA(cudaStreamWaitEvent(cc->stream, c->ev_core[set], 0));

@@ -108,10 +108,12 @@ __global__ void __launch_bounds__(128) triangulate_kernel(ProjPair pp, const flo
                                                            const float* __restrict__ x2, int n,
                                                            float* __restrict__ X, int normalize_w,
                                                            const int* __restrict__ n_dev = nullptr,
-                                                           const double* __restrict__ P_dev = nullptr) {
+                                                           const double* __restrict__ P_dev = nullptr,
+                                                           const int* __restrict__ idx = nullptr) {
   if (n_dev) n = min(n, *n_dev);             // row count produced by an earlier kernel of the same stream
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  const int src = idx ? __ldg(idx + i) : i;  // registration loop: triangulate only the rows data association selected
   if (P_dev) {                               // projection matrices produced on the device (registration loop)
 #pragma unroll
     for (int k = 0; k < 12; ++k) { pp.P1[k] = P_dev[k]; pp.P2[k] = P_dev[12 + k]; }
@@ -121,8 +123,8 @@ __global__ void __launch_bounds__(128) triangulate_kernel(ProjPair pp, const flo
     u1 = __ldg(x1 + i); v1 = __ldg(x1 + n + i);
     u2 = __ldg(x2 + i); v2 = __ldg(x2 + n + i);
   } else {                 // (N,2): one 8-byte read per view
-    float2 a = __ldg(reinterpret_cast<const float2*>(x1) + i);
-    float2 b = __ldg(reinterpret_cast<const float2*>(x2) + i);
+    float2 a = __ldg(reinterpret_cast<const float2*>(x1) + src);
+    float2 b = __ldg(reinterpret_cast<const float2*>(x2) + src);
     u1 = a.x; v1 = a.y; u2 = b.x; v2 = b.y;
   }
   // At[k][r] = A[r][k];  A rows: x*P[2]-P[0], y*P[2]-P[1] for view 1 then view 2
@@ -331,15 +333,15 @@ extern "C" int sfm_reproj_error(sfm_ctx* ctx, const float* X, int x_layout, cons
 
 // ---- registration-loop variants: counts and matrices in HBM, nothing synchronises (chain_dev.cuh)
 int sfm_triangulate_dev(sfm_ctx* ctx, const double* P1P2_dev, const float* x1, const float* x2, int n_cap,
-                        const int* n_dev, float* X, int out_layout) {
+                        const int* n_dev, float* X, int out_layout, const int32_t* idx) {
   if (n_cap <= 0) return SFM_OK;
   ProjPair pp;
   memset(&pp, 0, sizeof(pp));
   dim3 grid(div_up(n_cap, 128)), block(128);
   if (out_layout == 1)
-    SFM_LAUNCH(ctx, SFM_K_TRIANGULATE, (triangulate_kernel<1, 1><<<grid, block, 0, ctx->stream>>>(pp, x1, x2, n_cap, X, 1, n_dev, P1P2_dev)));
+    SFM_LAUNCH(ctx, SFM_K_TRIANGULATE, (triangulate_kernel<1, 1><<<grid, block, 0, ctx->stream>>>(pp, x1, x2, n_cap, X, 1, n_dev, P1P2_dev, idx)));
   else
-    SFM_LAUNCH(ctx, SFM_K_TRIANGULATE, (triangulate_kernel<1, 2><<<grid, block, 0, ctx->stream>>>(pp, x1, x2, n_cap, X, 1, n_dev, P1P2_dev)));
+    SFM_LAUNCH(ctx, SFM_K_TRIANGULATE, (triangulate_kernel<1, 2><<<grid, block, 0, ctx->stream>>>(pp, x1, x2, n_cap, X, 1, n_dev, P1P2_dev, idx)));
   return SFM_OK;
 }
 

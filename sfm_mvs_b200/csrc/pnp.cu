@@ -940,13 +940,20 @@ static const unsigned int* pnp_raw_table(sfm_ctx* ctx) {
   return tab[dev];
 }
 
+int sfm_pnp_subsets_dev(sfm_ctx* ctx, const int* n_dev, int32_t* subs_dev) {
+  const unsigned int* raw = pnp_raw_table(ctx);
+  SFM_REQUIRE(raw, "sfm_pnp_subsets_dev: RNG table allocation failed");
+  SFM_LAUNCH(ctx, SFM_K_MISC, (pnp_subsets_kernel<<<1, 1024, 0, ctx->stream>>>(n_dev, 100, raw, subs_dev)));
+  return SFM_OK;
+}
+
 int sfm_pnp_ransac_dev(sfm_ctx* ctx, const float* X, const float* px, int n_cap, const int* n_dev, const double* K,
                        const double* K_dev, double* pose6_dev, int32_t* inliers_dev, int32_t* n_inl_dev, int32_t* ok_dev,
-                       double* Rt_dev, double* P_dev, CamParams* cam_dev) {
+                       double* Rt_dev, double* P_dev, CamParams* cam_dev, const int32_t* subs_dev) {
   SFM_REQUIRE(n_cap >= 1, "sfm_pnp_ransac_dev: empty capacity");
   SFM_TRY(sfm_ws_begin(ctx));
-  const unsigned int* raw = pnp_raw_table(ctx);
-  SFM_REQUIRE(raw, "sfm_pnp_ransac_dev: RNG table allocation failed");
+  const unsigned int* raw = subs_dev ? nullptr : pnp_raw_table(ctx);
+  SFM_REQUIRE(subs_dev || raw, "sfm_pnp_ransac_dev: RNG table allocation failed");
   const PnpCam cam = make_pnp_cam(K);
   const int H = 100;
   const float thr2 = 64.0f;
@@ -963,9 +970,9 @@ int sfm_pnp_ransac_dev(sfm_ctx* ctx, const float* X, const float* px, int n_cap,
   PnpSubsets subs;
   subs.count = 0;
   SFM_CUDA(cudaMemsetAsync(dcounts, 0, sizeof(int32_t) * H, ctx->stream));
-  SFM_LAUNCH(ctx, SFM_K_MISC, (pnp_subsets_kernel<<<1, 1024, 0, ctx->stream>>>(n_dev, H, raw, dsubs)));
+  if (!subs_dev) SFM_LAUNCH(ctx, SFM_K_MISC, (pnp_subsets_kernel<<<1, 1024, 0, ctx->stream>>>(n_dev, H, raw, dsubs)));
   SFM_LAUNCH(ctx, SFM_K_PNP_EPNP, (pnp_epnp_kernel<<<H, 32, 0, ctx->stream>>>(X, px, n_cap, H, cam, subs, dposes, drt6, dvalid,
-                                                                            nullptr, n_dev, dsubs)));
+                                                                            nullptr, n_dev, subs_dev ? subs_dev : dsubs)));
   dim3 grid(div_up(n_cap, 256), div_up(H, PNP_HG));
   SFM_LAUNCH(ctx, SFM_K_PNP_SCORE, (pnp_score_kernel<<<grid, 256, 0, ctx->stream>>>(X, px, n_cap, dposes, dvalid, H, cam, thr2, dcounts,
                                                                                    nullptr, n_dev)));
