@@ -226,3 +226,18 @@ extern "C" int sfm_ctx_get_profile(sfm_ctx* c, int id, double* ms_total, int64_t
 }
 
 extern "C" int64_t sfm_ctx_launch_count(sfm_ctx* c) { return c ? c->total_launches : 0; }
+
+// A side context (the registration loop's association / output streams) hands its launch counts and, when
+// profiling, its per-kernel event times to the context the caller sees.
+void sfm_ctx_merge_profile(sfm_ctx* dst, sfm_ctx* src) {
+  if (!dst || !src) return;
+  drain_events(src);
+  for (int i = 0; i < SFM_K_COUNT; ++i) {
+    dst->ms[i] += src->ms[i];
+    dst->launches[i] += src->launches[i];
+    src->ms[i] = 0;
+    src->launches[i] = 0;
+  }
+  dst->total_launches += src->total_launches;
+  src->total_launches = 0;
+}

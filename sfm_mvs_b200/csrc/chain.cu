@@ -277,8 +277,7 @@ extern "C" void sfm_chain_destroy(sfm_chain* c) {
   for (sfm_ctx* side : {c->ctxB, c->ctxC})
     if (side) {
       cudaStreamSynchronize(side->stream);
-      if (c->ctx) c->ctx->total_launches += side->total_launches;
-      side->total_launches = 0;
+      sfm_ctx_merge_profile(c->ctx, side);
     }
   if (c->ctx && !c->ctx->chain_parked && c->ctxB && c->K_dev) {   // park: the next chain on this context reuses everything
     c->ctx->chain_parked = c;
@@ -351,6 +350,7 @@ extern "C" int sfm_chain_extend(sfm_chain* c, int n_pairs, const float* const* p
     SFM_CUDA(cudaMemsetAsync(c->recs, 0, sizeof(ViewRec) * (size_t)n_views, ctx->stream));
     sfm_ctx* cb = c->ctxB;
     sfm_ctx* cc = c->ctxC;
+    cb->profiling = cc->profiling = ctx->profiling;        // their kernels show up in the caller's profile
     SFM_CUDA(cudaEventRecord(c->ev_start, ctx->stream));
     SFM_CUDA(cudaStreamWaitEvent(cb->stream, c->ev_start, 0));          // records are zeroed before B / C write into them
     SFM_CUDA(cudaStreamWaitEvent(cc->stream, c->ev_start, 0));

@@ -66,6 +66,7 @@ struct sfm_ctx {
 
 void sfm_desc_pool_free(sfm_ctx* c);   // match.cu
 void sfm_chain_parked_free(sfm_ctx* c);   // chain.cu
+void sfm_ctx_merge_profile(sfm_ctx* dst, sfm_ctx* src);   // api.cu
 
 // ---- workspace -------------------------------------------------------------------------
 int sfm_ws_begin(sfm_ctx* c);                         // start of an API call: reset bump pointers

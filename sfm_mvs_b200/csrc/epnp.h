@@ -36,9 +36,16 @@ HM_HD inline void eig_sym(double* A, double* w, double* V) {
         if (apq == 0.0) continue;
         double app = A[p * N + p], aqq = A[q * N + q];
         if (fabs(apq) <= 1e-300) continue;
-        double theta = (aqq - app) / (2.0 * apq);
-        double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+        // tan(angle) = sgn(al) apq / (|al| + hypot(al, apq)), al = (aqq - app)/2  (the textbook theta form, one
+        // division and one square root cheaper)
+        double al = 0.5 * (aqq - app);
+        double rr = sqrt(al * al + apq * apq);
+        double t = apq / (al + (al >= 0.0 ? rr : -rr));
+#ifdef __CUDA_ARCH__
+        double c = rsqrt(t * t + 1.0), s = t * c;
+#else
         double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+#endif
         for (int k = 0; k < N; ++k) {   // columns p,q
           double akp = A[k * N + p], akq = A[k * N + q];
           A[k * N + p] = c * akp - s * akq;

@@ -303,8 +303,30 @@ __global__ void __launch_bounds__(32) pnp_epnp_kernel(const float* __restrict__ 
       double sgn = sh.V[m * 12 + big] < 0.0 ? -1.0 : 1.0;
       for (int k = 0; k < 12; ++k) sh.v4[12 * r + k] = sgn * sh.V[m * 12 + k];
     }
-    const double* v[4] = {sh.v4, sh.v4 + 12, sh.v4 + 24, sh.v4 + 36};
-    hm::epnp_L_rho(v, reinterpret_cast<const double(*)[3]>(sh.cws), sh.L, sh.rho);
+  }
+  __syncwarp();
+  // L (6 x 10) and rho (6): one entry per lane-step.  Row i <-> control-point pair (a,b); column <-> (p,q) of v_p.v_q
+  for (int e = lane; e < 66; e += 32) {
+    const int i = (e < 60) ? e / 10 : e - 60;
+    const int pa = (i < 3) ? 0 : ((i < 5) ? 1 : 2);
+    const int pb = (i < 3) ? i + 1 : ((i < 5) ? i - 1 : 3);
+    if (e < 60) {
+      const int col = e - 10 * i;
+      // columns: 0 (0,0) 1 (0,1) 2 (1,1) 3 (0,2) 4 (1,2) 5 (2,2) 6 (0,3) 7 (1,3) 8 (2,3) 9 (3,3)
+      const int q = (col < 1) ? 0 : ((col < 3) ? 1 : ((col < 6) ? 2 : 3));
+      const int p = col - ((q * (q + 1)) >> 1);
+      const double* vp = sh.v4 + 12 * p;
+      const double* vq = sh.v4 + 12 * q;
+      double d = 0.0;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) d += (vp[3 * pa + k] - vp[3 * pb + k]) * (vq[3 * pa + k] - vq[3 * pb + k]);
+      sh.L[e] = (p == q) ? d : 2.0 * d;
+    } else {
+      double d = 0.0;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { const double x = sh.cws[3 * pa + k] - sh.cws[3 * pb + k]; d += x * x; }
+      sh.rho[i] = d;
+    }
   }
   __syncwarp();
   tick(4);
@@ -321,7 +343,7 @@ __global__ void __launch_bounds__(32) pnp_epnp_kernel(const float* __restrict__ 
   tick(5);
   if (lane == N) {
     double rv[3];
-    hm::rodrigues_to_vector(R, rv);
+    hm::rotation_log(R, rv);        // R = U V^T of the absolute orientation: orthonormal already, no second SVD
     double* P = poses + 12 * (size_t)h;
     double Rr[9];
     hm::rodrigues_to_matrix(rv, Rr);
@@ -575,7 +597,15 @@ __device__ inline void pnp_refine(const float* __restrict__ X,
       double x = R[0] * Xw[0] + R[1] * Xw[1] + R[2] * Xw[2] + tx;
       double y = R[3] * Xw[0] + R[4] * Xw[1] + R[5] * Xw[2] + ty;
       double z = R[6] * Xw[0] + R[7] * Xw[1] + R[8] * Xw[2] + tz;
-      double iz = z != 0.0 ? 1.0 / z : 1.0;
+      double iz = 1.0;
+      if (fabs(z) > 1e-30 && fabs(z) < 1e30) {   // reciprocal by float seed + Newton steps (double accuracy, no division chain)
+        iz = (double)(1.0f / (float)z);
+        iz = iz * (2.0 - z * iz);
+        iz = iz * (2.0 - z * iz);
+        iz = iz * (2.0 - z * iz);
+      } else if (z != 0.0) {
+        iz = 1.0 / z;
+      }
       double xn = x * iz, yn = y * iz;
       double ex = xn * cam.fx + cam.cx - ox, ey = yn * cam.fy + cam.cy - oy;
       acc[27] += ex * ex + ey * ey;
