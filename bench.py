@@ -256,6 +256,9 @@ def run_engine(args):
                     "traffic": None, "peak_source": pk["source"] + ", sustained bf16 (kernel timed inside a long step)",
                     "algorithmic_flops_per_launch": flops, "pairs_per_launch": V - 1, "avg_launch_us": 1e6 * t_launch,
                     "launches": mt["launches"],
+                    "note": "K1 is the path's dense contraction (the kernel north_star sets a tensor-pipe target for). By time the "
+                            "registration loop is dominated by the latency-bound PnP kernels (one warp per EPnP hypothesis, a "
+                            "single-CTA LM refinement): see kernel_time_share / DESIGN.md.",
                     "share_of_kernel_time": shares.get("match_tc")}
 
     out = {
