@@ -157,20 +157,25 @@ __device__ __forceinline__ void warp_jacobi12(EpnpShared& sh, int lane) {
     if (off * 0.5 <= 1e-28 * diag || off == 0.0) break;
     for (int round = 0; round < 11; ++round) {
       if (lane < 6) {
-        int p = (lane == 0) ? 11 : (round + lane) % 11;
-        int q = (lane == 0) ? round : (round - lane + 11) % 11;
+        int p = round + lane, q = round - lane + 11;          // (round +- lane) mod 11 without a division
+        p -= (p >= 11) ? 11 : 0;
+        q -= (q >= 11) ? 11 : 0;
+        if (lane == 0) { p = 11; q = round; }
         if (p > q) { int t = p; p = q; q = t; }
         const double apq = sh.A[p * 12 + q], app = sh.A[p * 12 + p], aqq = sh.A[q * 12 + q];
         double c = 1.0, s = 0.0;
-        if (fabs(apq) > 1e-300) {
-          // tan of the rotation angle in float32 (MUFU sqrt / divide); (c, s) from it in float64, so the
-          // rotation is orthogonal to working precision and merely annihilates a_pq to ~1e-7 relative —
-          // the residue is carried exactly (no forced zero) and vanishes in the next sweeps.
+        if (fabs(apq) > 1e-150) {
+          // t = apq / (al + sgn(al) hypot(al, apq)) with one reciprocal square root (hypot = s2 rsqrt(s2)) and a
+          // Newton reciprocal seeded in float32 — no float64 division or square root on this dependent chain;
+          // (c, s) = (rsqrt(1 + t^2), t c) is orthogonal to working precision whatever the error of t.
           const double al = 0.5 * (aqq - app);
-          const double sc = 1.0 / fmax(fabs(al), fabs(apq));
-          const float fa = (float)(al * sc), fb = (float)(apq * sc);
-          const float fr = sqrtf(fa * fa + fb * fb);
-          const double t = (double)(fb / (fa + (fa >= 0.f ? fr : -fr)));
+          const double s2 = al * al + apq * apq;
+          const double r = s2 * rsqrt(s2);
+          const double den = al + (al >= 0.0 ? r : -r);
+          double id = (double)(1.0f / (float)den);
+          id = id * (2.0 - den * id);
+          id = id * (2.0 - den * id);
+          const double t = (fabs(den) > 1e-30 && fabs(den) < 1e30) ? apq * id : apq / den;
           c = rsqrt(t * t + 1.0);
           s = t * c;
         }
@@ -287,21 +292,28 @@ __global__ void __launch_bounds__(32) pnp_epnp_kernel(const float* __restrict__ 
   tick(2);
   warp_jacobi12(sh, lane);
   tick(3);
-  if (lane == 0) {
-    // the four eigenvectors of the smallest eigenvalues, smallest first, largest component positive
-    double w[12];
-    bool used[12];
-    for (int i = 0; i < 12; ++i) { w[i] = sh.A[13 * i]; used[i] = false; }
-    for (int r = 0; r < 4; ++r) {
-      int m = -1;
-      for (int i = 0; i < 12; ++i)
-        if (!used[i] && (m < 0 || w[i] < w[m])) m = i;
-      used[m] = true;
-      int big = 0;
-      for (int k = 1; k < 12; ++k)
-        if (fabs(sh.V[m * 12 + k]) > fabs(sh.V[m * 12 + big])) big = k;
-      double sgn = sh.V[m * 12 + big] < 0.0 ? -1.0 : 1.0;
-      for (int k = 0; k < 12; ++k) sh.v4[12 * r + k] = sgn * sh.V[m * 12 + k];
+  // the four eigenvectors of the smallest eigenvalues, smallest first, largest component positive: lane e < 12
+  // ranks its eigenvalue among the twelve (ties by index, like a stable selection) and, if it is one of the
+  // four smallest, copies its eigenvector row
+  if (lane < 12) {
+    const double we = sh.A[13 * lane];
+    int rank = 0;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+      const double wi = sh.A[13 * i];
+      rank += (wi < we || (wi == we && i < lane)) ? 1 : 0;
+    }
+    if (rank < 4) {
+      double row[12];
+      double big = 0.0, bigv = 0.0;
+#pragma unroll
+      for (int k = 0; k < 12; ++k) {
+        row[k] = sh.V[lane * 12 + k];
+        if (fabs(row[k]) > big) { big = fabs(row[k]); bigv = row[k]; }
+      }
+      const double sgn = bigv < 0.0 ? -1.0 : 1.0;
+#pragma unroll
+      for (int k = 0; k < 12; ++k) sh.v4[12 * rank + k] = sgn * row[k];
     }
   }
   __syncwarp();
@@ -453,6 +465,33 @@ struct PoseJac {
   double dR[3][9];   // dR/drvec_k
 };
 
+// The same, split over three threads of three different warps (K is a compile-time constant per call site, so
+// nothing is indexed dynamically): each forms R in registers and its own dR/dr_K; the K = 0 caller publishes R.
+template <int K>
+__device__ inline void pose_jacobian_setup_k(const double* rv, PoseJac* pj) {
+  double R[9];
+  hm::rodrigues_to_matrix(rv, R);
+  if (K == 0)
+    for (int i = 0; i < 9; ++i) pj->R[i] = R[i];
+  const double th2 = rv[0] * rv[0] + rv[1] * rv[1] + rv[2] * rv[2];
+  const double e[3] = {K == 0 ? 1.0 : 0.0, K == 1 ? 1.0 : 0.0, K == 2 ? 1.0 : 0.0};
+  double S[9];
+  if (th2 < 1e-24) {
+    S[0] = 0; S[1] = -e[2]; S[2] = e[1]; S[3] = e[2]; S[4] = 0; S[5] = -e[0]; S[6] = -e[1]; S[7] = e[0]; S[8] = 0;
+    for (int i = 0; i < 9; ++i) pj->dR[K][i] = S[i];
+    return;
+  }
+  const double inv_th2 = 1.0 / th2;
+  // dR/dr_k = ( r_k [r]x + [ r x (I - R) e_k ]x ) R / |r|^2      (Gallego & Yezzi 2015)
+  const double m[3] = {e[0] - R[0 + K], e[1] - R[3 + K], e[2] - R[6 + K]};   // (I - R) e_k
+  const double c[3] = {rv[1] * m[2] - rv[2] * m[1], rv[2] * m[0] - rv[0] * m[2], rv[0] * m[1] - rv[1] * m[0]};
+  const double a[3] = {rv[K] * rv[0] + c[0], rv[K] * rv[1] + c[1], rv[K] * rv[2] + c[2]};
+  S[0] = 0; S[1] = -a[2]; S[2] = a[1]; S[3] = a[2]; S[4] = 0; S[5] = -a[0]; S[6] = -a[1]; S[7] = a[0]; S[8] = 0;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j)
+      pj->dR[K][3 * i + j] = (S[3 * i] * R[j] + S[3 * i + 1] * R[3 + j] + S[3 * i + 2] * R[6 + j]) * inv_th2;
+}
+
 __device__ inline void pose_jacobian_setup(const double* rv, PoseJac* pj) {
   hm::rodrigues_to_matrix(rv, pj->R);
   double th2 = rv[0] * rv[0] + rv[1] * rv[1] + rv[2] * rv[2];
@@ -557,11 +596,32 @@ __device__ inline double pow10_int(double k) {
   return r;
 }
 
+__device__ __forceinline__ uint32_t pnp_cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ double pnp_ld_dsmem(const double* p, uint32_t rank) {
+  uint32_t a = (uint32_t)__cvta_generic_to_shared(p), ra;
+  double v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(rank));
+  asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(ra) : "memory");
+  return v;
+}
+
+// NCTA > 1: the CTAs of a cluster split the inliers; every pass their 28 partial sums meet through distributed
+// shared memory (one cluster barrier per pass, partials double-buffered) and EVERY CTA then runs the identical
+// scalar LM logic on the identical totals, so no parameter broadcast is needed.  The accumulation is bound by
+// one SM's float64 throughput (measured 7.7 k of ~14 k cycles per pass at 2000 inliers); 8 SMs take that to ~1 k.
+template <int NCTA>
 __device__ inline void pnp_refine(const float* __restrict__ X,
                                                                     const float* __restrict__ px,
                                                                     const int* __restrict__ inliers, PnpCam cam,
-                                                                    int max_iter, PnpResult* __restrict__ res) {
+                                                                    int max_iter, PnpResult* __restrict__ res,
+                                                                    long long* __restrict__ dbg = nullptr) {
   __shared__ double sh[REFINE_THREADS / 32][REFINE_NACC];
+  __shared__ double part[2][REFINE_NACC];
+  const uint32_t crank = NCTA > 1 ? pnp_cluster_rank() : 0u;
   __shared__ double red[REFINE_NACC];
   __shared__ PoseJac pj;
   __shared__ double param[6], prev_param[6], JtJ[21], JtE[6];
@@ -583,13 +643,17 @@ __device__ inline void pnp_refine(const float* __restrict__ X,
   for (int guard = 0; guard < 2000; ++guard) {
     const int state = s_state;       // 0: first linearisation, 1: candidate check, 2: done
     if (state == 2) break;
-    if (threadIdx.x == 0) pose_jacobian_setup(param, &pj);
+    if (dbg && guard == 1 && threadIdx.x == 0) dbg[4] = clock64();
+    if (threadIdx.x == 0) pose_jacobian_setup_k<0>(param, &pj);          // three warps, one dR/dr_k each
+    else if (threadIdx.x == 32) pose_jacobian_setup_k<1>(param, &pj);
+    else if (threadIdx.x == 64) pose_jacobian_setup_k<2>(param, &pj);
     __syncthreads();
+    if (dbg && guard == 1 && threadIdx.x == 0) dbg[5] = clock64();
     double acc[REFINE_NACC];
 #pragma unroll
     for (int k = 0; k < REFINE_NACC; ++k) acc[k] = 0.0;
     const double tx = param[3], ty = param[4], tz = param[5];
-    for (int q = threadIdx.x; q < m; q += REFINE_THREADS) {
+    for (int q = (int)crank * REFINE_THREADS + threadIdx.x; q < m; q += NCTA * REFINE_THREADS) {
       const int i = inliers[q];
       const double Xw[3] = {(double)X[3 * (size_t)i], (double)X[3 * (size_t)i + 1], (double)X[3 * (size_t)i + 2]};
       const double ox = (double)px[2 * (size_t)i], oy = (double)px[2 * (size_t)i + 1];
@@ -631,7 +695,22 @@ __device__ inline void pnp_refine(const float* __restrict__ X,
 #pragma unroll
       for (int a = 0; a < 6; ++a) acc[21 + a] += J[0][a] * ex + J[1][a] * ey;
     }
+    if (dbg && guard == 1 && threadIdx.x == 0) dbg[6] = clock64();
     block_reduce_acc(acc, sh, red);
+    if (NCTA > 1) {
+      const int par = guard & 1;
+      if (threadIdx.x < REFINE_NACC) part[par][threadIdx.x] = red[threadIdx.x];
+      asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+      asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+      if (threadIdx.x < REFINE_NACC) {
+        double t = 0.0;
+#pragma unroll
+        for (int r = 0; r < NCTA; ++r) t += pnp_ld_dsmem(&part[par][threadIdx.x], (uint32_t)r);
+        red[threadIdx.x] = t;
+      }
+      __syncthreads();
+    }
+    if (dbg && guard == 1 && threadIdx.x == 0) dbg[7] = clock64();
     if (threadIdx.x == 0) {
       const double err_norm = sqrt(red[27]);
       bool relinearise = (state == 0);
@@ -667,9 +746,13 @@ __device__ inline void pnp_refine(const float* __restrict__ X,
     }
     __syncthreads();
   }
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == 0 && crank == 0) {
     for (int k = 0; k < 3; ++k) { res->rvec[k] = param[k]; res->tvec[k] = param[3 + k]; }
     res->refine_iters = iters;
+  }
+  if (NCTA > 1) {        // nobody leaves while a peer may still read its partial sums
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
   }
 }
 
@@ -749,27 +832,12 @@ struct PoseOut {              // registration loop: what the next launches need,
   double* P;                  // 12: K [R|t]
   CamParams* cam;             // projectPoints operands of the reference's ReprojectionError (sfm.py:84,88)
   const double* K;            // 9 (device)
+  long long* dbg;             // diagnostics: clock64 at the phase boundaries of the tail kernel
 };
 
-// Tail of the RANSAC in ONE single-CTA launch: replay of the stopping rule (thread 0), the winner's
-// inlier list (stable compaction), the LM refinement.
-__global__ void __launch_bounds__(REFINE_THREADS) pnp_finish_kernel(const float* __restrict__ X, const float* __restrict__ px,
-                                                                    int n, const int* __restrict__ counts,
-                                                                    const unsigned char* __restrict__ valid, int H,
-                                                                    double conf, const double* __restrict__ poses,
-                                                                    const double* __restrict__ rt6, PnpCam cam, float thr2,
-                                                                    int refine_iters, int* __restrict__ inliers,
-                                                                    PnpResult* __restrict__ res,
-                                                                    const int* __restrict__ n_dev = nullptr,
-                                                                    PoseOut po = PoseOut()) {
-  if (n_dev) n = min(n, *n_dev);
-  if (threadIdx.x == 0) pnp_replay(counts, valid, n, H, conf, rt6, res);
-  __threadfence_block();
-  __syncthreads();
-  pnp_inliers(X, px, n, poses, cam, thr2, res, inliers);
-  if (refine_iters > 0) pnp_refine(X, px, inliers, cam, refine_iters, res);
-  __syncthreads();
-  if (threadIdx.x == 0 && po.pose6) {        // registration loop: the result stays in HBM
+// registration loop: the result stays in HBM — pose, counts, [R|t], K[R|t], projectPoints operands
+__device__ inline void pnp_publish(const PnpResult* __restrict__ res, const PoseOut& po) {
+  {
     double p6[6];
     for (int k = 0; k < 3; ++k) { p6[k] = res->rvec[k]; p6[3 + k] = res->tvec[k]; po.pose6[k] = p6[k]; po.pose6[3 + k] = p6[3 + k]; }
     *po.n_inl = res->ok ? res->n_inliers : 0;
@@ -799,6 +867,42 @@ __global__ void __launch_bounds__(REFINE_THREADS) pnp_finish_kernel(const float*
       po.cam->fx = K[0]; po.cam->fy = K[4]; po.cam->cx = K[2]; po.cam->cy = K[5];
     }
   }
+
+}
+
+// Tail of the RANSAC in ONE single-CTA launch: replay of the stopping rule (thread 0), the winner's
+// inlier list (stable compaction), the LM refinement.
+__global__ void __launch_bounds__(REFINE_THREADS) pnp_finish_kernel(const float* __restrict__ X, const float* __restrict__ px,
+                                                                    int n, const int* __restrict__ counts,
+                                                                    const unsigned char* __restrict__ valid, int H,
+                                                                    double conf, const double* __restrict__ poses,
+                                                                    const double* __restrict__ rt6, PnpCam cam, float thr2,
+                                                                    int refine_iters, int* __restrict__ inliers,
+                                                                    PnpResult* __restrict__ res,
+                                                                    const int* __restrict__ n_dev = nullptr,
+                                                                    PoseOut po = PoseOut()) {
+  if (n_dev) n = min(n, *n_dev);
+  auto tick = [&](int k) { if (po.dbg && threadIdx.x == 0) po.dbg[k] = clock64(); };
+  tick(0);
+  if (threadIdx.x == 0) pnp_replay(counts, valid, n, H, conf, rt6, res);
+  __threadfence_block();
+  __syncthreads();
+  tick(1);
+  pnp_inliers(X, px, n, poses, cam, thr2, res, inliers);
+  tick(2);
+  if (refine_iters > 0) pnp_refine<1>(X, px, inliers, cam, refine_iters, res, po.dbg);
+  __syncthreads();
+  tick(3);
+  if (threadIdx.x == 0 && po.pose6) pnp_publish(res, po);
+}
+
+// LM refinement over a cluster of CTAs (registration loop; the tail kernel has produced the inlier list).
+constexpr int REFINE_CLUSTER = 8;
+__global__ void __cluster_dims__(REFINE_CLUSTER, 1, 1) __launch_bounds__(REFINE_THREADS)
+    pnp_refine_cluster_kernel(const float* __restrict__ X, const float* __restrict__ px, const int* __restrict__ inliers,
+                              PnpCam cam, int refine_iters, PnpResult* __restrict__ res, PoseOut po) {
+  pnp_refine<REFINE_CLUSTER>(X, px, inliers, cam, refine_iters, res, nullptr);
+  if (threadIdx.x == 0 && pnp_cluster_rank() == 0 && po.pose6) pnp_publish(res, po);
 }
 
 static PnpCam make_pnp_cam(const double* K) {
@@ -925,9 +1029,18 @@ static int pnp_ransac_impl(sfm_ctx* ctx, const float* X, const float* px, int n,
   SFM_TRY(hs_alloc_t(ctx, 1, &hres));
   SFM_TRY(hs_alloc_t(ctx, (size_t)n, &hinl));
   // model_points == npoints (n == 5): OpenCV returns the EPnP pose of all five points, all inliers, no refinement
+  PoseOut po0 = PoseOut();
+  if (getenv("SFM_PNP_TIMELINE")) SFM_TRY(ws_alloc_t(ctx, 8, &po0.dbg));
   SFM_LAUNCH(ctx, SFM_K_PNP_REFINE, (pnp_finish_kernel<<<1, REFINE_THREADS, 0, ctx->stream>>>(
                                         dX, dpx, n, dcounts, n == 5 ? nullptr : dvalid, n == 5 ? 1 : H, confidence, dposes, drt6,
-                                        cam, thr2_eff, n == 5 ? 0 : 20, dinl, dres)));
+                                        cam, thr2_eff, n == 5 ? 0 : 20, dinl, dres, nullptr, po0)));
+  if (po0.dbg) {
+    long long hs[8];
+    SFM_CUDA(cudaMemcpyAsync(hs, po0.dbg, sizeof(hs), cudaMemcpyDeviceToHost, ctx->stream));
+    SFM_CUDA(cudaStreamSynchronize(ctx->stream));
+    fprintf(stderr, "[pnp tail cycles] replay %lld | inliers %lld | refine %lld  (second pass: setup %lld, accumulate %lld, reduce %lld)\n",
+            hs[1] - hs[0], hs[2] - hs[1], hs[3] - hs[2], hs[5] - hs[4], hs[6] - hs[5], hs[7] - hs[6]);
+  }
   // ---- single copy back (the inlier list only when the caller wants it on the host)
   SFM_CUDA(cudaMemcpyAsync(hres, dres, sizeof(PnpResult), cudaMemcpyDeviceToHost, ctx->stream));
   const bool inl_host = inliers && !sfm_is_device_ptr(inliers);
@@ -1008,9 +1121,18 @@ int sfm_pnp_ransac_dev(sfm_ctx* ctx, const float* X, const float* px, int n_cap,
                                                                                    nullptr, n_dev)));
   PoseOut po;
   po.pose6 = pose6_dev; po.n_inl = n_inl_dev; po.ok = ok_dev; po.Rt = Rt_dev; po.P = P_dev; po.cam = cam_dev; po.K = K_dev;
+  po.dbg = nullptr;
+  if (getenv("SFM_PNP_SINGLE_CTA_REFINE")) {
+    SFM_LAUNCH(ctx, SFM_K_PNP_REFINE, (pnp_finish_kernel<<<1, REFINE_THREADS, 0, ctx->stream>>>(
+                                          X, px, n_cap, dcounts, dvalid, H, 0.99, dposes, drt6, cam, thr2, 20, inliers_dev, dres,
+                                          n_dev, po)));
+    return SFM_OK;
+  }
   SFM_LAUNCH(ctx, SFM_K_PNP_REFINE, (pnp_finish_kernel<<<1, REFINE_THREADS, 0, ctx->stream>>>(
-                                        X, px, n_cap, dcounts, dvalid, H, 0.99, dposes, drt6, cam, thr2, 20, inliers_dev, dres, n_dev,
-                                        po)));
+                                        X, px, n_cap, dcounts, dvalid, H, 0.99, dposes, drt6, cam, thr2, 0, inliers_dev, dres, n_dev,
+                                        PoseOut())));
+  SFM_LAUNCH(ctx, SFM_K_PNP_REFINE, (pnp_refine_cluster_kernel<<<REFINE_CLUSTER, REFINE_THREADS, 0, ctx->stream>>>(
+                                        X, px, inliers_dev, cam, 20, dres, po)));
   return SFM_OK;
 }
 

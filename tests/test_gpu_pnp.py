@@ -176,7 +176,8 @@ def test_native_and_streamed_chain_equal_the_python_loop(engine, monkeypatch):
     """sfm_chain_run (the loop in the library) and register_host (chunked upload + sfm_chain_extend) run the same
     kernels in the same order as the Python loop.  With SFM_CHAIN_SYNC=1 (host reads counts and pose per view, as
     the Python loop does) the results are identical bit for bit; the default synchronisation-free loop forms the
-    pose matrices on the device (device libm / FMA contraction), so poses agree to ~1e-12 and points to ~1e-6."""
+    pose matrices on the device (device libm / FMA contraction) and sums the LM normal equations over a cluster of
+    CTAs (different summation order), so poses agree to ~1e-8 and points to ~1e-6 — four orders inside the 1e-4 bar."""
     import torch
     from sfm_mvs_b200 import pipeline
     scene = synth.orbit_scene(9, 1200, seed=7)
@@ -207,7 +208,8 @@ def test_native_and_streamed_chain_equal_the_python_loop(engine, monkeypatch):
             assert o["err_pnp"] == e[0] and o["err_new"] == e[1]
             assert torch.equal(o["X_new"][:o["n_new"]], a["X_new"][:a["n_new"]])
         for o in (d, f):
-            assert np.abs(o["Rt"] - a["Rt"]).max() < 1e-9
-            assert abs(o["err_pnp"] - e[0]) <= 1e-6 * e[0] and abs(o["err_new"] - e[1]) <= 1e-6 * e[1]
+            assert np.abs(o["Rt"] - a["Rt"]).max() < 1e-7
+            # (projections are rounded to float32 before the differences: a 1e-9 pose change moves a few by one ulp)
+            assert abs(o["err_pnp"] - e[0]) <= 1e-5 * e[0] and abs(o["err_new"] - e[1]) <= 1e-5 * e[1]
             xa, xo = a["X_new"][:a["n_new"]].cpu().numpy(), o["X_new"][:o["n_new"]].cpu().numpy()
             assert np.abs(xo - xa).max() <= 1e-5 * np.abs(xa).max()
