@@ -199,7 +199,7 @@ def run_engine(args):
                 clouds = [o["X_new"][:o["n_new"]].to("cpu", non_blocking=True) for o in outs]
             ctx.sync()
             return outs, sum(c.numel() * 4 for c in clouds) + len(outs) * (16 + 96)
-        views = [pipeline.DeviceView(ctx, k, d) for k, d in zip(kps, dess)]      # K1b descriptor prep inside
+        views = pipeline.DeviceView.batch(ctx, kps, dess)                        # K1b descriptor prep inside (one launch)
         chain = pipeline.RegistrationChain(ctx, K)
         outs = chain.run(views, Rt0, Rt1)
         return outs, 0

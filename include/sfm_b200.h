@@ -110,6 +110,10 @@ int sfm_debug_match_tc_timeline(sfm_ctx* ctx, const sfm_desc* q, const sfm_desc*
 /* Resident form: prepare a view's descriptors once (K1b), match many times.
  * dtype 0 = float32, 1 = uint8. */
 int sfm_desc_create(sfm_ctx* ctx, const void* data, int dtype, int n, int dim, sfm_desc** out);
+/* Many 128-D sets in ONE K1b launch: data[k] are DEVICE arrays of n[k] rows; out[k] come back resolved
+ * (one synchronisation for the whole batch). */
+int sfm_desc_create_batched(sfm_ctx* ctx, int count, const void* const* data, int dtype, const int32_t* n,
+                            int dim, sfm_desc** out);
 void sfm_desc_destroy(sfm_desc* d);
 int sfm_desc_rows(const sfm_desc* d);
 int sfm_desc_is_exact(const sfm_desc* d);   /* 1 if integer-valued in [0,255] (tensor path ok) */

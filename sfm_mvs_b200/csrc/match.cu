@@ -216,6 +216,61 @@ extern "C" int sfm_desc_create(sfm_ctx* ctx, const void* data, int dtype, int n,
   return SFM_OK;
 }
 
+static void desc_apply_flags(sfm_desc* d, unsigned int f) {
+  d->exact = (f & 1u) == 0;
+  bool tc = d->exact && !(f & 2u) && d->dim == 128 && d->n > 0 && d->buf->tiles;
+  d->tiles = tc ? d->buf->tiles : nullptr;
+  d->sqnorm = tc ? d->buf->sqnorm : nullptr;
+  d->n_tiles = tc ? (d->n + 127) / 128 : 0;
+  d->resolved = true;
+}
+
+// Many 128-dimensional descriptor sets (DEVICE sources) prepared by ONE K1b launch; the domain flags of the
+// whole batch come back in one copy and the sets are returned resolved.
+extern "C" int sfm_desc_create_batched(sfm_ctx* ctx, int count, const void* const* data, int dtype, const int32_t* n,
+                                       int dim, sfm_desc** out) {
+  SFM_REQUIRE(ctx && count >= 0 && (count == 0 || (data && n && out)), "sfm_desc_create_batched: null argument");
+  SFM_REQUIRE(dtype == 0 || dtype == 1, "sfm_desc_create_batched: dtype must be 0 (float32) or 1 (uint8)");
+  SFM_REQUIRE(dim == 128, "sfm_desc_create_batched: 128-dimensional descriptors only (use sfm_desc_create otherwise)");
+  if (count == 0) return SFM_OK;
+  SFM_TRY(sfm_ws_begin(ctx));
+  std::vector<sfm_desc*> ds((size_t)count, nullptr);
+  int s = SFM_OK;
+  for (int k = 0; k < count && s == SFM_OK; ++k) {
+    if (n[k] <= 0 || !data[k] || !sfm_is_device_ptr(data[k])) {
+      sfm_set_error("sfm_desc_create_batched: set %d must be a non-empty device array", k);
+      s = SFM_ERR_INVALID;
+      break;
+    }
+    DescBuf* b = nullptr;
+    s = descbuf_acquire(ctx, n[k], dim, &b);
+    if (s != SFM_OK) break;
+    sfm_desc* d = new sfm_desc();
+    d->ctx = ctx; d->n = n[k]; d->dim = dim; d->buf = b; d->f32 = b->f32;
+    ds[k] = d;
+  }
+  unsigned int* flags = nullptr;
+  unsigned int* hflags = nullptr;
+  if (s == SFM_OK) s = ws_alloc_t(ctx, (size_t)count, &flags);
+  if (s == SFM_OK) s = hs_alloc_t(ctx, (size_t)count, &hflags);
+  if (s == SFM_OK && cudaMemsetAsync(flags, 0, sizeof(unsigned int) * count, ctx->stream) != cudaSuccess) s = SFM_ERR_CUDA;
+  if (s == SFM_OK) s = sfm_desc_prepare_launch_batched(ctx, count, ds.data(), data, dtype, flags);
+  if (s == SFM_OK && (cudaMemcpyAsync(hflags, flags, sizeof(unsigned int) * count, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+                      cudaStreamSynchronize(ctx->stream) != cudaSuccess)) {
+    sfm_set_error("sfm_desc_create_batched: %s", cudaGetErrorString(cudaGetLastError()));
+    s = SFM_ERR_CUDA;
+  }
+  if (s != SFM_OK) {
+    for (sfm_desc* d : ds) sfm_desc_destroy(d);
+    return s;
+  }
+  for (int k = 0; k < count; ++k) {
+    desc_apply_flags(ds[k], hflags[k]);
+    out[k] = ds[k];
+  }
+  return SFM_OK;
+}
+
 int sfm_desc_resolve(sfm_desc* d) {
   if (d->resolved) return SFM_OK;
   SFM_CUDA(cudaEventSynchronize(d->buf->ready));

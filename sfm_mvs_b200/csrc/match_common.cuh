@@ -54,6 +54,8 @@ int sfm_match_tc_launch(sfm_ctx* ctx, const sfm_desc* q, const sfm_desc* t, mkey
 int sfm_match_tc_launch_batched(sfm_ctx* ctx, int npairs, const sfm_desc* const* q, const sfm_desc* const* t,
                                 mkey_t** cand_out, int* nsub_out);
 int sfm_desc_prepare_launch(sfm_ctx* ctx, sfm_desc* d, const void* src, int dtype);
+int sfm_desc_prepare_launch_batched(sfm_ctx* ctx, int count, sfm_desc* const* d, const void* const* src, int dtype,
+                                    unsigned int* flags_dev);
 // match.cu
 // qf/tf non-null: candidates come from the tensor-core kernel ([nq][nsplit][3]); null: [nq][nsplit][2]
 int sfm_match_finalize(sfm_ctx* ctx, const mkey_t* cand, int nq, int nt, int nsplit, double ratio,

@@ -89,6 +89,30 @@ class Descriptors:
         check(lib.sfm_desc_create(ctx._h, arg.ptr, dtype, self.n, self.dim, C.byref(h)))
         self._h = h
 
+    @classmethod
+    def _from_handle(cls, ctx: "Context", handle, n: int, dim: int):
+        self = cls.__new__(cls)
+        self.ctx, self._h, self.n, self.dim = ctx, handle, int(n), int(dim)
+        return self
+
+    @classmethod
+    def batch(cls, ctx: "Context", sets):
+        """Descriptors of many views (CUDA tensors, (n,128) float32 or uint8, one dtype) prepared by ONE K1b launch
+        (sfm_desc_create_batched).  Anything else falls back to one call per set."""
+        import torch
+        ok = len(sets) > 0 and all(_is_torch(d) and d.is_cuda and d.dim() == 2 and d.shape[1] == 128 and d.shape[0] > 0
+                                   and d.is_contiguous() for d in sets)
+        ok = ok and len({d.dtype for d in sets}) == 1 and sets[0].dtype in (torch.float32, torch.uint8)
+        if not ok:
+            return [cls(ctx, d) for d in sets]
+        count = len(sets)
+        ptrs = np.array([d.data_ptr() for d in sets], np.uint64)
+        ns = np.array([d.shape[0] for d in sets], np.int32)
+        out = np.zeros((count,), np.uint64)
+        check(lib.sfm_desc_create_batched(ctx._h, count, ptrs.ctypes.data, 1 if sets[0].dtype == torch.uint8 else 0,
+                                          ns.ctypes.data, 128, out.ctypes.data))
+        return [cls._from_handle(ctx, C.c_void_p(int(h)), int(k), 128) for h, k in zip(out, ns)]
+
     @property
     def exact(self) -> bool:
         return bool(lib.sfm_desc_is_exact(self._h))

@@ -33,7 +33,7 @@ def _on_ctx_stream(fn):
 class DeviceView:
     """A view's keypoints and prepared descriptors resident in HBM."""
 
-    def __init__(self, ctx: _e.Context, kp, des):
+    def __init__(self, ctx: _e.Context, kp, des, desc=None):
         import torch
         self.ctx = ctx
         self.n = int(len(kp))
@@ -42,7 +42,17 @@ class DeviceView:
                 self.kp = kp.to(device=ctx.torch_device, dtype=torch.float32).contiguous()
             else:
                 self.kp = torch.from_numpy(np.ascontiguousarray(kp, np.float32)).to(ctx.torch_device)
-        self.desc = ctx.descriptors(des)
+        self.desc = desc if desc is not None else ctx.descriptors(des)
+
+    @classmethod
+    def batch(cls, ctx: _e.Context, kps, dess):
+        """Views whose descriptors are CUDA tensors: ONE K1b launch prepares all of them."""
+        if dess and all(_e._is_torch(d) and d.is_cuda for d in dess):
+            import torch
+            with torch.cuda.stream(ctx.torch_stream()):
+                descs = _e.Descriptors.batch(ctx, list(dess))
+            return [cls(ctx, k, None, desc=d) for k, d in zip(kps, descs)]
+        return [cls(ctx, k, d) for k, d in zip(kps, dess)]
 
 
 # sfm_view_out (include/sfm_b200.h)
@@ -330,7 +340,7 @@ def register_host(ctx: _e.Context, K, kps, dess, Rt0, Rt1, chunk: int = 25, rati
     try:
         for (lo, hi), ev in zip(bounds, events):
             ts.wait_event(ev)
-            views += [DeviceView(ctx, kp_d[i], des_d[i]) for i in range(lo, hi)]
+            views += DeviceView.batch(ctx, kp_d[lo:hi], des_d[lo:hi])
             pairs = [(i, i + 1) for i in range(max(lo - 1, 0), hi - 1)]
             if not pairs:
                 continue

@@ -160,3 +160,29 @@ def test_batched_pairs_equal_single_pair_calls(engine):
     if sizes[0][1] > 2:
         cidx, _ = cvpath.knn2_arrays(sets[0][0], sets[0][1])
         assert np.array_equal(idx[0].cpu().numpy(), cidx)
+
+
+def test_batched_descriptor_preparation_equals_per_view(engine):
+    """sfm_desc_create_batched (one K1b launch for many views, mixed sizes) gives the same matches as per-view sets;
+    a non-integer set inside the batch is flagged and still matched by the fp32 kernel."""
+    import torch
+    rng = np.random.default_rng(5)
+    sets = [synth.sift_like_descriptors(n, seed=30 + k) for k, n in enumerate((700, 129, 1500, 256, 1))]
+    sets[3] = sets[3] + rng.random(sets[3].shape, dtype=np.float32) * 0.3
+    dev = engine.torch_device
+    with torch.cuda.stream(engine.torch_stream()):
+        tens = [torch.from_numpy(s).to(dev) for s in sets]
+    batch = sfm.Descriptors.batch(engine, tens)
+    single = [engine.descriptors(s) for s in sets]
+    assert [d.exact for d in batch] == [d.exact for d in single] == [True, True, True, False, True]
+    from sfm_mvs_b200._lib import check, lib
+    for a in range(len(sets) - 1):
+        n = sets[a].shape[0]
+        out = []
+        for q, t in ((batch[a], batch[a + 1]), (single[a], single[a + 1])):
+            idx = torch.zeros((n, 2), dtype=torch.int32, device=dev)
+            good = torch.zeros((n,), dtype=torch.uint8, device=dev)
+            check(lib.sfm_desc_match(engine._h, q._h, t._h, 0.7, idx.data_ptr(), None, good.data_ptr(), None, 0))
+            engine.sync()
+            out.append((idx.cpu().numpy(), good.cpu().numpy()))
+        assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
