@@ -195,10 +195,8 @@ def run_engine(args):
             # end to end through the public host-array entry: chunked upload on a copy stream overlapping
             # descriptor prep + batched match + registration (pipeline.register_host), clouds read back
             outs = pipeline.register_host(ctx, K, kps, dess, Rt0, Rt1)
-            with torch.cuda.stream(ts):
-                clouds = [o["X_new"][:o["n_new"]].to("cpu", non_blocking=True) for o in outs]
-            ctx.sync()
-            return outs, sum(c.numel() * 4 for c in clouds) + len(outs) * (16 + 96)
+            clouds = pipeline.fetch_clouds(ctx, outs)
+            return outs, sum(c.size * 4 for c in clouds) + len(outs) * (16 + 96)
         views = pipeline.DeviceView.batch(ctx, kps, dess)                        # K1b descriptor prep inside (one launch)
         chain = pipeline.RegistrationChain(ctx, K)
         outs = chain.run(views, Rt0, Rt1)

@@ -292,7 +292,8 @@ class NativeChain:
             o = out[v]
             outs.append(dict(Rt=o["Rt"].reshape(3, 4).copy(), X_new=X_all[int(off[v]):int(off[v + 1])], n_new=int(o["n_new"]),
                              n_pnp=int(o["n_pnp"]), n_inl=int(o["n_inl"]), n_match=int(o["n_match"]),
-                             err_pnp=float(o["err_pnp"]), err_new=float(o["err_new"])))
+                             err_pnp=float(o["err_pnp"]), err_new=float(o["err_new"]),
+                             _slab=(X_all, int(off[v]))))       # fetch_clouds copies a call's points back in one piece
         return outs
 
     def close(self):
@@ -306,6 +307,28 @@ class NativeChain:
             self.close()
         except Exception:
             pass
+
+
+def fetch_clouds(ctx: _e.Context, outs):
+    """New 3-D points of every registered view as host arrays: one device->host copy per sfm_chain_extend call (the
+    points of a call are one slab), not one per view."""
+    import torch
+    slabs, host = {}, {}
+    for o in outs:
+        if "_slab" in o:
+            slabs[id(o["_slab"][0])] = o["_slab"][0]
+    with torch.cuda.stream(ctx.torch_stream()):
+        for k, t in slabs.items():
+            host[k] = t.to("cpu", non_blocking=True)
+    ctx.sync()
+    clouds = []
+    for o in outs:
+        if "_slab" in o:
+            t, lo = o["_slab"]
+            clouds.append(host[id(t)][lo:lo + o["n_new"]].numpy())
+        else:
+            clouds.append(o["X_new"][:o["n_new"]].cpu().numpy())
+    return clouds
 
 
 def register_host(ctx: _e.Context, K, kps, dess, Rt0, Rt1, chunk: int = 25, ratio: float = 0.70):
@@ -324,7 +347,10 @@ def register_host(ctx: _e.Context, K, kps, dess, Rt0, Rt1, chunk: int = 25, rati
     cs = getattr(ctx, "_copy_stream", None)          # one upload stream per context: torch's caching allocator keeps a
     if cs is None:                                    # pool per stream, a fresh stream per call would cudaMalloc every buffer
         cs = ctx._copy_stream = torch.cuda.Stream(device=dev)
-    bounds = [(lo, min(lo + chunk, V)) for lo in range(0, V, chunk)]
+    # a short first chunk gets the loop going while the bulk of the upload is still in flight
+    edges = [0] + [e for e in (min(8, chunk), chunk) if e < V] + list(range(2 * chunk, V, chunk)) + [V]
+    edges = sorted(set(edges))
+    bounds = list(zip(edges[:-1], edges[1:]))
     kp_d, des_d, events = [None] * V, [None] * V, []
     with torch.cuda.stream(cs):
         for lo, hi in bounds:
@@ -372,8 +398,9 @@ def register_chain(scene, ctx: _e.Context | None = None, n_views: int | None = N
         dviews = [DeviceView(ctx, v["kp"], v["des"].astype(des_dtype, copy=False)) for v in views]
         chain = RegistrationChain(ctx, scene["K"], hypothesis_fn=hypothesis_fn)
         outs = chain.run(dviews, Rt0, Rt1)
-    with torch.cuda.stream(ctx.torch_stream()):
-        for o in outs:
-            o["X_new"] = o["X_new"][:o["n_new"]].cpu().numpy()
-            o.pop("_keep", None)
+    clouds = fetch_clouds(ctx, outs)
+    for o, c in zip(outs, clouds):
+        o["X_new"] = c
+        o.pop("_keep", None)
+        o.pop("_slab", None)
     return outs
