@@ -126,3 +126,27 @@ def test_ba_create_rejects_bad_input(engine):
         sfm.BAProblem(engine, 6, 300, pb["cam_idx"], pb["pt_idx"][::-1].copy(), pb["obs"], pb["K"])   # not point-major
     with pytest.raises(sfm.error):
         sfm.BAProblem(engine, 2, 300, pb["cam_idx"], pb["pt_idx"], pb["obs"], pb["K"])                 # cam index out of range
+
+
+def test_full_size_problem_by_properties(engine):
+    """BASELINE configs[3] (500 cameras / 100k points / 1M observations): properties instead of the oracle —
+    K5's cost equals the float64 sum of its own residuals, the Jacobian blocks of a sample of observations equal the
+    numpy restatement, and LM iterations decrease the cost monotonically on accepted steps."""
+    import torch
+    pb = synth.ba_problem(500, 100_000, 10, seed=0)
+    prob = sfm.BAProblem(engine, 500, 100_000, pb["cam_idx"], pb["pt_idx"], pb["obs"], pb["K"])
+    prob.set_params(pb["cams0"], pb["pts0"])
+    out = prob.eval(0)
+    r = out["r"].astype(np.float64)
+    assert abs(out["cost"] - 0.5 * (r * r).sum()) <= 1e-6 * out["cost"]
+    sel = np.random.default_rng(1).choice(len(pb["obs"]), 2000, replace=False)
+    rr, Jc, Jp = restated.ba_residual_jacobian(pb["cams0"], pb["pts0"], pb["cam_idx"][sel], pb["pt_idx"][sel], pb["obs"][sel], pb["K"])
+    assert np.abs(out["r"][sel] - rr).max() <= 1e-4 * np.abs(rr).max()
+    assert np.abs(out["Jc"][sel] - Jc).max() <= 1e-5 * np.abs(Jc).max()
+    assert np.abs(out["Jp"][sel] - Jp).max() <= 1e-5 * np.abs(Jp).max()
+    hist = prob.solve(max_iters=4)
+    for h in hist:
+        if h["accepted"]:
+            assert h["cost_after"] <= h["cost_before"]
+    assert hist[-1]["cost_after"] < hist[0]["cost_before"]
+    prob.close()

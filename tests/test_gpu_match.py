@@ -186,3 +186,34 @@ def test_batched_descriptor_preparation_equals_per_view(engine):
             engine.sync()
             out.append((idx.cpu().numpy(), good.cpu().numpy()))
         assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+
+
+@pytest.mark.parametrize("n", [16384, 65536])
+def test_full_size_pairs_by_properties(engine, n):
+    """BASELINE configs[4] sizes (up to 64k x 64k per pair; the oracle would take minutes): size-independent
+    properties.  train = a permutation of query plus distinct extra rows => every query's nearest neighbour is its own
+    copy at distance 0 with the index the permutation says; the runner-up is strictly farther; and the 2-NN of a
+    sample of query rows equals an exact brute-force evaluation (float64 on integer data) done with torch."""
+    import torch
+    rng = np.random.default_rng(n)
+    q = synth.sift_like_descriptors(n, seed=n % 97)
+    # make rows unique (the generator can repeat a row at this size): stamp the row index into two components
+    q[:, 0] = (np.arange(n) % 251).astype(np.float32)
+    q[:, 1] = ((np.arange(n) // 251) % 251).astype(np.float32)
+    q[:, 2] = ((np.arange(n) // (251 * 251)) % 251).astype(np.float32)
+    perm = rng.permutation(n)
+    t = q[perm]
+    inv = np.empty(n, np.int64); inv[perm] = np.arange(n)
+    idx, dist, good, ng = engine.knn2(q, t, 0.70, mode=2)
+    assert np.array_equal(idx[:, 0], inv), "nearest neighbour is not the permuted copy"
+    assert np.all(dist[:, 0] == 0) and np.all(dist[:, 1] > 0)
+    assert ng == n and good.all()                        # 0 < 0.7 * d2 everywhere
+    rows = rng.choice(n, 48, replace=False)
+    tq = torch.from_numpy(q[rows]).to("cuda", torch.float64)
+    tt = torch.from_numpy(t).to("cuda", torch.float64)
+    d2 = ((tq * tq).sum(1)[:, None] + (tt * tt).sum(1)[None, :] - 2.0 * tq @ tt.T)       # exact: integers < 2^53
+    key = d2 * float(n) + torch.arange(n, device="cuda", dtype=torch.float64)[None, :]     # (distance, index) order
+    top = torch.topk(key, 2, dim=1, largest=False).indices.cpu().numpy()
+    assert np.array_equal(idx[rows], top)
+    ref_d = np.sqrt(torch.gather(d2, 1, torch.from_numpy(top).to("cuda")).cpu().numpy().astype(np.float32))
+    assert np.array_equal(dist[rows], ref_d)

@@ -213,3 +213,35 @@ def test_native_and_streamed_chain_equal_the_python_loop(engine, monkeypatch):
             assert abs(o["err_pnp"] - e[0]) <= 1e-5 * e[0] and abs(o["err_new"] - e[1]) <= 1e-5 * e[1]
             xa, xo = a["X_new"][:a["n_new"]].cpu().numpy(), o["X_new"][:o["n_new"]].cpu().numpy()
             assert np.abs(xo - xa).max() <= 1e-5 * np.abs(xa).max()
+
+
+def test_registration_at_baseline_descriptor_count(engine):
+    """BASELINE configs[2] shape (5000 descriptors per view; 30 views here to stay in seconds): against the oracle's
+    loop (the reference's cv2 calls) — identical match and association counts for every view, poses and new points
+    agreeing far inside the drift of incremental SfM — and the host-array entry (chunked upload, batched K1b / K1,
+    sfm_chain_extend) against the resident driver."""
+    import torch
+    from oracle import cvpath
+    from sfm_mvs_b200 import pipeline
+    scene = synth.orbit_scene(30, 5000, seed=11)
+    K = scene["K"]
+    Rt0 = np.hstack([scene["views"][0]["R"], scene["views"][0]["t"]])
+    Rt1 = np.hstack([scene["views"][1]["R"], scene["views"][1]["t"]])
+    outs = pipeline.register_host(engine, K, [v["kp"] for v in scene["views"]], [v["des"] for v in scene["views"]], Rt0, Rt1,
+                                  chunk=7)
+    ref = cvpath.register_chain(scene)
+    assert len(outs) == len(ref) == 28
+    for o, r in zip(outs, ref):
+        assert (o["n_match"], o["n_pnp"]) == (r["n_match"], r["n_pnp"])
+        assert abs(o["n_inl"] - r["n_inl"]) <= 0.01 * r["n_inl"] and o["n_new"] == len(r["X_new"])
+        assert np.abs(o["Rt"] - r["Rt"]).max() < 2e-3            # different minimal solver, same LM fixed point up to its tolerance
+        assert abs(o["err_new"] - r["err_new"]) < 0.05 * r["err_new"] + 1e-4
+    dev = engine.torch_device
+    with torch.cuda.stream(engine.torch_stream()):
+        kps = [torch.from_numpy(v["kp"]).to(dev) for v in scene["views"]]
+        dess = [torch.from_numpy(v["des"]).to(dev) for v in scene["views"]]
+    res = pipeline.RegistrationChain(engine, K).run(pipeline.DeviceView.batch(engine, kps, dess), Rt0, Rt1)
+    assert len(res) == 28
+    for a, b in zip(outs, res):
+        assert (a["n_match"], a["n_pnp"], a["n_inl"], a["n_new"]) == (b["n_match"], b["n_pnp"], b["n_inl"], b["n_new"])
+        assert np.abs(a["Rt"] - b["Rt"]).max() < 1e-7
