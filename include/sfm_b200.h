@@ -204,6 +204,15 @@ void sfm_chain_destroy(sfm_chain* chain);
 int sfm_chain_extend(sfm_chain* chain, int n_pairs, const float* const* pts_q, const float* const* pts_t,
                      const int32_t* n_match, float* const* X_new, sfm_view_out* out, int32_t* n_registered);
 
+/* cv2.recoverPose(E, pts0, pts1, K)                      sfm.py:311, isfm.py:83, test.py:250:
+ * the four (R, t) decompositions of E, every correspondence triangulated against each (float64 DLT as K2) and
+ * kept when it lies in front of both cameras closer than `dist` (cv2's default 50); returns the decomposition
+ * with the most points, OpenCV's tie order.  pts: (n,2) float32 (dtype 0) or float64 (dtype 2), host or device.
+ * mask_in (n, nullable) restricts the count like cv2's in/out mask; mask_out (n) holds 255 / 0. */
+int sfm_recover_pose(sfm_ctx* ctx, const double* E, const void* pts1, const void* pts2, int dtype, int n,
+                     const double* K, double dist, const uint8_t* mask_in, double* R, double* t,
+                     uint8_t* mask_out, int32_t* n_good);
+
 /* ------------------------------------------------------------------ hot path 3a: PnP-RANSAC
  * Replaces cv2.solvePnPRansac(X, p, K, d, ...) with OpenCV's defaults, which is what the
  * reference gets                                                sfm.py:67, test.py:319.

@@ -9,7 +9,7 @@ from .engine import (BAProblem, Context, Descriptors, epnp, nccl_unique_id, rans
                      rodrigues_to_matrix, rodrigues_to_vector)
 from .cv2_compat import (NORM_L2, RATIO, SOLVEPNP_ITERATIVE, BFMatcher, BundleAdjustment, DMatch, PnP,  # noqa: F401
                          ReprojectionError, Triangulation, common_points, default_context, knn2,
-                         match_keypoints, patch_cv2, set_default_context, solvePnPRansac, triangulatePoints,
+                         match_keypoints, patch_cv2, recoverPose, set_default_context, solvePnPRansac, triangulatePoints,
                          unpatch_cv2)
 from . import ba  # noqa: F401
 

@@ -363,6 +363,141 @@ int sfm_reproj_error_dev(sfm_ctx* ctx, const float* X, int x_layout, const float
   return SFM_OK;
 }
 
+// ============================================================================ recoverPose (second half)
+// cv2.recoverPose(E, pts0, pts1, K) as the reference calls it (sfm.py:311, isfm.py:83, test.py:250): the cheirality
+// test of the four (R, t) decompositions of E.  Per correspondence and candidate: the pixels are normalised with K
+// in float64, the point is triangulated by the same 4x4 DLT / Jacobi SVD as K2, and the candidate keeps it when
+// z*w > 0, z/w < dist, and the depth in the second camera is in (0, dist) — the conditions and their order are
+// OpenCV's.  One thread per correspondence evaluates all four candidates; counts by ballot/popc + atomics.
+struct PoseCand {
+  double P[4][12];       // [R1|t], [R2|t], [R1|-t], [R2|-t]
+  double fx, fy, cx, cy, dist;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(128) recover_pose_kernel(PoseCand pc, const T* __restrict__ p1, const T* __restrict__ p2, int n,
+                                                           const unsigned char* __restrict__ mask_in,
+                                                           unsigned char* __restrict__ masks /*4 x n*/, int* __restrict__ counts) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  bool keep[4] = {false, false, false, false};
+  if (i < n) {
+    // (x - cx) / fx in float64, like points.col(0) = (points.col(0) - cx) / fx on a CV_64F matrix
+    const double x1 = __ddiv_rn(__dsub_rn((double)p1[2 * (size_t)i], pc.cx), pc.fx);
+    const double y1 = __ddiv_rn(__dsub_rn((double)p1[2 * (size_t)i + 1], pc.cy), pc.fy);
+    const double x2 = __ddiv_rn(__dsub_rn((double)p2[2 * (size_t)i], pc.cx), pc.fx);
+    const double y2 = __ddiv_rn(__dsub_rn((double)p2[2 * (size_t)i + 1], pc.cy), pc.fy);
+    const bool in = !mask_in || mask_in[i] != 0;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      const double* P = pc.P[c];
+      // rows of the DLT matrix: x P0[2] - P0[0], y P0[2] - P0[1] with P0 = [I|0]; then the same for the candidate
+      double At[4][4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const double p00 = (k == 0) ? 1.0 : 0.0, p01 = (k == 1) ? 1.0 : 0.0, p02 = (k == 2) ? 1.0 : 0.0;
+        At[k][0] = __dsub_rn(__dmul_rn(x1, p02), p00);
+        At[k][1] = __dsub_rn(__dmul_rn(y1, p02), p01);
+        At[k][2] = __dsub_rn(__dmul_rn(x2, P[8 + k]), P[k]);
+        At[k][3] = __dsub_rn(__dmul_rn(y2, P[8 + k]), P[4 + k]);
+      }
+      double Q[4];
+      dlt_null_vector(At, Q);
+      bool m = __dmul_rn(Q[2], Q[3]) > 0.0;
+      const double X = __ddiv_rn(Q[0], Q[3]), Y = __ddiv_rn(Q[1], Q[3]), Z = __ddiv_rn(Q[2], Q[3]);
+      m = m && (Z < pc.dist);
+      // depth in the second camera: row 2 of P * (X, Y, Z, 1)
+      const double z2 = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(P[8], X), __dmul_rn(P[9], Y)), __dmul_rn(P[10], Z)), P[11]);
+      m = m && (z2 > 0.0) && (z2 < pc.dist);
+      keep[c] = m && in;
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    if (i < n) masks[(size_t)c * n + i] = keep[c] ? 255 : 0;
+    const unsigned b = __ballot_sync(0xffffffffu, keep[c]);
+    if ((threadIdx.x & 31) == 0 && b) atomicAdd(counts + c, __popc(b));
+  }
+}
+
+extern "C" int sfm_recover_pose(sfm_ctx* ctx, const double* E, const void* pts1, const void* pts2, int dtype, int n,
+                                const double* K, double dist, const uint8_t* mask_in, double* R, double* t,
+                                uint8_t* mask_out, int32_t* n_good) {
+  SFM_REQUIRE(ctx && E && pts1 && pts2 && K && R && t, "sfm_recover_pose: null argument");
+  SFM_REQUIRE(n >= 1, "sfm_recover_pose: need at least one correspondence");
+  SFM_REQUIRE(dtype == 0 || dtype == 2, "sfm_recover_pose: points must be float32 (0) or float64 (2)");
+  SFM_TRY(sfm_ws_begin(ctx));
+  // decomposeEssentialMat: E = U diag(1,1,0) V^T, det(U), det(V^T) made positive, R1 = U W V^T, R2 = U W^T V^T, t = u3
+  double U[9], W3[3], Vt[9];
+  hm::svd_square<3>(E, U, W3, Vt);
+  auto det3 = [](const double* M) {
+    return M[0] * (M[4] * M[8] - M[5] * M[7]) - M[1] * (M[3] * M[8] - M[5] * M[6]) + M[2] * (M[3] * M[7] - M[4] * M[6]);
+  };
+  if (det3(U) < 0) for (double& v : U) v = -v;
+  if (det3(Vt) < 0) for (double& v : Vt) v = -v;
+  const double Wm[9] = {0, 1, 0, -1, 0, 0, 0, 0, 1};
+  double UW[9], UWt[9], R1[9], R2[9], tv[3] = {U[2], U[5], U[8]};
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      double a = 0.0, b = 0.0;
+      for (int k = 0; k < 3; ++k) { a += U[3 * i + k] * Wm[3 * k + j]; b += U[3 * i + k] * Wm[3 * j + k]; }
+      UW[3 * i + j] = a; UWt[3 * i + j] = b;
+    }
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      double a = 0.0, b = 0.0;
+      for (int k = 0; k < 3; ++k) { a += UW[3 * i + k] * Vt[3 * k + j]; b += UWt[3 * i + k] * Vt[3 * k + j]; }
+      R1[3 * i + j] = a; R2[3 * i + j] = b;
+    }
+  PoseCand pc;
+  for (int c = 0; c < 4; ++c) {
+    const double* Rc = (c & 1) ? R2 : R1;
+    const double sg = (c & 2) ? -1.0 : 1.0;
+    for (int i = 0; i < 3; ++i) {
+      for (int j = 0; j < 3; ++j) pc.P[c][4 * i + j] = Rc[3 * i + j];
+      pc.P[c][4 * i + 3] = sg * tv[i];
+    }
+  }
+  pc.fx = K[0]; pc.fy = K[4]; pc.cx = K[2]; pc.cy = K[5]; pc.dist = dist;
+  const size_t esz = dtype == 0 ? sizeof(float) : sizeof(double);
+  const void *d1 = pts1, *d2 = pts2;
+  if (!sfm_is_device_ptr(pts1)) { char* p; SFM_TRY(ws_alloc_t(ctx, 2 * (size_t)n * esz, &p)); SFM_CUDA(cudaMemcpyAsync(p, pts1, 2 * (size_t)n * esz, cudaMemcpyHostToDevice, ctx->stream)); d1 = p; }
+  if (!sfm_is_device_ptr(pts2)) { char* p; SFM_TRY(ws_alloc_t(ctx, 2 * (size_t)n * esz, &p)); SFM_CUDA(cudaMemcpyAsync(p, pts2, 2 * (size_t)n * esz, cudaMemcpyHostToDevice, ctx->stream)); d2 = p; }
+  const uint8_t* dmask = nullptr;
+  SFM_TRY(dev_in(ctx, mask_in, (size_t)n, &dmask));
+  unsigned char* masks;
+  int* counts;
+  SFM_TRY(ws_alloc_t(ctx, (size_t)4 * n, &masks));
+  SFM_TRY(ws_alloc_t(ctx, 4, &counts));
+  SFM_CUDA(cudaMemsetAsync(counts, 0, 4 * sizeof(int), ctx->stream));
+  if (dtype == 0)
+    SFM_LAUNCH(ctx, SFM_K_TRIANGULATE, (recover_pose_kernel<float><<<div_up(n, 128), 128, 0, ctx->stream>>>(
+                                           pc, (const float*)d1, (const float*)d2, n, dmask, masks, counts)));
+  else
+    SFM_LAUNCH(ctx, SFM_K_TRIANGULATE, (recover_pose_kernel<double><<<div_up(n, 128), 128, 0, ctx->stream>>>(
+                                           pc, (const double*)d1, (const double*)d2, n, dmask, masks, counts)));
+  int* hc;
+  SFM_TRY(hs_alloc_t(ctx, 4, &hc));
+  SFM_CUDA(cudaMemcpyAsync(hc, counts, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  SFM_CUDA(cudaStreamSynchronize(ctx->stream));
+  // OpenCV's choice: the first candidate (order R1|t, R2|t, R1|-t, R2|-t) whose count is >= all others
+  const int g1 = hc[0], g2 = hc[1], g3 = hc[2], g4 = hc[3];
+  int win = 3;
+  if (g1 >= g2 && g1 >= g3 && g1 >= g4) win = 0;
+  else if (g2 >= g1 && g2 >= g3 && g2 >= g4) win = 1;
+  else if (g3 >= g1 && g3 >= g2 && g3 >= g4) win = 2;
+  const double* Rw = (win & 1) ? R2 : R1;
+  for (int k = 0; k < 9; ++k) R[k] = Rw[k];
+  for (int k = 0; k < 3; ++k) t[k] = ((win & 2) ? -1.0 : 1.0) * tv[k];
+  if (n_good) *n_good = hc[win];
+  if (mask_out) {
+    const bool dev = sfm_is_device_ptr(mask_out);
+    SFM_CUDA(cudaMemcpyAsync(mask_out, masks + (size_t)win * n, (size_t)n, dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
+                             ctx->stream));
+    if (!dev) SFM_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  return SFM_OK;
+}
+
 // ============================================================================ common_points
 // `np.where(pts2 == pts1[i])[0][0]` (sfm.py:221-226): the first row j of pts2 whose x equals pts1[i].x
 // OR whose y equals pts1[i].y (element-wise comparison — the reference's quirk), float32 equality.

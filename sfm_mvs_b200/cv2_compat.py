@@ -122,6 +122,40 @@ def triangulatePoints(projMatr1, projMatr2, projPoints1, projPoints2, ctx: _e.Co
     return (ctx or default_context()).triangulate(P1, P2, x1, x2, 0, 0, False)
 
 
+def recoverPose(E, points1, points2, cameraMatrix, R=None, t=None, mask=None, distanceThresh: float = 50.0,
+                ctx: _e.Context | None = None):
+    """cv2.recoverPose(E, pts0, pts1, K) as the reference calls it (sfm.py:311, isfm.py:83, test.py:250):
+    -> (number of points passing the cheirality test, R (3,3), t (3,1), mask (N,1) uint8 with 255 = kept).
+    points: (N,2) / (N,1,2) float32 or float64.  A given `mask` restricts the test to its non-zero rows (in/out
+    argument of cv2)."""
+    import ctypes as C
+    from ._lib import check, lib
+    ctx = ctx or default_context()
+    p1, p2 = np.asarray(points1), np.asarray(points2)
+    if p1.dtype not in (np.float32, np.float64):
+        p1 = p1.astype(np.float64)
+    p2 = p2.astype(p1.dtype, copy=False)
+    p1 = np.ascontiguousarray(p1.reshape(-1, 2))
+    p2 = np.ascontiguousarray(p2.reshape(-1, 2))
+    if p1.shape != p2.shape or p1.shape[0] < 1:
+        raise error(-1, "recoverPose: point arrays must both be (N,2) with N >= 1")
+    E = np.ascontiguousarray(E, np.float64)
+    K = np.ascontiguousarray(cameraMatrix, np.float64)
+    if E.shape != (3, 3) or K.shape != (3, 3):
+        raise error(-1, "recoverPose: E and cameraMatrix must be 3x3")
+    n = p1.shape[0]
+    m_in = None if mask is None else np.ascontiguousarray(np.asarray(mask).reshape(-1) != 0, np.uint8)
+    if m_in is not None and m_in.shape[0] != n:
+        raise error(-1, "recoverPose: mask length differs from the number of points")
+    Rm, tv = np.zeros((3, 3)), np.zeros((3, 1))
+    m_out = np.zeros((n, 1), np.uint8)
+    good = C.c_int32(0)
+    check(lib.sfm_recover_pose(ctx._h, _e._dptr(E), _e._dptr(p1), _e._dptr(p2), 0 if p1.dtype == np.float32 else 2, n,
+                               _e._dptr(K), float(distanceThresh), None if m_in is None else _e._dptr(m_in), _e._dptr(Rm),
+                               _e._dptr(tv), _e._dptr(m_out), C.byref(good)))
+    return int(good.value), Rm, tv, m_out
+
+
 def Triangulation(P1, P2, pts1, pts2, K=None, repeat=False, ctx: _e.Context | None = None):
     """sfm.py:45-56 — returns (pts1 as 2xN, pts2 as 2xN, cloud 4xN with row 3 == 1)."""
     a = pts1 if repeat else pts1.T
@@ -222,10 +256,12 @@ def patch_cv2(cv2_module=None):
     function definitions run unmodified on the GPU.  Returns a dict of the originals (to undo)."""
     import cv2 as _cv2
     m = cv2_module or _cv2
-    saved = dict(BFMatcher=m.BFMatcher, triangulatePoints=m.triangulatePoints, solvePnPRansac=m.solvePnPRansac)
+    saved = dict(BFMatcher=m.BFMatcher, triangulatePoints=m.triangulatePoints, solvePnPRansac=m.solvePnPRansac,
+                 recoverPose=m.recoverPose)
     m.BFMatcher = BFMatcher
     m.triangulatePoints = triangulatePoints
     m.solvePnPRansac = solvePnPRansac
+    m.recoverPose = recoverPose
     return saved
 
 

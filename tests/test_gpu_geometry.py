@@ -102,3 +102,34 @@ def test_common_points_equals_reference_semantics(engine, n1, n2, seed):
     r1, r2, rA, rB = cvpath.common_points(A, B, Cc)
     assert np.array_equal(i1, r1.astype(np.int64).reshape(-1)) and np.array_equal(i2, r2.astype(np.int64).reshape(-1))
     assert np.array_equal(tA, rA) and np.array_equal(tB, rB)
+
+
+@pytest.mark.parametrize("n,seed,dtype", [(800, 0, np.float32), (2500, 1, np.float32), (300, 2, np.float64), (50, 3, np.float32)])
+def test_recover_pose_equals_cv2(engine, n, seed, dtype):
+    """cv2.recoverPose (sfm.py:311): same R, t, count and per-point mask.  Synthetic two-view geometry with pixel
+    noise, 10 % gross outliers (behind-camera / wrong-depth cases for the cheirality test) and an essential matrix
+    from cv2.findEssentialMat, exactly the reference's sequence."""
+    rng = np.random.default_rng(seed)
+    K = synth.K_GUSTAV
+    X = np.column_stack([rng.uniform(-4, 4, n), rng.uniform(-3, 3, n), rng.uniform(4, 40, n)])
+    rvec = np.array([0.03, -0.25, 0.02]); tvec = np.array([1.0, 0.1, 0.2])
+    R_gt = cv2.Rodrigues(rvec)[0]
+    def proj(Xc):
+        return np.column_stack([K[0, 0] * Xc[:, 0] / Xc[:, 2] + K[0, 2], K[1, 1] * Xc[:, 1] / Xc[:, 2] + K[1, 2]])
+    p1 = proj(X) + rng.normal(0, 0.3, (n, 2))
+    p2 = proj(X @ R_gt.T + tvec) + rng.normal(0, 0.3, (n, 2))
+    bad = rng.choice(n, n // 10, replace=False)
+    p2[bad] += rng.uniform(-150, 150, (len(bad), 2))
+    p1, p2 = p1.astype(dtype), p2.astype(dtype)
+    E, emask = cv2.findEssentialMat(p1, p2, K, method=cv2.RANSAC, prob=0.999, threshold=0.4, mask=None)
+    E = E[:3]
+    for use_mask in (False, True):
+        if use_mask:
+            rc, Rc, tc, mc = cv2.recoverPose(E, p1, p2, K, mask=emask.copy())
+            ro, Ro, to, mo = sfm.recoverPose(E, p1, p2, K, mask=emask.copy(), ctx=engine)
+        else:
+            rc, Rc, tc, mc = cv2.recoverPose(E, p1, p2, K)
+            ro, Ro, to, mo = sfm.recoverPose(E, p1, p2, K, ctx=engine)
+        assert np.abs(Ro - Rc).max() < 1e-9 and np.abs(to - tc).max() < 1e-9
+        assert ro == rc
+        assert np.array_equal(mo.ravel() != 0, mc.ravel() != 0)
