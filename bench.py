@@ -251,7 +251,11 @@ def run_engine(args):
         ach = flops / t_launch / 1e12
         roofline = {"kernel": "match_tc_kernel (K1 tcgen05 distance GEMM + top-2 epilogue)", "bound": "tensor",
                     "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": ach / pk["bf16_sustained"],
-                    "traffic": None, "peak_source": pk["source"] + ", sustained bf16 (kernel timed inside a long step)",
+                    # dram__bytes_read.sum + dram__bytes_write.sum of this very launch (199 pairs x 5000 descriptors) from
+                    # one ncu --set full capture: profiles/r1v_match_tc_bench_199x5k.txt (327.9 + 84.1 MB); other sizes: null
+                    "traffic": 412.06e6 if (V == 200 and n == 5000) else None,
+                    "traffic_unit": "bytes per launch (ncu, profiles/r1v_match_tc_bench_199x5k.txt)",
+                    "peak_source": pk["source"] + ", sustained bf16 (kernel timed inside a long step)",
                     "algorithmic_flops_per_launch": flops, "pairs_per_launch": V - 1, "avg_launch_us": 1e6 * t_launch,
                     "launches": mt["launches"],
                     "note": "K1 is the path's dense contraction (the kernel north_star sets a tensor-pipe target for). By time the "
@@ -364,7 +368,9 @@ def bench_ba(args, ctx, world, rank, pk, barrier, max_over_ranks):
            "accepted": [bool(h["accepted"]) for h in hist],
            "iter_kernel_ms": {k: round(v["ms"], 3) for k, v in prof2.items()},
            "roofline_eval": {"kernel": "ba_eval_kernel (K5 residual + Jacobian blocks, materialised)", "bound": "hbm",
-                             "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"], "traffic": None,
+                             "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"],
+                             # ncu capture under the same flush conditions: profiles/r1d_ba_eval_kernel.txt (5.0 MB read + 74.0 MB written)
+                             "traffic": 79.0e6 if (world == 1 and O == 1_000_000) else None,
                              "algorithmic_bytes_per_launch": 96.0 * O, "avg_launch_us": 1e6 * t_eval,
                              "l2_policy": "256 MB flush between timed launches", "peak_source": pk["source"]}}
     prob.close()
