@@ -330,3 +330,55 @@ def ba_schur(r, Jc, Jp, cam_idx, pt_idx, n_cam, n_pt, lam: float = 0.0):
                 cb = cam_idx[ob]
                 S[6 * ca:6 * ca + 6, 6 * cb:6 * cb + 6] -= W[a] @ Hinv @ W[b].T
     return S, g, Hcc, bc, Hpp, bp
+
+
+# ------------------------------------------------------------------ recoverPose (sfm.py:311, isfm.py:83, test.py:250)
+def recover_pose(E, p1, p2, K, dist: float = 50.0, mask=None):
+    """Published algorithm of cv2.recoverPose restated in numpy (OpenCV 4.x, calib3d/five-point.cpp): normalise the
+    pixels with K, decompose E = U diag(1,1,0) V^T into R1 = U W V^T, R2 = U W^T V^T, t = u3 (det(U), det(V^T) made
+    positive), triangulate every correspondence against [R1|t], [R2|t], [R1|-t], [R2|-t] (DLT, smallest right
+    singular vector) and keep it when z*w > 0, z/w < dist and the depth in the second camera is in (0, dist); the
+    first candidate whose count is >= all others wins.  -> (count, R, t (3,1), mask (N,) bool)."""
+    E = np.asarray(E, np.float64)
+    K = np.asarray(K, np.float64)
+    a = np.asarray(p1, np.float64).reshape(-1, 2).copy()
+    b = np.asarray(p2, np.float64).reshape(-1, 2).copy()
+    for q in (a, b):
+        q[:, 0] = (q[:, 0] - K[0, 2]) / K[0, 0]
+        q[:, 1] = (q[:, 1] - K[1, 2]) / K[1, 1]
+    U, _, Vt = np.linalg.svd(E)
+    if np.linalg.det(U) < 0:
+        U = -U
+    if np.linalg.det(Vt) < 0:
+        Vt = -Vt
+    W = np.array([[0.0, 1.0, 0.0], [-1.0, 0.0, 0.0], [0.0, 0.0, 1.0]])
+    R1, R2, t = U @ W @ Vt, U @ W.T @ Vt, U[:, 2].copy()
+    n = len(a)
+    keep_in = np.ones(n, bool) if mask is None else (np.asarray(mask).reshape(-1) != 0)
+    P0 = np.hstack([np.eye(3), np.zeros((3, 1))])
+    cands = [(R1, t), (R2, t), (R1, -t), (R2, -t)]
+    masks = []
+    for R, tt in cands:
+        P = np.hstack([R, tt.reshape(3, 1)])
+        A = np.empty((n, 4, 4))
+        A[:, 0] = a[:, 0:1] * P0[2] - P0[0]
+        A[:, 1] = a[:, 1:2] * P0[2] - P0[1]
+        A[:, 2] = b[:, 0:1] * P[2] - P[0]
+        A[:, 3] = b[:, 1:2] * P[2] - P[1]
+        Q = np.linalg.svd(A)[2][:, 3, :]                 # (n,4) null vectors
+        m = Q[:, 2] * Q[:, 3] > 0
+        Xh = Q / Q[:, 3:4]
+        m &= Xh[:, 2] < dist
+        z2 = Xh @ P[2]
+        m &= (z2 > 0) & (z2 < dist)
+        masks.append(m & keep_in)
+    g = [int(m.sum()) for m in masks]
+    if g[0] >= g[1] and g[0] >= g[2] and g[0] >= g[3]:
+        w = 0
+    elif g[1] >= g[0] and g[1] >= g[2] and g[1] >= g[3]:
+        w = 1
+    elif g[2] >= g[0] and g[2] >= g[1] and g[2] >= g[3]:
+        w = 2
+    else:
+        w = 3
+    return g[w], cands[w][0], cands[w][1].reshape(3, 1), masks[w]

@@ -133,3 +133,5 @@ def test_recover_pose_equals_cv2(engine, n, seed, dtype):
         assert np.abs(Ro - Rc).max() < 1e-9 and np.abs(to - tc).max() < 1e-9
         assert ro == rc
         assert np.array_equal(mo.ravel() != 0, mc.ravel() != 0)
+        rr, Rr, tr, mr = restated.recover_pose(E, p1, p2, K, mask=emask if use_mask else None)     # the oracle agrees too
+        assert rr == ro and np.array_equal(mr, mo.ravel() != 0)

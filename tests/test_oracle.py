@@ -164,3 +164,29 @@ def test_chain_port_equals_reference_loop(golden):
     assert np.array_equal(np.array([o["err_new"] for o in outs]), g["err_new"])
     assert np.array_equal(np.array([o["err_pnp"] for o in outs]), g["err_pnp"])
     assert np.array_equal(np.vstack([o["X_new"] for o in outs]), g["X_new"])
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_restated_recover_pose_equals_cv2(seed):
+    """The numpy restatement of cv2.recoverPose (sfm.py:311) against cv2 itself: same pose, count and mask."""
+    rng = np.random.default_rng(seed)
+    K = synth.K_GUSTAV
+    n = 600
+    X = np.column_stack([rng.uniform(-4, 4, n), rng.uniform(-3, 3, n), rng.uniform(4, 40, n)])
+    R_gt = cv2.Rodrigues(np.array([0.03, -0.25, 0.02]))[0]
+    t_gt = np.array([1.0, 0.1, 0.2])
+    proj = lambda Y: np.column_stack([K[0, 0] * Y[:, 0] / Y[:, 2] + K[0, 2], K[1, 1] * Y[:, 1] / Y[:, 2] + K[1, 2]])
+    p1 = (proj(X) + rng.normal(0, 0.3, (n, 2))).astype(np.float32)
+    p2 = proj(X @ R_gt.T + t_gt) + rng.normal(0, 0.3, (n, 2))
+    bad = rng.choice(n, n // 10, replace=False)
+    p2[bad] += rng.uniform(-150, 150, (len(bad), 2))
+    p2 = p2.astype(np.float32)
+    E, emask = cv2.findEssentialMat(p1, p2, K, method=cv2.RANSAC, prob=0.999, threshold=0.4, mask=None)
+    E = E[:3]
+    rc, Rc, tc, mc = cv2.recoverPose(E, p1, p2, K)
+    ro, Ro, to, mo = restated.recover_pose(E, p1, p2, K)
+    assert ro == rc and np.abs(Ro - Rc).max() < 1e-9 and np.abs(to - tc).max() < 1e-9
+    assert np.array_equal(mo, mc.ravel() != 0)
+    rc, Rc, tc, mc = cv2.recoverPose(E, p1, p2, K, mask=emask.copy())
+    ro, Ro, to, mo = restated.recover_pose(E, p1, p2, K, mask=emask)
+    assert ro == rc and np.array_equal(mo, mc.ravel() != 0)
