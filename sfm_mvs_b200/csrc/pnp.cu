@@ -131,6 +131,9 @@ struct EpnpShared {
   double cs[12];        // (c, s) of the 6 rotations of a round
   double alphas[20], pw[15], us[10], cws[12], L[60], rho[6], v4[48];
   int pq[12];
+  // mixed-precision eigen-decomposition: float32 sweeps first (Af, Vf), float64 polish afterwards (T = scratch)
+  double T[144];
+  float Af[144], Vf[144], csf[12];
 };
 
 // Parallel-ordered two-sided Jacobi: a round rotates 6 disjoint index pairs at once.  With disjoint
@@ -140,13 +143,18 @@ struct EpnpShared {
 // float64 divisions and one square root of the textbook form (t = sgn(a) b / (|a| + hypot(a, b)),
 // c = rsqrt(1 + t^2)); the sweep stops at off^2 <= 1e-28 diag^2 (off/diag ~ 1e-14: the null-space
 // basis inside the degenerate eigenvalue is arbitrary anyway, see DESIGN.md "PnP parity").
-__device__ __forceinline__ void warp_jacobi12(EpnpShared& sh, int lane) {
-  for (int i = lane; i < 144; i += 32) sh.V[i] = (i / 12 == i % 12) ? 1.0 : 0.0;
-  __syncwarp();
-  for (int sweep = 0; sweep < 40; ++sweep) {
-    double off = 0.0, diag = 0.0;
+// One sweep-loop of the parallel-ordered Jacobi in precision T on (A, V) in shared memory; V must hold an
+// orthonormal start (identity or a previous estimate).  Stops when off^2 <= tol * diag^2 or after max_sweeps.
+#define JDBG 0
+__device__ long long g_jdbg[2];
+template <typename T>
+__device__ __forceinline__ int jacobi_sweeps(T* __restrict__ A, T* __restrict__ V, T* __restrict__ cs, int* __restrict__ pq,
+                                             int lane, int max_sweeps, T tol) {
+  int sweep = 0;
+  for (; sweep < max_sweeps; ++sweep) {
+    T off = 0, diag = 0;
     for (int i = lane; i < 144; i += 32) {
-      double a = sh.A[i];
+      const T a = A[i];
       if (i / 12 == i % 12) diag += a * a; else off += a * a;
     }
 #pragma unroll
@@ -154,68 +162,172 @@ __device__ __forceinline__ void warp_jacobi12(EpnpShared& sh, int lane) {
       off += __shfl_xor_sync(0xffffffffu, off, o);
       diag += __shfl_xor_sync(0xffffffffu, diag, o);
     }
-    if (off * 0.5 <= 1e-28 * diag || off == 0.0) break;
+    if (off * (T)0.5 <= tol * diag || off == (T)0) break;
     for (int round = 0; round < 11; ++round) {
+      long long tq0 = 0, tq1 = 0;
+      if (JDBG && sweep == 1 && round == 3) tq0 = clock64();
       if (lane < 6) {
         int p = round + lane, q = round - lane + 11;          // (round +- lane) mod 11 without a division
         p -= (p >= 11) ? 11 : 0;
         q -= (q >= 11) ? 11 : 0;
         if (lane == 0) { p = 11; q = round; }
         if (p > q) { int t = p; p = q; q = t; }
-        const double apq = sh.A[p * 12 + q], app = sh.A[p * 12 + p], aqq = sh.A[q * 12 + q];
-        double c = 1.0, s = 0.0;
-        if (fabs(apq) > 1e-150) {
-          // t = apq / (al + sgn(al) hypot(al, apq)) with one reciprocal square root (hypot = s2 rsqrt(s2)) and a
-          // Newton reciprocal seeded in float32 — no float64 division or square root on this dependent chain;
-          // (c, s) = (rsqrt(1 + t^2), t c) is orthogonal to working precision whatever the error of t.
-          const double al = 0.5 * (aqq - app);
-          const double s2 = al * al + apq * apq;
-          const double r = s2 * rsqrt(s2);
-          const double den = al + (al >= 0.0 ? r : -r);
-          double id = (double)(1.0f / (float)den);
-          id = id * (2.0 - den * id);
-          id = id * (2.0 - den * id);
-          const double t = (fabs(den) > 1e-30 && fabs(den) < 1e30) ? apq * id : apq / den;
-          c = rsqrt(t * t + 1.0);
-          s = t * c;
+        const T apq = A[p * 12 + q], app = A[p * 12 + p], aqq = A[q * 12 + q];
+        T c = 1, s = 0;
+        if (sizeof(T) == 8) {
+          if (fabs((double)apq) > 1e-150) {
+            // t = apq / (al + sgn(al) hypot(al, apq)) with one reciprocal square root (hypot = s2 rsqrt(s2)) and a
+            // Newton reciprocal seeded in float32 — no float64 division or square root on this dependent chain;
+            // (c, s) = (rsqrt(1 + t^2), t c) is orthogonal to working precision whatever the error of t.
+            const double al = 0.5 * ((double)aqq - (double)app), bq = (double)apq;
+            const double s2 = al * al + bq * bq;
+            const double r = s2 * rsqrt(s2);
+            const double den = al + (al >= 0.0 ? r : -r);
+            double id = (double)(1.0f / (float)den);
+            id = id * (2.0 - den * id);
+            id = id * (2.0 - den * id);
+            const double t = (fabs(den) > 1e-30 && fabs(den) < 1e30) ? bq * id : bq / den;
+            const double cc = rsqrt(t * t + 1.0);
+            c = (T)cc;
+            s = (T)(t * cc);
+          }
+        } else {
+          const float bq = (float)apq;
+          if (fabsf(bq) > 1e-30f) {
+            const float al = 0.5f * ((float)aqq - (float)app);
+            const float s2 = al * al + bq * bq;
+            const float r = s2 * rsqrtf(s2);
+            const float t = __fdividef(bq, al + (al >= 0.f ? r : -r));
+            const float cc = rsqrtf(t * t + 1.f);
+            c = (T)cc;
+            s = (T)(t * cc);
+          }
         }
-        sh.cs[2 * lane] = c; sh.cs[2 * lane + 1] = s;
-        sh.pq[2 * lane] = p; sh.pq[2 * lane + 1] = q;
+        cs[2 * lane] = c; cs[2 * lane + 1] = s;
+        pq[2 * lane] = p; pq[2 * lane + 1] = q;
       }
       __syncwarp();
-      // 36 blocks: rows (p1,q1) of pair kp, columns (p2,q2) of pair kq
+      if (JDBG && sweep == 1 && round == 3) tq1 = clock64();
+      // 36 blocks: rows (p1,q1) of pair kp, columns (p2,q2) of pair kq; 72 eigenvector-row items.  ALL loads of a
+      // lane's items are issued before any store (the items are disjoint, but the compiler cannot know that and
+      // would serialise load -> store -> load chains of ~30 cycles each)
+      int bi[2][4];
+      T bc[2][4], bv[2][4];
 #pragma unroll
       for (int n = 0; n < 2; ++n) {
-        const int b = lane + 32 * n;
-        if (b < 36) {
-          const int kp = b / 6, kq = b - 6 * kp;
-          const int p1 = sh.pq[2 * kp], q1 = sh.pq[2 * kp + 1], p2 = sh.pq[2 * kq], q2 = sh.pq[2 * kq + 1];
-          const double c1 = sh.cs[2 * kp], s1 = sh.cs[2 * kp + 1], c2 = sh.cs[2 * kq], s2 = sh.cs[2 * kq + 1];
-          const double a = sh.A[p1 * 12 + p2], bb = sh.A[p1 * 12 + q2], cc = sh.A[q1 * 12 + p2], d = sh.A[q1 * 12 + q2];
+        const int b = min(lane + 32 * n, 35);
+        const int kp = b / 6, kq = b - 6 * kp;
+        const int p1 = pq[2 * kp], q1 = pq[2 * kp + 1], p2 = pq[2 * kq], q2 = pq[2 * kq + 1];
+        bi[n][0] = p1 * 12 + p2; bi[n][1] = p1 * 12 + q2; bi[n][2] = q1 * 12 + p2; bi[n][3] = q1 * 12 + q2;
+        bc[n][0] = cs[2 * kp]; bc[n][1] = cs[2 * kp + 1]; bc[n][2] = cs[2 * kq]; bc[n][3] = cs[2 * kq + 1];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) bv[n][e] = A[bi[n][e]];
+      }
+      int vi[3][2];
+      T vc[3][2], vv[3][2];
+#pragma unroll
+      for (int n = 0; n < 3; ++n) {
+        const int it = min(lane + 32 * n, 71);
+        const int k = it / 12, j = it - 12 * k;
+        vi[n][0] = pq[2 * k] * 12 + j; vi[n][1] = pq[2 * k + 1] * 12 + j;
+        vc[n][0] = cs[2 * k]; vc[n][1] = cs[2 * k + 1];
+        vv[n][0] = V[vi[n][0]]; vv[n][1] = V[vi[n][1]];
+      }
+#pragma unroll
+      for (int n = 0; n < 2; ++n) {
+        if (lane + 32 * n < 36) {
+          const T c1 = bc[n][0], s1 = bc[n][1], c2 = bc[n][2], s2 = bc[n][3];
+          const T a = bv[n][0], bb = bv[n][1], cc = bv[n][2], d = bv[n][3];
           // rows: J1^T from the left
-          const double ra = c1 * a - s1 * cc, rb = c1 * bb - s1 * d, rc = s1 * a + c1 * cc, rd = s1 * bb + c1 * d;
+          const T ra = c1 * a - s1 * cc, rb = c1 * bb - s1 * d, rc = s1 * a + c1 * cc, rd = s1 * bb + c1 * d;
           // columns: J2 from the right
-          sh.A[p1 * 12 + p2] = c2 * ra - s2 * rb;
-          sh.A[p1 * 12 + q2] = s2 * ra + c2 * rb;
-          sh.A[q1 * 12 + p2] = c2 * rc - s2 * rd;
-          sh.A[q1 * 12 + q2] = s2 * rc + c2 * rd;
+          A[bi[n][0]] = c2 * ra - s2 * rb;
+          A[bi[n][1]] = s2 * ra + c2 * rb;
+          A[bi[n][2]] = c2 * rc - s2 * rd;
+          A[bi[n][3]] = s2 * rc + c2 * rd;
         }
       }
 #pragma unroll
       for (int n = 0; n < 3; ++n) {                  // eigenvector rows p,q of every rotation
-        const int it = lane + 32 * n;
-        if (it < 72) {
-          const int k = it / 12, j = it - 12 * k;
-          const int p = sh.pq[2 * k], q = sh.pq[2 * k + 1];
-          const double c = sh.cs[2 * k], s = sh.cs[2 * k + 1];
-          const double vp = sh.V[p * 12 + j], vq = sh.V[q * 12 + j];
-          sh.V[p * 12 + j] = c * vp - s * vq;
-          sh.V[q * 12 + j] = s * vp + c * vq;
+        if (lane + 32 * n < 72) {
+          const T c = vc[n][0], s = vc[n][1];
+          V[vi[n][0]] = c * vv[n][0] - s * vv[n][1];
+          V[vi[n][1]] = s * vv[n][0] + c * vv[n][1];
         }
       }
       __syncwarp();
+      if (JDBG && sweep == 1 && round == 3) g_jdbg[sizeof(T) == 8 ? 1 : 0] = (tq1 - tq0) * 100000 + (clock64() - tq1);
     }
   }
+  return sweep;
+}
+
+// Parallel-ordered two-sided Jacobi: a round rotates 6 disjoint index pairs at once.  With disjoint
+// pairs A' = J^T A J decomposes into 36 independent 2x2 blocks (row pair x column pair), each owned by
+// one lane, so a round is: 6 lanes form (c, s) -> one warp barrier -> every lane rewrites its blocks and
+// its share of the eigenvector rows -> one warp barrier.  The sweep stops at off^2 <= 1e-28 diag^2
+// (off/diag ~ 1e-14: the null-space basis inside the degenerate eigenvalue is arbitrary anyway, see
+// DESIGN.md "PnP parity").
+// Mixed precision: a round is a chain of dependent latencies, and most of the ~10 sweeps only bring the matrix
+// NEAR diagonal form.  So the first sweeps run in float32 on a copy (cheaper MUFU parameters, 4-cycle FMAs), the
+// float32 eigenvector estimate is re-orthonormalised in float64 (one Newton-Schulz step: 1e-7 -> 1e-14), the
+// ORIGINAL float64 matrix is rotated into that basis (A' = V A V^T, off-diagonal now ~1e-6) and float64 sweeps
+// finish from there (quadratic convergence: two of them).  The result is a float64 decomposition of the float64
+// matrix; float32 only chose the starting basis.
+__device__ __forceinline__ int warp_jacobi12(EpnpShared& sh, int lane) {
+  for (int i = lane; i < 144; i += 32) {
+    sh.Af[i] = (float)sh.A[i];
+    sh.Vf[i] = (i / 12 == i % 12) ? 1.f : 0.f;
+  }
+  __syncwarp();
+  const int nf = jacobi_sweeps<float>(sh.Af, sh.Vf, sh.csf, sh.pq, lane, 6, 1e-11f);
+  // V <- (1.5 I - 0.5 V V^T) V     (rows of V are the eigenvector estimates)
+  for (int e = lane; e < 144; e += 32) {
+    const int i = e / 12, j = e - 12 * i;
+    double g = 0.0;
+#pragma unroll
+    for (int k = 0; k < 12; ++k) g += (double)sh.Vf[i * 12 + k] * (double)sh.Vf[j * 12 + k];
+    sh.T[e] = ((i == j) ? 1.5 : 0.0) - 0.5 * g;
+  }
+  __syncwarp();
+  for (int e = lane; e < 144; e += 32) {
+    const int i = e / 12, j = e - 12 * i;
+    double v = 0.0;
+#pragma unroll
+    for (int k = 0; k < 12; ++k) v += sh.T[i * 12 + k] * (double)sh.Vf[k * 12 + j];
+    sh.V[e] = v;
+  }
+  __syncwarp();
+  // A' = V A V^T
+  for (int e = lane; e < 144; e += 32) {
+    const int i = e / 12, k = e - 12 * i;
+    double v = 0.0;
+#pragma unroll
+    for (int m = 0; m < 12; ++m) v += sh.V[i * 12 + m] * sh.A[m * 12 + k];
+    sh.T[e] = v;
+  }
+  __syncwarp();
+  for (int e = lane; e < 144; e += 32) {
+    const int i = e / 12, j = e - 12 * i;
+    double v = 0.0;
+#pragma unroll
+    for (int k = 0; k < 12; ++k) v += sh.T[i * 12 + k] * sh.V[j * 12 + k];
+    sh.A[e] = v;          // every lane read A only through T (previous phase): safe to overwrite after the barrier above
+  }
+  __syncwarp();
+  // symmetrise (A' is symmetric up to rounding; the sweeps assume it)
+  for (int e = lane; e < 144; e += 32) {
+    const int i = e / 12, j = e - 12 * i;
+    if (i < j) { const double m = 0.5 * (sh.A[i * 12 + j] + sh.A[j * 12 + i]); sh.T[e] = m; }
+  }
+  __syncwarp();
+  for (int e = lane; e < 144; e += 32) {
+    const int i = e / 12, j = e - 12 * i;
+    if (i < j) { sh.A[i * 12 + j] = sh.T[e]; sh.A[j * 12 + i] = sh.T[e]; }
+  }
+  __syncwarp();
+  const int nd = jacobi_sweeps<double>(sh.A, sh.V, sh.cs, sh.pq, lane, 40, 1e-28);
+  return nf * 100 + nd;       // diagnostics: sweeps per precision
 }
 
 // The RNG index stream depends only on N: for the default 100 iterations the host draws it (a few
@@ -290,8 +402,9 @@ __global__ void __launch_bounds__(32) pnp_epnp_kernel(const float* __restrict__ 
   }
   __syncwarp();
   tick(2);
-  warp_jacobi12(sh, lane);
+  const int sweeps = warp_jacobi12(sh, lane);
   tick(3);
+  if (dbg && h == 0 && lane == 0) { dbg[7] = sweeps; dbg[8] = g_jdbg[0]; dbg[9] = g_jdbg[1]; }
   // the four eigenvectors of the smallest eigenvalues, smallest first, largest component positive: lane e < 12
   // ranks its eigenvalue among the twelve (ties by index, like a stable selection) and, if it is one of the
   // four smallest, copies its eigenvector row
@@ -1009,14 +1122,15 @@ static int pnp_ransac_impl(sfm_ctx* ctx, const float* X, const float* px, int n,
     subs.count = (n > 5 && H <= 100) ? H : 0;
     if (subs.count) ransac_subsets(n, subs.count, subs.idx);
     long long* dbg = nullptr;
-    if (getenv("SFM_PNP_TIMELINE")) SFM_TRY(ws_alloc_t(ctx, 8, &dbg));
+    if (getenv("SFM_PNP_TIMELINE")) SFM_TRY(ws_alloc_t(ctx, 12, &dbg));
     SFM_LAUNCH(ctx, SFM_K_PNP_EPNP, (pnp_epnp_kernel<<<H, 32, 0, ctx->stream>>>(dX, dpx, n, H, cam, subs, dposes, drt6, dvalid, dbg)));
     if (dbg) {   // diagnostics: phase boundaries of hypothesis 0 in SM clocks
-      long long hs[8];
+      long long hs[12];
       SFM_CUDA(cudaMemcpyAsync(hs, dbg, sizeof(hs), cudaMemcpyDeviceToHost, ctx->stream));
       SFM_CUDA(cudaStreamSynchronize(ctx->stream));
-      fprintf(stderr, "[epnp cycles] subset+alphas %lld | MtM %lld | jacobi %lld | L,rho %lld | candidates %lld | rodrigues+store %lld\n",
-              hs[1] - hs[0], hs[2] - hs[1], hs[3] - hs[2], hs[4] - hs[3], hs[5] - hs[4], hs[6] - hs[5]);
+      fprintf(stderr, "[jacobi round] f32 params %lld update %lld | f64 params %lld update %lld\n", hs[8] / 100000, hs[8] % 100000, hs[9] / 100000, hs[9] % 100000);
+      fprintf(stderr, "[epnp cycles] subset+alphas %lld | MtM %lld | jacobi %lld (%lld float32 + %lld float64 sweeps) | L,rho %lld | candidates %lld | rodrigues+store %lld\n",
+              hs[1] - hs[0], hs[2] - hs[1], hs[3] - hs[2], hs[7] / 100, hs[7] % 100, hs[4] - hs[3], hs[5] - hs[4], hs[6] - hs[5]);
     }
   }
   SFM_CUDA(cudaMemsetAsync(dcounts, 0, sizeof(int32_t) * H, ctx->stream));
