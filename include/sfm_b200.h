@@ -72,7 +72,8 @@ enum {
   SFM_K_BA_SOLVE = 13,    /* reduced camera system Cholesky */
   SFM_K_MISC = 14,
   SFM_K_PNP_EPNP = 15,    /* batched 5-point EPnP minimal solver */
-  SFM_K_COUNT = 16
+  SFM_K_ESSENTIAL = 16,   /* five-point essential-matrix hypotheses + Sampson scoring */
+  SFM_K_COUNT = 17
 };
 const char* sfm_kernel_name(int kernel_id);
 /* When on, every kernel launch is bracketed by CUDA events on the ctx stream. */
@@ -212,6 +213,19 @@ int sfm_chain_extend(sfm_chain* chain, int n_pairs, const float* const* pts_q, c
 int sfm_recover_pose(sfm_ctx* ctx, const double* E, const void* pts1, const void* pts2, int dtype, int n,
                      const double* K, double dist, const uint8_t* mask_in, double* R, double* t,
                      uint8_t* mask_out, int32_t* n_good);
+
+/* cv2.findEssentialMat(pts0, pts1, K, method=RANSAC, prob, threshold, maxIters)
+ *                                                          sfm.py:307, isfm.py:80, test.py:247.
+ * OpenCV's loop restated: pixels normalised with K in float64, threshold / mean focal length, RNG(2^64-1)
+ * five-index subsets, Nister's five-point solver (<= 10 models per subset), Sampson error in float64 stored as
+ * float32 (inlier iff err <= (float)thr^2), accept when the count beats max(best, 4), RANSACUpdateNumIters.
+ * All maxIters subsets are solved and scored in parallel; one device thread replays the accept/stop recursion.
+ * pts: (n,2) float32 (dtype 0) or float64 (dtype 2), host or device.  E: 90 doubles (row-major 3x3 models);
+ * mask (n, nullable): 1 / 0 like cv2.  info[6] = {models written to E (0: failure / n < 5, 1: RANSAC winner,
+ * k <= 10: n == 5, every model of the single sample as cv2 stacks them), inlier count, iterations run,
+ * winning iteration, winning model within it, models scored}. */
+int sfm_find_essential_mat(sfm_ctx* ctx, const void* pts1, const void* pts2, int dtype, int n, const double* K,
+                           double prob, double threshold, int max_iters, double* E, uint8_t* mask, int32_t* info);
 
 /* ------------------------------------------------------------------ hot path 3a: PnP-RANSAC
  * Replaces cv2.solvePnPRansac(X, p, K, d, ...) with OpenCV's defaults, which is what the

@@ -382,3 +382,159 @@ def recover_pose(E, p1, p2, K, dist: float = 50.0, mask=None):
     else:
         w = 3
     return g[w], cands[w][0], cands[w][1].reshape(3, 1), masks[w]
+
+
+# ------------------------------------------------------------------ findEssentialMat (sfm.py:307, isfm.py:80, test.py:247)
+# Monomials of degree <= 3 in (x, y, z), in the elimination order of Nister's five-point method: the first ten are
+# eliminated (Gauss-Jordan), the last ten are x*[z^2 z 1], y*[z^2 z 1], [z^3 z^2 z 1].
+_E5_MONO = [(3, 0, 0), (0, 3, 0), (2, 1, 0), (1, 2, 0), (2, 0, 1), (2, 0, 0), (0, 2, 1), (0, 2, 0), (1, 1, 1), (1, 1, 0),
+            (1, 0, 2), (1, 0, 1), (1, 0, 0), (0, 1, 2), (0, 1, 1), (0, 1, 0), (0, 0, 3), (0, 0, 2), (0, 0, 1), (0, 0, 0)]
+_E5_INDEX = {m: i for i, m in enumerate(_E5_MONO)}
+
+
+def _pmul(a: dict, b: dict) -> dict:
+    out: dict = {}
+    for (ax, ay, az), av in a.items():
+        for (bx, by, bz), bv in b.items():
+            k = (ax + bx, ay + by, az + bz)
+            out[k] = out.get(k, 0.0) + av * bv
+    return out
+
+
+def _padd(a: dict, b: dict, sb: float = 1.0) -> dict:
+    out = dict(a)
+    for k, v in b.items():
+        out[k] = out.get(k, 0.0) + sb * v
+    return out
+
+
+def five_point_constraints(basis: np.ndarray) -> np.ndarray:
+    """The 10 x 20 coefficient matrix of det(E) = 0 and 2 E E^T E - tr(E E^T) E = 0 for E = x X + y Y + z Z + W
+    (basis rows X, Y, Z, W as 9-vectors), columns in _E5_MONO order.  Built by polynomial arithmetic."""
+    lin = [(1, 0, 0), (0, 1, 0), (0, 0, 1), (0, 0, 0)]
+    E = [[{lin[k]: float(basis[k, 3 * i + j]) for k in range(4)} for j in range(3)] for i in range(3)]
+    EEt = [[_padd(_padd(_pmul(E[i][0], E[j][0]), _pmul(E[i][1], E[j][1])), _pmul(E[i][2], E[j][2]))
+            for j in range(3)] for i in range(3)]
+    tr = _padd(_padd(EEt[0][0], EEt[1][1]), EEt[2][2])
+    rows = []
+    det = _padd(_padd(_pmul(E[0][0], _padd(_pmul(E[1][1], E[2][2]), _pmul(E[1][2], E[2][1]), -1.0)),
+                      _pmul(E[0][1], _padd(_pmul(E[1][0], E[2][2]), _pmul(E[1][2], E[2][0]), -1.0)), -1.0),
+                _pmul(E[0][2], _padd(_pmul(E[1][0], E[2][1]), _pmul(E[1][1], E[2][0]), -1.0)))
+    rows.append(det)
+    for i in range(3):
+        for j in range(3):
+            L = [_padd(EEt[i][k], tr, -0.5) if i == k else EEt[i][k] for k in range(3)]
+            rows.append(_padd(_padd(_pmul(L[0], E[0][j]), _pmul(L[1], E[1][j])), _pmul(L[2], E[2][j])))
+    M = np.zeros((10, 20))
+    for r, p in enumerate(rows):
+        for k, v in p.items():
+            M[r, _E5_INDEX[k]] = v
+    return M
+
+
+def five_point(q1: np.ndarray, q2: np.ndarray) -> np.ndarray:
+    """EMEstimatorCallback::runKernel of OpenCV's five-point.cpp (Nister 2004) restated: null space of the 5 x 9
+    epipolar system, the ten cubic constraints reduced against the first ten monomials, the 3 x 3 polynomial
+    matrix B(z) whose determinant is the degree-10 polynomial, one E = xX + yY + zZ + W (unit Frobenius norm) per
+    real root.  Normalised coordinates q1, q2 (5,2).  Returns (k,3,3), k <= 10.
+
+    Model ORDER: OpenCV visits the roots in the order its Durand-Kerner iteration leaves them, and the roots
+    themselves depend on the null-space basis its SVD happens to return — neither is part of the published
+    algorithm.  Here (and in the CUDA kernel) an iteration's models are ordered by ascending E[0,0]^2, which
+    does not depend on the basis; the order only matters when two models of ONE sample tie on the inlier count."""
+    q1 = np.asarray(q1, np.float64).reshape(-1, 2)
+    q2 = np.asarray(q2, np.float64).reshape(-1, 2)
+    # x2^T E x1 = 0 with E row-major in the 9-vector
+    Q = np.stack([q2[:, 0] * q1[:, 0], q2[:, 0] * q1[:, 1], q2[:, 0], q2[:, 1] * q1[:, 0], q2[:, 1] * q1[:, 1],
+                  q2[:, 1], q1[:, 0], q1[:, 1], np.ones(len(q1))], axis=1)
+    basis = np.linalg.svd(Q, full_matrices=True)[2][5:9]
+    M = five_point_constraints(basis)
+    try:
+        A = np.linalg.solve(M[:, :10], M[:, 10:])
+    except np.linalg.LinAlgError:
+        return np.zeros((0, 3, 3))
+    # rows 4/5, 6/7, 8/9 are <x^2 z>/<x^2>, <y^2 z>/<y^2>, <xyz>/<xy>: (row_a - z row_b) = x p3(z) + y q3(z) + r4(z)
+    B = [[None] * 3 for _ in range(3)]
+    for i in range(3):
+        ra, rb = A[2 * i + 4], A[2 * i + 5]
+        for c, (lo, hi) in enumerate(((0, 3), (3, 6), (6, 10))):
+            pa = np.concatenate([[0.0], ra[lo:hi]])        # descending powers of z
+            pb = np.concatenate([rb[lo:hi], [0.0]])
+            B[i][c] = pa - pb
+    mul = np.polymul
+    det = (np.polysub(mul(mul(B[0][0], B[1][1]), B[2][2]), mul(mul(B[0][0], B[1][2]), B[2][1]))
+           - np.polysub(mul(mul(B[0][1], B[1][0]), B[2][2]), mul(mul(B[0][1], B[1][2]), B[2][0]))
+           + np.polysub(mul(mul(B[0][2], B[1][0]), B[2][1]), mul(mul(B[0][2], B[1][1]), B[2][0])))
+    if not np.all(np.isfinite(det)):
+        return np.zeros((0, 3, 3))
+    roots = np.roots(det)
+    models = []
+    for r in roots:
+        if abs(r.imag) > 1e-10:
+            continue
+        z = float(r.real)
+        Bz = np.array([[np.polyval(B[i][c], z) for c in range(3)] for i in range(3)])
+        xy1 = np.linalg.svd(Bz)[2][2]
+        if abs(xy1[2]) < 1e-10:
+            continue
+        x, y = xy1[0] / xy1[2], xy1[1] / xy1[2]
+        Ev = x * basis[0] + y * basis[1] + z * basis[2] + basis[3]
+        Ev = Ev / np.linalg.norm(Ev)
+        models.append(Ev.reshape(3, 3))
+    models.sort(key=lambda e: e[0, 0] * e[0, 0])
+    return np.array(models).reshape(-1, 3, 3)
+
+
+def sampson_error(q1: np.ndarray, q2: np.ndarray, E: np.ndarray) -> np.ndarray:
+    """EMEstimatorCallback::computeError: (x2^T E x1)^2 / (|E x1|_xy^2 + |E^T x2|_xy^2), float64, stored float32."""
+    x1 = np.column_stack([q1, np.ones(len(q1))])
+    x2 = np.column_stack([q2, np.ones(len(q2))])
+    Ex1 = x1 @ E.T
+    Etx2 = x2 @ E
+    num = (x2 * Ex1).sum(1)
+    den = Ex1[:, 0] ** 2 + Ex1[:, 1] ** 2 + Etx2[:, 0] ** 2 + Etx2[:, 1] ** 2
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return (num * num / den).astype(np.float32)
+
+
+def find_essential_mat(p1, p2, K, prob: float = 0.999, threshold: float = 1.0, max_iters: int = 1000):
+    """cv2.findEssentialMat(p1, p2, K, method=RANSAC, prob, threshold, maxIters) restated (five-point.cpp +
+    ptsetreg.cpp): pixels normalised with K in float64, threshold divided by the mean focal length, RNG(2^64-1)
+    five-index subsets, every model of every sample scored with the Sampson error (float32, err <= thr^2), a model
+    accepted when its count beats max(best, 4), the iteration budget shrunk by RANSACUpdateNumIters.  No refit: the
+    returned E is the winning minimal-sample model.  -> (E (3,3) or None, mask (N,) bool, info)."""
+    K = np.asarray(K, np.float64)
+    q1 = np.asarray(p1, np.float64).reshape(-1, 2).copy()
+    q2 = np.asarray(p2, np.float64).reshape(-1, 2).copy()
+    n = len(q1)
+    for q in (q1, q2):
+        q[:, 0] = (q[:, 0] - K[0, 2]) / K[0, 0]
+        q[:, 1] = (q[:, 1] - K[1, 2]) / K[1, 1]
+    thr = threshold / ((K[0, 0] + K[1, 1]) / 2)
+    t2 = np.float32(thr * thr)
+    if n < 5:
+        return None, np.zeros(n, bool), dict(iters=0, best_iter=-1, best_model=-1)
+    if n == 5:
+        models = five_point(q1, q2)
+        if len(models) == 0:
+            return None, np.zeros(n, bool), dict(iters=0, best_iter=-1, best_model=-1)
+        return models.reshape(-1, 3), np.ones(n, bool), dict(iters=0, best_iter=0, best_model=0)
+    niters = max(max_iters, 1)
+    rng = CvRNG()
+    best, best_E, best_mask, best_it, best_m = 0, None, np.zeros(n, bool), -1, -1
+    it = 0
+    while it < niters:
+        s = []
+        while len(s) < 5:
+            j = rng.uniform(0, n)
+            if j not in s:
+                s.append(j)
+        models = five_point(q1[s], q2[s])
+        for mi, E in enumerate(models):
+            mask = sampson_error(q1, q2, E) <= t2
+            c = int(mask.sum())
+            if c > max(best, 4):
+                best, best_E, best_mask, best_it, best_m = c, E, mask, it, mi
+                niters = update_num_iters(prob, (n - c) / n, 5, niters)
+        it += 1
+    return best_E, best_mask, dict(iters=it, best_iter=best_it, best_model=best_m, best_count=best)

@@ -8,7 +8,7 @@ from ._lib import LIB_PATH, error  # noqa: F401  (import fails loudly if the lib
 from .engine import (BAProblem, Context, Descriptors, epnp, nccl_unique_id, ransac_subsets,  # noqa: F401
                      rodrigues_to_matrix, rodrigues_to_vector)
 from .cv2_compat import (NORM_L2, RATIO, SOLVEPNP_ITERATIVE, BFMatcher, BundleAdjustment, DMatch, PnP,  # noqa: F401
-                         ReprojectionError, Triangulation, common_points, default_context, knn2,
+                         ReprojectionError, Triangulation, common_points, default_context, findEssentialMat, knn2,
                          match_keypoints, patch_cv2, recoverPose, set_default_context, solvePnPRansac, triangulatePoints,
                          unpatch_cv2)
 from . import ba  # noqa: F401

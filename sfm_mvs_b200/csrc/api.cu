@@ -19,7 +19,7 @@ static const char* kKernelNames[SFM_K_COUNT] = {
     "desc_prep",   "match_tc",  "match_exact", "match_final", "match_gather",
     "triangulate", "reproj",    "pnp_score",   "pnp_refine",  "common_points",
     "ba_eval",     "ba_schur",  "ba_update",   "ba_solve",    "misc",
-    "pnp_epnp"};
+    "pnp_epnp", "essential"};
 
 extern "C" const char* sfm_kernel_name(int id) {
   return (id >= 0 && id < SFM_K_COUNT) ? kKernelNames[id] : "?";

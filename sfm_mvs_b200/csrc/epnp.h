@@ -18,12 +18,12 @@ namespace hm {
 // Cyclic Jacobi eigen-decomposition of a symmetric N x N matrix (row-major, destroyed).
 // On return w[] ascending, V rows = eigenvectors (V[i*N+k] = k-th component of eigenvector i).
 template <int N>
-HM_HD inline void eig_sym(double* A, double* w, double* V) {
+HM_HD inline void eig_sym(double* A, double* w, double* V, int max_sweeps = 60) {
   for (int i = 0; i < N; ++i) {
     for (int j = 0; j < N; ++j) V[i * N + j] = 0.0;
     V[i * N + i] = 1.0;
   }
-  for (int sweep = 0; sweep < 60; ++sweep) {
+  for (int sweep = 0; sweep < max_sweeps; ++sweep) {
     double off = 0.0, diag = 0.0;
     for (int i = 0; i < N; ++i) {
       diag += A[i * N + i] * A[i * N + i];
@@ -212,7 +212,7 @@ HM_HD inline void epnp_gauss_newton(const double* L, const double* rho, double* 
 HM_HD inline void epnp_MtM(const double* alphas, const double* us, int n, const EpnpCam& cam, double* MtM);
 
 // ---- stage 1a: control points and barycentric coordinates (alphas: n x 4)
-HM_HD inline void epnp_control_alphas(const double* pw, int n, double* alphas, double (*cws)[3]);
+HM_HD inline void epnp_control_alphas(const double* pw, int n, double* alphas, double (*cws)[3], int pca_sweeps = 60);
 
 // ---- stage 1: control points, barycentric coordinates, M^T M.  alphas: n x 4 scratch.
 HM_HD inline void epnp_build(const double* pw, const double* us, int n, const EpnpCam& cam, double* alphas,
@@ -221,7 +221,10 @@ HM_HD inline void epnp_build(const double* pw, const double* us, int n, const Ep
   epnp_MtM(alphas, us, n, cam, MtM);
 }
 
-HM_HD inline void epnp_control_alphas(const double* pw, int n, double* alphas, double (*cws)[3]) {
+// pca_sweeps bounds the Jacobi sweeps of the 3x3 covariance: the control points only have to be a well-conditioned
+// affine frame that the barycentric coordinates are computed from consistently — they do not have to be the exact
+// principal axes (4 sweeps bring the off-diagonal to ~1e-12; the batched kernel uses that).
+HM_HD inline void epnp_control_alphas(const double* pw, int n, double* alphas, double (*cws)[3], int pca_sweeps) {
   for (int k = 0; k < 3; ++k) cws[0][k] = 0.0;
   for (int i = 0; i < n; ++i)
     for (int k = 0; k < 3; ++k) cws[0][k] += pw[3 * i + k];
@@ -233,7 +236,7 @@ HM_HD inline void epnp_control_alphas(const double* pw, int n, double* alphas, d
       for (int k = 0; k < 3; ++k) C[3 * j + k] += d[j] * d[k];
   }
   double dc[3], uct[9];
-  eig_sym<3>(C, dc, uct);   // ascending; OpenCV's SVD order is descending
+  eig_sym<3>(C, dc, uct, pca_sweeps);   // ascending; OpenCV's SVD order is descending
   for (int i = 1; i < 4; ++i) {
     int e = 3 - i;
     double lam = dc[e] > 0.0 ? dc[e] : 0.0;

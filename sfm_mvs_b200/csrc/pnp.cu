@@ -26,6 +26,8 @@
 #include "chain_dev.cuh"
 #include "epnp.h"
 
+#include "ransac.cuh"
+
 namespace {
 
 struct PnpCam {
@@ -94,25 +96,6 @@ __global__ void __launch_bounds__(256) pnp_score_kernel(const float* __restrict_
   }
   __syncthreads();
   if (threadIdx.x < nh && s_count[threadIdx.x]) atomicAdd(&counts[h0 + threadIdx.x], s_count[threadIdx.x]);
-}
-
-// ------------------------------------------------------------------ RNG subset stream
-// cv::RNG (multiply-with-carry, state 2^64-1) as RANSACPointSetRegistrator::getSubset uses it:
-// 5 distinct indices per iteration, redraw on duplicates.
-__host__ __device__ inline void ransac_subsets(int n, int iters, int* out) {
-  unsigned long long state = 0xFFFFFFFFFFFFFFFFull;
-  for (int it = 0; it < iters; ++it) {
-    int* s = out + 5 * it;
-    for (int i = 0; i < 5; ++i) {
-      for (;;) {
-        state = (state & 0xFFFFFFFFull) * 4164903690ull + (state >> 32);
-        int j = (int)((unsigned int)state % (unsigned int)n);
-        bool dup = false;
-        for (int k = 0; k < i; ++k) dup |= (s[k] == j);
-        if (!dup) { s[i] = j; break; }
-      }
-    }
-  }
 }
 
 // ------------------------------------------------------------------ minimal solver
@@ -379,7 +362,7 @@ __global__ void __launch_bounds__(32) pnp_epnp_kernel(const float* __restrict__ 
       sh.pw[3 * k] = (double)X[3 * (size_t)j]; sh.pw[3 * k + 1] = (double)X[3 * (size_t)j + 1]; sh.pw[3 * k + 2] = (double)X[3 * (size_t)j + 2];
       hm::epnp_roundtrip_pixel(px[2 * (size_t)j], px[2 * (size_t)j + 1], ec, sh.us + 2 * k);
     }
-    hm::epnp_control_alphas(sh.pw, 5, sh.alphas, reinterpret_cast<double(*)[3]>(sh.cws));
+    hm::epnp_control_alphas(sh.pw, 5, sh.alphas, reinterpret_cast<double(*)[3]>(sh.cws), 4);
   }
   __syncwarp();
   tick(1);
@@ -489,17 +472,6 @@ struct PnpResult {          // device-resident, copied to the host once
   double rvec0[3], tvec0[3];
   int best_iter, iters_run, best_count, n_inliers, refine_iters, ok, pad0, pad1;
 };
-
-__device__ inline int update_num_iters(double p, double ep, int model_points, int max_iters) {
-  p = fmax(p, 0.0); p = fmin(p, 1.0);
-  ep = fmax(ep, 0.0); ep = fmin(ep, 1.0);
-  double num = fmax(1.0 - p, DBL_MIN);
-  double denom = 1.0 - pow(1.0 - ep, (double)model_points);
-  if (denom < DBL_MIN) return 0;
-  num = log(num);
-  denom = log(denom);
-  return (denom >= 0 || -num >= max_iters * (-denom)) ? max_iters : __double2int_rn(num / denom);
-}
 
 __device__ inline void pnp_replay(const int* __restrict__ counts, const unsigned char* __restrict__ valid, int n,
                                   int max_iters, double conf, const double* __restrict__ rt6,

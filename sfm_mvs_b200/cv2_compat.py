@@ -122,6 +122,54 @@ def triangulatePoints(projMatr1, projMatr2, projPoints1, projPoints2, ctx: _e.Co
     return (ctx or default_context()).triangulate(P1, P2, x1, x2, 0, 0, False)
 
 
+RANSAC = 8        # cv2.RANSAC
+LMEDS = 4         # cv2.LMEDS
+
+
+def findEssentialMat(points1, points2, cameraMatrix=None, method: int = RANSAC, prob: float = 0.999,
+                     threshold: float = 1.0, maxIters: int = 1000, mask=None, ctx: _e.Context | None = None):
+    """cv2.findEssentialMat(pts0, pts1, K, method=cv2.RANSAC, prob=0.999, threshold=0.4, mask=None) as the
+    reference calls it (sfm.py:307, isfm.py:80, test.py:247) -> (E (3,3) float64, mask (N,1) uint8 of 1 / 0).
+    N == 5 returns every model of the single sample stacked as (3k,3) like cv2; N < 5 or no model returns
+    (None, None) / (None, zeros).  Only the RANSAC method with a 3x3 camera matrix is implemented (the
+    reference uses nothing else); LMEDS / USAC and the focal+pp overload raise.  `mask` is output-only in cv2."""
+    import ctypes as C
+    from ._lib import check, lib
+    ctx = ctx or default_context()
+    if cameraMatrix is None or np.ndim(cameraMatrix) != 2:
+        raise error(-1, "findEssentialMat: the 3x3 cameraMatrix overload is the one implemented")
+    if int(method) != RANSAC:
+        raise error(-1, "findEssentialMat: only method=cv2.RANSAC is implemented")
+    p1, p2 = np.asarray(points1), np.asarray(points2)
+    if p1.dtype not in (np.float32, np.float64):
+        p1 = p1.astype(np.float64)
+    p2 = p2.astype(p1.dtype, copy=False)
+    if p1.size % 2 or p1.size != p2.size:
+        raise error(-215, "findEssentialMat: npoints >= 0 && points2.checkVector(2) == npoints")
+    p1 = np.ascontiguousarray(p1.reshape(-1, 2))
+    p2 = np.ascontiguousarray(p2.reshape(-1, 2))
+    K = np.ascontiguousarray(cameraMatrix, np.float64)
+    if K.shape != (3, 3):
+        raise error(-215, "findEssentialMat: cameraMatrix must be 3x3")
+    if not (0.0 < float(prob) < 1.0):
+        raise error(-215, "findEssentialMat: confidence > 0 && confidence < 1")
+    n = p1.shape[0]
+    if n < 5:
+        return None, None
+    E = np.zeros((10, 3, 3))
+    m_out = np.zeros((n, 1), np.uint8)
+    info = np.zeros(6, np.int32)
+    check(lib.sfm_find_essential_mat(ctx._h, _e._dptr(p1), _e._dptr(p2), 0 if p1.dtype == np.float32 else 2, n,
+                                     _e._dptr(K), float(prob), float(threshold), int(maxIters), _e._dptr(E),
+                                     _e._dptr(m_out), _e._dptr(info)))
+    k = int(info[0])
+    findEssentialMat.last_info = dict(models=k, inliers=int(info[1]), iters=int(info[2]), best_iter=int(info[3]),
+                                      best_model=int(info[4]), models_scored=int(info[5]))
+    if k == 0:
+        return None, m_out
+    return E[:k].reshape(3 * k, 3).copy(), m_out
+
+
 def recoverPose(E, points1, points2, cameraMatrix, R=None, t=None, mask=None, distanceThresh: float = 50.0,
                 ctx: _e.Context | None = None):
     """cv2.recoverPose(E, pts0, pts1, K) as the reference calls it (sfm.py:311, isfm.py:83, test.py:250):
@@ -257,8 +305,9 @@ def patch_cv2(cv2_module=None):
     import cv2 as _cv2
     m = cv2_module or _cv2
     saved = dict(BFMatcher=m.BFMatcher, triangulatePoints=m.triangulatePoints, solvePnPRansac=m.solvePnPRansac,
-                 recoverPose=m.recoverPose)
+                 recoverPose=m.recoverPose, findEssentialMat=m.findEssentialMat)
     m.BFMatcher = BFMatcher
+    m.findEssentialMat = findEssentialMat
     m.triangulatePoints = triangulatePoints
     m.solvePnPRansac = solvePnPRansac
     m.recoverPose = recoverPose

@@ -14,7 +14,7 @@ import numpy as np
 from . import _lib
 from ._lib import BaStats, PnpInfo, check, error, lib
 
-KERNEL_IDS = {lib.sfm_kernel_name(i).decode(): i for i in range(16)}
+KERNEL_IDS = {lib.sfm_kernel_name(i).decode(): i for i in range(17)}
 
 
 def _is_torch(x) -> bool:

@@ -163,8 +163,8 @@ class RegistrationChain:
     # ------------------------------------------------------------------ the loop
     @_on_ctx_stream
     def bootstrap(self, views, Rt0, Rt1, pm01: PairMatches):
-        """State when the reference's loop starts (sfm.py:304-339); the E-matrix / recoverPose
-        initialisation is out of scope, the second pose is given (as in oracle.cvpath)."""
+        """State when the reference's loop starts (sfm.py:304-339) for a given second pose Rt1 — from
+        two_view_init (the reference's E-matrix / recoverPose initialisation) or from the scene (as in oracle.cvpath)."""
         torch = self.torch
         P1, P2 = self.K @ Rt0, self.K @ Rt1
         M = pm01.n
@@ -404,3 +404,25 @@ def register_chain(scene, ctx: _e.Context | None = None, n_views: int | None = N
         o.pop("_keep", None)
         o.pop("_slab", None)
     return outs
+
+
+def two_view_init(pts0, pts1, K, Rt0=None, ctx=None):
+    """The reference's two-view initialisation, sfm.py:307-316, on the engine: findEssentialMat(RANSAC, 0.999, 0.4)
+    -> keep mask == 1 -> recoverPose -> keep mask > 0 -> second pose composed onto the first
+    (R1 = R R0, t1 = t0 + R0 t, exactly as sfm.py:314-315 writes it).
+    -> dict(E, Rt0, Rt1, pts0, pts1 (the surviving correspondences), n_essential, n_pose)."""
+    from . import cv2_compat as _c
+    K = np.asarray(K, np.float64)
+    Rt0 = np.hstack([np.eye(3), np.zeros((3, 1))]) if Rt0 is None else np.asarray(Rt0, np.float64)
+    pts0, pts1 = np.asarray(pts0), np.asarray(pts1)
+    E, mask = _c.findEssentialMat(pts0, pts1, K, method=_c.RANSAC, prob=0.999, threshold=0.4, mask=None, ctx=ctx)
+    if E is None:
+        raise _e.error(-1, "two_view_init: findEssentialMat found no model")
+    a, b = pts0[mask.ravel() == 1], pts1[mask.ravel() == 1]
+    n_e = len(a)
+    _, R, t, mask2 = _c.recoverPose(E[:3], a, b, K, ctx=ctx)
+    a, b = a[mask2.ravel() > 0], b[mask2.ravel() > 0]
+    Rt1 = np.empty((3, 4))
+    Rt1[:3, :3] = R @ Rt0[:3, :3]
+    Rt1[:3, 3] = Rt0[:3, 3] + Rt0[:3, :3] @ t.ravel()
+    return dict(E=E[:3], Rt0=Rt0, Rt1=Rt1, pts0=a, pts1=b, n_essential=n_e, n_pose=len(a))

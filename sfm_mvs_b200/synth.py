@@ -219,3 +219,26 @@ def ba_problem(n_cam: int = 500, n_pt: int = 100_000, obs_per_pt: int = 10, seed
         cam_idx=cam_idx.reshape(-1).copy(), pt_idx=pt_idx,
         obs=obs.reshape(-1, 2).astype(np.float32),
     )
+
+
+def two_view_pair(n: int, seed: int = 0, noise: float = 0.3, outliers: float = 0.2, dtype=np.float32, K=None):
+    """Correspondences of a two-view initialisation (the input of sfm.py:307-311): n points in front of both
+    cameras, a small rotation + sideways translation, Gaussian pixel noise and a fraction of gross mismatches.
+    -> (pts0 (n,2), pts1 (n,2), R, t)."""
+    rng = np.random.default_rng(seed)
+    K = K_GUSTAV if K is None else K
+    X = np.column_stack([rng.uniform(-4, 4, n), rng.uniform(-3, 3, n), rng.uniform(4, 40, n)])
+    rv = np.array([0.03, -0.25, 0.02]) + rng.normal(0, 0.02, 3)
+    th = np.linalg.norm(rv)
+    k = rv / th
+    Kx = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+    R = np.eye(3) + np.sin(th) * Kx + (1 - np.cos(th)) * (Kx @ Kx)
+    t = np.array([1.0, 0.1, 0.2]) + rng.normal(0, 0.05, 3)
+
+    def proj(Y):
+        return np.column_stack([K[0, 0] * Y[:, 0] / Y[:, 2] + K[0, 2], K[1, 1] * Y[:, 1] / Y[:, 2] + K[1, 2]])
+    p0 = proj(X) + rng.normal(0, noise, (n, 2))
+    p1 = proj(X @ R.T + t) + rng.normal(0, noise, (n, 2))
+    bad = rng.choice(n, int(outliers * n), replace=False)
+    p1[bad] += rng.uniform(-150, 150, (len(bad), 2))
+    return p0.astype(dtype), p1.astype(dtype), R, t

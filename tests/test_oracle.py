@@ -190,3 +190,43 @@ def test_restated_recover_pose_equals_cv2(seed):
     rc, Rc, tc, mc = cv2.recoverPose(E, p1, p2, K, mask=emask.copy())
     ro, Ro, to, mo = restated.recover_pose(E, p1, p2, K, mask=emask)
     assert ro == rc and np.array_equal(mo, mc.ravel() != 0)
+
+
+def _e_close(a, b):
+    """distance between two unit-norm essential matrices, sign-free"""
+    return min(np.abs(a - b).max(), np.abs(a + b).max())
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_restated_five_point_equals_cv2(seed):
+    """Nister's five-point solver restated (oracle/restated.py five_point) against OpenCV's: with exactly five
+    correspondences cv2.findEssentialMat returns every model of the minimal sample, stacked (sfm.py:307's solver).
+    Same number of models and the same matrices up to sign; the order is not comparable (see five_point)."""
+    K = synth.K_GUSTAV
+    p0, p1, _, _ = synth.two_view_pair(5, seed=100 + seed, noise=0.0, outliers=0.0)
+    Ec, mc = cv2.findEssentialMat(p0, p1, K, method=cv2.RANSAC, prob=0.999, threshold=0.4, mask=None)
+    Ec = np.zeros((0, 3, 3)) if Ec is None else Ec.reshape(-1, 3, 3)
+    q0 = (p0.astype(np.float64) - K[:2, 2]) / [K[0, 0], K[1, 1]]
+    q1 = (p1.astype(np.float64) - K[:2, 2]) / [K[0, 0], K[1, 1]]
+    Eo = restated.five_point(q0, q1)
+    assert len(Eo) == len(Ec) and len(Eo) >= 1
+    for e in Eo:
+        assert min(_e_close(e, c) for c in Ec) < 1e-6
+        # every model satisfies the five epipolar constraints and the cubic constraints
+        x0 = np.column_stack([q0, np.ones(5)]); x1 = np.column_stack([q1, np.ones(5)])
+        assert np.abs(np.einsum("ni,ij,nj->n", x1, e, x0)).max() < 1e-9
+        assert abs(np.linalg.det(e)) < 1e-9
+        assert np.abs(2 * e @ e.T @ e - np.trace(e @ e.T) * e).max() < 1e-9
+
+
+@pytest.mark.parametrize("n,seed", [(60, 0), (400, 1), (1500, 2)])
+def test_restated_find_essential_mat_equals_cv2(n, seed):
+    """The whole RANSAC loop restated (RNG subsets, Sampson error in float32, accept / RANSACUpdateNumIters) against
+    cv2.findEssentialMat with the reference's arguments (sfm.py:307): same inlier mask bit for bit, same E up to
+    sign."""
+    K = synth.K_GUSTAV
+    p0, p1, _, _ = synth.two_view_pair(n, seed=seed)
+    Ec, mc = cv2.findEssentialMat(p0, p1, K, method=cv2.RANSAC, prob=0.999, threshold=0.4, mask=None)
+    Eo, mo, info = restated.find_essential_mat(p0, p1, K, 0.999, 0.4)
+    assert np.array_equal(mo, mc.ravel() != 0) and int(mo.sum()) == info["best_count"] > 5
+    assert _e_close(Eo, Ec[:3]) < 1e-7
