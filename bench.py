@@ -278,6 +278,20 @@ def run_engine(args):
         "kernel_time_share": shares, "kernel_us_per_launch": per_launch_us, "roofline": roofline,
     }
 
+    # ---- two-view initialisation (sfm.py:307-316: findEssentialMat + recoverPose), once per scene in the reference;
+    # public API with host arrays, so copies are inside the timed calls.  Reported beside the headline, not in it.
+    if world == 1:
+        from sfm_mvs_b200 import pipeline as _pl
+        tv0, tv1, _, _ = synth.two_view_pair(int(0.6 * n), seed=7, outliers=0.3)
+        for _ in range(3):
+            init = _pl.two_view_init(tv0, tv1, scene["K"], ctx=ctx)
+        t0 = time.perf_counter()
+        for _ in range(10):
+            init = _pl.two_view_init(tv0, tv1, scene["K"], ctx=ctx)
+        out["two_view_init"] = {"engine_ms": (time.perf_counter() - t0) / 10 * 1e3, "correspondences": len(tv0),
+                                "survivors": int(init["n_pose"]), "cpu_ms": None,
+                                "what": "findEssentialMat(RANSAC, 0.999, 0.4) + recoverPose, host arrays in / out"}
+
     # ---- BA: GN iterations / s (configs[3]); points sharded over ranks, NCCL all-reduce of the reduced system
     if not args.no_ba:
         out["ba"] = bench_ba(args, ctx, world, rank, pk, barrier, max_over_ranks)
@@ -291,6 +305,12 @@ def run_engine(args):
         out["cpu_baseline"] = {"value": r / t, "unit": "views/s", "cores": cv2.getNumThreads(), "kind": "port",
                                "sample": f"first {nv} views of the same scene ({r} views registered, {t:.1f} s)",
                                "host_cpus": os.cpu_count(), "cv2": cv2.__version__}
+        if "two_view_init" in out:           # the same two lines of the reference on cv2 (sfm.py:307, :311)
+            t0 = time.perf_counter()
+            for _ in range(3):
+                E, m = cv2.findEssentialMat(tv0, tv1, scene["K"], method=cv2.RANSAC, prob=0.999, threshold=0.4, mask=None)
+                cv2.recoverPose(E, tv0[m.ravel() == 1], tv1[m.ravel() == 1], scene["K"])
+            out["two_view_init"]["cpu_ms"] = (time.perf_counter() - t0) / 3 * 1e3
     elif rank == 0:
         out["cpu_baseline"] = None
     if rank == 0:

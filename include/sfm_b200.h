@@ -52,6 +52,11 @@ int sfm_ctx_create(int device, void* stream, sfm_ctx** out);
 void sfm_ctx_destroy(sfm_ctx* ctx);
 int sfm_ctx_sync(sfm_ctx* ctx);
 void* sfm_ctx_stream(sfm_ctx* ctx);
+/* The stream outlives the context from now on (sfm_ctx_destroy synchronises but does not destroy it).  For hosts
+ * that hand the stream to another runtime whose objects may be released later: torch's pinned-host allocator
+ * records an event on every stream a buffer was used on when that buffer is freed, and a destroyed stream there
+ * aborts the process. */
+int sfm_ctx_detach_stream(sfm_ctx* ctx);
 int sfm_ctx_sm_count(sfm_ctx* ctx);
 
 /* Kernel identifiers for the profiling interface. */

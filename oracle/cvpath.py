@@ -123,8 +123,9 @@ def BundleAdjustment(points_3d, temp2, Rtnew, K, r_error):
 # --------------------------------------------------------------------------- per-view loop
 def bootstrap_two_views(scene):
     """State the reference holds when its loop starts (sfm.py:304-339), with the E-matrix/
-    recoverPose initialisation (out of scope) replaced by the scene's
-    ground-truth second pose so that every arm starts from identical bytes."""
+    recoverPose initialisation (covered separately: restated.find_essential_mat / recover_pose and
+    tests/test_gpu_essential.py) replaced by the scene's ground-truth second pose so that every arm of the
+    loop comparison starts from identical bytes."""
     K = scene["K"]
     v0, v1 = scene["views"][0], scene["views"][1]
     Rt0 = np.hstack([v0["R"], v0["t"].reshape(3, 1)])

@@ -54,6 +54,7 @@ PROTOTYPES = {
     "sfm_ctx_destroy": (None, [_vp]),
     "sfm_ctx_sync": (_i, [_vp]),
     "sfm_ctx_stream": (_vp, [_vp]),
+    "sfm_ctx_detach_stream": (_i, [_vp]),
     "sfm_ctx_sm_count": (_i, [_vp]),
     "sfm_kernel_name": (C.c_char_p, [_i]),
     "sfm_ctx_set_profiling": (_i, [_vp, _i]),

@@ -84,6 +84,11 @@ extern "C" int sfm_ctx_sync(sfm_ctx* c) {
   return SFM_OK;
 }
 extern "C" void* sfm_ctx_stream(sfm_ctx* c) { return c ? (void*)c->stream : nullptr; }
+extern "C" int sfm_ctx_detach_stream(sfm_ctx* c) {
+  SFM_REQUIRE(c, "sfm_ctx_detach_stream: ctx is NULL");
+  c->own_stream = false;
+  return SFM_OK;
+}
 extern "C" int sfm_ctx_sm_count(sfm_ctx* c) { return c ? c->sm_count : 0; }
 
 // ---------------------------------------------------------------------------- workspace

@@ -114,15 +114,17 @@ __device__ __forceinline__ double warp_sum_d(double v) {
 }
 
 // ------------------------------------------------------------------ K5: materialised evaluation
-// One persistent CTA of 1024 threads per SM; one observation per thread per trip: 16 B read (uv, cam
-// index, point index), 80 B written (r 8 B, Jc 48 B, Jp 24 B).  The per-camera table (C x 144 B,
+// One persistent CTA of 512 threads per SM (large problems); one observation per thread per trip: 16 B read (uv,
+// cam index, point index), 80 B written (r 8 B, Jc 48 B, Jp 24 B).  512 threads x 82 registers measured faster
+// than 768 x 72 or 1024 x 64 (28.0 / 31.0 / 33.2 us at 1 M observations): the kernel is bound by the shared-memory
+// and store queues, which fewer, longer-lived warps load more evenly, not by latency that more warps would hide.  The per-camera table (C x 144 B,
 // 72 KB at C = 500) is staged into shared memory by ONE bulk-copy instruction (cp.async.bulk, the TMA
 // engine, completion on an mbarrier) when it fits, so the random per-observation camera gather never
 // leaves the SM; otherwise it is read through L1.
 __device__ __forceinline__ uint32_t ba_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-template <int MODE, bool SMEM_CAMS>
-__global__ void __launch_bounds__(1024, 1) ba_eval_kernel(const float2* __restrict__ uv, const int* __restrict__ cam_idx,
+template <int MODE, bool SMEM_CAMS, int THREADS = 1024, bool PREFETCH_PT = false>
+__global__ void __launch_bounds__(THREADS, 1) ba_eval_kernel(const float2* __restrict__ uv, const int* __restrict__ cam_idx,
                                                           const int* __restrict__ pt_idx, int n_obs,
                                                           const double* __restrict__ cam_pre, int n_cam,
                                                           const double* __restrict__ pts, Intr K, double inv_n,
@@ -151,6 +153,13 @@ __global__ void __launch_bounds__(1024, 1) ba_eval_kernel(const float2* __restri
   float2 m_n = make_float2(0.f, 0.f);
   int c_n = 0, p_n = 0;
   if (o < n_obs) { m_n = __ldg(uv + o); c_n = __ldg(cam_idx + o); p_n = __ldg(pt_idx + o); }
+  // PREFETCH_PT: the point of the next trip is loaded a trip ahead as well (its index two trips ahead), so no
+  // DRAM / L2 latency is left on the per-trip dependent chain.
+  double X_n[3] = {0.0, 0.0, 0.0};
+  if (PREFETCH_PT) {
+    if (o < n_obs) { X_n[0] = __ldg(pts + 3 * (size_t)p_n); X_n[1] = __ldg(pts + 3 * (size_t)p_n + 1); X_n[2] = __ldg(pts + 3 * (size_t)p_n + 2); }
+    if (o + stride < n_obs) p_n = __ldg(pt_idx + o + stride);
+  }
   if (SMEM_CAMS) {           // wait for the bulk copy only now: the first index loads are already in flight
     const uint32_t bar = ba_smem_u32(&s_bar);
     uint32_t ok = 0;
@@ -163,8 +172,18 @@ __global__ void __launch_bounds__(1024, 1) ba_eval_kernel(const float2* __restri
   for (; o < n_obs; o += stride) {
     const float2 m = m_n;
     const int c = c_n, p = p_n;
-    const double X[3] = {__ldg(pts + 3 * (size_t)p), __ldg(pts + 3 * (size_t)p + 1), __ldg(pts + 3 * (size_t)p + 2)};
-    if (o + stride < n_obs) { m_n = __ldg(uv + o + stride); c_n = __ldg(cam_idx + o + stride); p_n = __ldg(pt_idx + o + stride); }
+    double X[3];
+    if (PREFETCH_PT) {
+      X[0] = X_n[0]; X[1] = X_n[1]; X[2] = X_n[2];
+      if (o + stride < n_obs) {     // p already is the NEXT trip's point index
+        X_n[0] = __ldg(pts + 3 * (size_t)p); X_n[1] = __ldg(pts + 3 * (size_t)p + 1); X_n[2] = __ldg(pts + 3 * (size_t)p + 2);
+        m_n = __ldg(uv + o + stride); c_n = __ldg(cam_idx + o + stride);
+      }
+      if (o + 2 * (size_t)stride < (size_t)n_obs) p_n = __ldg(pt_idx + o + 2 * stride);
+    } else {
+      X[0] = __ldg(pts + 3 * (size_t)p); X[1] = __ldg(pts + 3 * (size_t)p + 1); X[2] = __ldg(pts + 3 * (size_t)p + 2);
+      if (o + stride < n_obs) { m_n = __ldg(uv + o + stride); c_n = __ldg(cam_idx + o + stride); p_n = __ldg(pt_idx + o + stride); }
+    }
     double r[2];
     float Jc[2][6], Jp[2][3];
     if (MODE == 0) {
@@ -456,18 +475,25 @@ int launch_eval_v(sfm_ba* ba, const double* pts, float* r, float* Jc, float* Jp,
   sfm_ctx* ctx = ba->ctx;
   const size_t smem = SM ? ((cam_smem_bytes(ba) + 15) & ~(size_t)15) : 0;
   const double inv_n = 1.0 / (double)(ba->n_obs_total > 0 ? ba->n_obs_total : 1);
-  const int threads = ba->n_obs >= 64 * 1024 ? 1024 : 256;
+  const bool big = ba->n_obs >= 64 * 1024;
+  const int threads = big ? 512 : 256;
   int grid = std::max(1, std::min(div_up(ba->n_obs, threads), ctx->sm_count * (SM ? 1 : 2)));
   if (SM) {
     static bool attr = false;
     if (!attr) {
       SFM_CUDA(cudaFuncSetAttribute(ba_eval_kernel<MODE, SM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      SFM_CUDA(cudaFuncSetAttribute(ba_eval_kernel<MODE, SM, 512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       attr = true;
     }
   }
-  SFM_LAUNCH(ctx, SFM_K_BA_EVAL, (ba_eval_kernel<MODE, SM><<<grid, threads, smem, ctx->stream>>>(
-                                     ba->uv, ba->cam_idx, ba->pt_idx, ba->n_obs, ba->cam_pre, ba->n_cam, pts,
-                                     make_intr(ba), inv_n, r, Jc, Jp, cost_dev)));
+  if (big)
+    SFM_LAUNCH(ctx, SFM_K_BA_EVAL, (ba_eval_kernel<MODE, SM, 512, true><<<grid, threads, smem, ctx->stream>>>(
+                                       ba->uv, ba->cam_idx, ba->pt_idx, ba->n_obs, ba->cam_pre, ba->n_cam, pts,
+                                       make_intr(ba), inv_n, r, Jc, Jp, cost_dev)));
+  else
+    SFM_LAUNCH(ctx, SFM_K_BA_EVAL, (ba_eval_kernel<MODE, SM><<<grid, threads, smem, ctx->stream>>>(
+                                       ba->uv, ba->cam_idx, ba->pt_idx, ba->n_obs, ba->cam_pre, ba->n_cam, pts,
+                                       make_intr(ba), inv_n, r, Jc, Jp, cost_dev)));
   return SFM_OK;
 }
 

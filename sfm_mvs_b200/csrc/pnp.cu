@@ -128,8 +128,6 @@ struct EpnpShared {
 // basis inside the degenerate eigenvalue is arbitrary anyway, see DESIGN.md "PnP parity").
 // One sweep-loop of the parallel-ordered Jacobi in precision T on (A, V) in shared memory; V must hold an
 // orthonormal start (identity or a previous estimate).  Stops when off^2 <= tol * diag^2 or after max_sweeps.
-#define JDBG 0
-__device__ long long g_jdbg[2];
 template <typename T>
 __device__ __forceinline__ int jacobi_sweeps(T* __restrict__ A, T* __restrict__ V, T* __restrict__ cs, int* __restrict__ pq,
                                              int lane, int max_sweeps, T tol) {
@@ -147,8 +145,6 @@ __device__ __forceinline__ int jacobi_sweeps(T* __restrict__ A, T* __restrict__ 
     }
     if (off * (T)0.5 <= tol * diag || off == (T)0) break;
     for (int round = 0; round < 11; ++round) {
-      long long tq0 = 0, tq1 = 0;
-      if (JDBG && sweep == 1 && round == 3) tq0 = clock64();
       if (lane < 6) {
         int p = round + lane, q = round - lane + 11;          // (round +- lane) mod 11 without a division
         p -= (p >= 11) ? 11 : 0;
@@ -190,7 +186,6 @@ __device__ __forceinline__ int jacobi_sweeps(T* __restrict__ A, T* __restrict__ 
         pq[2 * lane] = p; pq[2 * lane + 1] = q;
       }
       __syncwarp();
-      if (JDBG && sweep == 1 && round == 3) tq1 = clock64();
       // 36 blocks: rows (p1,q1) of pair kp, columns (p2,q2) of pair kq; 72 eigenvector-row items.  ALL loads of a
       // lane's items are issued before any store (the items are disjoint, but the compiler cannot know that and
       // would serialise load -> store -> load chains of ~30 cycles each)
@@ -239,7 +234,6 @@ __device__ __forceinline__ int jacobi_sweeps(T* __restrict__ A, T* __restrict__ 
         }
       }
       __syncwarp();
-      if (JDBG && sweep == 1 && round == 3) g_jdbg[sizeof(T) == 8 ? 1 : 0] = (tq1 - tq0) * 100000 + (clock64() - tq1);
     }
   }
   return sweep;
@@ -387,7 +381,7 @@ __global__ void __launch_bounds__(32) pnp_epnp_kernel(const float* __restrict__ 
   tick(2);
   const int sweeps = warp_jacobi12(sh, lane);
   tick(3);
-  if (dbg && h == 0 && lane == 0) { dbg[7] = sweeps; dbg[8] = g_jdbg[0]; dbg[9] = g_jdbg[1]; }
+  if (dbg && h == 0 && lane == 0) { dbg[7] = sweeps; dbg[8] = 0; dbg[9] = 0; }
   // the four eigenvectors of the smallest eigenvalues, smallest first, largest component positive: lane e < 12
   // ranks its eigenvalue among the twelve (ties by index, like a stable selection) and, if it is one of the
   // four smallest, copies its eigenvector row

@@ -170,6 +170,9 @@ class Context:
         import torch
         if getattr(self, "_tstream", None) is None:
             self._tstream = torch.cuda.ExternalStream(self.stream, device=self.torch_device)
+            # torch objects tied to this stream (pinned host buffers of non_blocking copies record an event on it
+            # when they are freed) may outlive the context: the stream is never destroyed once torch has seen it
+            check(lib.sfm_ctx_detach_stream(self._h))
         return self._tstream
 
     def launch_count(self) -> int:

@@ -411,16 +411,16 @@ def two_view_init(pts0, pts1, K, Rt0=None, ctx=None):
     -> keep mask == 1 -> recoverPose -> keep mask > 0 -> second pose composed onto the first
     (R1 = R R0, t1 = t0 + R0 t, exactly as sfm.py:314-315 writes it).
     -> dict(E, Rt0, Rt1, pts0, pts1 (the surviving correspondences), n_essential, n_pose)."""
-    from . import cv2_compat as _c
+    from .cv2_compat import RANSAC, findEssentialMat, recoverPose
     K = np.asarray(K, np.float64)
     Rt0 = np.hstack([np.eye(3), np.zeros((3, 1))]) if Rt0 is None else np.asarray(Rt0, np.float64)
     pts0, pts1 = np.asarray(pts0), np.asarray(pts1)
-    E, mask = _c.findEssentialMat(pts0, pts1, K, method=_c.RANSAC, prob=0.999, threshold=0.4, mask=None, ctx=ctx)
+    E, mask = findEssentialMat(pts0, pts1, K, method=RANSAC, prob=0.999, threshold=0.4, mask=None, ctx=ctx)
     if E is None:
         raise _e.error(-1, "two_view_init: findEssentialMat found no model")
     a, b = pts0[mask.ravel() == 1], pts1[mask.ravel() == 1]
     n_e = len(a)
-    _, R, t, mask2 = _c.recoverPose(E[:3], a, b, K, ctx=ctx)
+    _, R, t, mask2 = recoverPose(E[:3], a, b, K, ctx=ctx)
     a, b = a[mask2.ravel() > 0], b[mask2.ravel() > 0]
     Rt1 = np.empty((3, 4))
     Rt1[:3, :3] = R @ Rt0[:3, :3]
