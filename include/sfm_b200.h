@@ -209,6 +209,12 @@ int sfm_chain_create(sfm_ctx* ctx, const double* K, const double* Rt0, const dou
 void sfm_chain_destroy(sfm_chain* chain);
 int sfm_chain_extend(sfm_chain* chain, int n_pairs, const float* const* pts_q, const float* const* pts_t,
                      const int32_t* n_match, float* const* X_new, sfm_view_out* out, int32_t* n_registered);
+/* sfm_chain_extend split in two, so the host can upload and match the next batch of pairs while this one
+ * registers: _async queues the whole call and returns, _collect waits for it and fills out[] (sized like
+ * sfm_chain_extend's).  One call in flight per chain; the bootstrap pair of a fresh chain still synchronises. */
+int sfm_chain_extend_async(sfm_chain* chain, int n_pairs, const float* const* pts_q, const float* const* pts_t,
+                           const int32_t* n_match, float* const* X_new);
+int sfm_chain_collect(sfm_chain* chain, sfm_view_out* out, int32_t* n_registered);
 
 /* cv2.recoverPose(E, pts0, pts1, K)                      sfm.py:311, isfm.py:83, test.py:250:
  * the four (R, t) decompositions of E, every correspondence triangulated against each (float64 DLT as K2) and

@@ -92,6 +92,8 @@ PROTOTYPES = {
     "sfm_chain_create": (_i, [_vp, _vp, _vp, _vp, _i, _pp]),
     "sfm_chain_destroy": (None, [_vp]),
     "sfm_chain_extend": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "sfm_chain_extend_async": (_i, [_vp, _i, _vp, _vp, _vp, _vp]),
+    "sfm_chain_collect": (_i, [_vp, _vp, _vp]),
     "sfm_desc_match_gather_batched": (_i, [_vp, _i, _vp, _vp, _d, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sfm_debug_match_tc_timeline": (_i, [_vp, _vp, _vp, _vp, _i, _vp]),
     "sfm_ba_set_params": (_i, [_vp, _vp, _vp]),

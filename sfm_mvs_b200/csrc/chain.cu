@@ -154,6 +154,11 @@ struct sfm_chain {
   struct ViewRec* hrecs = nullptr; // pinned
   int32_t* hcnt = nullptr;         // pinned
   double* herrs = nullptr;         // pinned
+  // a call queued by sfm_chain_extend_async and not collected yet
+  bool pending = false, pending_parsed = false;
+  int pend_reg = 0;
+  std::vector<int32_t> pend_nmatch;
+  std::vector<sfm_view_out> pend_out;
   // loop state (sfm.py:399-409)
   bool started = false;
   const float* prev_q = nullptr;   // previous pair's matches (re-triangulated for the next view)
@@ -312,9 +317,36 @@ static void sfm_chain_release(sfm_chain* c) {
 // registered by it); every further pair registers one view: out / X_new have one entry per registered
 // view of THIS call.  The match arrays of the last pair must stay alive until the next call (they are
 // re-triangulated against the next view, sfm.py:348-352).
-extern "C" int sfm_chain_extend(sfm_chain* c, int n_pairs, const float* const* pts_q, const float* const* pts_t,
-                                const int32_t* n_match, float* const* X_new, sfm_view_out* out, int32_t* n_registered) {
+static int chain_collect_impl(sfm_chain* c, sfm_view_out* out, int32_t* n_registered) {
+  sfm_ctx* ctx = c->ctx;
+  const int reg = c->pend_reg;
+  if (n_registered) *n_registered = 0;
+  if (!c->pending) return SFM_OK;
+  c->pending = false;
+  if (c->pending_parsed) {           // the host-synchronised loop already produced the records
+    for (int v = 0; v < reg; ++v) out[v] = c->pend_out[v];
+    if (n_registered) *n_registered = reg;
+    return SFM_OK;
+  }
+  SFM_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (int v = 0; v < reg; ++v) {
+    const ViewRec& r = c->hrecs[v];
+    sfm_view_out& o = out[v];
+    memcpy(o.Rt, r.Rt, sizeof(o.Rt));
+    o.err_pnp = r.err_pnp; o.err_new = r.err_new;
+    o.n_new = r.n_new; o.n_pnp = r.n_pnp; o.n_inl = r.n_inl; o.n_match = c->pend_nmatch[v];
+    SFM_REQUIRE(r.n_pnp >= 6, "registration failed: view %d shares %d points with the model", c->views_done - reg + v + 2, r.n_pnp);
+    SFM_REQUIRE(r.ok, "registration failed: solvePnPRansac found no consensus (view %d)", c->views_done - reg + v + 2);
+  }
+  if (n_registered) *n_registered = reg;
+  return SFM_OK;
+}
+
+static int chain_extend_impl(sfm_chain* c, int n_pairs, const float* const* pts_q, const float* const* pts_t,
+                             const int32_t* n_match, float* const* X_new, sfm_view_out* out, int32_t* n_registered,
+                             bool defer) {
   SFM_REQUIRE(c && n_pairs >= 0 && (n_pairs == 0 || (pts_q && pts_t && n_match)), "sfm_chain_extend: null argument");
+  SFM_REQUIRE(!c->pending, "sfm_chain_extend: the previous asynchronous call has not been collected");
   sfm_ctx* ctx = c->ctx;
   const double* K = c->K;
   int reg = 0;
@@ -322,6 +354,7 @@ extern "C" int sfm_chain_extend(sfm_chain* c, int n_pairs, const float* const* p
   for (int k = 0; k < n_pairs; ++k)
     SFM_REQUIRE(n_match[k] >= 6 && n_match[k] <= c->nmax, "sfm_chain_extend: pair %d has %d matches (need 6..%d)", k, n_match[k], c->nmax);
   const int n_views = n_pairs - (c->started ? 0 : 1);
+  if (defer) { c->pend_out.assign((size_t)(n_views > 0 ? n_views : 1), sfm_view_out()); out = c->pend_out.data(); }
   SFM_REQUIRE(n_views <= 0 || (X_new && out), "sfm_chain_extend: output arrays missing");
   SFM_REQUIRE(n_views < ERR_SLOTS, "sfm_chain_extend: at most %d views per call", ERR_SLOTS - 1);
   if (n_pairs == 0) return SFM_OK;
@@ -407,18 +440,10 @@ extern "C" int sfm_chain_extend(sfm_chain* c, int n_pairs, const float* const* p
     for (int k = 0; k < 2; ++k)
       if (c->set_used[k]) SFM_CUDA(cudaStreamWaitEvent(ctx->stream, c->ev_out[k], 0));   // the records are complete
     SFM_CUDA(cudaMemcpyAsync(c->hrecs, c->recs, sizeof(ViewRec) * (size_t)reg, cudaMemcpyDeviceToHost, ctx->stream));
-    SFM_CUDA(cudaStreamSynchronize(ctx->stream));
-    for (int v = 0; v < reg; ++v) {
-      const ViewRec& r = c->hrecs[v];
-      sfm_view_out& o = out[v];
-      memcpy(o.Rt, r.Rt, sizeof(o.Rt));
-      o.err_pnp = r.err_pnp; o.err_new = r.err_new;
-      o.n_new = r.n_new; o.n_pnp = r.n_pnp; o.n_inl = r.n_inl; o.n_match = n_match[k0 + v];
-      SFM_REQUIRE(r.n_pnp >= 6, "registration failed: view %d shares %d points with the model", c->views_done - reg + v + 2, r.n_pnp);
-      SFM_REQUIRE(r.ok, "registration failed: solvePnPRansac found no consensus (view %d)", c->views_done - reg + v + 2);
-    }
-    if (n_registered) *n_registered = reg;
-    return SFM_OK;
+    c->pending = true; c->pending_parsed = false; c->pend_reg = reg;
+    c->pend_nmatch.assign(n_match + k0, n_match + k0 + reg);
+    if (defer) return SFM_OK;                              // sfm_chain_collect synchronises and reads the records
+    return chain_collect_impl(c, out, n_registered);
   }
   for (int k = k0; k < n_pairs; ++k, ++reg) {
     const int M = n_match[k];
@@ -470,8 +495,27 @@ extern "C" int sfm_chain_extend(sfm_chain* c, int n_pairs, const float* const* p
     SFM_CUDA(cudaStreamSynchronize(ctx->stream));
     for (int v = 0; v < reg; ++v) { out[v].err_pnp = c->herrs[2 * v]; out[v].err_new = c->herrs[2 * v + 1]; }
   }
+  if (defer) { c->pending = true; c->pending_parsed = true; c->pend_reg = reg; return SFM_OK; }
   if (n_registered) *n_registered = reg;
   return SFM_OK;
+}
+
+extern "C" int sfm_chain_extend(sfm_chain* c, int n_pairs, const float* const* pts_q, const float* const* pts_t,
+                                const int32_t* n_match, float* const* X_new, sfm_view_out* out, int32_t* n_registered) {
+  return chain_extend_impl(c, n_pairs, pts_q, pts_t, n_match, X_new, out, n_registered, false);
+}
+
+// The same call split in two so that a host can prepare the next batch of pairs (upload, match) while this one
+// registers: _async queues every launch of the call and returns; _collect waits for it and fills the records.
+// One call may be in flight per chain.
+extern "C" int sfm_chain_extend_async(sfm_chain* c, int n_pairs, const float* const* pts_q, const float* const* pts_t,
+                                      const int32_t* n_match, float* const* X_new) {
+  return chain_extend_impl(c, n_pairs, pts_q, pts_t, n_match, X_new, nullptr, nullptr, true);
+}
+
+extern "C" int sfm_chain_collect(sfm_chain* c, sfm_view_out* out, int32_t* n_registered) {
+  SFM_REQUIRE(c && out, "sfm_chain_collect: null argument");
+  return chain_collect_impl(c, out, n_registered);
 }
 
 extern "C" int sfm_chain_run(sfm_ctx* ctx, const double* K, const double* Rt0, const double* Rt1, int n_pairs,

@@ -266,11 +266,14 @@ class NativeChain:
         self._alive = []          # match arrays of the last pair must outlive the next extend()
         self._fed = 0
 
-    def extend(self, matches):
+    def launch(self, matches):
+        """Queue the registration of the views these consecutive pairs add (sfm_chain_extend_async) and return;
+        collect() waits and returns the records.  One call in flight."""
         import torch
         n_pairs = len(matches)
+        self._inflight = None
         if n_pairs == 0:
-            return []
+            return
         first = self._fed == 0
         n = np.array([pm.n for pm in matches], np.int32)
         reg_n = n[1:] if first else n                      # matches of the pairs that register a view
@@ -281,12 +284,19 @@ class NativeChain:
         pq = np.array([pm.pts_q.data_ptr() for pm in matches], np.uint64)
         pt = np.array([pm.pts_t.data_ptr() for pm in matches], np.uint64)
         xn = np.ascontiguousarray(X_all.data_ptr() + off[:-1] * 12, np.uint64)
-        out = np.zeros((max(len(reg_n), 1),), dtype=VIEW_OUT)
-        nreg = C.c_int32(0)
-        check(lib.sfm_chain_extend(self._h, n_pairs, pq.ctypes.data, pt.ctypes.data, n.ctypes.data, xn.ctypes.data,
-                                   out.ctypes.data, C.byref(nreg)))
+        check(lib.sfm_chain_extend_async(self._h, n_pairs, pq.ctypes.data, pt.ctypes.data, n.ctypes.data, xn.ctypes.data))
         self._alive = [matches[-1], X_all]
         self._fed += n_pairs
+        self._inflight = (X_all, off, len(reg_n))
+
+    def collect(self):
+        if getattr(self, "_inflight", None) is None:
+            return []
+        X_all, off, n_views = self._inflight
+        self._inflight = None
+        out = np.zeros((max(n_views, 1),), dtype=VIEW_OUT)
+        nreg = C.c_int32(0)
+        check(lib.sfm_chain_collect(self._h, out.ctypes.data, C.byref(nreg)))
         outs = []
         for v in range(nreg.value):
             o = out[v]
@@ -295,6 +305,10 @@ class NativeChain:
                              err_pnp=float(o["err_pnp"]), err_new=float(o["err_new"]),
                              _slab=(X_all, int(off[v]))))       # fetch_clouds copies a call's points back in one piece
         return outs
+
+    def extend(self, matches):
+        self.launch(matches)
+        return self.collect()
 
     def close(self):
         if getattr(self, "_h", None):
@@ -360,19 +374,29 @@ def register_host(ctx: _e.Context, K, kps, dess, Rt0, Rt1, chunk: int = 25, rati
             ev = torch.cuda.Event()
             ev.record(cs)
             events.append(ev)
-    chain = RegistrationChain(ctx, K, ratio=ratio)
+    # Matching runs on a second context (own stream, workspace and descriptor pool) so that a chunk is prepared
+    # and matched — including the host reads of its match counts — while the previous chunk's views register on
+    # the main context; the registration loop is launched asynchronously and collected one chunk later.
+    mctx = getattr(ctx, "_match_ctx", None)
+    if mctx is None:
+        mctx = ctx._match_ctx = _e.Context(ctx.device)
+    ms = mctx.torch_stream()
+    chain = RegistrationChain(mctx, K, ratio=ratio)
     native = NativeChain(ctx, K, Rt0, Rt1, max(int(k.shape[0]) for k in kps))
     views, outs, keep = [], [], []
     try:
         for (lo, hi), ev in zip(bounds, events):
-            ts.wait_event(ev)
-            views += DeviceView.batch(ctx, kp_d[lo:hi], des_d[lo:hi])
+            ms.wait_event(ev)
+            views += DeviceView.batch(mctx, kp_d[lo:hi], des_d[lo:hi])
             pairs = [(i, i + 1) for i in range(max(lo - 1, 0), hi - 1)]
             if not pairs:
                 continue
             matches = chain.match_pairs(views, pairs)
             keep.append(matches)
-            outs += native.extend(matches)
+            mctx.sync()                       # the survivors of this chunk are in HBM
+            outs += native.collect()          # previous chunk's views
+            native.launch(matches)
+        outs += native.collect()
         ctx.sync()
     finally:
         native.close()
