@@ -197,9 +197,9 @@ def run_engine(args):
             outs = pipeline.register_host(ctx, K, kps, dess, Rt0, Rt1)
             clouds = pipeline.fetch_clouds(ctx, outs)
             return outs, sum(c.size * 4 for c in clouds) + len(outs) * (16 + 96)
-        views = pipeline.DeviceView.batch(ctx, kps, dess)                        # K1b descriptor prep inside (one launch)
-        chain = pipeline.RegistrationChain(ctx, K)
-        outs = chain.run(views, Rt0, Rt1)
+        # resident inputs: K1b descriptor prep + batched match on the matching context, chunk by chunk, while the
+        # registration loop of the previous chunk runs on the main one (pipeline.register_device)
+        outs = pipeline.register_device(ctx, K, kps, dess, Rt0, Rt1)
         return outs, 0
 
     registered = V - 2
@@ -245,18 +245,22 @@ def run_engine(args):
     mt = prof.get("match_tc")
     roofline = None
     if mt:
-        # 2*Nq*Nt*128 flops per pair; one K1 launch covers the V-1 consecutive pairs of the scene
-        flops = 2.0 * n * n * 128 * (V - 1)
+        # 2*Nq*Nt*128 flops per pair; the V-1 consecutive pairs of the scene are matched by a few batched K1
+        # launches per step (one per chunk of pipeline.register_device: 11 + 48 + 140 pairs at V = 200)
+        lps = mt["launches"] / args.steps                     # K1 launches per step
+        flops = 2.0 * n * n * 128 * (V - 1) / lps             # average algorithmic flops per launch
         t_launch = mt["ms"] * 1e-3 / mt["launches"]
         ach = flops / t_launch / 1e12
         roofline = {"kernel": "match_tc_kernel (K1 tcgen05 distance GEMM + top-2 epilogue)", "bound": "tensor",
                     "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": ach / pk["bf16_sustained"],
                     # dram__bytes_read.sum + dram__bytes_write.sum of this very launch (199 pairs x 5000 descriptors) from
                     # one ncu --set full capture: profiles/r1v_match_tc_bench_199x5k.txt (327.9 + 84.1 MB); other sizes: null
-                    "traffic": 412.06e6 if (V == 200 and n == 5000) else None,
-                    "traffic_unit": "bytes per launch (ncu, profiles/r1v_match_tc_bench_199x5k.txt)",
+                    "traffic": 412.06e6 / lps if (V == 200 and n == 5000) else None,
+                    "traffic_unit": "bytes per launch, averaged like `achieved`: the ncu capture holds the scene's 199 pairs in one "
+                                    "launch (profiles/r1v_match_tc_bench_199x5k.txt, 2.07 MB per pair); divided by the launches per step",
                     "peak_source": pk["source"] + ", sustained bf16 (kernel timed inside a long step)",
-                    "algorithmic_flops_per_launch": flops, "pairs_per_launch": V - 1, "avg_launch_us": 1e6 * t_launch,
+                    "algorithmic_flops_per_launch": flops, "pairs_per_launch": (V - 1) / lps, "launches_per_step": lps,
+                    "avg_launch_us": 1e6 * t_launch,
                     "launches": mt["launches"],
                     "note": "K1 is the path's dense contraction (the kernel north_star sets a tensor-pipe target for). By time the "
                             "registration loop is dominated by the latency-bound PnP kernels (one warp per EPnP hypothesis, a "

@@ -175,14 +175,25 @@ class Context:
             check(lib.sfm_ctx_detach_stream(self._h))
         return self._tstream
 
+    def _aux(self):
+        """Auxiliary contexts working for this one (pipeline.register_*: the matching context); their launches and
+        kernel times are reported with this context's."""
+        m = getattr(self, "_match_ctx", None)
+        return [m] if m is not None and getattr(m, "_h", None) else []
+
     def launch_count(self) -> int:
-        return int(lib.sfm_ctx_launch_count(self._h))
+        return int(lib.sfm_ctx_launch_count(self._h)) + sum(a.launch_count() for a in self._aux())
 
     def set_profiling(self, on: bool):
         check(lib.sfm_ctx_set_profiling(self._h, 1 if on else 0))
+        self._profiling_on = bool(on)
+        for a in self._aux():
+            a.set_profiling(on)
 
     def reset_profile(self):
         check(lib.sfm_ctx_reset_profile(self._h))
+        for a in self._aux():
+            a.reset_profile()
 
     def profile(self) -> dict:
         out = {}
@@ -191,6 +202,11 @@ class Context:
             check(lib.sfm_ctx_get_profile(self._h, i, C.byref(ms), C.byref(n)))
             if n.value:
                 out[name] = dict(ms=ms.value, launches=n.value)
+        for a in self._aux():
+            for name, p in a.profile().items():
+                q = out.setdefault(name, dict(ms=0.0, launches=0))
+                q["ms"] += p["ms"]
+                q["launches"] += p["launches"]
         return out
 
     # ------------------------------------------------------------------ hot path 1: matching

@@ -271,7 +271,8 @@ class NativeChain:
         collect() waits and returns the records.  One call in flight."""
         import torch
         n_pairs = len(matches)
-        self._inflight = None
+        if getattr(self, "_inflight", None) is not None:
+            raise _e.error(-1, "NativeChain.launch: the previous call has not been collected")
         if n_pairs == 0:
             return
         first = self._fed == 0
@@ -345,16 +346,73 @@ def fetch_clouds(ctx: _e.Context, outs):
     return clouds
 
 
+def _chunk_bounds(V: int, edges):
+    edges = sorted(set([0] + [e for e in edges if 0 < e < V] + [V]))
+    return list(zip(edges[:-1], edges[1:]))
+
+
+def _register_pipelined(ctx: _e.Context, K, kp_d, des_d, Rt0, Rt1, bounds, events, ratio: float, nmax: int):
+    """Chunks of device-resident views -> registered views.  Matching runs on a second context (own stream,
+    workspace and descriptor pool) so that a chunk is prepared and matched — including the host reads of its match
+    counts — while the previous chunk's views register on the main context; the registration loop is launched
+    asynchronously (sfm_chain_extend_async) and collected one chunk later."""
+    mctx = getattr(ctx, "_match_ctx", None)
+    if mctx is None:
+        mctx = ctx._match_ctx = _e.Context(ctx.device)
+        if ctx_profiling(ctx):
+            mctx.set_profiling(True)
+    ms = mctx.torch_stream()
+    chain = RegistrationChain(mctx, K, ratio=ratio)
+    native = NativeChain(ctx, K, Rt0, Rt1, nmax)
+    views, outs, keep = [], [], []
+    try:
+        for k, (lo, hi) in enumerate(bounds):
+            if events is not None:
+                ms.wait_event(events[k])
+            views += DeviceView.batch(mctx, kp_d[lo:hi], des_d[lo:hi])
+            pairs = [(i, i + 1) for i in range(max(lo - 1, 0), hi - 1)]
+            if not pairs:
+                continue
+            matches = chain.match_pairs(views, pairs)     # synchronises the matching context: survivors are in HBM
+            keep.append(matches)
+            outs += native.collect()                      # previous chunk's views
+            native.launch(matches)
+        outs += native.collect()
+        ctx.sync()
+    finally:
+        native.close()
+    return outs, keep
+
+
+def ctx_profiling(ctx: _e.Context) -> bool:
+    return bool(getattr(ctx, "_profiling_on", False))
+
+
+def register_device(ctx: _e.Context, K, kps, dess, Rt0, Rt1, ratio: float = 0.70):
+    """Device-resident views (torch CUDA tensors: keypoints (n,2) f32, descriptors (n,128)) -> registered views.
+    A short first chunk starts the registration loop; the remaining pairs are matched while it runs.  Boundaries
+    measured on the 200-view x 5000 set (ms per step): (8) 37.1, (16) 36.5, (8,25) 35.7, (12,60) 34.5, (16,64,128) 34.7,
+    (12,50,100,150) 34.8, (10,40,80,120,160) 35.2 — a chunk boundary costs a host round trip, a long match launch
+    running beside the loop slows it."""
+    import os
+    V = len(kps)
+    edges = os.environ.get("SFM_REGISTER_EDGES")          # tuning aid: comma-separated chunk boundaries
+    bounds = _chunk_bounds(V, [int(e) for e in edges.split(",")] if edges else (12, 60))
+    outs, keep = _register_pipelined(ctx, K, kps, dess, Rt0, Rt1, bounds, None, ratio, max(int(k.shape[0]) for k in kps))
+    for o in outs:
+        o["_keep"] = keep
+    return outs
+
+
 def register_host(ctx: _e.Context, K, kps, dess, Rt0, Rt1, chunk: int = 25, ratio: float = 0.70):
     """Host arrays in, registered views out — the call a user makes with a sequence of views whose keypoints
     (n,2) and descriptors (n,128) sit in host memory (numpy arrays or torch CPU tensors; pinned memory lets the
-    upload overlap).  Views are uploaded on a copy stream in chunks; descriptor preparation, the batched match
-    of a chunk's pairs and the registration of its views run on the engine stream while later chunks are
-    still crossing PCIe."""
+    upload overlap).  Views are uploaded on a copy stream in chunks; descriptor preparation and the batched match
+    of a chunk's pairs run on a matching context, the registration of its views on the engine stream, while later
+    chunks are still crossing PCIe."""
     import torch
     V = len(kps)
     dev = ctx.torch_device
-    ts = ctx.torch_stream()
     as_t = lambda a: a if _e._is_torch(a) else torch.from_numpy(np.ascontiguousarray(a))
     kps = [as_t(a) for a in kps]
     dess = [as_t(a) for a in dess]
@@ -362,9 +420,7 @@ def register_host(ctx: _e.Context, K, kps, dess, Rt0, Rt1, chunk: int = 25, rati
     if cs is None:                                    # pool per stream, a fresh stream per call would cudaMalloc every buffer
         cs = ctx._copy_stream = torch.cuda.Stream(device=dev)
     # a short first chunk gets the loop going while the bulk of the upload is still in flight
-    edges = [0] + [e for e in (min(8, chunk), chunk) if e < V] + list(range(2 * chunk, V, chunk)) + [V]
-    edges = sorted(set(edges))
-    bounds = list(zip(edges[:-1], edges[1:]))
+    bounds = _chunk_bounds(V, [min(8, chunk), chunk] + list(range(2 * chunk, V, chunk)))
     kp_d, des_d, events = [None] * V, [None] * V, []
     with torch.cuda.stream(cs):
         for lo, hi in bounds:
@@ -374,34 +430,9 @@ def register_host(ctx: _e.Context, K, kps, dess, Rt0, Rt1, chunk: int = 25, rati
             ev = torch.cuda.Event()
             ev.record(cs)
             events.append(ev)
-    # Matching runs on a second context (own stream, workspace and descriptor pool) so that a chunk is prepared
-    # and matched — including the host reads of its match counts — while the previous chunk's views register on
-    # the main context; the registration loop is launched asynchronously and collected one chunk later.
-    mctx = getattr(ctx, "_match_ctx", None)
-    if mctx is None:
-        mctx = ctx._match_ctx = _e.Context(ctx.device)
-    ms = mctx.torch_stream()
-    chain = RegistrationChain(mctx, K, ratio=ratio)
-    native = NativeChain(ctx, K, Rt0, Rt1, max(int(k.shape[0]) for k in kps))
-    views, outs, keep = [], [], []
-    try:
-        for (lo, hi), ev in zip(bounds, events):
-            ms.wait_event(ev)
-            views += DeviceView.batch(mctx, kp_d[lo:hi], des_d[lo:hi])
-            pairs = [(i, i + 1) for i in range(max(lo - 1, 0), hi - 1)]
-            if not pairs:
-                continue
-            matches = chain.match_pairs(views, pairs)
-            keep.append(matches)
-            mctx.sync()                       # the survivors of this chunk are in HBM
-            outs += native.collect()          # previous chunk's views
-            native.launch(matches)
-        outs += native.collect()
-        ctx.sync()
-    finally:
-        native.close()
+    outs, keep = _register_pipelined(ctx, K, kp_d, des_d, Rt0, Rt1, bounds, events, ratio, max(int(k.shape[0]) for k in kps))
     for o in outs:
-        o["_keep"] = (kp_d, des_d)      # uploaded on the copy stream: stay referenced until the caller drops the result
+        o["_keep"] = (kp_d, des_d, keep)      # uploaded on the copy stream: stay referenced until the caller drops the result
     return outs
 
 

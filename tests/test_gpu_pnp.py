@@ -245,3 +245,36 @@ def test_registration_at_baseline_descriptor_count(engine):
     for a, b in zip(outs, res):
         assert (a["n_match"], a["n_pnp"], a["n_inl"], a["n_new"]) == (b["n_match"], b["n_pnp"], b["n_inl"], b["n_new"])
         assert np.abs(a["Rt"] - b["Rt"]).max() < 1e-7
+    # the pipelined resident driver (matching context + sfm_chain_extend_async / collect, what bench.py times):
+    # the same kernels on the same data, so the same records bit for bit
+    pip = pipeline.register_device(engine, K, kps, dess, Rt0, Rt1)
+    assert len(pip) == 28
+    for a, b in zip(pip, res):
+        assert (a["n_match"], a["n_pnp"], a["n_inl"], a["n_new"]) == (b["n_match"], b["n_pnp"], b["n_inl"], b["n_new"])
+        assert np.array_equal(a["Rt"], b["Rt"]) and a["err_pnp"] == b["err_pnp"] and a["err_new"] == b["err_new"]
+        assert torch.equal(a["X_new"][:a["n_new"]], b["X_new"][:b["n_new"]])
+
+
+def test_chain_extend_async_needs_collect(engine):
+    """One asynchronous call in flight per chain: a second sfm_chain_extend_async before sfm_chain_collect is an
+    error, collect without a pending call returns nothing."""
+    from sfm_mvs_b200 import pipeline
+    scene = synth.orbit_scene(5, 900, seed=4)
+    K = scene["K"]
+    Rt0 = np.hstack([scene["views"][0]["R"], scene["views"][0]["t"]])
+    Rt1 = np.hstack([scene["views"][1]["R"], scene["views"][1]["t"]])
+    views = [pipeline.DeviceView(engine, v["kp"], v["des"]) for v in scene["views"]]
+    chain = pipeline.RegistrationChain(engine, K)
+    matches = chain.match_pairs(views, [(i, i + 1) for i in range(4)])
+    nc = pipeline.NativeChain(engine, K, Rt0, Rt1, max(pm.n for pm in matches))
+    try:
+        assert nc.collect() == []
+        nc.launch(matches[:3])
+        with pytest.raises(sfm.error):
+            nc.launch(matches[3:])
+        first = nc.collect()
+        assert len(first) == 2
+        nc.launch(matches[3:])
+        assert len(nc.collect()) == 1
+    finally:
+        nc.close()
