@@ -192,6 +192,7 @@ extern "C" int sfm_chain_create(sfm_ctx* ctx, const double* K, const double* Rt0
       matmul_K_Rt(K, Rt1, p->P2);
       p->started = false; p->prev_q = p->prev_t = nullptr; p->prev_n = 0; p->pts1 = p->points_3d = nullptr; p->n1 = 0;
       p->views_done = 0; p->set_used[0] = p->set_used[1] = false;
+      p->pending = p->pending_parsed = false; p->pend_reg = 0;     // an uncollected call died with its chain
       SFM_CUDA(cudaMemcpyAsync(p->K_dev, p->K, 9 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
       SFM_CUDA(cudaMemcpyAsync(p->P_view, p->P1, 12 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
       SFM_CUDA(cudaMemcpyAsync(p->P_view + 12, p->P2, 12 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));

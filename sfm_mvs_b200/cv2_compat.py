@@ -127,16 +127,15 @@ LMEDS = 4         # cv2.LMEDS
 
 
 def findEssentialMat(points1, points2, cameraMatrix=None, method: int = RANSAC, prob: float = 0.999,
-                     threshold: float = 1.0, maxIters: int = 1000, mask=None, ctx: _e.Context | None = None):
+                     threshold: float = 1.0, maxIters: int = 1000, mask=None, focal=None, pp=None,
+                     ctx: _e.Context | None = None):
     """cv2.findEssentialMat(pts0, pts1, K, method=cv2.RANSAC, prob=0.999, threshold=0.4, mask=None) as the
     reference calls it (sfm.py:307, isfm.py:80, test.py:247) -> (E (3,3) float64, mask (N,1) uint8 of 1 / 0).
     N == 5 returns every model of the single sample stacked as (3k,3) like cv2; N < 5 or no model returns
     (None, None) / (None, zeros).  Only the RANSAC method with a 3x3 camera matrix is implemented (the
     reference uses nothing else); LMEDS / USAC and the focal+pp overload raise.  `mask` is output-only in cv2."""
-    import ctypes as C
     from ._lib import check, lib
-    ctx = ctx or default_context()
-    if cameraMatrix is None or np.ndim(cameraMatrix) != 2:
+    if focal is not None or pp is not None or cameraMatrix is None or np.ndim(cameraMatrix) != 2:
         raise error(-1, "findEssentialMat: the 3x3 cameraMatrix overload is the one implemented")
     if int(method) != RANSAC:
         raise error(-1, "findEssentialMat: only method=cv2.RANSAC is implemented")
@@ -156,6 +155,7 @@ def findEssentialMat(points1, points2, cameraMatrix=None, method: int = RANSAC, 
     n = p1.shape[0]
     if n < 5:
         return None, None
+    ctx = ctx or default_context()
     E = np.zeros((10, 3, 3))
     m_out = np.zeros((n, 1), np.uint8)
     info = np.zeros(6, np.int32)

@@ -1,0 +1,45 @@
+"""Host-side logic that needs no GPU: chunking of the pipelined drivers, argument checks of the cv2-compatible
+wrappers that run before any device work."""
+import numpy as np
+import pytest
+
+import sfm_mvs_b200 as sfm
+from sfm_mvs_b200 import pipeline, synth
+
+
+def test_chunk_bounds():
+    assert pipeline._chunk_bounds(200, (12, 60)) == [(0, 12), (12, 60), (60, 200)]
+    assert pipeline._chunk_bounds(200, [8, 25] + list(range(50, 200, 25))) == \
+        [(0, 8), (8, 25), (25, 50), (50, 75), (75, 100), (100, 125), (125, 150), (150, 175), (175, 200)]
+    assert pipeline._chunk_bounds(5, (12, 60)) == [(0, 5)]
+    assert pipeline._chunk_bounds(12, (12, 60)) == [(0, 12)]
+    assert pipeline._chunk_bounds(30, (25, 8, 8, 0)) == [(0, 8), (8, 25), (25, 30)]
+    for V in (3, 13, 61, 200):
+        b = pipeline._chunk_bounds(V, (12, 60))
+        assert b[0][0] == 0 and b[-1][1] == V and all(x[1] == y[0] for x, y in zip(b, b[1:]))
+
+
+def test_find_essential_mat_argument_checks_need_no_device():
+    """cv2's behaviour at the boundary (sfm.py:307): fewer than five correspondences -> (None, None); mismatched
+    point arrays, a non-3x3 camera matrix, an unsupported method or a confidence outside (0, 1) raise."""
+    K = synth.K_GUSTAV
+    p0, p1, _, _ = synth.two_view_pair(4, seed=0)
+    assert sfm.findEssentialMat(p0, p1, K, method=8, prob=0.999, threshold=0.4) == (None, None)
+    q0, q1, _, _ = synth.two_view_pair(20, seed=0)
+    with pytest.raises(sfm.error):
+        sfm.findEssentialMat(q0, q1[:10], K)
+    with pytest.raises(sfm.error):
+        sfm.findEssentialMat(q0, q1, K[:2])
+    with pytest.raises(sfm.error):
+        sfm.findEssentialMat(q0, q1, K, method=4)
+    with pytest.raises(sfm.error):
+        sfm.findEssentialMat(q0, q1, K, prob=1.0)
+    with pytest.raises(sfm.error):
+        sfm.findEssentialMat(q0, q1, focal=1.0)          # the focal / pp overload is not implemented
+
+
+def test_two_view_pair_is_deterministic_and_has_the_stated_outlier_share():
+    a0, a1, R, t = synth.two_view_pair(500, seed=3, outliers=0.2)
+    b0, b1, _, _ = synth.two_view_pair(500, seed=3, outliers=0.2)
+    assert np.array_equal(a0, b0) and np.array_equal(a1, b1) and a0.dtype == np.float32
+    assert abs(np.linalg.det(R) - 1) < 1e-12 and np.abs(R @ R.T - np.eye(3)).max() < 1e-12
