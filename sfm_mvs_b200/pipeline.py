@@ -481,3 +481,29 @@ def two_view_init(pts0, pts1, K, Rt0=None, ctx=None):
     Rt1[:3, :3] = R @ Rt0[:3, :3]
     Rt1[:3, 3] = Rt0[:3, 3] + Rt0[:3, :3] @ t.ravel()
     return dict(E=E[:3], Rt0=Rt0, Rt1=Rt1, pts0=a, pts1=b, n_essential=n_e, n_pose=len(a))
+
+
+def pairwise_init(ctx: _e.Context, views, K, pairs=None, ratio: float = 0.70):
+    """isfm.py:68-87 — every earlier view j against the new view i: 2-NN + ratio matches (ALL pairs in one batched
+    K1 launch), then per pair findEssentialMat(RANSAC, 0.999, 0.4) -> mask -> recoverPose -> mask, as the reference
+    does it.  `views` are DeviceView; `pairs` defaults to all (j, i), j < i, in the reference's order (i outer).
+    -> list of dict(pair, n_match, n_essential, n_pose (what isfm.py prints), R, t, pts0, pts1)."""
+    V = len(views)
+    if pairs is None:
+        pairs = [(j, i) for i in range(V) for j in range(i)]
+    chain = RegistrationChain(ctx, K, ratio=ratio)
+    matches = chain.match_pairs(views, pairs)
+    out = []
+    for (j, i), pm in zip(pairs, matches):
+        p0 = pm.pts_q[:pm.n].cpu().numpy()
+        p1 = pm.pts_t[:pm.n].cpu().numpy()
+        rec = dict(pair=(j, i), n_match=pm.n, n_essential=0, n_pose=0, R=None, t=None, pts0=p0[:0], pts1=p1[:0])
+        if pm.n >= 5:
+            try:
+                init = two_view_init(p0, p1, K, ctx=ctx)
+                rec.update(n_essential=init["n_essential"], n_pose=init["n_pose"], R=init["Rt1"][:, :3].copy(),
+                           t=init["Rt1"][:, 3:].copy(), pts0=init["pts0"], pts1=init["pts1"])
+            except _e.error:
+                pass                      # no essential matrix for this pair (the reference would raise on E = None)
+        out.append(rec)
+    return out

@@ -119,3 +119,43 @@ def test_two_view_init_equals_reference_lines(engine):
     ang = np.degrees(np.arccos(np.clip((np.trace(out["Rt1"][:, :3] @ R_gt.T) - 1) / 2, -1, 1)))
     tdir = np.degrees(np.arccos(np.clip(out["Rt1"][:, 3] @ t_gt / np.linalg.norm(t_gt), -1, 1)))
     assert ang < 0.5 and tdir < 2.0
+
+
+def test_pairwise_init_equals_the_isfm_loop(engine):
+    """isfm.py:68-87 — all earlier views against each new view: match, findEssentialMat, recoverPose, survivor count
+    (the number isfm.py prints).  Against the same lines on stock cv2 (oracle.cvpath matching + cv2 calls)."""
+    from oracle import cvpath
+    from sfm_mvs_b200 import pipeline
+    scene = synth.orbit_scene(4, 1500, seed=11)
+    Ks = scene["K"]
+    views = [pipeline.DeviceView(engine, v["kp"], v["des"]) for v in scene["views"]]
+    got = pipeline.pairwise_init(engine, views, Ks)
+    assert [g["pair"] for g in got] == [(0, 1), (0, 2), (1, 2), (0, 3), (1, 3), (2, 3)]
+    for g in got:
+        j, i = g["pair"]
+        vj, vi = scene["views"][j], scene["views"][i]
+        p0, p1 = cvpath.match_keypoints(vj["kp"], vj["des"], vi["kp"], vi["des"])
+        assert g["n_match"] == len(p0)
+        E, mask = cv2.findEssentialMat(p0, p1, Ks, method=cv2.RANSAC, prob=0.999, threshold=0.4, mask=None)
+        a, b = p0[mask.ravel() == 1], p1[mask.ravel() == 1]
+        _, R, t, mask = cv2.recoverPose(E, a, b, Ks)
+        a, b = a[mask.ravel() > 0], b[mask.ravel() > 0]
+        assert g["n_essential"] == int((cv2.findEssentialMat(p0, p1, Ks, method=cv2.RANSAC, prob=0.999, threshold=0.4)[1] == 1).sum())
+        assert g["n_pose"] == len(a) and np.array_equal(g["pts0"], a) and np.array_equal(g["pts1"], b)
+        assert np.abs(g["R"] - R).max() < 1e-6 and np.abs(g["t"] - t).max() < 1e-6
+
+
+@pytest.mark.parametrize("n,seed,prob,thr,max_iters,dtype",
+                         [(500, 0, 0.99, 1.0, 50, np.float32), (800, 1, 0.9, 3.0, 1000, np.float32),
+                          (300, 2, 0.999, 0.4, 5, np.float64), (1000, 3, 0.5, 0.2, 1000, np.float32),
+                          (400, 4, 0.999, 0.05, 200, np.float64)])
+def test_find_essential_mat_parameter_variants(engine, n, seed, prob, thr, max_iters, dtype):
+    """Other confidences, thresholds, iteration caps and float64 points than the reference's call: same mask as cv2,
+    same iteration count and winner as the restated loop."""
+    p0, p1, _, _ = synth.two_view_pair(n, seed=seed, dtype=dtype)
+    Ec, mc = cv2.findEssentialMat(p0, p1, K, method=cv2.RANSAC, prob=prob, threshold=thr, maxIters=max_iters)
+    Eo, mo = sfm.findEssentialMat(p0, p1, K, method=cv2.RANSAC, prob=prob, threshold=thr, maxIters=max_iters, ctx=engine)
+    got = dict(sfm.findEssentialMat.last_info)
+    assert np.array_equal(mo, mc) and _e_close(Eo, Ec[:3]) < 1e-7
+    _, _, info = restated.find_essential_mat(p0, p1, K, prob, thr, max_iters)
+    assert (got["iters"], got["best_iter"], got["inliers"]) == (info["iters"], info["best_iter"], info["best_count"])

@@ -230,3 +230,19 @@ def test_restated_find_essential_mat_equals_cv2(n, seed):
     Eo, mo, info = restated.find_essential_mat(p0, p1, K, 0.999, 0.4)
     assert np.array_equal(mo, mc.ravel() != 0) and int(mo.sum()) == info["best_count"] > 5
     assert _e_close(Eo, Ec[:3]) < 1e-7
+
+
+E_VARIANTS = [(500, 0, 0.99, 1.0, 50, np.float32), (800, 1, 0.9, 3.0, 1000, np.float32), (300, 2, 0.999, 0.4, 5, np.float64),
+              (1000, 3, 0.5, 0.2, 1000, np.float32), (400, 4, 0.999, 0.05, 200, np.float64)]
+
+
+@pytest.mark.parametrize("n,seed,prob,thr,max_iters,dtype", E_VARIANTS)
+def test_restated_find_essential_mat_parameter_variants(n, seed, prob, thr, max_iters, dtype):
+    """Other confidences, thresholds, iteration caps and float64 points than the reference's call: the stopping rule
+    (RANSACUpdateNumIters against maxIters) and the threshold scaling by the mean focal length still give cv2's mask."""
+    K = synth.K_GUSTAV
+    p0, p1, _, _ = synth.two_view_pair(n, seed=seed, dtype=dtype)
+    Ec, mc = cv2.findEssentialMat(p0, p1, K, method=cv2.RANSAC, prob=prob, threshold=thr, maxIters=max_iters)
+    Eo, mo, info = restated.find_essential_mat(p0, p1, K, prob, thr, max_iters)
+    assert np.array_equal(mo, mc.ravel() != 0) and info["iters"] <= max_iters
+    assert _e_close(Eo, Ec[:3]) < 1e-7
