@@ -5,8 +5,10 @@ match(prev, new) + ratio test, re-triangulation of the previous pair's matches, 
 (common_points), PnP-RANSAC, reprojection error, triangulation of the new points, reprojection
 error.  Keypoints, descriptors, matches, 3-D points and masks live in HBM (torch CUDA tensors are
 used as plain device buffers); per view the host learns three integers (match / association
-counts) and the pose.  Matching does not depend on poses, so all consecutive pairs are matched up
-front in one stream-ordered batch (this is also the unit that shards over GPUs, isfm.py:68-87).
+counts) and the pose.  Matching does not depend on poses, so consecutive pairs are matched in batches
+(one K1 launch per batch; this is also the unit that shards over GPUs, isfm.py:68-87) on a second context
+while the registration loop of the previous batch runs (register_device / register_host).  two_view_init is
+the reference's initialisation (sfm.py:307-316), pairwise_init the all-earlier-views loop of isfm.py:68-87.
 """
 from __future__ import annotations
 
