@@ -237,6 +237,10 @@ int sfm_recover_pose(sfm_ctx* ctx, const double* E, const void* pts1, const void
  * winning iteration, winning model within it, models scored}. */
 int sfm_find_essential_mat(sfm_ctx* ctx, const void* pts1, const void* pts2, int dtype, int n, const double* K,
                            double prob, double threshold, int max_iters, double* E, uint8_t* mask, int32_t* info);
+/* Host utility (no GPU needed): Nister's five-point solver on ONE minimal sample — the code the hypothesis kernel
+ * runs, compiled for the host.  q1, q2: 5 x 2 normalised coordinates; E: 90 doubles (<= 10 row-major 3x3 models,
+ * unit Frobenius norm, ascending E00^2); n_models: how many. */
+int sfm_five_point(const double* q1, const double* q2, double* E, int32_t* n_models);
 
 /* ------------------------------------------------------------------ hot path 3a: PnP-RANSAC
  * Replaces cv2.solvePnPRansac(X, p, K, d, ...) with OpenCV's defaults, which is what the

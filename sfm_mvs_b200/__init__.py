@@ -5,7 +5,7 @@ hand-written sm_100a CUDA kernels (sfm_mvs_b200/csrc).  Importing this package r
 shared library; using it requires a CUDA device.  There is no CPU fallback.
 """
 from ._lib import LIB_PATH, error  # noqa: F401  (import fails loudly if the library is missing)
-from .engine import (BAProblem, Context, Descriptors, epnp, nccl_unique_id, ransac_subsets,  # noqa: F401
+from .engine import (BAProblem, Context, Descriptors, epnp, five_point, nccl_unique_id, ransac_subsets,  # noqa: F401
                      rodrigues_to_matrix, rodrigues_to_vector)
 from .cv2_compat import (NORM_L2, RATIO, SOLVEPNP_ITERATIVE, BFMatcher, BundleAdjustment, DMatch, PnP,  # noqa: F401
                          ReprojectionError, Triangulation, common_points, default_context, findEssentialMat, knn2,

@@ -49,14 +49,14 @@ __host__ __device__ constexpr int cubic_col_exp(int e) {
 __host__ __device__ constexpr int cubic_col(int q, int l) { return cubic_col_exp(quad_exp(q) + lin_exp(l)); }
 
 // q += s * a * b   (linear x linear -> quadratic)
-__device__ __forceinline__ void mul_ll(const double* a, const double* b, double* q, double s) {
+__host__ __device__ __forceinline__ void mul_ll(const double* a, const double* b, double* q, double s) {
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) q[quad_index(i, j)] += s * a[i] * b[j];
 }
 // c += q * l   (quadratic x linear -> cubic, scattered to the elimination order)
-__device__ __forceinline__ void mul_ql(const double* q, const double* l, double* c) {
+__host__ __device__ __forceinline__ void mul_ql(const double* q, const double* l, double* c) {
 #pragma unroll
   for (int i = 0; i < 10; ++i)
 #pragma unroll
@@ -66,7 +66,7 @@ __device__ __forceinline__ void mul_ql(const double* q, const double* l, double*
 // ---- null space of the 5x9 epipolar system: Gauss-Jordan with complete pivoting, then two rounds of modified
 // Gram-Schmidt so the four basis vectors are orthonormal (the solutions do not depend on the basis; an
 // orthonormal one keeps the cubic system well scaled).  basis[k][9], k = X, Y, Z, W.
-__device__ inline bool null_space_5x9(double (*Q)[9], double (*basis)[9]) {
+__host__ __device__ inline bool null_space_5x9(double (*Q)[9], double (*basis)[9]) {
   int perm[9];
   for (int j = 0; j < 9; ++j) perm[j] = j;
   for (int r = 0; r < 5; ++r) {
@@ -114,7 +114,7 @@ __device__ inline bool null_space_5x9(double (*Q)[9], double (*basis)[9]) {
 }
 
 // ---- the ten cubic constraints: det(E) = 0 and (E E^T - tr(E E^T)/2 I) E = 0, E = x X + y Y + z Z + W
-__device__ inline void build_constraints(const double (*basis)[9], double (*M)[20]) {
+__host__ __device__ inline void build_constraints(const double (*basis)[9], double (*M)[20]) {
   double e[9][4];
 #pragma unroll
   for (int c = 0; c < 9; ++c)
@@ -168,7 +168,7 @@ __device__ inline void build_constraints(const double (*basis)[9], double (*M)[2
 
 // Gauss-Jordan on the first ten columns (partial pivoting); afterwards row i reads
 // monomial_i + sum_j M[i][10+j] * tail_j = 0.
-__device__ inline bool reduce_constraints(double (*M)[20]) {
+__host__ __device__ inline bool reduce_constraints(double (*M)[20]) {
   for (int c = 0; c < 10; ++c) {
     int p = c;
     double best = fabs(M[c][c]);
@@ -191,7 +191,7 @@ __device__ inline bool reduce_constraints(double (*M)[20]) {
   return true;
 }
 
-__device__ __forceinline__ double horner(const double* c, int deg, double x) {   // ascending coefficients
+__host__ __device__ __forceinline__ double horner(const double* c, int deg, double x) {   // ascending coefficients
   double v = c[deg];
   for (int k = deg - 1; k >= 0; --k) v = fma(v, x, c[k]);
   return v;
@@ -199,7 +199,7 @@ __device__ __forceinline__ double horner(const double* c, int deg, double x) {  
 
 // A root of q (degree m, ascending coefficients) bracketed by [lo, hi] with sign(q(lo)) = slo != sign(q(hi)):
 // Newton steps kept inside the bracket, bisection otherwise.
-__device__ inline double bracketed_root(const double* q, int m, double lo, double hi, int slo) {
+__host__ __device__ inline double bracketed_root(const double* q, int m, double lo, double hi, int slo) {
   double x = 0.5 * (lo + hi), dxold = hi - lo, dx = dxold;
   for (int it = 0; it < 200; ++it) {
     double f = q[m], df = 0.0;
@@ -226,7 +226,7 @@ __device__ inline double bracketed_root(const double* q, int m, double lo, doubl
 // All real roots of p (ascending coefficients, degree n <= 10), ascending: the real roots of the k-th derivative
 // split the line into intervals on which the (k-1)-th derivative is monotonic, so each level's roots are
 // bracketed by the previous level's.  Roots of even multiplicity (no sign change) are not reported.
-__device__ inline int real_roots(const double* p, int n, double* roots) {
+__host__ __device__ inline int real_roots(const double* p, int n, double* roots) {
   // Fujiwara's bound on |root|
   double R = 0.0;
   for (int k = 1; k <= n; ++k) {
@@ -298,31 +298,16 @@ __global__ void e5_normalize_kernel(const void* __restrict__ p1, const void* __r
   qn[4 * i + 3] = (d - cy) / fy;
 }
 
-constexpr int E5_SOLVE_THREADS = 8;   // few lanes per warp: the 1000 independent solves spread over every SM and a
-                                      // warp waits only for the slowest of 8 data-dependent root searches
-__global__ void __launch_bounds__(32) e5_solve_kernel(const double* __restrict__ qn, const int* __restrict__ subsets,
-                                                      int iters, double* __restrict__ models /*iters x 10 x 9*/,
-                                                      int* __restrict__ nmodels) {
-  const int it = blockIdx.x * blockDim.x + threadIdx.x;
-  if (it >= iters) return;
+// One minimal sample: Q = the 5x9 epipolar system (destroyed).  Writes the essential matrices (unit Frobenius norm,
+// ascending E00^2) to out[10][9] and returns how many.  Host-callable too (sfm_five_point), so the CPU tests exercise
+// the very code the kernel runs.
+__host__ __device__ inline int five_point_solve(double (*Q)[9], double* out) {
   int nm = 0;
-  double* out = models + (size_t)it * E5_MAXM * 9;
   double basis[4][9];
   double M[10][20];
-  {
-    double Q[5][9];
-    for (int r = 0; r < 5; ++r) {
-      const int i = subsets[5 * it + r];
-      const double x1 = qn[4 * i], y1 = qn[4 * i + 1], x2 = qn[4 * i + 2], y2 = qn[4 * i + 3];
-      // x2^T E x1 = 0, E row-major
-      Q[r][0] = x2 * x1; Q[r][1] = x2 * y1; Q[r][2] = x2;
-      Q[r][3] = y2 * x1; Q[r][4] = y2 * y1; Q[r][5] = y2;
-      Q[r][6] = x1;      Q[r][7] = y1;      Q[r][8] = 1.0;
-    }
-    if (!null_space_5x9(Q, basis)) { nmodels[it] = 0; return; }
-  }
+  if (!null_space_5x9(Q, basis)) return 0;
   build_constraints(basis, M);
-  if (!reduce_constraints(M)) { nmodels[it] = 0; return; }
+  if (!reduce_constraints(M)) return 0;
   // B(z): rows <x^2 z> - z <x^2>, <y^2 z> - z <y^2>, <xyz> - z <xy>; each is x p3(z) + y q3(z) + r4(z).
   // Ascending coefficients; entries 0, 1 have degree 3, entry 2 degree 4.
   double B[3][3][5];
@@ -364,10 +349,10 @@ __global__ void __launch_bounds__(32) e5_solve_kernel(const double* __restrict__
   }
   bool finite = true;
   for (int k = 0; k < 11; ++k) finite = finite && isfinite(det[k]);
-  if (!finite) { nmodels[it] = 0; return; }
+  if (!finite) return 0;
   int deg = 10;
   while (deg > 1 && fabs(det[deg]) <= DBL_EPSILON) --deg;     // solvePoly's leading-coefficient trim
-  if (fabs(det[deg]) == 0.0) { nmodels[it] = 0; return; }
+  if (fabs(det[deg]) == 0.0) return 0;
   double roots[E5_MAXM];
   const int nr = real_roots(det, deg, roots);
   double key[E5_MAXM];
@@ -413,7 +398,26 @@ __global__ void __launch_bounds__(32) e5_solve_kernel(const double* __restrict__
     for (int c = 0; c < 9; ++c) out[9 * pos + c] = E[c];
     ++nm;
   }
-  nmodels[it] = nm;
+  return nm;
+}
+
+constexpr int E5_SOLVE_THREADS = 8;   // few lanes per warp: the 1000 independent solves spread over every SM and a
+                                      // warp waits only for the slowest of 8 data-dependent root searches
+__global__ void __launch_bounds__(32) e5_solve_kernel(const double* __restrict__ qn, const int* __restrict__ subsets,
+                                                      int iters, double* __restrict__ models /*iters x 10 x 9*/,
+                                                      int* __restrict__ nmodels) {
+  const int it = blockIdx.x * blockDim.x + threadIdx.x;
+  if (it >= iters) return;
+  double Q[5][9];
+  for (int r = 0; r < 5; ++r) {
+    const int i = subsets[5 * it + r];
+    const double x1 = qn[4 * i], y1 = qn[4 * i + 1], x2 = qn[4 * i + 2], y2 = qn[4 * i + 3];
+    // x2^T E x1 = 0, E row-major
+    Q[r][0] = x2 * x1; Q[r][1] = x2 * y1; Q[r][2] = x2;
+    Q[r][3] = y2 * x1; Q[r][4] = y2 * y1; Q[r][5] = y2;
+    Q[r][6] = x1;      Q[r][7] = y1;      Q[r][8] = 1.0;
+  }
+  nmodels[it] = five_point_solve(Q, models + (size_t)it * E5_MAXM * 9);
 }
 
 // EMEstimatorCallback::computeError: (x2^T E x1)^2 / (|E x1|_xy^2 + |E^T x2|_xy^2) in float64 with separately
@@ -502,6 +506,20 @@ __global__ void e5_mask_kernel(const double* __restrict__ qn, int n, const E5Res
 }
 
 }  // namespace
+
+// ---- host utility (usable without a GPU): the minimal solver on one sample of normalised coordinates
+extern "C" int sfm_five_point(const double* q1, const double* q2, double* E, int32_t* n_models) {
+  SFM_REQUIRE(q1 && q2 && E && n_models, "sfm_five_point: null argument");
+  double Q[5][9];
+  for (int r = 0; r < 5; ++r) {
+    const double x1 = q1[2 * r], y1 = q1[2 * r + 1], x2 = q2[2 * r], y2 = q2[2 * r + 1];
+    Q[r][0] = x2 * x1; Q[r][1] = x2 * y1; Q[r][2] = x2;
+    Q[r][3] = y2 * x1; Q[r][4] = y2 * y1; Q[r][5] = y2;
+    Q[r][6] = x1;      Q[r][7] = y1;      Q[r][8] = 1.0;
+  }
+  *n_models = five_point_solve(Q, E);
+  return SFM_OK;
+}
 
 extern "C" int sfm_find_essential_mat(sfm_ctx* ctx, const void* pts1, const void* pts2, int dtype, int n,
                                       const double* K, double prob, double threshold, int max_iters,

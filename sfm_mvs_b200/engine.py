@@ -384,6 +384,19 @@ def epnp(X, px, K):
     return R.reshape(3, 3), t
 
 
+def five_point(q1, q2):
+    """Nister's five-point solver on one minimal sample of normalised coordinates (5,2) — the hypothesis kernel's
+    code compiled for the host (sfm_five_point; no GPU needed).  -> (k,3,3) essential matrices, k <= 10."""
+    q1 = np.ascontiguousarray(q1, np.float64).reshape(-1, 2)
+    q2 = np.ascontiguousarray(q2, np.float64).reshape(-1, 2)
+    if q1.shape != (5, 2) or q2.shape != (5, 2):
+        raise error(-1, "five_point: needs exactly five correspondences")
+    E = np.zeros((10, 3, 3))
+    k = C.c_int32(0)
+    check(lib.sfm_five_point(_dptr(q1), _dptr(q2), _dptr(E), C.byref(k)))
+    return E[:k.value].copy()
+
+
 # ---------------------------------------------------------------------- hot path 3b: bundle adjustment
 class BAProblem:
     """A bundle-adjustment problem resident in HBM (sfm_ba).  Observations must be point-major."""

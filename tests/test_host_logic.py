@@ -43,3 +43,33 @@ def test_two_view_pair_is_deterministic_and_has_the_stated_outlier_share():
     b0, b1, _, _ = synth.two_view_pair(500, seed=3, outliers=0.2)
     assert np.array_equal(a0, b0) and np.array_equal(a1, b1) and a0.dtype == np.float32
     assert abs(np.linalg.det(R) - 1) < 1e-12 and np.abs(R @ R.T - np.eye(3)).max() < 1e-12
+
+
+def test_five_point_kernel_code_on_the_host_equals_the_oracle():
+    """sfm_five_point is the hypothesis kernel's solver (null space, cubic constraints, Gauss-Jordan, det B(z), real
+    roots by derivative bracketing) compiled for the host: 300 minimal samples against oracle/restated.py five_point
+    (numpy SVD null space + companion-matrix roots).  Same number of models, the same matrices in the same order."""
+    from oracle import restated
+    K = synth.K_GUSTAV
+    n_models, off_count, worst, loose = 0, 0, 0.0, 0
+    for seed in range(300):
+        p0, p1, _, _ = synth.two_view_pair(5, seed=1000 + seed, noise=0.3, outliers=0.0)
+        q0 = (p0.astype(np.float64) - K[:2, 2]) / [K[0, 0], K[1, 1]]
+        q1 = (p1.astype(np.float64) - K[:2, 2]) / [K[0, 0], K[1, 1]]
+        Eh = sfm.five_point(q0, q1)
+        Eo = restated.five_point(q0, q1)
+        x0, x1 = np.column_stack([q0, np.ones(5)]), np.column_stack([q1, np.ones(5)])
+        for e in Eh:                       # every model solves the minimal problem
+            assert np.abs(np.einsum("ni,ij,nj->n", x1, e, x0)).max() < 1e-9
+            assert np.abs(2 * e @ e.T @ e - np.trace(e @ e.T) * e).max() < 1e-7
+            assert abs(np.linalg.norm(e) - 1) < 1e-12
+        if len(Eh) != len(Eo):             # a near-double root found by one root finder only
+            off_count += 1
+            continue
+        for a, b in zip(Eh, Eo):
+            d = min(np.abs(a - b).max(), np.abs(a + b).max())
+            worst = max(worst, d)
+            loose += d > 1e-8
+            n_models += 1
+    assert off_count <= 3 and n_models > 1000
+    assert worst < 1e-5 and loose <= 0.02 * n_models
