@@ -73,3 +73,49 @@ def test_five_point_kernel_code_on_the_host_equals_the_oracle():
             n_models += 1
     assert off_count <= 3 and n_models > 1000
     assert worst < 1e-5 and loose <= 0.02 * n_models
+
+
+def test_five_point_kernel_code_on_the_host_equals_cv2_minimal_solver():
+    """Against OpenCV's own minimal solver: with exactly five correspondences cv2.findEssentialMat returns every model
+    of the sample.  Same number of models on every sample; matrices equal up to sign (a handful of ill-conditioned
+    roots differ beyond 1e-6 between ANY two implementations — Durand-Kerner vs bracketing vs companion matrix)."""
+    import cv2
+    K = synth.K_GUSTAV
+    same, models, matched = 0, 0, 0
+    N = 500
+    for seed in range(N):
+        p0, p1, _, _ = synth.two_view_pair(5, seed=5000 + seed, noise=0.3, outliers=0.0)
+        Ec, _ = cv2.findEssentialMat(p0, p1, K, method=cv2.RANSAC, prob=0.999, threshold=0.4)
+        Ec = np.zeros((0, 3, 3)) if Ec is None else Ec.reshape(-1, 3, 3)
+        q0 = (p0.astype(np.float64) - K[:2, 2]) / [K[0, 0], K[1, 1]]
+        q1 = (p1.astype(np.float64) - K[:2, 2]) / [K[0, 0], K[1, 1]]
+        Eh = sfm.five_point(q0, q1)
+        same += len(Eh) == len(Ec)
+        for e in Eh:
+            models += 1
+            matched += bool(len(Ec)) and min(min(np.abs(e - c).max(), np.abs(e + c).max()) for c in Ec) < 1e-6
+    assert same >= N - 2
+    assert matched >= 0.99 * models
+
+
+def test_five_point_degenerate_samples_terminate_with_finite_output():
+    """Identical views, duplicated correspondences, collinear points, extreme scales, all-zero input: the solver returns
+    (possibly zero) finite models and never hangs — the RANSAC loop feeds it whatever the index stream draws."""
+    r = np.random.default_rng(0)
+    for k in range(1200):
+        kind = k % 6
+        q0, q1 = r.uniform(-1, 1, (5, 2)), r.uniform(-1, 1, (5, 2))
+        if kind == 0:
+            q1 = q0.copy()
+        elif kind == 1:
+            q0[1], q1[1] = q0[0], q1[0]
+        elif kind == 2:
+            q0[:, 1], q1[:, 1] = 0.3 * q0[:, 0], 0.3 * q1[:, 0]
+        elif kind == 3:
+            q0, q1 = q0 * 1e-9, q1 * 1e-9
+        elif kind == 4:
+            q0, q1 = q0 * 1e6, q1 * 1e6
+        else:
+            q0[:], q1[:] = 0, 0
+        E = sfm.five_point(q0, q1)
+        assert E.shape[0] <= 10 and np.all(np.isfinite(E))
