@@ -353,7 +353,8 @@ def _chunk_bounds(V: int, edges):
     return list(zip(edges[:-1], edges[1:]))
 
 
-def _register_pipelined(ctx: _e.Context, K, kp_d, des_d, Rt0, Rt1, bounds, events, ratio: float, nmax: int):
+def _register_pipelined(ctx: _e.Context, K, kp_d, des_d, Rt0, Rt1, bounds, events, ratio: float, nmax: int,
+                        after_chunk=None):
     """Chunks of device-resident views -> registered views.  Matching runs on a second context (own stream,
     workspace and descriptor pool) so that a chunk is prepared and matched — including the host reads of its match
     counts — while the previous chunk's views register on the main context; the registration loop is launched
@@ -379,6 +380,8 @@ def _register_pipelined(ctx: _e.Context, K, kp_d, des_d, Rt0, Rt1, bounds, event
             keep.append(matches)
             outs += native.collect()                      # previous chunk's views
             native.launch(matches)
+            if after_chunk is not None:
+                after_chunk(k)
         outs += native.collect()
         ctx.sync()
     finally:
@@ -435,6 +438,45 @@ def register_host(ctx: _e.Context, K, kps, dess, Rt0, Rt1, chunk: int = 25, rati
     outs, keep = _register_pipelined(ctx, K, kp_d, des_d, Rt0, Rt1, bounds, events, ratio, max(int(k.shape[0]) for k in kps))
     for o in outs:
         o["_keep"] = (kp_d, des_d, keep)      # uploaded on the copy stream: stay referenced until the caller drops the result
+    return outs
+
+
+def register_host_interleaved(ctx: _e.Context, K, kps, dess, Rt0, Rt1, chunk: int = 25, ratio: float = 0.70, ahead: int = 2):
+    """EXPERIMENTAL — written at the end of round 1 after the GPU budget was spent; NOT yet run on a GPU and not used by
+    bench.py or the tests.  register_host with the host->device copies of chunk k + `ahead` submitted only after chunk
+    k's registration has been launched, instead of all copies up front: the first chunk's work no longer waits for
+    the host to queue every copy of the sequence."""
+    import torch
+    V = len(kps)
+    dev = ctx.torch_device
+    as_t = lambda a: a if _e._is_torch(a) else torch.from_numpy(np.ascontiguousarray(a))
+    kps = [as_t(a) for a in kps]
+    dess = [as_t(a) for a in dess]
+    cs = getattr(ctx, "_copy_stream", None)
+    if cs is None:
+        cs = ctx._copy_stream = torch.cuda.Stream(device=dev)
+    bounds = _chunk_bounds(V, [min(8, chunk), chunk] + list(range(2 * chunk, V, chunk)))
+    kp_d, des_d, events = [None] * V, [None] * V, [None] * len(bounds)
+
+    def upload(k):
+        if k >= len(bounds) or events[k] is not None:
+            return
+        lo, hi = bounds[k]
+        with torch.cuda.stream(cs):
+            for i in range(lo, hi):
+                kp_d[i] = kps[i].to(dev, non_blocking=True)
+                des_d[i] = dess[i].to(dev, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(cs)
+        events[k] = ev
+
+    for k in range(min(ahead, len(bounds))):
+        upload(k)
+    # a chunk without pairs never reaches after_chunk: chunk 0 always has pairs for V >= 3, later chunks always do
+    outs, keep = _register_pipelined(ctx, K, kp_d, des_d, Rt0, Rt1, bounds, events, ratio, max(int(k.shape[0]) for k in kps),
+                                     after_chunk=lambda k: upload(k + ahead))
+    for o in outs:
+        o["_keep"] = (kp_d, des_d, keep)
     return outs
 
 
