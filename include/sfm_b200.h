@@ -237,6 +237,13 @@ int sfm_recover_pose(sfm_ctx* ctx, const double* E, const void* pts1, const void
  * winning iteration, winning model within it, models scored}. */
 int sfm_find_essential_mat(sfm_ctx* ctx, const void* pts1, const void* pts2, int dtype, int n, const double* K,
                            double prob, double threshold, int max_iters, double* E, uint8_t* mask, int32_t* info);
+/* EXPERIMENTAL (not yet run on a GPU; unused by bench.py and the default tests): sfm_find_essential_mat for many
+ * pairs in a few launches — isfm.py:68-87 calls it once per pair, and one pair's 1000 solver threads leave the GPU
+ * almost empty.  pts1/pts2[k]: (n[k],2) float32 DEVICE arrays; masks[k]: device or host, nullable; E: npairs x 9;
+ * info: npairs x 6 as above.  Pairs with n < 6 are not attempted (info[6k] = 0): use the single-pair call. */
+int sfm_find_essential_mat_batched(sfm_ctx* ctx, int npairs, const float* const* pts1, const float* const* pts2,
+                                   const int32_t* n, const double* K, double prob, double threshold, int max_iters,
+                                   double* E, uint8_t* const* masks, int32_t* info);
 /* Host utility (no GPU needed): Nister's five-point solver on ONE minimal sample — the code the hypothesis kernel
  * runs, compiled for the host.  q1, q2: 5 x 2 normalised coordinates; E: 90 doubles (<= 10 row-major 3x3 models,
  * unit Frobenius norm, ascending E00^2); n_models: how many. */

@@ -85,6 +85,7 @@ PROTOTYPES = {
     "sfm_ba_destroy": (None, [_vp]),
     "sfm_ba_set_totals": (_i, [_vp, _i64, _i64]),
     "sfm_debug_match_tc_dump": (_i, [_vp, _vp, _vp, _vp, _i64]),
+    "sfm_find_essential_mat_batched": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _d, _d, _i, _vp, _vp, _vp]),
     "sfm_five_point": (_i, [_vp, _vp, _vp, _vp]),
     "sfm_find_essential_mat": (_i, [_vp, _vp, _vp, _i, _i, _vp, _d, _d, _i, _vp, _vp, _vp]),
     "sfm_recover_pose": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _d, _vp, _vp, _vp, _vp, _vp]),

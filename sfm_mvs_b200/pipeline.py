@@ -527,22 +527,51 @@ def two_view_init(pts0, pts1, K, Rt0=None, ctx=None):
     return dict(E=E[:3], Rt0=Rt0, Rt1=Rt1, pts0=a, pts1=b, n_essential=n_e, n_pose=len(a))
 
 
-def pairwise_init(ctx: _e.Context, views, K, pairs=None, ratio: float = 0.70):
+def pairwise_init(ctx: _e.Context, views, K, pairs=None, ratio: float = 0.70, batched: bool = False):
     """isfm.py:68-87 — every earlier view j against the new view i: 2-NN + ratio matches (ALL pairs in one batched
     K1 launch), then per pair findEssentialMat(RANSAC, 0.999, 0.4) -> mask -> recoverPose -> mask, as the reference
     does it.  `views` are DeviceView; `pairs` defaults to all (j, i), j < i, in the reference's order (i outer).
-    -> list of dict(pair, n_match, n_essential, n_pose (what isfm.py prints), R, t, pts0, pts1)."""
+    -> list of dict(pair, n_match, n_essential, n_pose (what isfm.py prints), R, t, pts0, pts1).
+    batched=True (EXPERIMENTAL, not yet run on a GPU) estimates all essential matrices with
+    sfm_find_essential_mat_batched instead of one call per pair."""
     V = len(views)
     if pairs is None:
         pairs = [(j, i) for i in range(V) for j in range(i)]
     chain = RegistrationChain(ctx, K, ratio=ratio)
     matches = chain.match_pairs(views, pairs)
+    Kc = np.ascontiguousarray(K, np.float64)
+    pre = None
+    if batched and matches:
+        import torch
+        P = len(matches)
+        n = np.array([pm.n for pm in matches], np.int32)
+        a1 = np.array([pm.pts_q.data_ptr() for pm in matches], np.uint64)
+        a2 = np.array([pm.pts_t.data_ptr() for pm in matches], np.uint64)
+        with torch.cuda.stream(ctx.torch_stream()):
+            mask_all = torch.zeros((int(max(n.sum(), 1)),), dtype=torch.uint8, device=ctx.torch_device)
+        off = np.concatenate([[0], np.cumsum(n)]).astype(np.int64)
+        am = np.ascontiguousarray(mask_all.data_ptr() + off[:-1], np.uint64)
+        E = np.zeros((P, 3, 3))
+        info = np.zeros((P, 6), np.int32)
+        check(lib.sfm_find_essential_mat_batched(ctx._h, P, a1.ctypes.data, a2.ctypes.data, n.ctypes.data, _e._dptr(Kc),
+                                                 0.999, 0.4, 1000, _e._dptr(E), am.ctypes.data, _e._dptr(info)))
+        ctx.sync()
+        pre = (E, info, mask_all.cpu().numpy(), off)
     out = []
-    for (j, i), pm in zip(pairs, matches):
+    for idx, ((j, i), pm) in enumerate(zip(pairs, matches)):
         p0 = pm.pts_q[:pm.n].cpu().numpy()
         p1 = pm.pts_t[:pm.n].cpu().numpy()
         rec = dict(pair=(j, i), n_match=pm.n, n_essential=0, n_pose=0, R=None, t=None, pts0=p0[:0], pts1=p1[:0])
-        if pm.n >= 5:
+        if pre is not None and pm.n >= 6:
+            E, info, mask_all, off = pre
+            if info[idx, 0] == 1:
+                from .cv2_compat import recoverPose
+                m = mask_all[off[idx]:off[idx + 1]] == 1
+                a, b = p0[m], p1[m]
+                _, R, t, m2 = recoverPose(E[idx], a, b, Kc, ctx=ctx)
+                a, b = a[m2.ravel() > 0], b[m2.ravel() > 0]
+                rec.update(n_essential=int(m.sum()), n_pose=len(a), R=R, t=t, pts0=a, pts1=b)
+        elif pm.n >= 5:
             try:
                 init = two_view_init(p0, p1, K, ctx=ctx)
                 rec.update(n_essential=init["n_essential"], n_pose=init["n_pose"], R=init["Rt1"][:, :3].copy(),
