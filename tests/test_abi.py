@@ -85,3 +85,20 @@ def test_epnp_host_solver_recovers_noise_free_pose():
         worst = max(worst, np.abs(uv2 - uv).max())
         assert abs(np.linalg.det(Re) - 1) < 1e-9
     assert worst < 0.05, worst       # float32 pixel quantisation only
+
+
+def test_library_sass_is_blackwell_native():
+    """What proves a Blackwell-native build (profiling guide): the match kernel issues tcgen05.mma on CTA pairs
+    (SASS `UTCHMMA.2CTA`), reads accumulators out of TMEM (`LDTM`), stages operands with the bulk-copy engine
+    (`UBLKCP`), and nothing in the library falls back to the legacy tensor path (`HMMA`, i.e. mma.sync / wmma).
+    The library holds sm_100a code only."""
+    cuobjdump = "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    lst = subprocess.run([cuobjdump, "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"\.(sm_\w+)\.", lst))
+    assert archs == {"sm_100a"}, archs
+    full = subprocess.run([cuobjdump, "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    k1 = full[full.index("match_tc_kernel"):]
+    assert "UTCHMMA.2CTA" in k1 and "LDTM" in k1 and "UBLKCP" in k1 and "UTCBAR" in k1
+    assert not re.search(r"\bHMMA\b", full) and not re.search(r"\b[HQI]GMMA\b", full)
