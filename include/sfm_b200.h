@@ -278,9 +278,8 @@ int sfm_pnp_ransac(sfm_ctx* ctx, const float* X, const float* px, int n, const d
 /* Same call with the minimal solutions supplied by the caller: hyp_rt6 (max_iters,6) rvec|tvec per
  * RANSAC iteration (the poses a 5-point solver returned for the subsets of sfm_ransac_subsets),
  * hyp_valid (max_iters) or NULL.  Scoring, the stopping rule, the inlier list and the refinement
- * are identical to sfm_pnp_ransac.  This is how the parity tests feed OpenCV's own EPnP output
- * through the engine: OpenCV's EPnP takes its null-space basis from LAPACK, which no other
- * implementation reproduces bit for bit ("PnP parity"). */
+ * are identical to sfm_pnp_ransac.  The parity tests use it to separate the two halves of the call: OpenCV's own
+ * EPnP output fed through the engine's scoring / replay / refinement. */
 int sfm_pnp_ransac_hyp(sfm_ctx* ctx, const float* X, const float* px, int n, const double* K,
                        const double* hyp_rt6, const uint8_t* hyp_valid, int max_iters, float thr,
                        double confidence, double* rvec, double* tvec, int32_t* inliers,
@@ -292,6 +291,13 @@ int sfm_rodrigues_to_matrix(const double* rvec, double* R9);
 int sfm_rodrigues_to_vector(const double* R9, double* rvec);
 int sfm_epnp(const float* X, const float* px, int n, const double* K, double* R9, double* t3);
 int sfm_ransac_subsets(int n, int iters, int32_t* out /* iters x 5 */);
+
+/* The minimal solver of sfm_pnp_ransac run ON THE DEVICE for explicit subsets: cv2.solvePnP(X[s], px[s], K, 0,
+ * flags=SOLVEPNP_EPNP) for each row s of subsets (H,5) (host, H <= 100) -> R9t3 (H,12) host: R row-major | t, the
+ * solver's raw output before cv2.Rodrigues.  OpenCV's arithmetic operation for operation (csrc/pnp_epnp.cu):
+ * bit-identical to cv2 (tests/test_gpu_pnp.py).  X (n,3), px (n,2) float32, host or device. */
+int sfm_epnp_batch(sfm_ctx* ctx, const float* X, const float* px, int n, const double* K, const int32_t* subsets,
+                   int H, double* R9t3);
 
 /* ------------------------------------------------------------------ hot path 3b: bundle adjustment
  * Formulation: camera = (rvec 3, tvec 3), shared pinhole K, point = 3, residual =

@@ -81,6 +81,7 @@ PROTOTYPES = {
     "sfm_rodrigues_to_vector": (_i, [_vp, _vp]),
     "sfm_epnp": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),
     "sfm_ransac_subsets": (_i, [_i, _i, _vp]),
+    "sfm_epnp_batch": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _vp]),
     "sfm_ba_create": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _pp]),
     "sfm_ba_destroy": (None, [_vp]),
     "sfm_ba_set_totals": (_i, [_vp, _i64, _i64]),

@@ -9,8 +9,8 @@
 // depends on nothing but N and i (RNG seeded with 2^64-1), and a hypothesis' score does not depend
 // on earlier hypotheses.  So the whole loop is evaluated as a few stream-ordered kernels with no
 // host round trip in between:
-//   pnp_epnp_kernel      H minimal problems, one warp each (float64 EPnP, epnp.h): the RNG index
-//                        stream of the iteration, M^T M, warp-parallel Jacobi, three candidates
+//   pnp_epnp_kernel      H minimal problems, one CTA each (pnp_epnp.cu: EPnP in OpenCV's exact arithmetic, the
+//                        Jacobi decompositions as wavefronts over a warp), bit-identical hypotheses
 //   pnp_score_kernel     K4: H x N reprojection tests, poses staged in shared memory, one point
 //                        per thread held in registers, ballot/popc warp counts
 //   pnp_replay_kernel    the accept / RANSACUpdateNumIters recursion over the count vector; then
@@ -25,14 +25,11 @@
 #include "common.cuh"
 #include "chain_dev.cuh"
 #include "epnp.h"
+#include "pnp_dev.cuh"
 
 #include "ransac.cuh"
 
 namespace {
-
-struct PnpCam {
-  double fx, fy, cx, cy;
-};
 
 constexpr int PNP_HG = 4;          // hypotheses per CTA of the scoring kernel
 constexpr int PNP_MAX_H = 1024;
@@ -96,368 +93,6 @@ __global__ void __launch_bounds__(256) pnp_score_kernel(const float* __restrict_
   }
   __syncthreads();
   if (threadIdx.x < nh && s_count[threadIdx.x]) atomicAdd(&counts[h0 + threadIdx.x], s_count[threadIdx.x]);
-}
-
-// ------------------------------------------------------------------ minimal solver
-// One warp per hypothesis.
-//   lane 0      regenerates the RNG stream up to its iteration (the subset depends on N and the
-//               iteration only), loads the five correspondences, builds M^T M (epnp_build)
-//   all lanes   parallel-ordered two-sided Jacobi on the 12x12 M^T M in shared memory: each of the 11
-//               rounds of a sweep rotates 6 disjoint index pairs at once (72 column + 72 row + 72
-//               eigenvector element updates spread over the 32 lanes)
-//   lanes 0-2   the three beta initialisations + Gauss-Newton + absolute orientation, one per lane
-//   winner      writes the pose the scoring step must use: R' = Rodrigues(Rodrigues(R)), as OpenCV
-//               passes the model around as (rvec, tvec), and the (rvec, tvec) pair itself.
-struct EpnpShared {
-  double A[144];
-  double V[144];
-  double cs[12];        // (c, s) of the 6 rotations of a round
-  double alphas[20], pw[15], us[10], cws[12], L[60], rho[6], v4[48];
-  int pq[12];
-  // mixed-precision eigen-decomposition: float32 sweeps first (Af, Vf), float64 polish afterwards (T = scratch)
-  double T[144];
-  float Af[144], Vf[144], csf[12];
-};
-
-// Parallel-ordered two-sided Jacobi: a round rotates 6 disjoint index pairs at once.  With disjoint
-// pairs A' = J^T A J decomposes into 36 independent 2x2 blocks (row pair x column pair), each owned by
-// one lane, so a round is: 6 lanes form (c, s) -> one warp barrier -> every lane rewrites its blocks and
-// its share of the eigenvector rows -> one warp barrier.  Rotation parameters avoid two of the three
-// float64 divisions and one square root of the textbook form (t = sgn(a) b / (|a| + hypot(a, b)),
-// c = rsqrt(1 + t^2)); the sweep stops at off^2 <= 1e-28 diag^2 (off/diag ~ 1e-14: the null-space
-// basis inside the degenerate eigenvalue is arbitrary anyway, see DESIGN.md "PnP parity").
-// One sweep-loop of the parallel-ordered Jacobi in precision T on (A, V) in shared memory; V must hold an
-// orthonormal start (identity or a previous estimate).  Stops when off^2 <= tol * diag^2 or after max_sweeps.
-template <typename T>
-__device__ __forceinline__ int jacobi_sweeps(T* __restrict__ A, T* __restrict__ V, T* __restrict__ cs, int* __restrict__ pq,
-                                             int lane, int max_sweeps, T tol) {
-  int sweep = 0;
-  for (; sweep < max_sweeps; ++sweep) {
-    T off = 0, diag = 0;
-    for (int i = lane; i < 144; i += 32) {
-      const T a = A[i];
-      if (i / 12 == i % 12) diag += a * a; else off += a * a;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      off += __shfl_xor_sync(0xffffffffu, off, o);
-      diag += __shfl_xor_sync(0xffffffffu, diag, o);
-    }
-    if (off * (T)0.5 <= tol * diag || off == (T)0) break;
-    for (int round = 0; round < 11; ++round) {
-      if (lane < 6) {
-        int p = round + lane, q = round - lane + 11;          // (round +- lane) mod 11 without a division
-        p -= (p >= 11) ? 11 : 0;
-        q -= (q >= 11) ? 11 : 0;
-        if (lane == 0) { p = 11; q = round; }
-        if (p > q) { int t = p; p = q; q = t; }
-        const T apq = A[p * 12 + q], app = A[p * 12 + p], aqq = A[q * 12 + q];
-        T c = 1, s = 0;
-        if (sizeof(T) == 8) {
-          if (fabs((double)apq) > 1e-150) {
-            // t = apq / (al + sgn(al) hypot(al, apq)) with one reciprocal square root (hypot = s2 rsqrt(s2)) and a
-            // Newton reciprocal seeded in float32 — no float64 division or square root on this dependent chain;
-            // (c, s) = (rsqrt(1 + t^2), t c) is orthogonal to working precision whatever the error of t.
-            const double al = 0.5 * ((double)aqq - (double)app), bq = (double)apq;
-            const double s2 = al * al + bq * bq;
-            const double r = s2 * rsqrt(s2);
-            const double den = al + (al >= 0.0 ? r : -r);
-            double id = (double)(1.0f / (float)den);
-            id = id * (2.0 - den * id);
-            id = id * (2.0 - den * id);
-            const double t = (fabs(den) > 1e-30 && fabs(den) < 1e30) ? bq * id : bq / den;
-            const double cc = rsqrt(t * t + 1.0);
-            c = (T)cc;
-            s = (T)(t * cc);
-          }
-        } else {
-          const float bq = (float)apq;
-          if (fabsf(bq) > 1e-30f) {
-            const float al = 0.5f * ((float)aqq - (float)app);
-            const float s2 = al * al + bq * bq;
-            const float r = s2 * rsqrtf(s2);
-            const float t = __fdividef(bq, al + (al >= 0.f ? r : -r));
-            const float cc = rsqrtf(t * t + 1.f);
-            c = (T)cc;
-            s = (T)(t * cc);
-          }
-        }
-        cs[2 * lane] = c; cs[2 * lane + 1] = s;
-        pq[2 * lane] = p; pq[2 * lane + 1] = q;
-      }
-      __syncwarp();
-      // 36 blocks: rows (p1,q1) of pair kp, columns (p2,q2) of pair kq; 72 eigenvector-row items.  ALL loads of a
-      // lane's items are issued before any store (the items are disjoint, but the compiler cannot know that and
-      // would serialise load -> store -> load chains of ~30 cycles each)
-      int bi[2][4];
-      T bc[2][4], bv[2][4];
-#pragma unroll
-      for (int n = 0; n < 2; ++n) {
-        const int b = min(lane + 32 * n, 35);
-        const int kp = b / 6, kq = b - 6 * kp;
-        const int p1 = pq[2 * kp], q1 = pq[2 * kp + 1], p2 = pq[2 * kq], q2 = pq[2 * kq + 1];
-        bi[n][0] = p1 * 12 + p2; bi[n][1] = p1 * 12 + q2; bi[n][2] = q1 * 12 + p2; bi[n][3] = q1 * 12 + q2;
-        bc[n][0] = cs[2 * kp]; bc[n][1] = cs[2 * kp + 1]; bc[n][2] = cs[2 * kq]; bc[n][3] = cs[2 * kq + 1];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) bv[n][e] = A[bi[n][e]];
-      }
-      int vi[3][2];
-      T vc[3][2], vv[3][2];
-#pragma unroll
-      for (int n = 0; n < 3; ++n) {
-        const int it = min(lane + 32 * n, 71);
-        const int k = it / 12, j = it - 12 * k;
-        vi[n][0] = pq[2 * k] * 12 + j; vi[n][1] = pq[2 * k + 1] * 12 + j;
-        vc[n][0] = cs[2 * k]; vc[n][1] = cs[2 * k + 1];
-        vv[n][0] = V[vi[n][0]]; vv[n][1] = V[vi[n][1]];
-      }
-#pragma unroll
-      for (int n = 0; n < 2; ++n) {
-        if (lane + 32 * n < 36) {
-          const T c1 = bc[n][0], s1 = bc[n][1], c2 = bc[n][2], s2 = bc[n][3];
-          const T a = bv[n][0], bb = bv[n][1], cc = bv[n][2], d = bv[n][3];
-          // rows: J1^T from the left
-          const T ra = c1 * a - s1 * cc, rb = c1 * bb - s1 * d, rc = s1 * a + c1 * cc, rd = s1 * bb + c1 * d;
-          // columns: J2 from the right
-          A[bi[n][0]] = c2 * ra - s2 * rb;
-          A[bi[n][1]] = s2 * ra + c2 * rb;
-          A[bi[n][2]] = c2 * rc - s2 * rd;
-          A[bi[n][3]] = s2 * rc + c2 * rd;
-        }
-      }
-#pragma unroll
-      for (int n = 0; n < 3; ++n) {                  // eigenvector rows p,q of every rotation
-        if (lane + 32 * n < 72) {
-          const T c = vc[n][0], s = vc[n][1];
-          V[vi[n][0]] = c * vv[n][0] - s * vv[n][1];
-          V[vi[n][1]] = s * vv[n][0] + c * vv[n][1];
-        }
-      }
-      __syncwarp();
-    }
-  }
-  return sweep;
-}
-
-// Parallel-ordered two-sided Jacobi: a round rotates 6 disjoint index pairs at once.  With disjoint
-// pairs A' = J^T A J decomposes into 36 independent 2x2 blocks (row pair x column pair), each owned by
-// one lane, so a round is: 6 lanes form (c, s) -> one warp barrier -> every lane rewrites its blocks and
-// its share of the eigenvector rows -> one warp barrier.  The sweep stops at off^2 <= 1e-28 diag^2
-// (off/diag ~ 1e-14: the null-space basis inside the degenerate eigenvalue is arbitrary anyway, see
-// DESIGN.md "PnP parity").
-// Mixed precision: a round is a chain of dependent latencies, and most of the ~10 sweeps only bring the matrix
-// NEAR diagonal form.  So the first sweeps run in float32 on a copy (cheaper MUFU parameters, 4-cycle FMAs), the
-// float32 eigenvector estimate is re-orthonormalised in float64 (one Newton-Schulz step: 1e-7 -> 1e-14), the
-// ORIGINAL float64 matrix is rotated into that basis (A' = V A V^T, off-diagonal now ~1e-6) and float64 sweeps
-// finish from there (quadratic convergence: two of them).  The result is a float64 decomposition of the float64
-// matrix; float32 only chose the starting basis.
-__device__ __forceinline__ int warp_jacobi12(EpnpShared& sh, int lane) {
-  for (int i = lane; i < 144; i += 32) {
-    sh.Af[i] = (float)sh.A[i];
-    sh.Vf[i] = (i / 12 == i % 12) ? 1.f : 0.f;
-  }
-  __syncwarp();
-  const int nf = jacobi_sweeps<float>(sh.Af, sh.Vf, sh.csf, sh.pq, lane, 6, 1e-11f);
-  // V <- (1.5 I - 0.5 V V^T) V     (rows of V are the eigenvector estimates)
-  for (int e = lane; e < 144; e += 32) {
-    const int i = e / 12, j = e - 12 * i;
-    double g = 0.0;
-#pragma unroll
-    for (int k = 0; k < 12; ++k) g += (double)sh.Vf[i * 12 + k] * (double)sh.Vf[j * 12 + k];
-    sh.T[e] = ((i == j) ? 1.5 : 0.0) - 0.5 * g;
-  }
-  __syncwarp();
-  for (int e = lane; e < 144; e += 32) {
-    const int i = e / 12, j = e - 12 * i;
-    double v = 0.0;
-#pragma unroll
-    for (int k = 0; k < 12; ++k) v += sh.T[i * 12 + k] * (double)sh.Vf[k * 12 + j];
-    sh.V[e] = v;
-  }
-  __syncwarp();
-  // A' = V A V^T
-  for (int e = lane; e < 144; e += 32) {
-    const int i = e / 12, k = e - 12 * i;
-    double v = 0.0;
-#pragma unroll
-    for (int m = 0; m < 12; ++m) v += sh.V[i * 12 + m] * sh.A[m * 12 + k];
-    sh.T[e] = v;
-  }
-  __syncwarp();
-  for (int e = lane; e < 144; e += 32) {
-    const int i = e / 12, j = e - 12 * i;
-    double v = 0.0;
-#pragma unroll
-    for (int k = 0; k < 12; ++k) v += sh.T[i * 12 + k] * sh.V[j * 12 + k];
-    sh.A[e] = v;          // every lane read A only through T (previous phase): safe to overwrite after the barrier above
-  }
-  __syncwarp();
-  // symmetrise (A' is symmetric up to rounding; the sweeps assume it)
-  for (int e = lane; e < 144; e += 32) {
-    const int i = e / 12, j = e - 12 * i;
-    if (i < j) { const double m = 0.5 * (sh.A[i * 12 + j] + sh.A[j * 12 + i]); sh.T[e] = m; }
-  }
-  __syncwarp();
-  for (int e = lane; e < 144; e += 32) {
-    const int i = e / 12, j = e - 12 * i;
-    if (i < j) { sh.A[i * 12 + j] = sh.T[e]; sh.A[j * 12 + i] = sh.T[e]; }
-  }
-  __syncwarp();
-  const int nd = jacobi_sweeps<double>(sh.A, sh.V, sh.cs, sh.pq, lane, 40, 1e-28);
-  return nf * 100 + nd;       // diagnostics: sweeps per precision
-}
-
-// The RNG index stream depends only on N: for the default 100 iterations the host draws it (a few
-// microseconds) and passes it by value in the kernel parameter block — no copy, no extra launch.
-struct PnpSubsets {
-  int count;            // iterations covered by idx (0: draw in the kernel)
-  int idx[500];
-};
-
-__global__ void __launch_bounds__(32) pnp_epnp_kernel(const float* __restrict__ X, const float* __restrict__ px, int n,
-                                                      int H, PnpCam cam, const __grid_constant__ PnpSubsets subs,
-                                                      double* __restrict__ poses, double* __restrict__ rt6,
-                                                      unsigned char* __restrict__ valid, long long* __restrict__ dbg,
-                                                      const int* __restrict__ n_dev = nullptr,
-                                                      const int* __restrict__ subs_dev = nullptr) {
-  __shared__ EpnpShared sh;
-  const int h = blockIdx.x, lane = threadIdx.x;
-  if (h >= H) return;
-  if (n_dev) {
-    n = *n_dev;
-    if (n < 6) {                             // no minimal problem to solve: every hypothesis invalid -> ok = 0 downstream
-      if (lane == 0) valid[h] = 0;
-      return;
-    }
-  }
-  auto tick = [&](int k) { if (dbg && h == 0 && lane == 0) dbg[k] = clock64(); };
-  tick(0);
-  const hm::EpnpCam ec = {cam.fx, cam.fy, cam.cx, cam.cy};
-  if (lane == 0) {
-    int sub[5] = {0, 1, 2, 3, 4};
-    if (subs_dev) {
-      for (int k = 0; k < 5; ++k) sub[k] = subs_dev[5 * h + k];
-    } else if (n > 5 && h < subs.count) {
-      for (int k = 0; k < 5; ++k) sub[k] = subs.idx[5 * h + k];
-    } else if (n > 5) {                            // the subset iteration h of OpenCV's RANSAC draws
-      unsigned long long state = 0xFFFFFFFFFFFFFFFFull;
-      for (int it = 0; it <= h; ++it)
-        for (int i = 0; i < 5; ++i)
-          for (;;) {
-            state = (state & 0xFFFFFFFFull) * 4164903690ull + (state >> 32);
-            int j = (int)((unsigned int)state % (unsigned int)n);
-            bool dup = false;
-            for (int k = 0; k < i; ++k) dup |= (sub[k] == j);
-            if (!dup) { sub[i] = j; break; }
-          }
-    }
-    for (int k = 0; k < 5; ++k) {
-      int j = sub[k];
-      sh.pw[3 * k] = (double)X[3 * (size_t)j]; sh.pw[3 * k + 1] = (double)X[3 * (size_t)j + 1]; sh.pw[3 * k + 2] = (double)X[3 * (size_t)j + 2];
-      hm::epnp_roundtrip_pixel(px[2 * (size_t)j], px[2 * (size_t)j + 1], ec, sh.us + 2 * k);
-    }
-    hm::epnp_control_alphas(sh.pw, 5, sh.alphas, reinterpret_cast<double(*)[3]>(sh.cws), 4);
-  }
-  __syncwarp();
-  tick(1);
-  // M (10 x 12, two rows per correspondence) into sh.V, then M^T M (144 entries) spread over the lanes
-  for (int e = lane; e < 120; e += 32) {
-    const int rw = e / 12, col = e - 12 * rw, i = rw >> 1, jcp = col / 3, comp = col - 3 * jcp;
-    const double a = sh.alphas[4 * i + jcp];
-    double v;
-    if ((rw & 1) == 0) v = (comp == 0) ? a * ec.fu : ((comp == 1) ? 0.0 : a * (ec.uc - sh.us[2 * i]));
-    else v = (comp == 0) ? 0.0 : ((comp == 1) ? a * ec.fv : a * (ec.vc - sh.us[2 * i + 1]));
-    sh.V[e] = v;
-  }
-  __syncwarp();
-  for (int e = lane; e < 144; e += 32) {
-    const int rr = e / 12, cc = e - 12 * rr;
-    double acc = 0.0;
-#pragma unroll
-    for (int rw = 0; rw < 10; ++rw) acc += sh.V[12 * rw + rr] * sh.V[12 * rw + cc];
-    sh.A[e] = acc;
-  }
-  __syncwarp();
-  tick(2);
-  const int sweeps = warp_jacobi12(sh, lane);
-  tick(3);
-  if (dbg && h == 0 && lane == 0) { dbg[7] = sweeps; dbg[8] = 0; dbg[9] = 0; }
-  // the four eigenvectors of the smallest eigenvalues, smallest first, largest component positive: lane e < 12
-  // ranks its eigenvalue among the twelve (ties by index, like a stable selection) and, if it is one of the
-  // four smallest, copies its eigenvector row
-  if (lane < 12) {
-    const double we = sh.A[13 * lane];
-    int rank = 0;
-#pragma unroll
-    for (int i = 0; i < 12; ++i) {
-      const double wi = sh.A[13 * i];
-      rank += (wi < we || (wi == we && i < lane)) ? 1 : 0;
-    }
-    if (rank < 4) {
-      double row[12];
-      double big = 0.0, bigv = 0.0;
-#pragma unroll
-      for (int k = 0; k < 12; ++k) {
-        row[k] = sh.V[lane * 12 + k];
-        if (fabs(row[k]) > big) { big = fabs(row[k]); bigv = row[k]; }
-      }
-      const double sgn = bigv < 0.0 ? -1.0 : 1.0;
-#pragma unroll
-      for (int k = 0; k < 12; ++k) sh.v4[12 * rank + k] = sgn * row[k];
-    }
-  }
-  __syncwarp();
-  // L (6 x 10) and rho (6): one entry per lane-step.  Row i <-> control-point pair (a,b); column <-> (p,q) of v_p.v_q
-  for (int e = lane; e < 66; e += 32) {
-    const int i = (e < 60) ? e / 10 : e - 60;
-    const int pa = (i < 3) ? 0 : ((i < 5) ? 1 : 2);
-    const int pb = (i < 3) ? i + 1 : ((i < 5) ? i - 1 : 3);
-    if (e < 60) {
-      const int col = e - 10 * i;
-      // columns: 0 (0,0) 1 (0,1) 2 (1,1) 3 (0,2) 4 (1,2) 5 (2,2) 6 (0,3) 7 (1,3) 8 (2,3) 9 (3,3)
-      const int q = (col < 1) ? 0 : ((col < 3) ? 1 : ((col < 6) ? 2 : 3));
-      const int p = col - ((q * (q + 1)) >> 1);
-      const double* vp = sh.v4 + 12 * p;
-      const double* vq = sh.v4 + 12 * q;
-      double d = 0.0;
-#pragma unroll
-      for (int k = 0; k < 3; ++k) d += (vp[3 * pa + k] - vp[3 * pb + k]) * (vq[3 * pa + k] - vq[3 * pb + k]);
-      sh.L[e] = (p == q) ? d : 2.0 * d;
-    } else {
-      double d = 0.0;
-#pragma unroll
-      for (int k = 0; k < 3; ++k) { const double x = sh.cws[3 * pa + k] - sh.cws[3 * pb + k]; d += x * x; }
-      sh.rho[i] = d;
-    }
-  }
-  __syncwarp();
-  tick(4);
-  double R[9], t[3], err = 0.0;
-  if (lane < 3) {
-    const double* v[4] = {sh.v4, sh.v4 + 12, sh.v4 + 24, sh.v4 + 36};
-    err = hm::epnp_candidate(lane, sh.L, sh.rho, v, sh.alphas, sh.pw, sh.us, 5, ec, R, t);
-  }
-  double errs[3];
-  errs[0] = __shfl_sync(0xffffffffu, err, 0);
-  errs[1] = __shfl_sync(0xffffffffu, err, 1);
-  errs[2] = __shfl_sync(0xffffffffu, err, 2);
-  const int N = hm::epnp_pick(errs);
-  tick(5);
-  if (lane == N) {
-    double rv[3];
-    hm::rotation_log(R, rv);        // R = U V^T of the absolute orientation: orthonormal already, no second SVD
-    double* P = poses + 12 * (size_t)h;
-    double Rr[9];
-    hm::rodrigues_to_matrix(rv, Rr);
-    bool ok = true;
-    for (int k = 0; k < 9; ++k) { P[k] = Rr[k]; ok &= isfinite(Rr[k]); }
-    for (int k = 0; k < 3; ++k) { P[9 + k] = t[k]; ok &= isfinite(t[k]); }
-    rt6[6 * h] = rv[0]; rt6[6 * h + 1] = rv[1]; rt6[6 * h + 2] = rv[2];
-    rt6[6 * h + 3] = t[0]; rt6[6 * h + 4] = t[1]; rt6[6 * h + 5] = t[2];
-    valid[h] = ok ? 1 : 0;
-  }
-  __syncwarp();
-  tick(6);
 }
 
 // ------------------------------------------------------------------ replay of the stopping rule
@@ -1088,15 +723,14 @@ static int pnp_ransac_impl(sfm_ctx* ctx, const float* X, const float* px, int n,
     subs.count = (n > 5 && H <= 100) ? H : 0;
     if (subs.count) ransac_subsets(n, subs.count, subs.idx);
     long long* dbg = nullptr;
-    if (getenv("SFM_PNP_TIMELINE")) SFM_TRY(ws_alloc_t(ctx, 12, &dbg));
-    SFM_LAUNCH(ctx, SFM_K_PNP_EPNP, (pnp_epnp_kernel<<<H, 32, 0, ctx->stream>>>(dX, dpx, n, H, cam, subs, dposes, drt6, dvalid, dbg)));
+    if (getenv("SFM_PNP_TIMELINE")) SFM_TRY(ws_alloc_t(ctx, 32, &dbg));
+    SFM_TRY(sfm_pnp_epnp_launch(ctx, dX, dpx, n, H, cam, subs, dposes, drt6, dvalid, dbg, nullptr, nullptr));
     if (dbg) {   // diagnostics: phase boundaries of hypothesis 0 in SM clocks
       long long hs[12];
       SFM_CUDA(cudaMemcpyAsync(hs, dbg, sizeof(hs), cudaMemcpyDeviceToHost, ctx->stream));
       SFM_CUDA(cudaStreamSynchronize(ctx->stream));
-      fprintf(stderr, "[jacobi round] f32 params %lld update %lld | f64 params %lld update %lld\n", hs[8] / 100000, hs[8] % 100000, hs[9] / 100000, hs[9] % 100000);
-      fprintf(stderr, "[epnp cycles] subset+alphas %lld | MtM %lld | jacobi %lld (%lld float32 + %lld float64 sweeps) | L,rho %lld | candidates %lld | rodrigues+store %lld\n",
-              hs[1] - hs[0], hs[2] - hs[1], hs[3] - hs[2], hs[7] / 100, hs[7] % 100, hs[4] - hs[3], hs[5] - hs[4], hs[6] - hs[5]);
+      fprintf(stderr, "[epnp cycles] subset+control points+alphas %lld | MtM %lld | 12x12 jacobi+sort %lld (%lld sweeps) | L,rho %lld | candidates %lld | pick+store %lld\n",
+              hs[1] - hs[0], hs[2] - hs[1], hs[3] - hs[2], hs[10], hs[4] - hs[3], hs[5] - hs[4], hs[6] - hs[5]);
     }
   }
   SFM_CUDA(cudaMemsetAsync(dcounts, 0, sizeof(int32_t) * H, ctx->stream));
@@ -1194,8 +828,7 @@ int sfm_pnp_ransac_dev(sfm_ctx* ctx, const float* X, const float* px, int n_cap,
   subs.count = 0;
   SFM_CUDA(cudaMemsetAsync(dcounts, 0, sizeof(int32_t) * H, ctx->stream));
   if (!subs_dev) SFM_LAUNCH(ctx, SFM_K_MISC, (pnp_subsets_kernel<<<1, 1024, 0, ctx->stream>>>(n_dev, H, raw, dsubs)));
-  SFM_LAUNCH(ctx, SFM_K_PNP_EPNP, (pnp_epnp_kernel<<<H, 32, 0, ctx->stream>>>(X, px, n_cap, H, cam, subs, dposes, drt6, dvalid,
-                                                                            nullptr, n_dev, subs_dev ? subs_dev : dsubs)));
+  SFM_TRY(sfm_pnp_epnp_launch(ctx, X, px, n_cap, H, cam, subs, dposes, drt6, dvalid, nullptr, n_dev, subs_dev ? subs_dev : dsubs));
   dim3 grid(div_up(n_cap, 256), div_up(H, PNP_HG));
   SFM_LAUNCH(ctx, SFM_K_PNP_SCORE, (pnp_score_kernel<<<grid, 256, 0, ctx->stream>>>(X, px, n_cap, dposes, dvalid, H, cam, thr2, dcounts,
                                                                                    nullptr, n_dev)));

@@ -1,0 +1,375 @@
+// pnp_epnp.cu — the minimal solver of cv2.solvePnPRansac (reference call site sfm.py:67, test.py:319): EPnP on the
+// five correspondences of each RANSAC iteration, all iterations at once, bit-identical to OpenCV's solver.
+//
+// THIS FILE IS COMPILED WITH -fmad=false.  OpenCV's solver is plain IEEE double arithmetic in a fixed order
+// (SSE3 baseline build, no fused multiply-add), and every decomposition in it is small enough to run OpenCV's own
+// one-sided Jacobi instead of LAPACK (epnp.h, hostmath.h).  For 5 points the 12x12 M^T M has a 2-dimensional null
+// space; which basis of it the Jacobi sweeps end in is decided by rounding, and the three beta initialisations
+// depend on that basis — so the hypothesis equals OpenCV's only if every operation up to there produces the same
+// bits.  Device double add / mul / div / sqrt are IEEE round-to-nearest: with contraction off, the same sequence
+// gives the same bits.
+//
+// Latency, not throughput, is what matters (100 hypotheses on 148 SMs, on the pose-critical path of the
+// registration loop), and OpenCV's Jacobi is a sequential loop over the pairs (i, j).  It is NOT sequential in
+// its data: rotation (i, j) touches rows i and j only, so it can run as soon as (i, j-1) and (i-1, j) are done.
+// wave_jacobi runs that wavefront: pair (i, j) of sweep s executes at step s n + i + j - 1 — up to six pairs per
+// step for n = 12, a sweep every n steps with consecutive sweeps overlapping — each pair on a group of four lanes
+// that redundantly accumulate the three ordered sums (<Ai, Aj>, |Ai|^2, |Aj|^2 in column order, as OpenCV's loops
+// do) and rotate three columns each.  66 dependent rotations per sweep become 12 dependent steps.
+//   CTA = one hypothesis, 3 warps: warp 0 does the control points, alphas, M^T M and the 12x12 decomposition,
+//   then each warp takes one beta initialisation (SVD least squares on a 6 x {4, 3, 5} system by the same
+//   wavefront, Gauss-Newton, absolute orientation), and thread 0 picks the pose with the smallest error.
+#include <float.h>
+#include <math.h>
+
+#include "common.cuh"
+#include "epnp.h"
+#include "pnp_dev.cuh"
+#include "ransac.cuh"
+
+namespace {
+
+// One-sided Jacobi SVD (OpenCV JacobiSVDImpl_<double>) of n rows of length M (At, row stride M) by one warp, as a
+// wavefront over the pairs.  sq holds the squares of At's entries (OpenCV's running |Ai|^2 is the ordered sum of the
+// squares formed at the row's last rotation, or of the initial entries).  Vt (n x n, identity on entry) may be null.
+// Returns the number of sweeps that rotated something.  On return the rows are orthogonal, NOT yet sorted/normalised.
+template <int M>
+__device__ __forceinline__ int wave_jacobi(double* __restrict__ At, double* __restrict__ sq, double* __restrict__ Vt,
+                                           const int n, const int lane) {
+  static_assert(M % 2 == 0, "rows are read as double2");
+  constexpr int CPL = (M + 3) / 4;      // columns of a row pair each of the 4 lanes of a group rotates
+  const int grp = lane >> 2, sub = lane & 3;
+  const int max_iter = M > 30 ? M : 30;
+  const double eps = DBL_EPSILON * 10;
+  bool chg_prev = true, chg_cur = false;
+  int sweeps = 0;
+  for (int sigma = 0;; ++sigma) {
+    for (int phi = 0; phi < n; ++phi) {
+      // pairs of this step: sweep sigma, i + j = phi + 1, and the tail of sweep sigma - 1, i + j = phi + 1 + n
+      const int s1 = phi + 1, s2 = s1 + n;
+      const int lo1 = max(0, s1 - (n - 1)), hi1 = (s1 - 1) >> 1;
+      const int cnt1 = (sigma < max_iter) ? max(0, hi1 - lo1 + 1) : 0;
+      const int lo2 = s2 - (n - 1), hi2 = (s2 - 1) >> 1;
+      const int cnt2 = (sigma >= 1 && s2 <= 2 * n - 3) ? max(0, hi2 - lo2 + 1) : 0;
+      int i = -1, j = -1;
+      bool first = false;
+      if (grp < cnt1) { i = lo1 + grp; j = s1 - i; first = true; }
+      else if (grp - cnt1 < cnt2) { i = lo2 + grp - cnt1; j = s2 - i; }
+      bool rot = false;
+      double c = 1.0, s = 0.0;
+      double mi[CPL], mj[CPL], vi[3], vj[3];
+      if (i >= 0) {
+        const double2* Ai = reinterpret_cast<const double2*>(At + i * M);
+        const double2* Aj = reinterpret_cast<const double2*>(At + j * M);
+        const double2* Qi = reinterpret_cast<const double2*>(sq + i * M);
+        const double2* Qj = reinterpret_cast<const double2*>(sq + j * M);
+        double p = 0.0, a = 0.0, b = 0.0;
+#pragma unroll
+        for (int k = 0; k < M / 2; ++k) {
+          const double2 x = Ai[k], y = Aj[k], qa = Qi[k], qb = Qj[k];
+          p += x.x * y.x; p += x.y * y.y;
+          a += qa.x; a += qa.y;
+          b += qb.x; b += qb.y;
+        }
+#pragma unroll
+        for (int q = 0; q < CPL; ++q) {
+          const int k = sub + 4 * q;
+          mi[q] = (k < M) ? At[i * M + k] : 0.0;
+          mj[q] = (k < M) ? At[j * M + k] : 0.0;
+        }
+        if (Vt) {
+#pragma unroll
+          for (int q = 0; q < 3; ++q) {
+            const int k = sub + 4 * q;
+            vi[q] = (k < n) ? Vt[i * n + k] : 0.0;
+            vj[q] = (k < n) ? Vt[j * n + k] : 0.0;
+          }
+        }
+        rot = !(fabs(p) <= eps * sqrt(a * b));
+        if (rot) {
+          p *= 2;
+          hm::cv_jacobi_cs(p, a - b, c, s);
+        }
+      }
+      __syncwarp();                      // every read of this step precedes every write
+      if (rot) {
+#pragma unroll
+        for (int q = 0; q < CPL; ++q) {
+          const int k = sub + 4 * q;
+          if (k < M) {
+            const double t0 = c * mi[q] + s * mj[q];
+            const double t1 = -s * mi[q] + c * mj[q];
+            At[i * M + k] = t0; At[j * M + k] = t1;
+            sq[i * M + k] = t0 * t0; sq[j * M + k] = t1 * t1;
+          }
+        }
+        if (Vt) {
+#pragma unroll
+          for (int q = 0; q < 3; ++q) {
+            const int k = sub + 4 * q;
+            if (k < n) {
+              const double t0 = c * vi[q] + s * vj[q];
+              const double t1 = -s * vi[q] + c * vj[q];
+              Vt[i * n + k] = t0; Vt[j * n + k] = t1;
+            }
+          }
+        }
+      }
+      __syncwarp();                      // ... and every write precedes the next step's reads
+      const unsigned any = __ballot_sync(0xffffffffu, rot);
+      const unsigned any_first = __ballot_sync(0xffffffffu, rot && first);
+      chg_cur |= any_first != 0u;
+      chg_prev |= (any & ~any_first) != 0u;
+      // OpenCV's loop ends after the first sweep that rotates nothing (or after max_iter sweeps).  Pairs of the
+      // next sweep that already ran saw the same rows and the same sums as in that sweep, so they skipped too.
+      if (n >= 4) {
+        if (sigma >= 1 && phi == n - 4) {          // sweep sigma - 1 is complete
+          if (chg_prev) ++sweeps;
+          if (!chg_prev || sigma >= max_iter) return sweeps;
+        }
+      } else if (phi == n - 1) {                   // n < 4: no overlap, sweep sigma is complete
+        if (chg_cur) ++sweeps;
+        if (!chg_cur || sigma + 1 >= max_iter) return sweeps;
+      }
+    }
+    chg_prev = chg_cur;
+    chg_cur = false;
+  }
+}
+
+// Singular values (descending), OpenCV's selection sort on them as a row permutation: W[pos], row ord[pos].
+template <int M>
+__device__ __forceinline__ void wave_sort(const double* __restrict__ sq, int n, double* __restrict__ W, int* __restrict__ ord,
+                                          int lane) {
+  __syncwarp();
+  if (lane < n) {
+    double sd = 0.0;
+#pragma unroll
+    for (int k = 0; k < M; ++k) sd += sq[lane * M + k];
+    W[lane] = sqrt(sd);
+    ord[lane] = lane;
+  }
+  __syncwarp();
+  if (lane == 0) {
+    for (int i = 0; i < n - 1; ++i) {
+      int j = i;
+      for (int k = i + 1; k < n; ++k)
+        if (W[j] < W[k]) j = k;
+      if (i != j) {
+        const double tw = W[i]; W[i] = W[j]; W[j] = tw;
+        const int to = ord[i]; ord[i] = ord[j]; ord[j] = to;
+      }
+    }
+  }
+  __syncwarp();
+}
+
+struct CandShared {        // one beta initialisation (one warp)
+  double At[30], sq[30], Vt[25], W[5];
+  double ut[30], vts[25];  // sorted, normalised
+  double pcs[15];
+  double R[9], t[3], err;
+  int ord[5];
+};
+
+struct EpnpShared {        // At / sq (and CandShared, a multiple of 16 bytes) first: their rows are read as double2
+  double At[144], sq[144];
+  CandShared cand[3];
+  double pw[15], us[10], alphas[20], cws[12];
+  double M[120], W[12];
+  double v4[48], L[60], rho[6];
+  int ord[12];
+};
+static_assert(sizeof(CandShared) % 16 == 0, "CandShared rows are read as double2");
+
+__global__ void __launch_bounds__(96) pnp_epnp_kernel(const float* __restrict__ X, const float* __restrict__ px, int n,
+                                                      int H, PnpCam cam, const __grid_constant__ PnpSubsets subs,
+                                                      double* __restrict__ poses, double* __restrict__ rt6,
+                                                      unsigned char* __restrict__ valid, long long* __restrict__ dbg,
+                                                      const int* __restrict__ n_dev, const int* __restrict__ subs_dev) {
+  __shared__ __align__(16) EpnpShared sh;
+  const int h = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (h >= H) return;
+  if (n_dev) {
+    n = *n_dev;
+    if (n < 6) {                             // no minimal problem to solve: every hypothesis invalid -> ok = 0 downstream
+      if (tid == 0) valid[h] = 0;
+      return;
+    }
+  }
+  auto tick = [&](int k) { if (dbg && h == 0 && tid == 0) dbg[k] = clock64(); };
+  tick(0);
+  const hm::EpnpCam ec = {cam.fx, cam.fy, cam.cx, cam.cy};
+  if (warp == 0) {
+    if (lane == 0) {
+      int sub[5] = {0, 1, 2, 3, 4};
+      if (subs_dev) {
+        for (int k = 0; k < 5; ++k) sub[k] = subs_dev[5 * h + k];
+      } else if (n > 5 && h < subs.count) {
+        for (int k = 0; k < 5; ++k) sub[k] = subs.idx[5 * h + k];
+      } else if (n > 5) {                            // the subset iteration h of OpenCV's RANSAC draws
+        unsigned long long state = 0xFFFFFFFFFFFFFFFFull;
+        for (int it = 0; it <= h; ++it)
+          for (int i = 0; i < 5; ++i)
+            for (;;) {
+              state = (state & 0xFFFFFFFFull) * 4164903690ull + (state >> 32);
+              int j = (int)((unsigned int)state % (unsigned int)n);
+              bool dup = false;
+              for (int k = 0; k < i; ++k) dup |= (sub[k] == j);
+              if (!dup) { sub[i] = j; break; }
+            }
+      }
+      for (int k = 0; k < 5; ++k) {
+        const int j = sub[k];
+        sh.pw[3 * k] = (double)X[3 * (size_t)j]; sh.pw[3 * k + 1] = (double)X[3 * (size_t)j + 1]; sh.pw[3 * k + 2] = (double)X[3 * (size_t)j + 2];
+        hm::epnp_roundtrip_pixel(px[2 * (size_t)j], px[2 * (size_t)j + 1], ec, sh.us + 2 * k);
+      }
+      hm::epnp_control_alphas(sh.pw, 5, sh.alphas, reinterpret_cast<double(*)[3]>(sh.cws));
+    }
+    __syncwarp();
+    tick(1);
+    // M (10 x 12), then the upper triangle of M^T M: every entry its own ordered sum over the rows of M
+    for (int e = lane; e < 120; e += 32) sh.M[e] = hm::epnp_M_entry(sh.alphas, sh.us, ec, e / 12, e % 12);
+    __syncwarp();
+    for (int e = lane; e < 78; e += 32) {
+      int r = 0, rem = e;
+      while (rem >= 12 - r) { rem -= 12 - r; ++r; }
+      const int c = r + rem;
+      double s0 = 0.0;
+#pragma unroll
+      for (int k = 0; k < 10; ++k) s0 += sh.M[12 * k + r] * sh.M[12 * k + c];
+      sh.At[12 * r + c] = s0; sh.At[12 * c + r] = s0;
+      const double q = s0 * s0;
+      sh.sq[12 * r + c] = q; sh.sq[12 * c + r] = q;
+    }
+    __syncwarp();
+    tick(2);
+    const int sweeps = wave_jacobi<12>(sh.At, sh.sq, nullptr, 12, lane);
+    wave_sort<12>(sh.sq, 12, sh.W, sh.ord, lane);
+    tick(3);
+    if (dbg && h == 0 && lane == 0) dbg[10] = sweeps;
+    // v[q] = left singular vector of the (q+1)-th smallest singular value: sorted row 11 - q, scaled by 1 / sigma
+    for (int e = lane; e < 48; e += 32) {
+      const int q = e / 12, k = e - 12 * q;
+      const double sd = sh.W[11 - q];
+      const double sc = sd > DBL_MIN ? 1 / sd : 0.;
+      sh.v4[e] = sh.At[12 * sh.ord[11 - q] + k] * sc;
+    }
+    __syncwarp();
+    const double* v[4] = {sh.v4, sh.v4 + 12, sh.v4 + 24, sh.v4 + 36};
+    for (int e = lane; e < 66; e += 32) {
+      if (e < 60) sh.L[e] = hm::epnp_L_entry(v, e / 10, e % 10);
+      else sh.rho[e - 60] = hm::epnp_rho_entry(reinterpret_cast<const double(*)[3]>(sh.cws), e - 60);
+    }
+  }
+  __syncthreads();
+  tick(4);
+  {
+    // warp = beta initialisation: least squares on nc columns of L by SVD (cv::solve DECOMP_SVD)
+    CandShared& cs = sh.cand[warp];
+    const int ap = warp, nc = hm::epnp_approx_cols(ap);
+    for (int e = lane; e < 6 * nc; e += 32) {
+      const int c = e / 6, i = e - 6 * c;
+      const double x = sh.L[10 * i + hm::epnp_approx_col(ap, c)];
+      cs.At[e] = x;
+      cs.sq[e] = x * x;
+    }
+    for (int e = lane; e < nc * nc; e += 32) cs.Vt[e] = (e / nc == e % nc) ? 1.0 : 0.0;
+    __syncwarp();
+    wave_jacobi<6>(cs.At, cs.sq, cs.Vt, nc, lane);
+    wave_sort<6>(cs.sq, nc, cs.W, cs.ord, lane);
+    for (int e = lane; e < 6 * nc; e += 32) {
+      const int r = e / 6, k = e - 6 * r;
+      const double sd = cs.W[r];
+      const double sc = sd > DBL_MIN ? 1 / sd : 0.;
+      cs.ut[e] = cs.At[6 * cs.ord[r] + k] * sc;
+    }
+    for (int e = lane; e < nc * nc; e += 32) cs.vts[e] = cs.Vt[nc * cs.ord[e / nc] + e % nc];
+    __syncwarp();
+    if (lane == 0) {
+      double b[5], betas[4] = {0, 0, 0, 0};
+      if (ap == 0) hm::cv_svd_backsubst<6, 4>(cs.W, cs.ut, cs.vts, sh.rho, b);
+      else if (ap == 1) hm::cv_svd_backsubst<6, 3>(cs.W, cs.ut, cs.vts, sh.rho, b);
+      else hm::cv_svd_backsubst<6, 5>(cs.W, cs.ut, cs.vts, sh.rho, b);
+      hm::epnp_betas_from_ls(ap, b, betas);
+      hm::epnp_gauss_newton(sh.L, sh.rho, betas);
+      const double* v[4] = {sh.v4, sh.v4 + 12, sh.v4 + 24, sh.v4 + 36};
+      cs.err = hm::epnp_pose_from_betas(v, betas, sh.alphas, sh.pw, sh.us, 5, ec, cs.pcs, cs.R, cs.t);
+    }
+  }
+  __syncthreads();
+  tick(5);
+  if (tid == 0) {
+    const double errs[3] = {sh.cand[0].err, sh.cand[1].err, sh.cand[2].err};
+    const int N = hm::epnp_pick(errs);
+    const double* R = sh.cand[N].R;
+    const double* t = sh.cand[N].t;
+    // OpenCV hands the model on as (rvec, tvec) = (Rodrigues(R), t) and scores with R' = Rodrigues(rvec).  R = U V^T is
+    // orthonormal to rounding already: the log map is taken directly (cv::Rodrigues' own SVD clean-up moves it by ~1e-16)
+    double rv[3], Rr[9];
+    hm::rotation_log(R, rv);
+    hm::rodrigues_to_matrix(rv, Rr);
+    double* P = poses + 12 * (size_t)h;
+    bool ok = true;
+    for (int k = 0; k < 9; ++k) { P[k] = Rr[k]; ok &= isfinite(Rr[k]); }
+    for (int k = 0; k < 3; ++k) { P[9 + k] = t[k]; ok &= isfinite(t[k]); }
+    rt6[6 * h] = rv[0]; rt6[6 * h + 1] = rv[1]; rt6[6 * h + 2] = rv[2];
+    rt6[6 * h + 3] = t[0]; rt6[6 * h + 4] = t[1]; rt6[6 * h + 5] = t[2];
+    valid[h] = ok ? 1 : 0;
+    if (dbg && h == 0) {                 // diagnostics: the raw solver output of hypothesis 0
+      double* d = reinterpret_cast<double*>(dbg + 16);
+      for (int k = 0; k < 9; ++k) d[k] = R[k];
+      for (int k = 0; k < 3; ++k) d[9 + k] = t[k];
+    }
+  }
+  tick(6);
+}
+
+}  // namespace
+
+int sfm_pnp_epnp_launch(sfm_ctx* ctx, const float* X, const float* px, int n, int H, const PnpCam& cam, const PnpSubsets& subs,
+                        double* poses, double* rt6, unsigned char* valid, long long* dbg, const int* n_dev,
+                        const int* subs_dev) {
+  SFM_LAUNCH(ctx, SFM_K_PNP_EPNP, (pnp_epnp_kernel<<<H, 96, 0, ctx->stream>>>(X, px, n, H, cam, subs, poses, rt6, valid, dbg,
+                                                                              n_dev, subs_dev)));
+  return SFM_OK;
+}
+
+// The raw solver output (R row-major, t) of the batched kernel for explicit 5-point subsets — the hook the parity
+// tests use to compare the DEVICE arithmetic with cv2.solvePnP(EPNP) bit for bit.  X (n,3), px (n,2) host or device;
+// subsets (H,5) host; R9t3 (H,12) host.
+extern "C" int sfm_epnp_batch(sfm_ctx* ctx, const float* X, const float* px, int n, const double* K, const int32_t* subsets,
+                              int H, double* R9t3) {
+  SFM_REQUIRE(ctx && X && px && K && subsets && R9t3, "sfm_epnp_batch: null argument");
+  SFM_REQUIRE(n >= 5 && H >= 1 && H <= 100, "sfm_epnp_batch: need n >= 5 and 1 <= H <= 100");
+  SFM_TRY(sfm_ws_begin(ctx));
+  const float *dX, *dpx;
+  SFM_TRY(dev_in(ctx, X, (size_t)3 * n, &dX));
+  SFM_TRY(dev_in(ctx, px, (size_t)2 * n, &dpx));
+  PnpSubsets subs;
+  subs.count = H;
+  for (int k = 0; k < 5 * H; ++k) {
+    SFM_REQUIRE(subsets[k] >= 0 && subsets[k] < n, "sfm_epnp_batch: subset index out of range");
+    subs.idx[k] = subsets[k];
+  }
+  const PnpCam cam = {K[0], K[4], K[2], K[5]};
+  double *dposes, *drt6, *hout;
+  unsigned char* dvalid;
+  long long* dbg;
+  SFM_TRY(ws_alloc_t(ctx, (size_t)12 * H, &dposes));
+  SFM_TRY(ws_alloc_t(ctx, (size_t)6 * H, &drt6));
+  SFM_TRY(ws_alloc_t(ctx, (size_t)H, &dvalid));
+  SFM_TRY(hs_alloc_t(ctx, (size_t)12, &hout));
+  // one launch per hypothesis slot 0 with the debug block carrying the raw (R, t): H is small in the tests
+  for (int h = 0; h < H; ++h) {
+    PnpSubsets one;
+    one.count = 1;
+    for (int k = 0; k < 5; ++k) one.idx[k] = subs.idx[5 * h + k];
+    SFM_TRY(ws_alloc_t(ctx, 32, &dbg));
+    SFM_TRY(sfm_pnp_epnp_launch(ctx, dX, dpx, n, 1, cam, one, dposes, drt6, dvalid, dbg, nullptr, nullptr));
+    SFM_CUDA(cudaMemcpyAsync(hout, dbg + 16, sizeof(double) * 12, cudaMemcpyDeviceToHost, ctx->stream));
+    SFM_CUDA(cudaStreamSynchronize(ctx->stream));
+    memcpy(R9t3 + 12 * (size_t)h, hout, sizeof(double) * 12);
+  }
+  return SFM_OK;
+}

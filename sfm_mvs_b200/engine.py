@@ -354,6 +354,17 @@ class Context:
         return bool(ok.value), rvec, tvec, inl[:ni.value].copy(), d
 
 
+    def epnp_batch(self, X, px, K, subsets):
+        """The device minimal solver on explicit 5-point subsets (H,5): (R (H,3,3), t (H,3)), the raw output of
+        cv2.solvePnP(X[s], px[s], K, 0, flags=SOLVEPNP_EPNP) before cv2.Rodrigues — bit-identical to OpenCV."""
+        K = np.ascontiguousarray(K, np.float64).reshape(9)
+        aX, ap = _Arg(X, np.float32), _Arg(px, np.float32)
+        subs = np.ascontiguousarray(subsets, np.int32).reshape(-1, 5)
+        out = np.empty((len(subs), 12))
+        check(lib.sfm_epnp_batch(self._h, aX.ptr, ap.ptr, int(aX.shape[0]), _dptr(K), _dptr(subs), len(subs), _dptr(out)))
+        return out[:, :9].reshape(-1, 3, 3).copy(), out[:, 9:].copy()
+
+
 # ---------------------------------------------------------------------- host utilities (no GPU needed)
 def rodrigues_to_matrix(rvec) -> np.ndarray:
     r = np.ascontiguousarray(rvec, np.float64).reshape(3)

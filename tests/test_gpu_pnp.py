@@ -69,12 +69,45 @@ def test_golden_pnp_inliers(engine, golden):
     ok, rvec, tvec, inl, _ = engine.pnp_ransac(X, p, g["K"], hypotheses=hyp, hyp_valid=valid)
     ok_now, _, _, inl_now = cv2.solvePnPRansac(X, p, g["K"], D0)
     assert ok and np.array_equal(inl, inl_now[:, 0])
-    # the committed fixture was produced by the reference's PnP() in the build container; OpenCV's EPnP
-    # depends on the host's LAPACK kernels, so only require it when this host reproduces the fixture
-    if np.array_equal(inl_now, g["pnp_inliers"]):
-        assert np.array_equal(inl, g["pnp_inliers"][:, 0])
-        R = sfm.rodrigues_to_matrix(rvec)
-        assert np.abs(R - g["pnp_R"]).max() < 1e-6 and np.abs(tvec - g["pnp_t"].ravel()).max() < 1e-5
+    # the committed fixture was produced by the reference's PnP() in the build container.  Everything up to the inlier
+    # list is OpenCV's own fixed-order arithmetic (no LAPACK below 25 rows), so it holds on every host; the default
+    # path (engine minimal solver) must reproduce it too
+    assert np.array_equal(inl, g["pnp_inliers"][:, 0])
+    ok2, rvec2, tvec2, inl2, _ = engine.pnp_ransac(X, p, g["K"])
+    assert ok2 and np.array_equal(inl2, g["pnp_inliers"][:, 0])
+    for rv, tv in ((rvec, tvec), (rvec2, tvec2)):
+        R = sfm.rodrigues_to_matrix(rv)
+        assert np.abs(R - g["pnp_R"]).max() < 1e-6 and np.abs(tv - g["pnp_t"].ravel()).max() < 1e-5
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_device_minimal_solver_is_bit_identical_to_cv2(engine, seed):
+    """pnp_epnp_kernel (csrc/pnp_epnp.cu) on the subsets of OpenCV's RANSAC stream against cv2.solvePnP(EPNP) on
+    the same five points: the same rotation and translation BIT FOR BIT (the raw solver output; cv2 hands it on
+    as cv2.Rodrigues(R), compared through that very call)."""
+    X, p = _problem(seed)
+    subs = sfm.ransac_subsets(len(X), 25)
+    R, t = engine.epnp_batch(X, p, K, subs)
+    for s, Re, te in zip(subs, R, t):
+        ok, rvec, tvec = cv2.solvePnP(X[s], p[s], K, D0, flags=cv2.SOLVEPNP_EPNP)
+        assert ok and np.array_equal(te, tvec.ravel()), s
+        assert np.array_equal(cv2.Rodrigues(Re)[0], rvec), s
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_ransac_default_path_inlier_mask_bit_exact(engine, seed):
+    """The product's default call — minimal solver, scoring, stopping rule and refinement all on the GPU — against
+    cv2.solvePnPRansac on the same inputs (0-60 % outliers, 0.1-2 px noise, 30-3000 points): identical inlier
+    list, pose within 1e-4."""
+    X, p = _problem(seed)
+    ok_ref, rvec_ref, tvec_ref, inl_ref = cv2.solvePnPRansac(X, p, K, D0, cv2.SOLVEPNP_ITERATIVE)
+    ok, rvec, tvec, inl, info = engine.pnp_ransac(X, p, K)
+    assert ok == ok_ref
+    if ok:
+        assert np.array_equal(inl, inl_ref[:, 0])
+        assert np.abs(rvec - rvec_ref.ravel()).max() <= 1e-4 * max(1.0, np.abs(rvec_ref).max())
+        assert np.abs(tvec - tvec_ref.ravel()).max() <= 1e-4 * max(1.0, np.abs(tvec_ref).max())
+        assert info["hyp_solved"] == 100
 
 
 def _solvable_problem(seed):
@@ -94,19 +127,17 @@ def _solvable_problem(seed):
 
 @pytest.mark.parametrize("seed", range(16))
 def test_ransac_with_engine_minimal_solver(engine, seed):
-    """Full GPU path (the engine's own EPnP).  OpenCV's EPnP takes its null-space basis from LAPACK, so the
-    individual hypotheses differ (PnP parity); the estimate must still be the same pose and the
-    same consensus set up to the points within noise of the 8 px threshold."""
+    """Full GPU path on the easier problems (<= 40 % outliers): identical inlier list, and the refined pose within
+    1e-3 px of OpenCV's on every consensus point."""
     X, p = _solvable_problem(seed)
     ok_ref, rvec_ref, tvec_ref, inl_ref = cv2.solvePnPRansac(X, p, K, D0)
     ok, rvec, tvec, inl, info = engine.pnp_ransac(X, p, K)
     assert ok == ok_ref
     if ok:
-        a, b = set(inl.tolist()), set(inl_ref[:, 0].tolist())
-        assert len(a & b) / len(a | b) > 0.97
+        assert np.array_equal(inl, inl_ref[:, 0])
         proj_ref, _ = cv2.projectPoints(X[inl_ref[:, 0]], rvec_ref, tvec_ref, K, None)
         proj, _ = cv2.projectPoints(X[inl_ref[:, 0]], rvec, tvec, K, None)
-        assert np.abs(proj - proj_ref).max() < 0.5       # same pose: < 0.5 px on every consensus point
+        assert np.abs(proj - proj_ref).max() < 1e-3
         assert np.all(np.diff(inl) > 0) and info["hyp_solved"] == 100
 
 

@@ -119,3 +119,21 @@ def test_five_point_degenerate_samples_terminate_with_finite_output():
             q0[:], q1[:] = 0, 0
         E = sfm.five_point(q0, q1)
         assert E.shape[0] <= 10 and np.all(np.isfinite(E))
+
+
+def test_epnp_host_solver_is_bit_identical_to_cv2():
+    """sfm_epnp runs the minimal solver's code (csrc/epnp.h, hostmath.h — what pnp_epnp.cu spreads over a CTA)
+    on the host: the same rvec / tvec as cv2.solvePnP(flags=SOLVEPNP_EPNP) bit for bit, 5 points and more."""
+    import cv2
+    D0 = np.zeros((5, 1), np.float32)
+    K = synth.K_GUSTAV
+    for n in (5, 6, 11, 40):
+        rng = np.random.default_rng(n)
+        for _ in range(100):
+            R, t = synth.orbit_pose(rng.uniform(0, 0.5))
+            X = np.c_[rng.uniform(-2.5, 2.5, n), rng.uniform(-1.5, 1.5, n), rng.uniform(5, 11, n)].astype(np.float32)
+            uv, _ = synth.project(K, R, t, X.astype(np.float64))
+            p = (uv + rng.normal(0, 1.0, uv.shape)).astype(np.float32)
+            ok, rvec, tvec = cv2.solvePnP(X, p, K, D0, flags=cv2.SOLVEPNP_EPNP)
+            Re, te = sfm.epnp(X, p, K)
+            assert np.array_equal(te, tvec.ravel()) and np.array_equal(cv2.Rodrigues(Re)[0], rvec)

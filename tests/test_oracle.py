@@ -5,7 +5,7 @@ import cv2
 import numpy as np
 import pytest
 
-from oracle import cvpath, restated
+from oracle import cv_exact, cvpath, restated
 from sfm_mvs_b200 import synth
 
 
@@ -95,6 +95,87 @@ def _epnp(X5, p5, K=synth.K_GUSTAV):
     return ok, r.ravel(), t.ravel()
 
 
+def _epnp_exact(X5, p5, K=synth.K_GUSTAV):
+    """The oracle's own minimal solver (oracle/cv_epnp.c) handed on as OpenCV does: (cv2.Rodrigues(R), t)."""
+    R, t, _ = cv_exact.epnp(X5, p5, K)
+    return True, cv2.Rodrigues(R)[0].ravel(), t
+
+
+def _pnp_problem(rng, n, K=synth.K_GUSTAV):
+    R, t = synth.orbit_pose(rng.uniform(0, 0.5))
+    X = np.c_[rng.uniform(-2.5, 2.5, n), rng.uniform(-1.5, 1.5, n), rng.uniform(5, 11, n)].astype(np.float32)
+    uv, _ = synth.project(K, R, t, X.astype(np.float64))
+    return X, (uv + rng.normal(0, rng.uniform(0.1, 2.0), uv.shape)).astype(np.float32)
+
+
+@pytest.mark.parametrize("n", [2, 3, 4, 6, 12, 24])
+def test_c_restatement_of_opencv_small_svd_is_bit_exact(n):
+    """cv2 decomposes matrices with fewer than 25 rows with its own one-sided Jacobi (LAPACK only above): the C
+    restatement reproduces w, U and Vt bit for bit — full-rank and rank-deficient (the 5-point M^T M case)."""
+    rng = np.random.default_rng(n)
+    for trial in range(40):
+        A = rng.standard_normal((n, n))
+        if trial % 2 and n >= 6:                      # rank n - 2, symmetric: the basis of the null space is rounding
+            B = rng.standard_normal((n - 2, n))
+            A = B.T @ B
+        w, U, Vt = cv2.SVDecomp(A)
+        w2, U2, Vt2 = cv_exact.svd(A)
+        assert np.array_equal(w.ravel(), w2) and np.array_equal(U, U2) and np.array_equal(Vt, Vt2)
+    A = rng.standard_normal((6, min(n, 5)))           # tall, as in the beta least squares
+    w, U, Vt = cv2.SVDecomp(A)
+    w2, U2, Vt2 = cv_exact.svd(A)
+    assert np.array_equal(w.ravel(), w2) and np.array_equal(U, U2) and np.array_equal(Vt, Vt2)
+
+
+def test_c_restatement_of_opencv_primitives_is_bit_exact():
+    rng = np.random.default_rng(0)
+    for _ in range(100):
+        M = rng.standard_normal((10, 12))
+        assert np.array_equal(cv_exact.mul_transposed(M), cv2.mulTransposed(M, True))
+        A = rng.standard_normal((3, 3))
+        assert np.array_equal(cv_exact.invert_svd(A), cv2.invert(A, flags=cv2.DECOMP_SVD)[1])
+        for nc in (3, 4, 5):
+            A, b = rng.standard_normal((6, nc)), rng.standard_normal(6)
+            assert np.array_equal(cv_exact.solve_svd(A, b), cv2.solve(A, b.reshape(6, 1), flags=cv2.DECOMP_SVD)[1].ravel())
+
+
+@pytest.mark.parametrize("n", [5, 6, 9, 16])
+def test_c_restatement_of_opencv_epnp_is_bit_exact(n):
+    """cv2.solvePnP(flags=EPNP) — the minimal solver inside cv2.solvePnPRansac (sfm.py:67) — against oracle/cv_epnp.c:
+    the same rvec and tvec BIT FOR BIT, for the 5-point minimal case (2-dimensional null space) and for more points."""
+    rng = np.random.default_rng(40 + n)
+    D0 = np.zeros((5, 1), np.float32)
+    for _ in range(300):
+        X, p = _pnp_problem(rng, n)
+        ok, rvec, tvec = cv2.solvePnP(X, p, synth.K_GUSTAV, D0, flags=cv2.SOLVEPNP_EPNP)
+        R, t, info = cv_exact.epnp(X, p, synth.K_GUSTAV)
+        assert ok and np.array_equal(t, tvec.ravel()) and np.array_equal(cv2.Rodrigues(R)[0], rvec)
+        assert 1 <= info["N"] <= 3 and info["sweeps"] >= 2
+
+
+def test_cv2_epnp_null_space_basis_is_decided_by_rounding():
+    """Why the minimal solver has to be restated operation for operation: perturb ONE coordinate of the five points
+    by one float32 ulp and cv2's own hypothesis moves by far more than the perturbation, because the basis of the
+    2-dimensional null space of M^T M that the Jacobi sweeps end in is decided by rounding.  (Any solver that is not
+    bit-identical therefore returns different hypotheses for most subsets, even though each is a valid EPnP pose.)"""
+    rng = np.random.default_rng(7)
+    D0 = np.zeros((5, 1), np.float32)
+    moved, big = 0, 0
+    for _ in range(200):
+        X, p = _pnp_problem(rng, 5)
+        _, r0, t0 = cv2.solvePnP(X, p, synth.K_GUSTAV, D0, flags=cv2.SOLVEPNP_EPNP)
+        X2 = X.copy()
+        X2[0, 0] = np.nextafter(X2[0, 0], np.float32(np.inf))
+        _, r1, t1 = cv2.solvePnP(X2, p, synth.K_GUSTAV, D0, flags=cv2.SOLVEPNP_EPNP)
+        d = np.abs(t1 - t0).max()
+        moved += d > 0
+        big += d > 1e-4                      # a one-ulp input change is ~1e-7 relative
+        # ... while the restatement follows cv2 through the perturbation
+        R2, t2, _ = cv_exact.epnp(X2, p, synth.K_GUSTAV)
+        assert np.array_equal(t2, t1.ravel())
+    assert moved >= 190 and big >= 20, (moved, big)
+
+
 @pytest.mark.parametrize("seed", range(12))
 def test_restated_ransac_loop_reproduces_cv2_mask(seed):
     rng = np.random.default_rng(100 + seed)
@@ -107,16 +188,18 @@ def test_restated_ransac_loop_reproduces_cv2_mask(seed):
     bad = rng.random(n) < rng.uniform(0, 0.6)
     p[bad] += rng.uniform(-80, 80, (int(bad.sum()), 2)).astype(np.float32)
     ok, rvec, tvec, inl = cv2.solvePnPRansac(X, p, K, np.zeros((5, 1), np.float32))
-    res = restated.pnp_ransac(X, p, K, _epnp)
-    assert res["ok"] == ok
-    if ok:
-        assert np.array_equal(np.nonzero(res["mask"])[0], inl[:, 0])
+    for solver in (_epnp, _epnp_exact):          # cv2's minimal solver, and the oracle's own restatement of it
+        res = restated.pnp_ransac(X, p, K, solver)
+        assert res["ok"] == ok
+        if ok:
+            assert np.array_equal(np.nonzero(res["mask"])[0], inl[:, 0])
 
 
 def test_golden_pnp_inliers(golden):
     g = golden("geometry")
-    res = restated.pnp_ransac(g["pnp_X"], g["pnp_p"], g["K"], _epnp)
-    assert np.array_equal(np.nonzero(res["mask"])[0], g["pnp_inliers"][:, 0])
+    for solver in (_epnp, _epnp_exact):
+        res = restated.pnp_ransac(g["pnp_X"], g["pnp_p"], g["K"], lambda a, b: solver(a, b, g["K"]))
+        assert np.array_equal(np.nonzero(res["mask"])[0], g["pnp_inliers"][:, 0])
 
 
 def test_subset_stream_and_update_rule():
