@@ -723,12 +723,24 @@ static int pnp_ransac_impl(sfm_ctx* ctx, const float* X, const float* px, int n,
     subs.count = (n > 5 && H <= 100) ? H : 0;
     if (subs.count) ransac_subsets(n, subs.count, subs.idx);
     long long* dbg = nullptr;
-    if (getenv("SFM_PNP_TIMELINE")) SFM_TRY(ws_alloc_t(ctx, 32, &dbg));
+    if (getenv("SFM_PNP_TIMELINE")) {          // =2: also per-step stamps inside the 12x12 decomposition (they cost ~100 cycles a step)
+      SFM_TRY(ws_alloc_t(ctx, 48, &dbg));
+      long long* hflag;
+      SFM_TRY(hs_alloc_t(ctx, 48, &hflag));
+      memset(hflag, 0, 48 * sizeof(long long));
+      hflag[47] = atoi(getenv("SFM_PNP_TIMELINE"));
+      SFM_CUDA(cudaMemcpyAsync(dbg, hflag, 48 * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+    }
     SFM_TRY(sfm_pnp_epnp_launch(ctx, dX, dpx, n, H, cam, subs, dposes, drt6, dvalid, dbg, nullptr, nullptr));
     if (dbg) {   // diagnostics: phase boundaries of hypothesis 0 in SM clocks
-      long long hs[12];
+      long long hs[32];
       SFM_CUDA(cudaMemcpyAsync(hs, dbg, sizeof(hs), cudaMemcpyDeviceToHost, ctx->stream));
       SFM_CUDA(cudaStreamSynchronize(ctx->stream));
+      fprintf(stderr, "[12x12 jacobi] %lld steps (%lld without a rotation): loads+sums+test %lld | rotation parameters %lld | writes+barriers %lld (cycles, lane 0)\n",
+              hs[15], hs[14], hs[11], hs[12], hs[13]);
+      fprintf(stderr, "[candidates N=4lin / N=2 / N=3] svd+sort %lld %lld %lld | backsubst+gauss-newton %lld %lld %lld | pose %lld %lld %lld\n",
+              hs[20] - hs[4], hs[21] - hs[4], hs[22] - hs[4], hs[23] - hs[20], hs[24] - hs[21], hs[25] - hs[22], hs[26] - hs[23],
+              hs[27] - hs[24], hs[28] - hs[25]);
       fprintf(stderr, "[epnp cycles] subset+control points+alphas %lld | MtM %lld | 12x12 jacobi+sort %lld (%lld sweeps) | L,rho %lld | candidates %lld | pick+store %lld\n",
               hs[1] - hs[0], hs[2] - hs[1], hs[3] - hs[2], hs[10], hs[4] - hs[3], hs[5] - hs[4], hs[6] - hs[5]);
     }

@@ -26,161 +26,30 @@
 #include "epnp.h"
 #include "pnp_dev.cuh"
 #include "ransac.cuh"
+#include "wave_jacobi.cuh"
 
 namespace {
 
-// One-sided Jacobi SVD (OpenCV JacobiSVDImpl_<double>) of n rows of length M (At, row stride M) by one warp, as a
-// wavefront over the pairs.  sq holds the squares of At's entries (OpenCV's running |Ai|^2 is the ordered sum of the
-// squares formed at the row's last rotation, or of the initial entries).  Vt (n x n, identity on entry) may be null.
-// Returns the number of sweeps that rotated something.  On return the rows are orthogonal, NOT yet sorted/normalised.
-template <int M>
-__device__ __forceinline__ int wave_jacobi(double* __restrict__ At, double* __restrict__ sq, double* __restrict__ Vt,
-                                           const int n, const int lane) {
-  static_assert(M % 2 == 0, "rows are read as double2");
-  constexpr int CPL = (M + 3) / 4;      // columns of a row pair each of the 4 lanes of a group rotates
-  const int grp = lane >> 2, sub = lane & 3;
-  const int max_iter = M > 30 ? M : 30;
-  const double eps = DBL_EPSILON * 10;
-  bool chg_prev = true, chg_cur = false;
-  int sweeps = 0;
-  for (int sigma = 0;; ++sigma) {
-    for (int phi = 0; phi < n; ++phi) {
-      // pairs of this step: sweep sigma, i + j = phi + 1, and the tail of sweep sigma - 1, i + j = phi + 1 + n
-      const int s1 = phi + 1, s2 = s1 + n;
-      const int lo1 = max(0, s1 - (n - 1)), hi1 = (s1 - 1) >> 1;
-      const int cnt1 = (sigma < max_iter) ? max(0, hi1 - lo1 + 1) : 0;
-      const int lo2 = s2 - (n - 1), hi2 = (s2 - 1) >> 1;
-      const int cnt2 = (sigma >= 1 && s2 <= 2 * n - 3) ? max(0, hi2 - lo2 + 1) : 0;
-      int i = -1, j = -1;
-      bool first = false;
-      if (grp < cnt1) { i = lo1 + grp; j = s1 - i; first = true; }
-      else if (grp - cnt1 < cnt2) { i = lo2 + grp - cnt1; j = s2 - i; }
-      bool rot = false;
-      double c = 1.0, s = 0.0;
-      double mi[CPL], mj[CPL], vi[3], vj[3];
-      if (i >= 0) {
-        const double2* Ai = reinterpret_cast<const double2*>(At + i * M);
-        const double2* Aj = reinterpret_cast<const double2*>(At + j * M);
-        const double2* Qi = reinterpret_cast<const double2*>(sq + i * M);
-        const double2* Qj = reinterpret_cast<const double2*>(sq + j * M);
-        double p = 0.0, a = 0.0, b = 0.0;
-#pragma unroll
-        for (int k = 0; k < M / 2; ++k) {
-          const double2 x = Ai[k], y = Aj[k], qa = Qi[k], qb = Qj[k];
-          p += x.x * y.x; p += x.y * y.y;
-          a += qa.x; a += qa.y;
-          b += qb.x; b += qb.y;
-        }
-#pragma unroll
-        for (int q = 0; q < CPL; ++q) {
-          const int k = sub + 4 * q;
-          mi[q] = (k < M) ? At[i * M + k] : 0.0;
-          mj[q] = (k < M) ? At[j * M + k] : 0.0;
-        }
-        if (Vt) {
-#pragma unroll
-          for (int q = 0; q < 3; ++q) {
-            const int k = sub + 4 * q;
-            vi[q] = (k < n) ? Vt[i * n + k] : 0.0;
-            vj[q] = (k < n) ? Vt[j * n + k] : 0.0;
-          }
-        }
-        rot = !(fabs(p) <= eps * sqrt(a * b));
-        if (rot) {
-          p *= 2;
-          hm::cv_jacobi_cs(p, a - b, c, s);
-        }
-      }
-      __syncwarp();                      // every read of this step precedes every write
-      if (rot) {
-#pragma unroll
-        for (int q = 0; q < CPL; ++q) {
-          const int k = sub + 4 * q;
-          if (k < M) {
-            const double t0 = c * mi[q] + s * mj[q];
-            const double t1 = -s * mi[q] + c * mj[q];
-            At[i * M + k] = t0; At[j * M + k] = t1;
-            sq[i * M + k] = t0 * t0; sq[j * M + k] = t1 * t1;
-          }
-        }
-        if (Vt) {
-#pragma unroll
-          for (int q = 0; q < 3; ++q) {
-            const int k = sub + 4 * q;
-            if (k < n) {
-              const double t0 = c * vi[q] + s * vj[q];
-              const double t1 = -s * vi[q] + c * vj[q];
-              Vt[i * n + k] = t0; Vt[j * n + k] = t1;
-            }
-          }
-        }
-      }
-      __syncwarp();                      // ... and every write precedes the next step's reads
-      const unsigned any = __ballot_sync(0xffffffffu, rot);
-      const unsigned any_first = __ballot_sync(0xffffffffu, rot && first);
-      chg_cur |= any_first != 0u;
-      chg_prev |= (any & ~any_first) != 0u;
-      // OpenCV's loop ends after the first sweep that rotates nothing (or after max_iter sweeps).  Pairs of the
-      // next sweep that already ran saw the same rows and the same sums as in that sweep, so they skipped too.
-      if (n >= 4) {
-        if (sigma >= 1 && phi == n - 4) {          // sweep sigma - 1 is complete
-          if (chg_prev) ++sweeps;
-          if (!chg_prev || sigma >= max_iter) return sweeps;
-        }
-      } else if (phi == n - 1) {                   // n < 4: no overlap, sweep sigma is complete
-        if (chg_cur) ++sweeps;
-        if (!chg_cur || sigma + 1 >= max_iter) return sweeps;
-      }
-    }
-    chg_prev = chg_cur;
-    chg_cur = false;
-  }
-}
-
-// Singular values (descending), OpenCV's selection sort on them as a row permutation: W[pos], row ord[pos].
-template <int M>
-__device__ __forceinline__ void wave_sort(const double* __restrict__ sq, int n, double* __restrict__ W, int* __restrict__ ord,
-                                          int lane) {
-  __syncwarp();
-  if (lane < n) {
-    double sd = 0.0;
-#pragma unroll
-    for (int k = 0; k < M; ++k) sd += sq[lane * M + k];
-    W[lane] = sqrt(sd);
-    ord[lane] = lane;
-  }
-  __syncwarp();
-  if (lane == 0) {
-    for (int i = 0; i < n - 1; ++i) {
-      int j = i;
-      for (int k = i + 1; k < n; ++k)
-        if (W[j] < W[k]) j = k;
-      if (i != j) {
-        const double tw = W[i]; W[i] = W[j]; W[j] = tw;
-        const int to = ord[i]; ord[i] = ord[j]; ord[j] = to;
-      }
-    }
-  }
-  __syncwarp();
-}
-
-struct CandShared {        // one beta initialisation (one warp)
-  double At[30], sq[30], Vt[25], W[5];
+struct CandShared {        // one beta initialisation (one warp); At / sq first: their rows are read as double2
+  double At[30], sq[30];
+  double Vt[25], W[5], Wtmp[5];
   double ut[30], vts[25];  // sorted, normalised
   double pcs[15];
   double R[9], t[3], err;
-  int ord[5];
+  int ord[5], pad[3];
+  int sched[40];
 };
+static_assert(sizeof(CandShared) % 16 == 0, "CandShared rows are read as double2");
 
-struct EpnpShared {        // At / sq (and CandShared, a multiple of 16 bytes) first: their rows are read as double2
+struct EpnpShared {
   double At[144], sq[144];
   CandShared cand[3];
   double pw[15], us[10], alphas[20], cws[12];
-  double M[120], W[12];
+  double M[120], W[12], Wtmp[12];
   double v4[48], L[60], rho[6];
   int ord[12];
+  int sched[96];
 };
-static_assert(sizeof(CandShared) % 16 == 0, "CandShared rows are read as double2");
 
 __global__ void __launch_bounds__(96) pnp_epnp_kernel(const float* __restrict__ X, const float* __restrict__ px, int n,
                                                       int H, PnpCam cam, const __grid_constant__ PnpSubsets subs,
@@ -224,6 +93,7 @@ __global__ void __launch_bounds__(96) pnp_epnp_kernel(const float* __restrict__ 
         sh.pw[3 * k] = (double)X[3 * (size_t)j]; sh.pw[3 * k + 1] = (double)X[3 * (size_t)j + 1]; sh.pw[3 * k + 2] = (double)X[3 * (size_t)j + 2];
         hm::epnp_roundtrip_pixel(px[2 * (size_t)j], px[2 * (size_t)j + 1], ec, sh.us + 2 * k);
       }
+      // control points and barycentric coordinates: two 3 x 3 decompositions, inherently serial (epnp.h)
       hm::epnp_control_alphas(sh.pw, 5, sh.alphas, reinterpret_cast<double(*)[3]>(sh.cws));
     }
     __syncwarp();
@@ -244,8 +114,9 @@ __global__ void __launch_bounds__(96) pnp_epnp_kernel(const float* __restrict__ 
     }
     __syncwarp();
     tick(2);
-    const int sweeps = wave_jacobi<12>(sh.At, sh.sq, nullptr, 12, lane);
-    wave_sort<12>(sh.sq, 12, sh.W, sh.ord, lane);
+    const int sweeps = (dbg && h == 0 && dbg[47] == 2) ? wave_jacobi<12, true>(sh.At, sh.sq, nullptr, sh.sched, 12, lane, dbg + 11)
+                                       : wave_jacobi<12>(sh.At, sh.sq, nullptr, sh.sched, 12, lane);
+    wave_sort<12>(sh.sq, 12, sh.W, sh.ord, sh.Wtmp, lane);
     tick(3);
     if (dbg && h == 0 && lane == 0) dbg[10] = sweeps;
     // v[q] = left singular vector of the (q+1)-th smallest singular value: sorted row 11 - q, scaled by 1 / sigma
@@ -276,8 +147,8 @@ __global__ void __launch_bounds__(96) pnp_epnp_kernel(const float* __restrict__ 
     }
     for (int e = lane; e < nc * nc; e += 32) cs.Vt[e] = (e / nc == e % nc) ? 1.0 : 0.0;
     __syncwarp();
-    wave_jacobi<6>(cs.At, cs.sq, cs.Vt, nc, lane);
-    wave_sort<6>(cs.sq, nc, cs.W, cs.ord, lane);
+    wave_jacobi<6>(cs.At, cs.sq, cs.Vt, cs.sched, nc, lane);
+    wave_sort<6>(cs.sq, nc, cs.W, cs.ord, cs.Wtmp, lane);
     for (int e = lane; e < 6 * nc; e += 32) {
       const int r = e / 6, k = e - 6 * r;
       const double sd = cs.W[r];
@@ -286,6 +157,7 @@ __global__ void __launch_bounds__(96) pnp_epnp_kernel(const float* __restrict__ 
     }
     for (int e = lane; e < nc * nc; e += 32) cs.vts[e] = cs.Vt[nc * cs.ord[e / nc] + e % nc];
     __syncwarp();
+    if (dbg && h == 0 && lane == 0) dbg[20 + warp] = clock64();
     if (lane == 0) {
       double b[5], betas[4] = {0, 0, 0, 0};
       if (ap == 0) hm::cv_svd_backsubst<6, 4>(cs.W, cs.ut, cs.vts, sh.rho, b);
@@ -293,8 +165,10 @@ __global__ void __launch_bounds__(96) pnp_epnp_kernel(const float* __restrict__ 
       else hm::cv_svd_backsubst<6, 5>(cs.W, cs.ut, cs.vts, sh.rho, b);
       hm::epnp_betas_from_ls(ap, b, betas);
       hm::epnp_gauss_newton(sh.L, sh.rho, betas);
+      if (dbg && h == 0) dbg[23 + warp] = clock64();
       const double* v[4] = {sh.v4, sh.v4 + 12, sh.v4 + 24, sh.v4 + 36};
       cs.err = hm::epnp_pose_from_betas(v, betas, sh.alphas, sh.pw, sh.us, 5, ec, cs.pcs, cs.R, cs.t);
+      if (dbg && h == 0) dbg[26 + warp] = clock64();
     }
   }
   __syncthreads();
@@ -317,7 +191,7 @@ __global__ void __launch_bounds__(96) pnp_epnp_kernel(const float* __restrict__ 
     rt6[6 * h + 3] = t[0]; rt6[6 * h + 4] = t[1]; rt6[6 * h + 5] = t[2];
     valid[h] = ok ? 1 : 0;
     if (dbg && h == 0) {                 // diagnostics: the raw solver output of hypothesis 0
-      double* d = reinterpret_cast<double*>(dbg + 16);
+      double* d = reinterpret_cast<double*>(dbg + 32);
       for (int k = 0; k < 9; ++k) d[k] = R[k];
       for (int k = 0; k < 3; ++k) d[9 + k] = t[k];
     }
@@ -365,9 +239,10 @@ extern "C" int sfm_epnp_batch(sfm_ctx* ctx, const float* X, const float* px, int
     PnpSubsets one;
     one.count = 1;
     for (int k = 0; k < 5; ++k) one.idx[k] = subs.idx[5 * h + k];
-    SFM_TRY(ws_alloc_t(ctx, 32, &dbg));
+    SFM_TRY(ws_alloc_t(ctx, 48, &dbg));
+    SFM_CUDA(cudaMemsetAsync(dbg, 0, 48 * sizeof(long long), ctx->stream));
     SFM_TRY(sfm_pnp_epnp_launch(ctx, dX, dpx, n, 1, cam, one, dposes, drt6, dvalid, dbg, nullptr, nullptr));
-    SFM_CUDA(cudaMemcpyAsync(hout, dbg + 16, sizeof(double) * 12, cudaMemcpyDeviceToHost, ctx->stream));
+    SFM_CUDA(cudaMemcpyAsync(hout, dbg + 32, sizeof(double) * 12, cudaMemcpyDeviceToHost, ctx->stream));
     SFM_CUDA(cudaStreamSynchronize(ctx->stream));
     memcpy(R9t3 + 12 * (size_t)h, hout, sizeof(double) * 12);
   }
