@@ -154,7 +154,8 @@ def register_view(state, view_prev, view_new, first: bool):
     with contextlib.redirect_stdout(io.StringIO()):
         i1, i2, temp1, temp2 = common_points(pts1, pts_, pts2)            # sfm.py:356
     com2, com_ = pts2[i2], pts_[i2]
-    Rot, trans, com2, X_in, com_ = PnP(points_3d[i1], com2, K, np.zeros((5, 1), np.float32),
+    pnp_X, pnp_p = points_3d[i1], com2                                    # what the reference hands to solvePnPRansac
+    Rot, trans, com2, X_in, com_ = PnP(pnp_X, com2, K, np.zeros((5, 1), np.float32),
                                        com_, initial=0)                  # sfm.py:362
     Rt = np.hstack((Rot, trans))
     Pnew = K @ Rt
@@ -164,7 +165,7 @@ def register_view(state, view_prev, view_new, first: bool):
     new_state = dict(K=K, P1=P2.copy(), P2=Pnew.copy(), pts0=pts_.copy(), pts1=pts2.copy(),
                      points_3d=None)
     out = dict(Rt=Rt, err_pnp=err_pnp, err_new=err_new, X_new=X_new[:, 0, :], n_pnp=len(i1),
-               n_inl=len(com2), n_match=len(pts_))
+               n_inl=len(com2), n_match=len(pts_), pnp_X=pnp_X, pnp_p=pnp_p)
     return new_state, out
 
 
