@@ -1,23 +1,28 @@
-// solve.cu — dense symmetric-positive-definite solve of the reduced camera system (n = 6C; 3000 at
-// C = 500), float64, hand-written right-looking blocked Cholesky, NB = 64, with look-ahead.
+// solve.cu — dense symmetric-positive-definite solve of the reduced camera system (n = 6C; 3000 at C = 500) in
+// float64: a tile Cholesky run as a dependency graph inside ONE persistent kernel, and the back substitution
+// inside a second one — no launch per block step, no grid-wide barrier.
 //
-//   A is (n+1) x n row-major, lower triangle used; row n carries the right-hand side, so the
-//   forward substitution L y = b falls out of the panel solves for free (row n ends up as y^T).
-//   The sequential part of a step — the 64x64 diagonal block — is factored by a whole CTA with the
-//   block distributed over registers (thread = one row x 16 columns) and ONE block barrier per
-//   column; it runs as a look-ahead inside the trailing update of the previous step (the CTA that
-//   owns the first tile of the update owns exactly the next diagonal block), so it overlaps the
-//   rest of that update.
-//     chol_diag_kernel   block 0 only
-//     chol_panel_kernel  rows below block k (incl. the rhs row): x L_kk^T = a, one row per thread,
-//                        L_kk and 1/diag staged in shared memory
-//     chol_syrk_kernel   A22 -= L21 L21^T, 64x64 tile per CTA, 4x4 per thread, K = 64 in two
-//                        32-wide shared-memory stages, lower-triangular tiles only; tile 0 then
-//                        factors diagonal block k+1
-//   backward substitution L^T x = y, 256-row super-blocks from the bottom up:
-//     back_diag_kernel   one CTA: four 64-row sub-steps (operands staged in shared memory with
-//                        coalesced loads; one barrier per unknown inside a sub-step)
-//     back_update_kernel earlier entries: y[i] -= sum_r L[k0+r][i] x[k0+r], 8 threads per entry
+// Layout: the lower triangle of S in 64 x 64 tiles, each tile contiguous and COLUMN-major (element (r, c) at
+// c * 64 + r), n padded to a multiple of 64 with an identity diagonal, plus one extra tile row whose row 0 is the
+// right-hand side -g: the forward substitution L y = b is then just the bottom row of the factorisation.
+// Column-major tiles make a finished tile L(i,k) directly the k-major operand of every later update.
+//
+// spd_factor_kernel (one CTA per SM, 256 threads).  Task = output tile (i, j), j <= i, claimed from an atomic
+// counter in column-major order — every task depends only on tasks earlier in that order, which are finished or
+// held by a running CTA, so spinning on their ready flags cannot deadlock.  A task is left-looking:
+//   acc (4 x 4 per thread, registers) <- A(i,j);  for k < j: wait L(i,k), L(j,k);  acc -= L(i,k) L(j,k)^T
+//   i == j: Cholesky of the 64 x 64 block (four 16-column panels, as before) and 1/diag
+//   i >  j: wait L(j,j);  X L(j,j)^T = acc, one row per thread
+//   store, __threadfence, release the tile's flag.
+// Each tile is written once and read as an operand afterwards; the trailing matrix never makes the
+// read-modify-write round trips through L2 that the right-looking version made at every step, and the ~100
+// launches (47 block steps x (panel, update)) with their drains are gone.
+//
+// spd_backsolve_kernel (one CTA per tile column + one "diagonal" CTA).  L^T x = y from the bottom in super-blocks
+// of 4 tile columns: column CTA c owns y_c (64 entries, in shared memory), subtracts L(rows of super-block s, c)^T
+// x_s as soon as x_s is published, for every super-block below its own, then publishes y_c; the diagonal CTA
+// waits for the four y_c of its super-block, solves the 256 x 256 triangle (64-row sub-steps by warp shuffles)
+// and publishes x_s.  No atomics: a column's entries are only ever touched by its own CTA.
 #include <math.h>
 
 #include "common.cuh"
@@ -25,27 +30,74 @@
 
 namespace {
 
-constexpr int NB = 64;
-constexpr int SB = 256;   // backward-substitution super-block
+constexpr int T = 64;           // tile edge
+constexpr int TT = T * T;
+constexpr int SBT = 4;          // tile columns per back-substitution super-block
 
-// Cholesky of the diagonal block at k0 by a 256-thread CTA.  Thread t holds row t%64, columns
-// 16*(t/64) .. +15 in registers.  The block is factored in four 16-column panels:
-//   inside a panel only its 64 owner threads work — per column two 64-thread named barriers (publish the
-//   diagonal, publish the scaled column) and <= 15 FMAs per thread for the columns of the same panel;
-//   after a panel ONE block barrier, then the threads holding columns to its right apply the whole rank-16
-//   update from shared memory (256 independent FMAs per thread).
-// 4 block barriers instead of 64, and the serial part is 64 x (two cheap barriers + a handful of FMAs).
-// Rows/columns >= nb are identity.  Writes L (lower) back to A and 1/diag(L) to dinv[k0 .. k0+63].
-// colbuf: 16 x (NB+2) doubles of shared memory.
-__device__ __forceinline__ void factor_diag_block(double* __restrict__ A, int n, int k0, double* __restrict__ dinv,
-                                                  int* __restrict__ info, double (*colbuf)[NB + 2]) {
-  const int nb = min(NB, n - k0);
+struct SpdPlan {
+  int n, ntc, ntasks;
+  double* tiles;                // tile-major, tiles column-major
+  double* inv;                  // ntc tiles: inverses of the diagonal blocks L(c,c) (lower triangular, column-major)
+  double* dinv;                 // 1 / diag(L), ntc * 64
+  double* ybuf;                 // ntc * 64: y_c as published by the column CTAs
+  double* xbuf;                 // ntc * 64: the solution
+  int* flags;                   // one per tile (+ one per inverse): 1 = the final tile is in memory
+  int* sync;                    // [0] task counter; [1 ..] back substitution flags: ycol_ready[ntc], x_ready[nsb]
+  int* info;
+};
+
+__host__ __device__ inline int tile_id(int i, int j, int ntc) { return (i < ntc ? i * (i + 1) / 2 : ntc * (ntc + 1) / 2) + j; }
+
+__device__ __forceinline__ int ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void wait_flag(const int* p) {
+  while (ld_acquire(p) == 0) __nanosleep(40);
+}
+
+// S (float32, lower triangle) and g -> float64 tiles.  grid = (tile id, 16 column groups), 256 threads.
+__global__ void __launch_bounds__(256) spd_pack_kernel(const float* __restrict__ S, const float* __restrict__ g, SpdPlan p) {
+  const int ntc = p.ntc, n = p.n;
+  int t = blockIdx.x, i, j;
+  const int ntri = ntc * (ntc + 1) / 2;
+  if (t < ntri) {
+    i = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+    while ((i + 1) * (i + 2) / 2 <= t) ++i;
+    while (i * (i + 1) / 2 > t) --i;
+    j = t - i * (i + 1) / 2;
+  } else {
+    i = ntc;
+    j = t - ntri;
+  }
+  double* dst = p.tiles + (size_t)t * TT;
+  for (int e = threadIdx.x; e < TT; e += blockDim.x) {
+    const int c = e >> 6, r = e & 63;                   // column-major within the tile
+    const int gr = T * i + r, gc = T * j + c;
+    double v;
+    if (i == ntc) v = (r == 0 && gc < n) ? -(double)g[gc] : 0.0;
+    else if (gr < n && gc < n) v = (gc <= gr) ? (double)S[(size_t)gr * n + gc] : 0.0;
+    else v = (gr == gc) ? 1.0 : 0.0;
+    dst[e] = v;
+  }
+}
+
+// Cholesky of a 64 x 64 block held column-major in shared memory (C), by 256 threads: thread t holds row t%64,
+// columns 16*(t/64) .. +15 in registers; four 16-column panels (inside a panel only its 64 owner threads work, two
+// 64-thread named barriers per column; after a panel one block barrier and the rank-16 update of the columns to its
+// right).  Writes L (lower, zeros above) column-major to `out` and 1/diag to dinv.  colbuf: 16 x (T+2) doubles.
+__device__ __forceinline__ void factor_block(const double* __restrict__ C, double* __restrict__ out, double* __restrict__ dinv,
+                                             int pivot_base, int* __restrict__ info, double (*colbuf)[T + 2]) {
   const int row = threadIdx.x & 63, cseg = threadIdx.x >> 6;
   double a[16];
 #pragma unroll
   for (int cc = 0; cc < 16; ++cc) {
     const int c = 16 * cseg + cc;
-    a[cc] = (row < nb && c <= row) ? A[(size_t)(k0 + row) * n + k0 + c] : ((c == row) ? 1.0 : 0.0);
+    a[cc] = (c <= row) ? C[c * T + row] : 0.0;
   }
 #pragma unroll 1
   for (int seg = 0; seg < 4; ++seg) {
@@ -54,18 +106,18 @@ __device__ __forceinline__ void factor_diag_block(double* __restrict__ A, int n,
       for (int jj = 0; jj < 16; ++jj) {
         const int j = 16 * seg + jj;
         double* cb = colbuf[jj];                        // cb[0..63] scaled column j, cb[64] raw diagonal
-        if (row == j) cb[NB] = a[jj];
+        if (row == j) cb[T] = a[jj];
         asm volatile("bar.sync 1, 64;" ::: "memory");
-        double d = cb[NB];
-        if (j < nb && !(d > 0.0)) {
-          if (row == j && info && *info == 0) *info = k0 + j + 1;   // not positive definite
+        double d = cb[T];
+        if (!(d > 0.0)) {
+          if (row == j && info && *info == 0) *info = pivot_base + j + 1;   // not positive definite
           d = 1.0;
         }
         const double rinv = rsqrt(d);
         const double li = (row == j) ? d * rinv : ((row > j) ? a[jj] * rinv : 0.0);   // L[row][j]
         a[jj] = li;
         cb[row] = li;
-        if (row == j) dinv[k0 + j] = rinv;
+        if (row == j) dinv[j] = rinv;
         asm volatile("bar.sync 1, 64;" ::: "memory");
 #pragma unroll
         for (int cc = jj + 1; cc < 16; ++cc) {          // remaining columns of this panel
@@ -91,243 +143,309 @@ __device__ __forceinline__ void factor_diag_block(double* __restrict__ A, int n,
 #pragma unroll
   for (int cc = 0; cc < 16; ++cc) {
     const int c = 16 * cseg + cc;
-    if (row < nb && c <= row) A[(size_t)(k0 + row) * n + k0 + c] = a[cc];
+    out[c * T + row] = (c <= row) ? a[cc] : 0.0;
   }
 }
 
-__global__ void __launch_bounds__(256) chol_diag_kernel(double* __restrict__ A, int n, int k0, double* __restrict__ dinv,
-                                                        int* __restrict__ info) {
-  __shared__ double colbuf[16][NB + 2];
-  factor_diag_block(A, n, k0, dinv, info, colbuf);
-}
+constexpr int FACTOR_SMEM = (2 * TT + 16 * (T + 2) + T) * (int)sizeof(double);
 
-// rows k0+nb .. n (the last one is the rhs row): solve x L_kk^T = a, one row per thread, the running
-// solution in registers (fully unrolled), L_kk (strictly lower) and 1/diag read as shared broadcasts.
-constexpr int PANEL_THREADS = 128;
-__global__ void __launch_bounds__(PANEL_THREADS) chol_panel_kernel(double* __restrict__ A, int n, int k0,
-                                                                   const double* __restrict__ dinv) {
-  __shared__ double L[NB][NB + 1];
-  __shared__ double di[NB];
-  const int nb = min(NB, n - k0);
-  for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) {
-    const int r = e / NB, c = e % NB;
-    L[r][c] = (r < nb && c < r) ? A[(size_t)(k0 + r) * n + k0 + c] : 0.0;
-  }
-  if (threadIdx.x < NB) di[threadIdx.x] = (threadIdx.x < nb) ? dinv[k0 + threadIdx.x] : 1.0;
-  __syncthreads();
-  const int row = k0 + nb + blockIdx.x * blockDim.x + threadIdx.x;
-  if (row > n) return;
-  double* a = A + (size_t)row * n + k0;
-  double x[NB];
-#pragma unroll
-  for (int j = 0; j < NB; ++j) x[j] = (j < nb) ? a[j] : 0.0;
-#pragma unroll
-  for (int j = 0; j < NB; ++j) {
-    double s0 = x[j], s1 = 0.0, s2 = 0.0, s3 = 0.0;    // four chains: the sum over k < j is latency-bound otherwise
-#pragma unroll
-    for (int k = 0; k < j; ++k) {
-      if ((k & 3) == 0) s0 = fma(-x[k], L[j][k], s0);
-      else if ((k & 3) == 1) s1 = fma(-x[k], L[j][k], s1);
-      else if ((k & 3) == 2) s2 = fma(-x[k], L[j][k], s2);
-      else s3 = fma(-x[k], L[j][k], s3);
-    }
-    x[j] = ((s0 + s1) + (s2 + s3)) * di[j];
-  }
-#pragma unroll
-  for (int j = 0; j < NB; ++j)
-    if (j < nb) a[j] = x[j];
-}
-
-// rows [base, n] (n+1-base of them, the last is the rhs row), columns [base, n)
-__global__ void __launch_bounds__(256) chol_syrk_kernel(double* __restrict__ A, int n, int k0, int nb,
-                                                        double* __restrict__ dinv, int* __restrict__ info) {
-  constexpr int KC = 32;
-  __shared__ double Pi[64][KC + 1];
-  __shared__ double Pj[64][KC + 1];
-  int t = blockIdx.x;
-  int ti = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
-  while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
-  while (ti * (ti + 1) / 2 > t) --ti;
-  const int tj = t - ti * (ti + 1) / 2;
-  const int base = k0 + nb;
-  const int i0 = base + ti * 64, j0 = base + tj * 64;
-  if (j0 >= n) return;
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  double acc[4][4];
-#pragma unroll
-  for (int a = 0; a < 4; ++a)
-#pragma unroll
-    for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
-  for (int kc = 0; kc < nb; kc += KC) {
-    if (kc) __syncthreads();
-    for (int e = threadIdx.x; e < 64 * KC; e += blockDim.x) {
-      const int r = e / KC, c = e % KC;
-      Pi[r][c] = (i0 + r <= n && kc + c < nb) ? A[(size_t)(i0 + r) * n + k0 + kc + c] : 0.0;
-      Pj[r][c] = (j0 + r < n && kc + c < nb) ? A[(size_t)(j0 + r) * n + k0 + kc + c] : 0.0;
-    }
+__global__ void __launch_bounds__(256, 1) spd_factor_kernel(SpdPlan p) {
+  extern __shared__ __align__(16) double smem[];
+  double* As = smem;                  // operand L(i,k), k-major: As[k * 64 + row]   (== the tile as stored)
+  double* Bs = smem + TT;             // operand L(j,k)
+  double (*colbuf)[T + 2] = reinterpret_cast<double(*)[T + 2]>(smem + 2 * TT);
+  double* di = smem + 2 * TT + 16 * (T + 2);
+  __shared__ int s_task;
+  const int ntc = p.ntc;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;        // rows 4 ty .. +3, columns tx + 16 b of the tile
+  for (;;) {
+    if (threadIdx.x == 0) s_task = atomicAdd(p.sync, 1);
     __syncthreads();
-#pragma unroll 8
-    for (int k = 0; k < KC; ++k) {
-      double av[4], bv[4];
+    const int q = s_task;
+    __syncthreads();
+    if (q >= p.ntasks + ntc) return;
+    if (q >= p.ntasks) {
+      // ---- inverse of a diagonal block, for the back substitution (off the factorisation's critical path: these
+      // tasks come last in the queue).  Column j of L^-1 by thread j: z_j = 1 / L_jj, z_i = -(sum_{m=j}^{i-1} L[i][m] z_m) / L_ii
+      const int c = q - p.ntasks;
+      const int id = tile_id(c, c, ntc);
+      if (threadIdx.x == 0) wait_flag(p.flags + id);
+      __syncthreads();
+      {
+        const double2* ga = reinterpret_cast<const double2*>(p.tiles + (size_t)id * TT);
+        double2* sa = reinterpret_cast<double2*>(As);
 #pragma unroll
-      for (int a = 0; a < 4; ++a) av[a] = Pi[ty + 16 * a][k];
-#pragma unroll
-      for (int b = 0; b < 4; ++b) bv[b] = Pj[tx + 16 * b][k];
-#pragma unroll
-      for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) acc[a][b] = fma(av[a], bv[b], acc[a][b]);
+        for (int e = 0; e < TT / 2 / 256; ++e) sa[threadIdx.x + 256 * e] = __ldcg(ga + threadIdx.x + 256 * e);
+        if (threadIdx.x < T) di[threadIdx.x] = __ldcg(p.dinv + T * c + threadIdx.x);
+      }
+      __syncthreads();
+      if (threadIdx.x < T) {
+        const int j = threadIdx.x;                  // Bs[i * 64 + j] = (L^-1)[i][j]
+#pragma unroll 1
+        for (int i = 0; i < T; ++i) {
+          double z = 0.0;
+          if (i == j) z = di[j];
+          else if (i > j) {
+            double s0 = 0.0, s1 = 0.0;
+            int m = j;
+            for (; m + 1 < i; m += 2) {
+              s0 = fma(As[m * T + i], Bs[m * T + j], s0);
+              s1 = fma(As[(m + 1) * T + i], Bs[(m + 1) * T + j], s1);
+            }
+            if (m < i) s0 = fma(As[m * T + i], Bs[m * T + j], s0);
+            z = -(s0 + s1) * di[i];
+          }
+          Bs[i * T + j] = z;
+        }
+      }
+      __syncthreads();
+      double* out = p.inv + (size_t)c * TT;
+      for (int e = threadIdx.x; e < TT; e += 256) out[e] = Bs[(e & 63) * T + (e >> 6)];      // column-major: (i, j) at j * 64 + i
+      __threadfence();
+      __syncthreads();
+      if (threadIdx.x == 0) st_release(p.flags + p.ntasks + c, 1);
+      continue;
     }
-  }
-#pragma unroll
-  for (int a = 0; a < 4; ++a)
+    // column-major task order: column j holds tiles (j, j) .. (ntc, j)
+    int j = 0, rem = q;
+    while (rem >= ntc + 1 - j) { rem -= ntc + 1 - j; ++j; }
+    const int i = j + rem;
+    double* tile = p.tiles + (size_t)tile_id(i, j, ntc) * TT;
+    double acc[4][4];                                             // acc[b][a]: column tx + 16 b, row 4 ty + a
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
-      const int i = i0 + ty + 16 * a, j = j0 + tx + 16 * b;
-      if (i <= n && j < n && j <= i) A[(size_t)i * n + j] -= acc[a][b];
+      const double2 lo = *reinterpret_cast<const double2*>(tile + (tx + 16 * b) * T + 4 * ty);
+      const double2 hi = *reinterpret_cast<const double2*>(tile + (tx + 16 * b) * T + 4 * ty + 2);
+      acc[b][0] = lo.x; acc[b][1] = lo.y; acc[b][2] = hi.x; acc[b][3] = hi.y;
     }
-  // look-ahead: tile 0 of the update is exactly diagonal block k+1 and now holds its final values
-  if (t == 0) {
-    __syncthreads();
-    factor_diag_block(A, n, base, dinv, info, reinterpret_cast<double(*)[NB + 2]>(&Pi[0][0]));
-  }
-}
-
-// One CTA per call: rows [k0, k0+sb) of L^T x = y in 64-row sub-steps from the bottom.
-__global__ void __launch_bounds__(256) back_diag_kernel(const double* __restrict__ A, int n, int k0, int sb,
-                                                        const double* __restrict__ dinv, double* __restrict__ y,
-                                                        double* __restrict__ x) {
-  __shared__ double ys[SB];
-  __shared__ double Ls[NB][NB + 1];
-  __shared__ double xs[NB];
-  for (int i = threadIdx.x; i < SB; i += blockDim.x) ys[i] = (i < sb) ? y[k0 + i] : 0.0;
-  const int nsub = (sb + NB - 1) / NB;
-  for (int s = nsub - 1; s >= 0; --s) {
-    const int r0 = k0 + s * NB;                       // global row of the sub-block
-    const int nb = min(NB, n - r0);
-    __syncthreads();
-    for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) {
-      const int r = e / NB, c = e % NB;
-      Ls[r][c] = (r < nb && c < r) ? A[(size_t)(r0 + r) * n + r0 + c] : 0.0;
-    }
-    __syncthreads();
-    // x_j = (v_j - sum_{i>j} L[i][j] x_i) / L_jj, unknown j owned by thread j (two warps)
-    double v = 0.0, di = 1.0;
-    if (threadIdx.x < NB) {
-      v = ys[s * NB + threadIdx.x];
-      di = (threadIdx.x < nb) ? dinv[r0 + threadIdx.x] : 1.0;
-    }
-    // 64 unknowns, bottom up.  Unknown j lives in lane j%32 of warp j/32; inside a 32-unknown half the solved value
-    // travels by shuffle (no barrier), the upper half's effect on the lower one is a 32x32 matvec.
-    if (threadIdx.x < NB) xs[threadIdx.x] = 0.0;
-    __syncthreads();
-    if (threadIdx.x >= 32 && threadIdx.x < NB) {       // upper half (unknowns 32..63), warp 1
-      const int l = threadIdx.x - 32;
-      for (int j = 31; j >= 0; --j) {
-        const double xj = __shfl_sync(0xffffffffu, v * di, j);
-        if (l == j) xs[32 + j] = xj;
-        if (l < j) v = fma(-Ls[32 + j][32 + l], xj, v);
+#pragma unroll 1
+    for (int k = 0; k < j; ++k) {
+      const int ia = tile_id(i, k, ntc), ib = tile_id(j, k, ntc);
+      if (threadIdx.x == 0) {
+        wait_flag(p.flags + ia);
+        if (ib != ia) wait_flag(p.flags + ib);
       }
-    }
-    __syncthreads();
-    if (threadIdx.x < 32) {                            // lower half (unknowns 0..31), warp 0
-      const int l = threadIdx.x;
-      double s0 = 0.0, s1 = 0.0;
-#pragma unroll 8
-      for (int r = 0; r < 32; r += 2) {
-        s0 = fma(Ls[32 + r][l], xs[32 + r], s0);
-        s1 = fma(Ls[33 + r][l], xs[33 + r], s1);
-      }
-      v -= s0 + s1;
-      for (int j = 31; j >= 0; --j) {
-        const double xj = __shfl_sync(0xffffffffu, v * di, j);
-        if (l == j) xs[j] = xj;
-        if (l < j) v = fma(-Ls[j][l], xj, v);
-      }
-    }
-    __syncthreads();
-    if ((int)threadIdx.x < nb) x[r0 + threadIdx.x] = xs[threadIdx.x];
-    // earlier rows of this super-block: y[i] -= sum_r L[r0+r][k0+i] x_s[r]
-    for (int i = threadIdx.x; i < s * NB; i += blockDim.x) {
-      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-      int r = 0;
-      for (; r + 3 < nb; r += 4) {
-        a0 = fma(A[(size_t)(r0 + r) * n + k0 + i], xs[r], a0);
-        a1 = fma(A[(size_t)(r0 + r + 1) * n + k0 + i], xs[r + 1], a1);
-        a2 = fma(A[(size_t)(r0 + r + 2) * n + k0 + i], xs[r + 2], a2);
-        a3 = fma(A[(size_t)(r0 + r + 3) * n + k0 + i], xs[r + 3], a3);
-      }
-      for (; r < nb; ++r) a0 = fma(A[(size_t)(r0 + r) * n + k0 + i], xs[r], a0);
-      ys[i] -= (a0 + a1) + (a2 + a3);
-    }
-  }
-}
-
-// y[i] -= sum_{r < sb} L[k0+r][i] x[k0+r] for i < k0; 8 threads per entry (rows r = q, q+8, ...),
-// 32 entries per CTA, so a warp-level load covers 32 consecutive doubles of one row of L.
-__global__ void __launch_bounds__(256) back_update_kernel(const double* __restrict__ A, int n, int k0, int sb,
-                                                          const double* __restrict__ x, double* __restrict__ y) {
-  __shared__ double xs[SB];
-  __shared__ double part[8][33];
-  for (int i = threadIdx.x; i < sb; i += blockDim.x) xs[i] = x[k0 + i];
-  __syncthreads();
-  const int lane = threadIdx.x & 31, q = threadIdx.x >> 5;
-  const int i = blockIdx.x * 32 + lane;
-  double a0 = 0.0, a1 = 0.0;
-  if (i < k0) {
-    int r = q;
-    for (; r + 8 < sb; r += 16) {
-      a0 = fma(A[(size_t)(k0 + r) * n + i], xs[r], a0);
-      a1 = fma(A[(size_t)(k0 + r + 8) * n + i], xs[r + 8], a1);
-    }
-    for (; r < sb; r += 8) a0 = fma(A[(size_t)(k0 + r) * n + i], xs[r], a0);
-  }
-  part[q][lane] = a0 + a1;
-  __syncthreads();
-  if (q == 0 && i < k0) {
-    double s = 0.0;
+      __syncthreads();
+      {
+        const double2* ga = reinterpret_cast<const double2*>(p.tiles + (size_t)ia * TT);
+        const double2* gb = reinterpret_cast<const double2*>(p.tiles + (size_t)ib * TT);
+        double2* sa = reinterpret_cast<double2*>(As);
+        double2* sb = reinterpret_cast<double2*>(Bs);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) s += part[k][lane];
-    y[i] -= s;
+        for (int e = 0; e < TT / 2 / 256; ++e) {
+          sa[threadIdx.x + 256 * e] = __ldcg(ga + threadIdx.x + 256 * e);
+          sb[threadIdx.x + 256 * e] = __ldcg(gb + threadIdx.x + 256 * e);
+        }
+      }
+      __syncthreads();
+#pragma unroll 4
+      for (int kk = 0; kk < T; ++kk) {
+        const double2 a01 = *reinterpret_cast<const double2*>(As + kk * T + 4 * ty);
+        const double2 a23 = *reinterpret_cast<const double2*>(As + kk * T + 4 * ty + 2);
+        const double av[4] = {a01.x, a01.y, a23.x, a23.y};
+        const double bv[4] = {Bs[kk * T + tx], Bs[kk * T + tx + 16], Bs[kk * T + tx + 32], Bs[kk * T + tx + 48]};
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+#pragma unroll
+          for (int a = 0; a < 4; ++a) acc[b][a] = fma(-av[a], bv[b], acc[b][a]);
+      }
+      __syncthreads();
+    }
+    // the updated block, column-major, into As
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      *reinterpret_cast<double2*>(As + (tx + 16 * b) * T + 4 * ty) = make_double2(acc[b][0], acc[b][1]);
+      *reinterpret_cast<double2*>(As + (tx + 16 * b) * T + 4 * ty + 2) = make_double2(acc[b][2], acc[b][3]);
+    }
+    if (i == j) {
+      __syncthreads();
+      factor_block(As, tile, p.dinv + T * j, T * j, p.info, colbuf);
+    } else {
+      const int id = tile_id(j, j, ntc);
+      if (threadIdx.x == 0) wait_flag(p.flags + id);
+      __syncthreads();
+      {
+        const double2* gb = reinterpret_cast<const double2*>(p.tiles + (size_t)id * TT);
+        double2* sb = reinterpret_cast<double2*>(Bs);
+#pragma unroll
+        for (int e = 0; e < TT / 2 / 256; ++e) sb[threadIdx.x + 256 * e] = __ldcg(gb + threadIdx.x + 256 * e);
+        if (threadIdx.x < T) di[threadIdx.x] = __ldcg(p.dinv + T * j + threadIdx.x);
+      }
+      __syncthreads();
+      // X L^T = A: row r of X by thread r, x_c = (a_c - sum_{m<c} x_m L[c][m]) / L[c][c]; the running row in
+      // registers, L[c][m] = Bs[m * 64 + c] read as a broadcast; four chains per sum
+      if (threadIdx.x < T) {
+        const int r = threadIdx.x;
+        double x[T];
+#pragma unroll
+        for (int c = 0; c < T; ++c) x[c] = As[c * T + r];
+#pragma unroll
+        for (int c = 0; c < T; ++c) {
+          double s0 = x[c], s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+          for (int m = 0; m < c; ++m) {
+            if ((m & 3) == 0) s0 = fma(-x[m], Bs[m * T + c], s0);
+            else if ((m & 3) == 1) s1 = fma(-x[m], Bs[m * T + c], s1);
+            else if ((m & 3) == 2) s2 = fma(-x[m], Bs[m * T + c], s2);
+            else s3 = fma(-x[m], Bs[m * T + c], s3);
+          }
+          x[c] = ((s0 + s1) + (s2 + s3)) * di[c];
+        }
+#pragma unroll
+        for (int c = 0; c < T; ++c) tile[c * T + r] = x[c];
+      }
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) st_release(p.flags + tile_id(i, j, ntc), 1);
   }
 }
 
-__global__ void widen_kernel(const float* __restrict__ S, const float* __restrict__ g, int n, double* __restrict__ A) {
-  const int r = blockIdx.y;
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= n) return;
-  const size_t idx = (size_t)r * n + c;
-  A[idx] = (r == n) ? -(double)g[c] : ((c <= r) ? (double)S[idx] : 0.0);
+// grid = 1 diagonal CTA (block 0) + ntc column CTAs, all co-resident (ntc + 1 <= SM count is required).
+__global__ void __launch_bounds__(256, 1) spd_backsolve_kernel(SpdPlan p) {
+  const int ntc = p.ntc, nsb = (ntc + SBT - 1) / SBT;
+  int* ycol_ready = p.sync + 1;
+  int* x_ready = p.sync + 1 + ntc;
+  __shared__ double ys[SBT * T];
+  __shared__ double xs[SBT * T];
+  if (blockIdx.x > 0) {
+    // ---- column CTA c: y_c -= L(tr, c)^T x_tr for every tile row tr of every super-block below its own
+    const int c = blockIdx.x - 1, mysb = c / SBT;
+    const double* rhs = p.tiles + (size_t)tile_id(ntc, c, ntc) * TT;       // row 0 of the rhs tile: element (0, col) at col * 64
+    if (threadIdx.x < T) ys[threadIdx.x] = rhs[threadIdx.x * T];
+    const int col = threadIdx.x >> 2, part = threadIdx.x & 3;
+    for (int sb = nsb - 1; sb > mysb; --sb) {
+      if (threadIdx.x == 0) wait_flag(x_ready + sb);
+      __syncthreads();
+      const int tr0 = sb * SBT, ntr = min(SBT, ntc - tr0);
+      for (int e = threadIdx.x; e < ntr * T; e += blockDim.x) xs[e] = __ldcg(p.xbuf + T * tr0 + e);
+      __syncthreads();
+      double s = 0.0;
+      for (int q = 0; q < ntr; ++q) {
+        const double* Lt = p.tiles + (size_t)tile_id(tr0 + q, c, ntc) * TT + col * T + part * 16;
+        const double* xv = xs + q * T + part * 16;
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+        for (int r = 0; r < 16; r += 4) {
+          const double2 l01 = __ldcg(reinterpret_cast<const double2*>(Lt + r));
+          const double2 l23 = __ldcg(reinterpret_cast<const double2*>(Lt + r + 2));
+          s0 = fma(l01.x, xv[r], s0); s1 = fma(l01.y, xv[r + 1], s1);
+          s0 = fma(l23.x, xv[r + 2], s0); s1 = fma(l23.y, xv[r + 3], s1);
+        }
+        s += s0 + s1;
+      }
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      if (part == 0) ys[col] -= s;
+      __syncthreads();
+    }
+    if (threadIdx.x < T) p.ybuf[T * c + threadIdx.x] = ys[threadIdx.x];
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) st_release(ycol_ready + c, 1);
+    return;
+  }
+  // ---- diagonal CTA: the super-blocks from the bottom up
+  for (int sb = nsb - 1; sb >= 0; --sb) {
+    const int c0 = sb * SBT, nc = min(SBT, ntc - c0);
+    if ((int)threadIdx.x < nc) {
+      wait_flag(ycol_ready + c0 + threadIdx.x);
+      wait_flag(p.flags + p.ntasks + c0 + threadIdx.x);          // (set by the factorisation kernel, long since)
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < nc * T; e += blockDim.x) ys[e] = __ldcg(p.ybuf + T * c0 + e);
+    const int col = threadIdx.x >> 2, part = threadIdx.x & 3;
+    for (int cc = nc - 1; cc >= 0; --cc) {
+      const int c = c0 + cc;
+      __syncthreads();
+      // x_c = L(c,c)^-T v: x_j = sum_{i >= j} (L^-1)[i][j] v_i, four lanes per unknown, the inverse read straight from
+      // L2 (column j of the tile is contiguous)
+      {
+        const double* Li = p.inv + (size_t)c * TT + col * T;
+        const double* v = ys + cc * T;
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+        for (int m = 0; m < 16; m += 2) {
+          s0 = fma(__ldcg(Li + part + 4 * m), v[part + 4 * m], s0);
+          s1 = fma(__ldcg(Li + part + 4 * m + 4), v[part + 4 * m + 4], s1);
+        }
+        double sx = s0 + s1;
+        sx += __shfl_xor_sync(0xffffffffu, sx, 1);
+        sx += __shfl_xor_sync(0xffffffffu, sx, 2);
+        if (part == 0) xs[cc * T + col] = sx;
+      }
+      __syncthreads();
+      // earlier columns of this super-block: y_{c'} -= L(c, c')^T x_c
+      const double* xo = xs + cc * T;
+      for (int cp = 0; cp < cc; ++cp) {
+        const double* Lt = p.tiles + (size_t)tile_id(c, c0 + cp, ntc) * TT + col * T;
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+        for (int m = 0; m < 16; m += 2) {
+          s0 = fma(__ldcg(Lt + part + 4 * m), xo[part + 4 * m], s0);
+          s1 = fma(__ldcg(Lt + part + 4 * m + 4), xo[part + 4 * m + 4], s1);
+        }
+        double sy = s0 + s1;
+        sy += __shfl_xor_sync(0xffffffffu, sy, 1);
+        sy += __shfl_xor_sync(0xffffffffu, sy, 2);
+        if (part == 0) ys[cp * T + col] -= sy;
+      }
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < nc * T; e += blockDim.x) p.xbuf[T * c0 + e] = xs[e];
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) st_release(x_ready + sb, 1);
+  }
+}
+
+__global__ void spd_copy_x_kernel(const double* __restrict__ xbuf, int n, double* __restrict__ x) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) x[i] = xbuf[i];
+}
+
+static SpdPlan make_plan(int n, double* A, int* info) {
+  SpdPlan p;
+  p.n = n;
+  p.ntc = div_up(n, T);
+  p.ntasks = p.ntc * (p.ntc + 1) / 2 + p.ntc;
+  const size_t ntiles = (size_t)p.ntasks;
+  p.tiles = A;
+  p.inv = A + ntiles * TT;
+  p.dinv = p.inv + (size_t)p.ntc * TT;
+  p.ybuf = p.dinv + (size_t)p.ntc * T;
+  p.xbuf = p.ybuf + (size_t)p.ntc * T;
+  p.flags = reinterpret_cast<int*>(p.xbuf + (size_t)p.ntc * T);
+  p.sync = p.flags + ntiles + p.ntc;
+  p.info = info;
+  return p;
 }
 
 }  // namespace
 
 size_t sfm_spd_scratch_doubles(int n) {
-  return ((size_t)n + 1) * n + (size_t)div_up(n, NB) * NB;
+  const size_t ntc = (size_t)div_up(n, T);
+  const size_t ntiles = ntc * (ntc + 1) / 2 + ntc;
+  const size_t ints = ntiles + ntc + 1 + ntc + (ntc + SBT - 1) / SBT + 16;
+  return (ntiles + ntc) * TT + 3 * ntc * T + (ints + 1) / 2;
 }
 
 int sfm_spd_solve(sfm_ctx* ctx, const float* S, const float* g, int n, double* A, double* x, int* info) {
-  const size_t total = (size_t)(n + 1) * n;
-  double* dinv = A + total;
-  SFM_LAUNCH(ctx, SFM_K_BA_SOLVE, (widen_kernel<<<dim3(div_up(n, 256), n + 1), 256, 0, ctx->stream>>>(S, g, n, A)));
+  SpdPlan p = make_plan(n, A, info);
+  SFM_REQUIRE(p.ntc + 1 <= ctx->sm_count, "sfm_spd_solve: %d unknowns need %d co-resident CTAs, the device has %d SMs", n,
+              p.ntc + 1, ctx->sm_count);
+  const size_t nints = (size_t)p.ntasks + p.ntc + 1 + p.ntc + (p.ntc + SBT - 1) / SBT;
+  SFM_CUDA(cudaMemsetAsync(p.flags, 0, nints * sizeof(int), ctx->stream));
   SFM_CUDA(cudaMemsetAsync(info, 0, sizeof(int), ctx->stream));
-  SFM_LAUNCH(ctx, SFM_K_BA_SOLVE, (chol_diag_kernel<<<1, 256, 0, ctx->stream>>>(A, n, 0, dinv, info)));
-  for (int k0 = 0; k0 < n; k0 += NB) {
-    const int nb = std::min(NB, n - k0);
-    const int rows_below = n + 1 - (k0 + nb);                 // >= 1: the rhs row
-    SFM_LAUNCH(ctx, SFM_K_BA_SOLVE, (chol_panel_kernel<<<div_up(rows_below, PANEL_THREADS), PANEL_THREADS, 0, ctx->stream>>>(A, n, k0, dinv)));
-    const int cols = n - (k0 + nb);
-    if (cols > 0) {
-      const int tiles = div_up(rows_below, 64);
-      SFM_LAUNCH(ctx, SFM_K_BA_SOLVE, (chol_syrk_kernel<<<tiles * (tiles + 1) / 2, 256, 0, ctx->stream>>>(A, n, k0, nb, dinv, info)));
-    }
+  SFM_LAUNCH(ctx, SFM_K_BA_SOLVE, (spd_pack_kernel<<<p.ntasks, 256, 0, ctx->stream>>>(S, g, p)));
+  static bool attr_set = false;
+  if (!attr_set) {
+    SFM_CUDA(cudaFuncSetAttribute(spd_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FACTOR_SMEM));
+    attr_set = true;
   }
-  double* y = A + (size_t)n * n;
-  for (int k0 = ((n - 1) / SB) * SB; k0 >= 0; k0 -= SB) {
-    const int sb = std::min(SB, n - k0);
-    SFM_LAUNCH(ctx, SFM_K_BA_SOLVE, (back_diag_kernel<<<1, 256, 0, ctx->stream>>>(A, n, k0, sb, dinv, y, x)));
-    if (k0 > 0)
-      SFM_LAUNCH(ctx, SFM_K_BA_SOLVE, (back_update_kernel<<<div_up(k0, 32), 256, 0, ctx->stream>>>(A, n, k0, sb, x, y)));
-  }
+  const int grid = std::min(ctx->sm_count, p.ntasks + p.ntc);
+  SFM_LAUNCH(ctx, SFM_K_BA_SOLVE, (spd_factor_kernel<<<grid, 256, FACTOR_SMEM, ctx->stream>>>(p)));
+  SFM_LAUNCH(ctx, SFM_K_BA_SOLVE, (spd_backsolve_kernel<<<p.ntc + 1, 256, 0, ctx->stream>>>(p)));
+  SFM_LAUNCH(ctx, SFM_K_BA_SOLVE, (spd_copy_x_kernel<<<div_up(n, 256), 256, 0, ctx->stream>>>(p.xbuf, n, x)));
   return SFM_OK;
 }
