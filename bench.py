@@ -30,6 +30,12 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+def log(msg):
+    """Progress on stderr (stdout carries the one JSON line)."""
+    if os.environ.get("RANK", "0") == "0":
+        print(f"[bench {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -44,6 +50,8 @@ def parse():
     ap.add_argument("--ba-points", type=int, default=100_000)
     ap.add_argument("--ba-obs-per-point", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-match-sweep", action="store_true")
+    ap.add_argument("--sweep-views", type=int, default=64, help="views of the all-pairs matching workload (isfm.py:68-87)")
     return ap.parse_args()
 
 
@@ -266,6 +274,7 @@ def run_engine(args):
         ms = e0.elapsed_time(e1)
         return max_over_ranks(ms), wall, ctx.launch_count() - l0, d2h
 
+    log(f"scene ready: {V} views x {n} descriptors, world {world}")
     for _ in range(args.warmup):
         outs, _ = step(kp_dev, des_dev, False)
     with ClockSampler(local) as cs:
@@ -277,6 +286,7 @@ def run_engine(args):
     ms_e2e, _, _, d2h_bytes = timed(kp_host, des_host, True, args.steps)
     e2e = world * registered * args.steps / (ms_e2e * 1e-3)
 
+    log(f"registration timed: {value:.0f} views/s resident, {e2e:.0f} end to end")
     # ---- per-kernel device time (CUDA events around every launch, same K steps) and the roofline
     ctx.set_profiling(True)
     ctx.reset_profile()
@@ -343,6 +353,11 @@ def run_engine(args):
                                 "survivors": int(init["n_pose"]), "cpu_ms": None,
                                 "what": "findEssentialMat(RANSAC, 0.999, 0.4) + recoverPose, host arrays in / out"}
 
+    # ---- descriptor-match sweep (configs[4]) and pair-sharded all-pairs matching (isfm.py:68-87) over the ranks
+    if not args.no_match_sweep:
+        out["match_sweep"] = bench_match(args, ctx, world, rank, pk, barrier, max_over_ranks)
+        log("match sweep done")
+
     # ---- BA: GN iterations / s (configs[3]); points sharded over ranks, NCCL all-reduce of the reduced system
     if not args.no_ba:
         out["ba"] = bench_ba(args, ctx, world, rank, pk, barrier, max_over_ranks)
@@ -365,10 +380,95 @@ def run_engine(args):
             out["two_view_init"]["cpu_ms"] = (time.perf_counter() - t0) / 3 * 1e3
     elif rank == 0:
         out["cpu_baseline"] = None
+    log("done")
     if rank == 0:
-        print(json.dumps(out))
+        print(json.dumps(out), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
+
+
+def bench_match(args, ctx, world, rank, pk, barrier, max_over_ranks):
+    """BASELINE configs[4]: (a) one pair of n x n 128-D descriptors, n = 1k .. 64k, on one GPU: time of the public
+    match call (K1 + K1c, outputs left in HBM), useful TFLOP/s = 2 n^2 128 / t and the operand bytes per second;
+    (b) weak scaling over pairs — the all-previous-views pair list of isfm.py:68-87 for `--sweep-views` views of the
+    synthetic scene split over the ranks by sharding.shard_pairs, every rank prepares the views and matches its shard
+    in one batched launch, counts all-reduced (NCCL), matches stay resident; (c) strong scaling — one 64k x 64k pair
+    split by query rows over the ranks.  All times are CUDA-event times on the engine stream, max over ranks."""
+    import torch
+    import torch.distributed as dist
+
+    from sfm_mvs_b200 import pipeline, sharding, synth
+
+    ts, dev = ctx.torch_stream(), ctx.torch_device
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(1234)
+
+    def rand_desc(n):            # integer-valued float32 with SIFT's norm (|d| ~ 512), identical on every rank
+        return torch.randint(0, 80, (n, 128), device=dev, generator=gen, dtype=torch.int32).to(torch.float32)
+
+    def timed_ms(fn, reps):
+        barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(ts)
+        for _ in range(reps):
+            fn()
+        e1.record(ts)
+        torch.cuda.synchronize()
+        return max_over_ranks(e0.elapsed_time(e1)) / reps
+
+    res = {}
+    with torch.cuda.stream(ts):
+        # (a) single pair, this GPU
+        single = []
+        for n in (1024, 2048, 4096, 8192, 16384, 32768, 65536):
+            q, t = rand_desc(n), rand_desc(n)
+            dq, dt = ctx.descriptors(q), ctx.descriptors(t)
+            assert dq.exact and dt.exact
+            call = lambda: ctx.knn2(dq, dt, 0.70, device_out=True)
+            for _ in range(3):
+                call()
+            ms = timed_ms(call, 10 if n <= 16384 else 4)
+            tf = 2.0 * n * n * 128 / (ms * 1e-3) / 1e12
+            single.append({"n": n, "ms": ms, "tflops": tf, "frac_of_burst_bf16_peak": tf / pk["bf16"],
+                           "operand_gbs": 2 * n * 160 * 2 / (ms * 1e-3) / 1e9})
+            del dq, dt, q, t
+        res["single_pair"] = single
+        # (b) all pairs of V views, sharded over the ranks
+        V = args.sweep_views
+        scene = synth.orbit_scene(V, args.desc, seed=0)
+        kps = [torch.from_numpy(v["kp"]).to(dev) for v in scene["views"]]
+        dess = [torch.from_numpy(v["des"]).to(dev) for v in scene["views"]]
+        pairs = sharding.all_pairs(V)
+        state = {}
+
+        def all_pairs_step():
+            views = pipeline.DeviceView.batch(ctx, kps, dess)
+            state["out"] = pipeline.match_pairs_sharded(ctx, views, pairs, rank, world, dist=dist if world > 1 else None)
+
+        for _ in range(2):
+            all_pairs_step()
+        ms = timed_ms(all_pairs_step, 3)
+        mine, matches, counts = state["out"]
+        res["all_pairs"] = {"views": V, "desc": args.desc, "pairs": len(pairs), "pairs_this_rank": len(mine), "ms": ms,
+                            "pairs_per_s": len(pairs) / (ms * 1e-3), "tflops": 2.0 * args.desc ** 2 * 128 * len(pairs) / (ms * 1e-3) / 1e12,
+                            "survivors_total": int(counts.sum().item()), "scaling": "strong (fixed pair list split over the ranks)",
+                            "exchange": "per-pair survivor counts all-reduced (int32 x pairs); matches stay on the owning GPU"}
+        state.clear()
+        del matches
+        # (c) one large pair split by query rows
+        n = 65536
+        q, t = rand_desc(n), rand_desc(n)
+        split = lambda: state.__setitem__("r", pipeline.match_rows_split(ctx, q, t, rank, world))
+        for _ in range(2):
+            split()
+        ms = timed_ms(split, 3)
+        lo, hi = state["r"]["lo"], state["r"]["hi"]
+        res["row_split"] = {"n": n, "rows_this_rank": hi - lo, "ms": ms, "tflops": 2.0 * n * n * 128 / (ms * 1e-3) / 1e12,
+                            "includes": "descriptor preparation (K1b) of this rank's query rows and of the train set",
+                            "scaling": "strong (query rows split over the ranks, no collective)"}
+    return res
 
 
 def bench_ba(args, ctx, world, rank, pk, barrier, max_over_ranks):

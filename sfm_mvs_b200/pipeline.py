@@ -32,6 +32,18 @@ def _on_ctx_stream(fn):
     return wrapper
 
 
+def _on_ctx_stream_fn(fn):
+    """The same for a function whose first argument is the context."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(ctx, *a, **k):
+        import torch
+        with torch.cuda.stream(ctx.torch_stream()):
+            return fn(ctx, *a, **k)
+    return wrapper
+
+
 class DeviceView:
     """A view's keypoints and prepared descriptors resident in HBM."""
 
@@ -63,7 +75,20 @@ VIEW_OUT = np.dtype([("Rt", np.float64, (12,)), ("err_pnp", np.float64), ("err_n
 
 
 class PairMatches:
-    __slots__ = ("pts_q", "pts_t", "qidx", "tidx", "n_dev", "n")
+    """The surviving matches of one pair: row range [lo, hi) of the batch's output slabs (views are cut on demand —
+    thousands of pairs come out of one launch and most callers only need the pointers)."""
+    __slots__ = ("_slabs", "lo", "hi", "k", "n")
+
+    def __init__(self, slabs, lo, hi, k, n):
+        self._slabs, self.lo, self.hi, self.k, self.n = slabs, lo, hi, k, n
+
+    pts_q = property(lambda self: self._slabs[0][self.lo:self.hi])
+    pts_t = property(lambda self: self._slabs[1][self.lo:self.hi])
+    qidx = property(lambda self: self._slabs[2][self.lo:self.hi])
+    tidx = property(lambda self: self._slabs[3][self.lo:self.hi])
+    n_dev = property(lambda self: self._slabs[4][self.k:self.k + 1])
+    ptr_q = property(lambda self: self._slabs[0].data_ptr() + 8 * self.lo)
+    ptr_t = property(lambda self: self._slabs[1].data_ptr() + 8 * self.lo)
 
 
 class RegistrationChain:
@@ -85,7 +110,7 @@ class RegistrationChain:
         n = len(pairs)
         if n == 0:
             return []
-        nq = np.array([views[a].n for a, _ in pairs], np.int64)
+        nq = np.array([v.n for v in views], np.int64)[[a for a, _ in pairs]]
         off = np.concatenate([[0], np.cumsum(nq)])
         tot = int(max(off[-1], 1))
         counts = torch.empty((n,), dtype=torch.int32, device=self.dev)
@@ -97,26 +122,22 @@ class RegistrationChain:
         def ptrs(base, stride):
             return np.ascontiguousarray(base + off[:-1] * stride, np.uint64)
 
-        hq = np.array([views[a].desc._h.value if hasattr(views[a].desc._h, "value") else views[a].desc._h for a, _ in pairs], np.uint64)
-        ht = np.array([views[b].desc._h.value if hasattr(views[b].desc._h, "value") else views[b].desc._h for _, b in pairs], np.uint64)
-        kq = np.array([views[a].kp.data_ptr() for a, _ in pairs], np.uint64)
-        kt = np.array([views[b].kp.data_ptr() for _, b in pairs], np.uint64)
+        # per-view handles and pointers once, then indexed by the pair list
+        hv = np.array([v.desc._h.value if hasattr(v.desc._h, "value") else v.desc._h for v in views], np.uint64)
+        kv = np.array([v.kp.data_ptr() for v in views], np.uint64)
+        pa = np.array([a for a, _ in pairs], np.int64)
+        pb = np.array([b for _, b in pairs], np.int64)
+        hq, ht, kq, kt = (np.ascontiguousarray(x) for x in (hv[pa], hv[pb], kv[pa], kv[pb]))
         a_pq, a_pt = ptrs(pts_q.data_ptr(), 8), ptrs(pts_t.data_ptr(), 8)
         a_qi, a_ti = ptrs(qidx.data_ptr(), 4), ptrs(tidx.data_ptr(), 4)
         check(lib.sfm_desc_match_gather_batched(self.ctx._h, n, hq.ctypes.data, ht.ctypes.data, self.ratio, kq.ctypes.data,
                                                 kt.ctypes.data, None, None, a_pq.ctypes.data, a_pt.ctypes.data,
                                                 a_qi.ctypes.data, a_ti.ctypes.data, counts.data_ptr()))
         self.ctx.sync()
-        host = counts.cpu().numpy()
-        out = []
-        for k in range(n):
-            pm = PairMatches()
-            lo, hi = int(off[k]), int(off[k + 1])
-            pm.pts_q, pm.pts_t, pm.qidx, pm.tidx = pts_q[lo:hi], pts_t[lo:hi], qidx[lo:hi], tidx[lo:hi]
-            pm.n_dev = counts[k:k + 1]
-            pm.n = int(host[k])
-            out.append(pm)
-        return out
+        host = counts.cpu().numpy().tolist()
+        slabs = (pts_q, pts_t, qidx, tidx, counts)
+        offs = off.tolist()
+        return [PairMatches(slabs, offs[k], offs[k + 1], k, host[k]) for k in range(n)]
 
     # ------------------------------------------------------------------ geometry helpers (device buffers)
     def _triangulate(self, P1, P2, x1, x2, n, out_layout):
@@ -284,8 +305,8 @@ class NativeChain:
         off = np.concatenate([[0], np.cumsum(cap)])
         with torch.cuda.stream(self.ctx.torch_stream()):
             X_all = torch.empty((int(max(off[-1], 1)), 3), dtype=torch.float32, device=self.ctx.torch_device)
-        pq = np.array([pm.pts_q.data_ptr() for pm in matches], np.uint64)
-        pt = np.array([pm.pts_t.data_ptr() for pm in matches], np.uint64)
+        pq = np.array([pm.ptr_q for pm in matches], np.uint64)
+        pt = np.array([pm.ptr_t for pm in matches], np.uint64)
         xn = np.ascontiguousarray(X_all.data_ptr() + off[:-1] * 12, np.uint64)
         check(lib.sfm_chain_extend_async(self._h, n_pairs, pq.ctypes.data, pt.ctypes.data, n.ctypes.data, xn.ctypes.data))
         self._alive = [matches[-1], X_all]
@@ -545,8 +566,8 @@ def pairwise_init(ctx: _e.Context, views, K, pairs=None, ratio: float = 0.70, ba
         import torch
         P = len(matches)
         n = np.array([pm.n for pm in matches], np.int32)
-        a1 = np.array([pm.pts_q.data_ptr() for pm in matches], np.uint64)
-        a2 = np.array([pm.pts_t.data_ptr() for pm in matches], np.uint64)
+        a1 = np.array([pm.ptr_q for pm in matches], np.uint64)
+        a2 = np.array([pm.ptr_t for pm in matches], np.uint64)
         with torch.cuda.stream(ctx.torch_stream()):
             mask_all = torch.zeros((int(max(n.sum(), 1)),), dtype=torch.uint8, device=ctx.torch_device)
         off = np.concatenate([[0], np.cumsum(n)]).astype(np.int64)
@@ -580,3 +601,34 @@ def pairwise_init(ctx: _e.Context, views, K, pairs=None, ratio: float = 0.70, ba
                 pass                      # no essential matrix for this pair (the reference would raise on E = None)
         out.append(rec)
     return out
+
+
+def match_pairs_sharded(ctx: _e.Context, views, pairs, rank: int = 0, world: int = 1, ratio: float = 0.70, dist=None):
+    """isfm.py:68-87's matching over `world` GPUs (one process per GPU): the pair list is split by
+    sharding.shard_pairs (longest-processing-time-first on Nq * Nt), this rank matches its shard in ONE batched K1
+    launch, the matches stay resident here and the per-pair survivor counts are all-reduced so that every rank knows
+    them.  No other data-path collective.  `views` are DeviceView on this rank's context (every rank holds the
+    descriptors of the views its pairs touch).  -> (my pair indices, their PairMatches, counts of all pairs)."""
+    from . import sharding
+    costs = [views[a].n * views[b].n for a, b in pairs]
+    mine = sharding.shard_pairs(pairs, costs, world)[rank]
+    chain = RegistrationChain(ctx, np.eye(3), ratio=ratio)
+    matches = chain.match_pairs(views, [pairs[k] for k in mine])
+    counts = sharding.gather_pair_counts([pm.n for pm in matches], mine, len(pairs), dist=dist, device=ctx.torch_device)
+    return mine, matches, counts
+
+
+@_on_ctx_stream_fn
+def match_rows_split(ctx: _e.Context, q_des, t_des, rank: int = 0, world: int = 1, ratio: float = 0.70):
+    """One large pair split by QUERY rows over `world` GPUs (BASELINE configs[4], strong scaling): a query row's two
+    nearest train rows do not depend on the other query rows, so rank r matches rows [lo, hi) of q_des (CUDA tensor
+    (nq,128)) against the whole of t_des and keeps its block of the result; no collective.
+    -> dict(lo, hi, idx (hi-lo,2), dist, good, n_good) with device tensors."""
+    from . import sharding
+    lo, hi = sharding.split_rows(int(q_des.shape[0]), world)[rank]
+    if hi <= lo:
+        return dict(lo=lo, hi=hi, idx=None, dist=None, good=None, n_good=0, q=None, t=None)
+    dq = ctx.descriptors(q_des[lo:hi])
+    dt = ctx.descriptors(t_des)
+    idx, dist_, good, ng = ctx.knn2(dq, dt, ratio, device_out=True)
+    return dict(lo=lo, hi=hi, idx=idx, dist=dist_, good=good, n_good=ng, q=dq, t=dt)

@@ -50,3 +50,36 @@ def ba_shard(problem: dict, rank: int, world: int) -> dict:
     return dict(K=problem["K"], cams0=problem["cams0"], pts0=problem["pts0"][p_lo:p_hi],
                 cam_idx=problem["cam_idx"][o_lo:o_hi], pt_idx=problem["pt_idx"][o_lo:o_hi] - p_lo,
                 obs=problem["obs"][o_lo:o_hi], p_lo=p_lo, p_hi=p_hi, totals=(n_pt, len(problem["pt_idx"])))
+
+
+def all_pairs(n_views: int):
+    """The pair list of isfm.py:68-87 in the reference's order: for every view i, every earlier view j."""
+    return [(j, i) for i in range(n_views) for j in range(i)]
+
+
+def split_rows(n_rows: int, world: int, align: int = 128):
+    """One big pair split by query rows (BASELINE configs[4], strong scaling): contiguous row ranges, boundaries
+    aligned to the matcher's 128-row query tile.  Returns [(lo, hi)] per rank (possibly empty ranges)."""
+    tiles = (n_rows + align - 1) // align
+    out = []
+    for r in range(world):
+        lo = min(n_rows, (tiles * r // world) * align)
+        hi = min(n_rows, (tiles * (r + 1) // world) * align)
+        out.append((lo, hi))
+    return out
+
+
+def gather_pair_counts(local_counts, my_pairs, n_pairs: int, dist=None, device=None):
+    """Survivor counts of ALL pairs on every rank.  The matches themselves stay resident on the rank that computed
+    them (nothing later in isfm.py needs them elsewhere: the essential matrix of a pair is estimated where its
+    matches are); only the per-pair counts — what isfm.py:86 prints — are exchanged: each rank writes its counts into
+    a zero vector at its pairs' slots and the vectors are summed (one all-reduce of n_pairs int32, NCCL on the GPUs,
+    gloo in the CPU tests).  dist: torch.distributed or None for a single rank."""
+    import torch
+    buf = torch.zeros((n_pairs,), dtype=torch.int32, device=device)
+    if len(my_pairs):
+        idx = torch.as_tensor(list(my_pairs), dtype=torch.long, device=device)
+        buf[idx] = torch.as_tensor(local_counts, dtype=torch.int32, device=device)
+    if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(buf)
+    return buf

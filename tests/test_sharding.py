@@ -93,3 +93,49 @@ def test_allreduced_partial_systems_equal_full_system_gloo():
         assert np.allclose(S_sum, S_full, rtol=1e-10, atol=1e-8)
         assert np.allclose(g_sum, g0, rtol=1e-10, atol=1e-8)
         assert abs(cost - 0.5 * float((r ** 2).sum())) < 1e-8
+
+
+def test_split_rows_covers_and_aligns():
+    for n in (0, 1, 127, 128, 5000, 65536):
+        for world in (1, 2, 3, 8):
+            parts = sharding.split_rows(n, world)
+            assert parts[0][0] == 0 and parts[-1][1] == n
+            for (a, b), (c, d) in zip(parts[:-1], parts[1:]):
+                assert b == c and a <= b and b % 128 == 0
+    assert sharding.all_pairs(4) == [(0, 1), (0, 2), (1, 2), (0, 3), (1, 3), (2, 3)]      # isfm.py:68-87 order
+
+
+def _pairs_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n = np.random.default_rng(0).integers(1000, 6000, 9)
+    pairs = sharding.all_pairs(9)
+    mine = sharding.shard_pairs(pairs, [n[a] * n[b] for a, b in pairs], world)[rank]
+    local = [int(n[pairs[k][0]] % 97 + n[pairs[k][1]] % 89) for k in mine]        # stands in for the survivor counts
+    counts = sharding.gather_pair_counts(local, mine, len(pairs), dist=dist)
+    q.put((rank, mine, counts.numpy().copy()))
+    dist.destroy_process_group()
+
+
+def test_pair_sharded_counts_are_complete_on_every_rank_gloo():
+    """The multi-GPU matching path (pipeline.match_pairs_sharded) on two CPU ranks: disjoint shards covering the pair
+    list, and after the one all-reduce every rank holds the count of every pair."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_pairs_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(2)], key=lambda x: x[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    n = np.random.default_rng(0).integers(1000, 6000, 9)
+    pairs = sharding.all_pairs(9)
+    want = np.array([int(n[a] % 97 + n[b] % 89) for a, b in pairs], np.int32)
+    assert sorted(res[0][1] + res[1][1]) == list(range(len(pairs))) and not set(res[0][1]) & set(res[1][1])
+    for _, _, counts in res:
+        assert np.array_equal(counts, want)
