@@ -133,7 +133,10 @@ __global__ void __launch_bounds__(96) pnp_epnp_kernel(const float* __restrict__ 
       else sh.rho[e - 60] = hm::epnp_rho_entry(reinterpret_cast<const double(*)[3]>(sh.cws), e - 60);
     }
   }
-  __syncthreads();
+  // lane 0 of warp 0 comes out of long serial sections: the warps (and the lanes of a warp) reach this point far
+  // apart, so the barrier is the non-aligned form, which does not require a warp to arrive converged
+  __syncwarp();
+  asm volatile("barrier.sync 0;" ::: "memory");
   tick(4);
   {
     // warp = beta initialisation: least squares on nc columns of L by SVD (cv::solve DECOMP_SVD)
@@ -171,7 +174,8 @@ __global__ void __launch_bounds__(96) pnp_epnp_kernel(const float* __restrict__ 
       if (dbg && h == 0) dbg[26 + warp] = clock64();
     }
   }
-  __syncthreads();
+  __syncwarp();
+  asm volatile("barrier.sync 0;" ::: "memory");
   tick(5);
   if (tid == 0) {
     const double errs[3] = {sh.cand[0].err, sh.cand[1].err, sh.cand[2].err};

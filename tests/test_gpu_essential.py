@@ -163,9 +163,6 @@ def test_find_essential_mat_parameter_variants(engine, n, seed, prob, thr, max_i
     assert (got["iters"], got["best_iter"], got["inliers"]) == (info["iters"], info["best_iter"], info["best_count"])
 
 
-@pytest.mark.skipif(os.environ.get("SFM_TEST_EXPERIMENTAL") != "1",
-                    reason="sfm_find_essential_mat_batched was written after the round's GPU budget was spent; "
-                           "set SFM_TEST_EXPERIMENTAL=1 to run it")
 def test_find_essential_mat_batched(engine):
     """All pairs' essential matrices in a few launches: the same records as one call per pair."""
     from sfm_mvs_b200 import pipeline
