@@ -562,7 +562,114 @@ def bench_ba(args, ctx, world, rank, pk, barrier, max_over_ranks):
                              "algorithmic_bytes_per_launch": 96.0 * O, "avg_launch_us": 1e6 * t_eval,
                              "l2_policy": "256 MB flush between timed launches", "peak_source": pk["source"]}}
     prob.close()
+    if world == 1:
+        res["fixture"] = bench_ba_fixture(ctx)
+        if not args.no_cpu_baseline:
+            res["cpu_comparators"] = bench_ba_cpu(ctx)
     return res
+
+
+def bench_ba_fixture(ctx):
+    """The reference's own reconstruction as a BA problem (57 cameras of pose.csv x 19 282 points of sparse.ply,
+    1 061 813 observations; tests/golden/gustav_scene.npz): LM from the perturbed start to convergence."""
+    import sfm_mvs_b200 as sfm
+    from sfm_mvs_b200 import synth
+    path = os.path.join(ROOT, "tests", "golden", "gustav_scene.npz")
+    if not os.path.isfile(path):
+        return None
+    g = np.load(path)
+    pb = synth.ba_problem_from_scene(g["K"], g["cams"], g["pts"])
+    prob = sfm.BAProblem(ctx, len(pb["cams0"]), len(pb["pts0"]), pb["cam_idx"], pb["pt_idx"], pb["obs"], pb["K"])
+    prob.set_params(pb["cams0"], pb["pts0"])
+    prob.solve(max_iters=3)
+    prob.set_params(pb["cams0"], pb["pts0"])
+    ctx.sync()
+    t0 = time.perf_counter()
+    hist = prob.solve(max_iters=30, ftol=1e-6)
+    ctx.sync()
+    dt = time.perf_counter() - t0
+    prob.close()
+    return {"workload": f"{len(pb['cams0'])} cams / {len(pb['pts0'])} points / {len(pb['obs'])} obs (pose.csv + sparse.ply of the reference)",
+            "iterations": len(hist), "seconds": dt, "iters_per_s": len(hist) / dt, "cost_first": hist[0]["cost_before"],
+            "cost_last": hist[-1]["cost_after"], "rms_px_last": float(np.sqrt(hist[-1]["cost_after"] / len(pb["obs"])))}
+
+
+def bench_ba_cpu(ctx):
+    """CPU arms beside the BA numbers: (a) the reference's BundleAdjustment (sfm.py:138-157, oracle port:
+    scipy TRF over a dense finite-difference Jacobian of a Python-loop residual) against the drop-in
+    sfm_mvs_b200.BundleAdjustment (same formulation, same optimiser, residual + Jacobian on the GPU) on the same
+    single-camera problems; (b) scipy's sparse TRF on the multi-camera formulation (notebook cell 6: jac_sparsity,
+    x_scale='jac', ftol=1e-4) against the engine's LM on the same small problem."""
+    from scipy.optimize import least_squares
+    from scipy.sparse import lil_matrix
+
+    import sfm_mvs_b200 as sfm
+    from oracle import cvpath
+    from sfm_mvs_b200 import synth
+    out = {"reference_BundleAdjustment": []}
+    K = synth.K_GUSTAV
+    for N in (50, 200):
+        rng = np.random.default_rng(N)
+        R, t = synth.orbit_pose(0.1)
+        Xw = np.c_[rng.uniform(-2, 2, N), rng.uniform(-1.5, 1.5, N), rng.uniform(5, 11, N)]
+        uv, _ = synth.project(K, R, t, Xw)
+        obs = (uv + rng.normal(0, 0.7, uv.shape)).astype(np.float32).T.copy()
+        X0 = (Xw + rng.normal(0, 0.03, Xw.shape)).astype(np.float32).reshape(N, 1, 3)
+        Rt0 = np.hstack([R, t])
+        sfm.BundleAdjustment(X0, obs, Rt0, K, 0.5, ctx=ctx)                      # warm-up
+        t0 = time.perf_counter()
+        Xe, pe, Rte = sfm.BundleAdjustment(X0, obs, Rt0, K, 0.5, ctx=ctx)
+        t_gpu = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        Xr, pr, Rtr = quiet(cvpath.BundleAdjustment, X0, obs, Rt0, K, 0.5)
+        t_cpu = time.perf_counter() - t0
+        out["reference_BundleAdjustment"].append({"N": N, "cpu_s": t_cpu, "engine_s": t_gpu, "speedup": t_cpu / t_gpu,
+                                                  "max_rel_dX": float(np.abs(Xe - Xr).max() / np.abs(Xr).max()),
+                                                  "max_abs_dRt": float(np.abs(Rte - Rtr).max())})
+    # (b) sparse TRF on [cams (rvec, tvec) | points], residual proj - obs
+    pb = synth.ba_problem(20, 2000, 5, seed=2)
+    C_, P_, O = 20, 2000, len(pb["obs"])
+    ci, pi = pb["cam_idx"], pb["pt_idx"]
+
+    Kb, obs64 = pb["K"], pb["obs"].astype(np.float64)
+
+    def fun(x):                      # notebook cells 3-5: rotate (Rodrigues' formula, vectorised) + project, residual proj - obs
+        cams, pts = x[:6 * C_].reshape(C_, 6), x[6 * C_:].reshape(P_, 3)
+        rv, X = cams[ci, :3], pts[pi]
+        th = np.linalg.norm(rv, axis=1)[:, None]
+        with np.errstate(invalid="ignore"):
+            v = np.nan_to_num(rv / th)
+        dot = np.sum(X * v, axis=1)[:, None]
+        Y = np.cos(th) * X + np.sin(th) * np.cross(v, X) + dot * (1 - np.cos(th)) * v + cams[ci, 3:]
+        uv = np.stack([Kb[0, 0] * Y[:, 0] / Y[:, 2] + Kb[0, 2], Kb[1, 1] * Y[:, 1] / Y[:, 2] + Kb[1, 2]], 1)
+        return (uv - obs64).ravel()
+
+    A = lil_matrix((2 * O, 6 * C_ + 3 * P_), dtype=int)
+    rows = np.arange(O)
+    for k in range(6):
+        A[2 * rows, 6 * ci + k] = 1
+        A[2 * rows + 1, 6 * ci + k] = 1
+    for k in range(3):
+        A[2 * rows, 6 * C_ + 3 * pi + k] = 1
+        A[2 * rows + 1, 6 * C_ + 3 * pi + k] = 1
+    x0 = np.hstack([pb["cams0"].ravel(), pb["pts0"].ravel()])
+    t0 = time.perf_counter()
+    sol = least_squares(fun, x0, jac_sparsity=A, x_scale="jac", ftol=1e-4, method="trf")
+    t_cpu = time.perf_counter() - t0
+    prob = sfm.BAProblem(ctx, C_, P_, ci, pi, pb["obs"], pb["K"])
+    prob.set_params(pb["cams0"], pb["pts0"])
+    prob.solve(max_iters=2)
+    prob.set_params(pb["cams0"], pb["pts0"])
+    ctx.sync()
+    t0 = time.perf_counter()
+    hist = prob.solve(max_iters=30, ftol=1e-4)
+    ctx.sync()
+    t_gpu = time.perf_counter() - t0
+    prob.close()
+    out["scipy_sparse_trf"] = {"workload": f"{C_} cams / {P_} points / {O} obs", "cpu_s": t_cpu, "cpu_nfev": int(sol.nfev),
+                               "cpu_cost": float(sol.cost), "engine_s": t_gpu, "engine_iters": len(hist),
+                               "engine_cost": hist[-1]["cost_after"], "speedup": t_cpu / t_gpu}
+    return out
 
 
 if __name__ == "__main__":

@@ -321,6 +321,13 @@ int sfm_ba_get_params(sfm_ba* ba, double* cams, double* pts);
  * sqrt(dx^2+dy^2)/n_obs, the residual of test.py:108-112 (r is then (n_obs,) and Jc/Jp NULL). */
 int sfm_ba_eval(sfm_ba* ba, int mode, float* r, float* Jc, float* Jp, double* cost);
 
+/* The reference's own single-camera formulation (sfm.py:104-157): x = [Rt 12 | K 9 | observed pixels (2,N) | points
+ * (N,3)], residual OptimReprojectionError(x) = ((p - proj)^2).ravel() / N in float64.  f0 (2N) receives the residual
+ * at x; J ((2N) x n_params, row-major; NULL to skip) the 2-point forward-difference Jacobian with
+ * scipy.optimize.least_squares' own steps — all 22 + 5N residual vectors in one launch.  cv2_compat.BundleAdjustment
+ * hands both to the reference's optimiser (scipy TRF).  x, f0, J: host or device. */
+int sfm_ba_reference_fd(sfm_ctx* ctx, const double* x, int n_params, int n_points, double* f0, double* J);
+
 typedef struct sfm_ba_stats {
   double cost_before;   /* 0.5*sum r^2 at the linearisation point */
   double cost_after;    /* at the candidate parameters */

@@ -120,6 +120,25 @@ def BundleAdjustment(points_3d, temp2, Rtnew, K, r_error):
             sol[0:12].reshape(3, 4))
 
 
+def OptimReprojectionError_tracks(x, cloud_len, poses_len, tracks_len, img_tot, track):
+    """test.py:85-113 — the multi-view residual of the track pipeline: x = [K 9 | poses img_tot x 12 | cloud N x 3 |
+    tracks N x 2 img_tot]; one value per (view, point), sqrt(dx^2 + dy^2) / (number of values), view-major.  The
+    reference reads the module-level `track` instead of the `tracks` it unpacks and takes columns i, i + 1 for view i
+    (test.py:99) — both reproduced, `track` passed explicitly."""
+    K = x[0:9].reshape(3, 3)
+    poses = x[9:9 + poses_len].reshape(img_tot, 12)
+    cloud = x[9 + poses_len:9 + poses_len + cloud_len].reshape(cloud_len // 3, 3)
+    error = []
+    for i in range(img_tot):
+        Rt = poses[i].reshape(3, 4)
+        r, _ = cv2.Rodrigues(Rt[:3, :3])
+        p = track[:, i:i + 2]
+        proj, _ = cv2.projectPoints(cloud, r, Rt[:3, 3], K, distCoeffs=None)
+        proj = proj[:, 0, :]
+        error += [np.sqrt((p[idx][0] - proj[idx][0]) ** 2 + (p[idx][1] - proj[idx][1]) ** 2) for idx in range(len(p))]
+    return np.array(error).ravel() / len(error)
+
+
 # --------------------------------------------------------------------------- per-view loop
 def bootstrap_two_views(scene):
     """State the reference holds when its loop starts (sfm.py:304-339), with the E-matrix/

@@ -121,6 +121,45 @@ def ba_small(ref):
     print("ba_small: cost0", float(res.sum()), "-> X shift", float(np.abs(Xo - X0[:, 0]).max()))
 
 
+def ba_tracks():
+    """test.py:85-113 — the multi-view residual of the track pipeline, executed from the reference's own def.  The def
+    reads the module-level `track` (not its `tracks` argument) and slices it `track[:, i:i + 2]` for view i — both
+    kept: the fixture records what the reference computes."""
+    defs = refload.load_reference_defs("test.py")
+    rng = np.random.default_rng(21)
+    K = synth.K_GUSTAV
+    img_tot, n = 3, 20
+    X = np.c_[rng.uniform(-2, 2, n), rng.uniform(-1.5, 1.5, n), rng.uniform(5, 11, n)]
+    poses = []
+    for i in range(img_tot):
+        R, t = synth.orbit_pose(0.05 * i)
+        poses.append(np.hstack([R, t]).ravel())
+    poses = np.array(poses)
+    track = rng.uniform(100, 900, (n, 2 * img_tot))                # what view i is compared with: columns i, i + 1
+    defs["OptimReprojectionError"].__globals__["track"] = track
+    x = np.hstack((K.ravel(), poses.ravel(), X.ravel(), track.ravel()))
+    res = _quiet(defs["OptimReprojectionError"], x, X.size, poses.size, track.size, img_tot)
+    np.savez_compressed(os.path.join(OUT, "ba_tracks.npz"), K=K, poses=poses, cloud=X, track=track, x=x, residual=res,
+                        img_tot=img_tot)
+    print("ba_tracks: residual sum", float(res.sum()), res.shape)
+
+
+def gustav_scene():
+    """The reference's shipped artifacts as a fixture: pose.csv (K + 57 projection matrices, sfm.py:423) and
+    Point_Cloud/sparse.ply (19 282 points, sfm.py:169-201) -> K, cameras as (rvec | tvec) = K^-1 P, points in world
+    units (file / 200, sfm.py:170).  Read with the product's own readers (sfm_mvs_b200.io)."""
+    from sfm_mvs_b200 import io as sio
+    K, Ps = sio.load_poses(os.path.join(refload.REFERENCE_ROOT, "pose.csv"))
+    pts, _ = sio.load_ply(os.path.join(refload.REFERENCE_ROOT, "Point_Cloud", "sparse.ply"))
+    cams = []
+    for P in Ps:
+        Rt = np.linalg.inv(K) @ P
+        U, _, Vt = np.linalg.svd(Rt[:, :3])
+        cams.append(np.concatenate([cv2.Rodrigues(U @ Vt)[0].ravel(), Rt[:, 3]]))
+    np.savez_compressed(os.path.join(OUT, "gustav_scene.npz"), K=K, cams=np.array(cams), pts=pts.astype(np.float32))
+    print("gustav_scene:", len(cams), "cameras,", len(pts), "points")
+
+
 def chain(ref):
     from oracle import cvpath  # matching half on arrays (find_features needs images)
     scene = synth.orbit_scene(7, 600, seed=3)
@@ -165,7 +204,7 @@ def main():
     assert refload.available(), "needs /root/reference (build container only)"
     os.makedirs(OUT, exist_ok=True)
     ref = refload.load_reference_defs()
-    real_pair(ref); geometry(ref); ba_small(ref); chain(ref)
+    real_pair(ref); geometry(ref); ba_small(ref); ba_tracks(); gustav_scene(); chain(ref)
 
 
 if __name__ == "__main__":

@@ -15,11 +15,11 @@ _ENGINE = {
     "_lib": ("LIB_PATH", "error"),
     "engine": ("BAProblem", "Context", "Descriptors", "epnp", "five_point", "nccl_unique_id", "ransac_subsets",
                "rodrigues_to_matrix", "rodrigues_to_vector"),
-    "cv2_compat": ("NORM_L2", "RATIO", "SOLVEPNP_ITERATIVE", "BFMatcher", "BundleAdjustment", "DMatch", "PnP",
+    "cv2_compat": ("NORM_L2", "RATIO", "SOLVEPNP_ITERATIVE", "BFMatcher", "BundleAdjustment", "BundleAdjustmentSE3", "DMatch", "PnP",
                    "ReprojectionError", "Triangulation", "common_points", "default_context", "findEssentialMat", "knn2",
                    "match_keypoints", "patch_cv2", "recoverPose", "set_default_context", "solvePnPRansac",
                    "triangulatePoints", "unpatch_cv2"),
-    "io": ("to_ply", "save_poses", "load_poses", "load_ply"),            # sfm.py:169-201, :423
+    "io": ("to_ply", "save_poses", "load_poses", "load_ply", "lookup_colors"),            # sfm.py:169-201, :423
 }
 _WHERE = {name: mod for mod, names in _ENGINE.items() for name in names}
 _SUBMODULES = ("_lib", "engine", "cv2_compat", "pipeline", "ba", "io", "sharding", "synth")

@@ -161,6 +161,7 @@ struct sfm_chain {
   std::vector<sfm_view_out> pend_out;
   // loop state (sfm.py:399-409)
   bool started = false;
+  bool dead = false;                // a view failed to register: later views were computed from an undefined pose
   const float* prev_q = nullptr;   // previous pair's matches (re-triangulated for the next view)
   const float* prev_t = nullptr;
   int prev_n = 0;
@@ -193,6 +194,7 @@ extern "C" int sfm_chain_create(sfm_ctx* ctx, const double* K, const double* Rt0
       p->started = false; p->prev_q = p->prev_t = nullptr; p->prev_n = 0; p->pts1 = p->points_3d = nullptr; p->n1 = 0;
       p->views_done = 0; p->set_used[0] = p->set_used[1] = false;
       p->pending = p->pending_parsed = false; p->pend_reg = 0;     // an uncollected call died with its chain
+      p->dead = false;
       SFM_CUDA(cudaMemcpyAsync(p->K_dev, p->K, 9 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
       SFM_CUDA(cudaMemcpyAsync(p->P_view, p->P1, 12 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
       SFM_CUDA(cudaMemcpyAsync(p->P_view + 12, p->P2, 12 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
@@ -336,8 +338,19 @@ static int chain_collect_impl(sfm_chain* c, sfm_view_out* out, int32_t* n_regist
     memcpy(o.Rt, r.Rt, sizeof(o.Rt));
     o.err_pnp = r.err_pnp; o.err_new = r.err_new;
     o.n_new = r.n_new; o.n_pnp = r.n_pnp; o.n_inl = r.n_inl; o.n_match = c->pend_nmatch[v];
-    SFM_REQUIRE(r.n_pnp >= 6, "registration failed: view %d shares %d points with the model", c->views_done - reg + v + 2, r.n_pnp);
-    SFM_REQUIRE(r.ok, "registration failed: solvePnPRansac found no consensus (view %d)", c->views_done - reg + v + 2);
+    if (r.n_pnp < 6 || !r.ok) {
+      // The whole call was queued before any record could be looked at: the views after this one were computed from
+      // its (undefined) pose.  out[0 .. v) are valid and reported; the chain cannot be extended any further.
+      c->dead = true;
+      if (n_registered) *n_registered = v;
+      if (r.n_pnp < 6)
+        sfm_set_error("registration failed: view %d shares %d points with the model (6 needed); %d view(s) of this call are valid",
+                      c->views_done - reg + v + 2, r.n_pnp, v);
+      else
+        sfm_set_error("registration failed: solvePnPRansac found no consensus (view %d); %d view(s) of this call are valid",
+                      c->views_done - reg + v + 2, v);
+      return SFM_ERR_INVALID;
+    }
   }
   if (n_registered) *n_registered = reg;
   return SFM_OK;
@@ -348,6 +361,7 @@ static int chain_extend_impl(sfm_chain* c, int n_pairs, const float* const* pts_
                              bool defer) {
   SFM_REQUIRE(c && n_pairs >= 0 && (n_pairs == 0 || (pts_q && pts_t && n_match)), "sfm_chain_extend: null argument");
   SFM_REQUIRE(!c->pending, "sfm_chain_extend: the previous asynchronous call has not been collected");
+  SFM_REQUIRE(!c->dead, "sfm_chain_extend: a view of an earlier call failed to register; the chain cannot be extended");
   sfm_ctx* ctx = c->ctx;
   const double* K = c->K;
   int reg = 0;

@@ -274,15 +274,31 @@ def common_points(pts1, pts2, pts3, ctx: _e.Context | None = None):
 
 
 # --------------------------------------------------------------------------- BundleAdjustment (sfm.py:138-157)
-def BundleAdjustment(points_3d, temp2, Rtnew, K, r_error, ctx: _e.Context | None = None, max_iters: int = 25):
-    """Same signature and return shapes as the reference: (X (N,3) f64, p (N,2) f64, Rt (3,4) f64).
+def BundleAdjustment(points_3d, temp2, Rtnew, K, r_error, ctx: _e.Context | None = None):
+    """sfm.py:138-157, same signature, same formulation, same optimiser: x0 = [Rt 12 | K 9 | temp2 (2,N) | points
+    (N,3)] — the pose as twelve unconstrained numbers, K and the observed pixels free, as the reference has it —
+    minimised by scipy.optimize.least_squares(gtol=r_error) (TRF, the reference's own driver, sfm.py:9,146).  What runs
+    on the GPU is what the reference spends its "half a minute per frame" on (sfm.py:378): the residual
+    OptimReprojectionError and the 22 + 5N residual evaluations of every finite-difference Jacobian, all in one launch
+    with scipy's own difference steps (csrc/ba_ref.cu), so the iterates follow the reference's.
+    Returns (X (N,3), p (N,2), Rt (3,4)) float64 like the reference."""
+    from scipy.optimize import least_squares
+    ctx = ctx or default_context()
+    x0 = np.hstack((np.asarray(Rtnew, np.float64).ravel(), np.asarray(K, np.float64).ravel(),
+                    np.asarray(temp2, np.float64).ravel(), np.asarray(points_3d, np.float64).ravel()))
+    n = (len(x0) - 21) // 5
+    if 21 + 5 * n != len(x0) or n < 1:
+        raise _e.error(-1, f"BundleAdjustment: {len(x0)} parameters are not [Rt 12 | K 9 | p (2,N) | X (N,3)]")
+    fun = lambda x: ctx.ba_reference_fd(x, n, want_jac=False)[0]
+    jac = lambda x: ctx.ba_reference_fd(x, n)[1]
+    sol = least_squares(fun=fun, x0=x0, jac=jac, gtol=r_error).x
+    rest = int(len(sol[21:]) * 0.4)                   # sfm.py:148-155
+    return sol[21 + rest:].reshape(-1, 3), sol[21:21 + rest].reshape(2, rest // 2).T, sol[0:12].reshape(3, 4)
 
-    The reference lets scipy move the pose (as 12 unconstrained numbers), K, the observed pixels and the
-    points under a dense finite-difference Jacobian (sfm.py:141-146) — "close to half a minute per frame"
-    (sfm.py:378).  The engine solves the well-posed version of the same problem: the camera moves on SE(3)
-    (rvec, tvec), K and the observations are data, analytic Jacobians, Schur-complement LM on the GPU.
-    The residual the reference evaluates, ((p-proj)^2)/N, is available bit-for-tolerance as mode 1 of
-    BAProblem.eval (parity-tested); r_error plays the reference's role of the stopping tolerance."""
+
+def BundleAdjustmentSE3(points_3d, temp2, Rtnew, K, ctx: _e.Context | None = None, max_iters: int = 25, ftol: float = 1e-10):
+    """The well-posed version of the same refinement, entirely on the GPU: the camera moves on SE(3) (rvec, tvec), K
+    and the observations are data, analytic Jacobians, Schur-complement LM (BAProblem).  Same return shapes."""
     ctx = ctx or default_context()
     X = np.asarray(points_3d, np.float64).reshape(-1, 3)
     obs = np.asarray(temp2, np.float32)
@@ -292,7 +308,7 @@ def BundleAdjustment(points_3d, temp2, Rtnew, K, r_error, ctx: _e.Context | None
     cam = np.concatenate([_e.rodrigues_to_vector(Rt[:, :3]), Rt[:, 3]])
     prob = _e.BAProblem(ctx, 1, n, np.zeros(n, np.int32), np.arange(n, dtype=np.int32), obs, K)
     prob.set_params(cam.reshape(1, 6), X)
-    prob.solve(max_iters=max_iters, ftol=1e-10)
+    prob.solve(max_iters=max_iters, ftol=ftol)
     cams, pts = prob.get_params()
     prob.close()
     Rt_out = np.hstack([_e.rodrigues_to_matrix(cams[0, :3]), cams[0, 3:].reshape(3, 1)])

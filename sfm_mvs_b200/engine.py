@@ -63,6 +63,33 @@ def _dptr(a: np.ndarray):
     return a.ctypes.data_as(C.c_void_p)
 
 
+def _stream_ordered(fn):
+    """Methods that accept or return torch CUDA tensors: the kernels run on the CONTEXT's stream, torch allocates
+    (and frees `.contiguous()` temporaries) on torch's CURRENT stream.  Run the call with the context's stream
+    current, after everything the caller has queued so far, and make the caller's stream wait for it — inputs written
+    on the caller's stream are complete before the kernels read them, outputs are complete before the caller's next
+    operation, and the caching allocator sees every buffer on the stream that uses it."""
+    import functools
+    import sys
+
+    @functools.wraps(fn)
+    def wrapper(self, *a, **k):
+        torch = sys.modules.get("torch")
+        if torch is None or not torch.cuda.is_initialized():
+            return fn(self, *a, **k)
+        ctx = self if isinstance(self, Context) else self.ctx
+        cur = torch.cuda.current_stream(ctx.torch_device)
+        own = ctx.torch_stream()
+        if cur == own:
+            return fn(self, *a, **k)
+        own.wait_stream(cur)
+        with torch.cuda.stream(own):
+            out = fn(self, *a, **k)
+        cur.wait_stream(own)
+        return out
+    return wrapper
+
+
 class Descriptors:
     """A view's descriptors prepared once (K1b) and resident in HBM (sfm_desc)."""
 
@@ -164,9 +191,9 @@ class Context:
         return torch.device("cuda", self.device)
 
     def torch_stream(self):
-        """The context's stream as a torch ExternalStream.  Code that mixes torch allocations / copies
-        with engine calls must run under `torch.cuda.stream(ctx.torch_stream())` so that both are ordered
-        on one stream (the engine's own stream is non-blocking w.r.t. the legacy default stream)."""
+        """The context's stream as a torch ExternalStream.  The methods that take or return CUDA tensors order
+        themselves against torch's current stream (_stream_ordered); code that calls the C ABI directly with torch
+        buffers (pipeline.py) runs under `torch.cuda.stream(ctx.torch_stream())`."""
         import torch
         if getattr(self, "_tstream", None) is None:
             self._tstream = torch.cuda.ExternalStream(self.stream, device=self.torch_device)
@@ -213,6 +240,7 @@ class Context:
     def descriptors(self, des) -> Descriptors:
         return des if isinstance(des, Descriptors) else Descriptors(self, des)
 
+    @_stream_ordered
     def knn2(self, q, t, ratio: float = 0.70, mode: int = 0, device_out: bool = False):
         """2-NN under L2 + Lowe ratio (sfm.py:259-265).  Returns idx (nq,2) i32, dist (nq,2) f32,
         good (nq,) uint8, n_good.  idx=-1 / dist=inf mark missing neighbours (nt < 2)."""
@@ -227,6 +255,7 @@ class Context:
         check(lib.sfm_desc_match(self._h, dq._h, dt._h, float(ratio), pidx, pdist, pgood, png, int(mode)))
         return idx, dist, good, (ng if device_out else int(ng[0]))
 
+    @_stream_ordered
     def match_gather(self, idx, good, kp_q, kp_t, n_hint: int | None = None):
         """sfm.py:267-268 on the device: survivors' keypoints, ascending queryIdx.  All arguments are
         torch CUDA tensors; returns (pts_q, pts_t, qidx, tidx, n) with capacity-nq tensors."""
@@ -252,6 +281,7 @@ class Context:
         return out
 
     # ------------------------------------------------------------------ hot path 2: triangulation
+    @_stream_ordered
     def triangulate(self, P1, P2, x1, x2, pts_layout: int = 0, out_layout: int = 0, normalize_w: bool = False):
         """cv2.triangulatePoints (sfm.py:53) [+ cloud/cloud[3] (sfm.py:54) if normalize_w].
         pts_layout 0: (2,N), 1: (N,2).  out_layout 0: (4,N), 1: (N,4), 2: (N,3)."""
@@ -270,6 +300,7 @@ class Context:
                                   1 if normalize_w else 0))
         return X
 
+    @_stream_ordered
     def reproj_error(self, X, x_layout: int, px, px_layout: int, Rt, K, want_proj: bool = False,
                      want_X3: bool = False, device_err: bool = False):
         """ReprojectionError core (sfm.py:84-95).  x_layout 0: (N,3), 1: (4,N), 2: (N,4);
@@ -290,6 +321,7 @@ class Context:
                                    pproj, pX3))
         return (err if device_err else float(err[0])), proj, X3
 
+    @_stream_ordered
     def common_points(self, pts1, pts2):
         """common_points (sfm.py:215-239) association.  Returns idx1, idx2 (trimmed on the host path),
         keep2 (uint8 mask over pts2 rows never chosen), n_common."""
@@ -308,6 +340,7 @@ class Context:
         return i1[:c], i2[:c], keep[:n2], c
 
     # ------------------------------------------------------------------ hot path 3a: PnP
+    @_stream_ordered
     def pnp_score(self, X, px, K, Rt, thr: float = 8.0, want_masks: bool = True):
         """K4: inlier counts (H,) and masks (H,N) of H poses Rt (H,3,4) — PnPRansacCallback::computeError."""
         K = np.ascontiguousarray(K, np.float64).reshape(9)
@@ -322,6 +355,7 @@ class Context:
         check(lib.sfm_pnp_score(self._h, aX.ptr, ap.ptr, n, _dptr(K), _dptr(Rt), H, float(thr), pc, pm))
         return counts, masks
 
+    @_stream_ordered
     def pnp_ransac(self, X, px, K, max_iters: int = 100, thr: float = 8.0, confidence: float = 0.99,
                    hypotheses=None, hyp_valid=None):
         """cv2.solvePnPRansac with OpenCV defaults (sfm.py:67).  Returns ok, rvec (3,), tvec (3,),
@@ -354,6 +388,16 @@ class Context:
         return bool(ok.value), rvec, tvec, inl[:ni.value].copy(), d
 
 
+    def ba_reference_fd(self, x, n_points: int, want_jac: bool = True):
+        """OptimReprojectionError (sfm.py:104-136) at x = [Rt 12 | K 9 | p (2,N) | X (N,3)] and, if wanted, its
+        forward-difference Jacobian with scipy's steps: (f0 (2N,), J (2N, 21+5N) or None), float64 host arrays."""
+        x = np.ascontiguousarray(x, np.float64).ravel()
+        f0 = np.empty(2 * n_points)
+        J = np.empty((2 * n_points, len(x))) if want_jac else None
+        check(lib.sfm_ba_reference_fd(self._h, _dptr(x), len(x), int(n_points), _dptr(f0), None if J is None else _dptr(J)))
+        return f0, J
+
+    @_stream_ordered
     def epnp_batch(self, X, px, K, subsets):
         """The device minimal solver on explicit 5-point subsets (H,5): (R (H,3,3), t (H,3)), the raw output of
         cv2.solvePnP(X[s], px[s], K, 0, flags=SOLVEPNP_EPNP) before cv2.Rodrigues — bit-identical to OpenCV."""
@@ -447,6 +491,7 @@ class BAProblem:
         check(lib.sfm_ba_get_params(self._h, _dptr(c), _dptr(p)))
         return c, p
 
+    @_stream_ordered
     def eval(self, mode: int = 0, want_r=True, want_J=True, device_out: bool = False):
         """K5.  Returns dict(r, Jc, Jp, cost)."""
         O = self.n_obs
@@ -459,6 +504,7 @@ class BAProblem:
         check(lib.sfm_ba_eval(self._h, int(mode), pr, pjc, pjp, pc))
         return dict(r=r, Jc=Jc, Jp=Jp, cost=cost if device_out else float(cost[0]))
 
+    @_stream_ordered
     def eval_into(self, mode, r, Jc, Jp, cost):
         """K5 into caller-owned device tensors (the benchmarked call: nothing allocated, nothing synchronised)."""
         check(lib.sfm_ba_eval(self._h, int(mode), None if r is None else r.data_ptr(),

@@ -72,3 +72,16 @@ def load_ply(fname):
     if n is not None and len(data) != n:
         raise ValueError(f"{fname}: header says {n} vertices, file has {len(data)}")
     return data[:, :3] / 200.0, data[:, 3:6].astype(np.uint8)
+
+
+def lookup_colors(img, pts):
+    """sfm.py:393-395 — the colour of every new point: pixel coordinates truncated to int32 (np.array(temp2,
+    dtype=np.int32)), then img[y, x] per point.  pts: (2,N) as the loop holds temp2, or (N,2); img: (H,W,3) uint8
+    (BGR as cv2.imread gives it).  -> (N,3), the rows the reference stacks into `colorstot` for to_ply."""
+    p = np.asarray(pts)
+    if p.ndim != 2 or 2 not in p.shape:
+        raise ValueError(f"lookup_colors: points must be (2,N) or (N,2), got {p.shape}")
+    if p.shape[0] != 2:
+        p = p.T
+    reg = np.array(p, dtype=np.int32)                 # the reference's cast: truncation toward zero
+    return np.asarray(img)[reg[1], reg[0]]

@@ -228,6 +228,8 @@ class RegistrationChain:
                                     temp1.data_ptr(), temp2.data_ptr(), cnt[1:2].data_ptr()))
         self.ctx.sync()
         c, m = (int(v) for v in cnt.cpu().numpy())
+        if c < 6:          # the same rule as the library's loop (chain.cu): the minimal problems draw 5 of at least 6 points
+            raise _e.error(-1, f"registration failed: the new view shares {c} points with the model (6 needed)")
         X_common = self._gather(points_3d, 3, i1, c)
         com2 = self._gather(pm.pts_t, 2, i2, c)
         ok, rvec, tvec, k, inl = self._pnp(X_common, com2, c)                           # sfm.py:362
@@ -309,7 +311,10 @@ class NativeChain:
         pt = np.array([pm.ptr_t for pm in matches], np.uint64)
         xn = np.ascontiguousarray(X_all.data_ptr() + off[:-1] * 12, np.uint64)
         check(lib.sfm_chain_extend_async(self._h, n_pairs, pq.ctypes.data, pt.ctypes.data, n.ctypes.data, xn.ctypes.data))
-        self._alive = [matches[-1], X_all]
+        # the queued call still re-triangulates the PREVIOUS call's last pair: it stays referenced until this call's
+        # collect(), together with this call's last pair and output slab
+        self._alive = [getattr(self, "_last_pair", None), matches[-1], X_all]
+        self._last_pair = matches[-1]
         self._fed += n_pairs
         self._inflight = (X_all, off, len(reg_n))
 
@@ -430,12 +435,14 @@ def register_device(ctx: _e.Context, K, kps, dess, Rt0, Rt1, ratio: float = 0.70
     return outs
 
 
-def register_host(ctx: _e.Context, K, kps, dess, Rt0, Rt1, chunk: int = 25, ratio: float = 0.70):
+def register_host(ctx: _e.Context, K, kps, dess, Rt0, Rt1, chunk: int = 25, ratio: float = 0.70, ahead: int = 2):
     """Host arrays in, registered views out — the call a user makes with a sequence of views whose keypoints
     (n,2) and descriptors (n,128) sit in host memory (numpy arrays or torch CPU tensors; pinned memory lets the
-    upload overlap).  Views are uploaded on a copy stream in chunks; descriptor preparation and the batched match
-    of a chunk's pairs run on a matching context, the registration of its views on the engine stream, while later
-    chunks are still crossing PCIe."""
+    upload overlap).  Views are uploaded on a copy stream in chunks (a short first chunk gets the loop going);
+    descriptor preparation and the batched match of a chunk's pairs run on a matching context, the registration of
+    its views on the engine stream, while later chunks are still crossing PCIe.  The copies of chunk k + `ahead` are
+    submitted only after chunk k's registration has been queued, so the first chunk's work does not wait for the host
+    to enqueue every copy of the sequence (measured on 200 x 5000: 48.0 -> 46.4 ms per step, tools/prof_e2e.py)."""
     import torch
     V = len(kps)
     dev = ctx.torch_device
@@ -444,37 +451,6 @@ def register_host(ctx: _e.Context, K, kps, dess, Rt0, Rt1, chunk: int = 25, rati
     dess = [as_t(a) for a in dess]
     cs = getattr(ctx, "_copy_stream", None)          # one upload stream per context: torch's caching allocator keeps a
     if cs is None:                                    # pool per stream, a fresh stream per call would cudaMalloc every buffer
-        cs = ctx._copy_stream = torch.cuda.Stream(device=dev)
-    # a short first chunk gets the loop going while the bulk of the upload is still in flight
-    bounds = _chunk_bounds(V, [min(8, chunk), chunk] + list(range(2 * chunk, V, chunk)))
-    kp_d, des_d, events = [None] * V, [None] * V, []
-    with torch.cuda.stream(cs):
-        for lo, hi in bounds:
-            for i in range(lo, hi):
-                kp_d[i] = kps[i].to(dev, non_blocking=True)
-                des_d[i] = dess[i].to(dev, non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record(cs)
-            events.append(ev)
-    outs, keep = _register_pipelined(ctx, K, kp_d, des_d, Rt0, Rt1, bounds, events, ratio, max(int(k.shape[0]) for k in kps))
-    for o in outs:
-        o["_keep"] = (kp_d, des_d, keep)      # uploaded on the copy stream: stay referenced until the caller drops the result
-    return outs
-
-
-def register_host_interleaved(ctx: _e.Context, K, kps, dess, Rt0, Rt1, chunk: int = 25, ratio: float = 0.70, ahead: int = 2):
-    """EXPERIMENTAL — written at the end of round 1 after the GPU budget was spent; NOT yet run on a GPU and not used by
-    bench.py or the tests.  register_host with the host->device copies of chunk k + `ahead` submitted only after chunk
-    k's registration has been launched, instead of all copies up front: the first chunk's work no longer waits for
-    the host to queue every copy of the sequence."""
-    import torch
-    V = len(kps)
-    dev = ctx.torch_device
-    as_t = lambda a: a if _e._is_torch(a) else torch.from_numpy(np.ascontiguousarray(a))
-    kps = [as_t(a) for a in kps]
-    dess = [as_t(a) for a in dess]
-    cs = getattr(ctx, "_copy_stream", None)
-    if cs is None:
         cs = ctx._copy_stream = torch.cuda.Stream(device=dev)
     bounds = _chunk_bounds(V, [min(8, chunk), chunk] + list(range(2 * chunk, V, chunk)))
     kp_d, des_d, events = [None] * V, [None] * V, [None] * len(bounds)
@@ -491,13 +467,14 @@ def register_host_interleaved(ctx: _e.Context, K, kps, dess, Rt0, Rt1, chunk: in
             ev.record(cs)
         events[k] = ev
 
-    for k in range(min(ahead, len(bounds))):
-        upload(k)
-    # a chunk without pairs never reaches after_chunk: chunk 0 always has pairs for V >= 3, later chunks always do
+    for k in range(len(bounds)):                      # chunks without pairs never reach after_chunk: upload them up front
+        lo, hi = bounds[k]
+        if k < ahead or hi - 1 <= max(lo - 1, 0):
+            upload(k)
     outs, keep = _register_pipelined(ctx, K, kp_d, des_d, Rt0, Rt1, bounds, events, ratio, max(int(k.shape[0]) for k in kps),
                                      after_chunk=lambda k: upload(k + ahead))
     for o in outs:
-        o["_keep"] = (kp_d, des_d, keep)
+        o["_keep"] = (kp_d, des_d, keep)      # uploaded on the copy stream: stay referenced until the caller drops the result
     return outs
 
 

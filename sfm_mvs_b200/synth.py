@@ -242,3 +242,54 @@ def two_view_pair(n: int, seed: int = 0, noise: float = 0.3, outliers: float = 0
     bad = rng.choice(n, int(outliers * n), replace=False)
     p1[bad] += rng.uniform(-150, 150, (len(bad), 2))
     return p0.astype(dtype), p1.astype(dtype), R, t
+
+
+def ba_problem_from_scene(K, cams, pts, width: float = 648.0, height: float = 968.0, seed: int = 0, px_noise: float = 0.5,
+                          cam_sigma: float = 2e-3, pt_sigma: float = 1e-2):
+    """A bundle-adjustment problem from a reconstructed scene: every point that projects inside the width x height
+    frame of a camera with positive depth is an observation of it (plus pixel noise); the start is the scene
+    perturbed.  With tests/golden/gustav_scene.npz (the 57 cameras of the reference's pose.csv and the 19 282
+    points of its Point_Cloud/sparse.ply) and the default 648 x 968 frame this is the 1 061 813-observation fixture
+    problem of SURVEY section 4 (every camera sees 18.1-19.0 k of the points).
+    Same dict as ba_problem; observations point-major."""
+    rng = np.random.default_rng(seed)
+    K = np.asarray(K, np.float64)
+    cams = np.asarray(cams, np.float64)
+    pts = np.asarray(pts, np.float64)
+    Rs = np.array([_rodrigues_mat(c[:3]) for c in cams])
+    ts = cams[:, 3:]
+    ci, pi, ob = [], [], []
+    B = 4096
+    for s in range(0, len(pts), B):
+        X = pts[s:s + B]
+        Y = np.einsum('cij,pj->pci', Rs, X) + ts[None]
+        z = Y[..., 2]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            u = K[0, 0] * Y[..., 0] / z + K[0, 2]
+            v = K[1, 1] * Y[..., 1] / z + K[1, 2]
+        vis = (z > 0) & (u >= 0) & (u < width) & (v >= 0) & (v < height)
+        p_loc, c_loc = np.nonzero(vis)                                  # point-major already
+        ci.append(c_loc.astype(np.int32))
+        pi.append((p_loc + s).astype(np.int32))
+        ob.append(np.stack([u[vis], v[vis]], 1))
+    cam_idx, pt_idx = np.concatenate(ci), np.concatenate(pi)
+    obs = np.concatenate(ob) + rng.normal(0.0, px_noise, (len(cam_idx), 2))
+    seen = np.zeros(len(pts), bool)
+    seen[pt_idx] = True
+    if not seen.all():                                                   # drop points no camera sees, renumber
+        remap = np.cumsum(seen) - 1
+        pts, pt_idx = pts[seen], remap[pt_idx].astype(np.int32)
+    cams0 = cams + rng.normal(0.0, cam_sigma, cams.shape)
+    pts0 = pts + rng.normal(0.0, pt_sigma, pts.shape)
+    return dict(K=K, cams_gt=cams, pts_gt=pts, cams0=cams0, pts0=pts0, cam_idx=cam_idx, pt_idx=pt_idx,
+                obs=obs.astype(np.float32))
+
+
+def _rodrigues_mat(r):
+    r = np.asarray(r, np.float64)
+    th = float(np.linalg.norm(r))
+    if th < 1e-15:
+        return np.eye(3)
+    k = r / th
+    Kx = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+    return np.cos(th) * np.eye(3) + (1 - np.cos(th)) * np.outer(k, k) + np.sin(th) * Kx

@@ -108,9 +108,50 @@ def test_first_step_matches_dense_normal_equations(engine):
     assert np.abs(d_p - dx[6 * C:]).max() <= 2e-3 * np.abs(dx[6 * C:]).max()
 
 
-def test_bundleadjustment_wrappers(engine, golden):
+def test_reference_formulation_residual_and_fd_jacobian(engine, golden):
+    """sfm_ba_reference_fd: OptimReprojectionError (sfm.py:104-136) at the golden x — against the value the reference's
+    own def produced — and its finite-difference Jacobian against scipy's approx_derivative over the oracle's port."""
+    from scipy.optimize._numdiff import approx_derivative
+    g = golden("ba_small")
+    n = g["X0"].shape[0]
+    f0, J = engine.ba_reference_fd(g["x"], n)
+    assert np.abs(f0 - g["residual"]).max() <= 1e-12 * np.abs(g["residual"]).max()
+    J_ref = approx_derivative(cvpath.OptimReprojectionError, g["x"], method="2-point", f0=cvpath.OptimReprojectionError(g["x"]))
+    assert J.shape == J_ref.shape == (2 * n, 21 + 5 * n)
+    assert np.abs(J - J_ref).max() <= 1e-6 * np.abs(J_ref).max()
+    assert np.array_equal(J != 0, J_ref != 0) or np.abs(J - J_ref)[(J != 0) != (J_ref != 0)].max() < 1e-9
+
+
+def test_bundleadjustment_equals_the_reference_result(engine, golden):
+    """sfm.py:138-157 through the drop-in: same formulation (pose as 12 numbers, K and observations free), same
+    optimiser (scipy TRF, gtol = r_error), residual and Jacobian evaluated on the GPU — against ba_X / ba_p / ba_Rt as
+    the reference's own BundleAdjustment returned them (tests/golden/ba_small.npz), and against the oracle's port on
+    a second problem."""
     g = golden("ba_small")
     X, p, Rt = sfm.BundleAdjustment(g["X0"], g["obs"], g["Rt"], g["K"], 0.5, ctx=engine)
+    n = g["X0"].shape[0]
+    assert X.shape == (n, 3) and p.shape == (n, 2) and Rt.shape == (3, 4)
+    assert np.abs(g["ba_X"] - g["X0"][:, 0]).max() > 1e-3          # the reference result is not the input ...
+    assert np.abs(X - g["ba_X"]).max() <= 1e-4 * np.abs(g["ba_X"]).max()
+    assert np.abs(p - g["ba_p"]).max() <= 1e-4 * np.abs(g["ba_p"]).max()
+    assert np.abs(Rt - g["ba_Rt"]).max() <= 1e-4
+    rng = np.random.default_rng(5)
+    K = synth.K_GUSTAV
+    R, t = synth.orbit_pose(0.11)
+    Xw = np.c_[rng.uniform(-2, 2, 40), rng.uniform(-1.5, 1.5, 40), rng.uniform(5, 11, 40)]
+    uv, _ = synth.project(K, R, t, Xw)
+    obs = (uv + rng.normal(0, 0.7, uv.shape)).astype(np.float32).T.copy()
+    X0 = (Xw + rng.normal(0, 0.03, Xw.shape)).astype(np.float32).reshape(40, 1, 3)
+    Rt0 = np.hstack([R, t])
+    Xr, pr, Rtr = cvpath.BundleAdjustment(X0, obs, Rt0, K, 0.5)
+    Xe, pe, Rte = sfm.BundleAdjustment(X0, obs, Rt0, K, 0.5, ctx=engine)
+    assert np.abs(Xe - Xr).max() <= 1e-4 * np.abs(Xr).max() and np.abs(pe - pr).max() <= 1e-4 * np.abs(pr).max()
+    assert np.abs(Rte - Rtr).max() <= 1e-4
+
+
+def test_bundleadjustment_wrappers(engine, golden):
+    g = golden("ba_small")
+    X, p, Rt = sfm.BundleAdjustmentSE3(g["X0"], g["obs"], g["Rt"], g["K"], ctx=engine)
     n = g["X0"].shape[0]
     assert X.shape == (n, 3) and p.shape == (n, 2) and Rt.shape == (3, 4)
     e_before = cvpath.ReprojectionError(g["X0"].reshape(n, 3), g["obs"].T, g["Rt"], g["K"], 0)[0]
@@ -118,6 +159,50 @@ def test_bundleadjustment_wrappers(engine, golden):
     assert e_after < e_before
     X2, R2, t2 = sfm.ba.bundle_adjustment(g["X0"].reshape(n, 3), g["obs"].T, None, g["K"], g["Rt"][:, :3], g["Rt"][:, 3:])
     assert np.allclose(X2, X, atol=1e-6) and R2.shape == (3, 3) and t2.shape == (3, 1)
+
+
+def test_track_pipeline_residual_mode_equals_the_reference(engine, golden):
+    """mode 2 of the evaluation kernel = the residual of test.py:85-113, one value per (view, point),
+    sqrt(dx^2 + dy^2) / n_obs — against the fixture produced by the reference's own def (which compares view i with
+    columns i, i + 1 of its global track table: the observations are built the same way)."""
+    g = golden("ba_tracks")
+    V, n = int(g["img_tot"]), g["cloud"].shape[0]
+    cams = np.array([np.concatenate([sfm.rodrigues_to_vector(P.reshape(3, 4)[:, :3]), P.reshape(3, 4)[:, 3]]) for P in g["poses"]])
+    cam_idx = np.tile(np.arange(V, dtype=np.int32), n)                      # point-major: point p, views 0..V-1
+    pt_idx = np.repeat(np.arange(n, dtype=np.int32), V)
+    obs = np.array([g["track"][pt, v:v + 2] for pt in range(n) for v in range(V)], np.float32)
+    prob = sfm.BAProblem(engine, V, n, cam_idx, pt_idx, obs, g["K"])
+    prob.set_params(cams, g["cloud"])
+    r2 = prob.eval(2, want_J=False)["r"].reshape(n, V)
+    ref = g["residual"].reshape(V, n).T                                     # the reference is view-major
+    assert np.abs(r2 - ref).max() <= 1e-4 * np.abs(ref).max()
+    prob.close()
+
+
+def test_fixture_problem_from_the_reference_artifacts(engine, golden):
+    """The reference's own reconstruction as a BA problem: the 57 cameras of pose.csv and the 19 282
+    points of Point_Cloud/sparse.ply (tests/golden/gustav_scene.npz, written by oracle/make_golden.py through the
+    product's pose.csv / PLY readers), 1 061 813 observations.  K5 against the numpy restatement on a sample, the
+    cost against the float64 sum of the residuals, and LM from the perturbed start back to the noise floor."""
+    g = golden("gustav_scene")
+    pb = synth.ba_problem_from_scene(g["K"], g["cams"], g["pts"])
+    assert len(pb["obs"]) == 1_061_813 and len(pb["pts0"]) == 19_282 and len(pb["cams0"]) == 57
+    prob = sfm.BAProblem(engine, 57, 19_282, pb["cam_idx"], pb["pt_idx"], pb["obs"], pb["K"])
+    prob.set_params(pb["cams0"], pb["pts0"])
+    out = prob.eval(0)
+    sel = np.random.default_rng(2).choice(len(pb["obs"]), 3000, replace=False)
+    rr, Jc, Jp = restated.ba_residual_jacobian(pb["cams0"], pb["pts0"], pb["cam_idx"][sel], pb["pt_idx"][sel], pb["obs"][sel], pb["K"])
+    assert np.abs(out["r"][sel] - rr).max() <= 1e-4 * np.abs(rr).max()
+    assert np.abs(out["Jc"][sel] - Jc).max() <= 1e-5 * np.abs(Jc).max()
+    r = out["r"].astype(np.float64)
+    assert abs(out["cost"] - 0.5 * (r * r).sum()) <= 1e-6 * out["cost"]
+    hist = prob.solve(max_iters=15)
+    noise_floor = 0.5 * 2 * len(pb["obs"]) * 0.5 ** 2                  # 0.5 px noise on both coordinates
+    assert hist[-1]["cost_after"] < 1.05 * noise_floor < 0.2 * hist[0]["cost_before"]
+    cams, pts = prob.get_params()
+    # gauge freedom (a similarity transform) aside, the scene comes back: compare reprojection, not coordinates
+    assert np.sqrt(2 * hist[-1]["cost_after"] / (2 * len(pb["obs"]))) < 0.52
+    prob.close()
 
 
 def test_ba_create_rejects_bad_input(engine):

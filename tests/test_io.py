@@ -54,3 +54,15 @@ def test_reads_the_reference_artifacts():
     assert abs(np.linalg.det(Rt[:, :3]) - 1.0) < 1e-9
     pts, col = sio.load_ply("/root/reference/Point_Cloud/sparse.ply")
     assert len(pts) == 19282 and col.dtype == np.uint8
+
+
+def test_lookup_colors_equals_the_reference_expression():
+    """sfm.py:392-395: pts1_reg = np.array(temp2, dtype=np.int32); colors = np.array([img2[l[1], l[0]] for l in pts1_reg.T])"""
+    from sfm_mvs_b200 import io as sio
+    rng = np.random.default_rng(3)
+    img2 = rng.integers(0, 256, (648, 968, 3), dtype=np.uint8)
+    temp2 = np.stack([rng.uniform(0, 967.9, 500), rng.uniform(0, 647.9, 500)]).astype(np.float32)     # (2,N) as in the loop
+    pts1_reg = np.array(temp2, dtype=np.int32)
+    want = np.array([img2[l[1], l[0]] for l in pts1_reg.T])
+    assert np.array_equal(sio.lookup_colors(img2, temp2), want)
+    assert np.array_equal(sio.lookup_colors(img2, temp2.T.copy()), want)

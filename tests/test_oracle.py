@@ -220,6 +220,14 @@ def test_cvpath_ba_equals_reference(golden):
     assert np.allclose(X, g["ba_X"], rtol=0, atol=1e-9) and np.allclose(Rt, g["ba_Rt"], atol=1e-9)
 
 
+def test_cvpath_track_residual_equals_reference(golden):
+    """test.py:85-113 (the residual of the track pipeline's BundleAdjustment) against the fixture produced by the
+    reference's own def, its global-`track` and column-stride quirks included."""
+    g = golden("ba_tracks")
+    res = cvpath.OptimReprojectionError_tracks(g["x"], g["cloud"].size, g["poses"].size, g["track"].size, int(g["img_tot"]), g["track"])
+    assert np.array_equal(res, g["residual"])
+
+
 def test_restated_ba_jacobian_equals_cv2_projectpoints():
     rng = np.random.default_rng(3)
     K = synth.K_GUSTAV

@@ -52,14 +52,10 @@ for rep in range(5):
     t2 = now()
     res = pipeline.register_device(ctx, K, kp_dev, des_dev, Rt0, Rt1)
     t3 = now()
-    t_il = float("nan")
-    try:                                          # experimental driver (copies submitted chunk by chunk)
-        o2 = pipeline.register_host_interleaved(ctx, K, kp_host, des_host, Rt0, Rt1)
-        pipeline.fetch_clouds(ctx, o2)
-        t_il = now() - t3
-        assert [o["n_match"] for o in o2] == [o["n_match"] for o in outs]
-    except Exception as exc:                      # noqa: BLE001  (a profiling script: report and go on)
-        print("register_host_interleaved failed:", exc)
+    o2 = pipeline.register_host(ctx, K, kp_host, des_host, Rt0, Rt1, ahead=10 ** 6)      # every copy submitted up front
+    pipeline.fetch_clouds(ctx, o2)
+    t_il = now() - t3
+    assert [o["n_match"] for o in o2] == [o["n_match"] for o in outs]
     print(f"rep {rep}: copy submission {1e3 * t_submit:.2f} ms (copies done after {1e3 * (t1 - t0):.2f}) | "
           f"register_host + fetch {1e3 * (t2 - t1):.2f} ms | register_device {1e3 * (t3 - t2):.2f} ms | "
-          f"interleaved host driver + fetch {1e3 * t_il:.2f} ms | {len(outs)} views")
+          f"all copies submitted up front {1e3 * t_il:.2f} ms | {len(outs)} views")
