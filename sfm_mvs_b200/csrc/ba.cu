@@ -129,9 +129,18 @@ __global__ void __launch_bounds__(THREADS, 1) ba_eval_kernel(const float2* __res
                                                           const double* __restrict__ cam_pre, int n_cam,
                                                           const double* __restrict__ pts, Intr K, double inv_n,
                                                           float* __restrict__ r_out, float* __restrict__ Jc_out,
-                                                          float* __restrict__ Jp_out, double* __restrict__ cost) {
+                                                          float* __restrict__ Jp_out, double* __restrict__ cost,
+                                                          unsigned long long* __restrict__ tl = nullptr) {
   extern __shared__ __align__(128) double s_cam[];
   __shared__ __align__(8) unsigned long long s_bar;
+  auto stamp = [&](int k) {          // diagnostics (SFM_BA_EVAL_TIMELINE): %globaltimer per CTA at the phase boundaries
+    if (tl && threadIdx.x == 0) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      tl[5 * blockIdx.x + k] = t;
+    }
+  };
+  stamp(0);
   if (SMEM_CAMS) {
     const uint32_t bar = ba_smem_u32(&s_bar);
     if (threadIdx.x == 0) {
@@ -169,6 +178,8 @@ __global__ void __launch_bounds__(THREADS, 1) ba_eval_kernel(const float2* __res
       if (spin > (1u << 22)) asm volatile("trap;");
     }
   }
+  stamp(1);
+  bool first_trip = true;
   for (; o < n_obs; o += stride) {
     const float2 m = m_n;
     const int c = c_n, p = p_n;
@@ -215,7 +226,9 @@ __global__ void __launch_bounds__(THREADS, 1) ba_eval_kernel(const float2* __res
         if (r_out) r_out[o] = (float)a;
       }
     }
+    if (first_trip) { stamp(2); first_trip = false; }
   }
+  stamp(3);
   if (cost) {
     local = warp_sum_d(local);
     __shared__ double s_part[32];
@@ -227,11 +240,22 @@ __global__ void __launch_bounds__(THREADS, 1) ba_eval_kernel(const float2* __res
       atomicAdd(cost, 0.5 * s);
     }
   }
+  stamp(4);
 }
 
 // ------------------------------------------------------------------ K6: fused Schur accumulation
 __device__ __forceinline__ void red_add_v2(float* addr, float a, float b) {
   asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+// S is stored by 6x6 camera blocks: block (ca, cb) is 36 contiguous floats (row-major inside), so a block's
+// contribution is 9 16-byte reductions into 144 contiguous bytes instead of 18 8-byte ones into 6 rows 12 KB apart
+// (K6 is bound by the number of reductions the L2 slices retire).
+__device__ __forceinline__ void red_add_block36(float* blk, const float* v) {
+#pragma unroll
+  for (int q = 0; q < 9; ++q) red_add_v4(blk + 4 * q, v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
 }
 
 // 3x3 symmetric (h = xx,xy,xz,yy,yz,zz) with damped diagonal -> inverse (same packing)
@@ -280,17 +304,15 @@ __device__ __forceinline__ void point_accumulate(WarpPoint& wp, int lane, int o_
 #pragma unroll
       for (int k = 0; k < 3; ++k) wp.W[a][3 * i + k] = (float)(Jc[0][i] * Jp[0][k] + Jc[1][i] * Jp[1][k]);
     if (accumulate_cam) {
-      float* Sd = S + (size_t)(6 * c) * ld + 6 * c;
+      float* Sd = S + ((size_t)c * (ld / 6) + c) * 36;
+      float blk[36];
 #pragma unroll
       for (int i = 0; i < 6; ++i) {
-        float row[6];
 #pragma unroll
-        for (int j = 0; j < 6; ++j) row[j] = (float)(Jc[0][i] * Jc[0][j] + Jc[1][i] * Jc[1][j]);
-        red_add_v2(Sd + (size_t)i * ld, row[0], row[1]);
-        red_add_v2(Sd + (size_t)i * ld + 2, row[2], row[3]);
-        red_add_v2(Sd + (size_t)i * ld + 4, row[4], row[5]);
-        atomicAdd(hdiag + 6 * c + i, row[i]);
+        for (int j = 0; j < 6; ++j) blk[6 * i + j] = (float)(Jc[0][i] * Jc[0][j] + Jc[1][i] * Jc[1][j]);
+        atomicAdd(hdiag + 6 * c + i, blk[7 * i]);
       }
+      red_add_block36(Sd, blk);
       float gc[6];
 #pragma unroll
       for (int i = 0; i < 6; ++i) gc[i] = (float)(Jc[0][i] * r[0] + Jc[1][i] * r[1]);
@@ -305,7 +327,8 @@ __device__ __forceinline__ void point_accumulate(WarpPoint& wp, int lane, int o_
   for (int k = 0; k < 3; ++k) bp[k] = warp_sum_d(b[k]);
 }
 
-constexpr int SCHUR_WARPS = 4;
+constexpr int SCHUR_WARPS = 12;     // with S stored by 6x6 blocks (16-byte reductions): 4 warps 0.79 ms, 8: 0.73, 12: 0.71 (row-major S, 8-byte: 0.90 / - / 1.04)
+constexpr int UPDATE_WARPS = 12;    // the point update is latency-bound: 0.33 -> 0.16 ms from 4 to 12 warps per SM
 
 // S -= sum_p W Hpp^-1 W^T (lower block triangle), g += bc - W Hpp^-1 bp, diag blocks += Hcc.
 template <bool SMEM_CAMS>
@@ -365,17 +388,14 @@ __global__ void __launch_bounds__(SCHUR_WARPS * 32) ba_schur_kernel(const float2
       if (ca < cb) continue;
       const float* Ta = wp.T[a];
       const float* Wb = wp.W[b];
-      float* Sd = S + (size_t)(6 * ca) * ld + 6 * cb;
+      float* Sd = S + ((size_t)ca * (ld / 6) + cb) * 36;
+      float blk[36];
 #pragma unroll
-      for (int i = 0; i < 6; ++i) {
-        float row[6];
+      for (int i = 0; i < 6; ++i)
 #pragma unroll
         for (int j = 0; j < 6; ++j)
-          row[j] = -(Ta[3 * i] * Wb[3 * j] + Ta[3 * i + 1] * Wb[3 * j + 1] + Ta[3 * i + 2] * Wb[3 * j + 2]);
-        red_add_v2(Sd + (size_t)i * ld, row[0], row[1]);
-        red_add_v2(Sd + (size_t)i * ld + 2, row[2], row[3]);
-        red_add_v2(Sd + (size_t)i * ld + 4, row[4], row[5]);
-      }
+          blk[6 * i + j] = -(Ta[3 * i] * Wb[3 * j] + Ta[3 * i + 1] * Wb[3 * j + 1] + Ta[3 * i + 2] * Wb[3 * j + 2]);
+      red_add_block36(Sd, blk);
     }
     __syncwarp();
   }
@@ -386,19 +406,19 @@ __global__ void __launch_bounds__(SCHUR_WARPS * 32) ba_schur_kernel(const float2
 // S[ii] += lambda * Hcc[ii]
 __global__ void ba_damp_kernel(float* __restrict__ S, int ld, const float* __restrict__ hdiag, double lambda, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) S[(size_t)i * ld + i] += (float)(lambda * (double)hdiag[i]);
+  if (i < n) S[((size_t)(i / 6) * (ld / 6) + i / 6) * 36 + 7 * (i % 6)] += (float)(lambda * (double)hdiag[i]);
 }
 
 // ------------------------------------------------------------------ back-substitution + update
 // dp = -Hpp_d^-1 (bp + sum_a W_a^T dc[cam_a]);  candidate point = point + dp
 template <bool SMEM_CAMS>
-__global__ void __launch_bounds__(SCHUR_WARPS * 32) ba_update_points_kernel(
+__global__ void __launch_bounds__(UPDATE_WARPS * 32) ba_update_points_kernel(
     const float2* __restrict__ uv, const int* __restrict__ cam_idx, const int* __restrict__ pt_start, int n_pt,
     const double* __restrict__ cam_pre, int n_cam, const double* __restrict__ pts, Intr K, double lambda,
     const double* __restrict__ dc, double* __restrict__ pts_new, double* __restrict__ step2) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   WarpPoint* wps = reinterpret_cast<WarpPoint*>(smem_raw);
-  double* s_cam = reinterpret_cast<double*>(smem_raw + sizeof(WarpPoint) * SCHUR_WARPS);
+  double* s_cam = reinterpret_cast<double*>(smem_raw + sizeof(WarpPoint) * UPDATE_WARPS);
   if (SMEM_CAMS) {
     for (int i = threadIdx.x; i < n_cam * CAM_PRE; i += blockDim.x) s_cam[i] = cam_pre[i];
     __syncthreads();
@@ -407,7 +427,7 @@ __global__ void __launch_bounds__(SCHUR_WARPS * 32) ba_update_points_kernel(
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   WarpPoint& wp = wps[warp];
   double step_local = 0.0;
-  for (int p = blockIdx.x * SCHUR_WARPS + warp; p < n_pt; p += gridDim.x * SCHUR_WARPS) {
+  for (int p = blockIdx.x * UPDATE_WARPS + warp; p < n_pt; p += gridDim.x * UPDATE_WARPS) {
     const int o_begin = __ldg(pt_start + p), nobs = __ldg(pt_start + p + 1) - o_begin;
     const double X[3] = {__ldg(pts + 3 * (size_t)p), __ldg(pts + 3 * (size_t)p + 1), __ldg(pts + 3 * (size_t)p + 2)};
     if (nobs <= 0) {
@@ -486,14 +506,33 @@ int launch_eval_v(sfm_ba* ba, const double* pts, float* r, float* Jc, float* Jp,
       attr = true;
     }
   }
+  unsigned long long* tl = nullptr;
+  if (big && getenv("SFM_BA_EVAL_TIMELINE")) {
+    SFM_TRY(ws_alloc_t(ctx, (size_t)5 * grid, &tl));
+    SFM_CUDA(cudaMemsetAsync(tl, 0, sizeof(unsigned long long) * 5 * grid, ctx->stream));
+  }
   if (big)
     SFM_LAUNCH(ctx, SFM_K_BA_EVAL, (ba_eval_kernel<MODE, SM, 512, true><<<grid, threads, smem, ctx->stream>>>(
                                        ba->uv, ba->cam_idx, ba->pt_idx, ba->n_obs, ba->cam_pre, ba->n_cam, pts,
-                                       make_intr(ba), inv_n, r, Jc, Jp, cost_dev)));
+                                       make_intr(ba), inv_n, r, Jc, Jp, cost_dev, tl)));
   else
     SFM_LAUNCH(ctx, SFM_K_BA_EVAL, (ba_eval_kernel<MODE, SM><<<grid, threads, smem, ctx->stream>>>(
                                        ba->uv, ba->cam_idx, ba->pt_idx, ba->n_obs, ba->cam_pre, ba->n_cam, pts,
                                        make_intr(ba), inv_n, r, Jc, Jp, cost_dev)));
+  if (tl) {
+    std::vector<unsigned long long> h((size_t)5 * grid);
+    SFM_CUDA(cudaMemcpyAsync(h.data(), tl, sizeof(unsigned long long) * h.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    SFM_CUDA(cudaStreamSynchronize(ctx->stream));
+    unsigned long long t0 = ~0ull;
+    for (int b = 0; b < grid; ++b) t0 = std::min(t0, h[5 * b]);
+    const char* names[5] = {"CTA start", "camera table in shared memory", "first trip done", "last trip done", "end"};
+    for (int k = 0; k < 5; ++k) {
+      unsigned long long lo = ~0ull, hi = 0, sum = 0;
+      for (int b = 0; b < grid; ++b) { const unsigned long long v = h[5 * b + k] - t0; lo = std::min(lo, v); hi = std::max(hi, v); sum += v; }
+      fprintf(stderr, "[ba_eval timeline] %-30s min %6.2f  mean %6.2f  max %6.2f us after the first CTA started\n", names[k], lo * 1e-3,
+              sum * 1e-3 / grid, hi * 1e-3);
+    }
+  }
   return SFM_OK;
 }
 
@@ -512,13 +551,13 @@ int build_system(sfm_ba* ba, double lambda) {
   SFM_CUDA(cudaMemsetAsync(ba->scal, 0, 8 * sizeof(double), ctx->stream));
   const size_t wp_bytes = sizeof(WarpPoint) * SCHUR_WARPS;
   const size_t smem_cams = cam_smem_bytes(ba);
-  const bool in_smem = wp_bytes + smem_cams <= 160 * 1024;
+  const bool in_smem = wp_bytes + smem_cams <= 216 * 1024;
   int grid = std::max(1, std::min(div_up(ba->n_pt, SCHUR_WARPS), ctx->sm_count * (in_smem ? 1 : 4)));
   if (ba->n_pt > 0) {
     if (in_smem) {
       static bool attr = false;
       if (!attr) {
-        SFM_CUDA(cudaFuncSetAttribute(ba_schur_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        SFM_CUDA(cudaFuncSetAttribute(ba_schur_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
         attr = true;
       }
       SFM_LAUNCH(ctx, SFM_K_BA_SCHUR, (ba_schur_kernel<true><<<grid, SCHUR_WARPS * 32, wp_bytes + smem_cams, ctx->stream>>>(
@@ -543,18 +582,18 @@ int build_system(sfm_ba* ba, double lambda) {
 
 int update_points(sfm_ba* ba, double lambda) {
   sfm_ctx* ctx = ba->ctx;
-  const size_t wp_bytes = sizeof(WarpPoint) * SCHUR_WARPS;
+  const size_t wp_bytes = sizeof(WarpPoint) * UPDATE_WARPS;
   const size_t smem_cams = cam_smem_bytes(ba);
-  const bool in_smem = wp_bytes + smem_cams <= 160 * 1024;
-  int grid = std::max(1, std::min(div_up(ba->n_pt, SCHUR_WARPS), ctx->sm_count * (in_smem ? 1 : 4)));
+  const bool in_smem = wp_bytes + smem_cams <= 216 * 1024;
+  int grid = std::max(1, std::min(div_up(ba->n_pt, UPDATE_WARPS), ctx->sm_count * (in_smem ? 1 : 4)));
   if (ba->n_pt == 0) return SFM_OK;
   if (in_smem) {
     static bool attr = false;
     if (!attr) {
-      SFM_CUDA(cudaFuncSetAttribute(ba_update_points_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+      SFM_CUDA(cudaFuncSetAttribute(ba_update_points_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
       attr = true;
     }
-    SFM_LAUNCH(ctx, SFM_K_BA_UPDATE, (ba_update_points_kernel<true><<<grid, SCHUR_WARPS * 32, wp_bytes + smem_cams, ctx->stream>>>(
+    SFM_LAUNCH(ctx, SFM_K_BA_UPDATE, (ba_update_points_kernel<true><<<grid, UPDATE_WARPS * 32, wp_bytes + smem_cams, ctx->stream>>>(
                                          ba->uv, ba->cam_idx, ba->pt_start, ba->n_pt, ba->cam_pre, ba->n_cam, ba->pts,
                                          make_intr(ba), lambda, ba->dc, ba->pts_new, ba->scal + 2)));
   } else {
@@ -563,7 +602,7 @@ int update_points(sfm_ba* ba, double lambda) {
       SFM_CUDA(cudaFuncSetAttribute(ba_update_points_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
       attr = true;
     }
-    SFM_LAUNCH(ctx, SFM_K_BA_UPDATE, (ba_update_points_kernel<false><<<grid, SCHUR_WARPS * 32, wp_bytes, ctx->stream>>>(
+    SFM_LAUNCH(ctx, SFM_K_BA_UPDATE, (ba_update_points_kernel<false><<<grid, UPDATE_WARPS * 32, wp_bytes, ctx->stream>>>(
                                          ba->uv, ba->cam_idx, ba->pt_start, ba->n_pt, ba->cam_pre, ba->n_cam, ba->pts,
                                          make_intr(ba), lambda, ba->dc, ba->pts_new, ba->scal + 2)));
   }
@@ -721,6 +760,16 @@ extern "C" int sfm_ba_read(sfm_ba* ba, int which, float* out, int64_t count) {
   else if (which == 2) { src = ba->hdiag; have = n; }
   SFM_REQUIRE(src, "sfm_ba_read: which=%d", which);
   SFM_REQUIRE(count <= have, "sfm_ba_read: count %lld > %lld", (long long)count, (long long)have);
+  if (which == 0) {            // S lives in 6x6 blocks (block (ca, cb) = 36 contiguous floats): hand it out row-major
+    SFM_REQUIRE(count == have && !sfm_is_device_ptr(out), "sfm_ba_read: S is read whole, into host memory");
+    std::vector<float> tiled((size_t)have);
+    SFM_CUDA(cudaMemcpyAsync(tiled.data(), src, sizeof(float) * (size_t)have, cudaMemcpyDeviceToHost, ba->ctx->stream));
+    SFM_CUDA(cudaStreamSynchronize(ba->ctx->stream));
+    const int C = ba->n_cam;
+    for (int r = 0; r < n; ++r)
+      for (int c = 0; c < n; ++c) out[(size_t)r * n + c] = tiled[((size_t)(r / 6) * C + c / 6) * 36 + 6 * (r % 6) + c % 6];
+    return SFM_OK;
+  }
   SFM_CUDA(cudaMemcpyAsync(out, src, sizeof(float) * (size_t)count, cudaMemcpyDefault, ba->ctx->stream));
   SFM_CUDA(cudaStreamSynchronize(ba->ctx->stream));
   return SFM_OK;

@@ -102,9 +102,11 @@ struct PnpResult {          // device-resident, copied to the host once
   int best_iter, iters_run, best_count, n_inliers, refine_iters, ok, pad0, pad1;
 };
 
+// rt6 (rvec | tvec per hypothesis) is given when the caller supplied the minimal solutions; the engine's own solver
+// leaves only the poses (R | t) and the winner's rvec — OpenCV's Rodrigues(R) — is formed here, for the winner alone.
 __device__ inline void pnp_replay(const int* __restrict__ counts, const unsigned char* __restrict__ valid, int n,
                                   int max_iters, double conf, const double* __restrict__ rt6,
-                                  PnpResult* __restrict__ res) {
+                                  const double* __restrict__ poses, PnpResult* __restrict__ res) {
   int niters = max_iters, best = 0, best_it = -1, it = 0;
   while (it < niters) {
     if ((!valid || valid[it]) && counts[it] > max(best, 4)) {
@@ -120,10 +122,18 @@ __device__ inline void pnp_replay(const int* __restrict__ counts, const unsigned
   res->ok = best_it >= 0 ? 1 : 0;
   res->n_inliers = 0;
   res->refine_iters = 0;
-  for (int k = 0; k < 3; ++k) {
-    double r = best_it >= 0 ? rt6[6 * best_it + k] : 0.0, t = best_it >= 0 ? rt6[6 * best_it + 3 + k] : 0.0;
-    res->rvec0[k] = r; res->tvec0[k] = t; res->rvec[k] = r; res->tvec[k] = t;
+  double rv[3] = {0.0, 0.0, 0.0}, tv[3] = {0.0, 0.0, 0.0};
+  if (best_it >= 0) {
+    if (rt6) {
+      for (int k = 0; k < 3; ++k) { rv[k] = rt6[6 * best_it + k]; tv[k] = rt6[6 * best_it + 3 + k]; }
+    } else {
+      double R[9];
+      for (int k = 0; k < 9; ++k) R[k] = poses[12 * (size_t)best_it + k];
+      hm::rotation_log(R, rv);
+      for (int k = 0; k < 3; ++k) tv[k] = poses[12 * (size_t)best_it + 9 + k];
+    }
   }
+  for (int k = 0; k < 3; ++k) { res->rvec0[k] = rv[k]; res->tvec0[k] = tv[k]; res->rvec[k] = rv[k]; res->tvec[k] = tv[k]; }
 }
 
 // Winner's inliers, ascending (single CTA, stable compaction); the test is re-evaluated with the
@@ -332,7 +342,9 @@ __device__ inline void pnp_refine(const float* __restrict__ X,
                                                                     const float* __restrict__ px,
                                                                     const int* __restrict__ inliers, PnpCam cam,
                                                                     int max_iter, PnpResult* __restrict__ res,
-                                                                    long long* __restrict__ dbg = nullptr) {
+                                                                    long long* __restrict__ dbg = nullptr,
+                                                                    const int* __restrict__ local_list = nullptr,
+                                                                    int local_n = 0) {
   __shared__ double sh[REFINE_THREADS / 32][REFINE_NACC];
   __shared__ double part[2][REFINE_NACC];
   const uint32_t crank = NCTA > 1 ? pnp_cluster_rank() : 0u;
@@ -367,8 +379,12 @@ __device__ inline void pnp_refine(const float* __restrict__ X,
 #pragma unroll
     for (int k = 0; k < REFINE_NACC; ++k) acc[k] = 0.0;
     const double tx = param[3], ty = param[4], tz = param[5];
-    for (int q = (int)crank * REFINE_THREADS + threadIdx.x; q < m; q += NCTA * REFINE_THREADS) {
-      const int i = inliers[q];
+    // the inliers this CTA sums over: its own slice of the list (fused tail kernel) or every NCTA-th block of the global one
+    const int q0 = local_list ? (int)threadIdx.x : (int)crank * REFINE_THREADS + (int)threadIdx.x;
+    const int q1 = local_list ? local_n : m;
+    const int qs = local_list ? REFINE_THREADS : NCTA * REFINE_THREADS;
+    for (int q = q0; q < q1; q += qs) {
+      const int i = local_list ? local_list[q] : inliers[q];
       const double Xw[3] = {(double)X[3 * (size_t)i], (double)X[3 * (size_t)i + 1], (double)X[3 * (size_t)i + 2]};
       const double ox = (double)px[2 * (size_t)i], oy = (double)px[2 * (size_t)i + 1];
       const double* R = pj.R;
@@ -598,7 +614,7 @@ __global__ void __launch_bounds__(REFINE_THREADS) pnp_finish_kernel(const float*
   if (n_dev) n = min(n, *n_dev);
   auto tick = [&](int k) { if (po.dbg && threadIdx.x == 0) po.dbg[k] = clock64(); };
   tick(0);
-  if (threadIdx.x == 0) pnp_replay(counts, valid, n, H, conf, rt6, res);
+  if (threadIdx.x == 0) pnp_replay(counts, valid, n, H, conf, rt6, poses, res);
   __threadfence_block();
   __syncthreads();
   tick(1);
@@ -617,6 +633,86 @@ __global__ void __cluster_dims__(REFINE_CLUSTER, 1, 1) __launch_bounds__(REFINE_
                               PnpCam cam, int refine_iters, PnpResult* __restrict__ res, PoseOut po) {
   pnp_refine<REFINE_CLUSTER>(X, px, inliers, cam, refine_iters, res, nullptr);
   if (threadIdx.x == 0 && pnp_cluster_rank() == 0 && po.pose6) pnp_publish(res, po);
+}
+
+// Tail of the RANSAC for the registration loop in ONE cluster launch: replay of the stopping rule (every CTA, same
+// result), the winner's inlier list — each CTA tests its contiguous slice of the points, compacts it in order and the
+// slice counts meet through distributed shared memory, so the global list is ascending — and the LM refinement over
+// the cluster, each CTA summing over its own slice.
+constexpr int TAIL_CHUNK = 2048;
+__device__ __forceinline__ int pnp_ld_dsmem_i32(const int* p, uint32_t rank) {
+  uint32_t a = (uint32_t)__cvta_generic_to_shared(p), ra;
+  int v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(rank));
+  asm volatile("ld.shared::cluster.s32 %0, [%1];" : "=r"(v) : "r"(ra) : "memory");
+  return v;
+}
+
+__global__ void __cluster_dims__(REFINE_CLUSTER, 1, 1) __launch_bounds__(REFINE_THREADS)
+    pnp_tail_cluster_kernel(const float* __restrict__ X, const float* __restrict__ px, int n, const int* __restrict__ counts,
+                            const unsigned char* __restrict__ valid, int H, double conf, const double* __restrict__ poses,
+                            PnpCam cam, float thr2, int refine_iters, int* __restrict__ inliers, PnpResult* __restrict__ res_out,
+                            const int* __restrict__ n_dev, PoseOut po) {
+  __shared__ PnpResult s_res;
+  __shared__ int s_list[TAIL_CHUNK];
+  __shared__ int s_cnt, s_warp_tot[REFINE_THREADS / 32];
+  __shared__ double s_P[12];
+  if (n_dev) n = min(n, *n_dev);
+  const uint32_t crank = pnp_cluster_rank();
+  if (threadIdx.x == 0) {
+    pnp_replay(counts, valid, n, H, conf, nullptr, poses, &s_res);
+    s_cnt = 0;
+  }
+  __syncthreads();
+  const int best = s_res.best_iter;                     // identical in every CTA of the cluster
+  if (best >= 0) {
+    if (threadIdx.x < 12) s_P[threadIdx.x] = poses[12 * (size_t)best + threadIdx.x];
+    __syncthreads();
+    const int chunk = (n + REFINE_CLUSTER - 1) / REFINE_CLUSTER;
+    const int lo = (int)crank * chunk, hi = min(n, lo + chunk);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int start = lo; start < hi; start += REFINE_THREADS) {
+      const int i = start + (int)threadIdx.x;
+      bool f = false;
+      if (i < hi) {
+        const float2 o = __ldg(reinterpret_cast<const float2*>(px) + i);
+        f = is_inlier(s_P, cam, __ldg(X + 3 * (size_t)i), __ldg(X + 3 * (size_t)i + 1), __ldg(X + 3 * (size_t)i + 2), o.x, o.y, thr2);
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, f);
+      if (lane == 0) s_warp_tot[w] = __popc(m);
+      __syncthreads();
+      int off = s_cnt;
+      for (int k = 0; k < w; ++k) off += s_warp_tot[k];
+      if (f) s_list[off + __popc(m & ((1u << lane) - 1u))] = i;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        int tot = 0;
+        for (int k = 0; k < REFINE_THREADS / 32; ++k) tot += s_warp_tot[k];
+        s_cnt += tot;
+      }
+      __syncthreads();
+    }
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    int offset = 0, total = 0;
+    for (uint32_t r = 0; r < REFINE_CLUSTER; ++r) {
+      const int c = pnp_ld_dsmem_i32(&s_cnt, r);
+      offset += (r < crank) ? c : 0;
+      total += c;
+    }
+    for (int k = threadIdx.x; k < s_cnt; k += REFINE_THREADS) inliers[offset + k] = s_list[k];
+    if (threadIdx.x == 0) s_res.n_inliers = total;
+    __syncthreads();
+    if (refine_iters > 0) pnp_refine<REFINE_CLUSTER>(X, px, nullptr, cam, refine_iters, &s_res, nullptr, s_list, s_cnt);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && crank == 0) {
+    *res_out = s_res;
+    if (po.pose6) pnp_publish(&s_res, po);
+  }
+  // nobody leaves while a peer may still read its shared memory (the counts; pnp_refine has its own closing barrier)
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 static PnpCam make_pnp_cam(const double* K) {
@@ -731,7 +827,7 @@ static int pnp_ransac_impl(sfm_ctx* ctx, const float* X, const float* px, int n,
       hflag[47] = atoi(getenv("SFM_PNP_TIMELINE"));
       SFM_CUDA(cudaMemcpyAsync(dbg, hflag, 48 * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
     }
-    SFM_TRY(sfm_pnp_epnp_launch(ctx, dX, dpx, n, H, cam, subs, dposes, drt6, dvalid, dbg, nullptr, nullptr));
+    SFM_TRY(sfm_pnp_epnp_launch(ctx, dX, dpx, n, H, cam, subs, dposes, dvalid, dbg, nullptr, nullptr));
     if (dbg) {   // diagnostics: phase boundaries of hypothesis 0 in SM clocks
       long long hs[32];
       SFM_CUDA(cudaMemcpyAsync(hs, dbg, sizeof(hs), cudaMemcpyDeviceToHost, ctx->stream));
@@ -758,7 +854,7 @@ static int pnp_ransac_impl(sfm_ctx* ctx, const float* X, const float* px, int n,
   PoseOut po0 = PoseOut();
   if (getenv("SFM_PNP_TIMELINE")) SFM_TRY(ws_alloc_t(ctx, 8, &po0.dbg));
   SFM_LAUNCH(ctx, SFM_K_PNP_REFINE, (pnp_finish_kernel<<<1, REFINE_THREADS, 0, ctx->stream>>>(
-                                        dX, dpx, n, dcounts, n == 5 ? nullptr : dvalid, n == 5 ? 1 : H, confidence, dposes, drt6,
+                                        dX, dpx, n, dcounts, n == 5 ? nullptr : dvalid, n == 5 ? 1 : H, confidence, dposes, hyp_rt6 ? drt6 : nullptr,
                                         cam, thr2_eff, n == 5 ? 0 : 20, dinl, dres, nullptr, po0)));
   if (po0.dbg) {
     long long hs[8];
@@ -826,12 +922,11 @@ int sfm_pnp_ransac_dev(sfm_ctx* ctx, const float* X, const float* px, int n_cap,
   const PnpCam cam = make_pnp_cam(K);
   const int H = 100;
   const float thr2 = 64.0f;
-  double *dposes, *drt6;
+  double* dposes;
   unsigned char* dvalid;
   int32_t *dcounts, *dsubs;
   PnpResult* dres;
   SFM_TRY(ws_alloc_t(ctx, (size_t)12 * H, &dposes));
-  SFM_TRY(ws_alloc_t(ctx, (size_t)6 * H, &drt6));
   SFM_TRY(ws_alloc_t(ctx, (size_t)H, &dvalid));
   SFM_TRY(ws_alloc_t(ctx, (size_t)H, &dcounts));
   SFM_TRY(ws_alloc_t(ctx, (size_t)5 * H, &dsubs));
@@ -840,7 +935,7 @@ int sfm_pnp_ransac_dev(sfm_ctx* ctx, const float* X, const float* px, int n_cap,
   subs.count = 0;
   SFM_CUDA(cudaMemsetAsync(dcounts, 0, sizeof(int32_t) * H, ctx->stream));
   if (!subs_dev) SFM_LAUNCH(ctx, SFM_K_MISC, (pnp_subsets_kernel<<<1, 1024, 0, ctx->stream>>>(n_dev, H, raw, dsubs)));
-  SFM_TRY(sfm_pnp_epnp_launch(ctx, X, px, n_cap, H, cam, subs, dposes, drt6, dvalid, nullptr, n_dev, subs_dev ? subs_dev : dsubs));
+  SFM_TRY(sfm_pnp_epnp_launch(ctx, X, px, n_cap, H, cam, subs, dposes, dvalid, nullptr, n_dev, subs_dev ? subs_dev : dsubs));
   dim3 grid(div_up(n_cap, 256), div_up(H, PNP_HG));
   SFM_LAUNCH(ctx, SFM_K_PNP_SCORE, (pnp_score_kernel<<<grid, 256, 0, ctx->stream>>>(X, px, n_cap, dposes, dvalid, H, cam, thr2, dcounts,
                                                                                    nullptr, n_dev)));
@@ -849,12 +944,17 @@ int sfm_pnp_ransac_dev(sfm_ctx* ctx, const float* X, const float* px, int n_cap,
   po.dbg = nullptr;
   if (getenv("SFM_PNP_SINGLE_CTA_REFINE")) {
     SFM_LAUNCH(ctx, SFM_K_PNP_REFINE, (pnp_finish_kernel<<<1, REFINE_THREADS, 0, ctx->stream>>>(
-                                          X, px, n_cap, dcounts, dvalid, H, 0.99, dposes, drt6, cam, thr2, 20, inliers_dev, dres,
+                                          X, px, n_cap, dcounts, dvalid, H, 0.99, dposes, nullptr, cam, thr2, 20, inliers_dev, dres,
                                           n_dev, po)));
     return SFM_OK;
   }
+  if (div_up(n_cap, REFINE_CLUSTER) <= TAIL_CHUNK && !getenv("SFM_PNP_SPLIT_TAIL")) {
+    SFM_LAUNCH(ctx, SFM_K_PNP_REFINE, (pnp_tail_cluster_kernel<<<REFINE_CLUSTER, REFINE_THREADS, 0, ctx->stream>>>(
+                                          X, px, n_cap, dcounts, dvalid, H, 0.99, dposes, cam, thr2, 20, inliers_dev, dres, n_dev, po)));
+    return SFM_OK;
+  }
   SFM_LAUNCH(ctx, SFM_K_PNP_REFINE, (pnp_finish_kernel<<<1, REFINE_THREADS, 0, ctx->stream>>>(
-                                        X, px, n_cap, dcounts, dvalid, H, 0.99, dposes, drt6, cam, thr2, 0, inliers_dev, dres, n_dev,
+                                        X, px, n_cap, dcounts, dvalid, H, 0.99, dposes, nullptr, cam, thr2, 0, inliers_dev, dres, n_dev,
                                         PoseOut())));
   SFM_LAUNCH(ctx, SFM_K_PNP_REFINE, (pnp_refine_cluster_kernel<<<REFINE_CLUSTER, REFINE_THREADS, 0, ctx->stream>>>(
                                         X, px, inliers_dev, cam, 20, dres, po)));

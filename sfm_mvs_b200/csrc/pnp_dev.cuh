@@ -14,9 +14,9 @@ struct PnpSubsets {
   int idx[500];
 };
 
-// H minimal problems, one CTA each.  poses: (H,12) R' (row-major 9) | t, the matrix OpenCV's scoring projects with;
-// rt6: (H,6) rvec | tvec; valid: (H).  n_dev / subs_dev: row count and subsets known to the device only.
+// H minimal problems, one CTA each.  poses: (H,12) R (row-major 9) | t, the solver's output; valid: (H).
+// n_dev / subs_dev: row count and subsets known to the device only.
 // dbg (optional, >= 48 words): clock64 stamps of hypothesis 0 at the phase boundaries, sweeps, raw (R, t).
 int sfm_pnp_epnp_launch(sfm_ctx* ctx, const float* X, const float* px, int n, int H, const PnpCam& cam, const PnpSubsets& subs,
-                        double* poses, double* rt6, unsigned char* valid, long long* dbg, const int* n_dev,
+                        double* poses, unsigned char* valid, long long* dbg, const int* n_dev,
                         const int* subs_dev);

@@ -53,7 +53,7 @@ struct EpnpShared {
 
 __global__ void __launch_bounds__(96) pnp_epnp_kernel(const float* __restrict__ X, const float* __restrict__ px, int n,
                                                       int H, PnpCam cam, const __grid_constant__ PnpSubsets subs,
-                                                      double* __restrict__ poses, double* __restrict__ rt6,
+                                                      double* __restrict__ poses,
                                                       unsigned char* __restrict__ valid, long long* __restrict__ dbg,
                                                       const int* __restrict__ n_dev, const int* __restrict__ subs_dev) {
   __shared__ __align__(16) EpnpShared sh;
@@ -182,17 +182,15 @@ __global__ void __launch_bounds__(96) pnp_epnp_kernel(const float* __restrict__ 
     const int N = hm::epnp_pick(errs);
     const double* R = sh.cand[N].R;
     const double* t = sh.cand[N].t;
-    // OpenCV hands the model on as (rvec, tvec) = (Rodrigues(R), t) and scores with R' = Rodrigues(rvec).  R = U V^T is
-    // orthonormal to rounding already: the log map is taken directly (cv::Rodrigues' own SVD clean-up moves it by ~1e-16)
-    double rv[3], Rr[9];
-    hm::rotation_log(R, rv);
-    hm::rodrigues_to_matrix(rv, Rr);
+    // OpenCV hands the model on as (rvec, tvec) = (Rodrigues(R), t) and scores with R' = Rodrigues(rvec): the round trip
+    // of an R = U V^T that is orthonormal to rounding moves it by ~1e-16, the same order as the last-place differences
+    // between this device's sin / cos / acos and the host libm's — and three transcendental calls executed once, cold,
+    // cost ~6 us of this kernel's critical path.  The scoring kernel projects with R itself; the winner's rvec (LM
+    // start, info) is formed by the replay, for the winner alone.
     double* P = poses + 12 * (size_t)h;
     bool ok = true;
-    for (int k = 0; k < 9; ++k) { P[k] = Rr[k]; ok &= isfinite(Rr[k]); }
+    for (int k = 0; k < 9; ++k) { P[k] = R[k]; ok &= isfinite(R[k]); }
     for (int k = 0; k < 3; ++k) { P[9 + k] = t[k]; ok &= isfinite(t[k]); }
-    rt6[6 * h] = rv[0]; rt6[6 * h + 1] = rv[1]; rt6[6 * h + 2] = rv[2];
-    rt6[6 * h + 3] = t[0]; rt6[6 * h + 4] = t[1]; rt6[6 * h + 5] = t[2];
     valid[h] = ok ? 1 : 0;
     if (dbg && h == 0) {                 // diagnostics: the raw solver output of hypothesis 0
       double* d = reinterpret_cast<double*>(dbg + 32);
@@ -206,9 +204,9 @@ __global__ void __launch_bounds__(96) pnp_epnp_kernel(const float* __restrict__ 
 }  // namespace
 
 int sfm_pnp_epnp_launch(sfm_ctx* ctx, const float* X, const float* px, int n, int H, const PnpCam& cam, const PnpSubsets& subs,
-                        double* poses, double* rt6, unsigned char* valid, long long* dbg, const int* n_dev,
+                        double* poses, unsigned char* valid, long long* dbg, const int* n_dev,
                         const int* subs_dev) {
-  SFM_LAUNCH(ctx, SFM_K_PNP_EPNP, (pnp_epnp_kernel<<<H, 96, 0, ctx->stream>>>(X, px, n, H, cam, subs, poses, rt6, valid, dbg,
+  SFM_LAUNCH(ctx, SFM_K_PNP_EPNP, (pnp_epnp_kernel<<<H, 96, 0, ctx->stream>>>(X, px, n, H, cam, subs, poses, valid, dbg,
                                                                               n_dev, subs_dev)));
   return SFM_OK;
 }
@@ -231,11 +229,10 @@ extern "C" int sfm_epnp_batch(sfm_ctx* ctx, const float* X, const float* px, int
     subs.idx[k] = subsets[k];
   }
   const PnpCam cam = {K[0], K[4], K[2], K[5]};
-  double *dposes, *drt6, *hout;
+  double *dposes, *hout;
   unsigned char* dvalid;
   long long* dbg;
   SFM_TRY(ws_alloc_t(ctx, (size_t)12 * H, &dposes));
-  SFM_TRY(ws_alloc_t(ctx, (size_t)6 * H, &drt6));
   SFM_TRY(ws_alloc_t(ctx, (size_t)H, &dvalid));
   SFM_TRY(hs_alloc_t(ctx, (size_t)12, &hout));
   // one launch per hypothesis slot 0 with the debug block carrying the raw (R, t): H is small in the tests
@@ -245,7 +242,7 @@ extern "C" int sfm_epnp_batch(sfm_ctx* ctx, const float* X, const float* px, int
     for (int k = 0; k < 5; ++k) one.idx[k] = subs.idx[5 * h + k];
     SFM_TRY(ws_alloc_t(ctx, 48, &dbg));
     SFM_CUDA(cudaMemsetAsync(dbg, 0, 48 * sizeof(long long), ctx->stream));
-    SFM_TRY(sfm_pnp_epnp_launch(ctx, dX, dpx, n, 1, cam, one, dposes, drt6, dvalid, dbg, nullptr, nullptr));
+    SFM_TRY(sfm_pnp_epnp_launch(ctx, dX, dpx, n, 1, cam, one, dposes, dvalid, dbg, nullptr, nullptr));
     SFM_CUDA(cudaMemcpyAsync(hout, dbg + 32, sizeof(double) * 12, cudaMemcpyDeviceToHost, ctx->stream));
     SFM_CUDA(cudaStreamSynchronize(ctx->stream));
     memcpy(R9t3 + 12 * (size_t)h, hout, sizeof(double) * 12);

@@ -44,6 +44,8 @@ struct SpdPlan {
   int* flags;                   // one per tile (+ one per inverse): 1 = the final tile is in memory
   int* sync;                    // [0] task counter; [1 ..] back substitution flags: ycol_ready[ntc], x_ready[nsb]
   int* info;
+  long long* stamps;            // diagnostics (SFM_SPD_TIMELINE): cycle counts of the phases of column `probe`'s critical tasks
+  int probe;
 };
 
 __host__ __device__ inline int tile_id(int i, int j, int ntc) { return (i < ntc ? i * (i + 1) / 2 : ntc * (ntc + 1) / 2) + j; }
@@ -80,7 +82,8 @@ __global__ void __launch_bounds__(256) spd_pack_kernel(const float* __restrict__
     const int gr = T * i + r, gc = T * j + c;
     double v;
     if (i == ntc) v = (r == 0 && gc < n) ? -(double)g[gc] : 0.0;
-    else if (gr < n && gc < n) v = (gc <= gr) ? (double)S[(size_t)gr * n + gc] : 0.0;
+    else if (gr < n && gc < n)       // S arrives in 6x6 blocks: block (a, b) = 36 contiguous floats, row-major inside
+      v = (gc <= gr) ? (double)S[((size_t)(gr / 6) * (n / 6) + gc / 6) * 36 + 6 * (gr % 6) + gc % 6] : 0.0;
     else v = (gr == gc) ? 1.0 : 0.0;
     dst[e] = v;
   }
@@ -105,10 +108,12 @@ __device__ __forceinline__ void factor_block(const double* __restrict__ C, doubl
 #pragma unroll
       for (int jj = 0; jj < 16; ++jj) {
         const int j = 16 * seg + jj;
-        double* cb = colbuf[jj];                        // cb[0..63] scaled column j, cb[64] raw diagonal
-        if (row == j) cb[T] = a[jj];
+        double* cb = colbuf[jj];
+        // ONE 64-thread barrier per column: every owner publishes its UNSCALED entry of column j, then reads the
+        // diagonal and the entries it needs and scales them itself (1 / sqrt(d) is formed redundantly by all 64)
+        cb[row] = a[jj];
         asm volatile("bar.sync 1, 64;" ::: "memory");
-        double d = cb[T];
+        double d = cb[j];
         if (!(d > 0.0)) {
           if (row == j && info && *info == 0) *info = pivot_base + j + 1;   // not positive definite
           d = 1.0;
@@ -116,15 +121,18 @@ __device__ __forceinline__ void factor_block(const double* __restrict__ C, doubl
         const double rinv = rsqrt(d);
         const double li = (row == j) ? d * rinv : ((row > j) ? a[jj] * rinv : 0.0);   // L[row][j]
         a[jj] = li;
-        cb[row] = li;
         if (row == j) dinv[j] = rinv;
-        asm volatile("bar.sync 1, 64;" ::: "memory");
+        const double lir = li * rinv;
 #pragma unroll
-        for (int cc = jj + 1; cc < 16; ++cc) {          // remaining columns of this panel
+        for (int cc = jj + 1; cc < 16; ++cc) {          // remaining columns of this panel: a_rc -= l_rj l_cj, l_cj = cb[c] rinv
           const int c = 16 * seg + cc;
-          if (row >= c) a[cc] = fma(-li, cb[c], a[cc]);
+          if (row >= c) a[cc] = fma(-lir, cb[c], a[cc]);
         }
       }
+      // the scaled columns of the panel for the rank-16 update of the columns to the right
+      asm volatile("bar.sync 1, 64;" ::: "memory");     // everybody is done reading the unscaled entries
+#pragma unroll
+      for (int jj = 0; jj < 16; ++jj) colbuf[jj][row] = a[jj];
     }
     __syncthreads();
     if (cseg > seg) {                                   // rank-16 update of the columns to the right
@@ -210,6 +218,9 @@ __global__ void __launch_bounds__(256, 1) spd_factor_kernel(SpdPlan p) {
     int j = 0, rem = q;
     while (rem >= ntc + 1 - j) { rem -= ntc + 1 - j; ++j; }
     const int i = j + rem;
+    const bool tl = p.stamps && j == p.probe && i <= j + 1 && threadIdx.x == 0;     // probe: tasks (j, j) and (j + 1, j)
+    long long* st = p.stamps + (i == j ? 0 : 8);
+    long long t_wait = 0, t_load = 0, t_mma = 0, t0 = 0;
     double* tile = p.tiles + (size_t)tile_id(i, j, ntc) * TT;
     double acc[4][4];                                             // acc[b][a]: column tx + 16 b, row 4 ty + a
 #pragma unroll
@@ -221,11 +232,13 @@ __global__ void __launch_bounds__(256, 1) spd_factor_kernel(SpdPlan p) {
 #pragma unroll 1
     for (int k = 0; k < j; ++k) {
       const int ia = tile_id(i, k, ntc), ib = tile_id(j, k, ntc);
+      if (tl) t0 = clock64();
       if (threadIdx.x == 0) {
         wait_flag(p.flags + ia);
         if (ib != ia) wait_flag(p.flags + ib);
       }
       __syncthreads();
+      if (tl) { const long long t = clock64(); t_wait += t - t0; t0 = t; }
       {
         const double2* ga = reinterpret_cast<const double2*>(p.tiles + (size_t)ia * TT);
         const double2* gb = reinterpret_cast<const double2*>(p.tiles + (size_t)ib * TT);
@@ -238,6 +251,7 @@ __global__ void __launch_bounds__(256, 1) spd_factor_kernel(SpdPlan p) {
         }
       }
       __syncthreads();
+      if (tl) { const long long t = clock64(); t_load += t - t0; t0 = t; }
 #pragma unroll 4
       for (int kk = 0; kk < T; ++kk) {
         const double2 a01 = *reinterpret_cast<const double2*>(As + kk * T + 4 * ty);
@@ -250,7 +264,9 @@ __global__ void __launch_bounds__(256, 1) spd_factor_kernel(SpdPlan p) {
           for (int a = 0; a < 4; ++a) acc[b][a] = fma(-av[a], bv[b], acc[b][a]);
       }
       __syncthreads();
+      if (tl) { const long long t = clock64(); t_mma += t - t0; t0 = t; }
     }
+    if (tl) { st[0] = t_wait; st[1] = t_load; st[2] = t_mma; st[3] = j; t0 = clock64(); }
     // the updated block, column-major, into As
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
@@ -260,10 +276,12 @@ __global__ void __launch_bounds__(256, 1) spd_factor_kernel(SpdPlan p) {
     if (i == j) {
       __syncthreads();
       factor_block(As, tile, p.dinv + T * j, T * j, p.info, colbuf);
+      if (tl) st[4] = clock64() - t0;
     } else {
       const int id = tile_id(j, j, ntc);
       if (threadIdx.x == 0) wait_flag(p.flags + id);
       __syncthreads();
+      if (tl) { const long long t = clock64(); st[4] = t - t0; t0 = t; }
       {
         const double2* gb = reinterpret_cast<const double2*>(p.tiles + (size_t)id * TT);
         double2* sb = reinterpret_cast<double2*>(Bs);
@@ -294,10 +312,13 @@ __global__ void __launch_bounds__(256, 1) spd_factor_kernel(SpdPlan p) {
 #pragma unroll
         for (int c = 0; c < T; ++c) tile[c * T + r] = x[c];
       }
+      if (tl) st[5] = clock64() - t0;
     }
+    if (tl) t0 = clock64();
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) st_release(p.flags + tile_id(i, j, ntc), 1);
+    if (tl) st[6] = clock64() - t0;
   }
 }
 
@@ -418,6 +439,8 @@ static SpdPlan make_plan(int n, double* A, int* info) {
   p.flags = reinterpret_cast<int*>(p.xbuf + (size_t)p.ntc * T);
   p.sync = p.flags + ntiles + p.ntc;
   p.info = info;
+  p.stamps = nullptr;
+  p.probe = 0;
   return p;
 }
 
@@ -444,7 +467,22 @@ int sfm_spd_solve(sfm_ctx* ctx, const float* S, const float* g, int n, double* A
     attr_set = true;
   }
   const int grid = std::min(ctx->sm_count, p.ntasks + p.ntc);
+  long long* dstamps = nullptr;
+  if (getenv("SFM_SPD_TIMELINE")) {
+    SFM_TRY(ws_alloc_t(ctx, 16, &dstamps));
+    SFM_CUDA(cudaMemsetAsync(dstamps, 0, 16 * sizeof(long long), ctx->stream));
+    p.stamps = dstamps;
+    p.probe = std::min(p.ntc - 2, std::max(1, atoi(getenv("SFM_SPD_TIMELINE"))));
+  }
   SFM_LAUNCH(ctx, SFM_K_BA_SOLVE, (spd_factor_kernel<<<grid, 256, FACTOR_SMEM, ctx->stream>>>(p)));
+  if (dstamps) {
+    long long h[16];
+    SFM_CUDA(cudaMemcpyAsync(h, dstamps, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    SFM_CUDA(cudaStreamSynchronize(ctx->stream));
+    fprintf(stderr, "[spd column %lld] diagonal task: wait %lld | load %lld | update %lld | cholesky %lld | publish %lld  ||  tile below: wait %lld | load %lld | update %lld | "
+            "wait for L(k,k) %lld | triangular solve (incl. load) %lld | publish %lld   (cycles, %lld update steps each)\n",
+            h[3], h[0], h[1], h[2], h[4], h[6], h[8], h[9], h[10], h[12], h[13], h[14], h[3]);
+  }
   SFM_LAUNCH(ctx, SFM_K_BA_SOLVE, (spd_backsolve_kernel<<<p.ntc + 1, 256, 0, ctx->stream>>>(p)));
   SFM_LAUNCH(ctx, SFM_K_BA_SOLVE, (spd_copy_x_kernel<<<div_up(n, 256), 256, 0, ctx->stream>>>(p.xbuf, n, x)));
   return SFM_OK;
