@@ -45,18 +45,21 @@ __device__ __forceinline__ void dlt_null_vector(double (&At)[4][4], double (&out
         double a = W[i], b = W[j], p = 0.0;
 #pragma unroll
         for (int k = 0; k < 4; ++k) p += At[i][k] * At[j][k];
-        if (fabs(p) <= eps * sqrt(a * b)) continue;
+        // This kernel re-triangulates on the pose-critical path of the registration loop, one thread per point: its
+        // time is (rotations) x (dependent latency of one rotation).  OpenCV's test is decided on the squares where
+        // that is certain (hostmath.h), and OpenCV's (c, s) — a hypot, two quotients and two square roots, ~550
+        // cycles of dependent float64 latency — is formed from two reciprocal square roots instead:
+        //   gamma = hypot(p, beta);  q = (gamma + |beta|) / (2 gamma) = (1 + |beta| / gamma) / 2;
+        //   r1 = sqrt(q);  r2 = p / (2 gamma r1)   ->   ig = rsqrt(p^2 + beta^2), q = (1 + |beta| ig) / 2,
+        //   iq = rsqrt(q), r1 = q iq, r2 = p ig iq / 2          (~180 cycles; same rotation to a few ulp)
+        if (hm::cv_jacobi_skip(p, a, b, eps)) continue;
         p *= 2.0;
-        double beta = a - b, gamma = sqrt(p * p + beta * beta);   // moderate magnitudes: no overflow guard needed
-        double c, s;
-        if (beta < 0.0) {
-          double delta = (gamma - beta) * 0.5;
-          s = sqrt(delta / gamma);
-          c = p / (gamma * s * 2.0);
-        } else {
-          c = sqrt((gamma + beta) / (gamma * 2.0));
-          s = p / (gamma * c * 2.0);
-        }
+        const double beta = a - b;
+        const double ig = rsqrt(p * p + beta * beta);
+        const double q = 0.5 + 0.5 * fabs(beta) * ig;
+        const double iq = rsqrt(q);
+        const double r1 = q * iq, r2 = 0.5 * p * ig * iq;
+        const double c = beta < 0.0 ? r2 : r1, s = beta < 0.0 ? r1 : r2;
         a = 0.0;
         b = 0.0;
 #pragma unroll
