@@ -304,7 +304,7 @@ __device__ __forceinline__ void point_accumulate(WarpPoint& wp, int lane, int o_
 #pragma unroll
       for (int k = 0; k < 3; ++k) wp.W[a][3 * i + k] = (float)(Jc[0][i] * Jp[0][k] + Jc[1][i] * Jp[1][k]);
     if (accumulate_cam) {
-      float* Sd = S + ((size_t)c * (ld / 6) + c) * 36;
+      float* Sd = S + ((size_t)c * (c + 1) / 2 + c) * 36;
       float blk[36];
 #pragma unroll
       for (int i = 0; i < 6; ++i) {
@@ -388,7 +388,7 @@ __global__ void __launch_bounds__(SCHUR_WARPS * 32) ba_schur_kernel(const float2
       if (ca < cb) continue;
       const float* Ta = wp.T[a];
       const float* Wb = wp.W[b];
-      float* Sd = S + ((size_t)ca * (ld / 6) + cb) * 36;
+      float* Sd = S + ((size_t)ca * (ca + 1) / 2 + cb) * 36;
       float blk[36];
 #pragma unroll
       for (int i = 0; i < 6; ++i)
@@ -406,7 +406,7 @@ __global__ void __launch_bounds__(SCHUR_WARPS * 32) ba_schur_kernel(const float2
 // S[ii] += lambda * Hcc[ii]
 __global__ void ba_damp_kernel(float* __restrict__ S, int ld, const float* __restrict__ hdiag, double lambda, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) S[((size_t)(i / 6) * (ld / 6) + i / 6) * 36 + 7 * (i % 6)] += (float)(lambda * (double)hdiag[i]);
+  if (i < n) S[((size_t)(i / 6) * (i / 6 + 1) / 2 + i / 6) * 36 + 7 * (i % 6)] += (float)(lambda * (double)hdiag[i]);
 }
 
 // ------------------------------------------------------------------ back-substitution + update
@@ -639,7 +639,10 @@ extern "C" int sfm_ba_create(sfm_ctx* ctx, int n_cam, int n_pt, int n_obs, const
   ba->n_pt_total = n_pt; ba->n_obs_total = n_obs;
   memcpy(ba->K, K, 9 * sizeof(double));
   const int n = 6 * n_cam;
-  ba->sys_count = (size_t)n * n + 2 * (size_t)n;
+  // S: the lower block triangle only, block (ca, cb), cb <= ca, = 36 contiguous floats at ((ca (ca+1) / 2) + cb) * 36 —
+  // half the bytes to clear, to all-reduce and to keep in L2
+  const size_t s_floats = (size_t)n_cam * (n_cam + 1) / 2 * 36;
+  ba->sys_count = s_floats + 2 * (size_t)n;
   cudaError_t e = cudaSuccess;
   auto A = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes ? bytes : 16); };
   A((void**)&ba->uv, sizeof(float2) * (size_t)n_obs);
@@ -661,7 +664,7 @@ extern "C" int sfm_ba_create(sfm_ctx* ctx, int n_cam, int n_pt, int n_obs, const
     sfm_ba_destroy(ba);
     return SFM_ERR_NOMEM;
   }
-  ba->g = ba->S + (size_t)n * n;
+  ba->g = ba->S + s_floats;
   ba->hdiag = ba->g + n;
   cudaStream_t st = ctx->stream;
   if (n_obs) {
@@ -760,14 +763,17 @@ extern "C" int sfm_ba_read(sfm_ba* ba, int which, float* out, int64_t count) {
   else if (which == 2) { src = ba->hdiag; have = n; }
   SFM_REQUIRE(src, "sfm_ba_read: which=%d", which);
   SFM_REQUIRE(count <= have, "sfm_ba_read: count %lld > %lld", (long long)count, (long long)have);
-  if (which == 0) {            // S lives in 6x6 blocks (block (ca, cb) = 36 contiguous floats): hand it out row-major
+  if (which == 0) {            // S lives as the lower triangle of 6x6 blocks: hand it out row-major (upper blocks zero)
     SFM_REQUIRE(count == have && !sfm_is_device_ptr(out), "sfm_ba_read: S is read whole, into host memory");
-    std::vector<float> tiled((size_t)have);
-    SFM_CUDA(cudaMemcpyAsync(tiled.data(), src, sizeof(float) * (size_t)have, cudaMemcpyDeviceToHost, ba->ctx->stream));
+    const size_t s_floats = (size_t)ba->n_cam * (ba->n_cam + 1) / 2 * 36;
+    std::vector<float> tiled(s_floats);
+    SFM_CUDA(cudaMemcpyAsync(tiled.data(), src, sizeof(float) * s_floats, cudaMemcpyDeviceToHost, ba->ctx->stream));
     SFM_CUDA(cudaStreamSynchronize(ba->ctx->stream));
-    const int C = ba->n_cam;
     for (int r = 0; r < n; ++r)
-      for (int c = 0; c < n; ++c) out[(size_t)r * n + c] = tiled[((size_t)(r / 6) * C + c / 6) * 36 + 6 * (r % 6) + c % 6];
+      for (int c = 0; c < n; ++c) {
+        const size_t ca = r / 6, cb = c / 6;
+        out[(size_t)r * n + c] = cb <= ca ? tiled[(ca * (ca + 1) / 2 + cb) * 36 + 6 * (r % 6) + c % 6] : 0.f;
+      }
     return SFM_OK;
   }
   SFM_CUDA(cudaMemcpyAsync(out, src, sizeof(float) * (size_t)count, cudaMemcpyDefault, ba->ctx->stream));

@@ -109,13 +109,11 @@ int sfm_ba_allreduce_system(sfm_ba* ba) {
   SFM_NCCL(g_nccl.AllReduce(ba->S, ba->S, ba->sys_count, NCCL_FLOAT, NCCL_SUM, (nccl_comm_t)ba->comm, st));
   SFM_NCCL(g_nccl.AllReduce(ba->scal, ba->scal, 1, NCCL_DOUBLE, NCCL_SUM, (nccl_comm_t)ba->comm, st));
   SFM_NCCL(g_nccl.GroupEnd());
-  ba->ctx->total_launches += 2;
   return SFM_OK;
 }
 
 int sfm_ba_allreduce_scalars(sfm_ba* ba) {
   if (!ba->comm || ba->world == 1) return SFM_OK;
   SFM_NCCL(g_nccl.AllReduce(ba->scal + 1, ba->scal + 1, 2, NCCL_DOUBLE, NCCL_SUM, (nccl_comm_t)ba->comm, ba->ctx->stream));
-  ba->ctx->total_launches += 1;
   return SFM_OK;
 }

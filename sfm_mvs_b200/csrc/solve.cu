@@ -82,8 +82,8 @@ __global__ void __launch_bounds__(256) spd_pack_kernel(const float* __restrict__
     const int gr = T * i + r, gc = T * j + c;
     double v;
     if (i == ntc) v = (r == 0 && gc < n) ? -(double)g[gc] : 0.0;
-    else if (gr < n && gc < n)       // S arrives in 6x6 blocks: block (a, b) = 36 contiguous floats, row-major inside
-      v = (gc <= gr) ? (double)S[((size_t)(gr / 6) * (n / 6) + gc / 6) * 36 + 6 * (gr % 6) + gc % 6] : 0.0;
+    else if (gr < n && gc < n)       // S arrives as the lower triangle of 6x6 blocks: block (a, b), b <= a, at (a (a+1) / 2 + b) * 36
+      v = (gc <= gr) ? (double)S[((size_t)(gr / 6) * (gr / 6 + 1) / 2 + gc / 6) * 36 + 6 * (gr % 6) + gc % 6] : 0.0;
     else v = (gr == gc) ? 1.0 : 0.0;
     dst[e] = v;
   }

@@ -4,7 +4,7 @@
 
 #include "common.cuh"
 
-// Solves S x = -g.  S (n x n float32 stored by 6x6 blocks — block (a, b) = 36 contiguous floats —, lower triangle read;
+// Solves S x = -g.  S (float32, the lower triangle of 6x6 blocks: block (a, b), b <= a, = 36 contiguous floats at (a (a+1) / 2 + b) * 36;
 // n is a multiple of 6), g (n float32), A: (n+1) x n float64
 // scratch (factor L is left in its lower triangle), x (n float64), info: device int, 0 or the
 // 1-based index of the first non-positive pivot.  Stream-ordered, no host synchronisation.

@@ -51,11 +51,14 @@ class DeviceView:
         import torch
         self.ctx = ctx
         self.n = int(len(kp))
-        with torch.cuda.stream(ctx.torch_stream()):
-            if _e._is_torch(kp):
-                self.kp = kp.to(device=ctx.torch_device, dtype=torch.float32).contiguous()
-            else:
-                self.kp = torch.from_numpy(np.ascontiguousarray(kp, np.float32)).to(ctx.torch_device)
+        if _e._is_torch(kp) and kp.is_cuda and kp.dtype == torch.float32 and kp.is_contiguous() and kp.device == ctx.torch_device:
+            self.kp = kp                      # resident already: nothing to enqueue (thousands of views per call otherwise pay
+        else:                                 # a stream-context switch each)
+            with torch.cuda.stream(ctx.torch_stream()):
+                if _e._is_torch(kp):
+                    self.kp = kp.to(device=ctx.torch_device, dtype=torch.float32).contiguous()
+                else:
+                    self.kp = torch.from_numpy(np.ascontiguousarray(kp, np.float32)).to(ctx.torch_device)
         self.desc = desc if desc is not None else ctx.descriptors(des)
 
     @classmethod
@@ -587,8 +590,9 @@ def match_pairs_sharded(ctx: _e.Context, views, pairs, rank: int = 0, world: int
     them.  No other data-path collective.  `views` are DeviceView on this rank's context (every rank holds the
     descriptors of the views its pairs touch).  -> (my pair indices, their PairMatches, counts of all pairs)."""
     from . import sharding
-    costs = [views[a].n * views[b].n for a, b in pairs]
-    mine = sharding.shard_pairs(pairs, costs, world)[rank]
+    nv = np.array([v.n for v in views], np.float64)
+    pa = np.array(pairs, np.int64).reshape(-1, 2)
+    mine = sharding.shard_pairs(pairs, nv[pa[:, 0]] * nv[pa[:, 1]], world)[rank]
     chain = RegistrationChain(ctx, np.eye(3), ratio=ratio)
     matches = chain.match_pairs(views, [pairs[k] for k in mine])
     counts = sharding.gather_pair_counts([pm.n for pm in matches], mine, len(pairs), dist=dist, device=ctx.torch_device)

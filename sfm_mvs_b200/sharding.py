@@ -15,15 +15,24 @@ import numpy as np
 
 
 def shard_pairs(pairs, costs, world: int):
-    """LPT assignment.  Returns a list (per rank) of lists of pair indices, each ascending."""
+    """LPT assignment (longest processing time first: every pair, in order of decreasing cost, goes to the least
+    loaded rank; ties to the lowest rank).  Returns a list (per rank) of lists of pair indices, each ascending.
+    Equal costs — every view has the same number of descriptors — make LPT a round robin, taken without the loop
+    (the list has V^2 / 2 entries and this runs inside the timed matching call)."""
+    import heapq
     costs = np.asarray(costs, dtype=np.float64)
+    n = len(costs)
+    if world <= 1:
+        return [list(range(n))]
+    if n and costs.min() == costs.max():
+        return [list(range(r, n, world)) for r in range(world)]
     order = np.argsort(-costs, kind="stable")
-    load = np.zeros(world)
+    heap = [(0.0, r) for r in range(world)]
     out = [[] for _ in range(world)]
-    for k in order:
-        r = int(np.argmin(load))
-        out[r].append(int(k))
-        load[r] += costs[k]
+    for k in order.tolist():
+        load, r = heapq.heappop(heap)
+        out[r].append(k)
+        heapq.heappush(heap, (load + costs[k], r))
     return [sorted(o) for o in out]
 
 
