@@ -30,8 +30,8 @@
 
 namespace {
 
-struct CandShared {        // one beta initialisation (one warp); At / sq first: their rows are read as double2
-  double At[30], sq[30];
+struct CandShared {        // one beta initialisation (one warp); At first: its rows are read as double2
+  double At[30];
   double Vt[25], W[5], Wtmp[5];
   double ut[30], vts[25];  // sorted, normalised
   double pcs[15];
@@ -42,7 +42,7 @@ struct CandShared {        // one beta initialisation (one warp); At / sq first:
 static_assert(sizeof(CandShared) % 16 == 0, "CandShared rows are read as double2");
 
 struct EpnpShared {
-  double At[144], sq[144];
+  double At[144];
   CandShared cand[3];
   double pw[15], us[10], alphas[20], cws[12];
   double M[120], W[12], Wtmp[12];
@@ -109,14 +109,12 @@ __global__ void __launch_bounds__(96) pnp_epnp_kernel(const float* __restrict__ 
 #pragma unroll
       for (int k = 0; k < 10; ++k) s0 += sh.M[12 * k + r] * sh.M[12 * k + c];
       sh.At[12 * r + c] = s0; sh.At[12 * c + r] = s0;
-      const double q = s0 * s0;
-      sh.sq[12 * r + c] = q; sh.sq[12 * c + r] = q;
     }
     __syncwarp();
     tick(2);
-    const int sweeps = (dbg && h == 0 && dbg[47] == 2) ? wave_jacobi<12, true>(sh.At, sh.sq, nullptr, sh.sched, 12, lane, dbg + 11)
-                                       : wave_jacobi<12>(sh.At, sh.sq, nullptr, sh.sched, 12, lane);
-    wave_sort<12>(sh.sq, 12, sh.W, sh.ord, sh.Wtmp, lane);
+    const int sweeps = (dbg && h == 0 && dbg[47] == 2) ? wave_jacobi<12, true>(sh.At, nullptr, sh.sched, 12, lane, dbg + 11)
+                                       : wave_jacobi<12>(sh.At, nullptr, sh.sched, 12, lane);
+    wave_sort<12>(sh.At, 12, sh.W, sh.ord, sh.Wtmp, lane);
     tick(3);
     if (dbg && h == 0 && lane == 0) dbg[10] = sweeps;
     // v[q] = left singular vector of the (q+1)-th smallest singular value: sorted row 11 - q, scaled by 1 / sigma
@@ -146,12 +144,11 @@ __global__ void __launch_bounds__(96) pnp_epnp_kernel(const float* __restrict__ 
       const int c = e / 6, i = e - 6 * c;
       const double x = sh.L[10 * i + hm::epnp_approx_col(ap, c)];
       cs.At[e] = x;
-      cs.sq[e] = x * x;
     }
     for (int e = lane; e < nc * nc; e += 32) cs.Vt[e] = (e / nc == e % nc) ? 1.0 : 0.0;
     __syncwarp();
-    wave_jacobi<6>(cs.At, cs.sq, cs.Vt, cs.sched, nc, lane);
-    wave_sort<6>(cs.sq, nc, cs.W, cs.ord, cs.Wtmp, lane);
+    wave_jacobi<6>(cs.At, cs.Vt, cs.sched, nc, lane);
+    wave_sort<6>(cs.At, nc, cs.W, cs.ord, cs.Wtmp, lane);
     for (int e = lane; e < 6 * nc; e += 32) {
       const int r = e / 6, k = e - 6 * r;
       const double sd = cs.W[r];

@@ -10,12 +10,11 @@
 namespace {
 
 // One-sided Jacobi SVD (OpenCV JacobiSVDImpl_<double>) of n rows of length M (At, row stride M) by one warp, as a
-// wavefront over the pairs.  sq holds the squares of At's entries (OpenCV's running |Ai|^2 is the ordered sum of the
-// squares formed at the row's last rotation, or of the initial entries).  Vt (n x n, identity on entry) may be null.
+// wavefront over the pairs.  Vt (n x n, identity on entry) may be null.
 // sched: n x 8 words of scratch.  Returns the number of sweeps that rotated something.  On return the rows are
 // orthogonal, NOT yet sorted / normalised.
 template <int M, bool TIMED = false>
-__device__ __noinline__ int wave_jacobi(double* __restrict__ At, double* __restrict__ sq, double* __restrict__ Vt,
+__device__ __noinline__ int wave_jacobi(double* __restrict__ At, double* __restrict__ Vt,
                                         int* __restrict__ sched, const int n, const int lane,
                                         long long* __restrict__ stamps = nullptr) {
   static_assert(M % 2 == 0, "rows are read as double2");
@@ -54,16 +53,16 @@ __device__ __noinline__ int wave_jacobi(double* __restrict__ At, double* __restr
       double p = 0.0, a = 0.0, b = 0.0;
       double mi[CPL], mj[CPL], vi[3], vj[3];
       if (act) {
+        // OpenCV's running |Ai|^2 is the ordered sum of the squares formed at the row's last rotation (or of the
+        // initial entries): the squares of the entries as they stand — recomputed here rather than kept in a second array
         const double2* Ai = reinterpret_cast<const double2*>(At + i * M);
         const double2* Aj = reinterpret_cast<const double2*>(At + j * M);
-        const double2* Qi = reinterpret_cast<const double2*>(sq + i * M);
-        const double2* Qj = reinterpret_cast<const double2*>(sq + j * M);
 #pragma unroll
         for (int k = 0; k < M / 2; ++k) {
-          const double2 x = Ai[k], y = Aj[k], qa = Qi[k], qb = Qj[k];
+          const double2 x = Ai[k], y = Aj[k];
           p += x.x * y.x; p += x.y * y.y;
-          a += qa.x; a += qa.y;
-          b += qb.x; b += qb.y;
+          a += x.x * x.x; a += x.y * x.y;
+          b += y.x * y.x; b += y.y * y.y;
         }
 #pragma unroll
         for (int q = 0; q < CPL; ++q) {
@@ -110,7 +109,6 @@ __device__ __noinline__ int wave_jacobi(double* __restrict__ At, double* __restr
               const double t0 = c * mi[q] + s * mj[q];
               const double t1 = -s * mi[q] + c * mj[q];
               At[i * M + k] = t0; At[j * M + k] = t1;
-              sq[i * M + k] = t0 * t0; sq[j * M + k] = t1 * t1;
             }
           }
           if (Vt) {
@@ -158,14 +156,14 @@ __device__ __noinline__ int wave_jacobi(double* __restrict__ At, double* __restr
 // ord[pos].  Distinct values have one descending order, found by ranking in parallel; equal values (never seen on
 // this path) take the serial loop with OpenCV's swaps.
 template <int M>
-__device__ __forceinline__ void wave_sort(const double* __restrict__ sq, int n, double* __restrict__ W, int* __restrict__ ord,
+__device__ __forceinline__ void wave_sort(const double* __restrict__ At, int n, double* __restrict__ W, int* __restrict__ ord,
                                           double* __restrict__ Wtmp, int lane) {
   __syncwarp();
   double w = 0.0;
   if (lane < n) {
     double sd = 0.0;
 #pragma unroll
-    for (int k = 0; k < M; ++k) sd += sq[lane * M + k];
+    for (int k = 0; k < M; ++k) { const double t = At[lane * M + k]; sd += t * t; }
     w = sqrt(sd);
     Wtmp[lane] = w;
   }
