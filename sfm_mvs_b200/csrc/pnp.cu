@@ -761,15 +761,178 @@ extern "C" int sfm_pnp_score(sfm_ctx* ctx, const float* X, const float* px, int 
   return SFM_OK;
 }
 
+// ---- npoints == 4: cv2.solvePnPRansac does not iterate — model_points == npoints, so it calls
+// solvePnP(flags = SOLVEPNP_P3P) once: the perspective-three-point problem on the first three correspondences, the
+// fourth choosing among its (up to four) solutions by reprojection error, every point reported as an inlier, no
+// refinement (calib3d solvepnp.cpp).  OpenCV's p3p.cpp is not restated operation for operation (its result is the
+// root of a quartic, not a rounding-order-dependent decision): this is Grunert's formulation — the three cosine-law
+// equations in the depths s1, s2 = u s1, s3 = v s1 reduced to a quartic in v — with the four roots found by one lane
+// each (Durand-Kerner, then Newton on the real axis) and the pose from the two triangles' orthonormal frames.
+// Agreement with cv2: R, t to ~1e-5 (cv2's own solution leaves ~1e-5 px on the three points), same root chosen.
+__device__ inline void p3p_frame(const double* A, const double* B, const double* C, double* F /*3x3, columns e1 e2 e3*/) {
+  double e1[3] = {B[0] - A[0], B[1] - A[1], B[2] - A[2]};
+  double w[3] = {C[0] - A[0], C[1] - A[1], C[2] - A[2]};
+  double n1 = rsqrt(e1[0] * e1[0] + e1[1] * e1[1] + e1[2] * e1[2]);
+  for (int k = 0; k < 3; ++k) e1[k] *= n1;
+  double e3[3] = {e1[1] * w[2] - e1[2] * w[1], e1[2] * w[0] - e1[0] * w[2], e1[0] * w[1] - e1[1] * w[0]};
+  double n3 = rsqrt(e3[0] * e3[0] + e3[1] * e3[1] + e3[2] * e3[2]);
+  for (int k = 0; k < 3; ++k) e3[k] *= n3;
+  const double e2[3] = {e3[1] * e1[2] - e3[2] * e1[1], e3[2] * e1[0] - e3[0] * e1[2], e3[0] * e1[1] - e3[1] * e1[0]};
+  for (int k = 0; k < 3; ++k) { F[3 * k] = e1[k]; F[3 * k + 1] = e2[k]; F[3 * k + 2] = e3[k]; }
+}
+
+__global__ void __launch_bounds__(32) pnp_p3p4_kernel(const float* __restrict__ X, const float* __restrict__ px, PnpCam cam,
+                                                      int32_t* __restrict__ inl, PnpResult* __restrict__ res) {
+  const int lane = threadIdx.x;
+  double P[4][3], f[4][3], q[4][2];
+  for (int i = 0; i < 4; ++i) {
+    for (int k = 0; k < 3; ++k) P[i][k] = (double)X[3 * i + k];
+    q[i][0] = (double)px[2 * i]; q[i][1] = (double)px[2 * i + 1];
+    const double x = (q[i][0] - cam.cx) / cam.fx, y = (q[i][1] - cam.cy) / cam.fy;
+    const double nn = rsqrt(x * x + y * y + 1.0);
+    f[i][0] = x * nn; f[i][1] = y * nn; f[i][2] = nn;
+  }
+  auto d2 = [&](int i, int j) { double s = 0; for (int k = 0; k < 3; ++k) s += (P[i][k] - P[j][k]) * (P[i][k] - P[j][k]); return s; };
+  auto dt = [&](int i, int j) { return f[i][0] * f[j][0] + f[i][1] * f[j][1] + f[i][2] * f[j][2]; };
+  const double a2 = d2(1, 2), b2 = d2(0, 2), c2 = d2(0, 1);
+  const double ca = dt(1, 2), cb = dt(0, 2), cg = dt(0, 1);
+  bool good = a2 > 0.0 && b2 > 0.0 && c2 > 0.0;
+  const double ib2 = good ? 1.0 / b2 : 0.0;
+  const double qq = (a2 - c2) * ib2, rr = (a2 + c2) * ib2;
+  double A[5];
+  A[4] = (qq - 1) * (qq - 1) - 4 * c2 * ib2 * ca * ca;
+  A[3] = 4 * (qq * (1 - qq) * cb - (1 - rr) * ca * cg + 2 * c2 * ib2 * ca * ca * cb);
+  A[2] = 2 * (qq * qq - 1 + 2 * qq * qq * cb * cb + 2 * (b2 - c2) * ib2 * ca * ca - 4 * rr * ca * cb * cg + 2 * (b2 - a2) * ib2 * cg * cg);
+  A[1] = 4 * (-qq * (1 + qq) * cb + 2 * a2 * ib2 * cg * cg * cb - (1 - rr) * ca * cg);
+  A[0] = (1 + qq) * (1 + qq) - 4 * a2 * ib2 * cg * cg;
+  good = good && fabs(A[4]) > 1e-14 * (fabs(A[3]) + fabs(A[2]) + fabs(A[1]) + fabs(A[0]));
+  // monic quartic v^4 + m3 v^3 + m2 v^2 + m1 v + m0: lanes 0..3 hold one root each (Durand-Kerner, simultaneous updates)
+  const double i4 = good ? 1.0 / A[4] : 0.0;
+  const double m3 = A[3] * i4, m2 = A[2] * i4, m1 = A[1] * i4, m0 = A[0] * i4;
+  const double bound = 1.0 + fmax(fmax(fabs(m3), fabs(m2)), fmax(fabs(m1), fabs(m0)));
+  const int r4 = lane & 3;
+  // starting points on a circle inside the Cauchy bound, not symmetric about the real axis
+  double zr = 0.5 * bound * cos(0.4 + 1.5707963267948966 * r4), zi = 0.5 * bound * sin(0.4 + 1.5707963267948966 * r4);
+#pragma unroll 1
+  for (int it = 0; it < 200; ++it) {
+    // p(z) by Horner, complex
+    double pr = 1.0, pi = 0.0;
+    const double cs[4] = {m3, m2, m1, m0};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const double tr = pr * zr - pi * zi + cs[k], ti = pr * zi + pi * zr;
+      pr = tr; pi = ti;
+    }
+    double dr = 1.0, di = 0.0;
+#pragma unroll
+    for (int o = 1; o < 4; ++o) {
+      const int src = (lane & ~3) | ((r4 + o) & 3);
+      const double orr = __shfl_sync(0xffffffffu, zr, src), oi = __shfl_sync(0xffffffffu, zi, src);
+      const double er = zr - orr, ei = zi - oi;
+      const double tr = dr * er - di * ei, ti = dr * ei + di * er;
+      dr = tr; di = ti;
+    }
+    const double den = dr * dr + di * di;
+    double sr = 0.0, si = 0.0;
+    if (den > 0.0) { sr = (pr * dr + pi * di) / den; si = (pi * dr - pr * di) / den; }
+    zr -= sr; zi -= si;
+    const bool conv = fabs(sr) + fabs(si) <= 1e-15 * (fabs(zr) + fabs(zi));
+    if (__all_sync(0xffffffffu, conv)) break;
+  }
+  // real roots (a double root carries ~1e-8 of imaginary noise), polished on the real axis
+  double v = zr;
+  bool sol = good && lane < 4 && isfinite(zr) && isfinite(zi) && fabs(zi) <= 1e-6 * fmax(1.0, fabs(zr));
+  if (sol) {
+    for (int it = 0; it < 3; ++it) {
+      const double pv = (((v + m3) * v + m2) * v + m1) * v + m0;
+      const double dv = ((4 * v + 3 * m3) * v + 2 * m2) * v + m1;
+      if (dv != 0.0 && isfinite(pv / dv)) v -= pv / dv;
+    }
+    sol = v > 0.0;
+  }
+  double R[9], t[3], err = INFINITY;
+  if (sol) {
+    const double den = 2 * (cg - v * ca);
+    const double u = ((qq - 1) * v * v - 2 * qq * cb * v + 1 + qq) / den;
+    const double s1sq = b2 / (1 + v * v - 2 * v * cb);
+    sol = den != 0.0 && u > 0.0 && s1sq > 0.0 && isfinite(u) && isfinite(s1sq);
+    if (sol) {
+      const double s1 = sqrt(s1sq), s2 = u * s1, s3 = v * s1;
+      double C[3][3];
+      for (int k = 0; k < 3; ++k) { C[0][k] = s1 * f[0][k]; C[1][k] = s2 * f[1][k]; C[2][k] = s3 * f[2][k]; }
+      double Fw[9], Fc[9];
+      p3p_frame(P[0], P[1], P[2], Fw);
+      p3p_frame(C[0], C[1], C[2], Fc);
+      for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) R[3 * i + j] = Fc[3 * i] * Fw[3 * j] + Fc[3 * i + 1] * Fw[3 * j + 1] + Fc[3 * i + 2] * Fw[3 * j + 2];
+      for (int i = 0; i < 3; ++i) t[i] = C[0][i] - (R[3 * i] * P[0][0] + R[3 * i + 1] * P[0][1] + R[3 * i + 2] * P[0][2]);
+      const double xc = R[0] * P[3][0] + R[1] * P[3][1] + R[2] * P[3][2] + t[0];
+      const double yc = R[3] * P[3][0] + R[4] * P[3][1] + R[5] * P[3][2] + t[1];
+      const double zc = R[6] * P[3][0] + R[7] * P[3][1] + R[8] * P[3][2] + t[2];
+      const double eu = xc / zc * cam.fx + cam.cx - q[3][0], ev = yc / zc * cam.fy + cam.cy - q[3][1];
+      err = eu * eu + ev * ev;
+      sol = isfinite(err);
+      if (!sol) err = INFINITY;
+    }
+  }
+  // the solution with the smallest error on the fourth point; ties to the lowest lane
+  double best = err;
+  int who = sol ? lane : 64;
+  for (int o = 16; o > 0; o >>= 1) {
+    const double oe = __shfl_xor_sync(0xffffffffu, best, o);
+    const int ow = __shfl_xor_sync(0xffffffffu, who, o);
+    if (oe < best || (oe == best && ow < who)) { best = oe; who = ow; }
+  }
+  if (who == 64) {
+    if (lane == 0) {
+      res->ok = 0; res->n_inliers = 0; res->best_iter = -1; res->iters_run = 0; res->best_count = 0; res->refine_iters = 0;
+      for (int k = 0; k < 3; ++k) { res->rvec[k] = res->tvec[k] = res->rvec0[k] = res->tvec0[k] = 0.0; }
+    }
+    return;
+  }
+  if (lane == who) {
+    double rv[3];
+    hm::rotation_log(R, rv);
+    for (int k = 0; k < 3; ++k) { res->rvec[k] = res->rvec0[k] = rv[k]; res->tvec[k] = res->tvec0[k] = t[k]; }
+    res->ok = 1; res->n_inliers = 4; res->best_iter = 0; res->iters_run = 1; res->best_count = 4; res->refine_iters = 0;
+    for (int k = 0; k < 4; ++k) inl[k] = k;
+  }
+}
+
 static int pnp_ransac_impl(sfm_ctx* ctx, const float* X, const float* px, int n, const double* K,
                            const double* hyp_rt6, const uint8_t* hyp_valid, int max_iters, float thr,
                            double confidence, double* rvec, double* tvec, int32_t* inliers, int32_t* n_inliers,
                            int32_t* ok, sfm_pnp_info* info) {
   SFM_REQUIRE(ctx && X && px && K && rvec && tvec && ok, "sfm_pnp_ransac: null argument");
   SFM_REQUIRE(n >= 4, "sfm_pnp_ransac: needs at least 4 correspondences (cv2 asserts npoints >= 4), got %d", n);
-  if (n == 4) {
-    sfm_set_error("sfm_pnp_ransac: the 4-point case runs P3P in OpenCV; not provided by this engine");
-    return SFM_ERR_UNSUPPORTED;
+  if (n == 4) {          // model_points == npoints: one P3P solve, all four points inliers (pnp_p3p4_kernel)
+    SFM_TRY(sfm_ws_begin(ctx));
+    const float *dX4, *dpx4;
+    SFM_TRY(dev_in(ctx, X, (size_t)12, &dX4));
+    SFM_TRY(dev_in(ctx, px, (size_t)8, &dpx4));
+    PnpResult *dres4, *hres4;
+    int32_t *dinl4, *hinl4;
+    SFM_TRY(ws_alloc_t(ctx, 1, &dres4));
+    SFM_TRY(ws_alloc_t(ctx, 4, &dinl4));
+    SFM_TRY(hs_alloc_t(ctx, 1, &hres4));
+    SFM_TRY(hs_alloc_t(ctx, 4, &hinl4));
+    SFM_LAUNCH(ctx, SFM_K_PNP_EPNP, (pnp_p3p4_kernel<<<1, 32, 0, ctx->stream>>>(dX4, dpx4, make_pnp_cam(K), dinl4, dres4)));
+    SFM_CUDA(cudaMemcpyAsync(hres4, dres4, sizeof(PnpResult), cudaMemcpyDeviceToHost, ctx->stream));
+    SFM_CUDA(cudaStreamSynchronize(ctx->stream));
+    *ok = hres4->ok;
+    for (int k = 0; k < 3; ++k) { rvec[k] = hres4->rvec[k]; tvec[k] = hres4->tvec[k]; }
+    const int ni4 = hres4->ok ? 4 : 0;
+    if (n_inliers) *n_inliers = ni4;
+    if (inliers && ni4) {
+      if (sfm_is_device_ptr(inliers)) SFM_CUDA(cudaMemcpyAsync(inliers, dinl4, sizeof(int32_t) * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+      else for (int k = 0; k < 4; ++k) inliers[k] = k;
+    }
+    if (info) {
+      info->iters_run = hres4->iters_run; info->best_iter = hres4->best_iter; info->hyp_solved = 1; info->refine_iters = 0;
+      for (int k = 0; k < 3; ++k) { info->rvec_ransac[k] = hres4->rvec0[k]; info->tvec_ransac[k] = hres4->tvec0[k]; }
+    }
+    (void)hinl4;
+    return SFM_OK;
   }
   SFM_REQUIRE(max_iters >= 1 && max_iters <= PNP_MAX_H, "sfm_pnp_ransac: iterationsCount %d out of range", max_iters);
   SFM_TRY(sfm_ws_begin(ctx));

@@ -161,6 +161,32 @@ def test_solvepnpransac_surface(engine):
     assert ok5 and inl5[:, 0].tolist() == [0, 1, 2, 3, 4]
 
 
+@pytest.mark.parametrize("seed", range(12))
+def test_four_points_is_p3p_with_the_fourth_as_referee(engine, seed):
+    """npoints == 4: cv2.solvePnPRansac runs no RANSAC — model_points == npoints — but one solvePnP(SOLVEPNP_P3P): the
+    three-point problem on rows 0-2, row 3 choosing among its solutions, all four reported as inliers, no refinement.
+    The engine solves the same minimal problem on the device (Grunert's quartic, csrc/pnp.cu pnp_p3p4_kernel): same
+    return convention, the same solution chosen, pose within the north_star 1e-4 (cv2's own P3P leaves ~1e-5 px on its
+    three points, so tighter than ~1e-5 is not there to be had)."""
+    rng = np.random.default_rng(100 + seed)
+    X = (rng.random((4, 3)) * 2).astype(np.float32)
+    X[:, 2] += 4
+    R, _ = cv2.Rodrigues(rng.normal(size=3) * 0.3)
+    t = rng.normal(size=3) * 0.3
+    p = (K @ (R @ X.T + t[:, None])).T
+    p = (p[:, :2] / p[:, 2:] + rng.normal(size=(4, 2)) * (seed % 3)).astype(np.float32)     # exact, 1 px and 2 px noise
+    okc, rc, tc, inlc = cv2.solvePnPRansac(X, p, K, D0, cv2.SOLVEPNP_ITERATIVE)
+    ok, rv, tv, inl = sfm.solvePnPRansac(X, p, K, D0, cv2.SOLVEPNP_ITERATIVE, ctx=engine)
+    assert ok == okc
+    if okc:
+        assert np.array_equal(inl, inlc) and inl.dtype == inlc.dtype and inl[:, 0].tolist() == [0, 1, 2, 3]
+        assert np.abs(cv2.Rodrigues(rv)[0] - cv2.Rodrigues(rc)[0]).max() < 1e-4 and np.abs(tv - tc).max() < 1e-4
+        pr, _ = cv2.projectPoints(X[:3], rv, tv, K, D0)
+        assert np.abs(pr[:, 0] - p[:3]).max() < 1e-3          # a P3P solution: exact on its three points
+    else:
+        assert inl is None
+
+
 # ----------------------------------------------------------------------------- the per-view loop
 def _cv_hyp_fn(X, p):
     return _cv_hypotheses(np.ascontiguousarray(X), np.ascontiguousarray(p))
