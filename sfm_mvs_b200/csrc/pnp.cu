@@ -242,16 +242,36 @@ __device__ inline void pose_jacobian_setup(const double* rv, PoseJac* pj) {
 
 constexpr int REFINE_THREADS = 256;
 constexpr int REFINE_NACC = 28;   // 21 (upper JtJ) + 6 (Jt e) + 1 (|e|^2)
+constexpr int REFINE_CACHED = 2;  // inliers per thread kept in registers across the LM passes
 
+// keep one of (a, b) according to `up`, add the partner lane's other one: after the exchange the lane pair holds
+// the pairwise sums of a (lower lane) and b (upper lane) — one shuffle for two values
+__device__ __forceinline__ double fold_pair(double a, double b, bool up, int o) {
+  const double send = up ? a : b, keep = up ? b : a;
+  return keep + __shfl_xor_sync(0xffffffffu, send, o);
+}
+
+// Sum of the 28 accumulators over the CTA.  Inside a warp the reduction is a reduce-scatter (the values are halved
+// with the lanes: 28 -> 14 -> 7 -> 4 -> 2 -> 1 per lane, 28 shuffles of a double instead of 140); lane l ends up
+// with the warp's total of value vidx(l).
 __device__ inline void block_reduce_acc(double* acc, double (*sh)[REFINE_NACC], double* out) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2, b0 = lane & 1;
+  double v14[14], v7[7], v4[4], v2[2];
 #pragma unroll
-  for (int k = 0; k < REFINE_NACC; ++k) {
-    double v = acc[k];
+  for (int k = 0; k < 14; ++k) v14[k] = fold_pair(acc[k], acc[k + 14], b4, 16);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == 0) sh[w][k] = v;
-  }
+  for (int k = 0; k < 7; ++k) v7[k] = fold_pair(v14[k], v14[k + 7], b3, 8);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) v4[k] = fold_pair(v7[k], v7[k + 4], b2, 4);
+  v4[3] = v7[3] + __shfl_xor_sync(0xffffffffu, v7[3], 4);
+  v2[0] = fold_pair(v4[0], v4[2], b1, 2);
+  v2[1] = fold_pair(v4[1], v4[3], b1, 2);
+  const double v = fold_pair(v2[0], v2[1], b0, 1);
+  const int s3 = (b0 ? 1 : 0) + (b1 ? 2 : 0);
+  const int i7 = s3 < 3 ? s3 + (b2 ? 4 : 0) : 3;
+  const int idx = i7 + (b3 ? 7 : 0) + (b4 ? 14 : 0);
+  if (!(s3 == 3 && b2)) sh[w][idx] = v;              // value 3 of the 7 is held by both halves: the lower one writes
   __syncthreads();
   if (threadIdx.x < REFINE_NACC) {
     double s = 0.0;
@@ -364,6 +384,23 @@ __device__ inline void pnp_refine(const float* __restrict__ X,
     prev_err = 0.0;
   }
   __syncthreads();
+  // the inliers this CTA sums over: its own slice of the list (fused tail kernel) or every NCTA-th block of the global
+  // one.  The list does not change between the passes: a thread's first REFINE_CACHED points stay in registers, so a
+  // pass starts computing at once instead of behind an index -> point chain of global loads.
+  const int q0 = local_list ? (int)threadIdx.x : (int)crank * REFINE_THREADS + (int)threadIdx.x;
+  const int q1 = local_list ? local_n : m;
+  const int qs = local_list ? REFINE_THREADS : NCTA * REFINE_THREADS;
+  double cX[REFINE_CACHED][3], cpx[REFINE_CACHED][2];
+#pragma unroll
+  for (int slot = 0; slot < REFINE_CACHED; ++slot) {
+    const int q = q0 + slot * qs;
+    cX[slot][0] = cX[slot][1] = cX[slot][2] = cpx[slot][0] = cpx[slot][1] = 0.0;
+    if (q < q1) {
+      const int i = local_list ? local_list[q] : inliers[q];
+      cX[slot][0] = (double)X[3 * (size_t)i]; cX[slot][1] = (double)X[3 * (size_t)i + 1]; cX[slot][2] = (double)X[3 * (size_t)i + 2];
+      cpx[slot][0] = (double)px[2 * (size_t)i]; cpx[slot][1] = (double)px[2 * (size_t)i + 1];
+    }
+  }
   // Every pass evaluates the residual AND the normal equations at `param`: when the candidate is
   // accepted its linearisation is already there (OpenCV's CHECK_ERR -> CALC_J pair in one pass).
   for (int guard = 0; guard < 2000; ++guard) {
@@ -379,14 +416,18 @@ __device__ inline void pnp_refine(const float* __restrict__ X,
 #pragma unroll
     for (int k = 0; k < REFINE_NACC; ++k) acc[k] = 0.0;
     const double tx = param[3], ty = param[4], tz = param[5];
-    // the inliers this CTA sums over: its own slice of the list (fused tail kernel) or every NCTA-th block of the global one
-    const int q0 = local_list ? (int)threadIdx.x : (int)crank * REFINE_THREADS + (int)threadIdx.x;
-    const int q1 = local_list ? local_n : m;
-    const int qs = local_list ? REFINE_THREADS : NCTA * REFINE_THREADS;
-    for (int q = q0; q < q1; q += qs) {
-      const int i = local_list ? local_list[q] : inliers[q];
-      const double Xw[3] = {(double)X[3 * (size_t)i], (double)X[3 * (size_t)i + 1], (double)X[3 * (size_t)i + 2]};
-      const double ox = (double)px[2 * (size_t)i], oy = (double)px[2 * (size_t)i + 1];
+    for (int q = q0, slot = 0; q < q1; q += qs, ++slot) {
+      double Xw[3], ox, oy;
+      static_assert(REFINE_CACHED == 2, "the cached slots are selected by hand (static register indices)");
+      if (slot < REFINE_CACHED) {
+        const bool s0 = slot == 0;
+        Xw[0] = s0 ? cX[0][0] : cX[1][0]; Xw[1] = s0 ? cX[0][1] : cX[1][1]; Xw[2] = s0 ? cX[0][2] : cX[1][2];
+        ox = s0 ? cpx[0][0] : cpx[1][0]; oy = s0 ? cpx[0][1] : cpx[1][1];
+      } else {
+        const int i = local_list ? local_list[q] : inliers[q];
+        Xw[0] = (double)X[3 * (size_t)i]; Xw[1] = (double)X[3 * (size_t)i + 1]; Xw[2] = (double)X[3 * (size_t)i + 2];
+        ox = (double)px[2 * (size_t)i]; oy = (double)px[2 * (size_t)i + 1];
+      }
       const double* R = pj.R;
       double x = R[0] * Xw[0] + R[1] * Xw[1] + R[2] * Xw[2] + tx;
       double y = R[3] * Xw[0] + R[4] * Xw[1] + R[5] * Xw[2] + ty;
