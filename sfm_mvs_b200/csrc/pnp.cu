@@ -284,40 +284,7 @@ __device__ inline void block_reduce_acc(double* acc, double (*sh)[REFINE_NACC], 
 // Solve (A with diag *= 1+lambda) x = b for the symmetric 6x6 normal matrix (upper packed row-major
 // in a21): Cholesky; a non-positive pivot (rank-deficient configuration) falls back to the
 // eigen-decomposition pseudo-inverse, which is what OpenCV's DECOMP_SVD solve amounts to.
-__device__ inline void solve6_damped(const double* a21, const double* b, double lambda, double* x) {
-  double A[36];
-  int k = 0;
-  for (int i = 0; i < 6; ++i)
-    for (int j = i; j < 6; ++j) { A[6 * i + j] = a21[k]; A[6 * j + i] = a21[k]; ++k; }
-  for (int i = 0; i < 6; ++i) A[7 * i] *= 1.0 + lambda;
-  double Lc[36];
-  bool pd = true;
-  for (int j = 0; j < 6 && pd; ++j) {
-    double d = A[7 * j];
-    for (int m = 0; m < j; ++m) d -= Lc[6 * j + m] * Lc[6 * j + m];
-    if (!(d > 1e-14 * fabs(A[7 * j]))) { pd = false; break; }
-    const double rj = rsqrt(d);           // Lc[j][j] = d * rj; its reciprocal rj serves every later division
-    Lc[7 * j] = rj;                       // (the diagonal is stored inverted)
-    for (int i = j + 1; i < 6; ++i) {
-      double v = A[6 * i + j];
-      for (int m = 0; m < j; ++m) v -= Lc[6 * i + m] * Lc[6 * j + m];
-      Lc[6 * i + j] = v * rj;
-    }
-  }
-  if (pd) {
-    double y[6];
-    for (int i = 0; i < 6; ++i) {
-      double v = b[i];
-      for (int m = 0; m < i; ++m) v -= Lc[6 * i + m] * y[m];
-      y[i] = v * Lc[7 * i];
-    }
-    for (int i = 5; i >= 0; --i) {
-      double v = y[i];
-      for (int m = i + 1; m < 6; ++m) v -= Lc[6 * m + i] * x[m];
-      x[i] = v * Lc[7 * i];
-    }
-    return;
-  }
+__device__ __noinline__ void solve6_pinv(double* A, const double* b, double* x) {
   double w[6], V[36];
   hm::eig_sym<6>(A, w, V);
   double wmax = fabs(w[5]) > fabs(w[0]) ? fabs(w[5]) : fabs(w[0]);
@@ -330,6 +297,62 @@ __device__ inline void solve6_damped(const double* a21, const double* b, double 
     d /= w[e];
     for (int i = 0; i < 6; ++i) x[i] += d * V[6 * e + i];
   }
+}
+
+// Every loop has constant bounds and is unrolled: the 6 x 6 factor lives in registers (this runs on one thread, on
+// the refinement's critical path, once per LM pass).
+__device__ inline void solve6_damped(const double* a21, const double* b, double lambda, double* x) {
+  double A[6][6], Lc[6][6];
+  {
+    int k = 0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+      for (int j = i; j < 6; ++j) { A[i][j] = a21[k]; A[j][i] = a21[k]; ++k; }
+  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i) A[i][i] *= 1.0 + lambda;
+  bool pd = true;
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    double d = A[j][j];
+#pragma unroll
+    for (int m = 0; m < j; ++m) d -= Lc[j][m] * Lc[j][m];
+    pd = pd && (d > 1e-14 * fabs(A[j][j]));
+    const double rj = rsqrt(pd ? d : 1.0);           // Lc[j][j] = d * rj; its reciprocal rj serves every later division
+    Lc[j][j] = rj;                                   // (the diagonal is stored inverted)
+#pragma unroll
+    for (int i = j + 1; i < 6; ++i) {
+      double v = A[i][j];
+#pragma unroll
+      for (int m = 0; m < j; ++m) v -= Lc[i][m] * Lc[j][m];
+      Lc[i][j] = v * rj;
+    }
+  }
+  if (pd) {
+    double y[6], xx[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      double v = b[i];
+#pragma unroll
+      for (int m = 0; m < i; ++m) v -= Lc[i][m] * y[m];
+      y[i] = v * Lc[i][i];
+    }
+#pragma unroll
+    for (int i = 5; i >= 0; --i) {
+      double v = y[i];
+#pragma unroll
+      for (int m = i + 1; m < 6; ++m) v -= Lc[m][i] * xx[m];
+      xx[i] = v * Lc[i][i];
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) x[i] = xx[i];
+    return;
+  }
+  double Af[36];
+  for (int i = 0; i < 6; ++i)
+    for (int j = 0; j < 6; ++j) Af[6 * i + j] = A[i][j];
+  solve6_pinv(Af, b, x);
 }
 
 // 10^k for the integer-valued log10(lambda) of OpenCV's LM schedule
@@ -353,6 +376,12 @@ __device__ __forceinline__ double pnp_ld_dsmem(const double* p, uint32_t rank) {
   return v;
 }
 
+__device__ __forceinline__ void pnp_st_dsmem(double* p, uint32_t rank, double v) {
+  uint32_t a = (uint32_t)__cvta_generic_to_shared(p), ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(rank));
+  asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(ra), "d"(v) : "memory");
+}
+
 // NCTA > 1: the CTAs of a cluster split the inliers; every pass their 28 partial sums meet through distributed
 // shared memory (one cluster barrier per pass, partials double-buffered) and EVERY CTA then runs the identical
 // scalar LM logic on the identical totals, so no parameter broadcast is needed.  The accumulation is bound by
@@ -366,7 +395,7 @@ __device__ inline void pnp_refine(const float* __restrict__ X,
                                                                     const int* __restrict__ local_list = nullptr,
                                                                     int local_n = 0) {
   __shared__ double sh[REFINE_THREADS / 32][REFINE_NACC];
-  __shared__ double part[2][REFINE_NACC];
+  __shared__ double part[2][NCTA][REFINE_NACC];      // [parity][source CTA]: written by the peers
   const uint32_t crank = NCTA > 1 ? pnp_cluster_rank() : 0u;
   __shared__ double red[REFINE_NACC];
   __shared__ PoseJac pj;
@@ -469,19 +498,26 @@ __device__ inline void pnp_refine(const float* __restrict__ X,
     if (dbg && guard == 1 && threadIdx.x == 0) dbg[6] = clock64();
     block_reduce_acc(acc, sh, red);
     if (NCTA > 1) {
+      // every CTA PUSHES its 28 partial sums into every peer's shared memory (remote stores do not wait), one cluster
+      // barrier, then the totals are summed from local memory in rank order — identical in every CTA
       const int par = guard & 1;
-      if (threadIdx.x < REFINE_NACC) part[par][threadIdx.x] = red[threadIdx.x];
+      if (threadIdx.x < REFINE_NACC * NCTA) {
+        const int k = threadIdx.x % REFINE_NACC;
+        const uint32_t r = threadIdx.x / REFINE_NACC;
+        pnp_st_dsmem(&part[par][crank][k], r, red[k]);
+      }
       asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
       asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
       if (threadIdx.x < REFINE_NACC) {
         double t = 0.0;
 #pragma unroll
-        for (int r = 0; r < NCTA; ++r) t += pnp_ld_dsmem(&part[par][threadIdx.x], (uint32_t)r);
+        for (int r = 0; r < NCTA; ++r) t += part[par][r][threadIdx.x];
         red[threadIdx.x] = t;
       }
       __syncthreads();
     }
     if (dbg && guard == 1 && threadIdx.x == 0) dbg[7] = clock64();
+    if (dbg && threadIdx.x == 0) dbg[11] = guard + 1;
     if (threadIdx.x == 0) {
       const double err_norm = sqrt(red[27]);
       bool relinearise = (state == 0);
@@ -515,6 +551,7 @@ __device__ inline void pnp_refine(const float* __restrict__ X,
         s_state = 1;
       }
     }
+    if (dbg && guard == 1 && threadIdx.x == 0) dbg[10] = clock64();
     __syncthreads();
   }
   if (threadIdx.x == 0 && crank == 0) {
@@ -700,11 +737,14 @@ __global__ void __cluster_dims__(REFINE_CLUSTER, 1, 1) __launch_bounds__(REFINE_
   __shared__ double s_P[12];
   if (n_dev) n = min(n, *n_dev);
   const uint32_t crank = pnp_cluster_rank();
+  auto tick = [&](int k) { if (po.dbg && threadIdx.x == 0 && crank == 0) po.dbg[k] = clock64(); };
+  tick(0);
   if (threadIdx.x == 0) {
     pnp_replay(counts, valid, n, H, conf, nullptr, poses, &s_res);
     s_cnt = 0;
   }
   __syncthreads();
+  tick(1);
   const int best = s_res.best_iter;                     // identical in every CTA of the cluster
   if (best >= 0) {
     if (threadIdx.x < 12) s_P[threadIdx.x] = poses[12 * (size_t)best + threadIdx.x];
@@ -744,8 +784,11 @@ __global__ void __cluster_dims__(REFINE_CLUSTER, 1, 1) __launch_bounds__(REFINE_
     for (int k = threadIdx.x; k < s_cnt; k += REFINE_THREADS) inliers[offset + k] = s_list[k];
     if (threadIdx.x == 0) s_res.n_inliers = total;
     __syncthreads();
-    if (refine_iters > 0) pnp_refine<REFINE_CLUSTER>(X, px, nullptr, cam, refine_iters, &s_res, nullptr, s_list, s_cnt);
+    tick(2);
+    if (refine_iters > 0) pnp_refine<REFINE_CLUSTER>(X, px, nullptr, cam, refine_iters, &s_res, crank == 0 ? po.dbg : nullptr, s_list, s_cnt);
     __syncthreads();
+    tick(3);
+    if (po.dbg && threadIdx.x == 0 && crank == 0) { po.dbg[8] = s_res.refine_iters; po.dbg[9] = total; }
   }
   if (threadIdx.x == 0 && crank == 0) {
     *res_out = s_res;
@@ -1153,8 +1196,16 @@ int sfm_pnp_ransac_dev(sfm_ctx* ctx, const float* X, const float* px, int n_cap,
     return SFM_OK;
   }
   if (div_up(n_cap, REFINE_CLUSTER) <= TAIL_CHUNK && !getenv("SFM_PNP_SPLIT_TAIL")) {
+    if (getenv("SFM_PNP_TIMELINE")) SFM_TRY(ws_alloc_t(ctx, 16, &po.dbg));
     SFM_LAUNCH(ctx, SFM_K_PNP_REFINE, (pnp_tail_cluster_kernel<<<REFINE_CLUSTER, REFINE_THREADS, 0, ctx->stream>>>(
                                           X, px, n_cap, dcounts, dvalid, H, 0.99, dposes, cam, thr2, 20, inliers_dev, dres, n_dev, po)));
+    if (po.dbg) {      // diagnostics only: this synchronises the otherwise asynchronous chain
+      long long hs[16];
+      SFM_CUDA(cudaMemcpyAsync(hs, po.dbg, sizeof(hs), cudaMemcpyDeviceToHost, ctx->stream));
+      SFM_CUDA(cudaStreamSynchronize(ctx->stream));
+      fprintf(stderr, "[pnp cluster tail cycles] replay %lld | inliers %lld | refine %lld (%lld LM iterations in %lld passes, %lld inliers; pass 2: setup %lld, accumulate %lld, reduce %lld, scalar LM step %lld)\n",
+              hs[1] - hs[0], hs[2] - hs[1], hs[3] - hs[2], hs[8], hs[11], hs[9], hs[5] - hs[4], hs[6] - hs[5], hs[7] - hs[6], hs[10] - hs[7]);
+    }
     return SFM_OK;
   }
   SFM_LAUNCH(ctx, SFM_K_PNP_REFINE, (pnp_finish_kernel<<<1, REFINE_THREADS, 0, ctx->stream>>>(

@@ -16,3 +16,8 @@ ctx = sfm.Context(0)
 for _ in range(3):
     ok, r, tt, inl, info = ctx.pnp_ransac(X.astype(np.float32), p.astype(np.float32), K)
 print(info["iters_run"], info["refine_iters"], len(inl))
+
+# the registration loop's fused tail (cluster of 8 CTAs): a short chain at the bench's descriptor count
+from sfm_mvs_b200 import pipeline
+scene = synth.orbit_scene(5, int(sys.argv[2]) if len(sys.argv) > 2 else 5000, seed=1)
+pipeline.register_chain(scene, ctx)
