@@ -191,13 +191,30 @@ struct PoseJac {
 
 // The same, split over three threads of three different warps (K is a compile-time constant per call site, so
 // nothing is indexed dynamically): each forms R in registers and its own dR/dr_K; the K = 0 caller publishes R.
+// exp map for the LM linearisation: one sincos, 1 / theta by rsqrt beside the square root instead of behind it
+// (the refinement is not a bit-exact path: OpenCV sums its normal equations through a GEMM)
+__device__ inline void rodrigues_lm(const double* r, double th2, double* R) {
+  if (th2 < DBL_EPSILON * DBL_EPSILON) {
+    R[0] = 1; R[1] = 0; R[2] = 0; R[3] = 0; R[4] = 1; R[5] = 0; R[6] = 0; R[7] = 0; R[8] = 1;
+    return;
+  }
+  const double it = rsqrt(th2), theta = th2 * it;
+  double s, c;
+  sincos(theta, &s, &c);
+  const double c1 = 1.0 - c;
+  const double x = r[0] * it, y = r[1] * it, z = r[2] * it;
+  R[0] = c + c1 * (x * x);     R[1] = c1 * (x * y) - s * z; R[2] = c1 * (x * z) + s * y;
+  R[3] = c1 * (x * y) + s * z; R[4] = c + c1 * (y * y);     R[5] = c1 * (y * z) - s * x;
+  R[6] = c1 * (x * z) - s * y; R[7] = c1 * (y * z) + s * x; R[8] = c + c1 * (z * z);
+}
+
 template <int K>
 __device__ inline void pose_jacobian_setup_k(const double* rv, PoseJac* pj) {
   double R[9];
-  hm::rodrigues_to_matrix(rv, R);
+  const double th2 = rv[0] * rv[0] + rv[1] * rv[1] + rv[2] * rv[2];
+  rodrigues_lm(rv, th2, R);
   if (K == 0)
     for (int i = 0; i < 9; ++i) pj->R[i] = R[i];
-  const double th2 = rv[0] * rv[0] + rv[1] * rv[1] + rv[2] * rv[2];
   const double e[3] = {K == 0 ? 1.0 : 0.0, K == 1 ? 1.0 : 0.0, K == 2 ? 1.0 : 0.0};
   double S[9];
   if (th2 < 1e-24) {
@@ -739,8 +756,18 @@ __global__ void __cluster_dims__(REFINE_CLUSTER, 1, 1) __launch_bounds__(REFINE_
   const uint32_t crank = pnp_cluster_rank();
   auto tick = [&](int k) { if (po.dbg && threadIdx.x == 0 && crank == 0) po.dbg[k] = clock64(); };
   tick(0);
+  // the replay walks the iterations one by one: counts and validity come into shared memory in one coalesced load
+  // first, instead of one global-memory latency per iteration of the walk
+  __shared__ int s_counts[128];
+  __shared__ unsigned char s_valid[128];
+  const bool staged = H <= 128;
+  if (staged && (int)threadIdx.x < H) {
+    s_counts[threadIdx.x] = counts[threadIdx.x];
+    s_valid[threadIdx.x] = valid ? valid[threadIdx.x] : (unsigned char)1;
+  }
+  __syncthreads();
   if (threadIdx.x == 0) {
-    pnp_replay(counts, valid, n, H, conf, nullptr, poses, &s_res);
+    pnp_replay(staged ? s_counts : counts, staged ? s_valid : valid, n, H, conf, nullptr, poses, &s_res);
     s_cnt = 0;
   }
   __syncthreads();
