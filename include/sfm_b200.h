@@ -328,6 +328,13 @@ int sfm_ba_eval(sfm_ba* ba, int mode, float* r, float* Jc, float* Jp, double* co
  * hands both to the reference's optimiser (scipy TRF).  x, f0, J: host or device. */
 int sfm_ba_reference_fd(sfm_ctx* ctx, const double* x, int n_params, int n_points, double* f0, double* J);
 
+/* The linear solve of one LM step on its own (csrc/solve.cu): S x = -g for the reduced camera system of
+ * ba.bundle_adjustment's normal equations — S symmetric positive definite, given as the lower triangle of 6x6 camera
+ * blocks (block (a, b), b <= a, = 36 row-major float32 at ((a (a+1)) / 2 + b) * 36), g (6 n_cams) float32, x (6 n_cams)
+ * float64, *info = 0 or the 1-based index of the first non-positive pivot.  Host arrays.  The LM step calls the same
+ * solver on device buffers; this entry exists so that it can be checked against a dense factorisation directly. */
+int sfm_reduced_solve(sfm_ctx* ctx, const float* S_blocks, const float* g, int n_cams, double* x, int32_t* info);
+
 typedef struct sfm_ba_stats {
   double cost_before;   /* 0.5*sum r^2 at the linearisation point */
   double cost_after;    /* at the candidate parameters */

@@ -239,15 +239,21 @@ __global__ void __launch_bounds__(256, 1) spd_factor_kernel(SpdPlan p) {
       }
       __syncthreads();
       if (tl) { const long long t = clock64(); t_wait += t - t0; t0 = t; }
+      const double* Bop = (ib == ia) ? As : Bs;                 // the diagonal task multiplies a tile by itself: one load
       {
         const double2* ga = reinterpret_cast<const double2*>(p.tiles + (size_t)ia * TT);
         const double2* gb = reinterpret_cast<const double2*>(p.tiles + (size_t)ib * TT);
         double2* sa = reinterpret_cast<double2*>(As);
         double2* sb = reinterpret_cast<double2*>(Bs);
+        if (ib == ia) {
 #pragma unroll
-        for (int e = 0; e < TT / 2 / 256; ++e) {
-          sa[threadIdx.x + 256 * e] = __ldcg(ga + threadIdx.x + 256 * e);
-          sb[threadIdx.x + 256 * e] = __ldcg(gb + threadIdx.x + 256 * e);
+          for (int e = 0; e < TT / 2 / 256; ++e) sa[threadIdx.x + 256 * e] = __ldcg(ga + threadIdx.x + 256 * e);
+        } else {
+#pragma unroll
+          for (int e = 0; e < TT / 2 / 256; ++e) {
+            sa[threadIdx.x + 256 * e] = __ldcg(ga + threadIdx.x + 256 * e);
+            sb[threadIdx.x + 256 * e] = __ldcg(gb + threadIdx.x + 256 * e);
+          }
         }
       }
       __syncthreads();
@@ -257,7 +263,7 @@ __global__ void __launch_bounds__(256, 1) spd_factor_kernel(SpdPlan p) {
         const double2 a01 = *reinterpret_cast<const double2*>(As + kk * T + 4 * ty);
         const double2 a23 = *reinterpret_cast<const double2*>(As + kk * T + 4 * ty + 2);
         const double av[4] = {a01.x, a01.y, a23.x, a23.y};
-        const double bv[4] = {Bs[kk * T + tx], Bs[kk * T + tx + 16], Bs[kk * T + tx + 32], Bs[kk * T + tx + 48]};
+        const double bv[4] = {Bop[kk * T + tx], Bop[kk * T + tx + 16], Bop[kk * T + tx + 32], Bop[kk * T + tx + 48]};
 #pragma unroll
         for (int b = 0; b < 4; ++b)
 #pragma unroll
@@ -485,5 +491,26 @@ int sfm_spd_solve(sfm_ctx* ctx, const float* S, const float* g, int n, double* A
   }
   SFM_LAUNCH(ctx, SFM_K_BA_SOLVE, (spd_backsolve_kernel<<<p.ntc + 1, 256, 0, ctx->stream>>>(p)));
   SFM_LAUNCH(ctx, SFM_K_BA_SOLVE, (spd_copy_x_kernel<<<div_up(n, 256), 256, 0, ctx->stream>>>(p.xbuf, n, x)));
+  return SFM_OK;
+}
+
+extern "C" int sfm_reduced_solve(sfm_ctx* ctx, const float* S_blocks, const float* g, int n_cams, double* x, int32_t* info) {
+  SFM_REQUIRE(ctx && S_blocks && g && x && info, "sfm_reduced_solve: null argument");
+  SFM_REQUIRE(n_cams >= 1, "sfm_reduced_solve: no cameras");
+  SFM_TRY(sfm_ws_begin(ctx));
+  const int n = 6 * n_cams;
+  const size_t nblk = (size_t)n_cams * (n_cams + 1) / 2;
+  const float *dS, *dg;
+  SFM_TRY(dev_in(ctx, S_blocks, nblk * 36, &dS));
+  SFM_TRY(dev_in(ctx, g, (size_t)n, &dg));
+  double *A, *dx;
+  int* dinfo;
+  SFM_TRY(ws_alloc_t(ctx, sfm_spd_scratch_doubles(n), &A));
+  SFM_TRY(ws_alloc_t(ctx, (size_t)n, &dx));
+  SFM_TRY(ws_alloc_t(ctx, 1, &dinfo));
+  SFM_TRY(sfm_spd_solve(ctx, dS, dg, n, A, dx, dinfo));
+  SFM_CUDA(cudaMemcpyAsync(x, dx, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  SFM_CUDA(cudaMemcpyAsync(info, dinfo, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  SFM_CUDA(cudaStreamSynchronize(ctx->stream));
   return SFM_OK;
 }

@@ -397,6 +397,22 @@ class Context:
         check(lib.sfm_ba_reference_fd(self._h, _dptr(x), len(x), int(n_points), _dptr(f0), None if J is None else _dptr(J)))
         return f0, J
 
+    def reduced_solve(self, S, g):
+        """S x = -g for a dense symmetric positive definite S (6C x 6C, only its lower triangle is read) — the reduced
+        camera system solve of an LM step (csrc/solve.cu) on its own.  Returns (x float64, info)."""
+        S = np.asarray(S)
+        n = S.shape[0]
+        C = n // 6
+        if S.shape != (n, n) or n != 6 * C or C < 1:
+            raise ValueError("reduced_solve: S must be (6C, 6C)")
+        ia, ib = np.tril_indices(C)
+        blocks = np.ascontiguousarray(S.reshape(C, 6, C, 6).transpose(0, 2, 1, 3)[ia, ib], np.float32)     # (a (a+1) / 2 + b): row-major tril order
+        g = np.ascontiguousarray(g, np.float32).ravel()
+        x = np.empty(n)
+        info = np.zeros(1, np.int32)
+        check(lib.sfm_reduced_solve(self._h, _dptr(blocks), _dptr(g), C, _dptr(x), _dptr(info)))
+        return x, int(info[0])
+
     @_stream_ordered
     def epnp_batch(self, X, px, K, subsets):
         """The device minimal solver on explicit 5-point subsets (H,5): (R (H,3,3), t (H,3)), the raw output of

@@ -64,6 +64,28 @@ def test_schur_system_equals_oracle(engine):
     assert np.allclose(hd, np.array([np.diag(h) for h in Hcc]).ravel(), rtol=1e-5)
 
 
+@pytest.mark.parametrize("C", [1, 7, 11, 50, 200, 500])
+def test_reduced_solve_equals_dense_factorisation(engine, C):
+    """The tile-Cholesky graph + flag-driven back substitution (csrc/solve.cu) on its own: S x = -g against LAPACK on
+    the same float32 data, from one tile (n = 6) to BASELINE configs[3]'s 500 cameras (n = 3000, 47 tile columns)."""
+    rng = np.random.default_rng(C)
+    n = 6 * C
+    B = rng.normal(size=(n, n + 8))
+    S = (B @ B.T / n + 0.5 * np.eye(n)).astype(np.float32)
+    S = np.tril(S) + np.tril(S, -1).T                      # what the solver reads: the lower triangle
+    g = rng.normal(size=n).astype(np.float32)
+    x, info = engine.reduced_solve(S, g)
+    ref = np.linalg.solve(S.astype(np.float64), -g.astype(np.float64))
+    assert info == 0
+    assert np.abs(x - ref).max() <= 1e-10 * np.abs(ref).max(), np.abs(x - ref).max() / np.abs(ref).max()
+    # not positive definite: reported, not silently solved
+    Sbad = S.copy()
+    k = n // 2
+    Sbad[k, k] = -1.0
+    _, info_bad = engine.reduced_solve(Sbad, g)
+    assert 1 <= info_bad <= k + 1
+
+
 def test_lm_iterations_reduce_cost_like_dense_gauss_newton(engine):
     pb = _small(seed=2, n_cam=8, n_pt=400, opp=5)
     prob = _make(engine, pb)

@@ -28,6 +28,8 @@ if "pnp" in parts:         # minimal solver (Jacobi wavefront), scoring, replay 
     p = (uv + rng.normal(0, 0.5, uv.shape)).astype(np.float32)
     ok, rvec, tvec, inl, info = ctx.pnp_ransac(X, p, K)
     print("pnp ok", ok, len(inl))
+    ok4, r4, t4, inl4, _ = ctx.pnp_ransac(X[:4], p[:4], K)            # npoints == 4: the P3P kernel
+    print("p3p ok", ok4, None if inl4 is None else len(inl4))
 if "chain" in parts:       # the registration loop: three streams, clustered LM, hash association
     outs = pipeline.register_chain(scene, ctx=ctx)
     print("chain ok", len(outs), [o["n_inl"] for o in outs])
@@ -38,6 +40,9 @@ if "ba" in parts:          # K5, K6, tile Cholesky graph, back substitution, upd
     out = prob.eval(0)
     hist = prob.solve(max_iters=3)
     print("ba ok", hist[0]["cost_before"], hist[-1]["cost_after"])
+    B = np.random.default_rng(2).normal(size=(132, 140))
+    x, info = ctx.reduced_solve(B @ B.T / 132 + 0.5 * np.eye(132), np.ones(132))       # three tile columns
+    print("solve ok", info)
     prob.close()
 if "init" in parts:        # five-point RANSAC + recoverPose
     tv0, tv1, _, _ = synth.two_view_pair(300, seed=3)
