@@ -34,30 +34,6 @@ namespace {
 constexpr int PNP_HG = 4;          // hypotheses per CTA of the scoring kernel
 constexpr int PNP_MAX_H = 1024;
 
-// cv2.projectPoints with zero distortion, operation for operation (see geometry.cu project_cv).
-__device__ __forceinline__ void project_pose(const double* __restrict__ P /*R row-major 9 | t 3*/, const PnpCam& c,
-                                             double X, double Y, double Z, double& u, double& v) {
-  double x = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(P[0], X), __dmul_rn(P[1], Y)), __dmul_rn(P[2], Z)), P[9]);
-  double y = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(P[3], X), __dmul_rn(P[4], Y)), __dmul_rn(P[5], Z)), P[10]);
-  double z = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(P[6], X), __dmul_rn(P[7], Y)), __dmul_rn(P[8], Z)), P[11]);
-  z = (z != 0.0) ? __ddiv_rn(1.0, z) : 1.0;
-  x = __dmul_rn(x, z);
-  y = __dmul_rn(y, z);
-  u = __dadd_rn(__dmul_rn(x, c.fx), c.cx);
-  v = __dadd_rn(__dmul_rn(y, c.fy), c.cy);
-}
-
-// PnPRansacCallback::computeError + findInliers: projection in float64 stored as float32,
-// err = dx*dx + dy*dy in float32 with separately rounded products, inlier iff err <= thr^2.
-__device__ __forceinline__ bool is_inlier(const double* __restrict__ P, const PnpCam& c, float X, float Y, float Z,
-                                          float ox, float oy, float thr2) {
-  double u, v;
-  project_pose(P, c, (double)X, (double)Y, (double)Z, u, v);
-  float dx = __fsub_rn(ox, (float)u), dy = __fsub_rn(oy, (float)v);
-  float e = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
-  return e <= thr2;
-}
-
 // ------------------------------------------------------------------ K4 scoring
 // poses: (H, 12) doubles = R (9, row-major) then t (3).  counts must be zero on entry.
 __global__ void __launch_bounds__(256) pnp_score_kernel(const float* __restrict__ X, const float* __restrict__ px,
@@ -1101,7 +1077,7 @@ static int pnp_ransac_impl(sfm_ctx* ctx, const float* X, const float* px, int n,
       hflag[47] = atoi(getenv("SFM_PNP_TIMELINE"));
       SFM_CUDA(cudaMemcpyAsync(dbg, hflag, 48 * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
     }
-    SFM_TRY(sfm_pnp_epnp_launch(ctx, dX, dpx, n, H, cam, subs, dposes, dvalid, dbg, nullptr, nullptr));
+    SFM_TRY(sfm_pnp_epnp_launch(ctx, dX, dpx, n, H, cam, subs, dposes, dvalid, dbg, nullptr, nullptr, nullptr, 0.f));
     if (dbg) {   // diagnostics: phase boundaries of hypothesis 0 in SM clocks
       long long hs[32];
       SFM_CUDA(cudaMemcpyAsync(hs, dbg, sizeof(hs), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1207,12 +1183,10 @@ int sfm_pnp_ransac_dev(sfm_ctx* ctx, const float* X, const float* px, int n_cap,
   SFM_TRY(ws_alloc_t(ctx, 1, &dres));
   PnpSubsets subs;
   subs.count = 0;
-  SFM_CUDA(cudaMemsetAsync(dcounts, 0, sizeof(int32_t) * H, ctx->stream));
   if (!subs_dev) SFM_LAUNCH(ctx, SFM_K_MISC, (pnp_subsets_kernel<<<1, 1024, 0, ctx->stream>>>(n_dev, H, raw, dsubs)));
-  SFM_TRY(sfm_pnp_epnp_launch(ctx, X, px, n_cap, H, cam, subs, dposes, dvalid, nullptr, n_dev, subs_dev ? subs_dev : dsubs));
-  dim3 grid(div_up(n_cap, 256), div_up(H, PNP_HG));
-  SFM_LAUNCH(ctx, SFM_K_PNP_SCORE, (pnp_score_kernel<<<grid, 256, 0, ctx->stream>>>(X, px, n_cap, dposes, dvalid, H, cam, thr2, dcounts,
-                                                                                   nullptr, n_dev)));
+  // every hypothesis CTA scores its own pose over all points when it is done (K4's arithmetic, pnp_dev.cuh): no
+  // separate scoring launch on the pose-critical path
+  SFM_TRY(sfm_pnp_epnp_launch(ctx, X, px, n_cap, H, cam, subs, dposes, dvalid, nullptr, n_dev, subs_dev ? subs_dev : dsubs, dcounts, thr2));
   PoseOut po;
   po.pose6 = pose6_dev; po.n_inl = n_inl_dev; po.ok = ok_dev; po.Rt = Rt_dev; po.P = P_dev; po.cam = cam_dev; po.K = K_dev;
   po.dbg = nullptr;

@@ -55,14 +55,17 @@ __global__ void __launch_bounds__(96) pnp_epnp_kernel(const float* __restrict__ 
                                                       int H, PnpCam cam, const __grid_constant__ PnpSubsets subs,
                                                       double* __restrict__ poses,
                                                       unsigned char* __restrict__ valid, long long* __restrict__ dbg,
-                                                      const int* __restrict__ n_dev, const int* __restrict__ subs_dev) {
+                                                      const int* __restrict__ n_dev, const int* __restrict__ subs_dev,
+                                                      int* __restrict__ counts, float thr2) {
   __shared__ __align__(16) EpnpShared sh;
   const int h = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (h >= H) return;
+  __shared__ double s_pose[12];
+  __shared__ int s_ok, s_cnt;
   if (n_dev) {
     n = *n_dev;
     if (n < 6) {                             // no minimal problem to solve: every hypothesis invalid -> ok = 0 downstream
-      if (tid == 0) valid[h] = 0;
+      if (tid == 0) { valid[h] = 0; if (counts) counts[h] = 0; }
       return;
     }
   }
@@ -189,6 +192,11 @@ __global__ void __launch_bounds__(96) pnp_epnp_kernel(const float* __restrict__ 
     for (int k = 0; k < 9; ++k) { P[k] = R[k]; ok &= isfinite(R[k]); }
     for (int k = 0; k < 3; ++k) { P[9 + k] = t[k]; ok &= isfinite(t[k]); }
     valid[h] = ok ? 1 : 0;
+    if (counts) {
+      for (int k = 0; k < 12; ++k) s_pose[k] = P[k];
+      s_ok = ok ? 1 : 0;
+      s_cnt = 0;
+    }
     if (dbg && h == 0) {                 // diagnostics: the raw solver output of hypothesis 0
       double* d = reinterpret_cast<double*>(dbg + 32);
       for (int k = 0; k < 9; ++k) d[k] = R[k];
@@ -196,15 +204,33 @@ __global__ void __launch_bounds__(96) pnp_epnp_kernel(const float* __restrict__ 
     }
   }
   tick(6);
+  if (counts) {
+    // K4 inside the solver: this hypothesis's consensus over all points, by the CTA that produced it
+    __syncwarp();
+    asm volatile("barrier.sync 0;" ::: "memory");
+    int c = 0;
+    if (s_ok) {
+      for (int i = tid; i < n; i += 96) {
+        const float2 o = __ldg(reinterpret_cast<const float2*>(px) + i);
+        c += is_inlier(s_pose, cam, __ldg(X + 3 * (size_t)i), __ldg(X + 3 * (size_t)i + 1), __ldg(X + 3 * (size_t)i + 2), o.x, o.y, thr2) ? 1 : 0;
+      }
+    }
+    __syncwarp();
+    c = __reduce_add_sync(0xffffffffu, c);
+    if (lane == 0 && c) atomicAdd(&s_cnt, c);
+    __syncwarp();
+    asm volatile("barrier.sync 0;" ::: "memory");
+    if (tid == 0) counts[h] = s_cnt;
+  }
 }
 
 }  // namespace
 
 int sfm_pnp_epnp_launch(sfm_ctx* ctx, const float* X, const float* px, int n, int H, const PnpCam& cam, const PnpSubsets& subs,
                         double* poses, unsigned char* valid, long long* dbg, const int* n_dev,
-                        const int* subs_dev) {
+                        const int* subs_dev, int* counts, float thr2) {
   SFM_LAUNCH(ctx, SFM_K_PNP_EPNP, (pnp_epnp_kernel<<<H, 96, 0, ctx->stream>>>(X, px, n, H, cam, subs, poses, valid, dbg,
-                                                                              n_dev, subs_dev)));
+                                                                              n_dev, subs_dev, counts, thr2)));
   return SFM_OK;
 }
 
@@ -239,7 +265,7 @@ extern "C" int sfm_epnp_batch(sfm_ctx* ctx, const float* X, const float* px, int
     for (int k = 0; k < 5; ++k) one.idx[k] = subs.idx[5 * h + k];
     SFM_TRY(ws_alloc_t(ctx, 48, &dbg));
     SFM_CUDA(cudaMemsetAsync(dbg, 0, 48 * sizeof(long long), ctx->stream));
-    SFM_TRY(sfm_pnp_epnp_launch(ctx, dX, dpx, n, 1, cam, one, dposes, dvalid, dbg, nullptr, nullptr));
+    SFM_TRY(sfm_pnp_epnp_launch(ctx, dX, dpx, n, 1, cam, one, dposes, dvalid, dbg, nullptr, nullptr, nullptr, 0.f));
     SFM_CUDA(cudaMemcpyAsync(hout, dbg + 32, sizeof(double) * 12, cudaMemcpyDeviceToHost, ctx->stream));
     SFM_CUDA(cudaStreamSynchronize(ctx->stream));
     memcpy(R9t3 + 12 * (size_t)h, hout, sizeof(double) * 12);
