@@ -1087,8 +1087,8 @@ static int pnp_ransac_impl(sfm_ctx* ctx, const float* X, const float* px, int n,
       fprintf(stderr, "[candidates N=4lin / N=2 / N=3] svd+sort %lld %lld %lld | backsubst+gauss-newton %lld %lld %lld | pose %lld %lld %lld\n",
               hs[20] - hs[4], hs[21] - hs[4], hs[22] - hs[4], hs[23] - hs[20], hs[24] - hs[21], hs[25] - hs[22], hs[26] - hs[23],
               hs[27] - hs[24], hs[28] - hs[25]);
-      fprintf(stderr, "[epnp cycles] subset+control points+alphas %lld | MtM %lld | 12x12 jacobi+sort %lld (%lld sweeps) | L,rho %lld | candidates %lld | pick+store %lld\n",
-              hs[1] - hs[0], hs[2] - hs[1], hs[3] - hs[2], hs[10], hs[4] - hs[3], hs[5] - hs[4], hs[6] - hs[5]);
+      fprintf(stderr, "[epnp cycles] subset+control points+alphas %lld | MtM %lld | 12x12 jacobi+sort %lld (%lld sweeps) | L,rho %lld | candidates %lld | pick %lld, store %lld, rest %lld\n",
+              hs[1] - hs[0], hs[2] - hs[1], hs[3] - hs[2], hs[10], hs[4] - hs[3], hs[5] - hs[4], hs[7] - hs[5], hs[8] - hs[7], hs[6] - hs[8]);
     }
   }
   SFM_CUDA(cudaMemsetAsync(dcounts, 0, sizeof(int32_t) * H, ctx->stream));

@@ -36,6 +36,7 @@ struct CandShared {        // one beta initialisation (one warp); At first: its 
   double ut[30], vts[25];  // sorted, normalised
   double pcs[15];
   double R[9], t[3], err;
+  double gnA[24], gnb[6], gnbeta[4];   // Gauss-Newton: the 6 x 4 system, its right-hand side, the betas
   int ord[5], pad[3];
   int sched[40];
 };
@@ -51,7 +52,101 @@ struct EpnpShared {
   int sched[96];
 };
 
-__global__ void __launch_bounds__(96) pnp_epnp_kernel(const float* __restrict__ X, const float* __restrict__ px, int n,
+// ---- the solver's Gauss-Newton refinement of the betas (five iterations of a 6 x 4 Householder least squares,
+// hm::epnp_gauss_newton) by one warp.  Every number is the result of the same operations in the same order as in the
+// serial routine; what runs side by side is what does not depend on each other: the 30 entries of the system, and,
+// at Householder step k, the columns to its right AND the right-hand side (the serial code reflects b in a second
+// pass; reflections 0..k-1 have been applied to it by then either way).  The scalar part of a step (pivot scan with
+// its off-by-one, scaling, sigma) is computed redundantly by every lane.
+__device__ __forceinline__ double gn_A_entry(const double* l, const double* b, int c) {
+  switch (c) {
+    case 0: return 2 * l[0] * b[0] + l[1] * b[1] + l[3] * b[2] + l[6] * b[3];
+    case 1: return l[1] * b[0] + 2 * l[2] * b[1] + l[4] * b[2] + l[7] * b[3];
+    case 2: return l[3] * b[0] + l[4] * b[1] + 2 * l[5] * b[2] + l[8] * b[3];
+    default: return l[6] * b[0] + l[7] * b[1] + l[8] * b[2] + 2 * l[9] * b[3];
+  }
+}
+__device__ __forceinline__ double gn_r_entry(const double* l, const double* b, double rho) {
+  return rho - (l[0] * b[0] * b[0] + l[1] * b[0] * b[1] + l[2] * b[1] * b[1] + l[3] * b[0] * b[2] +
+                l[4] * b[1] * b[2] + l[5] * b[2] * b[2] + l[6] * b[0] * b[3] + l[7] * b[1] * b[3] +
+                l[8] * b[2] * b[3] + l[9] * b[3] * b[3]);
+}
+
+__device__ __forceinline__ void gauss_newton_warp(const double* __restrict__ L, const double* __restrict__ rho, double* gA,
+                                               double* gb, double* gbeta, int lane) {
+  double x[4] = {0, 0, 0, 0};                       // (every lane carries the same x)
+#pragma unroll 1
+  for (int it = 0; it < 5; ++it) {
+    {
+      const double b[4] = {gbeta[0], gbeta[1], gbeta[2], gbeta[3]};
+      if (lane < 24) gA[lane] = gn_A_entry(L + 10 * (lane >> 2), b, lane & 3);
+      else if (lane < 30) gb[lane - 24] = gn_r_entry(L + 10 * (lane - 24), b, rho[lane - 24]);
+    }
+    __syncwarp();
+    double A1[4], A2[4];
+    bool dead = false;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (!dead) {
+        double colk[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) colk[i] = (i >= k) ? gA[i * 4 + k] : 0.0;
+        double eta = fabs(colk[k]);
+#pragma unroll
+        for (int i = k + 1; i < 6; ++i) {
+          const double elt = fabs(colk[i - 1]);
+          if (eta < elt) eta = elt;
+        }
+        if (eta == 0) dead = true;
+        if (!dead) {
+          const double inv_eta = 1. / eta;
+          double sum2 = 0.0;
+#pragma unroll
+          for (int i = k; i < 6; ++i) {
+            colk[i] *= inv_eta;
+            sum2 += colk[i] * colk[i];
+          }
+          double sigma = sqrt(sum2);
+          if (colk[k] < 0) sigma = -sigma;
+          colk[k] += sigma;
+          A1[k] = sigma * colk[k];
+          A2[k] = -eta * sigma;
+          // lane j - (k+1) reflects column j > k of A; the next lane reflects b
+          const int j = k + 1 + lane;
+          if (j <= 4) {
+            double* col = (j < 4) ? gA + j : gb;
+            const int stride = (j < 4) ? 4 : 1;
+            double sum = 0;
+#pragma unroll
+            for (int i = k; i < 6; ++i) sum += colk[i] * col[i * stride];
+            const double tau = sum / A1[k];
+#pragma unroll
+            for (int i = k; i < 6; ++i) col[i * stride] -= tau * colk[i];
+          }
+          __syncwarp();
+        }
+      }
+    }
+    if (!dead) {
+      x[3] = gb[3] / A2[3];
+#pragma unroll
+      for (int i = 2; i >= 0; --i) {
+        double sum = 0;
+#pragma unroll
+        for (int j = i + 1; j < 4; ++j) sum += gA[i * 4 + j] * x[j];
+        x[i] = (gb[i] - sum) / A2[i];
+      }
+    }
+    __syncwarp();
+    if (lane < 4) {
+      const double xv = lane == 0 ? x[0] : (lane == 1 ? x[1] : (lane == 2 ? x[2] : x[3]));
+      gbeta[lane] += xv;
+    }
+    __syncwarp();
+  }
+}
+
+__global__ void __launch_bounds__(96, 1) pnp_epnp_kernel(const float* __restrict__ X, const float* __restrict__ px, int n,
                                                       int H, PnpCam cam, const __grid_constant__ PnpSubsets subs,
                                                       double* __restrict__ poses,
                                                       unsigned char* __restrict__ valid, long long* __restrict__ dbg,
@@ -167,8 +262,13 @@ __global__ void __launch_bounds__(96) pnp_epnp_kernel(const float* __restrict__ 
       else if (ap == 1) hm::cv_svd_backsubst<6, 3>(cs.W, cs.ut, cs.vts, sh.rho, b);
       else hm::cv_svd_backsubst<6, 5>(cs.W, cs.ut, cs.vts, sh.rho, b);
       hm::epnp_betas_from_ls(ap, b, betas);
-      hm::epnp_gauss_newton(sh.L, sh.rho, betas);
-      if (dbg && h == 0) dbg[23 + warp] = clock64();
+      for (int k = 0; k < 4; ++k) cs.gnbeta[k] = betas[k];
+    }
+    __syncwarp();
+    gauss_newton_warp(sh.L, sh.rho, cs.gnA, cs.gnb, cs.gnbeta, lane);
+    if (dbg && h == 0 && lane == 0) dbg[23 + warp] = clock64();
+    if (lane == 0) {
+      const double betas[4] = {cs.gnbeta[0], cs.gnbeta[1], cs.gnbeta[2], cs.gnbeta[3]};
       const double* v[4] = {sh.v4, sh.v4 + 12, sh.v4 + 24, sh.v4 + 36};
       cs.err = hm::epnp_pose_from_betas(v, betas, sh.alphas, sh.pw, sh.us, 5, ec, cs.pcs, cs.R, cs.t);
       if (dbg && h == 0) dbg[26 + warp] = clock64();
@@ -180,6 +280,7 @@ __global__ void __launch_bounds__(96) pnp_epnp_kernel(const float* __restrict__ 
   if (tid == 0) {
     const double errs[3] = {sh.cand[0].err, sh.cand[1].err, sh.cand[2].err};
     const int N = hm::epnp_pick(errs);
+    if (dbg && h == 0) dbg[7] = clock64();
     const double* R = sh.cand[N].R;
     const double* t = sh.cand[N].t;
     // OpenCV hands the model on as (rvec, tvec) = (Rodrigues(R), t) and scores with R' = Rodrigues(rvec): the round trip
@@ -192,6 +293,7 @@ __global__ void __launch_bounds__(96) pnp_epnp_kernel(const float* __restrict__ 
     for (int k = 0; k < 9; ++k) { P[k] = R[k]; ok &= isfinite(R[k]); }
     for (int k = 0; k < 3; ++k) { P[9 + k] = t[k]; ok &= isfinite(t[k]); }
     valid[h] = ok ? 1 : 0;
+    if (dbg && h == 0) dbg[8] = clock64();
     if (counts) {
       for (int k = 0; k < 12; ++k) s_pose[k] = P[k];
       s_ok = ok ? 1 : 0;
