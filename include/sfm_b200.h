@@ -58,6 +58,10 @@ void* sfm_ctx_stream(sfm_ctx* ctx);
  * aborts the process. */
 int sfm_ctx_detach_stream(sfm_ctx* ctx);
 int sfm_ctx_sm_count(sfm_ctx* ctx);
+/* n host -> device copies queued on `stream` (NULL: the context's stream) in one call — the upload of a chunk of views
+ * (the reference holds keypoints and descriptors of every image as separate arrays, sfm.py:246-252).  Pinned sources
+ * copy asynchronously.  dst[i] device, src[i] host, bytes[i] >= 0. */
+int sfm_upload_batch(sfm_ctx* ctx, void* stream, int n, void* const* dst, const void* const* src, const int64_t* bytes);
 
 /* Kernel identifiers for the profiling interface. */
 enum {

@@ -246,3 +246,16 @@ void sfm_ctx_merge_profile(sfm_ctx* dst, sfm_ctx* src) {
   dst->total_launches += src->total_launches;
   src->total_launches = 0;
 }
+
+// n host -> device copies queued on `stream` in one call: the upload of a chunk of views (keypoints and descriptors of
+// every view are separate host arrays) costs the host one native loop instead of one interpreter round trip per array.
+extern "C" int sfm_upload_batch(sfm_ctx* c, void* stream, int n, void* const* dst, const void* const* src, const int64_t* bytes) {
+  SFM_REQUIRE(c && (n == 0 || (dst && src && bytes)), "sfm_upload_batch: null argument");
+  SFM_CUDA(cudaSetDevice(c->device));
+  cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+  for (int i = 0; i < n; ++i) {
+    SFM_REQUIRE(bytes[i] >= 0 && (bytes[i] == 0 || (dst[i] && src[i])), "sfm_upload_batch: bad entry %d", i);
+    if (bytes[i]) SFM_CUDA(cudaMemcpyAsync(dst[i], src[i], (size_t)bytes[i], cudaMemcpyHostToDevice, s));
+  }
+  return SFM_OK;
+}

@@ -438,14 +438,18 @@ def register_device(ctx: _e.Context, K, kps, dess, Rt0, Rt1, ratio: float = 0.70
     return outs
 
 
-def register_host(ctx: _e.Context, K, kps, dess, Rt0, Rt1, chunk: int = 25, ratio: float = 0.70, ahead: int = 2):
+def register_host(ctx: _e.Context, K, kps, dess, Rt0, Rt1, chunk: int = 25, ratio: float = 0.70, ahead: int = 2,
+                  edges=None):
     """Host arrays in, registered views out — the call a user makes with a sequence of views whose keypoints
     (n,2) and descriptors (n,128) sit in host memory (numpy arrays or torch CPU tensors; pinned memory lets the
     upload overlap).  Views are uploaded on a copy stream in chunks (a short first chunk gets the loop going);
     descriptor preparation and the batched match of a chunk's pairs run on a matching context, the registration of
     its views on the engine stream, while later chunks are still crossing PCIe.  The copies of chunk k + `ahead` are
     submitted only after chunk k's registration has been queued, so the first chunk's work does not wait for the host
-    to enqueue every copy of the sequence (measured on 200 x 5000: 48.0 -> 46.4 ms per step, tools/prof_e2e.py)."""
+    to enqueue every copy of the sequence; a chunk's arrays land in one device slab per kind and are queued by one
+    native call (sfm_upload_batch).  What separates this from the resident driver (35.8 against 32.8 ms on 200 x 5000):
+    ~1.1 ms because the loop's latency-bound kernels run slower while 520 MB cross PCIe (tools/prof_e2e_contention.py),
+    the first chunk's upload, the read-back of the clouds, and the extra chunk boundaries."""
     import torch
     V = len(kps)
     dev = ctx.torch_device
@@ -455,7 +459,16 @@ def register_host(ctx: _e.Context, K, kps, dess, Rt0, Rt1, chunk: int = 25, rati
     cs = getattr(ctx, "_copy_stream", None)          # one upload stream per context: torch's caching allocator keeps a
     if cs is None:                                    # pool per stream, a fresh stream per call would cudaMalloc every buffer
         cs = ctx._copy_stream = torch.cuda.Stream(device=dev)
-    bounds = _chunk_bounds(V, [min(8, chunk), chunk] + list(range(2 * chunk, V, chunk)))
+    import os
+    env = os.environ.get("SFM_HOST_EDGES")              # tuning aid: comma-separated chunk boundaries
+    if env:
+        edges = [int(e) for e in env.split(",")]
+    # chunk k + 1 must cross PCIe (and be matched) while chunk k registers: ~60 us per view of upload against ~166 us per
+    # view of registration lets the chunks grow threefold; a boundary costs a host round trip.  Measured on 200 x 5000
+    # (ms per step, tools/prof_e2e.py): (8,25,50,...,175) 36.6, (12,60) 36.5, (8,40,100) 36.3, (8,32,96) 35.8
+    if edges is None:
+        edges = [8, 32, 96] + list(range(224, V, 128)) if chunk == 25 else [min(8, chunk), chunk] + list(range(2 * chunk, V, chunk))
+    bounds = _chunk_bounds(V, list(edges))
     kp_d, des_d, events = [None] * V, [None] * V, [None] * len(bounds)
 
     def upload(k):
@@ -463,9 +476,25 @@ def register_host(ctx: _e.Context, K, kps, dess, Rt0, Rt1, chunk: int = 25, rati
             return
         lo, hi = bounds[k]
         with torch.cuda.stream(cs):
-            for i in range(lo, hi):
-                kp_d[i] = kps[i].to(dev, non_blocking=True)
-                des_d[i] = dess[i].to(dev, non_blocking=True)
+            for src, dst in ((kps, kp_d), (dess, des_d)):
+                part = src[lo:hi]
+                t0 = part[0]
+                if all((not t.is_cuda) and t.is_contiguous() and t.dtype == t0.dtype and t.shape[1:] == t0.shape[1:] for t in part):
+                    # one device slab per chunk, every view a row range of it; the copies are queued by ONE native call
+                    # (sfm_upload_batch) instead of one interpreter round trip per array
+                    rows = [int(t.shape[0]) for t in part]
+                    slab = torch.empty((sum(rows),) + tuple(t0.shape[1:]), dtype=t0.dtype, device=dev)
+                    row_bytes = slab.element_size() * int(np.prod(t0.shape[1:], dtype=np.int64))
+                    offs = np.concatenate([[0], np.cumsum(rows)])
+                    nbytes = np.asarray(rows, np.int64) * row_bytes
+                    dptr = (slab.data_ptr() + offs[:-1] * row_bytes).astype(np.uint64)
+                    sptr = np.fromiter((t.data_ptr() for t in part), np.uint64, len(part))
+                    _e.check(_e.lib.sfm_upload_batch(ctx._h, int(cs.cuda_stream), len(part), _e._dptr(dptr), _e._dptr(sptr), _e._dptr(nbytes)))
+                    for j, i in enumerate(range(lo, hi)):
+                        dst[i] = slab[int(offs[j]):int(offs[j + 1])]
+                else:
+                    for i in range(lo, hi):
+                        dst[i] = src[i].to(dev, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(cs)
         events[k] = ev
