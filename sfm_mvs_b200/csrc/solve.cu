@@ -89,6 +89,17 @@ __global__ void __launch_bounds__(256) spd_pack_kernel(const float* __restrict__
   }
 }
 
+// 1 / sqrt(d) for a pivot known to be a positive normal number: the hardware seed and two Newton steps, without the
+// range handling of rsqrt() — this sits on the factorisation's critical chain once per column.
+__device__ __forceinline__ double rsqrt_normal(double d) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+  const double h = 0.5 * d;
+  y = y * fma(-h * y, y, 1.5);
+  y = y * fma(-h * y, y, 1.5);
+  return y;
+}
+
 // Cholesky of a 64 x 64 block held column-major in shared memory (C), by 256 threads: thread t holds row t%64,
 // columns 16*(t/64) .. +15 in registers; four 16-column panels (inside a panel only its 64 owner threads work, two
 // 64-thread named barriers per column; after a panel one block barrier and the rank-16 update of the columns to its
@@ -118,7 +129,7 @@ __device__ __forceinline__ void factor_block(const double* __restrict__ C, doubl
           if (row == j && info && *info == 0) *info = pivot_base + j + 1;   // not positive definite
           d = 1.0;
         }
-        const double rinv = rsqrt(d);
+        const double rinv = rsqrt_normal(d);
         const double li = (row == j) ? d * rinv : ((row > j) ? a[jj] * rinv : 0.0);   // L[row][j]
         a[jj] = li;
         if (row == j) dinv[j] = rinv;
