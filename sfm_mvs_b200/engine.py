@@ -9,6 +9,8 @@ from __future__ import annotations
 
 import ctypes as C
 
+import weakref
+
 import numpy as np
 
 from . import _lib
@@ -115,11 +117,13 @@ class Descriptors:
         h = C.c_void_p()
         check(lib.sfm_desc_create(ctx._h, arg.ptr, dtype, self.n, self.dim, C.byref(h)))
         self._h = h
+        ctx._children.add(self)
 
     @classmethod
     def _from_handle(cls, ctx: "Context", handle, n: int, dim: int):
         self = cls.__new__(cls)
         self.ctx, self._h, self.n, self.dim = ctx, handle, int(n), int(dim)
+        ctx._children.add(self)
         return self
 
     @classmethod
@@ -165,10 +169,22 @@ class Context:
         self._h = h
         self.device = int(device)
         self.sm_count = lib.sfm_ctx_sm_count(h)
+        # descriptor sets, BA problems and chains return their buffers to pools of the context when they are destroyed:
+        # an explicit close() of the context closes what is still alive on it first
+        self._children = weakref.WeakSet()
 
     # ------------------------------------------------------------------ plumbing
     def close(self):
         if getattr(self, "_h", None):
+            for child in list(getattr(self, "_children", ())):
+                try:
+                    child.close()
+                except Exception:
+                    pass
+            for name in ("_match_ctx",):
+                sub = getattr(self, name, None)
+                if sub is not None:
+                    sub.close()
             lib.sfm_ctx_destroy(self._h)
             self._h = None
 
@@ -483,6 +499,7 @@ class BAProblem:
         check(lib.sfm_ba_create(ctx._h, self.n_cam, self.n_pt, self.n_obs, _dptr(cam_idx), _dptr(pt_idx), _dptr(obs),
                                 _dptr(K), C.byref(h)))
         self._h = h
+        ctx._children.add(self)
         if totals is not None:
             check(lib.sfm_ba_set_totals(h, int(totals[0]), int(totals[1])))
 

@@ -293,6 +293,7 @@ class NativeChain:
         check(lib.sfm_chain_create(ctx._h, _e._dptr(K), _e._dptr(Rt0), _e._dptr(Rt1), int(max(max_matches, 6)), C.byref(self._h)))
         self._alive = []          # match arrays of the last pair must outlive the next extend()
         self._fed = 0
+        ctx._children.add(self)
 
     def launch(self, matches):
         """Queue the registration of the views these consecutive pairs add (sfm_chain_extend_async) and return;

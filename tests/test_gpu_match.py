@@ -217,3 +217,18 @@ def test_full_size_pairs_by_properties(engine, n):
     assert np.array_equal(idx[rows], top)
     ref_d = np.sqrt(torch.gather(d2, 1, torch.from_numpy(top).to("cuda")).cpu().numpy().astype(np.float32))
     assert np.array_equal(dist[rows], ref_d)
+
+
+def test_closing_a_context_closes_what_lives_on_it():
+    """Descriptor sets, BA problems and chains hand their buffers back to pools of their context when destroyed: an
+    explicit Context.close() therefore closes them first, and their later destruction is a no-op (not a use after free)."""
+    ctx = sfm.Context(0)
+    rng = np.random.default_rng(0)
+    d = sfm.Descriptors(ctx, rng.integers(0, 200, (300, 128)).astype(np.uint8))
+    pb = synth.ba_problem(4, 60, 3, seed=1)
+    prob = sfm.BAProblem(ctx, 4, 60, pb["cam_idx"], pb["pt_idx"], pb["obs"], pb["K"])
+    ctx.close()
+    assert not d._h and not prob._h and not ctx._h
+    d.close()
+    prob.close()
+    del d, prob
