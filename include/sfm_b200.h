@@ -339,6 +339,13 @@ int sfm_ba_reference_fd(sfm_ctx* ctx, const double* x, int n_params, int n_point
  * solver on device buffers; this entry exists so that it can be checked against a dense factorisation directly. */
 int sfm_reduced_solve(sfm_ctx* ctx, const float* S_blocks, const float* g, int n_cams, double* x, int32_t* info);
 
+/* The same system by the solver the LM step uses by default (csrc/pcg.cu): block-Jacobi preconditioned conjugate
+ * gradients to a relative residual of 1e-8, one persistent kernel.  *solved = 1: x is the solution; 0: the system was
+ * not positive definite or did not converge (the LM step then falls back to the factorisation above).  *iterations
+ * (may be NULL): iterations used.  Host arrays. */
+int sfm_reduced_solve_pcg(sfm_ctx* ctx, const float* S_blocks, const float* g, int n_cams, double* x, int32_t* solved,
+                          int32_t* iterations);
+
 typedef struct sfm_ba_stats {
   double cost_before;   /* 0.5*sum r^2 at the linearisation point */
   double cost_after;    /* at the candidate parameters */

@@ -106,6 +106,7 @@ PROTOTYPES = {
     "sfm_ba_reference_fd": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     "sfm_reduced_solve": (_i, [_vp, _vp, _vp, _i, _vp, _vp]),
     "sfm_upload_batch": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),
+    "sfm_reduced_solve_pcg": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "sfm_ba_build_system": (_i, [_vp, _d]),
     "sfm_ba_read": (_i, [_vp, _i, _vp, _i64]),
     "sfm_nccl_unique_id": (_i, [_vp]),

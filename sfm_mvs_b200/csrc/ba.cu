@@ -473,8 +473,17 @@ __global__ void ba_update_cams_kernel(const double* __restrict__ cams, const dou
   if ((threadIdx.x & 31) == 0 && d != 0.0) atomicAdd(step2, d);
 }
 
+// Conjugate gradients first (pcg.cu: ~50 iterations of an L2-resident matrix-vector product instead of a chain of 6C
+// dependent columns); the tile Cholesky runs behind it only if it reports failure (its kernels return at once otherwise).
+// SFM_BA_SOLVER=cholesky selects the factorisation alone.
 int solve_reduced_system(sfm_ba* ba) {
-  return sfm_spd_solve(ba->ctx, ba->S, ba->g, 6 * ba->n_cam, ba->A64, ba->dc, ba->info);
+  const int n = 6 * ba->n_cam;
+  static const bool chol_only = [] { const char* e = getenv("SFM_BA_SOLVER"); return e && e[0] == 'c'; }();
+  if (ba->pcg && !chol_only) {
+    SFM_TRY(sfm_spd_pcg(ba->ctx, ba->S, ba->g, n, ba->pcg, ba->dc, ba->info + 1, ba->info, ba->info + 2));
+    return sfm_spd_solve(ba->ctx, ba->S, ba->g, n, ba->A64, ba->dc, ba->info, ba->info + 1);
+  }
+  return sfm_spd_solve(ba->ctx, ba->S, ba->g, n, ba->A64, ba->dc, ba->info);
 }
 
 Intr make_intr(const sfm_ba* ba) {
@@ -658,7 +667,8 @@ extern "C" int sfm_ba_create(sfm_ctx* ctx, int n_cam, int n_pt, int n_obs, const
   A((void**)&ba->A64, sizeof(double) * sfm_spd_scratch_doubles(n));
   A((void**)&ba->dc, sizeof(double) * (size_t)n);
   A((void**)&ba->scal, sizeof(double) * 8);
-  A((void**)&ba->info, sizeof(int));
+  A((void**)&ba->info, 4 * sizeof(int));
+  if (sfm_spd_pcg_fits(ctx, n)) A((void**)&ba->pcg, sizeof(double) * sfm_pcg_scratch_doubles(n));
   if (e != cudaSuccess) {
     sfm_set_error("sfm_ba_create: cudaMalloc failed: %s", cudaGetErrorString(e));
     sfm_ba_destroy(ba);
@@ -685,7 +695,7 @@ extern "C" void sfm_ba_destroy(sfm_ba* ba) {
   if (ba->ctx) { cudaSetDevice(ba->ctx->device); cudaStreamSynchronize(ba->ctx->stream); }
   sfm_ba_comm_destroy(ba);
   void* ptrs[] = {ba->uv, ba->cam_idx, ba->pt_idx, ba->pt_start, ba->cams, ba->cams_new, ba->pts, ba->pts_new,
-                  ba->cam_pre, ba->S, ba->A64, ba->dc, ba->scal, ba->info};
+                  ba->cam_pre, ba->S, ba->A64, ba->dc, ba->scal, ba->info, ba->pcg};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   delete ba;

@@ -25,7 +25,8 @@ struct sfm_ba {
   double* A64 = nullptr;                       // float64 copy factored in place
   double* dc = nullptr;                        // camera step (6C)
   double* scal = nullptr;                      // [0] cost at linearisation, [1] cost at candidate, [2] |dp|^2, [3] |dc|^2
-  int* info = nullptr;                         // Cholesky status
+  int* info = nullptr;                         // solve status: [0] Cholesky info (0 = ok), [1] 1 = the CG solver produced dc, [2] its iterations
+  double* pcg = nullptr;                       // scratch of the conjugate-gradient solver (pcg.cu), null when it does not apply
   // C1 exchange
   void* comm = nullptr;                        // ncclComm_t
   int rank = 0, world = 1;

@@ -46,6 +46,7 @@ struct SpdPlan {
   int* info;
   long long* stamps;            // diagnostics (SFM_SPD_TIMELINE): cycle counts of the phases of column `probe`'s critical tasks
   int probe;
+  const int* skip;              // device word: 1 = the system is already solved (pcg.cu), every kernel returns at once
 };
 
 __host__ __device__ inline int tile_id(int i, int j, int ntc) { return (i < ntc ? i * (i + 1) / 2 : ntc * (ntc + 1) / 2) + j; }
@@ -64,6 +65,7 @@ __device__ __forceinline__ void wait_flag(const int* p) {
 
 // S (float32, lower triangle) and g -> float64 tiles.  grid = (tile id, 16 column groups), 256 threads.
 __global__ void __launch_bounds__(256) spd_pack_kernel(const float* __restrict__ S, const float* __restrict__ g, SpdPlan p) {
+  if (p.skip && *p.skip == 1) return;
   const int ntc = p.ntc, n = p.n;
   int t = blockIdx.x, i, j;
   const int ntri = ntc * (ntc + 1) / 2;
@@ -175,6 +177,7 @@ __global__ void __launch_bounds__(256, 1) spd_factor_kernel(SpdPlan p) {
   double (*colbuf)[T + 2] = reinterpret_cast<double(*)[T + 2]>(smem + 2 * TT);
   double* di = smem + 2 * TT + 16 * (T + 2);
   __shared__ int s_task;
+  if (p.skip && *p.skip == 1) return;
   const int ntc = p.ntc;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;        // rows 4 ty .. +3, columns tx + 16 b of the tile
   for (;;) {
@@ -341,6 +344,7 @@ __global__ void __launch_bounds__(256, 1) spd_factor_kernel(SpdPlan p) {
 
 // grid = 1 diagonal CTA (block 0) + ntc column CTAs, all co-resident (ntc + 1 <= SM count is required).
 __global__ void __launch_bounds__(256, 1) spd_backsolve_kernel(SpdPlan p) {
+  if (p.skip && *p.skip == 1) return;
   const int ntc = p.ntc, nsb = (ntc + SBT - 1) / SBT;
   int* ycol_ready = p.sync + 1;
   int* x_ready = p.sync + 1 + ntc;
@@ -437,7 +441,8 @@ __global__ void __launch_bounds__(256, 1) spd_backsolve_kernel(SpdPlan p) {
   }
 }
 
-__global__ void spd_copy_x_kernel(const double* __restrict__ xbuf, int n, double* __restrict__ x) {
+__global__ void spd_copy_x_kernel(const double* __restrict__ xbuf, int n, double* __restrict__ x, const int* __restrict__ skip) {
+  if (skip && *skip == 1) return;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) x[i] = xbuf[i];
 }
@@ -458,6 +463,7 @@ static SpdPlan make_plan(int n, double* A, int* info) {
   p.info = info;
   p.stamps = nullptr;
   p.probe = 0;
+  p.skip = nullptr;
   return p;
 }
 
@@ -470,13 +476,14 @@ size_t sfm_spd_scratch_doubles(int n) {
   return (ntiles + ntc) * TT + 3 * ntc * T + (ints + 1) / 2;
 }
 
-int sfm_spd_solve(sfm_ctx* ctx, const float* S, const float* g, int n, double* A, double* x, int* info) {
+int sfm_spd_solve(sfm_ctx* ctx, const float* S, const float* g, int n, double* A, double* x, int* info, const int* skip_if) {
   SpdPlan p = make_plan(n, A, info);
+  p.skip = skip_if;
   SFM_REQUIRE(p.ntc + 1 <= ctx->sm_count, "sfm_spd_solve: %d unknowns need %d co-resident CTAs, the device has %d SMs", n,
               p.ntc + 1, ctx->sm_count);
   const size_t nints = (size_t)p.ntasks + p.ntc + 1 + p.ntc + (p.ntc + SBT - 1) / SBT;
   SFM_CUDA(cudaMemsetAsync(p.flags, 0, nints * sizeof(int), ctx->stream));
-  SFM_CUDA(cudaMemsetAsync(info, 0, sizeof(int), ctx->stream));
+  if (!skip_if) SFM_CUDA(cudaMemsetAsync(info, 0, sizeof(int), ctx->stream));      // (behind the CG solver: it has written info)
   SFM_LAUNCH(ctx, SFM_K_BA_SOLVE, (spd_pack_kernel<<<p.ntasks, 256, 0, ctx->stream>>>(S, g, p)));
   static bool attr_set = false;
   if (!attr_set) {
@@ -501,7 +508,7 @@ int sfm_spd_solve(sfm_ctx* ctx, const float* S, const float* g, int n, double* A
             h[3], h[0], h[1], h[2], h[4], h[6], h[8], h[9], h[10], h[12], h[13], h[14], h[3]);
   }
   SFM_LAUNCH(ctx, SFM_K_BA_SOLVE, (spd_backsolve_kernel<<<p.ntc + 1, 256, 0, ctx->stream>>>(p)));
-  SFM_LAUNCH(ctx, SFM_K_BA_SOLVE, (spd_copy_x_kernel<<<div_up(n, 256), 256, 0, ctx->stream>>>(p.xbuf, n, x)));
+  SFM_LAUNCH(ctx, SFM_K_BA_SOLVE, (spd_copy_x_kernel<<<div_up(n, 256), 256, 0, ctx->stream>>>(p.xbuf, n, x, p.skip)));
   return SFM_OK;
 }
 
@@ -523,5 +530,33 @@ extern "C" int sfm_reduced_solve(sfm_ctx* ctx, const float* S_blocks, const floa
   SFM_CUDA(cudaMemcpyAsync(x, dx, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
   SFM_CUDA(cudaMemcpyAsync(info, dinfo, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   SFM_CUDA(cudaStreamSynchronize(ctx->stream));
+  return SFM_OK;
+}
+
+extern "C" int sfm_reduced_solve_pcg(sfm_ctx* ctx, const float* S_blocks, const float* g, int n_cams, double* x, int32_t* solved,
+                                     int32_t* iterations) {
+  SFM_REQUIRE(ctx && S_blocks && g && x && solved, "sfm_reduced_solve_pcg: null argument");
+  SFM_REQUIRE(n_cams >= 1, "sfm_reduced_solve_pcg: no cameras");
+  const int n = 6 * n_cams;
+  SFM_REQUIRE(sfm_spd_pcg_fits(ctx, n), "sfm_reduced_solve_pcg: %d cameras exceed the shared-memory-resident vectors", n_cams);
+  SFM_TRY(sfm_ws_begin(ctx));
+  const size_t nblk = (size_t)n_cams * (n_cams + 1) / 2;
+  const float *dS, *dg;
+  SFM_TRY(dev_in(ctx, S_blocks, nblk * 36, &dS));
+  SFM_TRY(dev_in(ctx, g, (size_t)n, &dg));
+  double *scratch, *dx;
+  int* dwords;
+  SFM_TRY(ws_alloc_t(ctx, sfm_pcg_scratch_doubles(n), &scratch));
+  SFM_TRY(ws_alloc_t(ctx, (size_t)n, &dx));
+  SFM_TRY(ws_alloc_t(ctx, 4, &dwords));
+  SFM_CUDA(cudaMemsetAsync(dx, 0, sizeof(double) * n, ctx->stream));
+  SFM_CUDA(cudaMemsetAsync(dwords, 0, 4 * sizeof(int), ctx->stream));
+  SFM_TRY(sfm_spd_pcg(ctx, dS, dg, n, scratch, dx, dwords, dwords + 1, dwords + 2));
+  int h[4];
+  SFM_CUDA(cudaMemcpyAsync(x, dx, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  SFM_CUDA(cudaMemcpyAsync(h, dwords, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+  SFM_CUDA(cudaStreamSynchronize(ctx->stream));
+  *solved = h[0];
+  if (iterations) *iterations = h[2];
   return SFM_OK;
 }

@@ -413,9 +413,10 @@ class Context:
         check(lib.sfm_ba_reference_fd(self._h, _dptr(x), len(x), int(n_points), _dptr(f0), None if J is None else _dptr(J)))
         return f0, J
 
-    def reduced_solve(self, S, g):
+    def reduced_solve(self, S, g, method: str = "cholesky"):
         """S x = -g for a dense symmetric positive definite S (6C x 6C, only its lower triangle is read) — the reduced
-        camera system solve of an LM step (csrc/solve.cu) on its own.  Returns (x float64, info)."""
+        camera system solve of an LM step on its own.  method "cholesky" (csrc/solve.cu) returns (x float64, info);
+        "pcg" (csrc/pcg.cu, the LM step's default) returns (x, solved, iterations)."""
         S = np.asarray(S)
         n = S.shape[0]
         C = n // 6
@@ -426,6 +427,10 @@ class Context:
         g = np.ascontiguousarray(g, np.float32).ravel()
         x = np.empty(n)
         info = np.zeros(1, np.int32)
+        if method == "pcg":
+            its = np.zeros(1, np.int32)
+            check(lib.sfm_reduced_solve_pcg(self._h, _dptr(blocks), _dptr(g), C, _dptr(x), _dptr(info), _dptr(its)))
+            return x, bool(info[0]), int(its[0])
         check(lib.sfm_reduced_solve(self._h, _dptr(blocks), _dptr(g), C, _dptr(x), _dptr(info)))
         return x, int(info[0])
 

@@ -86,6 +86,30 @@ def test_reduced_solve_equals_dense_factorisation(engine, C):
     assert 1 <= info_bad <= k + 1
 
 
+@pytest.mark.parametrize("C", [1, 7, 50, 200, 500])
+def test_reduced_solve_by_conjugate_gradients(engine, C):
+    """The LM step's default linear solver (csrc/pcg.cu: block-Jacobi preconditioned conjugate gradients in one persistent
+    kernel) against LAPACK on the same float32 data; a system that is not positive definite is reported as unsolved
+    (the LM step then runs the factorisation)."""
+    rng = np.random.default_rng(100 + C)
+    n = 6 * C
+    B = rng.normal(size=(n, n + 8))
+    S = (B @ B.T / n + 0.5 * np.eye(n)).astype(np.float32)
+    S = np.tril(S) + np.tril(S, -1).T
+    g = rng.normal(size=n).astype(np.float32)
+    x, solved, its = engine.reduced_solve(S, g, method="pcg")
+    ref = np.linalg.solve(S.astype(np.float64), -g.astype(np.float64))
+    assert solved and 1 <= its <= 400
+    assert np.abs(x - ref).max() <= 1e-6 * np.abs(ref).max(), (its, np.abs(x - ref).max() / np.abs(ref).max())
+    # the same system twice gives the same bits (fixed summation order, no atomics)
+    x2, _, its2 = engine.reduced_solve(S, g, method="pcg")
+    assert its2 == its and np.array_equal(x, x2)
+    Sbad = S.copy()
+    Sbad[n // 2, n // 2] = -1.0
+    _, solved_bad, _ = engine.reduced_solve(Sbad, g, method="pcg")
+    assert not solved_bad
+
+
 def test_lm_iterations_reduce_cost_like_dense_gauss_newton(engine):
     pb = _small(seed=2, n_cam=8, n_pt=400, opp=5)
     prob = _make(engine, pb)
