@@ -349,6 +349,7 @@ int sfm_spd_pcg(sfm_ctx* ctx, const float* S, const float* g, int n, double* scr
   P.parts = std::max(1, std::min(std::min(64, P.C), total_warps / P.C));
   P.units = P.C * P.parts;
   P.max_iter = 400;
+  if (const char* e = getenv("SFM_PCG_MAX_ITER")) P.max_iter = std::max(1, atoi(e));      // (tests: 1 forces the fallback path)
   P.tol2 = 1e-8 * 1e-8;
   P.S = S;
   P.g = g;
@@ -361,6 +362,7 @@ int sfm_spd_pcg(sfm_ctx* ctx, const float* S, const float* g, int n, double* scr
   P.stamps = getenv("SFM_PCG_TIMELINE") ? reinterpret_cast<long long*>(scratch + 2 * (size_t)P.units * 6 + 2) : nullptr;
   SFM_CUDA(cudaMemsetAsync(P.bar, 0, 2 * sizeof(unsigned int), ctx->stream));
   SFM_CUDA(cudaMemsetAsync(status_dev, 0, sizeof(int), ctx->stream));
+  if (info) SFM_CUDA(cudaMemsetAsync(info, 0, sizeof(int), ctx->stream));      // (the fallback behind this solve sets it on a bad pivot)
   const size_t smem = pcg_smem_bytes(n);
   static size_t attr_set = 0;
   if (smem > attr_set) {

@@ -154,6 +154,23 @@ def test_first_step_matches_dense_normal_equations(engine):
     assert np.abs(d_p - dx[6 * C:]).max() <= 2e-3 * np.abs(dx[6 * C:]).max()
 
 
+def test_lm_step_falls_back_to_the_factorisation(engine, monkeypatch):
+    """When the conjugate-gradient solver reports failure (here: forced by allowing it one iteration) the tile Cholesky
+    behind it produces the step — same answer as the dense solve, solve_info 0."""
+    monkeypatch.setenv("SFM_PCG_MAX_ITER", "1")
+    pb = _small(seed=5, n_cam=12, n_pt=300, opp=4)
+    prob = _make(engine, pb)
+    st = prob.gn_step(1e-3)
+    monkeypatch.delenv("SFM_PCG_MAX_ITER")
+    prob2 = _make(engine, pb)
+    st2 = prob2.gn_step(1e-3)
+    assert st["solve_info"] == 0 and st2["solve_info"] == 0 and st["accepted"] and st2["accepted"]
+    c1, p1 = prob.get_params()
+    c2, p2 = prob2.get_params()
+    assert np.abs(c1 - c2).max() <= 1e-6 * np.abs(c2 - pb["cams0"]).max()
+    assert abs(st["cost_after"] - st2["cost_after"]) <= 1e-9 * st2["cost_after"]
+
+
 def test_reference_formulation_residual_and_fd_jacobian(engine, golden):
     """sfm_ba_reference_fd: OptimReprojectionError (sfm.py:104-136) at the golden x — against the value the reference's
     own def produced — and its finite-difference Jacobian against scipy's approx_derivative over the oracle's port."""
