@@ -479,7 +479,11 @@ __global__ void ba_update_cams_kernel(const double* __restrict__ cams, const dou
 int solve_reduced_system(sfm_ba* ba) {
   const int n = 6 * ba->n_cam;
   static const bool chol_only = [] { const char* e = getenv("SFM_BA_SOLVER"); return e && e[0] == 'c'; }();
-  if (ba->pcg && !chol_only) {
+  // small systems (a few tile columns) are factored faster than iterated: the iteration has a floor of one grid barrier
+  // and two L2 round trips whatever n is
+  int min_n = 600;
+  if (const char* e = getenv("SFM_PCG_MIN_N")) min_n = atoi(e);
+  if (ba->pcg && !chol_only && n >= min_n) {
     SFM_TRY(sfm_spd_pcg(ba->ctx, ba->S, ba->g, n, ba->pcg, ba->dc, ba->info + 1, ba->info, ba->info + 2));
     return sfm_spd_solve(ba->ctx, ba->S, ba->g, n, ba->A64, ba->dc, ba->info, ba->info + 1);
   }
@@ -823,7 +827,9 @@ extern "C" int sfm_ba_gn_step(sfm_ba* ba, double lambda, sfm_ba_stats* stats) {
     stats->grad_norm = 0.0;
     stats->accepted = ok ? 1 : 0;
     stats->solve_info = *hinfo;
-    stats->lambda_next = ok ? fmax(lambda / 10.0, 1e-12) : fmin(fmax(lambda, 1e-6) * 10.0, 1e12);
+    // the damping is not taken below 1e-6: S is accumulated in float32, and a relative damping under its rounding
+    // (~1e-7) leaves the gauge directions numerically singular — any solver then returns a step dominated by them
+    stats->lambda_next = ok ? fmax(lambda / 10.0, 1e-6) : fmin(fmax(lambda, 1e-6) * 10.0, 1e12);
   }
   return SFM_OK;
 }

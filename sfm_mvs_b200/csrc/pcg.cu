@@ -186,10 +186,11 @@ __global__ void __launch_bounds__(PCG_THREADS, 1) spd_pcg_kernel(PcgPlan P) {
   if (s_fail || !isfinite(bb) || !isfinite(rz)) state = 2;
   else if (bb == 0.0) state = 1;
   int it = 0;
+  bool verifying = false;
   const int gw = blockIdx.x * PCG_WARPS + warp, total_warps = gridDim.x * PCG_WARPS;
   const bool tl = P.stamps && blockIdx.x == 0 && tid == 0;
   long long t_mv = 0, t_bar = 0, t_vec = 0, t_v1 = 0, t_v2 = 0, t_v3 = 0, t0 = tl ? clock64() : 0, t1 = 0;
-  while (state == 0 && it < P.max_iter) {
+  while (state == 0 && (it < P.max_iter || verifying)) {
     // ---- S p: one unit per warp
     double* part = P.partial + (size_t)(it & 1) * P.units * 6;
     for (int u = gw; u < P.units; u += total_warps) {
@@ -271,6 +272,18 @@ __global__ void __launch_bounds__(PCG_THREADS, 1) spd_pcg_kernel(PcgPlan P) {
       }
     }
     if (tl) { t1 = clock64(); t_v1 += t1 - t0; }
+    if (verifying) {
+      // p held x: w = S x.  The recursively updated residual has converged; the TRUE residual b - S x decides — on a
+      // numerically singular system (lambda ~ 1e-7 on float32 data) the two part ways and x is not a solution.
+      double tr_l = 0.0;
+      for (int i = tid; i < n; i += PCG_THREADS) {
+        const double d = -(double)P.g[i] - ws[i];
+        tr_l += d * d;
+      }
+      const double tr = block_sum(tr_l, red);
+      state = (isfinite(tr) && tr <= 1e4 * P.tol2 * bb) ? 1 : 2;       // within 100 x the tolerance
+      break;
+    }
     const double pw = block_sum(pw_l, red);
     if (!(pw > 0.0) || !isfinite(pw)) { state = 2; break; }
     const double alpha = rz / pw;
@@ -301,7 +314,12 @@ __global__ void __launch_bounds__(PCG_THREADS, 1) spd_pcg_kernel(PcgPlan P) {
     if (tl) { const long long t = clock64(); t_v3 += t - t1; t1 = t; }
     ++it;
     if (!isfinite(rr) || !isfinite(rz_new)) { state = 2; break; }
-    if (rr <= P.tol2 * bb) { state = 1; break; }
+    if (rr <= P.tol2 * bb) {             // one more product, with x in the place of p
+      verifying = true;
+      for (int i = tid; i < n; i += PCG_THREADS) ps[i] = xs[i];
+      __syncthreads();
+      continue;
+    }
     const double beta = rz_new / rz;
     rz = rz_new;
     for (int i = tid; i < n; i += PCG_THREADS) ps[i] = ws[i] + beta * ps[i];

@@ -158,11 +158,12 @@ def test_lm_step_falls_back_to_the_factorisation(engine, monkeypatch):
     """When the conjugate-gradient solver reports failure (here: forced by allowing it one iteration) the tile Cholesky
     behind it produces the step — same answer as the dense solve, solve_info 0."""
     monkeypatch.setenv("SFM_PCG_MAX_ITER", "1")
+    monkeypatch.setenv("SFM_PCG_MIN_N", "6")           # (systems this small are factored directly by default)
     pb = _small(seed=5, n_cam=12, n_pt=300, opp=4)
     prob = _make(engine, pb)
     st = prob.gn_step(1e-3)
     monkeypatch.delenv("SFM_PCG_MAX_ITER")
-    prob2 = _make(engine, pb)
+    prob2 = _make(engine, pb)                          # conjugate gradients this time
     st2 = prob2.gn_step(1e-3)
     assert st["solve_info"] == 0 and st2["solve_info"] == 0 and st["accepted"] and st2["accepted"]
     c1, p1 = prob.get_params()
