@@ -43,6 +43,8 @@ if "ba" in parts:          # K5, K6, tile Cholesky graph, back substitution, upd
     B = np.random.default_rng(2).normal(size=(132, 140))
     x, info = ctx.reduced_solve(B @ B.T / 132 + 0.5 * np.eye(132), np.ones(132))       # three tile columns
     print("solve ok", info)
+    x2, solved, its = ctx.reduced_solve(B @ B.T / 132 + 0.5 * np.eye(132), np.ones(132), method="pcg")     # CG kernel: grid barrier
+    print("pcg ok", solved, its, float(np.abs(x - x2).max()))
     prob.close()
 if "init" in parts:        # five-point RANSAC + recoverPose
     tv0, tv1, _, _ = synth.two_view_pair(300, seed=3)
