@@ -268,15 +268,17 @@ __device__ __forceinline__ void inv_sym3(const double* h, double lambda, double*
   inv[3] = (a * f - c * c) * id; inv[4] = (b * c - a * e) * id; inv[5] = (a * d - b * b) * id;
 }
 
-struct WarpPoint {            // per-warp shared scratch of the fused kernels
-  float W[BA_MAXO][18];       // W_a = Jc^T Jp   (6x3)
-  float T[BA_MAXO][18];       // T_a = W_a * Hpp^-1
-  int cam[BA_MAXO];
+template <int CAP>
+struct WarpPoint {            // per-warp shared scratch of the fused kernels, for points with up to CAP observations
+  float W[CAP][18];           // W_a = Jc^T Jp   (6x3)
+  float T[CAP][18];           // T_a = W_a * Hpp^-1
+  int cam[CAP];
 };
 
 // Per point (one warp): accumulate Hpp/bp over its observations, per-observation W, Hcc/bc via
 // atomics; returns (in every lane) Hpp (6), bp (3).  MODE_UPDATE additionally needs dc.
-__device__ __forceinline__ void point_accumulate(WarpPoint& wp, int lane, int o_begin, int nobs,
+template <int CAP>
+__device__ __forceinline__ void point_accumulate(WarpPoint<CAP>& wp, int lane, int o_begin, int nobs,
                                                  const float2* __restrict__ uv, const int* __restrict__ cam_idx,
                                                  const double* __restrict__ cams, const double* X, const Intr& K,
                                                  bool accumulate_cam, float* __restrict__ S, int ld,
@@ -327,12 +329,19 @@ __device__ __forceinline__ void point_accumulate(WarpPoint& wp, int lane, int o_
   for (int k = 0; k < 3; ++k) bp[k] = warp_sum_d(b[k]);
 }
 
-constexpr int SCHUR_WARPS = 12;     // with S stored by 6x6 blocks (16-byte reductions): 4 warps 0.79 ms, 8: 0.73, 12: 0.71 (row-major S, 8-byte: 0.90 / - / 1.04)
-constexpr int UPDATE_WARPS = 12;    // the point update is latency-bound: 0.33 -> 0.16 ms from 4 to 12 warps per SM
+// Warps per CTA of the two per-point kernels (one CTA per SM: the camera table takes 72 KB of its shared memory).  Both
+// are bound by latency — the index -> camera -> geometry chain of a point, the shared-memory round trips of its pairs
+// (ncu: issue slots 28 % busy, 12 of 32 lanes active on average) — and the per-warp scratch is sized by the problem's
+// largest point (CAP = 16 or 64 observations), so that more warps fit when the points are small.  Measured at 1 M
+// observations, 10 per point: Schur 0.79 / 0.73 / 0.71 ms with 4 / 8 / 12 warps of CAP 64 and 0.63 ms with 12 or 20 of
+// CAP 16 (it does not scale further: with the 55 block reductions of a point left out it takes 0.33 ms — the other
+// half is the L2 retiring 9 sector reductions per 6x6 block); the update 0.33 ms at 4 warps, 0.16 at 12, 0.11 at 20.
+template <int CAP> struct FusedWarps { static constexpr int N = 12; };
+template <> struct FusedWarps<16> { static constexpr int N = 20; };
 
 // S -= sum_p W Hpp^-1 W^T (lower block triangle), g += bc - W Hpp^-1 bp, diag blocks += Hcc.
-template <bool SMEM_CAMS>
-__global__ void __launch_bounds__(SCHUR_WARPS * 32) ba_schur_kernel(const float2* __restrict__ uv,
+template <bool SMEM_CAMS, int CAP>
+__global__ void __launch_bounds__(FusedWarps<CAP>::N * 32) ba_schur_kernel(const float2* __restrict__ uv,
                                                                     const int* __restrict__ cam_idx,
                                                                     const int* __restrict__ pt_start, int n_pt,
                                                                     const double* __restrict__ cam_pre, int n_cam,
@@ -341,17 +350,18 @@ __global__ void __launch_bounds__(SCHUR_WARPS * 32) ba_schur_kernel(const float2
                                                                     float* __restrict__ g, float* __restrict__ hdiag,
                                                                     double* __restrict__ cost) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  WarpPoint* wps = reinterpret_cast<WarpPoint*>(smem_raw);
-  double* s_cam = reinterpret_cast<double*>(smem_raw + sizeof(WarpPoint) * SCHUR_WARPS);
+  constexpr int WARPS = FusedWarps<CAP>::N;
+  WarpPoint<CAP>* wps = reinterpret_cast<WarpPoint<CAP>*>(smem_raw);
+  double* s_cam = reinterpret_cast<double*>(smem_raw + sizeof(WarpPoint<CAP>) * WARPS);
   if (SMEM_CAMS) {
     for (int i = threadIdx.x; i < n_cam * CAM_PRE; i += blockDim.x) s_cam[i] = cam_pre[i];
     __syncthreads();
   }
   const double* cams = SMEM_CAMS ? s_cam : cam_pre;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  WarpPoint& wp = wps[warp];
+  WarpPoint<CAP>& wp = wps[warp];
   double cost_local = 0.0;
-  for (int p = blockIdx.x * SCHUR_WARPS + warp; p < n_pt; p += gridDim.x * SCHUR_WARPS) {
+  for (int p = blockIdx.x * WARPS + warp; p < n_pt; p += gridDim.x * WARPS) {
     const int o_begin = __ldg(pt_start + p), nobs = __ldg(pt_start + p + 1) - o_begin;
     if (nobs <= 0) continue;
     const double X[3] = {__ldg(pts + 3 * (size_t)p), __ldg(pts + 3 * (size_t)p + 1), __ldg(pts + 3 * (size_t)p + 2)};
@@ -411,23 +421,24 @@ __global__ void ba_damp_kernel(float* __restrict__ S, int ld, const float* __res
 
 // ------------------------------------------------------------------ back-substitution + update
 // dp = -Hpp_d^-1 (bp + sum_a W_a^T dc[cam_a]);  candidate point = point + dp
-template <bool SMEM_CAMS>
-__global__ void __launch_bounds__(UPDATE_WARPS * 32) ba_update_points_kernel(
+template <bool SMEM_CAMS, int CAP>
+__global__ void __launch_bounds__(FusedWarps<CAP>::N * 32) ba_update_points_kernel(
     const float2* __restrict__ uv, const int* __restrict__ cam_idx, const int* __restrict__ pt_start, int n_pt,
     const double* __restrict__ cam_pre, int n_cam, const double* __restrict__ pts, Intr K, double lambda,
     const double* __restrict__ dc, double* __restrict__ pts_new, double* __restrict__ step2) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  WarpPoint* wps = reinterpret_cast<WarpPoint*>(smem_raw);
-  double* s_cam = reinterpret_cast<double*>(smem_raw + sizeof(WarpPoint) * UPDATE_WARPS);
+  constexpr int WARPS = FusedWarps<CAP>::N;
+  WarpPoint<CAP>* wps = reinterpret_cast<WarpPoint<CAP>*>(smem_raw);
+  double* s_cam = reinterpret_cast<double*>(smem_raw + sizeof(WarpPoint<CAP>) * WARPS);
   if (SMEM_CAMS) {
     for (int i = threadIdx.x; i < n_cam * CAM_PRE; i += blockDim.x) s_cam[i] = cam_pre[i];
     __syncthreads();
   }
   const double* cams = SMEM_CAMS ? s_cam : cam_pre;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  WarpPoint& wp = wps[warp];
+  WarpPoint<CAP>& wp = wps[warp];
   double step_local = 0.0;
-  for (int p = blockIdx.x * UPDATE_WARPS + warp; p < n_pt; p += gridDim.x * UPDATE_WARPS) {
+  for (int p = blockIdx.x * WARPS + warp; p < n_pt; p += gridDim.x * WARPS) {
     const int o_begin = __ldg(pt_start + p), nobs = __ldg(pt_start + p + 1) - o_begin;
     const double X[3] = {__ldg(pts + 3 * (size_t)p), __ldg(pts + 3 * (size_t)p + 1), __ldg(pts + 3 * (size_t)p + 2)};
     if (nobs <= 0) {
@@ -555,6 +566,67 @@ int launch_eval(sfm_ba* ba, const double* pts, float* r, float* Jc, float* Jp, d
   return launch_eval_v<MODE, false>(ba, pts, r, Jc, Jp, cost_dev);
 }
 
+template <int CAP>
+int launch_schur(sfm_ba* ba, double lambda) {
+  sfm_ctx* ctx = ba->ctx;
+  constexpr int WARPS = FusedWarps<CAP>::N;
+  const int n = 6 * ba->n_cam;
+  const size_t wp_bytes = sizeof(WarpPoint<CAP>) * WARPS;
+  const size_t smem_cams = cam_smem_bytes(ba);
+  const bool in_smem = wp_bytes + smem_cams <= 216 * 1024;
+  const int grid = std::max(1, std::min(div_up(ba->n_pt, WARPS), ctx->sm_count * (in_smem ? 1 : 4)));
+  if (in_smem) {
+    static bool attr = false;
+    if (!attr) {
+      SFM_CUDA(cudaFuncSetAttribute(ba_schur_kernel<true, CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
+      attr = true;
+    }
+    SFM_LAUNCH(ctx, SFM_K_BA_SCHUR, (ba_schur_kernel<true, CAP><<<grid, WARPS * 32, wp_bytes + smem_cams, ctx->stream>>>(
+                                        ba->uv, ba->cam_idx, ba->pt_start, ba->n_pt, ba->cam_pre, ba->n_cam, ba->pts,
+                                        make_intr(ba), lambda, ba->S, n, ba->g, ba->hdiag, ba->scal + 0)));
+  } else {
+    static bool attr = false;
+    if (!attr) {
+      SFM_CUDA(cudaFuncSetAttribute(ba_schur_kernel<false, CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+      attr = true;
+    }
+    SFM_LAUNCH(ctx, SFM_K_BA_SCHUR, (ba_schur_kernel<false, CAP><<<grid, WARPS * 32, wp_bytes, ctx->stream>>>(
+                                        ba->uv, ba->cam_idx, ba->pt_start, ba->n_pt, ba->cam_pre, ba->n_cam, ba->pts,
+                                        make_intr(ba), lambda, ba->S, n, ba->g, ba->hdiag, ba->scal + 0)));
+  }
+  return SFM_OK;
+}
+
+template <int CAP>
+int launch_update(sfm_ba* ba, double lambda) {
+  sfm_ctx* ctx = ba->ctx;
+  constexpr int WARPS = FusedWarps<CAP>::N;
+  const size_t wp_bytes = sizeof(WarpPoint<CAP>) * WARPS;
+  const size_t smem_cams = cam_smem_bytes(ba);
+  const bool in_smem = wp_bytes + smem_cams <= 216 * 1024;
+  const int grid = std::max(1, std::min(div_up(ba->n_pt, WARPS), ctx->sm_count * (in_smem ? 1 : 4)));
+  if (in_smem) {
+    static bool attr = false;
+    if (!attr) {
+      SFM_CUDA(cudaFuncSetAttribute(ba_update_points_kernel<true, CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
+      attr = true;
+    }
+    SFM_LAUNCH(ctx, SFM_K_BA_UPDATE, (ba_update_points_kernel<true, CAP><<<grid, WARPS * 32, wp_bytes + smem_cams, ctx->stream>>>(
+                                         ba->uv, ba->cam_idx, ba->pt_start, ba->n_pt, ba->cam_pre, ba->n_cam, ba->pts,
+                                         make_intr(ba), lambda, ba->dc, ba->pts_new, ba->scal + 2)));
+  } else {
+    static bool attr = false;
+    if (!attr) {
+      SFM_CUDA(cudaFuncSetAttribute(ba_update_points_kernel<false, CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+      attr = true;
+    }
+    SFM_LAUNCH(ctx, SFM_K_BA_UPDATE, (ba_update_points_kernel<false, CAP><<<grid, WARPS * 32, wp_bytes, ctx->stream>>>(
+                                         ba->uv, ba->cam_idx, ba->pt_start, ba->n_pt, ba->cam_pre, ba->n_cam, ba->pts,
+                                         make_intr(ba), lambda, ba->dc, ba->pts_new, ba->scal + 2)));
+  }
+  return SFM_OK;
+}
+
 int build_system(sfm_ba* ba, double lambda) {
   sfm_ctx* ctx = ba->ctx;
   const int n = 6 * ba->n_cam;
@@ -562,30 +634,9 @@ int build_system(sfm_ba* ba, double lambda) {
   // S | g | hdiag are one allocation (sys_f32) so a single memset / all-reduce covers them
   SFM_CUDA(cudaMemsetAsync(ba->S, 0, ba->sys_count * sizeof(float), ctx->stream));
   SFM_CUDA(cudaMemsetAsync(ba->scal, 0, 8 * sizeof(double), ctx->stream));
-  const size_t wp_bytes = sizeof(WarpPoint) * SCHUR_WARPS;
-  const size_t smem_cams = cam_smem_bytes(ba);
-  const bool in_smem = wp_bytes + smem_cams <= 216 * 1024;
-  int grid = std::max(1, std::min(div_up(ba->n_pt, SCHUR_WARPS), ctx->sm_count * (in_smem ? 1 : 4)));
   if (ba->n_pt > 0) {
-    if (in_smem) {
-      static bool attr = false;
-      if (!attr) {
-        SFM_CUDA(cudaFuncSetAttribute(ba_schur_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
-        attr = true;
-      }
-      SFM_LAUNCH(ctx, SFM_K_BA_SCHUR, (ba_schur_kernel<true><<<grid, SCHUR_WARPS * 32, wp_bytes + smem_cams, ctx->stream>>>(
-                                          ba->uv, ba->cam_idx, ba->pt_start, ba->n_pt, ba->cam_pre, ba->n_cam, ba->pts,
-                                          make_intr(ba), lambda, ba->S, n, ba->g, ba->hdiag, ba->scal + 0)));
-    } else {
-      static bool attr = false;
-      if (!attr) {
-        SFM_CUDA(cudaFuncSetAttribute(ba_schur_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-        attr = true;
-      }
-      SFM_LAUNCH(ctx, SFM_K_BA_SCHUR, (ba_schur_kernel<false><<<grid, SCHUR_WARPS * 32, wp_bytes, ctx->stream>>>(
-                                          ba->uv, ba->cam_idx, ba->pt_start, ba->n_pt, ba->cam_pre, ba->n_cam, ba->pts,
-                                          make_intr(ba), lambda, ba->S, n, ba->g, ba->hdiag, ba->scal + 0)));
-    }
+    if (ba->max_deg <= 16) SFM_TRY((launch_schur<16>(ba, lambda)));
+    else SFM_TRY((launch_schur<BA_MAXO>(ba, lambda)));
   }
   // exchange step (C1): sum of the partial systems and of the cost over ranks
   SFM_TRY(sfm_ba_allreduce_system(ba));
@@ -594,32 +645,9 @@ int build_system(sfm_ba* ba, double lambda) {
 }
 
 int update_points(sfm_ba* ba, double lambda) {
-  sfm_ctx* ctx = ba->ctx;
-  const size_t wp_bytes = sizeof(WarpPoint) * UPDATE_WARPS;
-  const size_t smem_cams = cam_smem_bytes(ba);
-  const bool in_smem = wp_bytes + smem_cams <= 216 * 1024;
-  int grid = std::max(1, std::min(div_up(ba->n_pt, UPDATE_WARPS), ctx->sm_count * (in_smem ? 1 : 4)));
   if (ba->n_pt == 0) return SFM_OK;
-  if (in_smem) {
-    static bool attr = false;
-    if (!attr) {
-      SFM_CUDA(cudaFuncSetAttribute(ba_update_points_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
-      attr = true;
-    }
-    SFM_LAUNCH(ctx, SFM_K_BA_UPDATE, (ba_update_points_kernel<true><<<grid, UPDATE_WARPS * 32, wp_bytes + smem_cams, ctx->stream>>>(
-                                         ba->uv, ba->cam_idx, ba->pt_start, ba->n_pt, ba->cam_pre, ba->n_cam, ba->pts,
-                                         make_intr(ba), lambda, ba->dc, ba->pts_new, ba->scal + 2)));
-  } else {
-    static bool attr = false;
-    if (!attr) {
-      SFM_CUDA(cudaFuncSetAttribute(ba_update_points_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-      attr = true;
-    }
-    SFM_LAUNCH(ctx, SFM_K_BA_UPDATE, (ba_update_points_kernel<false><<<grid, UPDATE_WARPS * 32, wp_bytes, ctx->stream>>>(
-                                         ba->uv, ba->cam_idx, ba->pt_start, ba->n_pt, ba->cam_pre, ba->n_cam, ba->pts,
-                                         make_intr(ba), lambda, ba->dc, ba->pts_new, ba->scal + 2)));
-  }
-  return SFM_OK;
+  if (ba->max_deg <= 16) return launch_update<16>(ba, lambda);
+  return launch_update<BA_MAXO>(ba, lambda);
 }
 
 }  // namespace
@@ -639,7 +667,9 @@ extern "C" int sfm_ba_create(sfm_ctx* ctx, int n_cam, int n_pt, int n_obs, const
     SFM_REQUIRE(o == 0 || pt_idx[o] >= pt_idx[o - 1], "sfm_ba_create: observations must be sorted point-major (pt_idx non-decreasing)");
     start[(size_t)pt_idx[o] + 1]++;
   }
+  int ba_max_deg = 0;
   for (int p = 0; p < n_pt; ++p) {
+    ba_max_deg = std::max(ba_max_deg, start[(size_t)p + 1]);
     if (start[(size_t)p + 1] > BA_MAXO) {
       sfm_set_error("sfm_ba_create: point %d has %d observations; the fused kernels handle at most %d", p, start[(size_t)p + 1], BA_MAXO);
       return SFM_ERR_UNSUPPORTED;
@@ -650,6 +680,7 @@ extern "C" int sfm_ba_create(sfm_ctx* ctx, int n_cam, int n_pt, int n_obs, const
   sfm_ba* ba = new sfm_ba();
   ba->ctx = ctx; ba->n_cam = n_cam; ba->n_pt = n_pt; ba->n_obs = n_obs;
   ba->n_pt_total = n_pt; ba->n_obs_total = n_obs;
+  ba->max_deg = ba_max_deg;
   memcpy(ba->K, K, 9 * sizeof(double));
   const int n = 6 * n_cam;
   // S: the lower block triangle only, block (ca, cb), cb <= ca, = 36 contiguous floats at ((ca (ca+1) / 2) + cb) * 36 —

@@ -14,6 +14,7 @@ struct sfm_ba {
   int* cam_idx = nullptr;
   int* pt_idx = nullptr;
   int* pt_start = nullptr;
+  int max_deg = 0;                             // most observations of one point (sizes the per-warp scratch of the fused kernels)
   // parameters and step candidates
   double *cams = nullptr, *cams_new = nullptr, *pts = nullptr, *pts_new = nullptr;
   double* cam_pre = nullptr;                   // [C] 144-byte records: R, t float64 | Jl float32
