@@ -312,8 +312,10 @@ __device__ __forceinline__ void point_accumulate(WarpPoint<CAP>& wp, int lane, i
       for (int i = 0; i < 6; ++i) {
 #pragma unroll
         for (int j = 0; j < 6; ++j) blk[6 * i + j] = (float)(Jc[0][i] * Jc[0][j] + Jc[1][i] * Jc[1][j]);
-        atomicAdd(hdiag + 6 * c + i, blk[7 * i]);
       }
+      red_add_v2(hdiag + 6 * c, blk[0], blk[7]);
+      red_add_v2(hdiag + 6 * c + 2, blk[14], blk[21]);
+      red_add_v2(hdiag + 6 * c + 4, blk[28], blk[35]);
       red_add_block36(Sd, blk);
       float gc[6];
 #pragma unroll
