@@ -362,6 +362,17 @@ __global__ void __launch_bounds__(FusedWarps<CAP>::N * 32) ba_schur_kernel(const
   const double* cams = SMEM_CAMS ? s_cam : cam_pre;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   WarpPoint<CAP>& wp = wps[warp];
+  // (a, b), a <= b, of the q-th unordered pair, q = b (b + 1) / 2 + a: a table for small points
+  __shared__ unsigned char s_tri[CAP <= 16 ? 2 * 136 : 2];
+  if (CAP <= 16) {
+    for (int q = threadIdx.x; q < 136; q += blockDim.x) {
+      int b = 0;
+      while ((b + 1) * (b + 2) / 2 <= q) ++b;
+      s_tri[2 * q] = (unsigned char)(q - b * (b + 1) / 2);
+      s_tri[2 * q + 1] = (unsigned char)b;
+    }
+    __syncthreads();
+  }
   double cost_local = 0.0;
   for (int p = blockIdx.x * WARPS + warp; p < n_pt; p += gridDim.x * WARPS) {
     const int o_begin = __ldg(pt_start + p), nobs = __ldg(pt_start + p + 1) - o_begin;
@@ -392,22 +403,47 @@ __global__ void __launch_bounds__(FusedWarps<CAP>::N * 32) ba_schur_kernel(const
       red_add_v2(gp + 4, gc[4], gc[5]);
     }
     __syncwarp();
-    // ordered pairs (a,b) with cam_a >= cam_b: block (cam_a, cam_b) -= T_a W_b^T
-    const int npair = nobs * nobs;
-    for (int q = lane; q < npair; q += 32) {
-      const int a = q / nobs, b = q - a * nobs;
-      const int ca = wp.cam[a], cb = wp.cam[b];
-      if (ca < cb) continue;
-      const float* Ta = wp.T[a];
-      const float* Wb = wp.W[b];
-      float* Sd = S + ((size_t)ca * (ca + 1) / 2 + cb) * 36;
-      float blk[36];
+    // Unordered observation pairs a <= b, oriented by camera index: block (c_hi, c_lo) -= T_hi W_lo^T.  NINE lanes per
+    // pair, three pairs per step: lane k of a group forms elements 4k .. 4k+3 of the 6x6 block and issues ONE 16-byte
+    // reduction, so the nine reductions of a block come from one instruction and reach L2 as the 5 sectors the block
+    // spans — the kernel is bound by the sector reductions L2 retires (9 per block when every lane updates its own
+    // block: 0.59 ms, 0.33 ms with the block reductions left out).
+    // Two observations of ONE camera (a != b, equal cameras) contribute both orientations to the same diagonal block.
+    const int ntri = nobs * (nobs + 1) / 2;
+    const int grp = lane / 9, kq = lane - 9 * grp;
+    if (grp < 3) {
+      for (int t0 = 0; t0 < ntri; t0 += 3) {
+        const int q = t0 + grp;
+        if (q < ntri) {
+          int a, b;
+          if (CAP <= 16) {
+            a = s_tri[2 * q]; b = s_tri[2 * q + 1];
+          } else {
+            b = (int)((sqrtf(8.f * (float)q + 1.f) - 1.f) * 0.5f);
+            while ((b + 1) * (b + 2) / 2 <= q) ++b;
+            while (b * (b + 1) / 2 > q) --b;
+            a = q - b * (b + 1) / 2;
+          }
+          const int ca = wp.cam[a], cb = wp.cam[b];
+          const bool sw = ca < cb;
+          int hi = sw ? b : a, lo = sw ? a : b;
+          const int chi = sw ? cb : ca, clo = sw ? ca : cb;
+          float* Sd = S + ((size_t)chi * (chi + 1) / 2 + clo) * 36 + 4 * kq;
+          const int reps = (a != b && ca == cb) ? 2 : 1;
+          for (int rep = 0; rep < reps; ++rep) {
+            const float* Ta = wp.T[hi];
+            const float* Wb = wp.W[lo];
+            float v[4];
 #pragma unroll
-      for (int i = 0; i < 6; ++i)
-#pragma unroll
-        for (int j = 0; j < 6; ++j)
-          blk[6 * i + j] = -(Ta[3 * i] * Wb[3 * j] + Ta[3 * i + 1] * Wb[3 * j + 1] + Ta[3 * i + 2] * Wb[3 * j + 2]);
-      red_add_block36(Sd, blk);
+            for (int e = 0; e < 4; ++e) {
+              const int m = 4 * kq + e, i = m / 6, j = m - 6 * i;
+              v[e] = -(Ta[3 * i] * Wb[3 * j] + Ta[3 * i + 1] * Wb[3 * j + 1] + Ta[3 * i + 2] * Wb[3 * j + 2]);
+            }
+            red_add_v4(Sd, v[0], v[1], v[2], v[3]);
+            const int tmp = hi; hi = lo; lo = tmp;
+          }
+        }
+      }
     }
     __syncwarp();
   }
