@@ -272,6 +272,8 @@ template <int CAP>
 struct WarpPoint {            // per-warp shared scratch of the fused kernels, for points with up to CAP observations
   float W[CAP][18];           // W_a = Jc^T Jp   (6x3)
   float T[CAP][18];           // T_a = W_a * Hpp^-1
+  float J[CAP][12];           // Jc of the observation (2x6): its Hcc = Jc^T Jc joins the (a, a) block update of the Schur kernel
+  float gc[CAP][6];           // Jc^T r of the observation: joins the one reduction of g per observation
   int cam[CAP];
 };
 
@@ -306,23 +308,17 @@ __device__ __forceinline__ void point_accumulate(WarpPoint<CAP>& wp, int lane, i
 #pragma unroll
       for (int k = 0; k < 3; ++k) wp.W[a][3 * i + k] = (float)(Jc[0][i] * Jp[0][k] + Jc[1][i] * Jp[1][k]);
     if (accumulate_cam) {
-      float* Sd = S + ((size_t)c * (c + 1) / 2 + c) * 36;
-      float blk[36];
+      // Hcc and bc of the observation are NOT reduced here: they ride on the (a, a) block update and on the g update
+      // of the Schur kernel's later phases (one set of reductions per observation instead of two)
 #pragma unroll
       for (int i = 0; i < 6; ++i) {
-#pragma unroll
-        for (int j = 0; j < 6; ++j) blk[6 * i + j] = (float)(Jc[0][i] * Jc[0][j] + Jc[1][i] * Jc[1][j]);
+        wp.J[a][i] = Jc[0][i];
+        wp.J[a][6 + i] = Jc[1][i];
+        wp.gc[a][i] = (float)(Jc[0][i] * r[0] + Jc[1][i] * r[1]);
       }
-      red_add_v2(hdiag + 6 * c, blk[0], blk[7]);
-      red_add_v2(hdiag + 6 * c + 2, blk[14], blk[21]);
-      red_add_v2(hdiag + 6 * c + 4, blk[28], blk[35]);
-      red_add_block36(Sd, blk);
-      float gc[6];
-#pragma unroll
-      for (int i = 0; i < 6; ++i) gc[i] = (float)(Jc[0][i] * r[0] + Jc[1][i] * r[1]);
-      red_add_v2(g + 6 * c, gc[0], gc[1]);
-      red_add_v2(g + 6 * c + 2, gc[2], gc[3]);
-      red_add_v2(g + 6 * c + 4, gc[4], gc[5]);
+      red_add_v2(hdiag + 6 * c, Jc[0][0] * Jc[0][0] + Jc[1][0] * Jc[1][0], Jc[0][1] * Jc[0][1] + Jc[1][1] * Jc[1][1]);
+      red_add_v2(hdiag + 6 * c + 2, Jc[0][2] * Jc[0][2] + Jc[1][2] * Jc[1][2], Jc[0][3] * Jc[0][3] + Jc[1][3] * Jc[1][3]);
+      red_add_v2(hdiag + 6 * c + 4, Jc[0][4] * Jc[0][4] + Jc[1][4] * Jc[1][4], Jc[0][5] * Jc[0][5] + Jc[1][5] * Jc[1][5]);
     }
   }
 #pragma unroll
@@ -396,7 +392,7 @@ __global__ void __launch_bounds__(FusedWarps<CAP>::N * 32) ba_schur_kernel(const
       for (int k = 0; k < 18; ++k) wp.T[a][k] = t[k];
       float gc[6];
 #pragma unroll
-      for (int i = 0; i < 6; ++i) gc[i] = -(float)(t[3 * i] * bp[0] + t[3 * i + 1] * bp[1] + t[3 * i + 2] * bp[2]);
+      for (int i = 0; i < 6; ++i) gc[i] = wp.gc[a][i] - (float)(t[3 * i] * bp[0] + t[3 * i + 1] * bp[1] + t[3 * i + 2] * bp[2]);
       float* gp = g + 6 * wp.cam[a];
       red_add_v2(gp, gc[0], gc[1]);
       red_add_v2(gp + 2, gc[2], gc[3]);
@@ -438,6 +434,7 @@ __global__ void __launch_bounds__(FusedWarps<CAP>::N * 32) ba_schur_kernel(const
             for (int e = 0; e < 4; ++e) {
               const int m = 4 * kq + e, i = m / 6, j = m - 6 * i;
               v[e] = -(Ta[3 * i] * Wb[3 * j] + Ta[3 * i + 1] * Wb[3 * j + 1] + Ta[3 * i + 2] * Wb[3 * j + 2]);
+              if (a == b) v[e] += wp.J[a][i] * wp.J[a][j] + wp.J[a][6 + i] * wp.J[a][6 + j];      // + Hcc of the observation
             }
             red_add_v4(Sd, v[0], v[1], v[2], v[3]);
             const int tmp = hi; hi = lo; lo = tmp;
