@@ -365,6 +365,7 @@ int sfm_spd_pcg(sfm_ctx* ctx, const float* S, const float* g, int n, double* scr
   const int grid = ctx->sm_count;
   const int total_warps = grid * PCG_WARPS;
   P.parts = std::max(1, std::min(std::min(64, P.C), total_warps / P.C));
+  if (const char* e = getenv("SFM_PCG_PARTS")) P.parts = std::max(1, std::min(std::min(64, P.C), atoi(e)));      // (tuning aid)
   P.units = P.C * P.parts;
   P.max_iter = 400;
   if (const char* e = getenv("SFM_PCG_MAX_ITER")) P.max_iter = std::max(1, atoi(e));      // (tests: 1 forces the fallback path)
