@@ -346,7 +346,8 @@ __global__ void __launch_bounds__(FusedWarps<CAP>::N * 32) ba_schur_kernel(const
                                                                     const double* __restrict__ pts, Intr K,
                                                                     double lambda, float* __restrict__ S, int ld,
                                                                     float* __restrict__ g, float* __restrict__ hdiag,
-                                                                    double* __restrict__ cost) {
+                                                                    double* __restrict__ cost, float* __restrict__ Tbuf,
+                                                                    double* __restrict__ qp) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int WARPS = FusedWarps<CAP>::N;
   WarpPoint<CAP>* wps = reinterpret_cast<WarpPoint<CAP>*>(smem_raw);
@@ -377,6 +378,11 @@ __global__ void __launch_bounds__(FusedWarps<CAP>::N * 32) ba_schur_kernel(const
     double hpp[6], bp[3], hinv[6];
     point_accumulate(wp, lane, o_begin, nobs, uv, cam_idx, cams, X, K, true, S, ld, g, hdiag, hpp, bp, &cost_local);
     inv_sym3(hpp, lambda, hinv);
+    if (qp && lane == 0) {
+      qp[3 * (size_t)p] = -(hinv[0] * bp[0] + hinv[1] * bp[1] + hinv[2] * bp[2]);
+      qp[3 * (size_t)p + 1] = -(hinv[1] * bp[0] + hinv[3] * bp[1] + hinv[4] * bp[2]);
+      qp[3 * (size_t)p + 2] = -(hinv[2] * bp[0] + hinv[4] * bp[1] + hinv[5] * bp[2]);
+    }
     __syncwarp();
     // T_a = W_a Hinv ; g[ca] -= T_a bp
     for (int a = lane; a < nobs; a += 32) {
@@ -390,6 +396,11 @@ __global__ void __launch_bounds__(FusedWarps<CAP>::N * 32) ba_schur_kernel(const
       }
 #pragma unroll
       for (int k = 0; k < 18; ++k) wp.T[a][k] = t[k];
+      if (Tbuf) {                      // kept for the back substitution: dp = -Hinv bp - sum_a T_a^T dc[cam_a]
+        float2* dst = reinterpret_cast<float2*>(Tbuf + 18 * (size_t)(o_begin + a));
+#pragma unroll
+        for (int k = 0; k < 9; ++k) dst[k] = make_float2(t[2 * k], t[2 * k + 1]);
+      }
       float gc[6];
 #pragma unroll
       for (int i = 0; i < 6; ++i) gc[i] = wp.gc[a][i] - (float)(t[3 * i] * bp[0] + t[3 * i + 1] * bp[1] + t[3 * i + 2] * bp[2]);
@@ -510,6 +521,50 @@ __global__ void __launch_bounds__(FusedWarps<CAP>::N * 32) ba_update_points_kern
   if (lane == 0 && step2 && step_local != 0.0) atomicAdd(step2, step_local);
 }
 
+// The same back substitution from what the Schur kernel left behind: T_a = W_a Hpp^-1 of every observation (18 float32)
+// and q_p = -Hpp^-1 bp of every point, so that dp = q_p - sum_a T_a^T dc[cam_a] is a stream over 72 bytes per observation
+// (one thread per point: its observations are contiguous) instead of a second evaluation of the geometry and its
+// Jacobians.  dc (6 C doubles) in shared memory.
+__global__ void __launch_bounds__(256) ba_update_points_lin_kernel(const int* __restrict__ cam_idx, const int* __restrict__ pt_start,
+                                                                   int n_pt, const float* __restrict__ Tbuf,
+                                                                   const double* __restrict__ qp, const double* __restrict__ pts,
+                                                                   const double* __restrict__ dc, int n_cam, int dc_in_smem,
+                                                                   double* __restrict__ pts_new, double* __restrict__ step2) {
+  extern __shared__ __align__(16) double s_dc[];
+  if (dc_in_smem) {
+    for (int i = threadIdx.x; i < 6 * n_cam; i += blockDim.x) s_dc[i] = dc[i];
+    __syncthreads();
+  }
+  const double* dcs = dc_in_smem ? s_dc : dc;
+  double local = 0.0;
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n_pt; p += gridDim.x * blockDim.x) {
+    const int o0 = __ldg(pt_start + p), o1 = __ldg(pt_start + p + 1);
+    const double X0 = __ldg(pts + 3 * (size_t)p), X1 = __ldg(pts + 3 * (size_t)p + 1), X2 = __ldg(pts + 3 * (size_t)p + 2);
+    if (o1 <= o0) {
+      pts_new[3 * (size_t)p] = X0; pts_new[3 * (size_t)p + 1] = X1; pts_new[3 * (size_t)p + 2] = X2;
+      continue;
+    }
+    double v0 = qp[3 * (size_t)p], v1 = qp[3 * (size_t)p + 1], v2 = qp[3 * (size_t)p + 2];
+    for (int o = o0; o < o1; ++o) {
+      const float2* T2 = reinterpret_cast<const float2*>(Tbuf + 18 * (size_t)o);
+      const double* d = dcs + 6 * __ldg(cam_idx + o);
+      float t[18];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) { const float2 q = __ldg(T2 + k); t[2 * k] = q.x; t[2 * k + 1] = q.y; }
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        v0 -= (double)t[3 * i] * d[i];
+        v1 -= (double)t[3 * i + 1] * d[i];
+        v2 -= (double)t[3 * i + 2] * d[i];
+      }
+    }
+    pts_new[3 * (size_t)p] = X0 + v0; pts_new[3 * (size_t)p + 1] = X1 + v1; pts_new[3 * (size_t)p + 2] = X2 + v2;
+    local += v0 * v0 + v1 * v1 + v2 * v2;
+  }
+  local = warp_sum_d(local);
+  if ((threadIdx.x & 31) == 0 && step2 && local != 0.0) atomicAdd(step2, local);
+}
+
 __global__ void ba_update_cams_kernel(const double* __restrict__ cams, const double* __restrict__ dc, int n,
                                       double* __restrict__ cams_new, double* __restrict__ step2) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -618,7 +673,7 @@ int launch_schur(sfm_ba* ba, double lambda) {
     }
     SFM_LAUNCH(ctx, SFM_K_BA_SCHUR, (ba_schur_kernel<true, CAP><<<grid, WARPS * 32, wp_bytes + smem_cams, ctx->stream>>>(
                                         ba->uv, ba->cam_idx, ba->pt_start, ba->n_pt, ba->cam_pre, ba->n_cam, ba->pts,
-                                        make_intr(ba), lambda, ba->S, n, ba->g, ba->hdiag, ba->scal + 0)));
+                                        make_intr(ba), lambda, ba->S, n, ba->g, ba->hdiag, ba->scal + 0, ba->Tbuf, ba->qp)));
   } else {
     static bool attr = false;
     if (!attr) {
@@ -627,7 +682,7 @@ int launch_schur(sfm_ba* ba, double lambda) {
     }
     SFM_LAUNCH(ctx, SFM_K_BA_SCHUR, (ba_schur_kernel<false, CAP><<<grid, WARPS * 32, wp_bytes, ctx->stream>>>(
                                         ba->uv, ba->cam_idx, ba->pt_start, ba->n_pt, ba->cam_pre, ba->n_cam, ba->pts,
-                                        make_intr(ba), lambda, ba->S, n, ba->g, ba->hdiag, ba->scal + 0)));
+                                        make_intr(ba), lambda, ba->S, n, ba->g, ba->hdiag, ba->scal + 0, ba->Tbuf, ba->qp)));
   }
   return SFM_OK;
 }
@@ -681,6 +736,17 @@ int build_system(sfm_ba* ba, double lambda) {
 
 int update_points(sfm_ba* ba, double lambda) {
   if (ba->n_pt == 0) return SFM_OK;
+  static const bool recompute = getenv("SFM_BA_UPDATE_RECOMPUTE") != nullptr;
+  if (ba->Tbuf && ba->qp && !recompute) {
+    sfm_ctx* ctx = ba->ctx;
+    const size_t smem = sizeof(double) * 6 * (size_t)ba->n_cam;
+    const int in_smem = smem <= 48 * 1024;
+    const int grid = std::max(1, std::min(div_up(ba->n_pt, 256), ctx->sm_count * 8));
+    SFM_LAUNCH(ctx, SFM_K_BA_UPDATE, (ba_update_points_lin_kernel<<<grid, 256, in_smem ? smem : 0, ctx->stream>>>(
+                                         ba->cam_idx, ba->pt_start, ba->n_pt, ba->Tbuf, ba->qp, ba->pts, ba->dc, ba->n_cam, in_smem,
+                                         ba->pts_new, ba->scal + 2)));
+    return SFM_OK;
+  }
   if (ba->max_deg <= 16) return launch_update<16>(ba, lambda);
   return launch_update<BA_MAXO>(ba, lambda);
 }
@@ -738,6 +804,8 @@ extern "C" int sfm_ba_create(sfm_ctx* ctx, int n_cam, int n_pt, int n_obs, const
   A((void**)&ba->dc, sizeof(double) * (size_t)n);
   A((void**)&ba->scal, sizeof(double) * 8);
   A((void**)&ba->info, 4 * sizeof(int));
+  A((void**)&ba->Tbuf, sizeof(float) * 18 * (size_t)n_obs);
+  A((void**)&ba->qp, sizeof(double) * 3 * (size_t)n_pt);
   if (sfm_spd_pcg_fits(ctx, n)) A((void**)&ba->pcg, sizeof(double) * sfm_pcg_scratch_doubles(n));
   if (e != cudaSuccess) {
     sfm_set_error("sfm_ba_create: cudaMalloc failed: %s", cudaGetErrorString(e));
@@ -765,7 +833,7 @@ extern "C" void sfm_ba_destroy(sfm_ba* ba) {
   if (ba->ctx) { cudaSetDevice(ba->ctx->device); cudaStreamSynchronize(ba->ctx->stream); }
   sfm_ba_comm_destroy(ba);
   void* ptrs[] = {ba->uv, ba->cam_idx, ba->pt_idx, ba->pt_start, ba->cams, ba->cams_new, ba->pts, ba->pts_new,
-                  ba->cam_pre, ba->S, ba->A64, ba->dc, ba->scal, ba->info, ba->pcg};
+                  ba->cam_pre, ba->S, ba->A64, ba->dc, ba->scal, ba->info, ba->pcg, ba->Tbuf, ba->qp};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   delete ba;

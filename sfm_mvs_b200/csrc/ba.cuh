@@ -25,6 +25,8 @@ struct sfm_ba {
   size_t sys_count = 0;
   double* A64 = nullptr;                       // float64 copy factored in place
   double* dc = nullptr;                        // camera step (6C)
+  float* Tbuf = nullptr;                       // [O][18] T_a = W_a Hpp^-1 of the current linearisation (Schur kernel -> back substitution)
+  double* qp = nullptr;                        // [P][3] -Hpp^-1 bp of the current linearisation
   double* scal = nullptr;                      // [0] cost at linearisation, [1] cost at candidate, [2] |dp|^2, [3] |dc|^2
   int* info = nullptr;                         // solve status: [0] Cholesky info (0 = ok), [1] 1 = the CG solver produced dc, [2] its iterations
   double* pcg = nullptr;                       // scratch of the conjugate-gradient solver (pcg.cu), null when it does not apply
