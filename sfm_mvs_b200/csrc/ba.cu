@@ -16,7 +16,10 @@
 //   cams double[C][6] (rvec|tvec)   pts double[P][3]   (+ candidate copies for step rejection)
 //   cam_pre 144-byte records [C]: R (9) | t (3) float64, Jl (9 of 12) float32 — rotation matrix and the
 //                          left Jacobian of SO(3), recomputed once per linearisation by ba_cam_prep_kernel
-//   S float[6C][6C] reduced camera system (lower block triangle filled), g float[6C]
+//   S float[C (C+1) / 2][36] reduced camera system: the lower triangle of 6x6 blocks, block (a, b), b <= a, at
+//                          (a (a+1) / 2 + b) * 36, row-major inside the block; g float[6C]; hdiag float[6C] = diag(Hcc)
+//   Tbuf float[O][18], qp double[P][3]   T_a = W_a Hpp^-1 and -Hpp^-1 bp of the current linearisation: written by the
+//                          Schur kernel, streamed by the back substitution
 // Per observation:  Yr = R X,  Y = Yr + t,  (u,v) = (fx Y.x/Y.z + cx, fy Y.y/Y.z + cy)
 //   d(u,v)/dY = [[fx/z, 0, -fx Y.x/z^2], [0, fy/z, -fy Y.y/z^2]]
 //   Jc[:,0:3] = d(u,v)/dY * [ Jl e_k x Yr ]_k   (since dR/dr_k = [Jl e_k]x R),  Jc[:,3:6] = d(u,v)/dY
