@@ -417,13 +417,10 @@ class Context:
         """S x = -g for a dense symmetric positive definite S (6C x 6C, only its lower triangle is read) — the reduced
         camera system solve of an LM step on its own.  method "cholesky" (csrc/solve.cu) returns (x float64, info);
         "pcg" (csrc/pcg.cu, the LM step's default) returns (x, solved, iterations)."""
-        S = np.asarray(S)
-        n = S.shape[0]
+        from .layout import pack_lower_blocks
+        blocks = pack_lower_blocks(S)
+        n = int(np.asarray(S).shape[0])
         C = n // 6
-        if S.shape != (n, n) or n != 6 * C or C < 1:
-            raise ValueError("reduced_solve: S must be (6C, 6C)")
-        ia, ib = np.tril_indices(C)
-        blocks = np.ascontiguousarray(S.reshape(C, 6, C, 6).transpose(0, 2, 1, 3)[ia, ib], np.float32)     # (a (a+1) / 2 + b): row-major tril order
         g = np.ascontiguousarray(g, np.float32).ravel()
         x = np.empty(n)
         info = np.zeros(1, np.int32)

@@ -139,3 +139,23 @@ def test_pair_sharded_counts_are_complete_on_every_rank_gloo():
     assert sorted(res[0][1] + res[1][1]) == list(range(len(pairs))) and not set(res[0][1]) & set(res[1][1])
     for _, _, counts in res:
         assert np.array_equal(counts, want)
+
+
+def test_packed_lower_block_layout_round_trip():
+    """The reduced camera system's HBM layout (csrc/ba.cu): block (a, b), b <= a, at (a (a + 1) / 2 + b) * 36."""
+    from sfm_mvs_b200.layout import pack_lower_blocks, unpack_lower_blocks
+    rng = np.random.default_rng(0)
+    C = 7
+    B = rng.normal(size=(6 * C, 6 * C))
+    S = B @ B.T
+    blocks = pack_lower_blocks(S)
+    assert blocks.shape == (C * (C + 1) // 2, 6, 6) and blocks.dtype == np.float32
+    for a in range(C):
+        for b in range(a + 1):
+            assert np.array_equal(blocks[a * (a + 1) // 2 + b], S[6 * a:6 * a + 6, 6 * b:6 * b + 6].astype(np.float32))
+    back = unpack_lower_blocks(blocks)
+    assert np.allclose(back, S.astype(np.float32), rtol=0, atol=0)
+    low = unpack_lower_blocks(blocks, symmetric=False)
+    assert np.all(low[:6, 6:] == 0) and np.array_equal(low[6:12, :6], back[6:12, :6])
+    with pytest.raises(ValueError):
+        pack_lower_blocks(np.zeros((7, 7)))
