@@ -22,8 +22,8 @@ _ENGINE = {
     "io": ("to_ply", "save_poses", "load_poses", "load_ply", "lookup_colors"),            # sfm.py:169-201, :423
 }
 _WHERE = {name: mod for mod, names in _ENGINE.items() for name in names}
-_SUBMODULES = ("_lib", "engine", "cv2_compat", "pipeline", "ba", "io", "sharding", "synth")
-__all__ = sorted(_WHERE) + ["ba", "pipeline", "io", "sharding", "synth"]
+_SUBMODULES = ("_lib", "engine", "cv2_compat", "pipeline", "ba", "io", "layout", "sharding", "synth")
+__all__ = sorted(_WHERE) + ["ba", "pipeline", "io", "layout", "sharding", "synth"]
 
 
 def __getattr__(name):
