@@ -421,6 +421,11 @@ __global__ void __launch_bounds__(FusedWarps<CAP>::N * 32) ba_schur_kernel(const
     // Two observations of ONE camera (a != b, equal cameras) contribute both orientations to the same diagonal block.
     const int ntri = nobs * (nobs + 1) / 2;
     const int grp = lane / 9, kq = lane - 9 * grp;
+    // this lane's four elements m0 .. m0+3 of the row-major 6x6 block: rows i0 (and i0 + 1 when the run crosses a row
+    // end), columns j0, j0+1, ... mod 6 with j0 in {0, 4, 2} — even, so the four W rows it needs (3 floats each,
+    // wrapping from row 5 to row 0) are six aligned 8-byte reads
+    const int m0 = 4 * kq, i0 = m0 / 6, j0 = m0 - 6 * i0;
+    const int i1 = i0 < 5 ? i0 + 1 : i0;
     if (grp < 3) {
       for (int t0 = 0; t0 < ntri; t0 += 3) {
         const int q = t0 + grp;
@@ -443,12 +448,30 @@ __global__ void __launch_bounds__(FusedWarps<CAP>::N * 32) ba_schur_kernel(const
           for (int rep = 0; rep < reps; ++rep) {
             const float* Ta = wp.T[hi];
             const float* Wb = wp.W[lo];
+            float w[12];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+              int idx = 3 * j0 + 2 * k;
+              idx = idx >= 18 ? idx - 18 : idx;
+              const float2 t2 = *reinterpret_cast<const float2*>(Wb + idx);
+              w[2 * k] = t2.x; w[2 * k + 1] = t2.y;
+            }
+            const float ta0 = Ta[3 * i0], ta1 = Ta[3 * i0 + 1], ta2 = Ta[3 * i0 + 2];
+            const float tb0 = Ta[3 * i1], tb1 = Ta[3 * i1 + 1], tb2 = Ta[3 * i1 + 2];
             float v[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              const int m = 4 * kq + e, i = m / 6, j = m - 6 * i;
-              v[e] = -(Ta[3 * i] * Wb[3 * j] + Ta[3 * i + 1] * Wb[3 * j + 1] + Ta[3 * i + 2] * Wb[3 * j + 2]);
-              if (a == b) v[e] += wp.J[a][i] * wp.J[a][j] + wp.J[a][6 + i] * wp.J[a][6 + j];      // + Hcc of the observation
+              const bool nxt = j0 + e >= 6;                   // this element lies in row i0 + 1
+              const float x0 = nxt ? tb0 : ta0, x1 = nxt ? tb1 : ta1, x2 = nxt ? tb2 : ta2;
+              v[e] = -(x0 * w[3 * e] + x1 * w[3 * e + 1] + x2 * w[3 * e + 2]);
+            }
+            if (a == b) {                                       // + Hcc = Jc^T Jc of the observation
+              const float* Ja = wp.J[a];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int m = m0 + e, i = m / 6, j = m - 6 * i;
+                v[e] += Ja[i] * Ja[j] + Ja[6 + i] * Ja[6 + j];
+              }
             }
             red_add_v4(Sd, v[0], v[1], v[2], v[3]);
             const int tmp = hi; hi = lo; lo = tmp;

@@ -312,7 +312,8 @@ __global__ void __launch_bounds__(96, 1) pnp_epnp_kernel(const float* __restrict
     asm volatile("barrier.sync 0;" ::: "memory");
     int c = 0;
     if (s_ok) {
-      for (int i = tid; i < n; i += 96) {
+#pragma unroll 4
+      for (int i = tid; i < n; i += 96) {        // (unrolled: four points' division chains in flight per thread)
         const float2 o = __ldg(reinterpret_cast<const float2*>(px) + i);
         c += is_inlier(s_pose, cam, __ldg(X + 3 * (size_t)i), __ldg(X + 3 * (size_t)i + 1), __ldg(X + 3 * (size_t)i + 2), o.x, o.y, thr2) ? 1 : 0;
       }
