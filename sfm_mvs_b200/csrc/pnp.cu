@@ -361,13 +361,6 @@ __device__ __forceinline__ uint32_t pnp_cluster_rank() {
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
   return r;
 }
-__device__ __forceinline__ double pnp_ld_dsmem(const double* p, uint32_t rank) {
-  uint32_t a = (uint32_t)__cvta_generic_to_shared(p), ra;
-  double v;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(rank));
-  asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(ra) : "memory");
-  return v;
-}
 
 __device__ __forceinline__ void pnp_st_dsmem(double* p, uint32_t rank, double v) {
   uint32_t a = (uint32_t)__cvta_generic_to_shared(p), ra;
