@@ -187,7 +187,9 @@ __global__ void __launch_bounds__(PCG_THREADS, 1) spd_pcg_kernel(PcgPlan P) {
   else if (bb == 0.0) state = 1;
   int it = 0;
   bool verifying = false;
-  const int gw = blockIdx.x * PCG_WARPS + warp, total_warps = gridDim.x * PCG_WARPS;
+  // units are dealt round-robin over the CTAs (unit u -> CTA u mod grid): 1000 units on 148 SMs are 6 or 7 per SM, where
+  // filling the CTAs one after the other gave 125 SMs eight units each and left 23 idle
+  const int gw = warp * gridDim.x + blockIdx.x, total_warps = gridDim.x * PCG_WARPS;
   const bool tl = P.stamps && blockIdx.x == 0 && tid == 0;
   long long t_mv = 0, t_bar = 0, t_vec = 0, t_v1 = 0, t_v2 = 0, t_v3 = 0, t0 = tl ? clock64() : 0, t1 = 0;
   while (state == 0 && (it < P.max_iter || verifying)) {
