@@ -29,7 +29,7 @@ namespace {
 
 constexpr int PCG_THREADS = 256;
 constexpr int PCG_WARPS = PCG_THREADS / 32;
-constexpr int PCG_KMAX = 14;              // elements per thread of a vector: n <= 256 * 14 (the shared-memory limit is ~3200)
+constexpr int PCG_NB = 3;                 // block rows of the vectors a thread owns: C <= 256 * 3
 
 struct PcgPlan {
   int n, C, parts, units, max_iter;
@@ -38,7 +38,7 @@ struct PcgPlan {
   const float* g;
   double* x;
   double* partial;              // [2][units][6]
-  unsigned int* bar;            // [0] arrivals, [1] generation
+  unsigned int* bar;            // [0] arrivals, [1] barriers completed
   int* status;                  // 1: x holds the solution; 0: not solved
   int* info;                    // the LM step's solve_info word: zeroed on success
   int* iters;
@@ -54,34 +54,51 @@ __device__ __forceinline__ void st_release_u32(unsigned int* p, unsigned int v) 
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// every CTA of the (co-resident) grid; `gen` is thread 0's copy of the generation word
-__device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int& gen) {
+// Every CTA of the (co-resident) grid: one arrival counter (bar[0]) and one generation word (bar[1]) that thread 0
+// polls; both are monotonic within a launch (zeroed before it), nothing is reset.  (Measured against per-CTA flag words
+// that every CTA polls — no atomics, but 148 CTAs polling five lines: 11.0 k cycles per barrier against 4.7 k.)
+__device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int gen) {
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
     const unsigned int prev = atomicAdd(&bar[0], 1u);
-    if (prev == gridDim.x - 1) {
-      bar[0] = 0;
-      st_release_u32(&bar[1], gen + 1);
-    } else {
-      while (ld_acquire_u32(&bar[1]) == gen) {}
-    }
-    gen += 1;
+    if (prev == gen * gridDim.x - 1) st_release_u32(&bar[1], gen);
+    else
+      while (ld_acquire_u32(&bar[1]) < gen) {}
   }
   __syncthreads();
 }
 
-// the same value in every thread, fixed summation order
-__device__ __forceinline__ double block_sum(double v, double* red) {
+// the same value in every thread, fixed summation order; `red` (PCG_WARPS doubles per value) must not be in use by an
+// earlier call that some warp has not left yet: the call sites alternate between disjoint areas
+__device__ __forceinline__ double block_sum1(double v, double* red) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  __syncthreads();                                   // red is free again
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
   __syncthreads();
   double s = 0.0;
 #pragma unroll
   for (int w = 0; w < PCG_WARPS; ++w) s += red[w];
   return s;
+}
+__device__ __forceinline__ void block_sum2(double v0, double v1, double* red /*2 PCG_WARPS*/, double& s0, double& s1) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    v0 += __shfl_xor_sync(0xffffffffu, v0, o);
+    v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    red[threadIdx.x >> 5] = v0;
+    red[PCG_WARPS + (threadIdx.x >> 5)] = v1;
+  }
+  __syncthreads();
+  s0 = 0.0;
+  s1 = 0.0;
+#pragma unroll
+  for (int w = 0; w < PCG_WARPS; ++w) {
+    s0 += red[w];
+    s1 += red[PCG_WARPS + w];
+  }
 }
 
 __device__ __forceinline__ int tri(int i, int j) { return i * (i + 1) / 2 + j; }   // j <= i
@@ -130,206 +147,355 @@ __device__ inline bool invert_block6(const float* __restrict__ blk, double* __re
   return ok;
 }
 
+// the lanes of a warp over one 6 x 6 float32 block: lane = 9 * slot + c reads the c-th 16-byte piece of the block in
+// `slot` (three blocks per step, lanes 27 .. 31 idle), so a step of the row part is ONE contiguous 432-byte request —
+// with a lane per block the same bytes were 32 pieces 144 bytes apart, and the product was bound by the ~16 k cache
+// wavefronts of an iteration, not by L2 (measured 14.3 k cycles).  Piece c holds the flat elements 4c .. 4c + 3 of the
+// row-major block: two of row ilo (columns j0, j0 + 1) and two of row ihi (columns j2, j2 + 1), ihi = ilo or ilo + 1.
+struct LaneMap {
+  bool act;
+  int slot, c, ilo, ihi, j0, j2;
+};
+__device__ __forceinline__ LaneMap lane_map(int lane) {
+  LaneMap m;
+  m.act = lane < 27;
+  m.slot = m.act ? lane / 9 : 0;
+  m.c = m.act ? lane - 9 * m.slot : 0;
+  const int e0 = 4 * m.c;
+  m.ilo = e0 / 6;
+  m.ihi = (e0 + 3) / 6;
+  m.j0 = e0 - 6 * m.ilo;
+  m.j2 = (m.j0 + 2) % 6;
+  return m;
+}
+
+constexpr int PCG_BATCH = 8;              // 16-byte loads of a lane in flight
+
+__device__ __forceinline__ double2 lds2(const double* p) { return *reinterpret_cast<const double2*>(p); }
+
+// y_a restricted to the column blocks [b0, b1) of block row a, in every lane (fixed summation order).  Full batches
+// carry no predicates (the idle lanes 27 .. 31 repeat lanes 0 .. 4 and are discarded at the end), so the PCG_BATCH
+// loads of a lane are issued back to back; the ragged end of a range is one batch with clamped addresses and zeroed values.
+__device__ __forceinline__ void row_times_p(const float* __restrict__ S, const double* __restrict__ ps, int a, int b0, int b1,
+                                            const LaneMap& m, double* __restrict__ y /*6*/) {
+  const float4* S4 = reinterpret_cast<const float4*>(S);
+  double lo = 0.0, hi = 0.0, t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
+  // ---- stored blocks (a, b), b < a: contiguous in memory; y_a += B p_b
+  {
+    const int l0 = b0, nL = min(b1, a) - b0;
+    const float4* rowq = S4 + ((size_t)a * (a + 1) / 2 + l0 + m.slot) * 9 + m.c;
+    const double* pq = ps + 6 * (l0 + m.slot);
+    int s0 = 0;
+    for (; s0 + 3 * PCG_BATCH <= nL; s0 += 3 * PCG_BATCH) {
+      float4 v[PCG_BATCH];
+#pragma unroll
+      for (int u = 0; u < PCG_BATCH; ++u) v[u] = __ldg(rowq + (long long)(s0 + 3 * u) * 9);
+#pragma unroll
+      for (int u = 0; u < PCG_BATCH; ++u) {
+        const double* pb_ = pq + 6 * (s0 + 3 * u);
+        const double2 pa = lds2(pb_ + m.j0), pb = lds2(pb_ + m.j2);
+        lo += (double)v[u].x * pa.x + (double)v[u].y * pa.y;
+        hi += (double)v[u].z * pb.x + (double)v[u].w * pb.y;
+      }
+    }
+    if (s0 < nL) {
+      float4 v[PCG_BATCH];
+#pragma unroll
+      for (int u = 0; u < PCG_BATCH; ++u) {
+        const int bi = s0 + 3 * u + m.slot;
+        v[u] = __ldg(rowq + (long long)(min(bi, nL - 1) - m.slot) * 9);
+        if (bi >= nL) v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < PCG_BATCH; ++u) {
+        const double* pb_ = pq + 6 * (min(s0 + 3 * u + m.slot, nL - 1) - m.slot);
+        const double2 pa = lds2(pb_ + m.j0), pb = lds2(pb_ + m.j2);
+        lo += (double)v[u].x * pa.x + (double)v[u].y * pa.y;
+        hi += (double)v[u].z * pb.x + (double)v[u].w * pb.y;
+      }
+    }
+  }
+  // ---- stored blocks (b, a), b > a: one 144-byte block per slot; y_a += B^T p_b
+  {
+    const int l0 = max(b0, a + 1), nT = b1 - l0;
+    const float4* colq = S4 + (size_t)a * 9 + m.c;
+    int s0 = 0;
+    for (; s0 + 3 * PCG_BATCH <= nT; s0 += 3 * PCG_BATCH) {
+      float4 v[PCG_BATCH];
+#pragma unroll
+      for (int u = 0; u < PCG_BATCH; ++u) {
+        const size_t b = (size_t)(l0 + s0 + 3 * u + m.slot);
+        v[u] = __ldg(colq + (b * (b + 1) / 2) * 9);
+      }
+#pragma unroll
+      for (int u = 0; u < PCG_BATCH; ++u) {
+        const double* pb_ = ps + 6 * (l0 + s0 + 3 * u + m.slot);
+        const double pl = pb_[m.ilo], ph = pb_[m.ihi];
+        t0 += (double)v[u].x * pl;
+        t1 += (double)v[u].y * pl;
+        t2 += (double)v[u].z * ph;
+        t3 += (double)v[u].w * ph;
+      }
+    }
+    if (s0 < nT) {
+      float4 v[PCG_BATCH];
+#pragma unroll
+      for (int u = 0; u < PCG_BATCH; ++u) {
+        const int bi = s0 + 3 * u + m.slot;
+        const size_t b = (size_t)(l0 + min(bi, nT - 1));
+        v[u] = __ldg(colq + (b * (b + 1) / 2) * 9);
+        if (bi >= nT) v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < PCG_BATCH; ++u) {
+        const double* pb_ = ps + 6 * (l0 + min(s0 + 3 * u + m.slot, nT - 1));
+        const double pl = pb_[m.ilo], ph = pb_[m.ihi];
+        t0 += (double)v[u].x * pl;
+        t1 += (double)v[u].y * pl;
+        t2 += (double)v[u].z * ph;
+        t3 += (double)v[u].w * ph;
+      }
+    }
+  }
+  // ---- the diagonal block through its lower triangle: element (i, j), j <= i, serves row i, and column j when j < i
+  if (b0 <= a && a < b1) {
+    float4 v = __ldg(S4 + ((size_t)a * (a + 1) / 2 + a) * 9 + m.c);
+    if (m.slot != 0) v = make_float4(0.f, 0.f, 0.f, 0.f);
+    const double* pa = ps + 6 * a;
+    const double pl = pa[m.ilo], ph = pa[m.ihi];
+    const double2 q0 = lds2(pa + m.j0), q2 = lds2(pa + m.j2);
+    const double vx = v.x, vy = v.y, vz = v.z, vw = v.w;
+    lo += (m.j0 <= m.ilo ? vx : 0.0) * q0.x + (m.j0 + 1 <= m.ilo ? vy : 0.0) * q0.y;
+    hi += (m.j2 <= m.ihi ? vz : 0.0) * q2.x + (m.j2 + 1 <= m.ihi ? vw : 0.0) * q2.y;
+    t0 += (m.j0 < m.ilo ? vx : 0.0) * pl;
+    t1 += (m.j0 + 1 < m.ilo ? vy : 0.0) * pl;
+    t2 += (m.j2 < m.ihi ? vz : 0.0) * ph;
+    t3 += (m.j2 + 1 < m.ihi ? vw : 0.0) * ph;
+  }
+  if (!m.act) lo = hi = t0 = t1 = t2 = t3 = 0.0;
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    double v = (m.ilo == j ? lo : 0.0) + (m.ihi == j ? hi : 0.0) + (m.j0 == j ? t0 : 0.0) + (m.j0 + 1 == j ? t1 : 0.0) +
+               (m.j2 == j ? t2 : 0.0) + (m.j2 + 1 == j ? t3 : 0.0);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    y[j] = v;
+  }
+}
+
+// z = M^-1 r for one block (M^-1 as its lower triangle in shared memory); returns r . z
+__device__ __forceinline__ double precondition6(const double* __restrict__ M, const double* r, double* z) {
+  double rz = 0.0;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    double v = 0.0;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) v += M[j <= i ? tri(i, j) : tri(j, i)] * r[j];
+    z[i] = v;
+    rz += r[i] * v;
+  }
+  return rz;
+}
+
 __global__ void __launch_bounds__(PCG_THREADS, 1) spd_pcg_kernel(PcgPlan P) {
   extern __shared__ __align__(16) double sm[];
   const int n = P.n, C = P.C, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  double* xs = sm;                 // the four vectors, identical in every CTA
-  double* rs = xs + n;
-  double* ps = rs + n;
-  double* ws = ps + n;             // S p, then z = M^-1 r
-  double* Ms = ws + n;             // 21 C: inverses of the diagonal blocks, lower triangles
-  double* red = Ms + 21 * (size_t)C;
+  double* xs = sm;                 // x and p, identical in every CTA (p is what the product reads)
+  double* ps = xs + n;
+  double* Ms = ps + n;             // 21 C: inverses of the diagonal blocks, lower triangles
+  double* red = Ms + 21 * (size_t)C;      // three reduction areas
   __shared__ int s_fail;
-  unsigned int gen = 0;
-  if (tid == 0) {
-    gen = ld_acquire_u32(&P.bar[1]);
-    s_fail = 0;
-  }
+  if (tid == 0) s_fail = 0;
   __syncthreads();
+  // A thread OWNS the block rows a = tid + 256 k (k < PCG_NB) of every vector, in every CTA alike: its residual stays
+  // in registers, x and p in its own shared-memory slots, and the updates need no index arithmetic and no barrier
+  // other than the one that publishes p.
+  double r[PCG_NB][6], z[PCG_NB][6];
+  double bb_l = 0.0, rz_l = 0.0;
   // ---- preconditioner and start: x = 0, r = b = -g, z = M^-1 r, p = z
   for (int a = tid; a < C; a += PCG_THREADS) {
     const float* blk = P.S + ((size_t)a * (a + 1) / 2 + a) * 36;
     float b36[36];
 #pragma unroll
-    for (int k = 0; k < 9; ++k) {
-      const float4 q = __ldg(reinterpret_cast<const float4*>(blk) + k);
-      b36[4 * k] = q.x; b36[4 * k + 1] = q.y; b36[4 * k + 2] = q.z; b36[4 * k + 3] = q.w;
+    for (int q4 = 0; q4 < 9; ++q4) {
+      const float4 q = __ldg(reinterpret_cast<const float4*>(blk) + q4);
+      b36[4 * q4] = q.x; b36[4 * q4 + 1] = q.y; b36[4 * q4 + 2] = q.z; b36[4 * q4 + 3] = q.w;
     }
     double M[21];
     if (!invert_block6(b36, M)) s_fail = 1;
 #pragma unroll
-    for (int k = 0; k < 21; ++k) Ms[21 * (size_t)a + k] = M[k];
+    for (int q = 0; q < 21; ++q) Ms[21 * (size_t)a + q] = M[q];
   }
-  for (int i = tid; i < n; i += PCG_THREADS) {
-    xs[i] = 0.0;
-    rs[i] = -(double)P.g[i];
-  }
-  __syncthreads();
-  double bb_l = 0.0, rz_l = 0.0;
-  for (int i = tid; i < n; i += PCG_THREADS) bb_l += rs[i] * rs[i];
-  for (int a = tid; a < C; a += PCG_THREADS) {
-    const double* M = Ms + 21 * (size_t)a;
-    const double* r = rs + 6 * a;
 #pragma unroll
-    for (int i = 0; i < 6; ++i) {
-      double v = 0.0;
+  for (int k = 0; k < PCG_NB; ++k) {
+    const int a = tid + PCG_THREADS * k;
+    if (a < C) {
 #pragma unroll
-      for (int j = 0; j < 6; ++j) v += M[j <= i ? tri(i, j) : tri(j, i)] * r[j];
-      ws[6 * a + i] = v;
-      ps[6 * a + i] = v;
-      rz_l += r[i] * v;
+      for (int i = 0; i < 6; ++i) {
+        r[k][i] = -(double)P.g[6 * a + i];
+        bb_l += r[k][i] * r[k][i];
+        xs[6 * a + i] = 0.0;
+      }
+      rz_l += precondition6(Ms + 21 * (size_t)a, r[k], z[k]);      // (this thread's own blocks: no barrier needed)
+#pragma unroll
+      for (int i = 0; i < 6; ++i) ps[6 * a + i] = z[k][i];
+    } else {
+#pragma unroll
+      for (int i = 0; i < 6; ++i) r[k][i] = z[k][i] = 0.0;
     }
   }
-  const double bb = block_sum(bb_l, red);
-  double rz = block_sum(rz_l, red);
+  double bb, rz;
+  block_sum2(bb_l, rz_l, red + PCG_WARPS, bb, rz);           // (its barriers publish p and s_fail)
   int state = 0;                   // 0 running, 1 converged, 2 failed
   if (s_fail || !isfinite(bb) || !isfinite(rz)) state = 2;
   else if (bb == 0.0) state = 1;
   int it = 0;
+  unsigned int gen = 0;            // grid barriers passed
   bool verifying = false;
-  // units are dealt round-robin over the CTAs (unit u -> CTA u mod grid): 1000 units on 148 SMs are 6 or 7 per SM, where
-  // filling the CTAs one after the other gave 125 SMs eight units each and left 23 idle
+  // units are dealt round-robin over the CTAs (unit u -> CTA u mod grid): 1000 units on 148 SMs are 6 or 7 per SM
   const int gw = warp * gridDim.x + blockIdx.x, total_warps = gridDim.x * PCG_WARPS;
-  const bool tl = P.stamps && blockIdx.x == 0 && tid == 0;
-  long long t_mv = 0, t_bar = 0, t_vec = 0, t_v1 = 0, t_v2 = 0, t_v3 = 0, t0 = tl ? clock64() : 0, t1 = 0;
+  const LaneMap lm = lane_map(lane);
+  const bool tl = P.stamps && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1) && tid == 0;
+  long long t_mv = 0, t_bar = 0, t_vec = 0, t_v1 = 0, t0 = tl ? clock64() : 0;
   while (state == 0 && (it < P.max_iter || verifying)) {
     // ---- S p: one unit per warp
-    double* part = P.partial + (size_t)(it & 1) * P.units * 6;
+    double* part = P.partial + (size_t)(gen & 1) * P.units * 6;
     for (int u = gw; u < P.units; u += total_warps) {
       const int a = u / P.parts, pi = u - a * P.parts;
       const int b0 = (int)((long long)C * pi / P.parts), b1 = (int)((long long)C * (pi + 1) / P.parts);
-      double acc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-      for (int b = b0 + lane; b < b1; b += 32) {
-        const size_t blk = (b <= a) ? ((size_t)a * (a + 1) / 2 + b) : ((size_t)b * (b + 1) / 2 + a);
-        const float4* q = reinterpret_cast<const float4*>(P.S + blk * 36);
-        float B[36];
-#pragma unroll
-        for (int k = 0; k < 9; ++k) {
-          const float4 v = __ldg(q + k);
-          B[4 * k] = v.x; B[4 * k + 1] = v.y; B[4 * k + 2] = v.z; B[4 * k + 3] = v.w;
-        }
-        const double* pb = ps + 6 * b;
-        const double p0 = pb[0], p1 = pb[1], p2 = pb[2], p3 = pb[3], p4 = pb[4], p5 = pb[5];
-        if (b == a) {              // the diagonal block through its lower triangle
-#pragma unroll
-          for (int i = 0; i < 6; ++i) {
-            const double pv[6] = {p0, p1, p2, p3, p4, p5};
-            double v = 0.0;
-#pragma unroll
-            for (int j = 0; j < 6; ++j) v += (double)(j <= i ? B[6 * i + j] : B[6 * j + i]) * pv[j];
-            acc[i] += v;
-          }
-        } else if (b < a) {
-#pragma unroll
-          for (int i = 0; i < 6; ++i)
-            acc[i] += (double)B[6 * i] * p0 + (double)B[6 * i + 1] * p1 + (double)B[6 * i + 2] * p2 + (double)B[6 * i + 3] * p3 +
-                      (double)B[6 * i + 4] * p4 + (double)B[6 * i + 5] * p5;
-        } else {
-#pragma unroll
-          for (int i = 0; i < 6; ++i)
-            acc[i] += (double)B[i] * p0 + (double)B[6 + i] * p1 + (double)B[12 + i] * p2 + (double)B[18 + i] * p3 +
-                      (double)B[24 + i] * p4 + (double)B[30 + i] * p5;
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < 6; ++i) {
-        double v = acc[i];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        acc[i] = v;
-      }
+      double y[6];
+      row_times_p(P.S, ps, a, b0, b1, lm, y);
       if (lane < 6) {
-        const double v = lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : lane == 3 ? acc[3] : lane == 4 ? acc[4] : acc[5];
+        const double v = lane == 0 ? y[0] : lane == 1 ? y[1] : lane == 2 ? y[2] : lane == 3 ? y[3] : lane == 4 ? y[4] : y[5];
         part[(size_t)u * 6 + lane] = v;
       }
     }
     if (tl) { const long long t = clock64(); t_mv += t - t0; t0 = t; }
-    grid_barrier(P.bar, gen);
+    grid_barrier(P.bar, ++gen);
     if (tl) { const long long t = clock64(); t_bar += t - t0; t0 = t; }
-    // ---- the vector part, replicated: w = S p (from the partial sums), alpha, x, r, z, beta, p
-    double pw_l = 0.0;
-    {
-      // a thread's elements i = tid + 256 k together: their loads of the partial sums are all in flight at once
-      double v[PCG_KMAX];
+    // ---- the vector part, replicated: w = S p (from the partial sums) for the rows this thread owns
+    double w[PCG_NB][6];
 #pragma unroll
-      for (int k = 0; k < PCG_KMAX; ++k) v[k] = 0.0;
-#pragma unroll 4
-      for (int pi = 0; pi < P.parts; ++pi) {
+    for (int k = 0; k < PCG_NB; ++k) {
 #pragma unroll
-        for (int k = 0; k < PCG_KMAX; ++k) {
-          const int i = tid + PCG_THREADS * k;
-          if (i < n) {
-            const int a = i / 6, c = i - 6 * a;
-            v[k] += __ldcg(part + ((size_t)a * P.parts + pi) * 6 + c);
+      for (int i = 0; i < 6; ++i) w[k][i] = 0.0;
+    }
+    if (P.parts == 2) {            // (the 500-camera case: all loads of a thread in flight at once)
+      double2 q[PCG_NB][6];
+#pragma unroll
+      for (int k = 0; k < PCG_NB; ++k) {
+        const int a = tid + PCG_THREADS * k;
+        const double2* src = reinterpret_cast<const double2*>(part + (size_t)(a < C ? a : 0) * 12);
+#pragma unroll
+        for (int h = 0; h < 6; ++h) q[k][h] = a < C ? __ldcg(src + h) : make_double2(0.0, 0.0);
+      }
+#pragma unroll
+      for (int k = 0; k < PCG_NB; ++k) {
+#pragma unroll
+        for (int h = 0; h < 3; ++h) {
+          w[k][2 * h] = q[k][h].x + q[k][3 + h].x;
+          w[k][2 * h + 1] = q[k][h].y + q[k][3 + h].y;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < PCG_NB; ++k) {
+        const int a = tid + PCG_THREADS * k;
+        if (a < C) {
+          for (int pi = 0; pi < P.parts; ++pi) {
+            const double2* src = reinterpret_cast<const double2*>(part + ((size_t)a * P.parts + pi) * 6);
+#pragma unroll
+            for (int h = 0; h < 3; ++h) {
+              const double2 v = __ldcg(src + h);
+              w[k][2 * h] += v.x;
+              w[k][2 * h + 1] += v.y;
+            }
           }
         }
       }
-#pragma unroll
-      for (int k = 0; k < PCG_KMAX; ++k) {
-        const int i = tid + PCG_THREADS * k;
-        if (i < n) {
-          ws[i] = v[k];
-          pw_l += ps[i] * v[k];
-        }
-      }
     }
-    if (tl) { t1 = clock64(); t_v1 += t1 - t0; }
+    if (tl) { const long long t = clock64(); t_v1 += t - t0; }
     if (verifying) {
       // p held x: w = S x.  The recursively updated residual has converged; the TRUE residual b - S x decides — on a
       // numerically singular system (lambda ~ 1e-7 on float32 data) the two part ways and x is not a solution.
       double tr_l = 0.0;
-      for (int i = tid; i < n; i += PCG_THREADS) {
-        const double d = -(double)P.g[i] - ws[i];
-        tr_l += d * d;
+#pragma unroll
+      for (int k = 0; k < PCG_NB; ++k) {
+        const int a = tid + PCG_THREADS * k;
+        if (a < C) {
+#pragma unroll
+          for (int i = 0; i < 6; ++i) {
+            const double d = -(double)P.g[6 * a + i] - w[k][i];
+            tr_l += d * d;
+          }
+        }
       }
-      const double tr = block_sum(tr_l, red);
+      double tr, unused;
+      block_sum2(tr_l, 0.0, red + PCG_WARPS, tr, unused);
       state = (isfinite(tr) && tr <= 1e4 * P.tol2 * bb) ? 1 : 2;       // within 100 x the tolerance
       break;
     }
-    const double pw = block_sum(pw_l, red);
-    if (!(pw > 0.0) || !isfinite(pw)) { state = 2; break; }
-    const double alpha = rz / pw;
-    double rr_l = 0.0;
-    for (int i = tid; i < n; i += PCG_THREADS) {
-      xs[i] += alpha * ps[i];
-      const double r = rs[i] - alpha * ws[i];
-      rs[i] = r;
-      rr_l += r * r;
-    }
-    __syncthreads();
-    double rz_l2 = 0.0;
-    for (int a = tid; a < C; a += PCG_THREADS) {
-      const double* M = Ms + 21 * (size_t)a;
-      const double* r = rs + 6 * a;
+    double pw_l = 0.0;
 #pragma unroll
-      for (int i = 0; i < 6; ++i) {
-        double v = 0.0;
+    for (int k = 0; k < PCG_NB; ++k) {
+      const int a = tid + PCG_THREADS * k;
+      if (a < C) {
 #pragma unroll
-        for (int j = 0; j < 6; ++j) v += M[j <= i ? tri(i, j) : tri(j, i)] * r[j];
-        ws[6 * a + i] = v;
-        rz_l2 += r[i] * v;
+        for (int i = 0; i < 6; ++i) pw_l += ps[6 * a + i] * w[k][i];
       }
     }
-    if (tl) { const long long t = clock64(); t_v2 += t - t1; t1 = t; }
-    const double rr = block_sum(rr_l, red);
-    const double rz_new = block_sum(rz_l2, red);
-    if (tl) { const long long t = clock64(); t_v3 += t - t1; t1 = t; }
+    const double pw = block_sum1(pw_l, red);
+    if (!(pw > 0.0) || !isfinite(pw)) { state = 2; break; }
+    const double alpha = rz / pw;
+    double rr_l = 0.0, rz_l2 = 0.0;
+#pragma unroll
+    for (int k = 0; k < PCG_NB; ++k) {
+      const int a = tid + PCG_THREADS * k;
+      if (a < C) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+          xs[6 * a + i] += alpha * ps[6 * a + i];
+          r[k][i] -= alpha * w[k][i];
+          rr_l += r[k][i] * r[k][i];
+        }
+        rz_l2 += precondition6(Ms + 21 * (size_t)a, r[k], z[k]);
+      }
+    }
+    double rr, rz_new;
+    block_sum2(rr_l, rz_l2, red + PCG_WARPS, rr, rz_new);
     ++it;
     if (!isfinite(rr) || !isfinite(rz_new)) { state = 2; break; }
     if (rr <= P.tol2 * bb) {             // one more product, with x in the place of p
       verifying = true;
-      for (int i = tid; i < n; i += PCG_THREADS) ps[i] = xs[i];
+#pragma unroll
+      for (int k = 0; k < PCG_NB; ++k) {
+        const int a = tid + PCG_THREADS * k;
+        if (a < C) {
+#pragma unroll
+          for (int i = 0; i < 6; ++i) ps[6 * a + i] = xs[6 * a + i];
+        }
+      }
       __syncthreads();
       continue;
     }
     const double beta = rz_new / rz;
     rz = rz_new;
-    for (int i = tid; i < n; i += PCG_THREADS) ps[i] = ws[i] + beta * ps[i];
+#pragma unroll
+    for (int k = 0; k < PCG_NB; ++k) {
+      const int a = tid + PCG_THREADS * k;
+      if (a < C) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) ps[6 * a + i] = z[k][i] + beta * ps[6 * a + i];
+      }
+    }
     __syncthreads();
     if (tl) { const long long t = clock64(); t_vec += t - t0; t0 = t; }
   }
   __syncthreads();
-  if (tl) { P.stamps[0] = t_mv; P.stamps[1] = t_bar; P.stamps[2] = t_vec; P.stamps[3] = it; P.stamps[4] = t_v1; P.stamps[5] = t_v2; P.stamps[6] = t_v3; }
+  if (tl) {
+    long long* st = P.stamps + (blockIdx.x == 0 ? 0 : 5);
+    st[0] = t_mv; st[1] = t_bar; st[2] = t_vec; st[3] = it; st[4] = t_v1;
+  }
   if (blockIdx.x == 0) {
     const bool ok = state == 1;
     if (ok)
@@ -342,7 +508,7 @@ __global__ void __launch_bounds__(PCG_THREADS, 1) spd_pcg_kernel(PcgPlan P) {
   }
 }
 
-size_t pcg_smem_bytes(int n) { return sizeof(double) * ((size_t)4 * n + (size_t)21 * (n / 6) + PCG_WARPS + 2); }
+size_t pcg_smem_bytes(int n) { return sizeof(double) * ((size_t)2 * n + (size_t)21 * (n / 6) + 3 * PCG_WARPS + 2); }
 
 }  // namespace
 
@@ -353,7 +519,7 @@ size_t sfm_pcg_scratch_doubles(int n) {
 
 bool sfm_spd_pcg_fits(sfm_ctx* ctx, int n) {
   (void)ctx;
-  return n % 6 == 0 && n >= 6 && n <= PCG_THREADS * PCG_KMAX && pcg_smem_bytes(n) <= 216 * 1024;
+  return n % 6 == 0 && n >= 6 && n <= 6 * PCG_THREADS * PCG_NB && pcg_smem_bytes(n) <= 216 * 1024;
 }
 
 // Queues the solve on the context's stream.  scratch: sfm_pcg_scratch_doubles(n) doubles.  status_dev (device int):
@@ -392,12 +558,12 @@ int sfm_spd_pcg(sfm_ctx* ctx, const float* S, const float* g, int n, double* scr
   }
   SFM_LAUNCH(ctx, SFM_K_BA_SOLVE, (spd_pcg_kernel<<<grid, PCG_THREADS, smem, ctx->stream>>>(P)));
   if (P.stamps) {
-    long long h[7];
+    long long h[10];
     SFM_CUDA(cudaMemcpyAsync(h, P.stamps, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
     SFM_CUDA(cudaStreamSynchronize(ctx->stream));
     const long long k = h[3] ? h[3] : 1;
-    fprintf(stderr, "[pcg n=%d] %lld iterations: matrix-vector product %lld | grid barrier %lld | vector part %lld (partial sums %lld, first dot + x, r, z %lld, two dots %lld) cycles per iteration (CTA 0)\n",
-            n, h[3], h[0] / k, h[1] / k, h[2] / k, h[4] / k, h[5] / k, h[6] / k);
+    fprintf(stderr, "[pcg n=%d] %lld iterations: matrix-vector product %lld | grid barrier %lld | vector part %lld (partial sums %lld) cycles per iteration on CTA 0; %lld | %lld | %lld (%lld) on the last CTA\n",
+            n, h[3], h[0] / k, h[1] / k, h[2] / k, h[4] / k, h[5] / k, h[6] / k, h[7] / k, h[9] / k);
   }
   return SFM_OK;
 }
