@@ -8,14 +8,18 @@
 // S arrives as the packed lower triangle of 6x6 blocks (block (a, b), b <= a, 36 row-major float32 at (a (a+1) / 2 + b) * 36),
 // exactly what the Schur kernel wrote and the all-reduce summed; nothing is repacked.
 //
-//   matrix-vector product: unit = (block row a, one of `parts` column ranges), one unit per WARP (2C = 1000 units on 1184
-//     warps at C = 500): y_a += B_ab p_b for the stored blocks b <= a and y_a += B_ba^T p_b for b > a (every stored block is
-//     read twice per product, from L2), lanes over the column blocks, one shuffle reduction, six doubles per unit into
-//     a parity-double-buffered array — no atomics, fixed summation order.
-//   ONE grid barrier per iteration (arrive counter + generation word, acquire / release).
-//   vector part: x, r, p, z live in EVERY CTA's shared memory and every CTA performs the identical updates and the
-//     identical (fixed-tree) dot products on them — 12 elements per thread — so alpha, beta and the convergence verdict
-//     need no second barrier and no broadcast: all CTAs hold bit-identical state and leave the loop together.
+//   matrix-vector product: block rows are dealt round-robin over the CTAs (row a -> CTA a mod grid: three or four rows
+//     per SM at C = 500) and a CTA cuts each of its rows into column ranges, one (row, range) per WARP: y_a += B_ab p_b
+//     for the stored blocks b < a (contiguous in memory) and y_a += B_ba^T p_b for b > a (every stored block is read
+//     twice per product, from L2).  The lanes of a warp lie over the 16-byte pieces of three blocks per step, so a
+//     step of the row part is one contiguous 432-byte request; loads are issued eight steps deep.  One shuffle
+//     reduction per range, the ranges of a row summed in shared memory in a fixed order, S p written as ONE vector of n
+//     doubles (parity-double-buffered) — no atomics, bit-reproducible.
+//   ONE grid barrier per iteration (arrival counter + generation word, acquire / release, both monotonic).
+//   vector part: x, p and the inverted diagonal blocks live in EVERY CTA's shared memory, and every CTA performs the
+//     identical updates and the identical (fixed-tree) dot products — a thread OWNS the block rows tid, tid + 256, ..:
+//     its residual stays in registers, x and p in its own shared-memory slots — so alpha, beta and the convergence
+//     verdict need no second grid barrier and no broadcast: all CTAs hold bit-identical state and leave the loop together.
 //
 // Failure (a diagonal block or p^T S p not positive, no convergence in max_iter iterations, n too large for the
 // vectors to fit in shared memory) is reported in *status; the caller then runs the Cholesky path (sfm_spd_solve takes
@@ -32,12 +36,12 @@ constexpr int PCG_WARPS = PCG_THREADS / 32;
 constexpr int PCG_NB = 3;                 // block rows of the vectors a thread owns: C <= 256 * 3
 
 struct PcgPlan {
-  int n, C, parts, units, max_iter;
+  int n, C, max_iter;
   double tol2;                  // (relative residual)^2
   const float* S;
   const float* g;
   double* x;
-  double* partial;              // [2][units][6]
+  double* w;                    // [2][n]: S p, parity-double-buffered
   unsigned int* bar;            // [0] arrivals, [1] barriers completed
   int* status;                  // 1: x holds the solution; 0: not solved
   int* info;                    // the LM step's solve_info word: zeroed on success
@@ -149,8 +153,7 @@ __device__ inline bool invert_block6(const float* __restrict__ blk, double* __re
 
 // the lanes of a warp over one 6 x 6 float32 block: lane = 9 * slot + c reads the c-th 16-byte piece of the block in
 // `slot` (three blocks per step, lanes 27 .. 31 idle), so a step of the row part is ONE contiguous 432-byte request —
-// with a lane per block the same bytes were 32 pieces 144 bytes apart, and the product was bound by the ~16 k cache
-// wavefronts of an iteration, not by L2 (measured 14.3 k cycles).  Piece c holds the flat elements 4c .. 4c + 3 of the
+// with a lane per block the same bytes were 32 pieces 144 bytes apart (ncu: the L1 the busiest unit of the kernel).  Piece c holds the flat elements 4c .. 4c + 3 of the
 // row-major block: two of row ilo (columns j0, j0 + 1) and two of row ihi (columns j2, j2 + 1), ihi = ilo or ilo + 1.
 struct LaneMap {
   bool act;
@@ -352,66 +355,52 @@ __global__ void __launch_bounds__(PCG_THREADS, 1) spd_pcg_kernel(PcgPlan P) {
   int it = 0;
   unsigned int gen = 0;            // grid barriers passed
   bool verifying = false;
-  // units are dealt round-robin over the CTAs (unit u -> CTA u mod grid): 1000 units on 148 SMs are 6 or 7 per SM
-  const int gw = warp * gridDim.x + blockIdx.x, total_warps = gridDim.x * PCG_WARPS;
+  // Block rows are dealt round-robin over the CTAs (row a -> CTA a mod grid: three or four rows per SM at C = 500), and
+  // a CTA cuts each of its rows into `parts` column ranges, one per warp — so the ranges of a row are summed inside the
+  // CTA (shared memory, fixed order) and S p leaves as ONE vector of n doubles: every CTA reads 24 KB of it after the
+  // barrier, where per-range partial sums from all over the grid were 48 KB (and 4.4 k cycles of 148 SMs on the same lines).
+  const int grid = gridDim.x;
+  const int rows = (int)blockIdx.x < C ? (C - 1 - (int)blockIdx.x) / grid + 1 : 0;
+  const int parts = rows ? max(1, PCG_WARPS / rows) : 1;
+  __shared__ double ysm[PCG_WARPS][6];
   const LaneMap lm = lane_map(lane);
   const bool tl = P.stamps && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1) && tid == 0;
   long long t_mv = 0, t_bar = 0, t_vec = 0, t_v1 = 0, t0 = tl ? clock64() : 0;
   while (state == 0 && (it < P.max_iter || verifying)) {
-    // ---- S p: one unit per warp
-    double* part = P.partial + (size_t)(gen & 1) * P.units * 6;
-    for (int u = gw; u < P.units; u += total_warps) {
-      const int a = u / P.parts, pi = u - a * P.parts;
-      const int b0 = (int)((long long)C * pi / P.parts), b1 = (int)((long long)C * (pi + 1) / P.parts);
+    // ---- S p: one (row, column range) per warp
+    double* wout = P.w + (size_t)(gen & 1) * n;
+    if (warp < rows * parts) {
+      const int slot = warp / parts, pi = warp - slot * parts;
+      const int a = (int)blockIdx.x + slot * grid;
+      const int b0 = (int)((long long)C * pi / parts), b1 = (int)((long long)C * (pi + 1) / parts);
       double y[6];
       row_times_p(P.S, ps, a, b0, b1, lm, y);
       if (lane < 6) {
         const double v = lane == 0 ? y[0] : lane == 1 ? y[1] : lane == 2 ? y[2] : lane == 3 ? y[3] : lane == 4 ? y[4] : y[5];
-        part[(size_t)u * 6 + lane] = v;
+        ysm[warp][lane] = v;
       }
+    }
+    __syncthreads();
+    if (tid < 6 * rows) {
+      const int slot = tid / 6, i = tid - 6 * slot;
+      double v = 0.0;
+      for (int pi = 0; pi < parts; ++pi) v += ysm[slot * parts + pi][i];
+      wout[6 * ((int)blockIdx.x + slot * grid) + i] = v;
     }
     if (tl) { const long long t = clock64(); t_mv += t - t0; t0 = t; }
     grid_barrier(P.bar, ++gen);
     if (tl) { const long long t = clock64(); t_bar += t - t0; t0 = t; }
-    // ---- the vector part, replicated: w = S p (from the partial sums) for the rows this thread owns
+    // ---- the vector part, replicated: w = S p for the rows this thread owns
     double w[PCG_NB][6];
 #pragma unroll
     for (int k = 0; k < PCG_NB; ++k) {
+      const int a = tid + PCG_THREADS * k;
+      const double2* src = reinterpret_cast<const double2*>(wout + 6 * (a < C ? a : 0));
 #pragma unroll
-      for (int i = 0; i < 6; ++i) w[k][i] = 0.0;
-    }
-    if (P.parts == 2) {            // (the 500-camera case: all loads of a thread in flight at once)
-      double2 q[PCG_NB][6];
-#pragma unroll
-      for (int k = 0; k < PCG_NB; ++k) {
-        const int a = tid + PCG_THREADS * k;
-        const double2* src = reinterpret_cast<const double2*>(part + (size_t)(a < C ? a : 0) * 12);
-#pragma unroll
-        for (int h = 0; h < 6; ++h) q[k][h] = a < C ? __ldcg(src + h) : make_double2(0.0, 0.0);
-      }
-#pragma unroll
-      for (int k = 0; k < PCG_NB; ++k) {
-#pragma unroll
-        for (int h = 0; h < 3; ++h) {
-          w[k][2 * h] = q[k][h].x + q[k][3 + h].x;
-          w[k][2 * h + 1] = q[k][h].y + q[k][3 + h].y;
-        }
-      }
-    } else {
-#pragma unroll
-      for (int k = 0; k < PCG_NB; ++k) {
-        const int a = tid + PCG_THREADS * k;
-        if (a < C) {
-          for (int pi = 0; pi < P.parts; ++pi) {
-            const double2* src = reinterpret_cast<const double2*>(part + ((size_t)a * P.parts + pi) * 6);
-#pragma unroll
-            for (int h = 0; h < 3; ++h) {
-              const double2 v = __ldcg(src + h);
-              w[k][2 * h] += v.x;
-              w[k][2 * h + 1] += v.y;
-            }
-          }
-        }
+      for (int h = 0; h < 3; ++h) {
+        const double2 q = a < C ? __ldcg(src + h) : make_double2(0.0, 0.0);
+        w[k][2 * h] = q.x;
+        w[k][2 * h + 1] = q.y;
       }
     }
     if (tl) { const long long t = clock64(); t_v1 += t - t0; }
@@ -514,12 +503,13 @@ size_t pcg_smem_bytes(int n) { return sizeof(double) * ((size_t)2 * n + (size_t)
 
 size_t sfm_pcg_scratch_doubles(int n) {
   const size_t C = (size_t)n / 6;
-  return 2 * (C * 64) * 6 + 16;            // partial sums for up to 64 parts per block row, barrier words, counters
+  return 2 * C * 6 + 16;                   // S p twice (parity), barrier words, counters
 }
 
 bool sfm_spd_pcg_fits(sfm_ctx* ctx, int n) {
-  (void)ctx;
-  return n % 6 == 0 && n >= 6 && n <= 6 * PCG_THREADS * PCG_NB && pcg_smem_bytes(n) <= 216 * 1024;
+  const int C = n / 6;
+  return n % 6 == 0 && n >= 6 && C <= PCG_THREADS * PCG_NB && (C + ctx->sm_count - 1) / ctx->sm_count <= PCG_WARPS &&
+         pcg_smem_bytes(n) <= 216 * 1024;
 }
 
 // Queues the solve on the context's stream.  scratch: sfm_pcg_scratch_doubles(n) doubles.  status_dev (device int):
@@ -531,22 +521,18 @@ int sfm_spd_pcg(sfm_ctx* ctx, const float* S, const float* g, int n, double* scr
   P.n = n;
   P.C = n / 6;
   const int grid = ctx->sm_count;
-  const int total_warps = grid * PCG_WARPS;
-  P.parts = std::max(1, std::min(std::min(64, P.C), total_warps / P.C));
-  if (const char* e = getenv("SFM_PCG_PARTS")) P.parts = std::max(1, std::min(std::min(64, P.C), atoi(e)));      // (tuning aid)
-  P.units = P.C * P.parts;
   P.max_iter = 400;
   if (const char* e = getenv("SFM_PCG_MAX_ITER")) P.max_iter = std::max(1, atoi(e));      // (tests: 1 forces the fallback path)
   P.tol2 = 1e-8 * 1e-8;
   P.S = S;
   P.g = g;
   P.x = x;
-  P.partial = scratch;
-  P.bar = reinterpret_cast<unsigned int*>(scratch + 2 * (size_t)P.units * 6);
+  P.w = scratch;
+  P.bar = reinterpret_cast<unsigned int*>(scratch + 2 * (size_t)n);
   P.status = status_dev;
   P.info = info;
   P.iters = iters_dev;
-  P.stamps = getenv("SFM_PCG_TIMELINE") ? reinterpret_cast<long long*>(scratch + 2 * (size_t)P.units * 6 + 2) : nullptr;
+  P.stamps = getenv("SFM_PCG_TIMELINE") ? reinterpret_cast<long long*>(scratch + 2 * (size_t)n + 2) : nullptr;
   SFM_CUDA(cudaMemsetAsync(P.bar, 0, 2 * sizeof(unsigned int), ctx->stream));
   SFM_CUDA(cudaMemsetAsync(status_dev, 0, sizeof(int), ctx->stream));
   if (info) SFM_CUDA(cudaMemsetAsync(info, 0, sizeof(int), ctx->stream));      // (the fallback behind this solve sets it on a bad pivot)
@@ -562,7 +548,7 @@ int sfm_spd_pcg(sfm_ctx* ctx, const float* S, const float* g, int n, double* scr
     SFM_CUDA(cudaMemcpyAsync(h, P.stamps, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
     SFM_CUDA(cudaStreamSynchronize(ctx->stream));
     const long long k = h[3] ? h[3] : 1;
-    fprintf(stderr, "[pcg n=%d] %lld iterations: matrix-vector product %lld | grid barrier %lld | vector part %lld (partial sums %lld) cycles per iteration on CTA 0; %lld | %lld | %lld (%lld) on the last CTA\n",
+    fprintf(stderr, "[pcg n=%d] %lld iterations: matrix-vector product %lld | grid barrier %lld | vector part %lld (reading S p %lld) cycles per iteration on CTA 0; %lld | %lld | %lld (%lld) on the last CTA\n",
             n, h[3], h[0] / k, h[1] / k, h[2] / k, h[4] / k, h[5] / k, h[6] / k, h[7] / k, h[9] / k);
   }
   return SFM_OK;
