@@ -610,8 +610,17 @@ int solve_reduced_system(sfm_ba* ba) {
   // and two L2 round trips whatever n is
   int min_n = 600;
   if (const char* e = getenv("SFM_PCG_MIN_N")) min_n = atoi(e);
+  // An LM step is solved to a relative residual of 1e-5, not to the 1e-8 the solver reaches on its own
+  // (sfm_reduced_solve_pcg): S and g are accumulated in float32, so the system itself is only known to ~1e-6, and a
+  // damped step accepted on "the cost went down" gains nothing from digits beyond that — the iterations it saves
+  // (about a third) are the largest single item of the step.  SFM_BA_CG_TOL overrides.
+  double cg_tol = 1e-5;
+  if (const char* e = getenv("SFM_BA_CG_TOL")) {
+    const double t = atof(e);
+    if (t > 0.0 && t < 1.0) cg_tol = t;
+  }
   if (ba->pcg && !chol_only && n >= min_n) {
-    SFM_TRY(sfm_spd_pcg(ba->ctx, ba->S, ba->g, n, ba->pcg, ba->dc, ba->info + 1, ba->info, ba->info + 2));
+    SFM_TRY(sfm_spd_pcg(ba->ctx, ba->S, ba->g, n, ba->pcg, ba->dc, ba->info + 1, ba->info, ba->info + 2, cg_tol));
     return sfm_spd_solve(ba->ctx, ba->S, ba->g, n, ba->A64, ba->dc, ba->info, ba->info + 1);
   }
   return sfm_spd_solve(ba->ctx, ba->S, ba->g, n, ba->A64, ba->dc, ba->info);

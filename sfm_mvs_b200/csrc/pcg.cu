@@ -153,8 +153,9 @@ __device__ inline bool invert_block6(const float* __restrict__ blk, double* __re
 
 // the lanes of a warp over one 6 x 6 float32 block: lane = 9 * slot + c reads the c-th 16-byte piece of the block in
 // `slot` (three blocks per step, lanes 27 .. 31 idle), so a step of the row part is ONE contiguous 432-byte request —
-// with a lane per block the same bytes were 32 pieces 144 bytes apart (ncu: the L1 the busiest unit of the kernel).  Piece c holds the flat elements 4c .. 4c + 3 of the
-// row-major block: two of row ilo (columns j0, j0 + 1) and two of row ihi (columns j2, j2 + 1), ihi = ilo or ilo + 1.
+// with a lane per block the same bytes were 32 pieces 144 bytes apart (ncu: the L1 the busiest unit of the kernel).
+// Piece c holds the flat elements 4c .. 4c + 3 of the row-major block: two of row ilo (columns j0, j0 + 1) and two of
+// row ihi (columns j2, j2 + 1), ihi = ilo or ilo + 1.
 struct LaneMap {
   bool act;
   int slot, c, ilo, ihi, j0, j2;
@@ -421,7 +422,7 @@ __global__ void __launch_bounds__(PCG_THREADS, 1) spd_pcg_kernel(PcgPlan P) {
       }
       double tr, unused;
       block_sum2(tr_l, 0.0, red + PCG_WARPS, tr, unused);
-      state = (isfinite(tr) && tr <= 1e4 * P.tol2 * bb) ? 1 : 2;       // within 100 x the tolerance
+      state = (isfinite(tr) && tr <= fmin(1e4 * P.tol2, 1e-8) * bb) ? 1 : 2;       // within 100 x the tolerance, and 1e-4
       break;
     }
     double pw_l = 0.0;
@@ -513,9 +514,11 @@ bool sfm_spd_pcg_fits(sfm_ctx* ctx, int n) {
 }
 
 // Queues the solve on the context's stream.  scratch: sfm_pcg_scratch_doubles(n) doubles.  status_dev (device int):
-// 1 when x holds the solution, 0 when the caller's fallback has to run.  iters_dev: optional device int.
+// 1 when x holds the solution, 0 when the caller's fallback has to run.  iters_dev: optional device int.  rel_tol:
+// |b - S x| <= rel_tol |b| of the recursively updated residual ends the iteration (the true residual is then checked).
 int sfm_spd_pcg(sfm_ctx* ctx, const float* S, const float* g, int n, double* scratch, double* x, int* status_dev, int* info,
-                int* iters_dev) {
+                int* iters_dev, double rel_tol) {
+  SFM_REQUIRE(rel_tol > 0.0 && rel_tol < 1.0, "sfm_spd_pcg: relative tolerance %g", rel_tol);
   SFM_REQUIRE(sfm_spd_pcg_fits(ctx, n), "sfm_spd_pcg: %d unknowns do not fit the shared-memory-resident vectors", n);
   PcgPlan P;
   P.n = n;
@@ -523,7 +526,7 @@ int sfm_spd_pcg(sfm_ctx* ctx, const float* S, const float* g, int n, double* scr
   const int grid = ctx->sm_count;
   P.max_iter = 400;
   if (const char* e = getenv("SFM_PCG_MAX_ITER")) P.max_iter = std::max(1, atoi(e));      // (tests: 1 forces the fallback path)
-  P.tol2 = 1e-8 * 1e-8;
+  P.tol2 = rel_tol * rel_tol;
   P.S = S;
   P.g = g;
   P.x = x;

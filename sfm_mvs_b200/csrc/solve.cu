@@ -551,7 +551,7 @@ extern "C" int sfm_reduced_solve_pcg(sfm_ctx* ctx, const float* S_blocks, const 
   SFM_TRY(ws_alloc_t(ctx, 4, &dwords));
   SFM_CUDA(cudaMemsetAsync(dx, 0, sizeof(double) * n, ctx->stream));
   SFM_CUDA(cudaMemsetAsync(dwords, 0, 4 * sizeof(int), ctx->stream));
-  SFM_TRY(sfm_spd_pcg(ctx, dS, dg, n, scratch, dx, dwords, dwords + 1, dwords + 2));
+  SFM_TRY(sfm_spd_pcg(ctx, dS, dg, n, scratch, dx, dwords, dwords + 1, dwords + 2, 1e-8));
   int h[4];
   SFM_CUDA(cudaMemcpyAsync(x, dx, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
   SFM_CUDA(cudaMemcpyAsync(h, dwords, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));

@@ -21,4 +21,4 @@ int sfm_spd_solve(sfm_ctx* ctx, const float* S, const float* g, int n, double* A
 size_t sfm_pcg_scratch_doubles(int n);
 bool sfm_spd_pcg_fits(sfm_ctx* ctx, int n);
 int sfm_spd_pcg(sfm_ctx* ctx, const float* S, const float* g, int n, double* scratch, double* x, int* status_dev, int* info,
-                int* iters_dev);
+                int* iters_dev, double rel_tol);
