@@ -558,7 +558,9 @@ def bench_ba(args, ctx, world, rank, pk, barrier, max_over_ranks):
     ctx.set_profiling(False)
     res = {"metric": "BA GN-iters/sec", "value": iters / (ms * 1e-3), "unit": "iters/s", "ms_per_iter": ms / iters,
            "config": {"workload": f"BA {C_} cams / {P_} points / {P_ * opp} obs synthetic, LM iterations, BASELINE configs[3]",
-                      "sharding": f"points over {world} rank(s); NCCL all-reduce of S|g|diag(Hcc) (lower block triangle, {C_ * (C_ + 1) // 2 * 36 * 4 / 1e6:.0f} MB f32) per iteration"},
+                      "sharding": f"points over {world} rank(s); NCCL all-reduce of S|g|diag(Hcc) (lower block triangle, {C_ * (C_ + 1) // 2 * 36 * 4 / 1e6:.0f} MB f32) per iteration",
+                      "linear_solver": "block-Jacobi PCG on the reduced camera system (one persistent kernel), relative residual "
+                                       + os.environ.get("SFM_BA_CG_TOL", "1e-5") + " per LM step"},
            "cost_first": hist[0]["cost_before"], "cost_last": hist[-1]["cost_after"],
            "cost_trajectory": [round(h["cost_after"], 3) for h in hist],
            "accepted": [bool(h["accepted"]) for h in hist],

@@ -357,8 +357,11 @@ typedef struct sfm_ba_stats {
 } sfm_ba_stats;
 
 /* One damped Gauss-Newton (LM) iteration: K6 fused JtJ/Schur accumulation (no Jacobian in HBM),
- * [all-reduce of the reduced camera system if a communicator is attached], dense Cholesky of the
- * 6C x 6C system, back-substitution, parameter update, new cost; rejected steps are rolled back. */
+ * [all-reduce of the reduced camera system if a communicator is attached], the 6C x 6C system by
+ * block-Jacobi preconditioned conjugate gradients to a relative residual of 1e-5 (environment
+ * SFM_BA_CG_TOL overrides; the system is float32 data) with the tile Cholesky as fallback and for
+ * systems under 600 unknowns, back-substitution, parameter update, new cost; rejected steps are
+ * rolled back. */
 int sfm_ba_gn_step(sfm_ba* ba, double lambda, sfm_ba_stats* stats);
 
 /* Device views for tests and for a host-side exchange step (float32, row-major):

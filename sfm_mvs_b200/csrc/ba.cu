@@ -600,7 +600,7 @@ __global__ void ba_update_cams_kernel(const double* __restrict__ cams, const dou
   if ((threadIdx.x & 31) == 0 && d != 0.0) atomicAdd(step2, d);
 }
 
-// Conjugate gradients first (pcg.cu: ~50 iterations of an L2-resident matrix-vector product instead of a chain of 6C
+// Conjugate gradients first (pcg.cu: 20 - 40 iterations of an L2-resident matrix-vector product instead of a chain of 6C
 // dependent columns); the tile Cholesky runs behind it only if it reports failure (its kernels return at once otherwise).
 // SFM_BA_SOLVER=cholesky selects the factorisation alone.
 int solve_reduced_system(sfm_ba* ba) {
