@@ -1,6 +1,6 @@
 """compute-sanitizer target: every kernel family of the path once, at tiny sizes.
 usage (GPU box): compute-sanitizer --tool {memcheck,racecheck,synccheck} python tools/sanitize.py [part ...]
-parts: match pnp chain ba init (default: all)"""
+parts: match pnp chain ba init (default: all), pcg (the CG solver alone, several block rows per CTA)"""
 import os
 import sys
 
@@ -46,6 +46,14 @@ if "ba" in parts:          # K5, K6, tile Cholesky graph, back substitution, upd
     x2, solved, its = ctx.reduced_solve(B @ B.T / 132 + 0.5 * np.eye(132), np.ones(132), method="pcg")     # CG kernel: grid barrier
     print("pcg ok", solved, its, float(np.abs(x - x2).max()))
     prob.close()
+if "pcg" in parts:         # CG kernel at 300 cameras: two or three block rows per CTA, ranges summed in shared memory
+    rng = np.random.default_rng(4)
+    B = rng.normal(size=(1800, 1808))
+    S = (B @ B.T / 1800 + 0.5 * np.eye(1800)).astype(np.float32)
+    g = rng.normal(size=1800).astype(np.float32)
+    x, solved, its = ctx.reduced_solve(S, g, method="pcg")
+    ref = np.linalg.solve(np.tril(S).astype(np.float64) + np.tril(S, -1).T.astype(np.float64), -g.astype(np.float64))
+    print("pcg ok", solved, its, float(np.abs(x - ref).max() / np.abs(ref).max()))
 if "init" in parts:        # five-point RANSAC + recoverPose
     tv0, tv1, _, _ = synth.two_view_pair(300, seed=3)
     init = pipeline.two_view_init(tv0, tv1, K, ctx=ctx)
