@@ -332,6 +332,56 @@ def ba_schur(r, Jc, Jp, cam_idx, pt_idx, n_cam, n_pt, lam: float = 0.0):
     return S, g, Hcc, bc, Hpp, bp
 
 
+def reduced_solve_pcg(S, g, tol: float = 1e-8, max_iter: int = 400):
+    """S x = -g by block-Jacobi (6x6) preconditioned conjugate gradients — the algorithm of the engine's LM-step solver
+    (csrc/pcg.cu) in float64 numpy: x0 = 0, the iteration ends when the recursively updated residual is below
+    tol * |g|, and the TRUE residual b - S x must then be within min(100 tol, 1e-4) of |g|.  Only the lower triangle of
+    S is read.  Returns (x, solved, iterations); solved is False on a non-positive diagonal block or p^T S p, on
+    max_iter, or when the true residual fails the check (the engine then runs the factorisation)."""
+    S = np.asarray(S, np.float64)
+    S = np.tril(S) + np.tril(S, -1).T
+    b = -np.asarray(g, np.float64).ravel()
+    n = b.size
+    C = n // 6
+    Minv = np.empty((C, 6, 6))
+    for a in range(C):
+        blk = S[6 * a:6 * a + 6, 6 * a:6 * a + 6]
+        try:
+            L = np.linalg.cholesky(blk)
+        except np.linalg.LinAlgError:
+            return np.zeros(n), False, 0
+        Li = np.linalg.inv(L)
+        Minv[a] = Li.T @ Li
+    prec = lambda r: np.einsum("cij,cj->ci", Minv, r.reshape(C, 6)).ravel()
+    x = np.zeros(n)
+    r = b.copy()
+    bb = float(r @ r)
+    if bb == 0.0:
+        return x, True, 0
+    z = prec(r)
+    p = z.copy()
+    rz = float(r @ z)
+    for it in range(1, max_iter + 1):
+        w = S @ p
+        pw = float(p @ w)
+        if not (pw > 0.0) or not np.isfinite(pw):
+            return x, False, it - 1
+        alpha = rz / pw
+        x += alpha * p
+        r -= alpha * w
+        rr = float(r @ r)
+        z = prec(r)
+        rz_new = float(r @ z)
+        if not np.isfinite(rr) or not np.isfinite(rz_new):
+            return x, False, it
+        if rr <= tol * tol * bb:
+            d = b - S @ x
+            return x, bool(d @ d <= min(1e4 * tol * tol, 1e-8) * bb), it
+        p = z + (rz_new / rz) * p
+        rz = rz_new
+    return x, False, max_iter
+
+
 # ------------------------------------------------------------------ recoverPose (sfm.py:311, isfm.py:83, test.py:250)
 def recover_pose(E, p1, p2, K, dist: float = 50.0, mask=None):
     """Published algorithm of cv2.recoverPose restated in numpy (OpenCV 4.x, calib3d/five-point.cpp): normalise the

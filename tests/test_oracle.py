@@ -371,3 +371,40 @@ def test_restated_find_essential_mat_geometries(name):
     else:
         assert np.array_equal(mo, mc.ravel() != 0)
         assert _e_close(Eo, Ec[:3]) < 1e-5
+
+
+@pytest.mark.parametrize("C", [1, 7, 60])
+def test_restated_conjugate_gradients_equal_lapack(C):
+    """oracle.restated.reduced_solve_pcg — the algorithm of the engine's LM-step solver (csrc/pcg.cu) — against LAPACK:
+    to 1e-6 at the solver's own tolerance (1e-8), and at the tolerance an LM step uses (1e-5) a solution whose residual
+    is below it and which needs fewer iterations; an indefinite system is reported, not solved."""
+    rng = np.random.default_rng(200 + C)
+    n = 6 * C
+    B = rng.normal(size=(n, n + 8))
+    S = (B @ B.T / n + 0.5 * np.eye(n)).astype(np.float32)
+    g = rng.normal(size=n).astype(np.float32)
+    S64 = np.tril(S).astype(np.float64) + np.tril(S, -1).T.astype(np.float64)
+    ref = np.linalg.solve(S64, -g.astype(np.float64))
+    x, solved, its = restated.reduced_solve_pcg(S, g)
+    assert solved and 1 <= its <= 400
+    assert np.abs(x - ref).max() <= 1e-6 * np.abs(ref).max()
+    x5, solved5, its5 = restated.reduced_solve_pcg(S, g, tol=1e-5)
+    assert solved5 and its5 <= its
+    assert np.linalg.norm(-g - S64 @ x5) <= 1e-5 * np.linalg.norm(g) * (1 + 1e-6)
+    assert np.abs(x5 - ref).max() <= 1e-3 * np.abs(ref).max()
+    Sbad = S.copy()
+    Sbad[n // 2, n // 2] = -1.0
+    assert not restated.reduced_solve_pcg(Sbad, g)[1]
+
+
+def test_restated_conjugate_gradients_on_a_damped_schur_system():
+    """The same on what the LM step really solves: the damped reduced camera system of a small BA problem."""
+    from sfm_mvs_b200 import synth
+    pb = synth.ba_problem(8, 300, 4, seed=4)
+    r, Jc, Jp = restated.ba_residual_jacobian(pb["cams0"], pb["pts0"], pb["cam_idx"], pb["pt_idx"], pb["obs"], pb["K"])
+    S, g, *_ = restated.ba_schur(r, Jc, Jp, pb["cam_idx"], pb["pt_idx"], 8, 300, lam=1e-3)
+    ref = np.linalg.solve(S, -g)
+    x, solved, its = restated.reduced_solve_pcg(S, g)
+    assert solved and np.abs(x - ref).max() <= 1e-6 * np.abs(ref).max(), its
+    x5, solved5, its5 = restated.reduced_solve_pcg(S, g, tol=1e-5)
+    assert solved5 and its5 < its
