@@ -21,7 +21,6 @@ for rep in range(2):                                   # the second pass is the 
         costs.append(round(st["cost_after"], 4)); acc.append(bool(st["accepted"]))
     ctx.sync()
     out["ms_per_iter"] = (time.perf_counter() - t0) * 100.0
-out["cost_before"] = None
 out["costs"], out["accepted"] = costs, acc
 out["final_cost"] = prob.eval(0, want_r=False, want_J=False)["cost"]
 print(json.dumps(out))
