@@ -159,3 +159,52 @@ def test_packed_lower_block_layout_round_trip():
     assert np.all(low[:6, 6:] == 0) and np.array_equal(low[6:12, :6], back[6:12, :6])
     with pytest.raises(ValueError):
         pack_lower_blocks(np.zeros((7, 7)))
+
+
+# ---------------------------------------------------------------- properties over arbitrary inputs (hypothesis)
+from hypothesis import given, settings, strategies as st
+
+
+@settings(max_examples=60, deadline=None)
+@given(st.lists(st.integers(1, 10_000), min_size=0, max_size=60), st.integers(1, 9))
+def test_shard_pairs_properties(costs, world):
+    """Every pair on exactly one rank, indices ascending per rank, and the LPT bound: no rank carries more than the
+    mean load plus one largest pair."""
+    shards = sharding.shard_pairs([(0, 0)] * len(costs), costs, world)
+    assert len(shards) == (world if world > 1 else 1)
+    flat = sorted(k for s in shards for k in s)
+    assert flat == list(range(len(costs)))
+    assert all(s == sorted(s) for s in shards)
+    if costs:
+        loads = [sum(costs[k] for k in s) for s in shards]
+        assert max(loads) <= sum(costs) / len(shards) + max(costs)
+
+
+@settings(max_examples=60, deadline=None)
+@given(st.lists(st.integers(0, 7), min_size=0, max_size=40), st.integers(1, 9))
+def test_shard_points_properties(obs_per_point, world):
+    """Contiguous, disjoint point ranges covering all points (points without observations included), observation
+    ranges that are exactly those points' observations — for more ranks than points, too."""
+    n_pt = len(obs_per_point)
+    pt_idx = np.repeat(np.arange(n_pt, dtype=np.int32), obs_per_point)
+    parts = sharding.shard_points(pt_idx, n_pt, world)
+    assert len(parts) == world
+    assert parts[0][0] == 0 and parts[-1][1] == n_pt and parts[0][2] == 0 and parts[-1][3] == len(pt_idx)
+    for (p_lo, p_hi, o_lo, o_hi), nxt in zip(parts, parts[1:] + [None]):
+        assert p_lo <= p_hi and o_lo <= o_hi
+        assert o_hi - o_lo == int(np.sum(obs_per_point[p_lo:p_hi]))
+        if o_hi > o_lo:
+            assert pt_idx[o_lo] >= p_lo and pt_idx[o_hi - 1] < p_hi
+        if nxt is not None:
+            assert nxt[0] == p_hi and nxt[2] == o_hi
+
+
+@settings(max_examples=60, deadline=None)
+@given(st.integers(0, 70_000), st.integers(1, 9))
+def test_split_rows_properties(n_rows, world):
+    parts = sharding.split_rows(n_rows, world)
+    assert len(parts) == world and parts[0][0] == 0 and parts[-1][1] == n_rows
+    for (lo, hi), nxt in zip(parts, parts[1:] + [None]):
+        assert lo <= hi and (lo % 128 == 0 or lo == n_rows)
+        if nxt is not None:
+            assert nxt[0] == hi
